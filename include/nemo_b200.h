@@ -1,0 +1,161 @@
+/*
+ * libnemo_b200.so -- C ABI of the B200-native Nemo filter-and-detect hot path.
+ *
+ * The reference (borisbolliet/nemo-1) is pure Python and has no FFI; the seam this library sits under is
+ * the Python call surface pipelines._filterMapsAndMakeCatalogs uses (nemo/pipelines.py:211-214, 251-262,
+ * 273-275).  Each entry point below replaces the numpy/scipy/pixell call(s) cited beside it; the Python
+ * boundary (nemo_b200/filters.py, nemo_b200/photometry.py) binds them with ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (torch.Tensor.data_ptr()), row-major, caller-owned, unless marked
+ *     "host"; nothing is allocated behind the caller's back except FFT twiddle tables cached per (N, prec);
+ *   - prec selects the arithmetic/storage type T of maps and spectra: NB_PREC_F32 (0) or NB_PREC_F64 (1);
+ *     covariances, filters-in-full-plane, reductions, tables and spline evaluations are always fp64;
+ *   - real maps are [B, H, W]; half spectra are [B, H, Wc] complex(T) with Wc = W/2 + 1;
+ *   - H and W must be powers of two in 64..4096 for the FFT entry points (NB_ERR_UNSUPPORTED otherwise);
+ *   - every call is asynchronous on `stream` and returns 0 on success or a negative NB_ERR_* code, with a
+ *     message available from nb_last_error() (thread-local).
+ */
+#ifndef NEMO_B200_H
+#define NEMO_B200_H
+
+#include <cuda_runtime.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_PREC_F32 0
+#define NB_PREC_F64 1
+
+const char* nb_last_error(void);
+int nb_version(void);
+int nb_device_info(int* smCount, int* ccMajor, int* ccMinor);
+int nb_fft_size_supported(int n);
+
+/* K1: enmap.fft(enmap.apod(map, apodPix))  (nemo/filters.py:528, 551, 849; enmap.fft at :618, 649, 682 with
+ * apodPix = 0).  out = scale * rfft2(taper * in); the reference's normalisation is scale = 1/sqrt(H*W). */
+int nb_rfft2(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale,
+             cudaStream_t stream);
+
+/* Un-normalised inverse of nb_rfft2: out = scale * norm[b] * mask[b / maskDiv] * irfft2(spec) * (H*W).
+ * spec is overwritten (column pass is in place).  norm (fp64, [B]) and mask (u8, [B / maskDiv, H, W]) may be NULL. */
+int nb_irfft2(int prec, void* spec, void* out, int B, int H, int W, double scale, const double* norm,
+              const unsigned char* mask, int maskDiv, cudaStream_t stream);
+
+/* K4: MatchedFilter.applyFilter (nemo/filters.py:851-857) followed by "* psMask" (:717):
+ *   out[o] = scale * norm[o] * mask[o / S] * Re(ifft2_unnormalised(sum_f fmaps[o / S, f] * filt[o, f]))
+ * fmaps [nOut / S, F, H, Wc] complex(T); filtH [nOut, F, H, Wc] real T = the filter folded onto the half plane,
+ * (filt(k) + filt(-k)) / 2, which is what taking the real part of the full complex inverse transform does;
+ * scratch [nOut, H, Wc] complex(T).  norm / mask may be NULL. */
+int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratch, void* out, int nOut, int S,
+                    int F, int H, int W, double scale, const double* norm, const unsigned char* mask,
+                    cudaStream_t stream);
+
+/* K8: enmap.apply_window(data, pow) and the zero restore (nemo/filters.py:101-104; pipelines.py:229-232).
+ * wy [H], wx [Wc] (type T) hold the window already raised to pow; data [B, H, W] is transformed in place;
+ * pixels that were exactly 0 stay 0 when restoreZeros != 0.  scratch [B, H, Wc] complex(T). */
+int nb_window_deconv(int prec, void* data, void* scratch, int B, int H, int W, const void* wy, const void* wx,
+                     int restoreZeros, cudaStream_t stream);
+
+/* K2: noiseCov[i][j] = ndimage.gaussian_filter(Re(F_i conj(F_j)), (3, 3))  (nemo/filters.py:568-587), on the
+ * full [H, W] plane in unshifted layout with scipy's 'reflect' boundary, truncate = 4 (radius 12).
+ * fmaps [B, F, H, Wc] complex(T); cov [B, P, H, W] fp64 with P = F (F + 1) / 2 planes in the order
+ * (0,0), (0,1), .., (0,F-1), (1,1), ..; tmp same size as cov. */
+int nb_xpower_smooth(int prec, const void* fmaps, double* cov, double* tmp, int B, int F, int H, int W,
+                     double sigma, cudaStream_t stream);
+
+/* K3: filt[:, y, x] = inv(noiseCov[:, :, y, x]) @ (w * |fSignal[:, y, x]|)  (nemo/filters.py:624-630); exactly
+ * singular matrices leave 0, as the reference's try/except does.
+ * cov [nOut / S, P, H, W] fp64; fsig [(sigPerTile ? nOut : S), F, H, Wc] complex(T) template spectra;
+ * w host [F]; outputs: filtFull [nOut, F, H, W] fp64 (the reference's self.filt; may be NULL) and
+ * filtH [nOut, F, H, Wc] real T (folded, for nb_apply_filter). */
+int nb_build_filter(int prec, const double* cov, const void* fsig, const double* w, double* filtFull, void* filtH,
+                    int nOut, int S, int sigPerTile, int F, int H, int W, cudaStream_t stream);
+
+/* Fold a full-plane filter (e.g. one loaded from a cache, nemo/filters.py:784-794) onto the half plane. */
+int nb_fold_filter(int prec, const double* filtFull, void* filtH, int n, int H, int W, cudaStream_t stream);
+
+/* K5: normalisation scalars (nemo/filters.py:653-670, 686-687).  For each image b of map [B, H, W]:
+ * argmaxIdx[b] = np.argmax (first maximum in raster order), maxVal[b] its value, and, when mode == 1 ('yc'),
+ * centreVal[b] = bicubic-spline value at (cy, cx) (RectBivariateSpline(...)(cy, cx)); mode 0 skips it.
+ * signalNorm[b] = numer / (mode == 1 ? centreVal[b] : maxVal[b]). */
+int nb_template_norm(int prec, const void* map, int B, int H, int W, int mode, double cy, double cx, double numer,
+                     long long* argmaxIdx, double* maxVal, double* centreVal, double* signalNorm,
+                     cudaStream_t stream);
+
+/* fRelWeights (nemo/filters.py:664-670): value at pixel idx[b] of each frequency plane of
+ * Re(ifft_unnormalised(fmaps[b, f] * filtH[b, f])); out [B, F] fp64. */
+int nb_plane_values_at(int prec, const void* fmaps, const void* filtH, const long long* idx, double* out, int B,
+                       int F, int H, int W, cudaStream_t stream);
+
+/* Per-pixel median over frequencies of the weight maps (nemo/filters.py:360-363). */
+int nb_median_weights(int prec, const void* weights, void* out, int B, int F, int H, int W, cudaStream_t stream);
+
+/* K6: MapFilter.makeNoiseMap, grid branch, default 3-sigma-clipped estimator (nemo/filters.py:409-481).
+ * map [nImg, H, W] (already multiplied by psMask); wmed [nImg / S, H, W] median weights;
+ * yChunks host [ny + 1], xChunks host [nx + 1] (np.linspace(..., dtype=int)); overlapPix; numBins.
+ * Outputs: rms [nImg, H, W] T; table [nImg, ny * nx, numBins] fp64 cell RMS values; edges
+ * [nImg, ny * nx, numBins + 1] fp64 weight-bin edges (NaN for skipped cells). */
+int nb_cell_rms(int prec, const void* map, const void* wmed, int nImg, int S, int H, int W, const int* yChunks,
+                int ny, const int* xChunks, int nx, int overlapPix, int numBins, void* rms, double* table,
+                double* edges, cudaStream_t stream);
+
+/* K7: S/N map, edge trim and final masks (nemo/filters.py:716-758 Fourier class, :1112-1161 real-space class).
+ * In: map [nImg, H, W] (filtered * psMask), rms [nImg, H, W], psMask / surveyMask u8 [nImg / S, H, W].
+ * edgeCheck = rank_filter(|map + (1 - psMask)|, 0, size = (trimPix, trimPix)) > 0 (all ones when trimPix = 0);
+ * Out (may alias the inputs): data = map * edgeCheck (* edgeCheck*surveyMask*psMask unless realSpace),
+ * sn = where(rms > 0, map / rms, map) * maskOut with NaN -> 0, rms *= maskOut,
+ * maskOut u8 = edgeCheck * surveyMask * psMask * apodMask (apodMask trims apodPix - 1 pixels per edge).
+ * scratch: nImg * H * W bytes. */
+int nb_snr_mask(int prec, void* map, void* rms, const unsigned char* psMask, const unsigned char* surveyMask,
+                int nImg, int S, int H, int W, int trimPix, int apodPix, int realSpace, void* sn,
+                unsigned char* maskOut, unsigned char* scratch, cudaStream_t stream);
+
+/* S/N from a cached RMS map (nemo/pipelines.py:216-228): sn = where(rms > 0, map / rms, map). */
+int nb_snr_from_rms(int prec, const void* map, const void* rms, void* sn, int nImg, int S, int H, int W,
+                    cudaStream_t stream);
+
+/* K9: segmentation of (map > threshold) with 4-connectivity, numbered exactly like scipy.ndimage.label
+ * (raster order of each component's first pixel)  (nemo/photometry.py:212-214).
+ * The test is sign * map > threshold (sign = -1 for invertMap, photometry.py:52-53).
+ * labels [B, H, W] int32 (0 = background); nLabels [B] int32. */
+int nb_label4(int prec, const void* map, double threshold, double sign, int* labels, int* nLabels, int* scratch,
+              int B, int H, int W, cudaStream_t stream);
+/* number of int32 words nb_label4 needs in scratch */
+long long nb_label4_scratch_ints(int B, int H, int W);
+
+/* K10: ndimage.center_of_mass / ndimage.sum / ndimage.maximum_position per label, including label 0
+ * (nemo/photometry.py:215-220).  table [B, maxLabels + 1, 8] fp64 rows:
+ * {sum v, sum y*v, sum x*v, count, max v, first argmax (linear index), first pixel (linear index), unused};
+ * labels above maxLabels are ignored (compare nLabels to detect overflow).  v = sign * map. */
+int nb_label_moments(int prec, const void* map, double sign, const int* labels, double* table, int B, int H, int W,
+                     int maxLabels, cudaStream_t stream);
+
+/* K11: interpolate.RectBivariateSpline(arange(H), arange(W), img, kx=3, ky=3)(y, x) at K points
+ * (nemo/photometry.py:76-79, 122, 243-253, 295-333; filters.py:657-660).  imgIdx [K] int32 selects the image,
+ * yx [K, 2] fp64, out [K] fp64.  Cardinal cubic B-spline interpolation with a truncated (|n| <= 30) exact
+ * prefilter; differs from FITPACK's not-a-knot spline only within ~20 pixels of the image edge
+ * (by < 0.268^d relative at distance d). */
+int nb_spline_eval(int prec, const void* img, int B, int H, int W, const int* imgIdx, const double* yx, double* out,
+                   int K, double sign, cudaStream_t stream);
+
+/* K12: ndimage.gaussian_filter(data, (sigmaY, sigmaX)) (reflect, truncate 4), optionally subtracted from the
+ * input: out = subtract ? in - smooth : smooth  (nemo/maps.py:1355-1368, 1433-1458).  tmp [B, H, W] T. */
+int nb_gauss_filter(int prec, const void* in, void* tmp, void* out, int B, int H, int W, double sigmaY,
+                    double sigmaX, int subtract, cudaStream_t stream);
+
+/* K13: out[b] = scale * norm[b] * mask[b] * sum_f ndimage.convolve(in[b, f], kern[f]) (reflect)
+ * (nemo/filters.py:1200-1216, 1113).  in [B, F, H, W] T; kern [F, kh, kw] fp64 (odd kh, kw <= 63);
+ * planes [B, F, H, W] T receives the per-frequency convolutions when non-NULL (for fRelWeights, :1204-1211). */
+int nb_conv2d(int prec, const void* in, const double* kern, void* out, void* planes, int B, int F, int H, int W,
+              int kh, int kw, double scale, const double* norm, const unsigned char* mask, cudaStream_t stream);
+
+/* Small utilities used by the boundary module. */
+int nb_cast(int precIn, const void* in, int precOut, void* out, long long n, cudaStream_t stream);
+int nb_mask_to_u8(int precIn, const void* in, unsigned char* out, long long n, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,353 @@
+// Detection kernels (K9, K10, K11 of SURVEY.md section 2a).
+//   nb_label4         : ndimage.label(map > thr), 4-connectivity, scipy's numbering    photometry.py:212-214
+//   nb_label_moments  : center_of_mass / sum / maximum_position per label              photometry.py:215-220
+//   nb_spline_eval    : RectBivariateSpline(...)(y, x)                                 photometry.py:76-79, 122
+#include "nemo_b200_internal.h"
+#include "spline.cuh"
+
+// ------------------------------------------------------------------------------------------------------
+// K9.  Union-find on the linear pixel index; every root is the smallest index of its component, i.e. the
+// component's first pixel in raster order, so ranking the roots in index order reproduces scipy's labels.
+#define LBL_BLOCK 1024
+
+// L holds, for foreground pixels, the index *within the image* of a pixel of the same component with a smaller
+// or equal index (a parent pointer); -1 for background.
+template <typename T>
+__global__ void __launch_bounds__(LBL_BLOCK) label_init_img_kernel(const T* __restrict__ map, double thr, double sign,
+                                                                   int* __restrict__ L, int HW) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const size_t off = (size_t)blockIdx.y * HW + p;
+    const double v = sign * (double)map[off];
+    L[off] = (v > thr) ? p : -1;
+}
+
+__device__ __forceinline__ int uf_find(const int* L, int a) {
+    int r = L[a];
+    while (r != a) {
+        a = r;
+        r = L[a];
+    }
+    return a;
+}
+
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+    bool done = false;
+    while (!done) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a < b) {
+            const int old = atomicMin(&L[b], a);
+            done = (old == b);
+            b = old;
+        } else if (b < a) {
+            const int old = atomicMin(&L[a], b);
+            done = (old == a);
+            a = old;
+        } else {
+            done = true;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LBL_BLOCK) label_merge_kernel(int* Lall, int H, int W) {
+    const int HW = H * W;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    int* L = Lall + (size_t)blockIdx.y * HW;
+    if (L[p] < 0) return;
+    const int x = p % W;
+    if (x > 0 && L[p - 1] >= 0) uf_union(L, p, p - 1);
+    if (p >= W && L[p - W] >= 0) uf_union(L, p, p - W);
+}
+
+// flatten to roots and count roots per block
+__global__ void __launch_bounds__(LBL_BLOCK) label_flatten_kernel(int* Lall, int HW, int* __restrict__ blockCounts) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int* L = Lall + (size_t)blockIdx.y * HW;
+    int isRoot = 0;
+    if (p < HW && L[p] >= 0) {
+        const int r = uf_find(L, p);
+        isRoot = (r == p);
+        if (!isRoot) L[p] = r;  // roots are never rewritten, so concurrent finds stay valid
+    }
+    const int c = __syncthreads_count(isRoot);
+    if (threadIdx.x == 0) blockCounts[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = c;
+}
+
+// exclusive scan of the per-block root counts, one CTA per image
+__global__ void __launch_bounds__(1024) label_scan_kernel(int* __restrict__ blockCounts, int nBlocks, int* __restrict__ nLabels) {
+    int* bc = blockCounts + (size_t)blockIdx.x * nBlocks;
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < nBlocks; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = (i < nBlocks) ? bc[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_w[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            s_w[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int warpOff = (wid > 0) ? s_w[wid - 1] : 0;
+        if (i < nBlocks) bc[i] = carry + warpOff + inc - v;  // exclusive
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + warpOff + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) nLabels[blockIdx.x] = s_carry;
+}
+
+// roots receive -(label + 1) (labels start at 1, so codes are <= -2; -1 stays background)
+__global__ void __launch_bounds__(LBL_BLOCK) label_rank_kernel(int* __restrict__ Lall, int HW, const int* __restrict__ blockOffsets) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int* L = Lall + (size_t)blockIdx.y * HW;
+    const int isRoot = (p < HW && L[p] == p) ? 1 : 0;
+    __shared__ int s_w[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, isRoot);
+    const int before = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) s_w[wid] = __popc(bal);
+    __syncthreads();
+    if (wid == 0) {
+        int w = s_w[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        s_w[lane] = w;
+    }
+    __syncthreads();
+    if (isRoot) {
+        const int rank = blockOffsets[(size_t)blockIdx.y * gridDim.x + blockIdx.x] + ((wid > 0) ? s_w[wid - 1] : 0) + before;
+        L[p] = -(rank + 2);
+    }
+}
+
+__global__ void __launch_bounds__(LBL_BLOCK) label_final_kernel(const int* __restrict__ Lall, int* __restrict__ labels, int HW) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int* L = Lall + (size_t)blockIdx.y * HW;
+    const int v = L[p];
+    int lab = 0;
+    if (v <= -2)
+        lab = -v - 1;
+    else if (v >= 0)
+        lab = -L[v] - 1;
+    labels[(size_t)blockIdx.y * HW + p] = lab;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K10.  table rows: {sum v, sum y v, sum x v, count, max v (order-encoded until finalised), first argmax, first pixel, 0}
+__device__ __forceinline__ unsigned long long enc_ordered(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double dec_ordered(unsigned long long e) {
+    const unsigned long long b = (e & 0x8000000000000000ULL) ? (e & 0x7fffffffffffffffULL) : ~e;
+    return __longlong_as_double((long long)b);
+}
+
+__global__ void moments_init_kernel(double* __restrict__ table, long long nRows) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nRows) return;
+    double* t = table + r * 8;
+    t[0] = t[1] = t[2] = t[3] = 0.0;
+    reinterpret_cast<unsigned long long*>(t)[4] = 0ULL;  // below every encoded value
+    t[5] = INFINITY;
+    t[6] = INFINITY;
+    t[7] = 0.0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) moments_accum_kernel(const T* __restrict__ map, double sign, const int* __restrict__ labels,
+                                                            double* __restrict__ table, int H, int W, int maxLabels) {
+    const int HW = H * W;
+    const int img = blockIdx.y;
+    const T* m = map + (size_t)img * HW;
+    const int* lb = labels + (size_t)img * HW;
+    double* tab = table + (size_t)img * (maxLabels + 1) * 8;
+    // label 0 (background) is accumulated per thread and reduced; objects go straight to atomics
+    double s0 = 0, sy0 = 0, sx0 = 0, c0 = 0, mx0 = -INFINITY;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+        const int l = lb[p];
+        const double v = sign * (double)m[p];
+        const int y = p / W, x = p - y * W;
+        if (l == 0) {
+            s0 += v;
+            sy0 += v * (double)y;
+            sx0 += v * (double)x;
+            c0 += 1.0;
+            mx0 = fmax(mx0, v);
+        } else if (l <= maxLabels) {
+            double* t = tab + (size_t)l * 8;
+            atomicAdd(t + 0, v);
+            atomicAdd(t + 1, v * (double)y);
+            atomicAdd(t + 2, v * (double)x);
+            atomicAdd(t + 3, 1.0);
+            atomicMax(reinterpret_cast<unsigned long long*>(t) + 4, enc_ordered(v));
+            atomicMin(reinterpret_cast<unsigned long long*>(t) + 6, (unsigned long long)__double_as_longlong((double)p));
+        }
+    }
+    s0 = warp_sum(s0);
+    sy0 = warp_sum(sy0);
+    sx0 = warp_sum(sx0);
+    c0 = warp_sum(c0);
+    mx0 = warp_max(mx0);
+    if ((threadIdx.x & 31) == 0 && c0 > 0) {
+        atomicAdd(tab + 0, s0);
+        atomicAdd(tab + 1, sy0);
+        atomicAdd(tab + 2, sx0);
+        atomicAdd(tab + 3, c0);
+        atomicMax(reinterpret_cast<unsigned long long*>(tab) + 4, enc_ordered(mx0));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) moments_argmax_kernel(const T* __restrict__ map, double sign, const int* __restrict__ labels,
+                                                             double* __restrict__ table, int H, int W, int maxLabels) {
+    const int HW = H * W;
+    const int img = blockIdx.y;
+    const T* m = map + (size_t)img * HW;
+    const int* lb = labels + (size_t)img * HW;
+    double* tab = table + (size_t)img * (maxLabels + 1) * 8;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+        const int l = lb[p];
+        if (l > maxLabels) continue;
+        const double v = sign * (double)m[p];
+        double* t = tab + (size_t)l * 8;
+        if (enc_ordered(v) == reinterpret_cast<const unsigned long long*>(t)[4])
+            atomicMin(reinterpret_cast<unsigned long long*>(t) + 5, (unsigned long long)__double_as_longlong((double)p));
+    }
+}
+
+__global__ void moments_final_kernel(double* __restrict__ table, long long nRows) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nRows) return;
+    double* t = table + r * 8;
+    const unsigned long long e = reinterpret_cast<unsigned long long*>(t)[4];
+    t[4] = (e == 0ULL) ? -INFINITY : dec_ordered(e);
+    if (t[3] == 0.0) {
+        t[5] = -1.0;
+        t[6] = -1.0;
+    }
+    if (t[5] == INFINITY) t[5] = -1.0;
+    if (t[6] == INFINITY) t[6] = -1.0;  // label 0 has no tracked first pixel
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K11.  One warp per evaluation point.
+template <typename T>
+__global__ void __launch_bounds__(128) spline_eval_kernel(const T* __restrict__ img, int H, int W, const int* __restrict__ imgIdx,
+                                                          const double* __restrict__ yx, double* __restrict__ out, int K, double sign) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= K) return;  // whole warps exit together
+    const int b = imgIdx ? imgIdx[k] : 0;
+    const double v = spline_eval_warp<T>(img + (size_t)b * H * W, H, W, yx[2 * k], yx[2 * k + 1], sign);
+    if ((threadIdx.x & 31) == 0) out[k] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int nb_label4(int prec, const void* map, double threshold, double sign, int* labels, int* nLabels, int* scratch,
+              int B, int H, int W, cudaStream_t st) {
+    NB_REQUIRE(map && labels && nLabels && scratch && B > 0 && H > 0 && W > 0, NB_ERR_ARG, "nb_label4: bad arguments");
+    NB_REQUIRE((long long)H * W < 0x7fffffffLL, NB_ERR_UNSUPPORTED, "nb_label4: image too large");
+    const int HW = H * W;
+    const int nBlocks = (HW + LBL_BLOCK - 1) / LBL_BLOCK;
+    dim3 grid(nBlocks, B);
+    // scratch: [B, HW] parent pointers followed by [B, nBlocks] block counts
+    int* L = scratch;
+    int* blockCounts = scratch + (size_t)B * HW;
+    if (prec == NB_PREC_F64)
+        label_init_img_kernel<double><<<grid, LBL_BLOCK, 0, st>>>((const double*)map, threshold, sign, L, HW);
+    else if (prec == NB_PREC_F32)
+        label_init_img_kernel<float><<<grid, LBL_BLOCK, 0, st>>>((const float*)map, threshold, sign, L, HW);
+    else {
+        nb_set_error("nb_label4: bad precision %d", prec);
+        return NB_ERR_ARG;
+    }
+    NB_CHECK_LAUNCH();
+    label_merge_kernel<<<grid, LBL_BLOCK, 0, st>>>(L, H, W);
+    NB_CHECK_LAUNCH();
+    label_flatten_kernel<<<grid, LBL_BLOCK, 0, st>>>(L, HW, blockCounts);
+    NB_CHECK_LAUNCH();
+    label_scan_kernel<<<B, 1024, 0, st>>>(blockCounts, nBlocks, nLabels);
+    NB_CHECK_LAUNCH();
+    label_rank_kernel<<<grid, LBL_BLOCK, 0, st>>>(L, HW, blockCounts);
+    NB_CHECK_LAUNCH();
+    label_final_kernel<<<grid, LBL_BLOCK, 0, st>>>(L, labels, HW);
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+long long nb_label4_scratch_ints(int B, int H, int W) {
+    const long long HW = (long long)H * W;
+    return (long long)B * HW + (long long)B * ((HW + LBL_BLOCK - 1) / LBL_BLOCK);
+}
+
+int nb_label_moments(int prec, const void* map, double sign, const int* labels, double* table, int B, int H, int W,
+                     int maxLabels, cudaStream_t st) {
+    NB_REQUIRE(map && labels && table && B > 0 && maxLabels >= 0, NB_ERR_ARG, "nb_label_moments: bad arguments");
+    const long long nRows = (long long)B * (maxLabels + 1);
+    moments_init_kernel<<<(unsigned)((nRows + 255) / 256), 256, 0, st>>>(table, nRows);
+    NB_CHECK_LAUNCH();
+    const int HW = H * W;
+    int gx = (HW + 256 * 8 - 1) / (256 * 8);
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, B);
+    if (prec == NB_PREC_F64) {
+        moments_accum_kernel<double><<<grid, 256, 0, st>>>((const double*)map, sign, labels, table, H, W, maxLabels);
+        NB_CHECK_LAUNCH();
+        moments_argmax_kernel<double><<<grid, 256, 0, st>>>((const double*)map, sign, labels, table, H, W, maxLabels);
+    } else if (prec == NB_PREC_F32) {
+        moments_accum_kernel<float><<<grid, 256, 0, st>>>((const float*)map, sign, labels, table, H, W, maxLabels);
+        NB_CHECK_LAUNCH();
+        moments_argmax_kernel<float><<<grid, 256, 0, st>>>((const float*)map, sign, labels, table, H, W, maxLabels);
+    } else {
+        nb_set_error("nb_label_moments: bad precision %d", prec);
+        return NB_ERR_ARG;
+    }
+    NB_CHECK_LAUNCH();
+    moments_final_kernel<<<(unsigned)((nRows + 255) / 256), 256, 0, st>>>(table, nRows);
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+int nb_spline_eval(int prec, const void* img, int B, int H, int W, const int* imgIdx, const double* yx, double* out,
+                   int K, double sign, cudaStream_t st) {
+    NB_REQUIRE(img && yx && out && B > 0, NB_ERR_ARG, "nb_spline_eval: bad arguments");
+    if (K <= 0) return NB_OK;
+    const int wpb = 4;
+    const unsigned grid = (unsigned)((K + wpb - 1) / wpb);
+    if (prec == NB_PREC_F64)
+        spline_eval_kernel<double><<<grid, 32 * wpb, 0, st>>>((const double*)img, H, W, imgIdx, yx, out, K, sign);
+    else if (prec == NB_PREC_F32)
+        spline_eval_kernel<float><<<grid, 32 * wpb, 0, st>>>((const float*)img, H, W, imgIdx, yx, out, K, sign);
+    else {
+        nb_set_error("nb_spline_eval: bad precision %d", prec);
+        return NB_ERR_ARG;
+    }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,436 @@
+// Matched-filter construction kernels (K2, K3, K5 of SURVEY.md section 2a).
+//   nb_xpower_smooth : noiseCov[i][j] = gaussian_filter(Re(F_i conj F_j), (3,3))      filters.py:568-587
+//   nb_build_filter  : filt[:,k] = inv(noiseCov[:,:,k]) @ (w * |fSignal[:,k]|)         filters.py:624-630
+//   nb_fold_filter   : (filt(k) + filt(-k)) / 2 on the half plane
+//   nb_template_norm : argmax / max / spline value at the centre -> signalNorm         filters.py:653-662, 686-687
+//   nb_plane_values_at : per-frequency filtered-template values at one pixel            filters.py:664-670
+// All arithmetic here is fp64 whatever the storage type of the spectra.
+#include "nemo_b200_internal.h"
+#include "spline.cuh"
+#include "gauss.cuh"
+#include <math.h>
+
+// ------------------------------------------------------------------------------------------------------
+// K2 pass 1: one CTA per (image, ky).  The cross-power row over the full kx range is rebuilt from the half
+// spectrum (kx > W/2 comes from row -ky at W - kx), kept in shared memory as fp64, and smoothed along kx.
+template <typename T, int F>
+__global__ void __launch_bounds__(256) xpower_smooth_x_kernel(const typename V2<T>::type* __restrict__ fmaps,
+                                                              double* __restrict__ tmp, int H, int W, GaussW g) {
+    typedef typename V2<T>::type C2;
+    constexpr int P = F * (F + 1) / 2;
+    extern __shared__ double s_np[];  // [P][W]
+    const int ky = blockIdx.x, b = blockIdx.y;
+    const int Wc = W / 2 + 1;
+    const int kym = (H - ky) % H;
+    const C2* base = fmaps + (size_t)b * F * H * Wc;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        const int row = (x < Wc) ? ky : kym;
+        const int col = (x < Wc) ? x : (W - x);
+        double re[F], im[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            const C2 v = base[((size_t)f * H + row) * Wc + col];
+            re[f] = (double)v.x;
+            im[f] = (double)v.y;
+        }
+        int p = 0;
+#pragma unroll
+        for (int i = 0; i < F; ++i)
+#pragma unroll
+            for (int j = i; j < F; ++j) {
+                s_np[p * W + x] = re[i] * re[j] + im[i] * im[j];
+                ++p;
+            }
+    }
+    __syncthreads();
+    double* out = tmp + ((size_t)b * P * H + ky) * W;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const double* s = s_np + p * W;
+            double acc = 0;
+            if (x >= g.r && x + g.r < W) {
+                for (int d = -g.r; d <= g.r; ++d) acc += g.w[d + g.r] * s[x + d];
+            } else {
+                for (int d = -g.r; d <= g.r; ++d) acc += g.w[d + g.r] * s[reflect_idx(x + d, W)];
+            }
+            out[(size_t)p * H * W + x] = acc;
+        }
+    }
+}
+
+// K2 pass 2 (also the column pass of K12): smooth along y.  CTA tile 32 columns x TY rows, halo in shared memory.
+#define GY_TX 32
+#define GY_TY 64
+__global__ void __launch_bounds__(256) smooth_y_f64_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                           int H, int W, GaussW g) {
+    extern __shared__ double s_t[];  // [(GY_TY + 2r)][GY_TX]
+    const int x0 = blockIdx.x * GY_TX, y0 = blockIdx.y * GY_TY;
+    const size_t plane = (size_t)blockIdx.z * H * W;
+    const int tx = threadIdx.x % GY_TX, ty = threadIdx.x / GY_TX;  // 32 x 8
+    const int rows = GY_TY + 2 * g.r;
+    const int x = x0 + tx;
+    for (int i = ty; i < rows; i += 8) {
+        const int y = reflect_idx(y0 - g.r + i, H);
+        s_t[i * GY_TX + tx] = (x < W) ? in[plane + (size_t)y * W + x] : 0.0;
+    }
+    __syncthreads();
+    if (x >= W) return;
+    for (int i = ty; i < GY_TY; i += 8) {
+        const int y = y0 + i;
+        if (y >= H) break;
+        double acc = 0;
+        for (int d = 0; d <= 2 * g.r; ++d) acc += g.w[d] * s_t[(i + d) * GY_TX + tx];
+        out[plane + (size_t)y * W + x] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K3.  Solve the F x F system with partial pivoting (LAPACK-style); an exactly zero pivot marks the matrix
+// singular and yields zeros, which is what the reference's "except: continue" leaves in self.filt.
+template <int F> __device__ __forceinline__ void solve_sym(const double* c /*P packed upper*/, const double* rhs, double* x) {
+    double A[F][F], bb[F];
+    int p = 0;
+#pragma unroll
+    for (int i = 0; i < F; ++i)
+#pragma unroll
+        for (int j = i; j < F; ++j) {
+            A[i][j] = c[p];
+            A[j][i] = c[p];
+            ++p;
+        }
+#pragma unroll
+    for (int i = 0; i < F; ++i) bb[i] = rhs[i];
+    bool singular = false;
+#pragma unroll
+    for (int k = 0; k < F; ++k) {
+        // pivot search
+        int piv = k;
+        double best = fabs(A[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < F; ++i) {
+            const double v = fabs(A[i][k]);
+            if (v > best) {
+                best = v;
+                piv = i;
+            }
+        }
+#pragma unroll
+        for (int i = k + 1; i < F; ++i) {
+            if (i == piv) {
+#pragma unroll
+                for (int j = 0; j < F; ++j) {
+                    const double t = A[k][j];
+                    A[k][j] = A[i][j];
+                    A[i][j] = t;
+                }
+                const double t = bb[k];
+                bb[k] = bb[i];
+                bb[i] = t;
+            }
+        }
+        if (A[k][k] == 0.0) singular = true;
+        const double inv = 1.0 / A[k][k];
+#pragma unroll
+        for (int i = k + 1; i < F; ++i) {
+            const double m = A[i][k] * inv;
+#pragma unroll
+            for (int j = k + 1; j < F; ++j) A[i][j] -= m * A[k][j];
+            bb[i] -= m * bb[k];
+        }
+    }
+#pragma unroll
+    for (int i = F - 1; i >= 0; --i) {
+        double s = bb[i];
+#pragma unroll
+        for (int j = i + 1; j < F; ++j) s -= A[i][j] * x[j];
+        x[i] = s / A[i][i];
+    }
+    if (singular) {
+#pragma unroll
+        for (int i = 0; i < F; ++i) x[i] = 0.0;
+    }
+}
+
+struct FreqW {
+    double w[NB_MAX_FREQ];
+};
+
+template <typename T, int F>
+__global__ void __launch_bounds__(256) build_filter_kernel(const double* __restrict__ cov,
+                                                           const typename V2<T>::type* __restrict__ fsig, FreqW fw,
+                                                           double* __restrict__ filtFull, T* __restrict__ filtH, int S,
+                                                           int sigPerTile, int H, int W) {
+    typedef typename V2<T>::type C2;
+    constexpr int P = F * (F + 1) / 2;
+    const int Wc = W / 2 + 1;
+    const int kx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ky = blockIdx.y;
+    const int o = blockIdx.z;
+    if (kx >= Wc) return;
+    const int tile = o / S;
+    const int sidx = sigPerTile ? o : (o % S);
+    const int kym = (H - ky) % H, kxm = (W - kx) % W;
+    const double* cv = cov + (size_t)tile * P * H * W;
+    double rhs[F], c1[P], c2[P], x1[F], x2[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        const C2 v = fsig[(((size_t)sidx * F + f) * H + ky) * Wc + kx];
+        rhs[f] = fw.w[f] * hypot((double)v.x, (double)v.y);  // np.abs of a complex number is hypot
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        c1[p] = cv[((size_t)p * H + ky) * W + kx];
+        c2[p] = cv[((size_t)p * H + kym) * W + kxm];
+    }
+    solve_sym<F>(c1, rhs, x1);
+    solve_sym<F>(c2, rhs, x2);
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        filtH[(((size_t)o * F + f) * H + ky) * Wc + kx] = (T)(0.5 * (x1[f] + x2[f]));
+        if (filtFull) {
+            double* ff = filtFull + ((size_t)o * F + f) * H * W;
+            ff[(size_t)ky * W + kx] = x1[f];
+            if (kx > 0 && kx < W / 2) ff[(size_t)kym * W + kxm] = x2[f];
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) fold_filter_kernel(const double* __restrict__ filtFull, T* __restrict__ filtH,
+                                                          int H, int W) {
+    const int Wc = W / 2 + 1;
+    const int kx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ky = blockIdx.y;
+    if (kx >= Wc) return;
+    const double* ff = filtFull + (size_t)blockIdx.z * H * W;
+    const int kym = (H - ky) % H, kxm = (W - kx) % W;
+    filtH[((size_t)blockIdx.z * H + ky) * Wc + kx] = (T)(0.5 * (ff[(size_t)ky * W + kx] + ff[(size_t)kym * W + kxm]));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K5.  One CTA per image: first maximum in raster order; optional spline value at (cy, cx).
+template <typename T>
+__global__ void __launch_bounds__(1024) template_norm_kernel(const T* __restrict__ map, int H, int W, int mode,
+                                                             double cy, double cx, double numer,
+                                                             long long* __restrict__ argmaxIdx, double* __restrict__ maxVal,
+                                                             double* __restrict__ centreVal, double* __restrict__ signalNorm) {
+    const int b = blockIdx.x;
+    const T* img = map + (size_t)b * H * W;
+    const long long n = (long long)H * W;
+    double best = -INFINITY;
+    long long bi = n;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = (double)img[i];
+        if (v > best) {  // strided scan visits increasing i, so the first maximum per thread is kept
+            best = v;
+            bi = i;
+        }
+    }
+    __shared__ double s_v[32];
+    __shared__ long long s_i[32];
+    __shared__ double s_centre;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) {
+            best = ov;
+            bi = oi;
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_v[wid] = best;
+        s_i[wid] = bi;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = blockDim.x >> 5;
+        best = (lane < nw) ? s_v[lane] : -INFINITY;
+        bi = (lane < nw) ? s_i[lane] : n;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) {
+                best = ov;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            argmaxIdx[b] = bi;
+            maxVal[b] = best;
+        }
+    }
+    if (wid == 1 && mode == 1) {
+        const double v = spline_eval_warp<T>(img, H, W, cy, cx, 1.0);
+        if (lane == 0) s_centre = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double denom = best;
+        if (mode == 1) {
+            denom = s_centre;
+            if (centreVal) centreVal[b] = s_centre;
+        }
+        signalNorm[b] = numer / denom;
+    }
+}
+
+// value at one pixel (py, px) of Re(sum over the full plane of G(k) e^{+2 pi i k.p / N}) for a Hermitian G given
+// on the half plane: columns 0 and W/2 count once, the others twice.  One CTA per (frequency, image).
+template <typename T>
+__global__ void __launch_bounds__(256) plane_values_kernel(const typename V2<T>::type* __restrict__ fmaps,
+                                                           const T* __restrict__ filtH, const long long* __restrict__ idx,
+                                                           double* __restrict__ out, int F, int H, int W) {
+    typedef typename V2<T>::type C2;
+    const int f = blockIdx.x, b = blockIdx.y;
+    const int Wc = W / 2 + 1;
+    const long long p = idx[b];
+    const int py = (int)(p / W), px = (int)(p % W);
+    const size_t base = ((size_t)b * F + f) * H * Wc;
+    double acc = 0;
+    for (long long i = threadIdx.x; i < (long long)H * Wc; i += blockDim.x) {
+        const int ky = (int)(i / Wc), kx = (int)(i % Wc);
+        const C2 v = fmaps[base + i];
+        const double gr = (double)v.x * (double)filtH[base + i], gi = (double)v.y * (double)filtH[base + i];
+        // phase 2 pi (ky py / H + kx px / W), reduced exactly in integers before the division
+        const double ph = 2.0 * ((double)(((long long)ky * py) % H) / (double)H + (double)(((long long)kx * px) % W) / (double)W);
+        double sn, cs;
+        sincospi(ph, &sn, &cs);
+        const double term = gr * cs - gi * sn;
+        acc += (kx == 0 || kx == W / 2) ? term : 2.0 * term;
+    }
+    __shared__ double s[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s[i];
+        out[(size_t)b * F + f] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int F>
+static int xpower_smooth_tf(const void* fmaps, double* cov, double* tmp, int B, int H, int W, const GaussW& g, cudaStream_t st) {
+    typedef typename V2<T>::type C2;
+    constexpr int P = F * (F + 1) / 2;
+    const size_t smem = (size_t)P * W * sizeof(double);
+    NB_REQUIRE(smem <= 200 * 1024, NB_ERR_UNSUPPORTED, "nb_xpower_smooth: F=%d, W=%d needs too much shared memory", F, W);
+    if (smem > 48 * 1024)
+        NB_CHECK_CUDA(cudaFuncSetAttribute(xpower_smooth_x_kernel<T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    xpower_smooth_x_kernel<T, F><<<dim3(H, B), 256, smem, st>>>((const C2*)fmaps, tmp, H, W, g);
+    NB_CHECK_LAUNCH();
+    const size_t smem2 = (size_t)(GY_TY + 2 * g.r) * GY_TX * sizeof(double);
+    if (smem2 > 48 * 1024)
+        NB_CHECK_CUDA(cudaFuncSetAttribute(smooth_y_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    smooth_y_f64_kernel<<<dim3((W + GY_TX - 1) / GY_TX, (H + GY_TY - 1) / GY_TY, B * P), 256, smem2, st>>>(tmp, cov, H, W, g);
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+template <typename T, int F>
+static int build_filter_tf(const double* cov, const void* fsig, const double* w, double* filtFull, void* filtH, int nOut,
+                           int S, int sigPerTile, int H, int W, cudaStream_t st) {
+    typedef typename V2<T>::type C2;
+    FreqW fw;
+    for (int f = 0; f < NB_MAX_FREQ; ++f) fw.w[f] = f < F ? w[f] : 0.0;
+    const int Wc = W / 2 + 1;
+    build_filter_kernel<T, F><<<dim3((Wc + 255) / 256, H, nOut), 256, 0, st>>>(cov, (const C2*)fsig, fw, filtFull, (T*)filtH, S,
+                                                                             sigPerTile, H, W);
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+extern "C" {
+
+int nb_xpower_smooth(int prec, const void* fmaps, double* cov, double* tmp, int B, int F, int H, int W, double sigma,
+                     cudaStream_t st) {
+    NB_REQUIRE(fmaps && cov && tmp && B > 0 && H > 0 && W > 0 && (W % 2) == 0, NB_ERR_ARG, "nb_xpower_smooth: bad arguments");
+    NB_REQUIRE(F >= 1 && F <= NB_MAX_FREQ, NB_ERR_UNSUPPORTED, "nb_xpower_smooth: %d frequencies not supported", F);
+    GaussW g;
+    int rc = make_gauss(sigma, &g);
+    if (rc != NB_OK) return rc;
+    NB_REQUIRE(g.r < H && g.r < W, NB_ERR_UNSUPPORTED, "nb_xpower_smooth: map smaller than the smoothing kernel");
+#define XP(T)                                                                         \
+    switch (F) {                                                                      \
+        case 1: return xpower_smooth_tf<T, 1>(fmaps, cov, tmp, B, H, W, g, st);       \
+        case 2: return xpower_smooth_tf<T, 2>(fmaps, cov, tmp, B, H, W, g, st);       \
+        case 3: return xpower_smooth_tf<T, 3>(fmaps, cov, tmp, B, H, W, g, st);       \
+        default: return xpower_smooth_tf<T, 4>(fmaps, cov, tmp, B, H, W, g, st);      \
+    }
+    if (prec == NB_PREC_F64) { XP(double) }
+    if (prec == NB_PREC_F32) { XP(float) }
+#undef XP
+    nb_set_error("nb_xpower_smooth: bad precision %d", prec);
+    return NB_ERR_ARG;
+}
+
+int nb_build_filter(int prec, const double* cov, const void* fsig, const double* w, double* filtFull, void* filtH,
+                    int nOut, int S, int sigPerTile, int F, int H, int W, cudaStream_t st) {
+    NB_REQUIRE(cov && fsig && w && filtH && nOut > 0 && S > 0 && (W % 2) == 0, NB_ERR_ARG, "nb_build_filter: bad arguments");
+    NB_REQUIRE(F >= 1 && F <= NB_MAX_FREQ, NB_ERR_UNSUPPORTED, "nb_build_filter: %d frequencies not supported", F);
+#define BF(T)                                                                                             \
+    switch (F) {                                                                                          \
+        case 1: return build_filter_tf<T, 1>(cov, fsig, w, filtFull, filtH, nOut, S, sigPerTile, H, W, st); \
+        case 2: return build_filter_tf<T, 2>(cov, fsig, w, filtFull, filtH, nOut, S, sigPerTile, H, W, st); \
+        case 3: return build_filter_tf<T, 3>(cov, fsig, w, filtFull, filtH, nOut, S, sigPerTile, H, W, st); \
+        default: return build_filter_tf<T, 4>(cov, fsig, w, filtFull, filtH, nOut, S, sigPerTile, H, W, st); \
+    }
+    if (prec == NB_PREC_F64) { BF(double) }
+    if (prec == NB_PREC_F32) { BF(float) }
+#undef BF
+    nb_set_error("nb_build_filter: bad precision %d", prec);
+    return NB_ERR_ARG;
+}
+
+int nb_fold_filter(int prec, const double* filtFull, void* filtH, int n, int H, int W, cudaStream_t st) {
+    NB_REQUIRE(filtFull && filtH && n > 0 && (W % 2) == 0, NB_ERR_ARG, "nb_fold_filter: bad arguments");
+    const int Wc = W / 2 + 1;
+    dim3 grid((Wc + 255) / 256, H, n);
+    if (prec == NB_PREC_F64)
+        fold_filter_kernel<double><<<grid, 256, 0, st>>>(filtFull, (double*)filtH, H, W);
+    else if (prec == NB_PREC_F32)
+        fold_filter_kernel<float><<<grid, 256, 0, st>>>(filtFull, (float*)filtH, H, W);
+    else {
+        nb_set_error("nb_fold_filter: bad precision %d", prec);
+        return NB_ERR_ARG;
+    }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+int nb_template_norm(int prec, const void* map, int B, int H, int W, int mode, double cy, double cx, double numer,
+                     long long* argmaxIdx, double* maxVal, double* centreVal, double* signalNorm, cudaStream_t st) {
+    NB_REQUIRE(map && argmaxIdx && maxVal && signalNorm && B > 0, NB_ERR_ARG, "nb_template_norm: bad arguments");
+    if (prec == NB_PREC_F64)
+        template_norm_kernel<double><<<B, 1024, 0, st>>>((const double*)map, H, W, mode, cy, cx, numer, argmaxIdx, maxVal, centreVal, signalNorm);
+    else if (prec == NB_PREC_F32)
+        template_norm_kernel<float><<<B, 1024, 0, st>>>((const float*)map, H, W, mode, cy, cx, numer, argmaxIdx, maxVal, centreVal, signalNorm);
+    else {
+        nb_set_error("nb_template_norm: bad precision %d", prec);
+        return NB_ERR_ARG;
+    }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+int nb_plane_values_at(int prec, const void* fmaps, const void* filtH, const long long* idx, double* out, int B, int F,
+                       int H, int W, cudaStream_t st) {
+    NB_REQUIRE(fmaps && filtH && idx && out && B > 0 && F > 0, NB_ERR_ARG, "nb_plane_values_at: bad arguments");
+    if (prec == NB_PREC_F64)
+        plane_values_kernel<double><<<dim3(F, B), 256, 0, st>>>((const double2*)fmaps, (const double*)filtH, idx, out, F, H, W);
+    else if (prec == NB_PREC_F32)
+        plane_values_kernel<float><<<dim3(F, B), 256, 0, st>>>((const float2*)fmaps, (const float*)filtH, idx, out, F, H, W);
+    else {
+        nb_set_error("nb_plane_values_at: bad precision %d", prec);
+        return NB_ERR_ARG;
+    }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+}  // extern "C"

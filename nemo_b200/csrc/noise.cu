@@ -1,0 +1,516 @@
+// Noise / signal-to-noise kernels (K6, K7 of SURVEY.md section 2a).
+//   nb_median_weights : np.median over frequencies of the weight maps                 filters.py:360-363
+//   nb_cell_rms       : MapFilter.makeNoiseMap grid branch, 3-sigma clipped std       filters.py:409-481
+//   nb_snr_mask       : S/N, rank_filter edge trim, survey / apod masks               filters.py:716-758, 1112-1161
+//   nb_snr_from_rms   : S/N from a cached RMS map                                     pipelines.py:216-228
+#include "nemo_b200_internal.h"
+#include <math.h>
+
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) median_weights_kernel(const T* __restrict__ w, T* __restrict__ out, int F, long long HW) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const T* base = w + (size_t)blockIdx.y * F * HW + p;
+    T v[NB_MAX_FREQ];
+    for (int f = 0; f < F; ++f) v[f] = base[(size_t)f * HW];
+    // insertion sort of <= 4 values
+    for (int i = 1; i < F; ++i) {
+        const T key = v[i];
+        int j = i - 1;
+        while (j >= 0 && v[j] > key) {
+            v[j + 1] = v[j];
+            --j;
+        }
+        v[j + 1] = key;
+    }
+    T m;
+    if (F & 1)
+        m = v[F / 2];
+    else
+        m = (T)(((double)v[F / 2 - 1] + (double)v[F / 2]) * 0.5);  // np.median: mean of the middle two
+    out[(size_t)blockIdx.y * HW + p] = m;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K6.  One CTA per (cell, image).
+#define CR_THREADS 512
+#define CR_WARPS (CR_THREADS / 32)
+
+#define NB_MAX_CHUNKS 128
+struct Chunks {  // np.linspace(0, H, n + 1, dtype=int) boundaries, passed by value
+    int y[NB_MAX_CHUNKS + 1];
+    int x[NB_MAX_CHUNKS + 1];
+};
+
+struct CellGeom {
+    int y0, y1, x0, x1;
+};
+
+__device__ __forceinline__ CellGeom cell_geom(const Chunks& ch, int i, int k, int ov, int H, int W) {
+    CellGeom g;
+    g.y0 = max(ch.y[i] - ov, 0);
+    g.y1 = min(ch.y[i + 1] + ov, H);
+    g.x0 = max(ch.x[k] - ov, 0);
+    g.x1 = min(ch.x[k + 1] + ov, W);
+    return g;
+}
+
+// block-wide sum of two doubles; result valid in every thread
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* s_red) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) {
+        s_red[wid] = a;
+        s_red[CR_WARPS + wid] = b;
+    }
+    __syncthreads();
+    double ta = 0, tb = 0;
+#pragma unroll
+    for (int i = 0; i < CR_WARPS; ++i) {
+        ta += s_red[i];
+        tb += s_red[CR_WARPS + i];
+    }
+    a = ta;
+    b = tb;
+}
+
+__device__ __forceinline__ void block_minmax(double& mn, double& mx, double* s_red) {
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) {
+        s_red[wid] = mn;
+        s_red[CR_WARPS + wid] = mx;
+    }
+    __syncthreads();
+    double ta = INFINITY, tb = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < CR_WARPS; ++i) {
+        ta = fmin(ta, s_red[i]);
+        tb = fmax(tb, s_red[CR_WARPS + i]);
+    }
+    mn = ta;
+    mx = tb;
+}
+
+__device__ __forceinline__ unsigned long long enc_w(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double dec_w(unsigned long long e) {
+    const unsigned long long b = (e & 0x8000000000000000ULL) ? (e & 0x7fffffffffffffffULL) : ~e;
+    return __longlong_as_double((long long)b);
+}
+
+// k-th smallest (0-based) weight among the good pixels of the cell: MSB-first radix select, 8 bits per pass
+template <typename T>
+__device__ double select_kth(const T* __restrict__ m, const T* __restrict__ wm, int W, CellGeom g, long long k, int* s_hist,
+                             unsigned long long* s_sel) {
+    unsigned long long prefix = 0, maskbits = 0;
+    const int cw = g.x1 - g.x0;
+    const int n = (g.y1 - g.y0) * cw;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            const int r = e / cw, c = e - r * cw;
+            const size_t off = (size_t)(g.y0 + r) * W + g.x0 + c;
+            if (m[off] != (T)0) {
+                const unsigned long long key = enc_w((double)wm[off]);
+                if ((key & maskbits) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 255ULL)], 1);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long kk = (long long)s_sel[1];
+            if (pass == 0) kk = k;
+            int d = 0;
+            for (; d < 255; ++d) {
+                if (kk < s_hist[d]) break;
+                kk -= s_hist[d];
+            }
+            s_sel[0] = prefix | ((unsigned long long)d << shift);
+            s_sel[1] = (unsigned long long)kk;
+        }
+        __syncthreads();
+        prefix = s_sel[0];
+        maskbits |= 0xFFULL << shift;
+    }
+    __syncthreads();
+    return dec_w(prefix);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CR_THREADS) cell_rms_kernel(const T* __restrict__ map, const T* __restrict__ wmed, int S, int H,
+                                                              int W, const Chunks ch, int nx,
+                                                              int ov, int numBins, double* __restrict__ table,
+                                                              double* __restrict__ edges) {
+    __shared__ double s_red[2 * CR_WARPS];
+    __shared__ int s_hist[256];
+    __shared__ unsigned long long s_sel[2];
+    extern __shared__ double s_edges[];  // numBins + 1
+    const int cell = blockIdx.x, img = blockIdx.y;
+    const int ci = cell / nx, ck = cell % nx;
+    const CellGeom g = cell_geom(ch, ci, ck, ov, H, W);
+    const T* m = map + (size_t)img * H * W;
+    const T* wm = wmed + (size_t)(img / S) * H * W;
+    const int cw = g.x1 - g.x0;
+    const int n = (g.y1 - g.y0) * cw;
+    double* tab = table + ((size_t)img * gridDim.x + cell) * numBins;
+    double* edg = edges + ((size_t)img * gridDim.x + cell) * (numBins + 1);
+
+    // good pixels: count, weight range
+    double cnt = 0, dummy = 0, wmin = INFINITY, wmax = -INFINITY;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int r = e / cw, c = e - r * cw;
+        const size_t off = (size_t)(g.y0 + r) * W + g.x0 + c;
+        if (m[off] != (T)0) {
+            cnt += 1.0;
+            const double w = (double)wm[off];
+            wmin = fmin(wmin, w);
+            wmax = fmax(wmax, w);
+        }
+    }
+    block_sum2(cnt, dummy, s_red);
+    block_minmax(wmin, wmax, s_red);
+    if (cnt == 0) {  // filters.py:446-447
+        for (int b = threadIdx.x; b < numBins; b += blockDim.x) tab[b] = 0.0;
+        for (int b = threadIdx.x; b <= numBins; b += blockDim.x) edg[b] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    const long long nGood = (long long)cnt;
+    // bin edges: np.percentile(weights[good], p) for p = b * 100 / numBins, then max + 1e-6  (filters.py:450-454)
+    if (threadIdx.x == 0) {
+        s_edges[0] = wmin;
+        s_edges[numBins] = wmax + 1e-6;
+    }
+    for (int b = 1; b < numBins; ++b) {
+        const double p = (double)b * (100.0 / (double)numBins);  // np.arange(0, 100, 100/numBins)[b]
+        const double q = p / 100.0;
+        const double nn = (double)nGood;
+        const double vi = nn * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0;  // numpy's virtual index, method 'linear'
+        const double fl = floor(vi);
+        long long lo = (long long)fl, hi = lo + 1;
+        if (lo < 0) lo = 0;
+        if (lo > nGood - 1) lo = nGood - 1;
+        if (hi < 0) hi = 0;
+        if (hi > nGood - 1) hi = nGood - 1;
+        const double gmm = vi - fl;
+        const double a = select_kth<T>(m, wm, W, g, lo, s_hist, s_sel);
+        const double bb = (hi == lo) ? a : select_kth<T>(m, wm, W, g, hi, s_hist, s_sel);
+        const double diff = bb - a;
+        double res = a + diff * gmm;           // numpy _lerp
+        if (gmm >= 0.5) res = bb - diff * (1.0 - gmm);
+        if (gmm == 0.0) res = a;
+        if (threadIdx.x == 0) s_edges[b] = res;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b <= numBins; b += blockDim.x) edg[b] = s_edges[b];
+
+    for (int b = 0; b < numBins; ++b) {
+        const double lo = s_edges[b], hi = s_edges[b + 1];
+        // mean and std of the bin's good pixels
+        double c0 = 0, s0 = 0;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            const int r = e / cw, c = e - r * cw;
+            const size_t off = (size_t)(g.y0 + r) * W + g.x0 + c;
+            const double v = (double)m[off];
+            const double w = (double)wm[off];
+            if (v != 0.0 && w >= lo && w < hi) {
+                c0 += 1.0;
+                s0 += v;
+            }
+        }
+        block_sum2(c0, s0, s_red);
+        double rms = 0.0;
+        if (c0 > 0) {
+            double mean = s0 / c0;
+            double q0 = 0, d0 = 0;
+            for (int e = threadIdx.x; e < n; e += blockDim.x) {
+                const int r = e / cw, c = e - r * cw;
+                const size_t off = (size_t)(g.y0 + r) * W + g.x0 + c;
+                const double v = (double)m[off];
+                const double w = (double)wm[off];
+                if (v != 0.0 && w >= lo && w < hi) {
+                    const double d = v - mean;
+                    q0 += d * d;
+                }
+            }
+            block_sum2(q0, d0, s_red);
+            rms = sqrt(q0 / c0);
+            double prevC = -1.0, prevS = 0.0;
+            for (int it = 0; it < 10; ++it) {  // filters.py:473-477
+                const double thr = fabs(mean + 3.0 * rms);
+                double c1 = 0, s1 = 0;
+                for (int e = threadIdx.x; e < n; e += blockDim.x) {
+                    const int r = e / cw, c = e - r * cw;
+                    const size_t off = (size_t)(g.y0 + r) * W + g.x0 + c;
+                    const double v = (double)m[off];
+                    const double w = (double)wm[off];
+                    if (v != 0.0 && w >= lo && w < hi && fabs(v) < thr) {
+                        c1 += 1.0;
+                        s1 += v;
+                    }
+                }
+                block_sum2(c1, s1, s_red);
+                if (c1 == 0) continue;  // "if mask.sum() > 0": nothing changes, and nothing will in later passes
+                mean = s1 / c1;
+                double q1 = 0, d1 = 0;
+                for (int e = threadIdx.x; e < n; e += blockDim.x) {
+                    const int r = e / cw, c = e - r * cw;
+                    const size_t off = (size_t)(g.y0 + r) * W + g.x0 + c;
+                    const double v = (double)m[off];
+                    const double w = (double)wm[off];
+                    if (v != 0.0 && w >= lo && w < hi && fabs(v) < thr) {
+                        const double d = v - mean;
+                        q1 += d * d;
+                    }
+                }
+                block_sum2(q1, d1, s_red);
+                const double newRms = sqrt(q1 / c1);
+                // fixed point: the same threshold selects the same samples from here on
+                const bool fixed = (newRms == rms) && (c1 == prevC) && (s1 == prevS);
+                rms = newRms;
+                prevC = c1;
+                prevS = s1;
+                if (fixed) break;
+            }
+        }
+        if (threadIdx.x == 0) tab[b] = rms;
+    }
+}
+
+// every pixel takes the RMS of the last cell (raster order) that covers it, has rms > 0 and whose weight bin holds it
+template <typename T>
+__global__ void __launch_bounds__(256) paint_rms_kernel(const T* __restrict__ wmed, int S, int H, int W, const Chunks ch,
+                                                        int ny, int nx, int ov, int numBins,
+                                                        const double* __restrict__ table, const double* __restrict__ edges,
+                                                        T* __restrict__ rms) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, img = blockIdx.z;
+    if (x >= W) return;
+    const double w = (double)wmed[((size_t)(img / S) * H + y) * W + x];
+    const int nCells = ny * nx;
+    double val = 0.0;
+    bool found = false;
+    for (int i = ny - 1; i >= 0 && !found; --i) {
+        if (y < max(ch.y[i] - ov, 0) || y >= min(ch.y[i + 1] + ov, H)) continue;
+        for (int k = nx - 1; k >= 0 && !found; --k) {
+            if (x < max(ch.x[k] - ov, 0) || x >= min(ch.x[k + 1] + ov, W)) continue;
+            const int cell = i * nx + k;
+            const double* edg = edges + ((size_t)img * nCells + cell) * (numBins + 1);
+            if (isnan(edg[0])) continue;
+            const double* tab = table + ((size_t)img * nCells + cell) * numBins;
+            // the reference writes bins in ascending order, so the last bin that holds w and has rms > 0 wins
+            for (int b = numBins - 1; b >= 0; --b) {
+                if (w >= edg[b] && w < edg[b + 1] && tab[b] > 0.0) {
+                    val = tab[b];
+                    found = true;
+                    break;
+                }
+            }
+        }
+    }
+    rms[((size_t)img * H + y) * W + x] = (T)val;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K7.  rank_filter(a, 0, size=(T,T)) > 0  <=>  no zero of a inside the T x T window, whose offsets along each axis are
+// [-T/2, T-1-T/2] with scipy's reflect boundary.  Done separably: row pass with a prefix sum, then a sliding column sum
+// fused with the final elementwise step.
+template <typename T>
+__global__ void __launch_bounds__(256) edge_rows_kernel(const T* __restrict__ map, const unsigned char* __restrict__ ps, int S, int H,
+                                                        int W, int trim, unsigned char* __restrict__ rowAny) {
+    extern __shared__ int s_pre[];  // W + 1 prefix counts of zeros
+    __shared__ int s_part[256];
+    const int y = blockIdx.x, img = blockIdx.y;
+    const T* m = map + ((size_t)img * H + y) * W;
+    const unsigned char* p = ps + ((size_t)(img / S) * H + y) * W;
+    const int per = (W + blockDim.x - 1) / blockDim.x;
+    const int b0 = threadIdx.x * per, b1 = min(b0 + per, W);
+    int local = 0;
+    for (int x = b0; x < b1; ++x) {
+        const T a = m[x] + (T)(1 - (int)p[x]);
+        const int z = (a == (T)0) ? 1 : 0;
+        local += z;
+        s_pre[x + 1] = local;  // local inclusive, offset added below
+    }
+    s_part[threadIdx.x] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < (int)blockDim.x; ++i) {
+            const int t = s_part[i];
+            s_part[i] = run;
+            run += t;
+        }
+        s_pre[0] = 0;
+    }
+    __syncthreads();
+    const int offv = s_part[threadIdx.x];
+    for (int x = b0; x < b1; ++x) s_pre[x + 1] += offv;
+    __syncthreads();
+    const int lo = -(trim / 2), hi = trim - 1 - trim / 2;
+    unsigned char* out = rowAny + ((size_t)img * H + y) * W;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        const int a = x + lo, b = x + hi;
+        int cnt = s_pre[min(b, W - 1) + 1] - s_pre[max(a, 0)];
+        if (a < 0) cnt += s_pre[-a];                        // indices a..-1 reflect onto 0..-a-1
+        if (b >= W) cnt += s_pre[W] - s_pre[2 * W - 1 - b];  // indices W..b reflect onto 2W-1-b..W-1
+        out[x] = cnt > 0 ? 1 : 0;
+    }
+}
+
+#define EC_SEG 32
+template <typename T>
+__global__ void __launch_bounds__(128) edge_cols_final_kernel(T* map, T* rms, const unsigned char* __restrict__ ps,
+                                                              const unsigned char* __restrict__ survey, int S, int H, int W, int trim,
+                                                              int apodPix, int realSpace, const unsigned char* __restrict__ rowAny,
+                                                              T* sn, unsigned char* __restrict__ maskOut) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ys = blockIdx.y * EC_SEG, img = blockIdx.z;
+    if (x >= W) return;
+    const size_t ib = (size_t)img * H * W, tb = (size_t)(img / S) * H * W;
+    const unsigned char* ra = rowAny + ib;
+    const int lo = -(trim / 2), hi = trim - 1 - trim / 2;
+    int cnt = 0;
+    if (trim > 0) {
+        for (int d = lo; d <= hi; ++d) cnt += ra[(size_t)reflect_idx(ys + d, H) * W + x];
+    }
+    const int ye = min(ys + EC_SEG, H);
+    for (int y = ys; y < ye; ++y) {
+        const size_t o = (size_t)y * W + x;
+        const T m0 = map[ib + o];
+        const T r0 = rms[ib + o];
+        const T edge = (trim > 0 && cnt > 0) ? (T)0 : (T)1;
+        const T psv = (T)ps[tb + o], sv = (T)survey[tb + o];
+        T snv = (r0 > (T)0) ? m0 / r0 : m0;
+        T d = m0 * edge;
+        const T sm1 = edge * sv * psv;
+        if (!realSpace) d = d * sm1;
+        const bool apodOk = (apodPix <= 0) || (x >= apodPix - 1 && x <= W - apodPix && y >= apodPix - 1 && y <= H - apodPix);
+        const T mo = apodOk ? sm1 : (T)0;
+        snv = snv * mo;
+        if (snv != snv) snv = (T)0;
+        map[ib + o] = d;
+        sn[ib + o] = snv;
+        rms[ib + o] = r0 * mo;
+        maskOut[ib + o] = (mo != (T)0) ? 1 : 0;
+        if (trim > 0 && y + 1 < ye) {  // slide the window down by one row
+            cnt += ra[(size_t)reflect_idx(y + 1 + hi, H) * W + x];
+            cnt -= ra[(size_t)reflect_idx(y + lo, H) * W + x];
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) snr_from_rms_kernel(const T* __restrict__ map, const T* __restrict__ rms, T* __restrict__ sn,
+                                                           long long HW, int S) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const size_t o = (size_t)blockIdx.y * HW + p;
+    const T r = rms[(size_t)(blockIdx.y / S) * HW + p];
+    const T m = map[o];
+    sn[o] = (r > (T)0) ? m / r : m;
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+static int cell_rms_t(const void* map, const void* wmed, int nImg, int S, int H, int W, const int* yChunks, int ny,
+                      const int* xChunks, int nx, int ov, int numBins, void* rms, double* table, double* edges, cudaStream_t st) {
+    NB_REQUIRE(ny <= NB_MAX_CHUNKS && nx <= NB_MAX_CHUNKS, NB_ERR_UNSUPPORTED, "nb_cell_rms: more than %d noise cells per axis", NB_MAX_CHUNKS);
+    Chunks ch;
+    memset(&ch, 0, sizeof(ch));
+    for (int i = 0; i <= ny; ++i) ch.y[i] = yChunks[i];
+    for (int i = 0; i <= nx; ++i) ch.x[i] = xChunks[i];
+    cell_rms_kernel<T><<<dim3(ny * nx, nImg), CR_THREADS, sizeof(double) * (numBins + 1), st>>>(
+        (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges);
+    NB_CHECK_LAUNCH();
+    paint_rms_kernel<T><<<dim3((W + 255) / 256, H, nImg), 256, 0, st>>>((const T*)wmed, S, H, W, ch, ny, nx, ov, numBins, table,
+                                                                         edges, (T*)rms);
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+template <typename T>
+static int snr_mask_t(void* map, void* rms, const unsigned char* ps, const unsigned char* survey, int nImg, int S, int H, int W,
+                      int trim, int apodPix, int realSpace, void* sn, unsigned char* maskOut, unsigned char* scratch, cudaStream_t st) {
+    if (trim > 0) {
+        edge_rows_kernel<T><<<dim3(H, nImg), 256, sizeof(int) * (W + 1), st>>>((const T*)map, ps, S, H, W, trim, scratch);
+        NB_CHECK_LAUNCH();
+    }
+    edge_cols_final_kernel<T><<<dim3((W + 127) / 128, (H + EC_SEG - 1) / EC_SEG, nImg), 128, 0, st>>>(
+        (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut);
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+extern "C" {
+
+int nb_median_weights(int prec, const void* weights, void* out, int B, int F, int H, int W, cudaStream_t st) {
+    NB_REQUIRE(weights && out && B > 0 && F >= 1 && F <= NB_MAX_FREQ, NB_ERR_ARG, "nb_median_weights: bad arguments");
+    const long long HW = (long long)H * W;
+    dim3 grid((unsigned)((HW + 255) / 256), B);
+    if (prec == NB_PREC_F64)
+        median_weights_kernel<double><<<grid, 256, 0, st>>>((const double*)weights, (double*)out, F, HW);
+    else if (prec == NB_PREC_F32)
+        median_weights_kernel<float><<<grid, 256, 0, st>>>((const float*)weights, (float*)out, F, HW);
+    else {
+        nb_set_error("nb_median_weights: bad precision %d", prec);
+        return NB_ERR_ARG;
+    }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+int nb_cell_rms(int prec, const void* map, const void* wmed, int nImg, int S, int H, int W, const int* yChunks, int ny,
+                const int* xChunks, int nx, int overlapPix, int numBins, void* rms, double* table, double* edges,
+                cudaStream_t st) {
+    NB_REQUIRE(map && wmed && yChunks && xChunks && rms && table && edges && nImg > 0 && S > 0 && ny > 0 && nx > 0, NB_ERR_ARG,
+               "nb_cell_rms: bad arguments");
+    NB_REQUIRE(numBins >= 1 && numBins <= 64, NB_ERR_ARG, "nb_cell_rms: numBins %d out of range (1..64)", numBins);
+    if (prec == NB_PREC_F64)
+        return cell_rms_t<double>(map, wmed, nImg, S, H, W, yChunks, ny, xChunks, nx, overlapPix, numBins, rms, table, edges, st);
+    if (prec == NB_PREC_F32)
+        return cell_rms_t<float>(map, wmed, nImg, S, H, W, yChunks, ny, xChunks, nx, overlapPix, numBins, rms, table, edges, st);
+    nb_set_error("nb_cell_rms: bad precision %d", prec);
+    return NB_ERR_ARG;
+}
+
+int nb_snr_mask(int prec, void* map, void* rms, const unsigned char* psMask, const unsigned char* surveyMask, int nImg, int S,
+                int H, int W, int trimPix, int apodPix, int realSpace, void* sn, unsigned char* maskOut, unsigned char* scratch,
+                cudaStream_t st) {
+    NB_REQUIRE(map && rms && psMask && surveyMask && sn && maskOut && nImg > 0 && S > 0, NB_ERR_ARG, "nb_snr_mask: bad arguments");
+    NB_REQUIRE(trimPix == 0 || scratch, NB_ERR_ARG, "nb_snr_mask: scratch required when trimPix > 0");
+    NB_REQUIRE(trimPix >= 0 && trimPix <= H && trimPix <= W, NB_ERR_UNSUPPORTED, "nb_snr_mask: trimPix %d larger than the tile", trimPix);
+    NB_REQUIRE(W <= 8192, NB_ERR_UNSUPPORTED, "nb_snr_mask: tile too wide");
+    if (prec == NB_PREC_F64)
+        return snr_mask_t<double>(map, rms, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st);
+    if (prec == NB_PREC_F32)
+        return snr_mask_t<float>(map, rms, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st);
+    nb_set_error("nb_snr_mask: bad precision %d", prec);
+    return NB_ERR_ARG;
+}
+
+int nb_snr_from_rms(int prec, const void* map, const void* rms, void* sn, int nImg, int S, int H, int W, cudaStream_t st) {
+    NB_REQUIRE(map && rms && sn && nImg > 0 && S > 0, NB_ERR_ARG, "nb_snr_from_rms: bad arguments");
+    const long long HW = (long long)H * W;
+    dim3 grid((unsigned)((HW + 255) / 256), nImg);
+    if (prec == NB_PREC_F64)
+        snr_from_rms_kernel<double><<<grid, 256, 0, st>>>((const double*)map, (const double*)rms, (double*)sn, HW, S);
+    else if (prec == NB_PREC_F32)
+        snr_from_rms_kernel<float><<<grid, 256, 0, st>>>((const float*)map, (const float*)rms, (float*)sn, HW, S);
+    else {
+        nb_set_error("nb_snr_from_rms: bad precision %d", prec);
+        return NB_ERR_ARG;
+    }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,225 @@
+// Real-space filter kernels (K12, K13 of SURVEY.md section 2a) and small cast utilities.
+//   nb_gauss_filter : ndimage.gaussian_filter / maps.subtractBackground       maps.py:1355-1368, 1433-1458
+//   nb_conv2d       : ndimage.convolve with the truncated matched-filter kernel, summed over frequency
+//                                                                             filters.py:1200-1216
+// Accumulation is fp64; storage follows prec.
+#include "nemo_b200_internal.h"
+#include "gauss.cuh"
+
+// ------------------------------------------------------------------------------------------------------
+// K12 row pass: one CTA per row, the row staged in shared memory as fp64
+template <typename T>
+__global__ void __launch_bounds__(256) gauss_rows_kernel(const T* in, T* out, int W, GaussW g) {
+    extern __shared__ double s_row[];
+    const size_t base = (size_t)blockIdx.x * W;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) s_row[x] = (double)in[base + x];
+    __syncthreads();
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        double acc = 0;
+        if (x >= g.r && x + g.r < W) {
+            for (int d = -g.r; d <= g.r; ++d) acc += g.w[d + g.r] * s_row[x + d];
+        } else {
+            for (int d = -g.r; d <= g.r; ++d) acc += g.w[d + g.r] * s_row[reflect_idx(x + d, W)];
+        }
+        out[base + x] = (T)acc;
+    }
+}
+
+// K12 column pass: 32 columns x 64 rows per CTA with a reflected halo; out = subtract ? ref - smooth : smooth
+#define GC_TX 32
+#define GC_TY 64
+template <typename T>
+__global__ void __launch_bounds__(256) gauss_cols_kernel(const T* __restrict__ in, const T* ref, T* out, int H, int W, GaussW g,
+                                                         int subtract) {
+    extern __shared__ double s_t[];
+    const int x0 = blockIdx.x * GC_TX, y0 = blockIdx.y * GC_TY;
+    const size_t plane = (size_t)blockIdx.z * H * W;
+    const int tx = threadIdx.x % GC_TX, ty = threadIdx.x / GC_TX;
+    const int rows = GC_TY + 2 * g.r;
+    const int x = x0 + tx;
+    for (int i = ty; i < rows; i += 8) {
+        const int y = reflect_idx(y0 - g.r + i, H);
+        s_t[i * GC_TX + tx] = (x < W) ? (double)in[plane + (size_t)y * W + x] : 0.0;
+    }
+    __syncthreads();
+    if (x >= W) return;
+    for (int i = ty; i < GC_TY; i += 8) {
+        const int y = y0 + i;
+        if (y >= H) break;
+        double acc = 0;
+        for (int d = 0; d <= 2 * g.r; ++d) acc += g.w[d] * s_t[(i + d) * GC_TX + tx];
+        const size_t o = plane + (size_t)y * W + x;
+        // scipy rounds the smoothed map to the array dtype before maps.subtractBackground subtracts it
+        out[o] = subtract ? (T)(ref[o] - (T)acc) : (T)acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K13.  32 x 32 outputs per CTA; input tile with a (kh-1, kw-1) reflected halo and the kernel in shared memory.
+// ndimage.convolve: out[y, x] = sum_{a, b} kern[a, b] * in[y + kh/2 - a, x + kw/2 - b]   (odd kh, kw)
+#define CV_T 32
+template <typename T>
+__global__ void __launch_bounds__(256) conv2d_kernel(const T* __restrict__ in, const double* __restrict__ kern, T* __restrict__ out,
+                                                     T* __restrict__ planes, int F, int H, int W, int kh, int kw, double scale,
+                                                     const double* __restrict__ norm, const unsigned char* __restrict__ mask) {
+    extern __shared__ double s_mem[];
+    const int th = CV_T + kh - 1, tw = CV_T + kw - 1;
+    double* s_in = s_mem;             // [th][tw]
+    double* s_k = s_mem + th * tw;    // [kh][kw]
+    const int x0 = blockIdx.x * CV_T, y0 = blockIdx.y * CV_T, b = blockIdx.z;
+    const int tx = threadIdx.x % CV_T, ty = threadIdx.x / CV_T;  // 32 x 8, four rows per thread
+    const int ry = kh / 2, rx = kw / 2;
+    double acc[4] = {0, 0, 0, 0};
+    for (int f = 0; f < F; ++f) {
+        __syncthreads();
+        const T* src = in + ((size_t)b * F + f) * H * W;
+        for (int i = threadIdx.x; i < th * tw; i += blockDim.x) {
+            const int r = i / tw, c = i - r * tw;
+            s_in[i] = (double)src[(size_t)reflect_idx(y0 - ry + r, H) * W + reflect_idx(x0 - rx + c, W)];
+        }
+        for (int i = threadIdx.x; i < kh * kw; i += blockDim.x) s_k[i] = kern[(size_t)f * kh * kw + i];
+        __syncthreads();
+        double pa[4] = {0, 0, 0, 0};
+        for (int a = 0; a < kh; ++a) {
+            for (int c = 0; c < kw; ++c) {
+                const double kv = s_k[a * kw + c];
+                // input row (y + ry - a) sits at tile row (ty_out + 2*ry - a); column likewise
+                const int col = tx + 2 * rx - c;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pa[j] += kv * s_in[(ty + 8 * j + 2 * ry - a) * tw + col];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int y = y0 + ty + 8 * j, x = x0 + tx;
+            if (planes && y < H && x < W) planes[(((size_t)b * F + f) * H + y) * W + x] = (T)pa[j];
+            acc[j] += (double)(T)pa[j];  // each plane is an array of the map dtype before the sum over frequency
+        }
+    }
+    double fac = scale;
+    if (norm) fac *= norm[b];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int y = y0 + ty + 8 * j, x = x0 + tx;
+        if (y < H && x < W) {
+            double v = acc[j] * fac;
+            if (mask) v *= (double)mask[((size_t)b * H + y) * W + x];
+            out[((size_t)b * H + y) * W + x] = (T)v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (TO)in[i];
+}
+template <typename TI>
+__global__ void __launch_bounds__(256) mask_u8_kernel(const TI* __restrict__ in, unsigned char* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (in[i] != (TI)0) ? 1 : 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sub_kernel(const T* a, const T* b, T* o, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = a[i] - b[i];
+}
+
+extern "C" {
+
+int nb_gauss_filter(int prec, const void* in, void* tmp, void* out, int B, int H, int W, double sigmaY, double sigmaX,
+                    int subtract, cudaStream_t st) {
+    NB_REQUIRE(in && tmp && out && B > 0 && sigmaY > 0 && sigmaX > 0, NB_ERR_ARG, "nb_gauss_filter: bad arguments");
+    GaussW gy, gx;
+    int rc;
+    if ((rc = make_gauss(sigmaY, &gy)) != NB_OK) return rc;
+    if ((rc = make_gauss(sigmaX, &gx)) != NB_OK) return rc;
+    NB_REQUIRE(W <= 16384, NB_ERR_UNSUPPORTED, "nb_gauss_filter: tile too wide");
+    const size_t smemC = (size_t)(GC_TY + 2 * gy.r) * GC_TX * sizeof(double);
+    const long long n = (long long)B * H * W;
+    dim3 gridC((W + GC_TX - 1) / GC_TX, (H + GC_TY - 1) / GC_TY, B);
+#define GAUSS(T)                                                                                                          \
+    {                                                                                                                     \
+        if (smemC > 48 * 1024)                                                                                            \
+            NB_CHECK_CUDA(cudaFuncSetAttribute(gauss_cols_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC)); \
+        /* scipy filters axis 0 (y) first, then axis 1 (x); each pass rounds to the array dtype */                        \
+        gauss_cols_kernel<T><<<gridC, 256, smemC, st>>>((const T*)in, nullptr, (T*)tmp, H, W, gy, 0);                     \
+        NB_CHECK_LAUNCH();                                                                                                \
+        if (!subtract) {                                                                                                  \
+            gauss_rows_kernel<T><<<(unsigned)((size_t)B * H), 256, sizeof(double) * W, st>>>((const T*)tmp, (T*)out, W, gx); \
+            NB_CHECK_LAUNCH();                                                                                            \
+        } else {                                                                                                          \
+            gauss_rows_kernel<T><<<(unsigned)((size_t)B * H), 256, sizeof(double) * W, st>>>((const T*)tmp, (T*)tmp, W, gx); \
+            NB_CHECK_LAUNCH();                                                                                            \
+            sub_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)in, (const T*)tmp, (T*)out, n);          \
+            NB_CHECK_LAUNCH();                                                                                            \
+        }                                                                                                                 \
+        return NB_OK;                                                                                                     \
+    }
+    if (prec == NB_PREC_F64) GAUSS(double)
+    if (prec == NB_PREC_F32) GAUSS(float)
+#undef GAUSS
+    nb_set_error("nb_gauss_filter: bad precision %d", prec);
+    return NB_ERR_ARG;
+}
+
+int nb_conv2d(int prec, const void* in, const double* kern, void* out, void* planes, int B, int F, int H, int W, int kh,
+              int kw, double scale, const double* norm, const unsigned char* mask, cudaStream_t st) {
+    NB_REQUIRE(in && kern && out && B > 0 && F > 0, NB_ERR_ARG, "nb_conv2d: bad arguments");
+    NB_REQUIRE((kh & 1) && (kw & 1) && kh <= 63 && kw <= 63, NB_ERR_UNSUPPORTED, "nb_conv2d: kernel %dx%d not supported (odd sides <= 63)", kh, kw);
+    const size_t smem = sizeof(double) * ((size_t)(CV_T + kh - 1) * (CV_T + kw - 1) + (size_t)kh * kw);
+    dim3 grid((W + CV_T - 1) / CV_T, (H + CV_T - 1) / CV_T, B);
+#define CONV(T)                                                                                                           \
+    {                                                                                                                     \
+        if (smem > 48 * 1024)                                                                                             \
+            NB_CHECK_CUDA(cudaFuncSetAttribute(conv2d_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        conv2d_kernel<T><<<grid, 256, smem, st>>>((const T*)in, kern, (T*)out, (T*)planes, F, H, W, kh, kw, scale, norm, mask); \
+        NB_CHECK_LAUNCH();                                                                                                \
+        return NB_OK;                                                                                                     \
+    }
+    if (prec == NB_PREC_F64) CONV(double)
+    if (prec == NB_PREC_F32) CONV(float)
+#undef CONV
+    nb_set_error("nb_conv2d: bad precision %d", prec);
+    return NB_ERR_ARG;
+}
+
+int nb_cast(int precIn, const void* in, int precOut, void* out, long long n, cudaStream_t st) {
+    NB_REQUIRE(in && out && n >= 0, NB_ERR_ARG, "nb_cast: bad arguments");
+    if (n == 0) return NB_OK;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (precIn == NB_PREC_F32 && precOut == NB_PREC_F64)
+        cast_kernel<float, double><<<grid, 256, 0, st>>>((const float*)in, (double*)out, n);
+    else if (precIn == NB_PREC_F64 && precOut == NB_PREC_F32)
+        cast_kernel<double, float><<<grid, 256, 0, st>>>((const double*)in, (float*)out, n);
+    else if (precIn == NB_PREC_F64 && precOut == NB_PREC_F64)
+        cast_kernel<double, double><<<grid, 256, 0, st>>>((const double*)in, (double*)out, n);
+    else if (precIn == NB_PREC_F32 && precOut == NB_PREC_F32)
+        cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, n);
+    else {
+        nb_set_error("nb_cast: bad precision");
+        return NB_ERR_ARG;
+    }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+int nb_mask_to_u8(int precIn, const void* in, unsigned char* out, long long n, cudaStream_t st) {
+    NB_REQUIRE(in && out && n >= 0, NB_ERR_ARG, "nb_mask_to_u8: bad arguments");
+    if (n == 0) return NB_OK;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (precIn == NB_PREC_F32)
+        mask_u8_kernel<float><<<grid, 256, 0, st>>>((const float*)in, out, n);
+    else if (precIn == NB_PREC_F64)
+        mask_u8_kernel<double><<<grid, 256, 0, st>>>((const double*)in, out, n);
+    else {
+        nb_set_error("nb_mask_to_u8: bad precision");
+        return NB_ERR_ARG;
+    }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+}  // extern "C"

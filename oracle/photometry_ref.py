@@ -1,0 +1,178 @@
+"""
+numpy/scipy restatement of /root/reference/nemo/photometry.py:25-351.  TEST INFRASTRUCTURE -- see
+oracle/__init__.py.  Catalogs are lists of dicts (what the reference hands to
+``catalogs.catalogListToTab``, catalogs.py:443-468); astropy is absent so no Table is built.
+
+  getObjectPositions   photometry.py:193-222
+  findObjects          photometry.py:25-190   (measureShapes not restated)
+  getSNRValues         photometry.py:225-255
+  measureFluxes        photometry.py:258-351
+"""
+
+import numpy as np
+from scipy import ndimage, interpolate
+
+from . import signals_ref as signals
+from .wcs_stub import j2000ToGalactic
+
+
+def makeName(RADeg, decDeg, prefix='ACT-CL'):
+    """catalogs.py:259-274 (IAU style JHHMM.m+DDMM, truncated not rounded)."""
+    ra = RADeg / 15.0
+    h = int(ra)
+    m = (ra - h) * 60.0
+    raStr = "%02d%04.1f" % (h, np.floor(m * 10) / 10.0)
+    sign = '+' if decDeg >= 0 else '-'
+    d = abs(decDeg)
+    dd = int(d)
+    dm = int((d - dd) * 60.0)
+    return prefix + " J" + raStr + sign + "%02d%02d" % (dd, dm)
+
+
+def getObjectPositions(mapData, threshold, findCenterOfMass=True):
+    if threshold < 0:
+        raise Exception("Detection threshold (thresholdSigma in the config file) cannot be negative unless in forced photometry mode.")
+    sigPix = np.array(np.greater(mapData, threshold), dtype=int)
+    sigPixMask = np.equal(sigPix, 1)
+    segmentationMap, numObjects = ndimage.label(sigPix)
+    objIDs = np.unique(segmentationMap)
+    if findCenterOfMass == True:
+        objPositions = ndimage.center_of_mass(mapData, labels=segmentationMap, index=objIDs)
+    else:
+        objPositions = ndimage.maximum_position(mapData, labels=segmentationMap, index=objIDs)
+    objNumPix = ndimage.sum(sigPixMask, labels=segmentationMap, index=objIDs)
+    return objIDs, objPositions, objNumPix, segmentationMap
+
+
+def findObjects(filteredMapDict, threshold=3.0, minObjPix=3, rejectBorder=10, findCenterOfMass=True,
+                removeRings=True, ringThresholdSigma=0, invertMap=False, objIdent='ACT-CL', longNames=False,
+                verbose=True, useInterpolator=True, measureShapes=False, DS9RegionsPath=None):
+    if rejectBorder is None:
+        rejectBorder = 0
+    data = filteredMapDict['SNMap']
+    wcs = filteredMapDict['wcs']
+    flagMask = filteredMapDict['flagMask']
+    if invertMap == True:
+        data = data * -1
+    objIDs, objPositions, objNumPix, segMap = getObjectPositions(data, threshold, findCenterOfMass=findCenterOfMass)
+    if removeRings == True:
+        minRingPix = 30
+        ringIDs, ringPositions, ringNumPix, ringSegMap = getObjectPositions(data, ringThresholdSigma,
+                                                                           findCenterOfMass=True)
+        for i in range(len(ringIDs)):
+            if type(ringNumPix) != float and ringNumPix[i] > minRingPix:
+                y, x = ringPositions[i]
+                if ringSegMap[int(y), int(x)] != ringIDs[i]:
+                    ringSegMap[np.equal(ringSegMap, ringIDs[i])] = -1 * ringSegMap[np.equal(ringSegMap, ringIDs[i])]
+        ringMask = np.array(np.less(ringSegMap, 0), dtype=int)
+    else:
+        ringMask = None
+    if useInterpolator == True:
+        mapInterpolator = interpolate.RectBivariateSpline(np.arange(data.shape[0]), np.arange(data.shape[1]),
+                                                          data, kx=3, ky=3)
+    catalog = []
+    idNumCount = 1
+    for i in range(len(objIDs)):
+        if type(objNumPix) != float and objNumPix[i] > minObjPix:
+            objDict = {}
+            objDict['id'] = idNumCount
+            objDict['x'] = objPositions[i][1]
+            objDict['y'] = objPositions[i][0]
+            if ringMask is not None:
+                if ringMask[int(objDict['y']), int(objDict['x'])] > 0:
+                    continue
+            objDict['RADeg'], objDict['decDeg'] = wcs.pix2wcs(objDict['x'], objDict['y'])
+            if objDict['RADeg'] < 0:
+                objDict['RADeg'] = 360.0 + objDict['RADeg']
+            galLong, galLat = j2000ToGalactic(objDict['RADeg'], objDict['decDeg'])
+            objDict['galacticLatDeg'] = galLat
+            objDict['name'] = makeName(objDict['RADeg'], objDict['decDeg'], prefix=objIdent)
+            objDict['numSigPix'] = objNumPix[i]
+            objDict['template'] = filteredMapDict['label']
+            objDict['tileName'] = filteredMapDict['tileName']
+            if useInterpolator == True:
+                objDict['SNR'] = mapInterpolator(objDict['y'], objDict['x'])[0][0]
+            else:
+                objDict['SNR'] = data[int(round(objDict['y'])), int(round(objDict['x']))]
+            objDict['flags'] = flagMask[int(round(objDict['y'])), int(round(objDict['x']))]
+            if measureShapes == True:
+                raise Exception("oracle: measureShapes not restated")
+            if objDict['SNR'] > threshold:
+                catalog.append(objDict)
+            idNumCount = idNumCount + 1
+    return catalog
+
+
+def getSNRValues(catalog, SNMap, wcs, useInterpolator=True, invertMap=False, prefix=''):
+    if invertMap == True:
+        SNMap = SNMap * -1
+    if useInterpolator == True:
+        mapInterpolator = interpolate.RectBivariateSpline(np.arange(SNMap.shape[0]), np.arange(SNMap.shape[1]),
+                                                          SNMap, kx=3, ky=3)
+    for obj in catalog:
+        obj[prefix + 'SNR'] = 0.0
+    for obj in catalog:
+        x, y = wcs.wcs2pix(obj['RADeg'], obj['decDeg'])
+        if int(x) > 0 and int(x) < SNMap.shape[1] and int(y) > 0 and int(y) < SNMap.shape[0]:
+            if useInterpolator == True:
+                obj[prefix + 'SNR'] = mapInterpolator(y, x)[0][0]
+            else:
+                obj[prefix + 'SNR'] = SNMap[int(round(y)), int(round(x))]
+
+
+def measureFluxes(catalog, filteredMapDict, diagnosticsDir=None, photFilteredMapDict=None,
+                  useInterpolator=True, ycObsFreqGHz=148.0):
+    mapData = filteredMapDict['data']
+    wcs = filteredMapDict['wcs']
+    mapUnits = wcs.header['BUNIT']
+    if photFilteredMapDict is not None:
+        getSNRValues(catalog, photFilteredMapDict['SNMap'], wcs, prefix='fixed_', useInterpolator=useInterpolator)
+    if 'BEAMNSR' in wcs.header.keys():
+        beamSolidAngle_nsr = wcs.header['BEAMNSR']
+        obsFreqGHz = wcs.header['FREQGHZ']
+        reportJyFluxes = True
+    else:
+        reportJyFluxes = False
+
+    def _interp(m):
+        if useInterpolator == True:
+            return interpolate.RectBivariateSpline(np.arange(m.shape[0]), np.arange(m.shape[1]), m, kx=3, ky=3)
+        return None
+
+    mapDataList = [mapData]
+    interpolatorList = [_interp(mapData)]
+    prefixList = ['']
+    if photFilteredMapDict is not None:
+        mapDataList.append(photFilteredMapDict['data'])
+        prefixList.append('fixed_')
+        interpolatorList.append(_interp(photFilteredMapDict['data']))
+    keysToAdd = ['deltaT_c', 'err_deltaT_c']
+    if mapUnits == 'yc':
+        keysToAdd = keysToAdd + ['y_c', 'err_y_c']
+    elif mapUnits == 'uK':
+        keysToAdd = keysToAdd + ['fluxJy', 'err_fluxJy']
+    for prefix in prefixList:
+        for k in keysToAdd:
+            for obj in catalog:
+                obj[prefix + k] = 0.0
+    for obj in catalog:
+        x, y = wcs.wcs2pix(obj['RADeg'], obj['decDeg'])
+        for data, prefix, interpolator in zip(mapDataList, prefixList, interpolatorList):
+            if useInterpolator == True:
+                mapValue = interpolator(y, x)[0][0]
+            else:
+                mapValue = data[int(round(y)), int(round(x))]
+            if mapUnits == 'yc':
+                yc = mapValue
+                obj[prefix + 'y_c'] = yc / 1e-4
+                obj[prefix + 'err_y_c'] = obj[prefix + 'y_c'] / obj[prefix + 'SNR']
+                deltaTc = signals.convertToDeltaT(yc, obsFrequencyGHz=ycObsFreqGHz)
+                obj[prefix + 'deltaT_c'] = deltaTc
+                obj[prefix + 'err_deltaT_c'] = abs(deltaTc / obj[prefix + 'SNR'])
+            elif mapUnits == 'uK':
+                deltaTc = mapValue
+                obj[prefix + 'deltaT_c'] = deltaTc
+                obj[prefix + 'err_deltaT_c'] = deltaTc / obj[prefix + 'SNR']
+                if reportJyFluxes == True:
+                    obj[prefix + "fluxJy"] = signals.deltaTToJyPerSr(obj[prefix + 'deltaT_c'], obsFreqGHz) * beamSolidAngle_nsr * 1.e-9
+                    obj[prefix + "err_fluxJy"] = signals.deltaTToJyPerSr(obj[prefix + 'err_deltaT_c'], obsFreqGHz) * beamSolidAngle_nsr * 1.e-9

@@ -1,0 +1,164 @@
+"""
+Restatement of the signal / unit helpers the hot path calls.  TEST INFRASTRUCTURE -- see
+oracle/__init__.py.  Citations are to /root/reference/nemo.
+
+  fSZ                     signals.py:350-375
+  convertToDeltaT         maps.py:670-688
+  deltaTToJyPerSr         photometry.py:460-474
+  smoothMap               maps.py:1433-1458
+  subtractBackground      maps.py:1355-1368
+  makeBeamModelSignalMap  signals.py:587-619
+  gnfw line-of-sight integral  gnfw.py:35-110 ; makeArnaudModelProfile signals.py:448-502
+
+Template maps are *inputs* to the hot path: the pixell painter
+(signals.py:622-672) and pyccl cosmology are absent, so the Arnaud template here is the reference's
+'legacy' painter idea (1-D profile -> radius map -> beam convolution) with a flat LCDM theta500; the
+same arrays are handed to the oracle and to the CUDA path, so parity does not depend on it.
+"""
+
+import numpy as np
+from scipy import ndimage, interpolate, integrate
+from scipy.optimize import fmin
+
+from .wcs_stub import calcAngSepDeg
+
+TCMB = 2.72548
+# CODATA 2018 (what astropy.constants returns)
+_h = 6.62607015e-34
+_kB = 1.380649e-23
+_c = 299792458.0
+
+
+def fSZ(obsFrequencyGHz):
+    x = (_h * obsFrequencyGHz * 1e9) / (_kB * TCMB)
+    return x * ((np.exp(x) + 1) / (np.exp(x) - 1)) - 4.0
+
+
+def convertToDeltaT(mapData, obsFrequencyGHz=148):
+    return mapData * fSZ(obsFrequencyGHz) * (TCMB * 1e6)
+
+
+def deltaTToJyPerSr(temp, obsFreqGHz):
+    kB = _kB * 1e7
+    h = _h * 1e7
+    c = _c * 100
+    nu = obsFreqGHz * 1.e9
+    x = h * nu / (kB * TCMB)
+    cNu = 2 * (kB * TCMB) ** 3 / (h ** 2 * c ** 2) * x ** 4 / (4 * (np.sinh(x / 2.)) ** 2)
+    cNu *= 1e23
+    return temp * cNu * 1e-6 / TCMB
+
+
+def pixelScalesDeg(wcs, RADeg='centre', decDeg='centre'):
+    """x/y pixel scale at a sky position, as smoothMap computes it (maps.py:1444-1455)."""
+    ra0, dec0 = wcs.getCentreWCSCoords()
+    if RADeg != 'centre':
+        ra0 = float(RADeg)
+    if decDeg != 'centre':
+        dec0 = float(decDeg)
+    x0, y0 = wcs.wcs2pix(ra0, dec0)
+    ra1, dec1 = wcs.pix2wcs(x0 + 1, y0 + 1)
+    xPixScale = calcAngSepDeg(ra0, dec0, ra1, dec0)
+    yPixScale = calcAngSepDeg(ra0, dec0, ra0, dec1)
+    return xPixScale, yPixScale
+
+
+def smoothMap(data, wcs, RADeg='centre', decDeg='centre', smoothScaleDeg=5.0 / 60.0):
+    xPixScale, yPixScale = pixelScalesDeg(wcs, RADeg, decDeg)
+    return ndimage.gaussian_filter(data, (smoothScaleDeg / yPixScale, smoothScaleDeg / xPixScale))
+
+
+def subtractBackground(data, wcs, RADeg='centre', decDeg='centre', smoothScaleDeg=30.0 / 60.0):
+    return data - smoothMap(data, wcs, RADeg=RADeg, decDeg=decDeg, smoothScaleDeg=smoothScaleDeg)
+
+
+class BeamProfile(object):
+    """Tabulated radial beam (signals.py:82-137 with profile1d/rDeg given directly)."""
+
+    def __init__(self, profile1d, rDeg):
+        self.profile1d = np.asarray(profile1d, dtype=np.float64)
+        self.rDeg = np.asarray(rDeg, dtype=np.float64)
+
+
+def gaussianBeam(FWHMArcmin, maxDeg=0.5, n=1800):
+    rDeg = np.linspace(0.0, maxDeg, n)
+    sigmaDeg = FWHMArcmin / 60.0 / np.sqrt(8 * np.log(2))
+    return BeamProfile(np.exp(-0.5 * (rDeg / sigmaDeg) ** 2), rDeg)
+
+
+def makeBeamModelSignalMap(degreesMap, wcs, beam, amplitude=None):
+    if amplitude is None:
+        amplitude = 1.0
+    profile1d = amplitude * beam.profile1d
+    r2p = interpolate.interp1d(beam.rDeg, profile1d, bounds_error=False, fill_value=0.0)
+    return r2p(degreesMap)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GNFW (gnfw.py)
+GNFW_DEFAULT = {'P0': 8.403, 'c500': 1.177, 'gamma': 0.3081, 'alpha': 1.0510, 'beta': 5.4905,
+                'tol': 1e-7, 'npts': 100}
+
+
+def _gnfw_func(x, params):
+    G, A, B, c500, P0 = params['gamma'], params['alpha'], params['beta'], params['c500'], params['P0']
+    prof = np.zeros(x.shape)
+    mask = np.greater(x, 0)
+    prof[mask] = P0 * ((x[mask] * c500) ** -G * (1 + (x[mask] * c500) ** A) ** ((G - B) / A))
+    return prof
+
+
+def _gnfw_xfunc(x, b, params):
+    x = np.array(x)
+    if x.ndim == 0:
+        return _gnfw_xfunc([x], b, params)[0]
+    r = (x ** 2 + b ** 2) ** .5
+    y = x * _gnfw_func(r, params)
+    y[x == 0] = 0
+    return y
+
+
+def gnfwIntegrated(b, params=GNFW_DEFAULT):
+    G, A, B = params['gamma'], params['alpha'], params['beta']
+    TH, N = params.get('tol', 1e-6), params.get('npts', 200)
+    x_max = fmin(lambda x: -_gnfw_xfunc(x, b, params), b, disp=0)[0]
+    y_max = _gnfw_xfunc(x_max, b, params)
+    x_lo = (y_max * TH) ** (1 / (1 - G))
+    x_hi = (y_max * TH) ** (1 / (1 - B))
+    u_lo, u_hi = np.log(x_lo), np.log(x_hi)
+    du = (u_hi - u_lo) / N
+    x = np.exp(np.arange(u_lo, u_hi, du))
+    I1 = np.sum(du * _gnfw_xfunc(x, b, params))
+    x_hi = np.exp(u_hi)
+    I2 = x_lo ** (1 - G) / (1 - G) + x_hi ** (1 - B) / (1 - B)
+    return I1 + I2
+
+
+def calcTheta500Arcmin(z, M500, Om0=0.3, H0=70.0):
+    """theta500 for a flat LCDM cosmology (stands in for the pyccl call at signals.py:440-444)."""
+    G = 4.30091e-9  # Mpc (km/s)^2 / MSun
+    Ez = np.sqrt(Om0 * (1 + z) ** 3 + (1 - Om0))
+    rhoCrit = 3 * (H0 * Ez) ** 2 / (8 * np.pi * G)  # MSun / Mpc^3
+    R500Mpc = (3 * M500 / (4 * np.pi * 500 * rhoCrit)) ** (1 / 3.)
+    DC = integrate.quad(lambda zz: 1.0 / np.sqrt(Om0 * (1 + zz) ** 3 + (1 - Om0)), 0, z)[0] * (_c / 1e3) / H0
+    DA = DC / (1 + z)
+    return np.degrees(np.arctan(R500Mpc / DA)) * 60.0
+
+
+def makeArnaudModelProfile(z, M500, GNFWParams='default'):
+    if GNFWParams == 'default':
+        GNFWParams = GNFW_DEFAULT
+    bRange = np.logspace(np.log10(1e-6), np.log10(100), 300)
+    cylPProfile = []
+    tol = 1e-6
+    for i in range(len(bRange)):
+        cylPProfile.append(gnfwIntegrated(bRange[i], params=GNFWParams))
+        if i > 0 and abs(cylPProfile[i] - cylPProfile[i - 1]) < tol:
+            break
+    cylPProfile = np.array(cylPProfile)
+    bRange = bRange[:i + 1]
+    cylPProfile = cylPProfile / cylPProfile.max()
+    theta500Arcmin = calcTheta500Arcmin(z, M500)
+    thetaDegRange = bRange * (theta500Arcmin / 60.)
+    tckP = interpolate.splrep(thetaDegRange, cylPProfile)
+    return {'tckP': tckP, 'theta500Arcmin': theta500Arcmin, 'rDeg': thetaDegRange}
