@@ -1,0 +1,181 @@
+"""
+Catalog plumbing for the hot path's outputs (reference nemo/catalogs.py: catalogListToTab :443-468, makeName
+:259-274, makeOptimalCatalog :149-189).  The reference builds astropy Tables; astropy is optional here: a small
+column-oriented :class:`Table` with the handful of operations the hot path uses (add_column, row iteration
+with item assignment, len, column access, vstack, sort) stands in when it is absent.
+"""
+
+import numpy as np
+
+from . import wcs as _wcs
+
+XMATCH_RADIUS_DEG = 1.4 / 60.0
+
+COLUMN_NAMES = ['name', 'RADeg', 'decDeg', 'SNR', 'numSigPix', 'template', 'tileName', 'flags', 'galacticLatDeg',
+                'x', 'y', 'id', 'ellipse_PA', 'ellipse_A', 'ellipse_B', 'ellipse_x0', 'ellipse_y0', 'ellipse_e']
+
+
+class Column(object):
+    def __init__(self, data, name):
+        self.data = np.asarray(data)
+        self.name = name
+
+
+class _Row(object):
+    def __init__(self, table, index):
+        self._t = table
+        self._i = index
+
+    def __getitem__(self, key):
+        return self._t._cols[key][self._i]
+
+    def __setitem__(self, key, value):
+        self._t._cols[key][self._i] = value
+
+    def keys(self):
+        return self._t.keys()
+
+    def asDict(self):
+        return {k: self._t._cols[k][self._i] for k in self._t.keys()}
+
+
+class Table(object):
+    """Minimal stand-in for astropy.table.Table."""
+
+    def __init__(self, names=None):
+        self._cols = {}
+        if names is not None:
+            for n in names:
+                self._cols[n] = np.zeros(0)
+
+    def add_column(self, col, name=None):
+        if isinstance(col, Column):
+            name, data = col.name, col.data
+        else:
+            data = np.asarray(col)
+        if len(self._cols) > 0 and len(data) != len(self):
+            raise ValueError("column length mismatch")
+        self._cols[name] = np.array(data)
+
+    def keys(self):
+        return list(self._cols.keys())
+
+    @property
+    def colnames(self):
+        return self.keys()
+
+    def __len__(self):
+        for v in self._cols.values():
+            return len(v)
+        return 0
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return self._cols[key]
+        if isinstance(key, (int, np.integer)):
+            return _Row(self, int(key))
+        out = Table()
+        for k, v in self._cols.items():
+            out._cols[k] = v[key]
+        return out
+
+    def __setitem__(self, key, value):
+        self._cols[key] = np.asarray(value)
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield _Row(self, i)
+
+    def copy(self):
+        out = Table()
+        for k, v in self._cols.items():
+            out._cols[k] = v.copy()
+        return out
+
+    def remove_column(self, name):
+        del self._cols[name]
+
+    def sort(self, keys):
+        if isinstance(keys, str):
+            keys = [keys]
+        order = np.lexsort([self._cols[k] for k in reversed(keys)])
+        for k in self._cols:
+            self._cols[k] = self._cols[k][order]
+
+    def toRows(self):
+        return [r.asDict() for r in self]
+
+
+def vstack(tables):
+    tables = [t for t in tables if len(t) > 0]
+    out = Table()
+    if not tables:
+        return out
+    keys = tables[0].keys()
+    for k in keys:
+        out._cols[k] = np.concatenate([t[k] if k in t.keys() else np.full(len(t), -99) for t in tables])
+    return out
+
+
+def makeName(RADeg, decDeg, prefix='ACT-CL'):
+    """IAU-style name prefix JHHMM.m+DDMM (truncated, not rounded)."""
+    hours = (RADeg / 360.0) * 24.0
+    h = int(hours)
+    mins = (hours - h) * 60.0
+    sRA = "%02d%04.1f" % (h, np.floor(mins * 10 + 1e-9) / 10.0)
+    sign = '+' if decDeg > 0 else '-'
+    d = abs(decDeg)
+    dd = int(d)
+    dm = int((d - dd) * 60.0)
+    return prefix + " J" + sRA + sign + "%02d%02d" % (dd, dm)
+
+
+def makeLongName(RADeg, decDeg, prefix='ACT-CL'):
+    hours = (RADeg / 360.0) * 24.0
+    h = int(hours)
+    mins = (hours - h) * 60.0
+    m = int(mins)
+    secs = (mins - m) * 60.0
+    sign = '+' if decDeg > 0 else '-'
+    d = abs(decDeg)
+    dd = int(d)
+    dmins = (d - dd) * 60.0
+    dm = int(dmins)
+    dsecs = (dmins - dm) * 60.0
+    return prefix + " J%02d%02d%04.1f%s%02d%02d%04.1f" % (h, m, np.floor(secs * 10) / 10.0, sign, dd, dm, np.floor(dsecs * 10) / 10.0)
+
+
+def catalogListToTab(catalogList, keysToWrite=COLUMN_NAMES):
+    """List of per-object dicts -> table with the reference's column order."""
+    availKeys = list(catalogList[0].keys())
+    tab = Table()
+    for key in keysToWrite:
+        if key in availKeys:
+            arr = [obj[key] if obj[key] is not None else -99 for obj in catalogList]
+            tab.add_column(Column(arr, key))
+    return tab
+
+
+def makeOptimalCatalog(catalogDict, constraintsList=[]):
+    """Keeps, for every group of detections within XMATCH_RADIUS_DEG of each other across filters, the one with
+    the highest S/N; sorted by (RADeg, decDeg)."""
+    allCatalogs = [catalogDict[key]['catalog'] for key in catalogDict.keys() if len(catalogDict[key]['catalog']) > 0]
+    if len(allCatalogs) == 0:
+        return Table(names=('SNR', 'RADeg', 'decDeg'))
+    allCat = vstack(allCatalogs)
+    n = len(allCat)
+    toRemove = np.zeros(n, dtype=bool)
+    ra, dec, snr = allCat['RADeg'].astype(float), allCat['decDeg'].astype(float), allCat['SNR'].astype(float)
+    for i in range(n):
+        rDeg = _wcs.calcAngSepDeg(ra[i], dec[i], ra, dec)
+        xIndices = np.where(rDeg < XMATCH_RADIUS_DEG)[0]
+        if len(xIndices) > 1:
+            best = xIndices[np.argmax(snr[xIndices])]
+            for index in xIndices:
+                if index != best:
+                    toRemove[index] = True
+    merged = allCat[~toRemove]
+    merged.sort(['RADeg', 'decDeg'])
+    if constraintsList:
+        raise Exception("catalogCuts constraints are not supported yet")
+    return merged

@@ -1,0 +1,302 @@
+"""
+Tensor-level wrappers over the C ABI (include/nemo_b200.h).  A :class:`Ops` object fixes the arithmetic type
+(fp64 by default, as the reference computes in fp64 when fed float64 maps) and the device; every method takes
+and returns torch CUDA tensors, which are used purely as device-memory handles -- all arithmetic happens in
+``libnemo_b200.so``.  Calls are asynchronous on torch's current stream.
+"""
+
+import ctypes
+import numpy as np
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class Ops(object):
+
+    def __init__(self, precision='f64', device=None):
+        self.torch = _lib.require_cuda()
+        _lib.load()
+        torch = self.torch
+        if precision in ('f64', 'float64', 'fp64'):
+            self.prec, self.dtype, self.cdtype, self.npdtype = _lib.PREC_F64, torch.float64, torch.complex128, np.float64
+        elif precision in ('f32', 'float32', 'fp32'):
+            self.prec, self.dtype, self.cdtype, self.npdtype = _lib.PREC_F32, torch.float32, torch.complex64, np.float32
+        else:
+            raise _lib.NemoB200Error("precision must be 'f64' or 'f32' (given %r)" % (precision,))
+        self.precision = 'f64' if self.prec == _lib.PREC_F64 else 'f32'
+        self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        self.launches = 0  # kernels launched through this object (bookkeeping for bench.py's gpu_launches)
+
+    # -- helpers -------------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, shape, dtype=None):
+        return self.torch.empty(shape, dtype=dtype if dtype is not None else self.dtype, device=self.device)
+
+    def zeros(self, shape, dtype=None):
+        return self.torch.zeros(shape, dtype=dtype if dtype is not None else self.dtype, device=self.device)
+
+    def to_device(self, arr, dtype=None, pinned=False):
+        """Host array -> device tensor of the compute dtype (or `dtype`)."""
+        torch = self.torch
+        if isinstance(arr, torch.Tensor):
+            t = arr
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(arr))
+        want = dtype if dtype is not None else self.dtype
+        if t.device.type == 'cpu':
+            if t.dtype != want:
+                t = t.to(want)
+            if pinned:
+                t = t.pin_memory()
+            return t.to(self.device, non_blocking=True)
+        return t.to(want).contiguous()
+
+    def _check(self, t, dtype, name):
+        if t.dtype != dtype or not t.is_contiguous() or t.device != self.device:
+            raise _lib.NemoB200Error("%s must be a contiguous %s tensor on %s (got %s, contiguous=%s, %s)"
+                                     % (name, dtype, self.device, t.dtype, t.is_contiguous(), t.device))
+
+    # -- FFTs ----------------------------------------------------------------------------------------
+    def rfft2(self, x, apodPix=0, scale=None):
+        """enmap.fft(enmap.apod(x, apodPix)) on the half plane: [B, H, W] -> [B, H, W/2+1] complex."""
+        self._check(x, self.dtype, 'x')
+        B, H, W = x.shape
+        if scale is None:
+            scale = 1.0 / np.sqrt(float(H) * float(W))
+        out = self.empty((B, H, W // 2 + 1), self.cdtype)
+        _lib.call('nb_rfft2', self.prec, _ptr(x), _ptr(out), B, H, W, int(apodPix), float(scale), self._stream())
+        self.launches += 2
+        return out
+
+    def irfft2(self, spec, W, scale=1.0, norm=None, mask=None, maskDiv=1):
+        """Un-normalised inverse; `spec` is destroyed."""
+        self._check(spec, self.cdtype, 'spec')
+        B, H, Wc = spec.shape
+        out = self.empty((B, H, W))
+        _lib.call('nb_irfft2', self.prec, _ptr(spec), _ptr(out), B, H, W, float(scale), _ptr(norm), _ptr(mask), int(maskDiv),
+                  self._stream())
+        self.launches += 2
+        return out
+
+    def apply_filter(self, fmaps, filtH, S, scale=1.0, norm=None, mask=None, out=None, scratch=None):
+        """out[o] = scale * norm[o] * mask[o // S] * Re(ifft2(sum_f fmaps[o // S, f] * filt[o, f]))."""
+        self._check(fmaps, self.cdtype, 'fmaps')
+        self._check(filtH, self.dtype, 'filtH')
+        nT, F, H, Wc = fmaps.shape
+        nOut = filtH.shape[0]
+        W = (Wc - 1) * 2
+        if nOut != nT * S or tuple(filtH.shape[1:]) != (F, H, Wc):
+            raise _lib.NemoB200Error("apply_filter: shape mismatch fmaps %s filtH %s S %d" % (tuple(fmaps.shape), tuple(filtH.shape), S))
+        if scratch is None:
+            scratch = self.empty((nOut, H, Wc), self.cdtype)
+        if out is None:
+            out = self.empty((nOut, H, W))
+        if norm is not None:
+            self._check(norm, self.torch.float64, 'norm')
+        if mask is not None:
+            self._check(mask, self.torch.uint8, 'mask')
+        _lib.call('nb_apply_filter', self.prec, _ptr(fmaps), _ptr(filtH), _ptr(scratch), _ptr(out), nOut, int(S), F, H, W,
+                  float(scale), _ptr(norm), _ptr(mask), self._stream())
+        self.launches += 2
+        return out
+
+    def window_tables(self, H, W, power):
+        """(wy, wx) of enmap.apply_window raised to `power`, on the device (wx on the half plane)."""
+        wy = np.sinc(np.fft.fftfreq(H)) ** power
+        wx = (np.sinc(np.fft.fftfreq(W)) ** power)[:W // 2 + 1].copy()
+        wx[W // 2] = np.sinc(0.5) ** power  # fftfreq gives -0.5 at the Nyquist column; sinc is even
+        return self.to_device(wy), self.to_device(wx)
+
+    def apply_window(self, data, power, restoreZeros=False, tables=None, scratch=None):
+        """In-place enmap.apply_window(data, pow=power) (+ zero restore)."""
+        self._check(data, self.dtype, 'data')
+        B, H, W = data.shape
+        if tables is None:
+            tables = self.window_tables(H, W, power)
+        wy, wx = tables
+        if scratch is None:
+            scratch = self.empty((B, H, W // 2 + 1), self.cdtype)
+        _lib.call('nb_window_deconv', self.prec, _ptr(data), _ptr(scratch), B, H, W, _ptr(wy), _ptr(wx), 1 if restoreZeros else 0,
+                  self._stream())
+        self.launches += 3
+        return data
+
+    # -- filter construction ---------------------------------------------------------------------------
+    def xpower_smooth(self, fmaps, sigma=3.0):
+        self._check(fmaps, self.cdtype, 'fmaps')
+        B, F, H, Wc = fmaps.shape
+        W = (Wc - 1) * 2
+        P = F * (F + 1) // 2
+        cov = self.empty((B, P, H, W), self.torch.float64)
+        tmp = self.empty((B, P, H, W), self.torch.float64)
+        _lib.call('nb_xpower_smooth', self.prec, _ptr(fmaps), _ptr(cov), _ptr(tmp), B, F, H, W, float(sigma), self._stream())
+        self.launches += 2
+        return cov
+
+    def build_filter(self, cov, fsig, w, S, sigPerTile, wantFull=False):
+        self._check(cov, self.torch.float64, 'cov')
+        self._check(fsig, self.cdtype, 'fsig')
+        nT, P, H, W = cov.shape
+        F = fsig.shape[1]
+        nOut = nT * S
+        Wc = W // 2 + 1
+        filtH = self.empty((nOut, F, H, Wc))
+        filtFull = self.empty((nOut, F, H, W), self.torch.float64) if wantFull else None
+        warr = (ctypes.c_double * F)(*[float(v) for v in w])
+        _lib.call('nb_build_filter', self.prec, _ptr(cov), _ptr(fsig), warr, _ptr(filtFull), _ptr(filtH), nOut, int(S),
+                  1 if sigPerTile else 0, F, H, W, self._stream())
+        self.launches += 1
+        return filtH, filtFull
+
+    def fold_filter(self, filtFull):
+        self._check(filtFull, self.torch.float64, 'filtFull')
+        shp = filtFull.shape
+        H, W = shp[-2], shp[-1]
+        n = int(np.prod(shp[:-2]))
+        filtH = self.empty(tuple(shp[:-1]) + (W // 2 + 1,))
+        _lib.call('nb_fold_filter', self.prec, _ptr(filtFull), _ptr(filtH), n, H, W, self._stream())
+        self.launches += 1
+        return filtH
+
+    def template_norm(self, maps, mode, cy, cx, numer):
+        self._check(maps, self.dtype, 'maps')
+        B, H, W = maps.shape
+        t = self.torch
+        argmax = self.empty((B,), t.int64)
+        maxVal = self.empty((B,), t.float64)
+        centre = self.zeros((B,), t.float64)
+        norm = self.empty((B,), t.float64)
+        _lib.call('nb_template_norm', self.prec, _ptr(maps), B, H, W, int(mode), float(cy), float(cx), float(numer), _ptr(argmax),
+                  _ptr(maxVal), _ptr(centre), _ptr(norm), self._stream())
+        self.launches += 1
+        return norm, argmax, maxVal, centre
+
+    def plane_values_at(self, fmaps, filtH, idx):
+        self._check(fmaps, self.cdtype, 'fmaps')
+        self._check(filtH, self.dtype, 'filtH')
+        B, F, H, Wc = fmaps.shape
+        out = self.empty((B, F), self.torch.float64)
+        _lib.call('nb_plane_values_at', self.prec, _ptr(fmaps), _ptr(filtH), _ptr(idx), _ptr(out), B, F, H, (Wc - 1) * 2, self._stream())
+        self.launches += 1
+        return out
+
+    # -- noise, S/N -------------------------------------------------------------------------------------
+    def median_weights(self, weights):
+        self._check(weights, self.dtype, 'weights')
+        B, F, H, W = weights.shape
+        out = self.empty((B, H, W))
+        _lib.call('nb_median_weights', self.prec, _ptr(weights), _ptr(out), B, F, H, W, self._stream())
+        self.launches += 1
+        return out
+
+    def cell_rms(self, maps, wmed, S, yChunks, xChunks, overlapPix, numBins):
+        self._check(maps, self.dtype, 'maps')
+        self._check(wmed, self.dtype, 'wmed')
+        nImg, H, W = maps.shape
+        ny, nx = len(yChunks) - 1, len(xChunks) - 1
+        rms = self.empty((nImg, H, W))
+        table = self.empty((nImg, ny * nx, numBins), self.torch.float64)
+        edges = self.empty((nImg, ny * nx, numBins + 1), self.torch.float64)
+        yc = (ctypes.c_int * (ny + 1))(*[int(v) for v in yChunks])
+        xc = (ctypes.c_int * (nx + 1))(*[int(v) for v in xChunks])
+        _lib.call('nb_cell_rms', self.prec, _ptr(maps), _ptr(wmed), nImg, int(S), H, W, yc, ny, xc, nx, int(overlapPix), int(numBins),
+                  _ptr(rms), _ptr(table), _ptr(edges), self._stream())
+        self.launches += 2
+        return rms, table, edges
+
+    def snr_mask(self, maps, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace):
+        """In place on maps / rms; returns (data, SNMap, surveyMaskOut u8, rms)."""
+        self._check(maps, self.dtype, 'maps')
+        self._check(rms, self.dtype, 'rms')
+        self._check(psMask, self.torch.uint8, 'psMask')
+        self._check(surveyMask, self.torch.uint8, 'surveyMask')
+        nImg, H, W = maps.shape
+        sn = self.empty((nImg, H, W))
+        maskOut = self.empty((nImg, H, W), self.torch.uint8)
+        scratch = self.empty((nImg, H, W), self.torch.uint8) if trimPix > 0 else None
+        _lib.call('nb_snr_mask', self.prec, _ptr(maps), _ptr(rms), _ptr(psMask), _ptr(surveyMask), nImg, int(S), H, W, int(trimPix),
+                  int(apodPix), 1 if realSpace else 0, _ptr(sn), _ptr(maskOut), _ptr(scratch), self._stream())
+        self.launches += 2 if trimPix > 0 else 1
+        return maps, sn, maskOut, rms
+
+    def snr_from_rms(self, maps, rms, S=1):
+        self._check(maps, self.dtype, 'maps')
+        self._check(rms, self.dtype, 'rms')
+        nImg, H, W = maps.shape
+        sn = self.empty((nImg, H, W))
+        _lib.call('nb_snr_from_rms', self.prec, _ptr(maps), _ptr(rms), _ptr(sn), nImg, int(S), H, W, self._stream())
+        self.launches += 1
+        return sn
+
+    # -- detection ---------------------------------------------------------------------------------------
+    def label4(self, maps, threshold, sign=1.0):
+        self._check(maps, self.dtype, 'maps')
+        B, H, W = maps.shape
+        t = self.torch
+        labels = self.empty((B, H, W), t.int32)
+        nLabels = self.empty((B,), t.int32)
+        nScratch = _lib.load().nb_label4_scratch_ints(B, H, W)
+        scratch = self.empty((int(nScratch),), t.int32)
+        _lib.call('nb_label4', self.prec, _ptr(maps), float(threshold), float(sign), _ptr(labels), _ptr(nLabels), _ptr(scratch), B, H, W,
+                  self._stream())
+        self.launches += 6
+        return labels, nLabels
+
+    def label_moments(self, maps, labels, maxLabels, sign=1.0):
+        self._check(maps, self.dtype, 'maps')
+        self._check(labels, self.torch.int32, 'labels')
+        B, H, W = maps.shape
+        table = self.empty((B, int(maxLabels) + 1, 8), self.torch.float64)
+        _lib.call('nb_label_moments', self.prec, _ptr(maps), float(sign), _ptr(labels), _ptr(table), B, H, W, int(maxLabels), self._stream())
+        self.launches += 4
+        return table
+
+    def spline_eval(self, imgs, imgIdx, yx, sign=1.0):
+        self._check(imgs, self.dtype, 'imgs')
+        B, H, W = imgs.shape
+        K = int(yx.shape[0])
+        out = self.empty((K,), self.torch.float64)
+        if K == 0:
+            return out
+        self._check(yx, self.torch.float64, 'yx')
+        if imgIdx is not None:
+            self._check(imgIdx, self.torch.int32, 'imgIdx')
+        _lib.call('nb_spline_eval', self.prec, _ptr(imgs), B, H, W, _ptr(imgIdx), _ptr(yx), _ptr(out), K, float(sign), self._stream())
+        self.launches += 1
+        return out
+
+    # -- real-space path -----------------------------------------------------------------------------------
+    def gauss_filter(self, maps, sigmaY, sigmaX, subtract=False):
+        self._check(maps, self.dtype, 'maps')
+        shp = maps.shape
+        H, W = shp[-2], shp[-1]
+        B = int(np.prod(shp[:-2]))
+        tmp = self.empty(shp)
+        out = self.empty(shp)
+        _lib.call('nb_gauss_filter', self.prec, _ptr(maps), _ptr(tmp), _ptr(out), B, H, W, float(sigmaY), float(sigmaX),
+                  1 if subtract else 0, self._stream())
+        self.launches += 3 if subtract else 2
+        return out
+
+    def conv2d(self, maps, kern, scale=1.0, norm=None, mask=None, wantPlanes=False):
+        self._check(maps, self.dtype, 'maps')
+        self._check(kern, self.torch.float64, 'kern')
+        B, F, H, W = maps.shape
+        kh, kw = kern.shape[-2], kern.shape[-1]
+        out = self.empty((B, H, W))
+        planes = self.empty((B, F, H, W)) if wantPlanes else None
+        _lib.call('nb_conv2d', self.prec, _ptr(maps), _ptr(kern), _ptr(out), _ptr(planes), B, F, H, W, kh, kw, float(scale), _ptr(norm),
+                  _ptr(mask), self._stream())
+        self.launches += 1
+        return (out, planes) if wantPlanes else out
+
+    def scale_mask(self, maps, scale=1.0, norm=None, mask=None):
+        """maps * scale * norm[b] * mask[b] via a 1x1 convolution (keeps all arithmetic in the library)."""
+        one = self.to_device(np.ones((1, 1, 1)), self.torch.float64)
+        return self.conv2d(maps.unsqueeze(1).contiguous(), one, scale=scale, norm=norm, mask=mask)

@@ -1,0 +1,418 @@
+"""
+Kernel-level parity: every C-ABI entry point against the numpy / scipy call it replaces, on seeded inputs.
+Integer and index results (labels, argmax, masks) must be bit-exact; fp64 results must agree to the tolerance
+written beside each check.  Runs on the GPU box:  pytest tests -m gpu
+"""
+
+import numpy as np
+import pytest
+from scipy import ndimage, interpolate
+
+from oracle import pixell_shim as enmap
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops64():
+    from nemo_b200.ops import Ops
+    return Ops('f64')
+
+
+@pytest.fixture(scope="module")
+def ops32():
+    from nemo_b200.ops import Ops
+    return Ops('f32')
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _relerr(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(64, 64), (128, 256), (256, 128), (512, 512), (1024, 1024), (2048, 512), (64, 4096), (4096, 64)])
+@pytest.mark.parametrize("apod", [0, 20])
+def test_rfft2_f64(ops64, report, shape, apod):
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2,) + shape)
+    ref = np.fft.rfft2(enmap.apod(x, apod) if apod else x) / np.sqrt(shape[0] * shape[1])
+    got = _np(ops64.rfft2(ops64.to_device(x), apodPix=apod))
+    err = _relerr(got, ref)
+    report("rfft2_f64", shape=shape, apod=apod, relerr=err)
+    assert err < 1e-13
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (256, 512), (1024, 1024)])
+def test_rfft2_f32(ops32, report, shape):
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((2,) + shape).astype(np.float32)
+    ref = np.fft.rfft2(enmap.apod(x.astype(np.float64), 20)) / np.sqrt(shape[0] * shape[1])
+    got = _np(ops32.rfft2(ops32.to_device(x), apodPix=20))
+    err = _relerr(got, ref)
+    report("rfft2_f32", shape=shape, relerr=err)
+    assert err < 2e-6
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (128, 512), (1024, 1024), (512, 2048)])
+def test_irfft2_f64(ops64, report, shape):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((3,) + shape)
+    spec = np.fft.rfft2(x)
+    mask = (rng.random((3,) + shape) > 0.2).astype(np.uint8)
+    norm = rng.random(3) + 0.5
+    got = _np(ops64.irfft2(ops64.to_device(spec, ops64.cdtype), shape[1], scale=0.5, norm=ops64.to_device(norm),
+                           mask=ops64.to_device(mask, ops64.torch.uint8)))
+    ref = x * shape[0] * shape[1] * 0.5 * norm[:, None, None] * mask
+    err = _relerr(got, ref)
+    report("irfft2_f64", shape=shape, relerr=err)
+    assert err < 1e-13
+
+
+@pytest.mark.parametrize("F,S,shape", [(1, 1, (128, 128)), (2, 3, (256, 128)), (3, 2, (64, 256)), (2, 1, (1024, 1024))])
+def test_apply_filter_f64(ops64, report, F, S, shape):
+    rng = np.random.default_rng(4)
+    nT = 2
+    H, W = shape
+    maps = rng.standard_normal((nT, F, H, W))
+    filt = rng.random((nT * S, F, H, W))            # full plane, NOT symmetric under k -> -k
+    fm = np.fft.fft2(maps) / np.sqrt(H * W)
+    norm = rng.random(nT * S) + 0.5
+    mask = (rng.random((nT, H, W)) > 0.1).astype(np.uint8)
+    ref = np.empty((nT * S, H, W))
+    for o in range(nT * S):
+        ref[o] = np.real(np.fft.ifft2(fm[o // S] * filt[o]) * H * W).sum(axis=0) * norm[o] * mask[o // S]
+    fmaps = ops64.rfft2(ops64.to_device(maps.reshape(nT * F, H, W))).reshape(nT, F, H, W // 2 + 1)
+    filtH = ops64.fold_filter(ops64.to_device(filt))
+    got = _np(ops64.apply_filter(fmaps, filtH, S, norm=ops64.to_device(norm), mask=ops64.to_device(mask, ops64.torch.uint8)))
+    err = _relerr(got, ref)
+    report("apply_filter_f64", F=F, S=S, shape=shape, relerr=err)
+    assert err < 1e-12
+
+
+@pytest.mark.parametrize("shape", [(128, 128), (256, 512), (1024, 1024)])
+def test_window_deconv_f64(ops64, report, shape):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((2,) + shape)
+    x[:, :10, :] = 0
+    x[:, 50:60, 30:40] = 0
+    ref = enmap.apply_window(x, pow=-1.0)
+    ref[x == 0] = 0
+    got = _np(ops64.apply_window(ops64.to_device(x), -1.0, restoreZeros=True))
+    err = _relerr(got, ref)
+    assert np.array_equal(got == 0, x == 0)
+    ref2 = enmap.apply_window(x, pow=1.0)
+    got2 = _np(ops64.apply_window(ops64.to_device(x), 1.0, restoreZeros=False))
+    err2 = _relerr(got2, ref2)
+    report("window_f64", shape=shape, relerr=err, relerr_pow1=err2)
+    assert err < 1e-12 and err2 < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F,shape", [(1, (64, 128)), (2, (128, 64)), (3, (64, 64)), (2, (512, 512))])
+def test_xpower_smooth_f64(ops64, report, F, shape):
+    rng = np.random.default_rng(6)
+    H, W = shape
+    maps = rng.standard_normal((2, F, H, W)) * np.array([1.0, 3.0, 0.5])[:F][None, :, None, None]
+    maps[:, 1:] += maps[:, :1] * 5  # correlated frequencies
+    fm = np.fft.fft2(maps) / np.sqrt(H * W)
+    fmaps = ops64.rfft2(ops64.to_device(maps.reshape(2 * F, H, W))).reshape(2, F, H, W // 2 + 1)
+    cov = _np(ops64.xpower_smooth(fmaps, 3.0))
+    p = 0
+    worst = 0.0
+    for i in range(F):
+        for j in range(i, F):
+            for b in range(2):
+                ref = ndimage.gaussian_filter(np.real(fm[b, i] * fm[b, j].conj()), (3, 3))
+                worst = max(worst, _relerr(cov[b, p], ref))
+            p += 1
+    report("xpower_smooth_f64", F=F, shape=shape, relerr=worst)
+    assert worst < 1e-12
+
+
+@pytest.mark.parametrize("F,S,shape", [(1, 2, (64, 64)), (2, 2, (128, 64)), (3, 1, (64, 128))])
+def test_build_filter_f64(ops64, report, F, S, shape):
+    rng = np.random.default_rng(7)
+    H, W = shape
+    nT = 2
+    maps = rng.standard_normal((nT, F, H, W))
+    maps[:, 1:] += maps[:, :1] * 3
+    fm = np.fft.fft2(maps) / np.sqrt(H * W)
+    fmaps = ops64.rfft2(ops64.to_device(maps.reshape(nT * F, H, W))).reshape(nT, F, H, W // 2 + 1)
+    covT = ops64.xpower_smooth(fmaps, 3.0)
+    templ = rng.standard_normal((S, F, H, W))
+    fsigT = ops64.rfft2(ops64.to_device(templ.reshape(S * F, H, W))).reshape(S, F, H, W // 2 + 1)
+    w = rng.standard_normal(F)
+    filtH, filtFull = ops64.build_filter(covT, fsigT, w, S, sigPerTile=False, wantFull=True)
+    filtFull = _np(filtFull)
+    fsig = np.fft.fft2(templ) / np.sqrt(H * W)
+    worst = 0.0
+    for t in range(nT):
+        noiseCov = np.array([[ndimage.gaussian_filter(np.real(fm[t, i] * fm[t, j].conj()), (3, 3)) for j in range(F)] for i in range(F)])
+        cov = np.ascontiguousarray(np.moveaxis(noiseCov, (0, 1), (2, 3)))
+        for s in range(S):
+            rhs = np.moveaxis(w[:, None, None] * abs(fsig[s]), 0, 2)[..., None]
+            ref = np.moveaxis((np.linalg.inv(cov) @ rhs)[..., 0], 2, 0)
+            worst = max(worst, _relerr(filtFull[t * S + s], ref))
+    refH = 0.5 * (filtFull + np.roll(np.flip(filtFull, axis=(-2, -1)), (1, 1), axis=(-2, -1)))[..., :W // 2 + 1]
+    errH = _relerr(_np(filtH), refH)
+    report("build_filter_f64", F=F, S=S, shape=shape, relerr=worst, relerr_fold=errH)
+    assert worst < 1e-9 and errH < 1e-14
+
+
+def test_build_filter_singular(ops64):
+    H, W, F = 64, 64, 2
+    cov = np.zeros((1, 3, H, W))
+    cov[0, 0] = 2.0
+    cov[0, 1] = 1.0
+    cov[0, 2] = 0.5        # [[2, 1], [1, 0.5]] is exactly singular
+    cov[0, :, 5, 7] = [2.0, 0.0, 4.0]
+    templ = np.zeros((1, F, H, W))
+    templ[0, :, 0, 0] = 1.0
+    fsig = ops64.rfft2(ops64.to_device(templ.reshape(F, H, W))).reshape(1, F, H, W // 2 + 1)
+    filtH, filtFull = ops64.build_filter(ops64.to_device(cov), fsig, [1.0, 1.0], 1, False, wantFull=True)
+    ff = _np(filtFull)[0]
+    assert ff[0, 0, 0] == 0.0 and ff[1, 3, 3] == 0.0
+    np.testing.assert_allclose(ff[:, 5, 7], np.array([0.5, 0.25]) / np.sqrt(H * W), rtol=1e-14)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_template_norm_f64(ops64, report, mode):
+    rng = np.random.default_rng(8)
+    H, W = 256, 512
+    m = ndimage.gaussian_filter(rng.standard_normal((3, H, W)), 2.0)
+    m[1, 100, 200] = m[1].max() + 1.0
+    m[1, 150, 10] = m[1, 100, 200]      # tie: first in raster order wins
+    cy, cx = H / 2.0 - 0.3, W / 2.0 + 0.45
+    norm, argmax, maxVal, centre = ops64.template_norm(ops64.to_device(m), mode, cy, cx, 2e-4)
+    norm, argmax, maxVal, centre = _np(norm), _np(argmax), _np(maxVal), _np(centre)
+    for b in range(3):
+        assert argmax[b] == np.argmax(m[b])
+        assert maxVal[b] == m[b].max()
+        if mode == 1:
+            sp = interpolate.RectBivariateSpline(np.arange(H), np.arange(W), m[b], kx=3, ky=3)(cy, cx)[0][0]
+            assert abs(centre[b] - sp) < 1e-12 * max(1, abs(sp))
+            assert abs(norm[b] - 2e-4 / sp) <= 1e-10 * abs(2e-4 / sp)
+        else:
+            assert norm[b] == 2e-4 / m[b].max()
+    report("template_norm", mode=mode, ok=1)
+
+
+def test_plane_values_at_f64(ops64, report):
+    rng = np.random.default_rng(9)
+    B, F, H, W = 2, 2, 64, 128
+    maps = rng.standard_normal((B, F, H, W))
+    filt = rng.random((B, F, H, W))
+    fm = np.fft.fft2(maps) / np.sqrt(H * W)
+    cube = np.real(np.fft.ifft2(fm * filt) * H * W)
+    idx = np.array([np.argmax(cube[b].sum(axis=0)) for b in range(B)])
+    ref = np.array([[cube[b, f].flatten()[idx[b]] for f in range(F)] for b in range(B)])
+    fmaps = ops64.rfft2(ops64.to_device(maps.reshape(B * F, H, W))).reshape(B, F, H, W // 2 + 1)
+    filtH = ops64.fold_filter(ops64.to_device(filt))
+    got = _np(ops64.plane_values_at(fmaps, filtH, ops64.to_device(idx, ops64.torch.int64)))
+    err = _relerr(got, ref)
+    report("plane_values_at", relerr=err)
+    assert err < 1e-11
+
+
+# ----------------------------------------------------------------------------------------------------------
+def _oracle_noise(mapData, weightsList, pixDeg, gridArcmin, numBins):
+    from oracle import filters_ref
+    from oracle.wcs_stub import SimpleCARWCS
+    wcs = SimpleCARWCS(mapData.shape, pixDeg)
+    md = [{'data': mapData, 'weights': w, 'wcs': wcs, 'flagMask': np.zeros(mapData.shape, dtype=np.uint8), 'obsFreqGHz': 150.0,
+           'label': 'x', 'surveyMask': None, 'pointSourceMask': None} for w in weightsList]
+    params = {'noiseParams': {'noiseGridArcmin': gridArcmin}}
+    if numBins is not None:
+        params['noiseParams']['numNoiseBins'] = numBins
+    f = filters_ref.MapFilter('t', md, params)
+    return f.makeNoiseMap(mapData)
+
+
+def _chunks(n, gridSize):
+    return np.linspace(0, n, int(n / gridSize + 1), dtype=int)
+
+
+@pytest.mark.parametrize("numBins", [1, 4])
+@pytest.mark.parametrize("shape", [(256, 256), (300, 420)])
+def test_cell_rms_f64(ops64, report, numBins, shape):
+    rng = np.random.default_rng(10 + numBins)
+    H, W = shape
+    pixDeg = 0.5 / 60
+    gridArcmin = 20.0
+    gridSize = int(round((gridArcmin / 60.) / pixDeg))
+    sig = 1.0 + 2.0 * (np.arange(W)[None, :] > W // 2) + 0.2 * rng.random((H, W))
+    m = rng.standard_normal((H, W)) * sig
+    m[rng.random((H, W)) < 0.002] += 30.0           # outliers for the clip
+    m[:12, :] = 0
+    m[:, -9:] = 0
+    m[100:130, 50:200] = 0                          # a hole covering whole rows of some cells
+    w1 = 1.0 / sig ** 2
+    w2 = w1 * (0.5 + rng.random((H, W)))
+    w1[m == 0] = 0
+    weights = [w1, w2]
+    ref = _oracle_noise(m, weights, pixDeg, gridArcmin, numBins if numBins > 1 else None)
+    wm = ops64.median_weights(ops64.to_device(np.array(weights)[None]))
+    assert np.array_equal(_np(wm)[0], np.median(np.array(weights), axis=0))
+    rms, table, edges = ops64.cell_rms(ops64.to_device(m[None]), wm, 1, _chunks(H, gridSize), _chunks(W, gridSize), gridSize // 2, numBins)
+    got = _np(rms)[0]
+    err = _relerr(got, ref)
+    report("cell_rms_f64", numBins=numBins, shape=shape, relerr=err, zeros_equal=int(np.array_equal(got == 0, ref == 0)))
+    assert np.array_equal(got == 0, ref == 0)
+    assert err < 1e-12
+
+
+@pytest.mark.parametrize("trim,realSpace", [(0, False), (24, False), (31, True), (120, False)])
+def test_snr_mask_f64(ops64, report, trim, realSpace):
+    rng = np.random.default_rng(12)
+    H, W = 256, 320
+    m = rng.standard_normal((2, H, W))
+    m[:, :15, :] = 0
+    m[:, :, -7:] = 0
+    m[0, 200, 100] = 0
+    ps = np.ones((1, H, W), dtype=np.uint8)
+    ps[0, 60:70, 60:75] = 0
+    survey = (rng.random((1, H, W)) > 0.05).astype(np.uint8)
+    rmsIn = np.abs(rng.standard_normal((2, H, W))) + 0.1
+    rmsIn[:, 100:110, :] = 0
+    m = m * ps
+    apodPix = 20
+    refs = []
+    for b in range(2):
+        fm = m[b]
+        SN = np.zeros(fm.shape) + fm
+        valid = rmsIn[b] > 0
+        SN[valid] = SN[valid] / rmsIn[b][valid]
+        if trim > 0:
+            edge = np.array(ndimage.rank_filter(abs(fm + (1 - ps[0])), 0, size=(trim, trim)) > 0, dtype=float)
+        else:
+            edge = np.ones(fm.shape)
+        d = fm * edge
+        sm = edge * survey[0] * ps[0]
+        if not realSpace:
+            d = d * sm
+        apodMask = np.equal(enmap.apod(np.ones(fm.shape), apodPix), 1)
+        sm = sm * apodMask
+        SN = SN * sm
+        SN[np.isnan(SN)] = 0
+        refs.append((d, SN, sm, rmsIn[b] * sm))
+    t = ops64.torch
+    data, sn, maskOut, rms = ops64.snr_mask(ops64.to_device(m), ops64.to_device(rmsIn), ops64.to_device(ps, t.uint8),
+                                            ops64.to_device(survey, t.uint8), 2, trim, apodPix, realSpace)
+    for b in range(2):
+        assert np.array_equal(_np(maskOut)[b], refs[b][2].astype(np.uint8)), "mask differs (trim=%d)" % trim
+        assert np.array_equal(_np(data)[b], refs[b][0])
+        assert np.array_equal(_np(sn)[b], refs[b][1])
+        assert np.array_equal(_np(rms)[b], refs[b][3])
+    report("snr_mask_f64", trim=trim, realSpace=realSpace, ok=1)
+
+
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,smooth,thr", [((64, 64), 0.0, 1.0), ((256, 320), 1.5, 0.3), ((1024, 1024), 2.0, 0.5),
+                                               ((512, 2048), 3.0, 0.0), ((300, 301), 1.0, -0.2), ((1024, 1024), 0.0, 4.0)])
+def test_label4_and_moments(ops64, report, shape, smooth, thr):
+    rng = np.random.default_rng(13)
+    B = 2
+    m = rng.standard_normal((B,) + shape)
+    if smooth > 0:
+        m = np.array([ndimage.gaussian_filter(x, smooth) for x in m])
+        m /= m.std()
+    labels, nLabels = ops64.label4(ops64.to_device(m), thr)
+    labels, nLabels = _np(labels), _np(nLabels)
+    nmax = int(nLabels.max())
+    table = _np(ops64.label_moments(ops64.to_device(m), ops64.to_device(labels, ops64.torch.int32), nmax))
+    for b in range(B):
+        ref, n = ndimage.label(m[b] > thr)
+        assert nLabels[b] == n
+        assert np.array_equal(labels[b], ref), "labels differ"
+        ids = np.unique(ref)
+        com = np.array(ndimage.center_of_mass(m[b], labels=ref, index=ids))
+        npix = ndimage.sum(m[b] > thr, labels=ref, index=ids)
+        mpos = np.array(ndimage.maximum_position(m[b], labels=ref, index=ids))
+        t = table[b]
+        gotCom = np.stack([t[ids, 1] / t[ids, 0], t[ids, 2] / t[ids, 0]], axis=1)
+        if ids[0] == 0:
+            # background moments can cancel catastrophically; compare the sums instead
+            gotCom, com = gotCom[1:], com[1:]
+        assert np.abs(gotCom - com).max() < 1e-9 if len(com) else True
+        cnt = t[ids, 3].copy()
+        if ids[0] == 0:
+            cnt[0] = 0
+        assert np.array_equal(cnt, npix)
+        gotPos = np.stack([t[ids, 5] // shape[1], t[ids, 5] % shape[1]], axis=1)
+        assert np.array_equal(gotPos, mpos)
+    report("label4", shape=shape, smooth=smooth, thr=thr, nlabels=int(nLabels[0]))
+
+
+def test_label4_edge_cases(ops64):
+    t = ops64.torch
+    for m in [np.zeros((1, 64, 64)), np.ones((1, 64, 64)), np.eye(64)[None], np.indices((64, 64)).sum(axis=0)[None] % 2.0]:
+        labels, n = ops64.label4(ops64.to_device(m), 0.5)
+        ref, nref = ndimage.label(m[0] > 0.5)
+        assert int(_np(n)[0]) == nref
+        assert np.array_equal(_np(labels)[0], ref)
+    # spiral: one long snake, stresses the union-find
+    s = np.zeros((1, 128, 128))
+    for k in range(0, 64, 2):
+        s[0, k, k:128 - k] = 1
+        s[0, k:128 - k, 127 - k] = 1
+        s[0, 127 - k, k:128 - k] = 1
+        s[0, k + 2:128 - k, k] = 1
+    labels, n = ops64.label4(ops64.to_device(s), 0.5)
+    ref, nref = ndimage.label(s[0] > 0.5)
+    assert int(_np(n)[0]) == nref and np.array_equal(_np(labels)[0], ref)
+    # inverted sign (invertMap)
+    rng = np.random.default_rng(3)
+    m = rng.standard_normal((1, 100, 130))
+    labels, n = ops64.label4(ops64.to_device(m), 1.0, sign=-1.0)
+    ref, nref = ndimage.label(-m[0] > 1.0)
+    assert np.array_equal(_np(labels)[0], ref)
+
+
+def test_spline_eval_f64(ops64, report):
+    rng = np.random.default_rng(14)
+    B, H, W = 2, 200, 260
+    img = rng.standard_normal((B, H, W))
+    K = 300
+    yx = np.stack([rng.uniform(26, H - 27, K), rng.uniform(26, W - 27, K)], axis=1)
+    yx[:5] = np.round(yx[:5])               # exactly on pixels
+    idx = rng.integers(0, B, K).astype(np.int32)
+    got = _np(ops64.spline_eval(ops64.to_device(img), ops64.to_device(idx, ops64.torch.int32), ops64.to_device(yx)))
+    sp = [interpolate.RectBivariateSpline(np.arange(H), np.arange(W), img[b], kx=3, ky=3) for b in range(B)]
+    ref = np.array([sp[idx[k]](yx[k, 0], yx[k, 1])[0][0] for k in range(K)])
+    err = float(np.abs(got - ref).max())
+    report("spline_eval", abserr=err)
+    assert err < 1e-11
+
+
+@pytest.mark.parametrize("sig", [(3.0, 3.0), (7.3, 11.9), (1.0, 25.0)])
+def test_gauss_filter_f64(ops64, report, sig):
+    rng = np.random.default_rng(15)
+    x = rng.standard_normal((2, 200, 330))
+    ref = np.array([ndimage.gaussian_filter(a, sig) for a in x])
+    got = _np(ops64.gauss_filter(ops64.to_device(x), sig[0], sig[1]))
+    got2 = _np(ops64.gauss_filter(ops64.to_device(x), sig[0], sig[1], subtract=True))
+    err = _relerr(got, ref)
+    err2 = _relerr(got2, x - ref)
+    report("gauss_filter", sig=sig, relerr=err, relerr_sub=err2)
+    assert err < 1e-13 and err2 < 1e-13
+
+
+@pytest.mark.parametrize("k", [(29, 29), (5, 7), (1, 1), (63, 3)])
+def test_conv2d_f64(ops64, report, k):
+    rng = np.random.default_rng(16)
+    B, F, H, W = 2, 2, 150, 170
+    x = rng.standard_normal((B, F, H, W))
+    kern = rng.standard_normal((F,) + k)
+    norm = rng.random(B) + 0.5
+    mask = (rng.random((B, H, W)) > 0.2).astype(np.uint8)
+    ref = np.array([sum(ndimage.convolve(x[b, f], kern[f]) for f in range(F)) * norm[b] * 0.7 * mask[b] for b in range(B)])
+    got, planes = ops64.conv2d(ops64.to_device(x), ops64.to_device(kern, ops64.torch.float64), scale=0.7, norm=ops64.to_device(norm),
+                               mask=ops64.to_device(mask, ops64.torch.uint8), wantPlanes=True)
+    err = _relerr(_np(got), ref)
+    errP = _relerr(_np(planes)[1, 0], ndimage.convolve(x[1, 0], kern[0]))
+    report("conv2d", k=k, relerr=err, relerr_plane=errP)
+    assert err < 1e-12 and errP < 1e-12
