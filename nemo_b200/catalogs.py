@@ -122,7 +122,7 @@ def makeName(RADeg, decDeg, prefix='ACT-CL'):
     hours = (RADeg / 360.0) * 24.0
     h = int(hours)
     mins = (hours - h) * 60.0
-    sRA = "%02d%04.1f" % (h, np.floor(mins * 10 + 1e-9) / 10.0)
+    sRA = "%02d%04.1f" % (h, np.floor(mins * 10) / 10.0)
     sign = '+' if decDeg > 0 else '-'
     d = abs(decDeg)
     dd = int(d)
@@ -156,26 +156,49 @@ def catalogListToTab(catalogList, keysToWrite=COLUMN_NAMES):
     return tab
 
 
+def _crossMatchKeepBest(ra, dec, snr, radiusDeg):
+    """Boolean mask of rows to remove: for every row, all rows within radiusDeg of it except the one with the highest
+    S/N (first one on ties) are dropped.  Same outcome as the reference's O(n^2) loop (catalogs.py:171-183), with the
+    neighbour search done by a k-d tree on unit vectors and the reference's separation formula as the final test."""
+    from scipy.spatial import cKDTree
+    n = len(ra)
+    toRemove = np.zeros(n, dtype=bool)
+    if n < 2:
+        return toRemove
+    a, d = np.radians(ra), np.radians(dec)
+    xyz = np.stack([np.cos(d) * np.cos(a), np.cos(d) * np.sin(a), np.sin(d)], axis=1)
+    tree = cKDTree(xyz)
+    chord = 2 * np.sin(np.radians(radiusDeg * 1.01) / 2)
+    for i, nb in enumerate(tree.query_ball_point(xyz, chord)):
+        if len(nb) < 2:
+            continue
+        nb = np.sort(np.asarray(nb))
+        rDeg = _wcs.calcAngSepDeg(ra[i], dec[i], ra[nb], dec[nb])
+        xIndices = nb[rDeg < radiusDeg]
+        if len(xIndices) > 1:
+            best = xIndices[np.argmax(snr[xIndices])]
+            toRemove[xIndices[xIndices != best]] = True
+    return toRemove
+
+
 def makeOptimalCatalog(catalogDict, constraintsList=[]):
     """Keeps, for every group of detections within XMATCH_RADIUS_DEG of each other across filters, the one with
-    the highest S/N; sorted by (RADeg, decDeg)."""
+    the highest S/N; sorted by (RADeg, decDeg)  (catalogs.py:149-189)."""
     allCatalogs = [catalogDict[key]['catalog'] for key in catalogDict.keys() if len(catalogDict[key]['catalog']) > 0]
     if len(allCatalogs) == 0:
         return Table(names=('SNR', 'RADeg', 'decDeg'))
     allCat = vstack(allCatalogs)
-    n = len(allCat)
-    toRemove = np.zeros(n, dtype=bool)
     ra, dec, snr = allCat['RADeg'].astype(float), allCat['decDeg'].astype(float), allCat['SNR'].astype(float)
-    for i in range(n):
-        rDeg = _wcs.calcAngSepDeg(ra[i], dec[i], ra, dec)
-        xIndices = np.where(rDeg < XMATCH_RADIUS_DEG)[0]
-        if len(xIndices) > 1:
-            best = xIndices[np.argmax(snr[xIndices])]
-            for index in xIndices:
-                if index != best:
-                    toRemove[index] = True
-    merged = allCat[~toRemove]
+    merged = allCat[~_crossMatchKeepBest(ra, dec, snr, XMATCH_RADIUS_DEG)]
     merged.sort(['RADeg', 'decDeg'])
     if constraintsList:
         raise Exception("catalogCuts constraints are not supported yet")
     return merged
+
+
+def removeDuplicates(tab):
+    """Drops lower-S/N duplicates of the same object found in overlapping tiles (catalogs.py:520-565)."""
+    if len(tab) < 2:
+        return tab
+    ra, dec, snr = tab['RADeg'].astype(float), tab['decDeg'].astype(float), tab['SNR'].astype(float)
+    return tab[~_crossMatchKeepBest(ra, dec, snr, XMATCH_RADIUS_DEG)]

@@ -130,21 +130,22 @@ template <int F> __device__ __forceinline__ void solve_sym(const double* c /*P p
             }
         }
         if (A[k][k] == 0.0) singular = true;
-        const double inv = 1.0 / A[k][k];
+        // explicit round-to-nearest multiplies / subtractions: no FMA contraction, so every instance of this solve
+        // (a mode and its mirror are solved by different threads) rounds identically
 #pragma unroll
         for (int i = k + 1; i < F; ++i) {
-            const double m = A[i][k] * inv;
+            const double m = __ddiv_rn(A[i][k], A[k][k]);
 #pragma unroll
-            for (int j = k + 1; j < F; ++j) A[i][j] -= m * A[k][j];
-            bb[i] -= m * bb[k];
+            for (int j = k + 1; j < F; ++j) A[i][j] = __dsub_rn(A[i][j], __dmul_rn(m, A[k][j]));
+            bb[i] = __dsub_rn(bb[i], __dmul_rn(m, bb[k]));
         }
     }
 #pragma unroll
     for (int i = F - 1; i >= 0; --i) {
         double s = bb[i];
 #pragma unroll
-        for (int j = i + 1; j < F; ++j) s -= A[i][j] * x[j];
-        x[i] = s / A[i][i];
+        for (int j = i + 1; j < F; ++j) s = __dsub_rn(s, __dmul_rn(A[i][j], x[j]));
+        x[i] = __ddiv_rn(s, A[i][i]);
     }
     if (singular) {
 #pragma unroll
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(256) build_filter_kernel(const double* __restr
 #pragma unroll
     for (int f = 0; f < F; ++f) {
         const C2 v = fsig[(((size_t)sidx * F + f) * H + ky) * Wc + kx];
-        rhs[f] = fw.w[f] * hypot((double)v.x, (double)v.y);  // np.abs of a complex number is hypot
+        rhs[f] = __dmul_rn(fw.w[f], hypot((double)v.x, (double)v.y));  // np.abs of a complex number is hypot
     }
 #pragma unroll
     for (int p = 0; p < P; ++p) {
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(256) build_filter_kernel(const double* __restr
     solve_sym<F>(c2, rhs, x2);
 #pragma unroll
     for (int f = 0; f < F; ++f) {
-        filtH[(((size_t)o * F + f) * H + ky) * Wc + kx] = (T)(0.5 * (x1[f] + x2[f]));
+        filtH[(((size_t)o * F + f) * H + ky) * Wc + kx] = (T)(0.5 * __dadd_rn(x1[f], x2[f]));
         if (filtFull) {
             double* ff = filtFull + ((size_t)o * F + f) * H * W;
             ff[(size_t)ky * W + kx] = x1[f];

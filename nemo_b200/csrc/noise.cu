@@ -190,6 +190,10 @@ __global__ void __launch_bounds__(CR_THREADS) cell_rms_kernel(const T* __restric
         s_edges[numBins] = wmax + 1e-6;
     }
     for (int b = 1; b < numBins; ++b) {
+        if (wmin == wmax) {  // constant weights in the cell: every percentile is that constant
+            if (threadIdx.x == 0) s_edges[b] = wmin;
+            continue;
+        }
         const double p = (double)b * (100.0 / (double)numBins);  // np.arange(0, 100, 100/numBins)[b]
         const double q = p / 100.0;
         const double nn = (double)nGood;

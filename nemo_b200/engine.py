@@ -1,0 +1,170 @@
+"""
+Batched device pipeline for the filter -> noise -> S/N hot path.  Everything here works on torch CUDA tensors
+(handles) through :class:`nemo_b200.ops.Ops`; it is shared by the class API in ``filters.py`` (one tile, one
+scale) and by the tile x scale batches of ``pipelines.py``.  Image index convention for a batch of nT tiles
+and S filter scales: o = tile * S + scale.
+
+Reference arithmetic restated (nemo/filters.py): :526-529 input FFTs, :568-587 noise covariance, :590-630 filter,
+:635-688 normalisation, :699/:824-859 application, :716-758 noise / S-N / masks, :101-104 pixel-window undo.
+"""
+
+import numpy as np
+
+from . import signals
+from . import maps as nmaps
+
+
+# ------------------------------------------------------------------------------------------------------
+# host-side parameter logic
+def noiseGrid(shape, noiseParams, pixDeg):
+    """(yChunks, xChunks, overlapPix, numBins) of MapFilter.makeNoiseMap's grid branch (filters.py:412-429)."""
+    if noiseParams.get('noiseGridArcmin') == "smart":
+        raise Exception("noiseGridArcmin = 'smart' is not implemented in nemo_b200 (grid or None only)")
+    if 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] in ['biweight', 'percentile']:
+        raise Exception("RMSEstimator '%s' is not implemented in nemo_b200 (default 3-sigma clipping only)" % noiseParams['RMSEstimator'])
+    if 'noiseGridArcmin' not in noiseParams.keys() or noiseParams['noiseGridArcmin'] is None:
+        overlapPix = 0
+        numXChunks = 1
+        numYChunks = 1
+    else:
+        gridSize = int(round((noiseParams['noiseGridArcmin'] / 60.) / pixDeg))
+        overlapPix = int(gridSize / 2)
+        numXChunks = shape[1] / gridSize
+        numYChunks = shape[0] / gridSize
+    yChunks = np.linspace(0, shape[0], int(numYChunks + 1), dtype=int)
+    xChunks = np.linspace(0, shape[1], int(numXChunks + 1), dtype=int)
+    numBins = noiseParams['numNoiseBins'] if 'numNoiseBins' in noiseParams.keys() else 1
+    return yChunks, xChunks, overlapPix, int(numBins)
+
+
+def trimSizePix(params, pixDeg, realSpace):
+    """Edge-trim window of the rank filter (filters.py:728-735 Fourier class, :1137-1141 real-space class)."""
+    if realSpace:
+        if 'edgeTrimArcmin' in params.keys():
+            return int(round((params['edgeTrimArcmin'] / 60.) / pixDeg))
+        gridSize = int(round((params['noiseParams']['noiseGridArcmin'] / 60.) / pixDeg))
+        return int(round(gridSize * 3.0))
+    if 'edgeTrimArcmin' in params.keys() and params['edgeTrimArcmin'] > 0:
+        return int(round((params['edgeTrimArcmin'] / 60.) / pixDeg))
+    elif 'noiseGridArcmin' in params['noiseParams'] and params['noiseParams']['noiseGridArcmin'] != "smart" \
+            and params['noiseParams']['noiseGridArcmin'] is not None:
+        gridSize = int(round((params['noiseParams']['noiseGridArcmin'] / 60.) / pixDeg))
+        return int(round(gridSize * 3.0))
+    return 0
+
+
+def spectralWeights(mapDicts, params):
+    """Signal frequency weighting w (filters.py:589-611)."""
+    w = []
+    for mapDict in mapDicts:
+        if mapDict['units'] != 'yc':
+            if 'specWeight' in mapDict.keys():
+                w.append(mapDict['specWeight'])
+            else:
+                if params['outputUnits'] == 'yc':
+                    w.append(signals.fSZ(mapDict['obsFreqGHz']))
+                elif params['outputUnits'] == 'uK':
+                    if 'alpha' in params.keys() and params['alpha'] is not None:
+                        w.append(np.power(mapDict['obsFreqGHz'] / mapDicts[0]['obsFreqGHz'], params['alpha']))
+                    else:
+                        w.append(1.0)
+                else:
+                    raise Exception('need to specify "outputUnits" ("yc" or "uK") in filter params')
+        else:
+            w.append(1.0)
+    return np.array(w, dtype=np.float64)
+
+
+def normAmplitudes(mapDicts, params, y0=2e-4):
+    """Amplitudes handed to makeSignalTemplateMap for the normalisation templates (filters.py:639-646); None for 'uK'."""
+    if params['outputUnits'] != 'yc':
+        return None
+    amps = []
+    for mapDict in mapDicts:
+        if mapDict['units'] == 'yc':
+            amps.append(y0)
+        else:
+            amps.append(nmaps.convertToDeltaT(y0, mapDict['obsFreqGHz']))
+    return amps
+
+
+# ------------------------------------------------------------------------------------------------------
+# device pipeline
+def buildFourierFilters(ops, fmapsNoise, templUnit, templNorm, w, outputUnits, cy, cx, y0=2e-4, sigPerTile=False,
+                        wantFull=False, bckSubSigmas=None):
+    """Builds matched filters for nT tiles x S scales.
+
+    fmapsNoise [nT, F, H, Wc]    spectra the noise covariance is measured from
+    templUnit  [nS*, F, H, W]    unit-normalised signal templates (nS* = S, or nT*S when sigPerTile)
+    templNorm  same shape        templates with the normalisation amplitude, pixel window NOT yet applied ('yc');
+                                 ignored for 'uK' (the unit templates are used, filters.py:678-686)
+    Returns dict: filtH [nT*S, F, H, Wc], filtFull (or None), signalNorm [nT*S] fp64, fRelWeights [nT*S, F] (or None),
+    all on the device; nothing is synchronised.
+    """
+    torch = ops.torch
+    nT, F, H, Wc = fmapsNoise.shape
+    W = (Wc - 1) * 2
+    nS = templUnit.shape[0]
+    S = nS // nT if sigPerTile else nS
+    nOut = nT * S
+    cov = ops.xpower_smooth(fmapsNoise, 3.0)
+    fsig = ops.rfft2(templUnit.reshape(nS * F, H, W), apodPix=0).reshape(nS, F, H, Wc)
+    filtH, filtFull = ops.build_filter(cov, fsig, w, S, sigPerTile, wantFull=wantFull)
+    del cov
+    if outputUnits == 'yc':
+        tn = templNorm.reshape(nS * F, H, W).clone()
+        ops.apply_window(tn, 1.0, restoreZeros=False)   # enmap.apply_window(signalMap, pow=1.0), filters.py:647
+        fsigN = ops.rfft2(tn, apodPix=0).reshape(nS, F, H, Wc)
+        del tn
+        mode, numer = 1, y0
+    elif outputUnits == 'uK':
+        fsigN = fsig
+        mode, numer = 0, 1.0
+    else:
+        raise Exception('need to specify "outputUnits" ("yc" or "uK") in filter params')
+    # filteredSignal = applyFilter(fSignalMaps) with signalNorm still 1 (filters.py:653, 686)
+    filteredSignal = ops.empty((nOut, H, W))
+    scratch = ops.empty((S if not sigPerTile else nOut, H, Wc), ops.cdtype)
+    if sigPerTile:
+        ops.apply_filter(fsigN, filtH, 1, out=filteredSignal, scratch=scratch)
+    else:
+        for t in range(nT):
+            ops.apply_filter(fsigN, filtH[t * S:(t + 1) * S], 1, out=filteredSignal[t * S:(t + 1) * S], scratch=scratch)
+    if bckSubSigmas is not None:
+        filteredSignal = ops.gauss_filter(filteredSignal, bckSubSigmas[0], bckSubSigmas[1], subtract=True)
+    signalNorm, argmaxIdx, maxVal, centreVal = ops.template_norm(filteredSignal, mode, cy, cx, numer)
+    fRel = None
+    if outputUnits == 'yc':
+        if sigPerTile:
+            planes = ops.plane_values_at(fsigN, filtH, argmaxIdx)
+        else:
+            planes = ops.empty((nOut, F), torch.float64)
+            for t in range(nT):
+                planes[t * S:(t + 1) * S] = ops.plane_values_at(fsigN, filtH[t * S:(t + 1) * S].contiguous(), argmaxIdx[t * S:(t + 1) * S].contiguous())
+        # fRelWeight = plane value at the argmax pixel / total signal there (filters.py:664-670)
+        fRel = (planes, maxVal)
+    return {'filtH': filtH, 'filtFull': filtFull, 'signalNorm': signalNorm, 'fRel': fRel, 'S': S}
+
+
+def applyFourierFilters(ops, fmaps, filtH, S, signalNorm, psMask, bckSubSigmas=None):
+    """MatchedFilter.applyFilter (filters.py:824-859) for every (tile, scale), times psMask (:717)."""
+    if bckSubSigmas is None:
+        return ops.apply_filter(fmaps, filtH, S, norm=signalNorm, mask=psMask)
+    m = ops.apply_filter(fmaps, filtH, S)
+    m = ops.gauss_filter(m, bckSubSigmas[0], bckSubSigmas[1], subtract=True)
+    maskFull = psMask if S == 1 or psMask is None else psMask.repeat_interleave(S, dim=0)
+    return ops.scale_mask(m, norm=signalNorm, mask=maskFull)
+
+
+def noiseSNAndMasks(ops, filtered, wmed, psMask, surveyMask, S, grid, trimPix, apodPix, realSpace):
+    """makeNoiseMap + S/N + edge trim + masks (filters.py:719-758).  `filtered` is overwritten with `data`.
+    Returns (data, SNMap, surveyMaskOut u8, RMSMap, cellTable, cellEdges)."""
+    yChunks, xChunks, overlapPix, numBins = grid
+    rms, table, edges = ops.cell_rms(filtered, wmed, S, yChunks, xChunks, overlapPix, numBins)
+    data, sn, maskOut, rms = ops.snr_mask(filtered, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace)
+    return data, sn, maskOut, rms, table, edges
+
+
+def undoPixelWindow(ops, data, tables=None):
+    """filterMaps' final step (filters.py:101-104): deconvolve the pixel window, keep exact zeros."""
+    return ops.apply_window(data, -1.0, restoreZeros=True, tables=tables)

@@ -1,0 +1,645 @@
+"""
+Drop-in for the reference's ``nemo.filters`` on the hot path: same function / class / method names, arguments and
+returned dictionary (reference nemo/filters.py:54-109 ``filterMaps``; :112-516 ``MapFilter``; :519-859
+``MatchedFilter``; :862-1218 ``RealSpaceMatchedFilter``; :1222-1331 template mix-ins and concrete classes), with
+the arithmetic done by hand-written sm_100a CUDA kernels behind ``libnemo_b200.so``.  There is no CPU path.
+
+Differences a caller can see:
+  * the maps in the returned dictionary (``data``, ``SNMap``, ``surveyMask``) are :class:`nemo_b200.device.DeviceArray`
+    objects -- numpy-compatible (``np.asarray`` works) but kept on the GPU so ``photometry.findObjects`` /
+    ``measureFluxes`` do not copy them back and forth;
+  * map dictionaries may be plain dicts that already hold ``data``, ``weights``, ``surveyMask``,
+    ``pointSourceMask``, ``flagMask``, ``wcs``, ``obsFreqGHz``, ``units``, ``beamFileName`` (a path or a
+    ``signals.BeamProfile``); objects with a ``preprocess`` method (the reference's ``maps.MapDict``) are
+    preprocessed exactly as the reference does;
+  * filter caches are FITS when astropy is importable, ``.npz`` with the same content otherwise;
+  * options whose dependencies are absent raise instead of silently differing: noise methods ``model`` and
+    ``max(dataMap,CMB)``, ``noiseModelCatalog``, ``noiseGridArcmin: smart``, ``RMSEstimator`` biweight/percentile,
+    ``reshapeFilter``; tiles must have power-of-two sides (64..4096).
+"""
+
+import os
+import numpy as np
+from numpy import fft
+from scipy import interpolate
+
+from . import device
+from . import engine
+from . import maps
+from . import signals
+from . import wcs as _wcs
+from .device import DeviceArray
+
+
+# -------------------------------------------------------------------------------------------------------------
+def filterMaps(unfilteredMapsDictList, filterParams, tileName, diagnosticsDir='.', selFnDir='.', verbose=True,
+               undoPixelWindow=True, useCachedFilter=False, returnFilter=False):
+    """Builds and applies filters to the unfiltered map(s); same contract as the reference's ``filterMaps``."""
+    f = filterParams
+    label = f['label'] + "#" + tileName
+    if verbose:
+        print("... making filtered map %s" % (label))
+    filterClass = f['class'] if not isinstance(f['class'], str) else globals()[f['class']]
+    filterObj = filterClass(f['label'], unfilteredMapsDictList, f['params'], tileName=tileName,
+                            diagnosticsDir=diagnosticsDir, selFnDir=selFnDir)
+    filteredMapDict = filterObj.buildAndApply(useCachedFilter=useCachedFilter)
+
+    # Keywords needed for photometry later
+    filteredMapDict['wcs'].header['BUNIT'] = filteredMapDict['mapUnits']
+    if 'beamSolidAngle_nsr' in filteredMapDict.keys() and filteredMapDict['beamSolidAngle_nsr'] > 0:
+        filteredMapDict['wcs'].header['BEAMNSR'] = filteredMapDict['beamSolidAngle_nsr']
+        filteredMapDict['wcs'].header['FREQGHZ'] = filteredMapDict['obsFreqGHz']
+    filteredMapDict['wcs'].updateFromHeader()
+
+    if undoPixelWindow == True:
+        ops = filterObj.ops
+        data = filteredMapDict['data'].tensor.unsqueeze(0)
+        engine.undoPixelWindow(ops, data)
+        filteredMapDict['data'] = DeviceArray(data[0])
+
+    if returnFilter == True:
+        return filteredMapDict, filterObj
+    return filteredMapDict
+
+
+# -------------------------------------------------------------------------------------------------------------
+def _maskToU8(m, shape):
+    if m is None:
+        return np.ones(shape, dtype=np.uint8)
+    m = np.asarray(m)
+    return np.ascontiguousarray(np.not_equal(m, 0), dtype=np.uint8)
+
+
+class MapFilter(object):
+    """Base class: prepares the maps of one tile on the device and provides the noise-map machinery."""
+
+    def __init__(self, label, unfilteredMapsDictList, paramsDict, tileName='PRIMARY', writeFilter=False,
+                 forceRebuild=False, diagnosticsDir=None, selFnDir=None):
+        self.label = label
+        self.params = paramsDict
+        self.diagnosticsDir = diagnosticsDir
+        self.selFnDir = selFnDir
+        self.tileName = tileName
+        if diagnosticsDir is not None:
+            self.filterFileName = diagnosticsDir + os.path.sep + tileName + os.path.sep + "filter_%s#%s.fits" % (label, tileName)
+        else:
+            self.filterFileName = None
+        self.ops = device.getOps(self.params.get('precision') if hasattr(self.params, 'get') else None)
+
+        self.unfilteredMapsDictList = []
+        for mapDict in unfilteredMapsDictList:
+            if 'mapToUse' in self.params.keys() and mapDict['label'] != self.params['mapToUse']:
+                continue
+            newMapDict = mapDict.copy()
+            if hasattr(newMapDict, 'preprocess'):
+                newMapDict.preprocess(tileName=tileName, diagnosticsDir=diagnosticsDir)
+            self.unfilteredMapsDictList.append(newMapDict)
+        self.wcs = self.unfilteredMapsDictList[0]['wcs']
+        self.shape = tuple(self.unfilteredMapsDictList[0]['data'].shape)
+
+        self.flagMask = np.zeros(self.shape, dtype=int)
+        for i, mapDict in enumerate(self.unfilteredMapsDictList):
+            if mapDict.get('flagMask') is not None:
+                self.flagMask = self.flagMask + (np.asarray(mapDict['flagMask']) * (i + 1))
+
+        self.beamSolidAnglesDict = {}
+        for mapDict in self.unfilteredMapsDictList:
+            if 'solidAngle_nsr' in mapDict.keys():
+                solidAngle_nsr = mapDict['solidAngle_nsr']
+            elif isinstance(mapDict.get('beamFileName'), str):
+                solidAngle_nsr = 0.0
+                with open(mapDict['beamFileName'], "r") as inFile:
+                    for line in inFile.readlines():
+                        if line.find("solid angle") != -1:
+                            solidAngle_nsr = float(line.split("=")[1].split()[0])
+                            break
+            else:
+                solidAngle_nsr = 0.0
+            self.beamSolidAnglesDict[mapDict['obsFreqGHz']] = solidAngle_nsr
+
+        self.apodPix = 20
+        for mapDict in self.unfilteredMapsDictList:
+            if tuple(mapDict['data'].shape) != self.shape:
+                raise Exception("Maps at different frequencies have different dimensions!")
+        self.makeRadiansMap()
+        self.signalNorm = 1.0
+        self.fRelWeights = {}
+        self._filtFullT = None      # [F, H, W] fp64 on the device
+        self._filtHT = None         # [1, F, H, Wc] folded filter on the device
+        self._filtHost = None
+        self._dev = None
+
+    # -- device staging ---------------------------------------------------------------------------------
+    def _stage(self):
+        """Uploads this tile's maps once: data / weights [1, F, H, W], masks u8 [1, H, W], median weights."""
+        if self._dev is not None:
+            return self._dev
+        ops = self.ops
+        t = ops.torch
+        F = len(self.unfilteredMapsDictList)
+        H, W = self.shape
+        data = np.empty((1, F, H, W), dtype=ops.npdtype)
+        weights = np.empty((1, F, H, W), dtype=ops.npdtype)
+        for i, m in enumerate(self.unfilteredMapsDictList):
+            data[0, i] = np.asarray(m['data'])
+            weights[0, i] = np.asarray(m['weights']) if m.get('weights') is not None else 1.0
+        m0 = self.unfilteredMapsDictList[0]
+        dev = {'data': ops.to_device(data), 'weights': ops.to_device(weights),
+               'surveyMask': ops.to_device(_maskToU8(m0.get('surveyMask'), self.shape)[None], t.uint8),
+               'psMask': ops.to_device(_maskToU8(m0.get('pointSourceMask'), self.shape)[None], t.uint8)}
+        dev['wmed'] = ops.median_weights(dev['weights'])
+        self._dev = dev
+        return dev
+
+    @property
+    def filt(self):
+        """The filter in the reference's layout: float64 [F, H, W] on the full Fourier plane."""
+        if self._filtHost is None and self._filtFullT is not None:
+            self._filtHost = self._filtFullT.cpu().numpy()
+        return self._filtHost
+
+    @filt.setter
+    def filt(self, value):
+        self._filtHost = np.array(value, dtype=np.float64)
+        self._filtFullT = self.ops.to_device(self._filtHost, self.ops.torch.float64)
+        self._filtHT = self.ops.fold_filter(self._filtFullT).unsqueeze(0)
+
+    def makeRadiansMap(self):
+        """Map of distance in radians from the centre of the tile (filters.py:214-239)."""
+        shape = self.shape
+        x0 = int(shape[1] / 2)
+        y0 = int(shape[0] / 2)
+        ra0, dec0 = self.wcs.pix2wcs(x0, y0)
+        ra1, dec1 = self.wcs.pix2wcs(x0 + 1, y0 + 1)
+        self.degPerPixX = _wcs.calcAngSepDeg(ra0, dec0, ra1, dec0)
+        self.degPerPixY = _wcs.calcAngSepDeg(ra0, dec0, ra0, dec1)
+        xRadRange = np.array([np.arange(int(np.floor(-shape[1] / 2)), int(shape[1] / 2), dtype=np.float64)
+                              * np.radians(self.degPerPixX)] * shape[0])
+        yRadRange = np.array([np.arange(int(np.floor(-shape[0] / 2)), int(shape[0] / 2), dtype=np.float64)
+                              * np.radians(self.degPerPixY)] * shape[1]).transpose()
+        self.radiansMap = np.sqrt(xRadRange ** 2 + yRadRange ** 2)
+
+    def buildAndApply(self):
+        raise Exception("Called a base filter class without a buildAndApply() function implemented.")
+
+    def makeSignalTemplateMap(self, beam, amplitude=None):
+        raise Exception("Called a base filter class without a makeSignalTemplateMap() function implemented.")
+
+    def makeRealSpaceFilterProfile(self):
+        """1-d real-space profile of the filter and its angular range in arcmin (filters.py:282-304)."""
+        realSpace = fft.ifft2(self.filt).real
+        realSpace = fft.fftshift(realSpace)
+        x0 = int(realSpace.shape[2] / 2)
+        y0 = int(realSpace.shape[1] / 2)
+        normFactor = abs(realSpace[:, y0, x0:]).max()
+        prof = realSpace[:, y0, x0:] / normFactor
+        arcminRange = np.arange(0, prof.shape[1]) * self.degPerPixX * 60.0
+        return prof, arcminRange
+
+    def makeNoiseMap(self, mapData):
+        """Noise map from local 3-sigma-clipped measurements in grid cells (filters.py:345-483), on the GPU."""
+        ops = self.ops
+        dev = self._stage()
+        t = device.asTensor(mapData, ops)
+        if t.dim() == 2:
+            t = t.unsqueeze(0)
+        grid = engine.noiseGrid(self.shape, self.params['noiseParams'], self.wcs.getPixelSizeDeg())
+        rms, table, edges = ops.cell_rms(t.contiguous(), dev['wmed'], 1, *grid)
+        self.noiseTable = (table, edges)
+        return rms[0].cpu().numpy()
+
+    def loadFRelWeights(self):
+        self._loadFilterFile()
+
+    # -- filter cache -------------------------------------------------------------------------------------
+    def _cachePath(self):
+        if self.filterFileName is None:
+            return None
+        if os.path.exists(self.filterFileName):
+            return self.filterFileName
+        alt = self.filterFileName[:-5] + ".npz"
+        if os.path.exists(alt):
+            return alt
+        return None
+
+    def _saveFilterFile(self, arr, header):
+        os.makedirs(os.path.dirname(self.filterFileName), exist_ok=True)
+        try:
+            import astropy.io.fits as pyfits
+            img = pyfits.PrimaryHDU()
+            for k, v in header.items():
+                img.header[k] = v
+            img.data = arr
+            img.writeto(self.filterFileName, overwrite=True)
+        except ImportError:
+            np.savez(self.filterFileName[:-5] + ".npz", data=arr, headerKeys=np.array(list(header.keys())),
+                     headerVals=np.array([float(v) for v in header.values()]))
+
+    def _readFilterFile(self):
+        path = self._cachePath()
+        if path.endswith(".npz"):
+            with np.load(path) as z:
+                return z['data'], {str(k): float(v) for k, v in zip(z['headerKeys'], z['headerVals'])}
+        import astropy.io.fits as pyfits
+        with pyfits.open(path) as img:
+            return img[0].data, dict(img[0].header)
+
+
+# -------------------------------------------------------------------------------------------------------------
+class MatchedFilter(MapFilter):
+    """Multi-frequency matched filter in Fourier space (filters.py:519-859)."""
+
+    def _bckSubSigmas(self):
+        if 'bckSub' in self.params.keys() and 'bckSubScaleArcmin' in self.params.keys() and self.params['bckSub'] == True:
+            return maps.smoothScalesPix(self.wcs, smoothScaleDeg=self.params['bckSubScaleArcmin'] / 60.)
+        return None
+
+    def buildAndApply(self, useCachedFilter=False):
+        ops = self.ops
+        dev = self._stage()
+        F = len(self.unfilteredMapsDictList)
+        H, W = self.shape
+        Wc = W // 2 + 1
+        fMapsToFilter = ops.rfft2(dev['data'].reshape(F, H, W), apodPix=self.apodPix).reshape(1, F, H, Wc)
+
+        if self._cachePath() is None and useCachedFilter == False:
+            method = self.params['noiseParams']['method']
+            if method == 'dataMap':
+                if 'noiseModelCatalog' in self.params.keys() and self.params['noiseModelCatalog'] is not None:
+                    raise Exception("noiseModelCatalog needs maps.makeModelImage, which is outside the nemo_b200 hot path")
+                fMapsForNoise = fMapsToFilter       # same maps, same apodisation (filters.py:528 vs :551)
+            elif method in ['model', 'max(dataMap,CMB)']:
+                raise Exception("noise method '%s' needs pixell (simCMBMap / modlmap) and is not implemented in nemo_b200" % (method))
+            else:
+                raise Exception("'%s' is not a valid filter noise method name - fix the .yml config file" % (method))
+            w = engine.spectralWeights(self.unfilteredMapsDictList, self.params)
+            templUnit = np.array([self.makeSignalTemplateMap(m['beamFileName']) for m in self.unfilteredMapsDictList])
+            amps = engine.normAmplitudes(self.unfilteredMapsDictList, self.params)
+            if amps is not None:
+                templNorm = np.array([self.makeSignalTemplateMap(m['beamFileName'], amplitude=a)
+                                      for m, a in zip(self.unfilteredMapsDictList, amps)])
+                templNormT = ops.to_device(templNorm[None])
+            else:
+                templNormT = None
+            cRADeg, cDecDeg = self.wcs.getCentreWCSCoords()
+            cx, cy = self.wcs.wcs2pix(cRADeg, cDecDeg)
+            res = engine.buildFourierFilters(ops, fMapsForNoise, ops.to_device(templUnit[None]), templNormT, w,
+                                             self.params['outputUnits'], cy, cx, wantFull=True,
+                                             bckSubSigmas=self._bckSubSigmas())
+            self._filtHT = res['filtH']
+            self._filtFullT = res['filtFull'][0]
+            self._filtHost = None
+            self._signalNormT = res['signalNorm']
+            self.signalNorm = float(res['signalNorm'].cpu().numpy()[0])
+            self.fRelWeights = {}
+            if res['fRel'] is not None:
+                planes, total = res['fRel']
+                planes, total = planes.cpu().numpy()[0], float(total.cpu().numpy()[0])
+                for v, mapDict in zip(planes, self.unfilteredMapsDictList):
+                    self.fRelWeights[mapDict['obsFreqGHz']] = v / total
+        else:
+            print("... loading cached filter")
+            self.loadFilter()
+            self.params['saveRMSMap'] = False
+            self.params['saveFilter'] = False
+            self.params['savePlots'] = False
+
+        filteredMap = engine.applyFourierFilters(ops, fMapsToFilter, self._filtHT, 1, self._signalNormT, dev['psMask'],
+                                                 bckSubSigmas=self._bckSubSigmas())
+        del fMapsToFilter
+
+        if self.params['outputUnits'] == 'yc':
+            mapUnits = 'yc'
+            combinedObsFreqGHz = 'yc'
+            beamSolidAngle_nsr = 0.0
+        elif self.params['outputUnits'] == 'uK':
+            combinedObsFreqGHz = float(list(self.beamSolidAnglesDict.keys())[0])
+            mapUnits = 'uK'
+            beamSolidAngle_nsr = self.beamSolidAnglesDict[combinedObsFreqGHz]
+        else:
+            raise Exception('need to specify "outputUnits" ("yc" or "uK") in filter params')
+
+        pixDeg = self.wcs.getPixelSizeDeg()
+        grid = engine.noiseGrid(self.shape, self.params['noiseParams'], pixDeg)
+        trimPix = engine.trimSizePix(self.params, pixDeg, realSpace=False)
+        data, sn, maskOut, rms, table, edges = engine.noiseSNAndMasks(ops, filteredMap, dev['wmed'], dev['psMask'],
+                                                                      dev['surveyMask'], 1, grid, trimPix, self.apodPix, False)
+        self.noiseTable = (table, edges)
+        self.RMSMap = DeviceArray(rms[0])
+
+        if 'saveRMSMap' in self.params and self.params['saveRMSMap'] == True and self.selFnDir is not None:
+            self._saveRMSMap(rms[0])
+        if 'saveFilter' in self.params and self.params['saveFilter'] == True and self.filterFileName is not None:
+            header = {'SIGNORM': self.signalNorm}
+            for count, key in enumerate(self.fRelWeights.keys(), start=1):
+                header['RW%d_GHZ' % (count)] = key
+                header['RW%d' % (count)] = self.fRelWeights[key]
+            self._saveFilterFile(self.filt, header)
+
+        return {'data': DeviceArray(data[0]), 'wcs': self.wcs, 'obsFreqGHz': combinedObsFreqGHz, 'SNMap': DeviceArray(sn[0]),
+                'surveyMask': DeviceArray(maskOut[0]), 'flagMask': self.flagMask, 'mapUnits': mapUnits,
+                'beamSolidAngle_nsr': beamSolidAngle_nsr, 'label': self.label, 'tileName': self.tileName}
+
+    def _saveRMSMap(self, rmsT):
+        outDir = self.selFnDir + os.path.sep + self.tileName
+        os.makedirs(outDir, exist_ok=True)
+        path = outDir + os.path.sep + "RMSMap_%s#%s" % (self.label, self.tileName)
+        try:
+            import astropy.io.fits as pyfits
+            pyfits.CompImageHDU(np.array(rmsT.cpu().numpy(), dtype=np.float32), compression_type='RICE_1').writeto(path + ".fits", overwrite=True)
+        except ImportError:
+            np.save(path + ".npy", rmsT.cpu().numpy())
+
+    def loadFilter(self):
+        """Loads a previously saved filter (filters.py:784-794)."""
+        arr, header = self._readFilterFile()
+        self.filt = arr
+        self.signalNorm = float(header['SIGNORM'])
+        self._signalNormT = self.ops.to_device(np.array([self.signalNorm]), self.ops.torch.float64)
+        self.fRelWeights = {}
+        for i in range(1, 10):
+            if 'RW%d_GHZ' % (i) in header.keys():
+                self.fRelWeights[header['RW%d_GHZ' % (i)]] = header['RW%d' % (i)]
+
+    def _loadFilterFile(self):
+        self.loadFilter()
+
+    def reshapeFilter(self, shape):
+        raise Exception("reshapeFilter needs pixell.enmap.laxes and is not implemented in nemo_b200; "
+                        "apply the filter to maps with the shape it was built for")
+
+    def applyFilter(self, mapDataToFilter):
+        """Applies the filter to a cube [F, H, W]: real maps are apodised and transformed first; complex input is
+        taken as the full-plane FFT of real maps (filters.py:824-859).  Returns a numpy array."""
+        ops = self.ops
+        F = len(self.unfilteredMapsDictList)
+        H, W = self.shape
+        if isinstance(mapDataToFilter, DeviceArray):
+            mapDataToFilter = mapDataToFilter.tensor
+        if tuple(mapDataToFilter.shape) != (F, H, W):
+            self.reshapeFilter(mapDataToFilter.shape)
+        isTensor = hasattr(mapDataToFilter, 'data_ptr')
+        if not isTensor and 'complex' in np.asarray(mapDataToFilter).dtype.name:
+            half = np.ascontiguousarray(np.asarray(mapDataToFilter)[:, :, :W // 2 + 1])
+            fMaps = ops.to_device(half, ops.cdtype).reshape(1, F, H, W // 2 + 1)
+        else:
+            fMaps = ops.rfft2(device.asTensor(mapDataToFilter, ops).reshape(F, H, W).contiguous(),
+                              apodPix=self.apodPix).reshape(1, F, H, W // 2 + 1)
+        normT = ops.to_device(np.array([self.signalNorm], dtype=np.float64), ops.torch.float64)
+        out = engine.applyFourierFilters(ops, fMaps, self._filtHT, 1, normT, None, bckSubSigmas=self._bckSubSigmas())
+        return out[0].cpu().numpy()
+
+
+# -------------------------------------------------------------------------------------------------------------
+class RealSpaceMatchedFilter(MapFilter):
+    """Matched filter built in Fourier space on a noise region, truncated to a small real-space kernel and applied
+    by direct convolution (filters.py:862-1218)."""
+
+    def loadFilter(self):
+        arr, header = self._readFilterFile()
+        self.kern2d = np.array(arr, dtype=np.float64)
+        self.signalNorm = float(header['SIGNORM'])
+        self.bckSubScaleArcmin = header['BCKSCALE'] if 'BCKSCALE' in header.keys() else 0
+        self.applyRACentre = header['APP_RA']
+        self.applyDecCentre = header['APP_DEC']
+        self.fRelWeights = {}
+        for i in range(1, 10):
+            if 'RW%d_GHZ' % (i) in header.keys():
+                self.fRelWeights[header['RW%d_GHZ' % (i)]] = header['RW%d' % (i)]
+
+    def _kernelMapsDictList(self, RADecSection):
+        """The noise region the kernel is built from.  The reference re-reads it from disk with
+        mapDict['RADecSection'] (filters.py:920-929); in-memory tiles are cut with the WCS instead."""
+        out = []
+        for mapDict in self.unfilteredMapsDictList:
+            if RADecSection is None:
+                out.append(mapDict.copy())
+                continue
+            RAMin, RAMax, decMin, decMax = RADecSection
+            wcs = mapDict['wcs']
+            xa, ya = wcs.wcs2pix(RAMax, decMin)
+            xb, yb = wcs.wcs2pix(RAMin, decMax)
+            x0, x1 = int(round(min(xa, xb))), int(round(max(xa, xb)))
+            y0, y1 = int(round(min(ya, yb))), int(round(max(ya, yb)))
+            H, W = self.shape
+            x0, x1, y0, y1 = max(x0, 0), min(x1, W), max(y0, 0), min(y1, H)
+            if not hasattr(wcs, 'crpix'):
+                raise Exception("cutting a RADecSection needs a wcs with crpix/pixDeg (nemo_b200.wcs.CARWCS); "
+                                "pass noiseParams['RADecSection'] = None to use the whole tile")
+            newDict = mapDict.copy()
+            for key in ['data', 'weights', 'surveyMask', 'pointSourceMask', 'flagMask']:
+                if newDict.get(key) is not None:
+                    newDict[key] = np.ascontiguousarray(np.asarray(newDict[key])[y0:y1, x0:x1])
+            newDict['wcs'] = _wcs.CARWCS((y1 - y0, x1 - x0), wcs.pixDeg, wcs.crval, (wcs.crpix[0] - x0, wcs.crpix[1] - y0))
+            out.append(newDict)
+        return out
+
+    def buildKernel(self, RADecSection, RADeg='centre', decDeg='centre'):
+        """Builds the real-space kernel (filters.py:892-1041)."""
+        if self._cachePath() is not None:
+            return self.loadFilter()
+        kernelUnfilteredMapsDictList = self._kernelMapsDictList(RADecSection)
+        kernelLabel = "realSpaceKernel_%s" % (self.label)
+        matchedFilterClass = self.params['noiseParams']['matchedFilterClass']
+        if isinstance(matchedFilterClass, str):
+            matchedFilterClass = globals()[matchedFilterClass]
+        matchedFilter = matchedFilterClass(kernelLabel, kernelUnfilteredMapsDictList, self.params, tileName=self.tileName,
+                                           diagnosticsDir=None, selFnDir=None)
+        matchedFilter.buildAndApply()
+        self.matchedFilter = matchedFilter
+
+        kernelMaxArcmin = self.params['noiseParams']['kernelMaxArcmin']
+        prof, arcminRange = matchedFilter.makeRealSpaceFilterProfile()
+        rIndex = np.where(arcminRange > kernelMaxArcmin)[0][0]
+        mask = np.less(arcminRange, kernelMaxArcmin)
+        if 'symmetrize' in self.params['noiseParams'].keys() and self.params['noiseParams']['symmetrize'] == True:
+            rRadians = np.radians(arcminRange / 60.)
+            profile2d = []
+            for i in range(prof.shape[0]):
+                r2p = interpolate.interp1d(rRadians[mask], prof[i, mask], bounds_error=False, fill_value=0.0)
+                profile2d.append(r2p(matchedFilter.radiansMap))
+            profile2d = np.array(profile2d)
+        else:
+            profile2d = fft.ifft2(matchedFilter.filt).real
+            profile2d = fft.fftshift(profile2d)
+        z, y, x = np.where(abs(profile2d) == abs(profile2d).max())
+        y = y[0]
+        x = x[0]
+        yMin, yMax, xMin, xMax = y - rIndex, y + rIndex, x - rIndex, x + rIndex
+        if (yMax - yMin) % 2 == 0:
+            yMin = yMin + 1
+        if (xMax - xMin) % 2 == 0:
+            xMin = xMin + 1
+        self.kern2d = np.ascontiguousarray(profile2d[:, yMin:yMax, xMin:xMax])
+        if 'bckSubScaleArcmin' in self.params.keys():
+            self.bckSubScaleArcmin = self.params['bckSubScaleArcmin']
+        else:
+            func = np.min if np.greater(prof[0, 0], 0) == True else np.max
+            self.bckSubScaleArcmin = arcminRange[prof[0] == func(prof[0])][0]
+
+        signalMaps = []
+        for mapDict in self.unfilteredMapsDictList:
+            if self.params['outputUnits'] == 'yc':
+                y0 = 2e-4
+                if mapDict['obsFreqGHz'] is not None:
+                    signalMap = self.makeSignalTemplateMap(mapDict['beamFileName'],
+                                                           amplitude=maps.convertToDeltaT(y0, mapDict['obsFreqGHz']))
+                else:
+                    signalMap = self.makeSignalTemplateMap(mapDict['beamFileName'], amplitude=y0)
+            elif self.params['outputUnits'] == 'uK':
+                signalMap = self.makeSignalTemplateMap(mapDict['beamFileName'])
+            else:
+                raise Exception('need to specify "outputUnits" ("yc" or "uK") in filter params')
+            signalMaps.append(signalMap)
+        signalMaps = np.array(signalMaps)
+        filteredSignal = self.applyFilter(signalMaps, calcFRelWeights=True)
+        if self.params['outputUnits'] == 'yc':
+            self.signalNorm = y0 / filteredSignal.max()
+        else:
+            self.signalNorm = 1.0 / filteredSignal.max()
+
+        if self.filterFileName is not None:
+            header = {'SIGNORM': self.signalNorm, 'APP_RA': self.applyRACentre, 'APP_DEC': self.applyDecCentre}
+            if self.params['bckSub'] == True:
+                header['BCKSCALE'] = self.bckSubScaleArcmin
+            for count, key in enumerate(self.fRelWeights.keys(), start=1):
+                header['RW%d_GHZ' % (count)] = key
+                header['RW%d' % (count)] = self.fRelWeights[key]
+            self._saveFilterFile(self.kern2d, header)
+
+    def buildAndApply(self, useCachedFilter=False):
+        ops = self.ops
+        dev = self._stage()
+        if self._cachePath() is None:
+            RAMin, RAMax, decMin, decMax = self.wcs.getImageMinMaxWCSCoords()
+            section = self.params['noiseParams'].get('RADecSection')
+            if section == 'tileNoiseRegions':
+                RADecSection = [self.wcs.header['NRAMIN'], self.wcs.header['NRAMAX'],
+                                self.wcs.header['NDEMIN'], self.wcs.header['NDEMAX']]
+            elif section == 'auto':
+                cRA, cDec = self.wcs.getCentreWCSCoords()
+                halfSizeDeg = 2.0
+                RADecSection = [cRA - halfSizeDeg / np.cos(np.radians(cDec)), cRA + halfSizeDeg / np.cos(np.radians(cDec)),
+                                cDec - halfSizeDeg, cDec + halfSizeDeg]
+            else:
+                RADecSection = section
+            self.applyDecCentre = (decMax + decMin) / 2.
+            self.applyRACentre = (RAMax + RAMin) / 2.
+            self.buildKernel(RADecSection, RADeg=self.applyRACentre, decDeg=self.applyDecCentre)
+        else:
+            self.loadFilter()
+
+        # Apply the kernel to the *raw* tile (filters.py:1106-1110)
+        raw = []
+        for mapDict in self.unfilteredMapsDictList:
+            if hasattr(mapDict, 'loadTile'):
+                raw.append(mapDict.loadTile('mapFileName', tileName=self.tileName))
+            else:
+                raw.append(mapDict['rawData'] if mapDict.get('rawData') is not None else mapDict['data'])
+        rawT = ops.to_device(np.array(raw)[None])
+        normT = ops.to_device(np.array([self.signalNorm], dtype=np.float64), ops.torch.float64)
+        filteredMap = self._applyOnDevice(rawT, normT, dev['psMask'])
+
+        if self.params['outputUnits'] == 'yc':
+            mapUnits = 'yc'
+            combinedObsFreqGHz = 'yc'
+            beamSolidAngle_nsr = 0.0
+        elif self.params['outputUnits'] == 'uK':
+            if len(self.unfilteredMapsDictList) > 1:
+                raise Exception("multi-frequency filtering not currently supported for outputUnits 'uK' (point source finding)")
+            combinedObsFreqGHz = float(list(self.beamSolidAnglesDict.keys())[0])
+            mapUnits = 'uK'
+            beamSolidAngle_nsr = self.beamSolidAnglesDict[combinedObsFreqGHz]
+        else:
+            raise Exception('need to specify "outputUnits" ("yc" or "uK") in filter params')
+
+        pixDeg = self.wcs.getPixelSizeDeg()
+        grid = engine.noiseGrid(self.shape, self.params['noiseParams'], pixDeg)
+        trimPix = engine.trimSizePix(self.params, pixDeg, realSpace=True)
+        data, sn, maskOut, rms, table, edges = engine.noiseSNAndMasks(ops, filteredMap, dev['wmed'], dev['psMask'],
+                                                                      dev['surveyMask'], 1, grid, trimPix, self.apodPix, True)
+        self.noiseTable = (table, edges)
+        self.RMSMap = DeviceArray(rms[0])
+        return {'data': DeviceArray(data[0]), 'wcs': self.wcs, 'obsFreqGHz': combinedObsFreqGHz, 'SNMap': DeviceArray(sn[0]),
+                'surveyMask': DeviceArray(maskOut[0]), 'flagMask': self.flagMask, 'mapUnits': mapUnits,
+                'beamSolidAngle_nsr': beamSolidAngle_nsr, 'label': self.label, 'tileName': self.tileName}
+
+    def _applyOnDevice(self, cubeT, normT, psMask, wantPlanes=False):
+        """cubeT [B, F, H, W] -> [B, H, W]: optional Gaussian high-pass per frequency, kernel convolution, sum over
+        frequency, normalisation, point-source mask (filters.py:1188-1216, 1113)."""
+        ops = self.ops
+        if self.params['bckSub'] == True and self.bckSubScaleArcmin > 0:
+            sy, sx = maps.smoothScalesPix(self.wcs, RADeg=self.applyRACentre, decDeg=self.applyDecCentre,
+                                          smoothScaleDeg=self.bckSubScaleArcmin / 60.)
+            cubeT = ops.gauss_filter(cubeT.contiguous(), sy, sx, subtract=True)
+        kernT = ops.to_device(self.kern2d, ops.torch.float64)
+        return ops.conv2d(cubeT.contiguous(), kernT, norm=normT, mask=psMask, wantPlanes=wantPlanes)
+
+    def applyFilter(self, mapDataToFilter, calcFRelWeights=False):
+        """Applies the kernel to a cube [F, H, W] (filters.py:1172-1218).  Returns a numpy array."""
+        ops = self.ops
+        cubeT = device.asTensor(mapDataToFilter, ops)
+        if cubeT.dim() == 3:
+            cubeT = cubeT.unsqueeze(0)
+        normT = ops.to_device(np.array([self.signalNorm], dtype=np.float64), ops.torch.float64)
+        if calcFRelWeights == True:
+            out, planes = self._applyOnDevice(cubeT, normT, None, wantPlanes=True)
+            planes = planes[0].cpu().numpy()
+            self.fRelWeights = {}
+            maxIndex = np.argmax(planes.sum(axis=0))
+            totalSignal = planes.sum(axis=0).flatten()[maxIndex]
+            for plane, mapDict in zip(planes, self.unfilteredMapsDictList):
+                self.fRelWeights[mapDict['obsFreqGHz']] = plane.flatten()[maxIndex] / totalSignal
+        else:
+            out = self._applyOnDevice(cubeT, normT, None)
+        return out[0].cpu().numpy()
+
+
+# -------------------------------------------------------------------------------------------------------------
+class BeamFilter(MapFilter):
+    """Templates from ACT-style beam profiles (filters.py:1222-1233)."""
+
+    def makeSignalTemplateMap(self, beamFileName, amplitude=None):
+        return signals.makeBeamModelSignalMap(np.degrees(self.radiansMap), self.wcs, beamFileName, amplitude=amplitude)
+
+
+class ArnaudModelFilter(MapFilter):
+    """Templates from the Arnaud et al. (2010) GNFW profile (filters.py:1236-1252)."""
+
+    def makeSignalTemplateMap(self, beamFileName, amplitude=None):
+        return signals.makeArnaudModelSignalMap(self.params['z'], self.params['M500MSun'], np.degrees(self.radiansMap),
+                                                self.wcs, beam=beamFileName,
+                                                GNFWParams=self.params.get('GNFWParams', 'default'),
+                                                amplitude=amplitude, convolveWithBeam=True)
+
+
+class BattagliaModelFilter(MapFilter):
+    """Battaglia et al. (2012) templates need pyccl for the redshift evolution (filters.py:1255-1277)."""
+
+    def makeSignalTemplateMap(self, beamFileName, amplitude=None):
+        raise Exception("BattagliaModelFilter templates need pyccl, which nemo_b200 does not depend on; "
+                        "use ArnaudModelFilter or pass template maps directly to nemo_b200.pipelines")
+
+
+class ArnaudModelMatchedFilter(MatchedFilter, ArnaudModelFilter):
+    pass
+
+
+class BattagliaModelMatchedFilter(MatchedFilter, BattagliaModelFilter):
+    pass
+
+
+class BeamMatchedFilter(MatchedFilter, BeamFilter):
+    pass
+
+
+class ArnaudModelRealSpaceMatchedFilter(RealSpaceMatchedFilter, ArnaudModelFilter):
+    pass
+
+
+class BattagliaModelRealSpaceMatchedFilter(RealSpaceMatchedFilter, BattagliaModelFilter):
+    pass
+
+
+class BeamRealSpaceMatchedFilter(RealSpaceMatchedFilter, BeamFilter):
+    pass

@@ -1,0 +1,326 @@
+"""
+Batched tile x filter-scale driver: the body of the reference's ``pipelines._filterMapsAndMakeCatalogs``
+(nemo/pipelines.py:112-354) with its ``for tileName: for f in filtersList:`` loops turned into batched GPU
+launches, followed by the same cross-scale merge (``catalogs.makeOptimalCatalog``).  Tiles are sharded over
+ranks (one process per GPU); the only collectives are the catalog all-gather (pipelines.py:322) and the
+noise-table gather (pipelines.py:405) -- see ``nemo_b200.distributed``.
+
+Work items are independent (tile, scale) pairs; image index o = tile * S + scale.  All S scales of a tile stay on
+the same GPU so that the input FFTs and the smoothed noise covariance are shared between them and the
+``photFilter`` maps (pipelines.py:238-241) are local.
+"""
+
+import numpy as np
+
+from . import catalogs
+from . import device
+from . import engine
+from . import maps
+from . import photometry
+from . import signals
+from . import wcs as _wcs
+from . import filters as _filters
+
+FLUX_KEYS = {'yc': ['deltaT_c', 'err_deltaT_c', 'y_c', 'err_y_c'], 'uK': ['deltaT_c', 'err_deltaT_c', 'fluxJy', 'err_fluxJy']}
+
+
+class SimpleConfig(object):
+    """The slice of the reference's ``startUp.NemoConfig`` the hot path reads: ``parDict`` (thresholdSigma, minObjPix,
+    findCenterOfMass, removeRings, ringThresholdSigma, rejectBorder, objIdent, longNames, useInterpolator,
+    measureShapes, photFilter, mapFilters, catalogCuts), ``tileNames`` and the per-tile map dictionaries."""
+
+    DEFAULTS = {'removeRings': True, 'ringThresholdSigma': 3, 'rejectBorder': 0, 'measureShapes': False, 'objIdent': 'ACT-CL',
+                'longNames': False, 'useInterpolator': True, 'findCenterOfMass': True, 'photFilter': None, 'catalogCuts': [],
+                'undoPixelWindow': True}
+
+    def __init__(self, parDict, tileMaps, rank=0, size=1):
+        self.parDict = dict(self.DEFAULTS)
+        self.parDict.update(parDict)
+        self.tileMaps = tileMaps                  # {tileName: [mapDict per frequency]}
+        self.allTileNames = list(tileMaps.keys())
+        self.rank, self.size = rank, size
+        # tiles round-robin over ranks (the reference leaves rank 0 idle, startUp.py:390-404; here every rank works)
+        self.tileNames = self.allTileNames[rank::size] if size > 1 else list(self.allTileNames)
+
+
+# ------------------------------------------------------------------------------------------------------
+class TileBatch(object):
+    """Maps of nT tiles resident on the device: data / weights [nT, F, H, W], masks u8 [nT, H, W], median weights."""
+
+    def __init__(self, ops, tileNames, tileMaps, pinned=True):
+        torch = ops.torch
+        self.ops = ops
+        self.tileNames = list(tileNames)
+        self.mapDicts = [tileMaps[t] for t in self.tileNames]
+        nT = len(self.tileNames)
+        F = len(self.mapDicts[0])
+        H, W = self.mapDicts[0][0]['data'].shape
+        self.nT, self.F, self.H, self.W = nT, F, H, W
+        data = torch.empty((nT, F, H, W), dtype=ops.dtype, pin_memory=pinned)
+        weights = torch.empty((nT, F, H, W), dtype=ops.dtype, pin_memory=pinned)
+        survey = torch.empty((nT, H, W), dtype=torch.uint8, pin_memory=pinned)
+        ps = torch.empty((nT, H, W), dtype=torch.uint8, pin_memory=pinned)
+        for t, md in enumerate(self.mapDicts):
+            if len(md) != F:
+                raise Exception("all tiles of a batch need the same number of frequency maps")
+            for f, m in enumerate(md):
+                if tuple(m['data'].shape) != (H, W):
+                    raise Exception("all tiles of a batch need the same shape")
+                data[t, f] = torch.from_numpy(np.ascontiguousarray(m['data']))
+                weights[t, f] = torch.from_numpy(np.ascontiguousarray(m['weights']))
+            survey[t] = torch.from_numpy(_filters._maskToU8(md[0].get('surveyMask'), (H, W)))
+            ps[t] = torch.from_numpy(_filters._maskToU8(md[0].get('pointSourceMask'), (H, W)))
+        self.host = {'data': data, 'weights': weights, 'surveyMask': survey, 'psMask': ps}
+        self.h2dBytes = sum(int(v.numel()) * v.element_size() for v in self.host.values())
+        self.dev = None
+        self.wcsList = [md[0]['wcs'] for md in self.mapDicts]
+        self.flagMasks = []
+        for md in self.mapDicts:
+            fm = np.zeros((H, W), dtype=int)
+            for i, m in enumerate(md):
+                if m.get('flagMask') is not None:
+                    fm = fm + np.asarray(m['flagMask']) * (i + 1)
+            self.flagMasks.append(fm)
+
+    def upload(self):
+        """Host (pinned) -> device copies of this batch's inputs; asynchronous on the current stream."""
+        ops = self.ops
+        self.dev = {k: v.to(ops.device, non_blocking=True) for k, v in self.host.items()}
+        self.dev['wmed'] = ops.median_weights(self.dev['weights'])
+        return self.dev
+
+
+# ------------------------------------------------------------------------------------------------------
+class FilterSetTemplates(object):
+    """Host-made signal templates of a list of Fourier filters for one tile geometry, uploaded once and reused for
+    every tile with the same shape and pixel scale (template maps are inputs to the hot path)."""
+
+    def __init__(self, ops, filtersList, mapDicts, tileName='PRIMARY'):
+        self.filtersList = filtersList
+        self.S = len(filtersList)
+        unit, norm = [], []
+        self.w = None
+        self.outputUnits = None
+        for f in filtersList:
+            cls = f['class'] if not isinstance(f['class'], str) else getattr(_filters, f['class'])
+            if not issubclass(cls, _filters.MatchedFilter):
+                raise Exception("FilterSetTemplates handles Fourier-space matched filters only")
+            obj = cls.__new__(cls)
+            obj.params = f['params']
+            obj.unfilteredMapsDictList = mapDicts
+            obj.wcs = mapDicts[0]['wcs']
+            obj.shape = tuple(mapDicts[0]['data'].shape)
+            obj.makeRadiansMap()
+            w = engine.spectralWeights(mapDicts, f['params'])
+            if self.w is not None and (not np.array_equal(w, self.w) or f['params']['outputUnits'] != self.outputUnits):
+                raise Exception("filters of one batch need the same outputUnits and spectral weights")
+            self.w, self.outputUnits = w, f['params']['outputUnits']
+            unit.append([obj.makeSignalTemplateMap(m['beamFileName']) for m in mapDicts])
+            amps = engine.normAmplitudes(mapDicts, f['params'])
+            if amps is not None:
+                norm.append([obj.makeSignalTemplateMap(m['beamFileName'], amplitude=a) for m, a in zip(mapDicts, amps)])
+        self.geometry = (obj.shape, obj.degPerPixX, obj.degPerPixY)
+        self.unit = ops.to_device(np.array(unit))
+        self.norm = ops.to_device(np.array(norm)) if len(norm) > 0 else None
+        wcs = mapDicts[0]['wcs']
+        cRADeg, cDecDeg = wcs.getCentreWCSCoords()
+        self.cx, self.cy = wcs.wcs2pix(cRADeg, cDecDeg)
+
+
+def _sameNoiseSetup(filtersList):
+    def key(f):
+        p = f['params']
+        return (repr(sorted(p['noiseParams'].items())), p.get('edgeTrimArcmin'), p.get('bckSub'), p.get('bckSubScaleArcmin'))
+    return len(set(key(f) for f in filtersList)) == 1
+
+
+def filterTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=True, measureFluxes=True,
+                    invertMap=False, keepMaps=False):
+    """Filters every tile of `batch` at every scale of `filtersList` (Fourier matched filters with a common noise
+    set-up), detects objects and measures fluxes.  Returns (catalogDict, extras) where catalogDict maps
+    '<label>#<tileName>' -> {'catalog': Table or []} like the reference's, and extras holds the noise tables (and
+    the device maps when keepMaps)."""
+    if not _sameNoiseSetup(filtersList):
+        raise Exception("filters of one batch need identical noiseParams / edgeTrimArcmin / bckSub settings")
+    dev = batch.dev if batch.dev is not None else batch.upload()
+    nT, F, H, W, S = batch.nT, batch.F, batch.H, batch.W, len(filtersList)
+    Wc = W // 2 + 1
+    params0 = filtersList[0]['params']
+    wcs0 = batch.wcsList[0]
+    pixDeg = wcs0.getPixelSizeDeg()
+    bck = None
+    if 'bckSub' in params0.keys() and 'bckSubScaleArcmin' in params0.keys() and params0['bckSub'] == True:
+        bck = maps.smoothScalesPix(wcs0, smoothScaleDeg=params0['bckSubScaleArcmin'] / 60.)
+    method = params0['noiseParams']['method']
+    if method != 'dataMap' or params0.get('noiseModelCatalog') is not None:
+        raise Exception("nemo_b200 implements the 'dataMap' noise method without noiseModelCatalog")
+
+    # K1: apodised input FFTs, shared by the S scales of a tile (filters.py:526-529) and by the noise estimate (:551)
+    fmaps = ops.rfft2(dev['data'].reshape(nT * F, H, W), apodPix=20).reshape(nT, F, H, Wc)
+    # K2, K3, K5: filters and their normalisation
+    res = engine.buildFourierFilters(ops, fmaps, templates.unit, templates.norm, templates.w, templates.outputUnits,
+                                     templates.cy, templates.cx, bckSubSigmas=bck)
+    # K4: apply, times the point-source mask
+    filtered = engine.applyFourierFilters(ops, fmaps, res['filtH'], S, res['signalNorm'], dev['psMask'], bckSubSigmas=bck)
+    del fmaps
+    # K6, K7
+    grid = engine.noiseGrid((H, W), params0['noiseParams'], pixDeg)
+    trimPix = engine.trimSizePix(params0, pixDeg, realSpace=False)
+    data, sn, maskOut, rms, table, edges = engine.noiseSNAndMasks(ops, filtered, dev['wmed'], dev['psMask'], dev['surveyMask'],
+                                                                  S, grid, trimPix, 20, False)
+    # K8
+    if undoPixelWindow:
+        engine.undoPixelWindow(ops, data)
+
+    catalogDict = detectAndMeasure(ops, batch, filtersList, data, sn, templates.outputUnits, parDict,
+                                   measureFluxes=measureFluxes, invertMap=invertMap)
+    extras = {'noiseTable': table, 'noiseEdges': edges, 'signalNorm': res['signalNorm'], 'fRel': res['fRel']}
+    if keepMaps:
+        extras.update({'data': data, 'SNMap': sn, 'surveyMask': maskOut, 'RMSMap': rms, 'filtH': res['filtH']})
+    return catalogDict, extras
+
+
+def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measureFluxes=True, invertMap=False):
+    """K9-K11 for all (tile, scale) images, then the rows of every catalog (pipelines.py:251-284)."""
+    nT, S = batch.nT, len(filtersList)
+    H, W = batch.H, batch.W
+    wcsList = [batch.wcsList[o // S] for o in range(nT * S)]
+    flagList = [batch.flagMasks[o // S] for o in range(nT * S)]
+    labelList = [filtersList[o % S]['label'] for o in range(nT * S)]
+    tileList = [batch.tileNames[o // S] for o in range(nT * S)]
+    rows = photometry.findObjectsBatch(ops, sn, wcsList, flagList, labelList, tileList,
+                                       threshold=parDict['thresholdSigma'], minObjPix=parDict['minObjPix'],
+                                       rejectBorder=parDict['rejectBorder'], findCenterOfMass=parDict['findCenterOfMass'],
+                                       removeRings=parDict['removeRings'], ringThresholdSigma=parDict['ringThresholdSigma'],
+                                       invertMap=invertMap, objIdent=parDict['objIdent'], longNames=parDict['longNames'],
+                                       useInterpolator=parDict['useInterpolator'], measureShapes=parDict['measureShapes'])
+    photFilter = parDict.get('photFilter')
+    photScale = None
+    if photFilter is not None:
+        for s, f in enumerate(filtersList):
+            if f['label'] == photFilter:
+                photScale = s
+    useInterp = parDict['useInterpolator']
+    # all objects of the batch in one go: positions from (RADeg, decDeg) as the reference does (photometry.py:328)
+    flat = [(o, r) for o in range(nT * S) for r in rows[o]]
+    if len(flat) > 0 and (measureFluxes or photScale is not None):
+        xs = np.empty(len(flat))
+        ys = np.empty(len(flat))
+        for k, (o, r) in enumerate(flat):
+            xs[k], ys[k] = wcsList[o].wcs2pix(r['RADeg'], r['decDeg'])
+        yx = ops.to_device(np.stack([ys, xs], axis=1), ops.torch.float64)
+        own = ops.to_device(np.array([o for o, _ in flat], dtype=np.int32), ops.torch.int32)
+
+        def sample(imgs, idxT, sign=1.0):
+            if useInterp:
+                return ops.spline_eval(imgs, idxT, yx, sign=sign).cpu().numpy()
+            torch = ops.torch
+            yi = torch.as_tensor(np.round(ys).astype(np.int64), device=imgs.device)
+            xi = torch.as_tensor(np.round(xs).astype(np.int64), device=imgs.device)
+            return sign * imgs[idxT.long(), yi, xi].cpu().numpy().astype(np.float64)
+
+        vals = {}
+        if photScale is not None:
+            phot = ops.to_device(np.array([(o // S) * S + photScale for o, _ in flat], dtype=np.int32), ops.torch.int32)
+            inside = np.array([int(x) > 0 and int(x) < W and int(y) > 0 and int(y) < H for x, y in zip(xs, ys)])
+            fixedSNR = sample(sn, phot, sign=-1.0 if (invertMap and not measureFluxes) else 1.0)
+            vals['fixed_SNR'] = np.where(inside, fixedSNR, 0.0)
+        if measureFluxes:
+            vals[''] = sample(data, own)
+            if photScale is not None:
+                vals['fixed_'] = sample(data, phot)
+        for k, (o, r) in enumerate(flat):
+            if 'fixed_SNR' in vals:
+                r['fixed_SNR'] = float(vals['fixed_SNR'][k])
+            if not measureFluxes:
+                continue
+            for prefix in ['', 'fixed_'] if photScale is not None else ['']:
+                v = float(vals[prefix][k])
+                snr = r[prefix + 'SNR']
+                with np.errstate(divide='ignore', invalid='ignore'):
+                    if mapUnits == 'yc':
+                        r[prefix + 'y_c'] = v / 1e-4
+                        r[prefix + 'err_y_c'] = np.float64(r[prefix + 'y_c']) / snr
+                        deltaTc = maps.convertToDeltaT(v, obsFrequencyGHz=148.0)
+                        r[prefix + 'deltaT_c'] = deltaTc
+                        r[prefix + 'err_deltaT_c'] = abs(np.float64(deltaTc) / snr)
+                    else:
+                        r[prefix + 'deltaT_c'] = v
+                        r[prefix + 'err_deltaT_c'] = np.float64(v) / snr
+                        md0 = batch.mapDicts[o // S][0]
+                        nsr = md0.get('solidAngle_nsr', 0.0)
+                        if nsr > 0:
+                            r[prefix + 'fluxJy'] = photometry.deltaTToJyPerSr(r[prefix + 'deltaT_c'], md0['obsFreqGHz']) * nsr * 1.e-9
+                            r[prefix + 'err_fluxJy'] = photometry.deltaTToJyPerSr(r[prefix + 'err_deltaT_c'], md0['obsFreqGHz']) * nsr * 1.e-9
+                        else:
+                            r[prefix + 'fluxJy'] = 0.0
+                            r[prefix + 'err_fluxJy'] = 0.0
+    keys = list(catalogs.COLUMN_NAMES)
+    prefixes = ['', 'fixed_'] if photScale is not None else ['']
+    if photScale is not None:
+        keys.append('fixed_SNR')
+    if measureFluxes:
+        for prefix in prefixes:
+            keys += [prefix + k for k in FLUX_KEYS[mapUnits]]
+    catalogDict = {}
+    for o in range(nT * S):
+        label = labelList[o] + "#" + tileList[o]
+        catalogDict[label] = {'catalog': catalogs.catalogListToTab(rows[o], keysToWrite=keys) if len(rows[o]) > 0 else []}
+    return catalogDict
+
+
+# ------------------------------------------------------------------------------------------------------
+def _orderedFilters(parDict):
+    """photFilter first, then the others in config order (pipelines.py:153-167)."""
+    photFilter = parDict.get('photFilter')
+    filtersList = []
+    if photFilter is not None:
+        for f in parDict['mapFilters']:
+            if f['label'] == photFilter:
+                filtersList.append(f)
+    for f in parDict['mapFilters']:
+        if photFilter is not None and f['label'] == photFilter:
+            continue
+        filtersList.append(f)
+    return filtersList
+
+
+def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=False, measureFluxes=True, invertMap=False,
+                              verbose=True, tilesPerBatch=8, precision=None, comm=None):
+    """Runs the map filtering and catalog construction steps for this rank's tiles and returns the optimal catalog
+    (highest S/N detection across filter scales), gathered over ranks when `comm` (a
+    ``nemo_b200.distributed.Comm``) is given -- pipelines.py:33-109, 112-354.
+
+    Only Fourier-space matched filters with a common noise set-up are batched here; use ``filters.filterMaps`` +
+    ``photometry.findObjects`` directly for anything else.
+    """
+    if useCachedFilters or useCachedRMSMap:
+        raise Exception("cached filters / RMS maps: use nemo_b200.injection.InjectionRunner")
+    ops = device.getOps(precision)
+    parDict = config.parDict
+    filtersList = _orderedFilters(parDict)
+    catalogDict = {}
+    noiseTables = {}
+    templates = None
+    tileNames = list(config.tileNames)
+    for i in range(0, len(tileNames), tilesPerBatch):
+        names = tileNames[i:i + tilesPerBatch]
+        if verbose:
+            print(">>> [rank = %d] Making filtered maps - tiles %s" % (config.rank, names))
+        batch = TileBatch(ops, names, config.tileMaps)
+        if templates is None:
+            templates = FilterSetTemplates(ops, filtersList, batch.mapDicts[0], tileName=names[0])
+        cd, extras = filterTileBatch(ops, batch, filtersList, templates, parDict,
+                                     undoPixelWindow=parDict.get('undoPixelWindow', True), measureFluxes=measureFluxes,
+                                     invertMap=invertMap)
+        catalogDict.update(cd)
+        tab = extras['noiseTable'].cpu().numpy()
+        for o in range(tab.shape[0]):
+            noiseTables[filtersList[o % len(filtersList)]['label'] + "#" + names[o // len(filtersList)]] = tab[o]
+    optimalCatalog = catalogs.makeOptimalCatalog(catalogDict, constraintsList=parDict.get('catalogCuts', []))
+    if comm is not None and comm.size > 1:
+        from . import distributed
+        optimalCatalog = distributed.allGatherCatalog(comm, optimalCatalog, filtersList, config.allTileNames)
+    config.catalogDict = catalogDict
+    config.noiseTables = noiseTables
+    return optimalCatalog

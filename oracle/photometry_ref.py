@@ -22,7 +22,7 @@ def makeName(RADeg, decDeg, prefix='ACT-CL'):
     h = int(ra)
     m = (ra - h) * 60.0
     raStr = "%02d%04.1f" % (h, np.floor(m * 10) / 10.0)
-    sign = '+' if decDeg >= 0 else '-'
+    sign = '+' if decDeg > 0 else '-'
     d = abs(decDeg)
     dd = int(d)
     dm = int((d - dd) * 60.0)

@@ -1,0 +1,217 @@
+"""
+End-to-end parity of the drop-in boundary (nemo_b200.filters / photometry / pipelines) against the oracle on
+identical seeded inputs.  Tolerances are those of BASELINE.json's north_star: detection catalog identical above the
+S/N cut with positions within 0.01 px, S/N maps within 1e-4 (relative, with an absolute floor of 1e-4 because S/N
+crosses zero), segmentation labels bit-exact.  fp64 typically agrees to ~1e-10.
+"""
+
+import os
+import numpy as np
+import pytest
+
+from oracle import synth, filters_ref, photometry_ref
+
+pytestmark = pytest.mark.gpu
+
+DETECT = dict(threshold=4.0, minObjPix=1, findCenterOfMass=True, removeRings=True, ringThresholdSigma=3,
+              useInterpolator=True, rejectBorder=0)
+
+
+def _arnaud(label='Arnaud_M2e14_z0p4', M=2e14, z=0.4, grid=40., **extra):
+    p = {'M500MSun': M, 'z': z, 'noiseParams': {'method': 'dataMap', 'noiseGridArcmin': grid}, 'outputUnits': 'yc',
+         'edgeTrimArcmin': 0.}
+    p.update(extra)
+    return {'label': label, 'class': 'ArnaudModelMatchedFilter', 'params': p}
+
+
+def _beam(label='Beam', grid=20., numBins=None, **extra):
+    p = {'noiseParams': {'method': 'dataMap', 'noiseGridArcmin': grid}, 'outputUnits': 'uK', 'edgeTrimArcmin': 0.}
+    if numBins is not None:
+        p['noiseParams']['numNoiseBins'] = numBins
+    p.update(extra)
+    return {'label': label, 'class': 'BeamMatchedFilter', 'params': p}
+
+
+def _copyFilter(f):
+    import copy
+    return copy.deepcopy(f)
+
+
+def _compareMaps(got, ref, report, name):
+    sn, snRef = np.asarray(got['SNMap']), ref['SNMap']
+    d, dRef = np.asarray(got['data']), ref['data']
+    assert np.array_equal(np.asarray(got['surveyMask']) != 0, ref['surveyMask'] != 0), "survey masks differ"
+    errSN = float(np.abs(sn - snRef).max())
+    errData = float(np.abs(d - dRef).max() / np.abs(dRef).max())
+    report(name, maxabs_dSN=errSN, rel_dData=errData, zeros_equal=int(np.array_equal(d == 0, dRef == 0)))
+    assert np.allclose(sn, snRef, rtol=1e-4, atol=1e-4), "S/N maps differ: %g" % errSN
+    assert errData < 1e-4
+    assert np.array_equal(d == 0, dRef == 0)
+    assert got['mapUnits'] == ref['mapUnits'] and got['obsFreqGHz'] == ref['obsFreqGHz']
+    assert got['beamSolidAngle_nsr'] == ref['beamSolidAngle_nsr']
+    assert np.array_equal(got['flagMask'], ref['flagMask'])
+
+
+def _compareCatalogs(gotTab, refRows, keys):
+    n = len(gotTab) if not isinstance(gotTab, list) else 0
+    assert n == len(refRows), "catalog sizes differ: %d vs %d" % (n, len(refRows))
+    if n == 0:
+        return
+    gotRows = gotTab.toRows()
+    for a, b in zip(gotRows, refRows):
+        assert abs(a['x'] - b['x']) < 0.01 and abs(a['y'] - b['y']) < 0.01
+        assert a['numSigPix'] == b['numSigPix'] and a['id'] == b['id'] and a['flags'] == b['flags']
+        assert a['template'] == b['template'] and a['tileName'] == b['tileName']
+        # names truncate the coordinates, so an object sitting exactly on an arcminute boundary may differ by one
+        # digit for a 1e-13 px difference: accept the name of either side's coordinates
+        assert a['name'] in (b['name'], photometry_ref.makeName(a['RADeg'], a['decDeg']))
+        for k in keys:
+            assert abs(a[k] - b[k]) <= 1e-4 * abs(b[k]) + 1e-12, "%s: %g vs %g" % (k, a[k], b[k])
+
+
+@pytest.mark.parametrize("shape,seed", [((256, 256), 3), ((512, 512), 1)])
+def test_arnaud_matched_filter_single_frequency(report, shape, seed):
+    """BASELINE config 1 (reduced tile): 148 GHz white noise + clusters, Arnaud theta500 ~ 2.4', S/N > 4."""
+    from nemo_b200 import filters, photometry
+    mapDicts, truth = synth.makeTile(shape=shape, numObjects=10, kind='clusters', seed=seed)
+    f = _arnaud()
+    ref, refObj = filters_ref.filterMaps(mapDicts, _copyFilter(f), 'PRIMARY', returnFilter=True)
+    got, gotObj = filters.filterMaps(mapDicts, _copyFilter(f), 'PRIMARY', verbose=False, returnFilter=True)
+    _compareMaps(got, ref, report, "arnaud_F1_%dx%d" % shape)
+    assert abs(gotObj.signalNorm / refObj.signalNorm - 1) < 1e-9
+    assert np.abs(gotObj.filt - refObj.filt).max() <= 1e-9 * np.abs(refObj.filt).max()
+    for k in refObj.fRelWeights:
+        assert abs(gotObj.fRelWeights[k] - refObj.fRelWeights[k]) < 1e-9
+    refCat = photometry_ref.findObjects(ref, **DETECT)
+    photometry_ref.measureFluxes(refCat, ref, None)
+    gotCat = photometry.findObjects(got, **DETECT)
+    photometry.measureFluxes(gotCat, got, None)
+    assert len(refCat) >= 3
+    _compareCatalogs(gotCat, refCat, ['SNR', 'y_c', 'err_y_c', 'deltaT_c', 'err_deltaT_c', 'RADeg', 'decDeg', 'galacticLatDeg'])
+    # segmentation labels bit-exact on the GPU-made S/N map
+    ids, pos, npix, seg = photometry.getObjectPositions(got['SNMap'], 4.0)
+    rids, rpos, rnpix, rseg = photometry_ref.getObjectPositions(np.asarray(got['SNMap']), 4.0)
+    assert np.array_equal(seg, rseg) and np.array_equal(ids, rids) and np.array_equal(npix, rnpix)
+    assert np.abs(np.array(pos[1:]) - np.array(rpos[1:])).max() < 1e-9
+
+
+def test_beam_matched_filter_point_sources_with_masks(report):
+    """BASELINE config 2 (one reduced tile): point sources, uK output, numNoiseBins, zero border, point-source holes."""
+    from nemo_b200 import filters, photometry
+    mapDicts, truth = synth.makeTile(shape=(512, 512), freqsGHz=(148.0,), noiseUK=(100.0,), numObjects=40, kind='sources',
+                                     seed=1234, borderPix=30, psHoles=3)
+    rng = np.random.default_rng(5)
+    mapDicts[0]['weights'] = mapDicts[0]['weights'] * (0.6 + 0.8 * rng.random(mapDicts[0]['weights'].shape))
+    mapDicts[0]['flagMask'][200:260, 100:180] = 1
+    f = _beam(numBins=4, edgeTrimArcmin=10.0)
+    ref = filters_ref.filterMaps(mapDicts, _copyFilter(f), 'PRIMARY')
+    got = filters.filterMaps(mapDicts, _copyFilter(f), 'PRIMARY', verbose=False)
+    _compareMaps(got, ref, report, "beam_F1_bins4")
+    refCat = photometry_ref.findObjects(ref, **DETECT)
+    photometry_ref.measureFluxes(refCat, ref, None)
+    gotCat = photometry.findObjects(got, **DETECT)
+    photometry.measureFluxes(gotCat, got, None)
+    assert len(refCat) >= 10
+    _compareCatalogs(gotCat, refCat, ['SNR', 'deltaT_c', 'err_deltaT_c', 'fluxJy', 'err_fluxJy'])
+
+
+def test_two_frequency_matched_filter_with_cmb(report):
+    """BASELINE config 4 (one reduced tile): 90 + 150 GHz, CMB + noise, two Arnaud scales, photFilter columns."""
+    from nemo_b200 import filters, photometry
+    mapDicts, truth = synth.makeTile(shape=(512, 512), freqsGHz=(97.8, 149.6), noiseUK=(60.0, 40.0), beamFWHMArcmin=(2.2, 1.4),
+                                     numObjects=12, kind='clusters', cmb=True, seed=11)
+    fPhot = _arnaud('Arnaud_M2e14_z0p4', 2e14, 0.4, grid=40.)
+    fBig = _arnaud('Arnaud_M8e14_z0p2', 8e14, 0.2, grid=40.)
+    refPhot, refObj = filters_ref.filterMaps(mapDicts, _copyFilter(fPhot), 'T0', returnFilter=True)
+    gotPhot, gotObj = filters.filterMaps(mapDicts, _copyFilter(fPhot), 'T0', verbose=False, returnFilter=True)
+    _compareMaps(gotPhot, refPhot, report, "arnaud_F2_phot")
+    for k in refObj.fRelWeights:
+        assert abs(gotObj.fRelWeights[k] - refObj.fRelWeights[k]) < 1e-8
+    assert np.abs(gotObj.filt - refObj.filt).max() <= 1e-8 * np.abs(refObj.filt).max()
+    ref = filters_ref.filterMaps(mapDicts, _copyFilter(fBig), 'T0')
+    got = filters.filterMaps(mapDicts, _copyFilter(fBig), 'T0', verbose=False)
+    _compareMaps(got, ref, report, "arnaud_F2_big")
+    refCat = photometry_ref.findObjects(ref, **DETECT)
+    photometry_ref.measureFluxes(refCat, ref, None, photFilteredMapDict={'SNMap': refPhot['SNMap'], 'data': refPhot['data']})
+    gotCat = photometry.findObjects(got, **DETECT)
+    photometry.measureFluxes(gotCat, got, None, photFilteredMapDict={'SNMap': gotPhot['SNMap'], 'data': gotPhot['data']})
+    assert len(refCat) >= 3
+    _compareCatalogs(gotCat, refCat, ['SNR', 'y_c', 'fixed_SNR', 'fixed_y_c', 'fixed_err_y_c', 'fixed_deltaT_c'])
+
+
+def test_cached_filter_round_trip(tmp_path, report):
+    """saveFilter then useCachedFilter (the source-injection path, maps.py:2093): same maps as a fresh build."""
+    from nemo_b200 import filters
+    mapDicts, truth = synth.makeTile(shape=(256, 256), numObjects=5, kind='clusters', seed=21)
+    f = _arnaud(saveFilter=True)
+    d = str(tmp_path)
+    got1, obj1 = filters.filterMaps(mapDicts, _copyFilter(f), 'T0', diagnosticsDir=d, selFnDir=d, verbose=False, returnFilter=True)
+    assert obj1._cachePath() is not None
+    got2, obj2 = filters.filterMaps(mapDicts, _copyFilter(f), 'T0', diagnosticsDir=d, selFnDir=d, verbose=False,
+                                    useCachedFilter=True, returnFilter=True)
+    assert obj2.signalNorm == obj1.signalNorm
+    assert np.array_equal(np.asarray(got1['SNMap']), np.asarray(got2['SNMap']))
+    assert np.array_equal(np.asarray(got1['data']), np.asarray(got2['data']))
+    # applyFilter on real maps == what buildAndApply filtered
+    again = obj2.applyFilter(np.array([m['data'] for m in mapDicts]))
+    ref = filters_ref.filterMaps(mapDicts, _copyFilter(_arnaud()), 'T0', undoPixelWindow=False)
+    inner = ref['surveyMask'] > 0
+    assert np.abs(again[inner] - ref['data'][inner]).max() < 1e-9 * np.abs(ref['data']).max()
+    report("cached_filter", ok=1)
+
+
+def test_real_space_matched_filter_two_frequency(report):
+    """BASELINE config 3 (one reduced tile): 90 + 150 GHz real-space kernel, symmetrised, bckSub."""
+    from nemo_b200 import filters, photometry
+    mapDicts, truth = synth.makeTile(shape=(512, 512), freqsGHz=(97.8, 149.6), noiseUK=(60.0, 40.0), beamFWHMArcmin=(2.2, 1.4),
+                                     numObjects=10, kind='clusters', cmb=True, seed=31)
+    p = {'M500MSun': 2e14, 'z': 0.4, 'outputUnits': 'yc', 'bckSub': True, 'edgeTrimArcmin': 0.,
+         'noiseParams': {'method': 'dataMap', 'matchedFilterClass': 'ArnaudModelMatchedFilter', 'RADecSection': None,
+                         'kernelMaxArcmin': 7., 'symmetrize': True, 'noiseGridArcmin': 20.}}
+    f = {'label': 'ArnaudRS', 'class': 'ArnaudModelRealSpaceMatchedFilter', 'params': p}
+    ref, refObj = filters_ref.filterMaps(mapDicts, _copyFilter(f), 'T0', returnFilter=True)
+    got, gotObj = filters.filterMaps(mapDicts, _copyFilter(f), 'T0', verbose=False, returnFilter=True)
+    assert gotObj.kern2d.shape == refObj.kern2d.shape
+    assert np.abs(gotObj.kern2d - refObj.kern2d).max() <= 1e-8 * np.abs(refObj.kern2d).max()
+    assert abs(gotObj.bckSubScaleArcmin - refObj.bckSubScaleArcmin) < 1e-12
+    assert abs(gotObj.signalNorm / refObj.signalNorm - 1) < 1e-8
+    _compareMaps(got, ref, report, "realspace_F2")
+    refCat = photometry_ref.findObjects(ref, **DETECT)
+    photometry_ref.measureFluxes(refCat, ref, None)
+    gotCat = photometry.findObjects(got, **DETECT)
+    photometry.measureFluxes(gotCat, got, None)
+    _compareCatalogs(gotCat, refCat, ['SNR', 'y_c'])
+
+
+def test_batched_pipeline_matches_per_tile_oracle(report):
+    """Tile x scale batching: 3 tiles x 3 scales, photFilter first, optimal catalog."""
+    from nemo_b200 import pipelines, catalogs
+    tileMaps = {}
+    for t in range(3):
+        md, _ = synth.makeTile(shape=(256, 256), freqsGHz=(97.8, 149.6), noiseUK=(60.0, 40.0), beamFWHMArcmin=(2.2, 1.4),
+                               numObjects=6, kind='clusters', cmb=True, seed=100 + t)
+        tileMaps['tile%d' % t] = md
+    filtersList = [_arnaud('Arnaud_M1e14_z0p8', 1e14, 0.8), _arnaud('Arnaud_M2e14_z0p4', 2e14, 0.4), _arnaud('Arnaud_M8e14_z0p2', 8e14, 0.2)]
+    parDict = {'mapFilters': filtersList, 'photFilter': 'Arnaud_M2e14_z0p4', 'thresholdSigma': 4.0, 'minObjPix': 1,
+               'findCenterOfMass': True, 'useInterpolator': True, 'rejectBorder': 0}
+    config = pipelines.SimpleConfig(parDict, tileMaps)
+    opt = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=2)
+    # oracle: the reference's loop order (pipelines.py:179-286)
+    ordered = pipelines._orderedFilters(config.parDict)
+    assert ordered[0]['label'] == 'Arnaud_M2e14_z0p4'
+    nObj = 0
+    for tileName, md in tileMaps.items():
+        phot = None
+        for f in ordered:
+            ref = filters_ref.filterMaps(md, _copyFilter(f), tileName)
+            if f['label'] == parDict['photFilter']:
+                phot = {'SNMap': ref['SNMap'], 'data': ref['data']}
+            refCat = photometry_ref.findObjects(ref, threshold=4.0, minObjPix=1, findCenterOfMass=True, removeRings=True,
+                                                ringThresholdSigma=3, rejectBorder=0, useInterpolator=True)
+            photometry_ref.measureFluxes(refCat, ref, None, photFilteredMapDict=phot)
+            gotTab = config.catalogDict[f['label'] + "#" + tileName]['catalog']
+            _compareCatalogs(gotTab, refCat, ['SNR', 'y_c', 'err_y_c', 'fixed_SNR', 'fixed_y_c', 'deltaT_c'])
+            nObj += len(refCat)
+    assert nObj >= 6
+    assert len(opt) > 0 and len(opt) <= nObj
+    report("batched_pipeline", objects=nObj, optimal=len(opt))
