@@ -33,6 +33,14 @@ int nb_version(void);
 int nb_device_info(int* smCount, int* ccMajor, int* ccMinor);
 int nb_fft_size_supported(int n);
 
+/* Per-kernel timing with CUDA events (the reference only prints wall-clock "time since start",
+ * nemo/pipelines.py:106-107).  nb_prof_enable(1) clears the records and starts timing every kernel this library
+ * launches; nb_prof_report synchronises the device and writes "kernel,launches,total_ms\n" lines (first-launch
+ * order) into buf (host, cap bytes), returning the full length. */
+long long nb_launch_count(void); /* kernels launched by this library since it was loaded */
+int nb_prof_enable(int on);
+long long nb_prof_report(char* buf, long long cap);
+
 /* K1: enmap.fft(enmap.apod(map, apodPix))  (nemo/filters.py:528, 551, 849; enmap.fft at :618, 649, 682 with
  * apodPix = 0).  out = scale * rfft2(taper * in); the reference's normalisation is scale = 1/sqrt(H*W). */
 int nb_rfft2(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale,

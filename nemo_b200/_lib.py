@@ -25,6 +25,9 @@ _PROTOTYPES = {
     "nb_version": [],
     "nb_device_info": [ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)],
     "nb_fft_size_supported": [c_int],
+    "nb_launch_count": [],
+    "nb_prof_enable": [c_int],
+    "nb_prof_report": [ctypes.c_char_p, c_ll],
     "nb_rfft2": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_ptr],
     "nb_irfft2": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr, c_int, c_ptr],
     "nb_apply_filter": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr, c_ptr],
@@ -48,7 +51,7 @@ _PROTOTYPES = {
     "nb_cast": [c_int, c_ptr, c_int, c_ptr, c_ll, c_ptr],
     "nb_mask_to_u8": [c_int, c_ptr, c_ptr, c_ll, c_ptr],
 }
-_RESTYPES = {"nb_last_error": ctypes.c_char_p, "nb_label4_scratch_ints": c_ll}
+_RESTYPES = {"nb_last_error": ctypes.c_char_p, "nb_label4_scratch_ints": c_ll, "nb_prof_report": c_ll, "nb_launch_count": c_ll}
 
 EXPORTED_SYMBOLS = sorted(_PROTOTYPES.keys())
 
@@ -91,3 +94,28 @@ def require_cuda():
     if not torch.cuda.is_available():
         raise NemoB200Error("nemo_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
     return torch
+
+
+def launchCount():
+    """Kernels launched by libnemo_b200.so in this process so far."""
+    return int(load().nb_launch_count())
+
+
+def profEnable(on=True):
+    """Starts (and clears) or stops the library's per-kernel CUDA-event timers."""
+    load().nb_prof_enable(1 if on else 0)
+
+
+def profReport():
+    """{kernel name: (launches, total ms)} since the last profEnable(True); synchronises the device."""
+    lib = load()
+    cap = 1 << 16
+    buf = ctypes.create_string_buffer(cap)
+    n = lib.nb_prof_report(buf, cap)
+    if n < 0:
+        raise NemoB200Error("nb_prof_report failed (%d)" % n)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split(',')
+        out[name] = (int(cnt), float(ms))
+    return out

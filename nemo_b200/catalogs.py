@@ -117,32 +117,51 @@ def vstack(tables):
     return out
 
 
-def makeName(RADeg, decDeg, prefix='ACT-CL'):
-    """IAU-style name prefix JHHMM.m+DDMM (truncated, not rounded)."""
-    hours = (RADeg / 360.0) * 24.0
-    h = int(hours)
-    mins = (hours - h) * 60.0
-    sRA = "%02d%04.1f" % (h, np.floor(mins * 10) / 10.0)
+def _splitFraction(text):
+    """('12', 0.345) from '12.345': integer digits and the fractional part re-read from its printed digits, which is
+    how the reference derives minutes and seconds (catalogs.py:295-346) -- truncation, never rounding."""
+    whole, frac = text.split('.')
+    return whole, float('.' + frac)
+
+
+def _nameRA(RADeg, longFormat):
+    hoursText = "%.10f" % ((RADeg / 360) * 24) if not longFormat else str((RADeg / 360) * 24)
+    whole, frac = _splitFraction(hoursText)
+    out = whole.rjust(2, '0')[:2]
+    mins = frac * 60
+    if not longFormat:
+        minsText = "%.10f" % mins
+        return out + (minsText[:3].rjust(4, '0') if mins < 10 else minsText[:4])       # MM.m
+    minsText = str(mins)
+    out += minsText[:1].rjust(2, '0') if mins < 10 else minsText[:2]
+    secs = _splitFraction(minsText)[1] * 60
+    secsText = str(secs)
+    return out + (secsText[:3].rjust(4, '0') if secs < 10 else secsText[:4])           # SS.s
+
+
+def _nameDec(decDeg, longFormat):
+    text = str(decDeg)
     sign = '+' if decDeg > 0 else '-'
-    d = abs(decDeg)
-    dd = int(d)
-    dm = int((d - dd) * 60.0)
-    return prefix + " J" + sRA + sign + "%02d%02d" % (dd, dm)
+    whole, frac = _splitFraction(text.lstrip('-'))
+    out = sign + whole.rjust(2, '0')[:2]
+    mins = frac * 60
+    minsText = str(mins)
+    out += minsText[:1].rjust(2, '0') if mins < 10 else minsText[:2]
+    if longFormat:
+        secs = _splitFraction(minsText)[1] * 60
+        secsText = str(secs)
+        out += secsText[:3].rjust(4, '0') if secs < 10 else secsText[:4]
+    return out
+
+
+def makeName(RADeg, decDeg, prefix='ACT-CL'):
+    """Object name `prefix JHHMM.m+/-DDMM`, digits truncated as the reference does (catalogs.py:259-274, 295-346)."""
+    return prefix + " J" + _nameRA(float(RADeg), False) + _nameDec(float(decDeg), False)
 
 
 def makeLongName(RADeg, decDeg, prefix='ACT-CL'):
-    hours = (RADeg / 360.0) * 24.0
-    h = int(hours)
-    mins = (hours - h) * 60.0
-    m = int(mins)
-    secs = (mins - m) * 60.0
-    sign = '+' if decDeg > 0 else '-'
-    d = abs(decDeg)
-    dd = int(d)
-    dmins = (d - dd) * 60.0
-    dm = int(dmins)
-    dsecs = (dmins - dm) * 60.0
-    return prefix + " J%02d%02d%04.1f%s%02d%02d%04.1f" % (h, m, np.floor(secs * 10) / 10.0, sign, dd, dm, np.floor(dsecs * 10) / 10.0)
+    """Object name `prefix JHHMMSS.s+/-DDMMSS.s` (catalogs.py:277-292, 349-420)."""
+    return prefix + " J" + _nameRA(float(RADeg), True) + _nameDec(float(decDeg), True)
 
 
 def catalogListToTab(catalogList, keysToWrite=COLUMN_NAMES):

@@ -18,7 +18,105 @@ int nb_sm_count() {
     return n;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// per-kernel event timing
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+int g_nb_prof_on = 0;
+unsigned long long g_nb_launches = 0;
+namespace {
+struct ProfRec {
+    const char* name;
+    cudaEvent_t e0, e1;
+};
+std::mutex g_prof_mutex;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t g_prof_pending = nullptr;
+
+cudaEvent_t prof_event() {
+    cudaEvent_t e = nullptr;
+    if (!g_prof_pool.empty()) {
+        e = g_prof_pool.back();
+        g_prof_pool.pop_back();
+    } else if (cudaEventCreate(&e) != cudaSuccess) {
+        e = nullptr;
+    }
+    return e;
+}
+}  // namespace
+
+void nb_prof_begin_(cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (g_prof_pending) g_prof_pool.push_back(g_prof_pending);
+    g_prof_pending = prof_event();
+    if (g_prof_pending) cudaEventRecord(g_prof_pending, st);
+}
+
+void nb_prof_end_(const char* name, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (!g_prof_pending) return;
+    ProfRec r;
+    r.name = name;
+    r.e0 = g_prof_pending;
+    r.e1 = prof_event();
+    g_prof_pending = nullptr;
+    if (!r.e1) {
+        g_prof_pool.push_back(r.e0);
+        return;
+    }
+    cudaEventRecord(r.e1, st);
+    g_prof_recs.push_back(r);
+}
+
 extern "C" {
+
+long long nb_launch_count(void) { return (long long)__atomic_load_n(&g_nb_launches, __ATOMIC_RELAXED); }
+
+int nb_prof_enable(int on) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    for (auto& r : g_prof_recs) {
+        g_prof_pool.push_back(r.e0);
+        g_prof_pool.push_back(r.e1);
+    }
+    g_prof_recs.clear();
+    g_nb_prof_on = on ? 1 : 0;
+    return NB_OK;
+}
+
+long long nb_prof_report(char* buf, long long cap) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (cudaDeviceSynchronize() != cudaSuccess) return NB_ERR_CUDA;
+    std::map<std::string, std::pair<long long, double>> agg;
+    std::vector<std::string> order;
+    for (auto& r : g_prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+        auto it = agg.find(r.name);
+        if (it == agg.end()) {
+            agg[r.name] = std::make_pair(1LL, (double)ms);
+            order.push_back(r.name);
+        } else {
+            it->second.first += 1;
+            it->second.second += (double)ms;
+        }
+    }
+    std::string out;
+    char line[256];
+    for (auto& n : order) {
+        snprintf(line, sizeof(line), "%s,%lld,%.6f\n", n.c_str(), agg[n].first, agg[n].second);
+        out += line;
+    }
+    if (buf && cap > 0) {
+        const long long n = (long long)out.size() < cap - 1 ? (long long)out.size() : cap - 1;
+        memcpy(buf, out.data(), (size_t)n);
+        buf[n] = 0;
+    }
+    return (long long)out.size();
+}
 
 const char* nb_last_error(void) { return g_err; }
 

@@ -101,3 +101,19 @@ __host__ __device__ __forceinline__ int reflect_idx(int i, int n) {
 }
 
 int nb_sm_count();
+
+// Per-kernel CUDA-event timing (nb_prof_enable / nb_prof_report of the C ABI).  Off by default: the macros then cost
+// one load and a branch.  Every launch site is wrapped as { NB_PROF_BEGIN(st); kernel<<<..., st>>>(...); NB_PROF_END("name", st); }
+extern int g_nb_prof_on;
+extern unsigned long long g_nb_launches;  // kernels launched by this library since load (nb_launch_count)
+void nb_prof_begin_(cudaStream_t st);
+void nb_prof_end_(const char* name, cudaStream_t st);
+#define NB_PROF_BEGIN(st)                 \
+    do {                                  \
+        if (g_nb_prof_on) nb_prof_begin_(st); \
+    } while (0)
+#define NB_PROF_END(name, st)                 \
+    do {                                      \
+        __atomic_add_fetch(&g_nb_launches, 1ULL, __ATOMIC_RELAXED); \
+        if (g_nb_prof_on) nb_prof_end_(name, st); \
+    } while (0)

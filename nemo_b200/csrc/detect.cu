@@ -278,23 +278,23 @@ int nb_label4(int prec, const void* map, double threshold, double sign, int* lab
     int* L = scratch;
     int* blockCounts = scratch + (size_t)B * HW;
     if (prec == NB_PREC_F64)
-        label_init_img_kernel<double><<<grid, LBL_BLOCK, 0, st>>>((const double*)map, threshold, sign, L, HW);
+        { NB_PROF_BEGIN(st); label_init_img_kernel<double><<<grid, LBL_BLOCK, 0, st>>>((const double*)map, threshold, sign, L, HW); NB_PROF_END("label_init_img_kernel", st); }
     else if (prec == NB_PREC_F32)
-        label_init_img_kernel<float><<<grid, LBL_BLOCK, 0, st>>>((const float*)map, threshold, sign, L, HW);
+        { NB_PROF_BEGIN(st); label_init_img_kernel<float><<<grid, LBL_BLOCK, 0, st>>>((const float*)map, threshold, sign, L, HW); NB_PROF_END("label_init_img_kernel", st); }
     else {
         nb_set_error("nb_label4: bad precision %d", prec);
         return NB_ERR_ARG;
     }
     NB_CHECK_LAUNCH();
-    label_merge_kernel<<<grid, LBL_BLOCK, 0, st>>>(L, H, W);
+    { NB_PROF_BEGIN(st); label_merge_kernel<<<grid, LBL_BLOCK, 0, st>>>(L, H, W); NB_PROF_END("label_merge_kernel", st); }
     NB_CHECK_LAUNCH();
-    label_flatten_kernel<<<grid, LBL_BLOCK, 0, st>>>(L, HW, blockCounts);
+    { NB_PROF_BEGIN(st); label_flatten_kernel<<<grid, LBL_BLOCK, 0, st>>>(L, HW, blockCounts); NB_PROF_END("label_flatten_kernel", st); }
     NB_CHECK_LAUNCH();
-    label_scan_kernel<<<B, 1024, 0, st>>>(blockCounts, nBlocks, nLabels);
+    { NB_PROF_BEGIN(st); label_scan_kernel<<<B, 1024, 0, st>>>(blockCounts, nBlocks, nLabels); NB_PROF_END("label_scan_kernel", st); }
     NB_CHECK_LAUNCH();
-    label_rank_kernel<<<grid, LBL_BLOCK, 0, st>>>(L, HW, blockCounts);
+    { NB_PROF_BEGIN(st); label_rank_kernel<<<grid, LBL_BLOCK, 0, st>>>(L, HW, blockCounts); NB_PROF_END("label_rank_kernel", st); }
     NB_CHECK_LAUNCH();
-    label_final_kernel<<<grid, LBL_BLOCK, 0, st>>>(L, labels, HW);
+    { NB_PROF_BEGIN(st); label_final_kernel<<<grid, LBL_BLOCK, 0, st>>>(L, labels, HW); NB_PROF_END("label_final_kernel", st); }
     NB_CHECK_LAUNCH();
     return NB_OK;
 }
@@ -308,26 +308,26 @@ int nb_label_moments(int prec, const void* map, double sign, const int* labels, 
                      int maxLabels, cudaStream_t st) {
     NB_REQUIRE(map && labels && table && B > 0 && maxLabels >= 0, NB_ERR_ARG, "nb_label_moments: bad arguments");
     const long long nRows = (long long)B * (maxLabels + 1);
-    moments_init_kernel<<<(unsigned)((nRows + 255) / 256), 256, 0, st>>>(table, nRows);
+    { NB_PROF_BEGIN(st); moments_init_kernel<<<(unsigned)((nRows + 255) / 256), 256, 0, st>>>(table, nRows); NB_PROF_END("moments_init_kernel", st); }
     NB_CHECK_LAUNCH();
     const int HW = H * W;
     int gx = (HW + 256 * 8 - 1) / (256 * 8);
     if (gx < 1) gx = 1;
     dim3 grid(gx, B);
     if (prec == NB_PREC_F64) {
-        moments_accum_kernel<double><<<grid, 256, 0, st>>>((const double*)map, sign, labels, table, H, W, maxLabels);
+        { NB_PROF_BEGIN(st); moments_accum_kernel<double><<<grid, 256, 0, st>>>((const double*)map, sign, labels, table, H, W, maxLabels); NB_PROF_END("moments_accum_kernel", st); }
         NB_CHECK_LAUNCH();
-        moments_argmax_kernel<double><<<grid, 256, 0, st>>>((const double*)map, sign, labels, table, H, W, maxLabels);
+        { NB_PROF_BEGIN(st); moments_argmax_kernel<double><<<grid, 256, 0, st>>>((const double*)map, sign, labels, table, H, W, maxLabels); NB_PROF_END("moments_argmax_kernel", st); }
     } else if (prec == NB_PREC_F32) {
-        moments_accum_kernel<float><<<grid, 256, 0, st>>>((const float*)map, sign, labels, table, H, W, maxLabels);
+        { NB_PROF_BEGIN(st); moments_accum_kernel<float><<<grid, 256, 0, st>>>((const float*)map, sign, labels, table, H, W, maxLabels); NB_PROF_END("moments_accum_kernel", st); }
         NB_CHECK_LAUNCH();
-        moments_argmax_kernel<float><<<grid, 256, 0, st>>>((const float*)map, sign, labels, table, H, W, maxLabels);
+        { NB_PROF_BEGIN(st); moments_argmax_kernel<float><<<grid, 256, 0, st>>>((const float*)map, sign, labels, table, H, W, maxLabels); NB_PROF_END("moments_argmax_kernel", st); }
     } else {
         nb_set_error("nb_label_moments: bad precision %d", prec);
         return NB_ERR_ARG;
     }
     NB_CHECK_LAUNCH();
-    moments_final_kernel<<<(unsigned)((nRows + 255) / 256), 256, 0, st>>>(table, nRows);
+    { NB_PROF_BEGIN(st); moments_final_kernel<<<(unsigned)((nRows + 255) / 256), 256, 0, st>>>(table, nRows); NB_PROF_END("moments_final_kernel", st); }
     NB_CHECK_LAUNCH();
     return NB_OK;
 }
@@ -339,9 +339,9 @@ int nb_spline_eval(int prec, const void* img, int B, int H, int W, const int* im
     const int wpb = 4;
     const unsigned grid = (unsigned)((K + wpb - 1) / wpb);
     if (prec == NB_PREC_F64)
-        spline_eval_kernel<double><<<grid, 32 * wpb, 0, st>>>((const double*)img, H, W, imgIdx, yx, out, K, sign);
+        { NB_PROF_BEGIN(st); spline_eval_kernel<double><<<grid, 32 * wpb, 0, st>>>((const double*)img, H, W, imgIdx, yx, out, K, sign); NB_PROF_END("spline_eval_kernel", st); }
     else if (prec == NB_PREC_F32)
-        spline_eval_kernel<float><<<grid, 32 * wpb, 0, st>>>((const float*)img, H, W, imgIdx, yx, out, K, sign);
+        { NB_PROF_BEGIN(st); spline_eval_kernel<float><<<grid, 32 * wpb, 0, st>>>((const float*)img, H, W, imgIdx, yx, out, K, sign); NB_PROF_END("spline_eval_kernel", st); }
     else {
         nb_set_error("nb_spline_eval: bad precision %d", prec);
         return NB_ERR_ARG;

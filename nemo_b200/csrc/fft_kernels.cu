@@ -390,8 +390,8 @@ static int rfft_rows_t(const T* in, typename V2<T>::type* out, int B, int H, int
         typedef RowCfg<T, WW> Cfg;                                                                            \
         if ((rc = set_smem(rfft_rows_kernel<T, WW>, Cfg::SMEM)) != NB_OK) return rc;                          \
         const unsigned grid = (unsigned)((nrows + Cfg::RPB - 1) / Cfg::RPB);                                  \
-        rfft_rows_kernel<T, WW><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(in, out, H, nrows, tp, (T)scale,      \
-                                                                       (const C2*)twM, (const C2*)twW);      \
+        { NB_PROF_BEGIN(st); rfft_rows_kernel<T, WW><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(in, out, H, nrows, tp, (T)scale,      \
+                                                                       (const C2*)twM, (const C2*)twW); NB_PROF_END("rfft_rows_kernel", st); }      \
     }
     switch (W) {
         case 64: ROWS_FWD(64); break;
@@ -421,8 +421,8 @@ static int irfft_rows_t(const typename V2<T>::type* in, T* out, int B, int H, in
         typedef RowCfg<T, WW> Cfg;                                                                            \
         if ((rc = set_smem(irfft_rows_kernel<T, WW>, Cfg::SMEM)) != NB_OK) return rc;                         \
         const unsigned grid = (unsigned)((nrows + Cfg::RPB - 1) / Cfg::RPB);                                  \
-        irfft_rows_kernel<T, WW><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(in, out, H, nrows, ep, (const C2*)twM, \
-                                                                        (const C2*)twW);                     \
+        { NB_PROF_BEGIN(st); irfft_rows_kernel<T, WW><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(in, out, H, nrows, ep, (const C2*)twM, \
+                                                                        (const C2*)twW); NB_PROF_END("irfft_rows_kernel", st); }                     \
     }
     switch (W) {
         case 64: ROWS_INV(64); break;
@@ -452,10 +452,10 @@ static int fft_cols_t(const typename V2<T>::type* in, typename V2<T>::type* out,
         dim3 grid((Wc + Cfg::C - 1) / Cfg::C, B);                                                            \
         if (dir < 0) {                                                                                       \
             if ((rc = set_smem(fft_cols_kernel<T, NN, -1>, Cfg::SMEM)) != NB_OK) return rc;                  \
-            fft_cols_kernel<T, NN, -1><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(in, out, Wc, (const C2*)tw, (T)scale); \
+            { NB_PROF_BEGIN(st); fft_cols_kernel<T, NN, -1><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(in, out, Wc, (const C2*)tw, (T)scale); NB_PROF_END("fft_cols_kernel", st); } \
         } else {                                                                                             \
             if ((rc = set_smem(fft_cols_kernel<T, NN, +1>, Cfg::SMEM)) != NB_OK) return rc;                  \
-            fft_cols_kernel<T, NN, +1><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(in, out, Wc, (const C2*)tw, (T)scale); \
+            { NB_PROF_BEGIN(st); fft_cols_kernel<T, NN, +1><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(in, out, Wc, (const C2*)tw, (T)scale); NB_PROF_END("fft_cols_kernel", st); } \
         }                                                                                                    \
     }
     NB_DISPATCH_N(H, COLS)
@@ -476,7 +476,7 @@ static int fft_cols_apply_tf(const typename V2<T>::type* fmaps, const T* filt, t
         typedef ColCfg<T, NN> Cfg;                                                                           \
         dim3 grid((Wc + Cfg::C - 1) / Cfg::C, nOut);                                                         \
         if ((rc = set_smem(fft_cols_apply_kernel<T, NN, F>, Cfg::SMEM)) != NB_OK) return rc;                 \
-        fft_cols_apply_kernel<T, NN, F><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(fmaps, filt, out, Wc, S, (const C2*)tw); \
+        { NB_PROF_BEGIN(st); fft_cols_apply_kernel<T, NN, F><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(fmaps, filt, out, Wc, S, (const C2*)tw); NB_PROF_END("fft_cols_apply_kernel", st); } \
     }
     NB_DISPATCH_N(H, COLS_APPLY)
 #undef COLS_APPLY
@@ -495,7 +495,7 @@ static int fft_cols_window_t(typename V2<T>::type* data, int B, int H, int Wc, c
         typedef ColCfg<T, NN> Cfg;                                                                           \
         dim3 grid((Wc + Cfg::C - 1) / Cfg::C, B);                                                            \
         if ((rc = set_smem(fft_cols_window_kernel<T, NN>, Cfg::SMEM)) != NB_OK) return rc;                   \
-        fft_cols_window_kernel<T, NN><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(data, Wc, wy, wx, (const C2*)tw); \
+        { NB_PROF_BEGIN(st); fft_cols_window_kernel<T, NN><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(data, Wc, wy, wx, (const C2*)tw); NB_PROF_END("fft_cols_window_kernel", st); } \
     }
     NB_DISPATCH_N(H, COLS_WIN)
 #undef COLS_WIN

@@ -323,12 +323,12 @@ static int xpower_smooth_tf(const void* fmaps, double* cov, double* tmp, int B, 
     NB_REQUIRE(smem <= 200 * 1024, NB_ERR_UNSUPPORTED, "nb_xpower_smooth: F=%d, W=%d needs too much shared memory", F, W);
     if (smem > 48 * 1024)
         NB_CHECK_CUDA(cudaFuncSetAttribute(xpower_smooth_x_kernel<T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    xpower_smooth_x_kernel<T, F><<<dim3(H, B), 256, smem, st>>>((const C2*)fmaps, tmp, H, W, g);
+    { NB_PROF_BEGIN(st); xpower_smooth_x_kernel<T, F><<<dim3(H, B), 256, smem, st>>>((const C2*)fmaps, tmp, H, W, g); NB_PROF_END("xpower_smooth_x_kernel", st); }
     NB_CHECK_LAUNCH();
     const size_t smem2 = (size_t)(GY_TY + 2 * g.r) * GY_TX * sizeof(double);
     if (smem2 > 48 * 1024)
         NB_CHECK_CUDA(cudaFuncSetAttribute(smooth_y_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    smooth_y_f64_kernel<<<dim3((W + GY_TX - 1) / GY_TX, (H + GY_TY - 1) / GY_TY, B * P), 256, smem2, st>>>(tmp, cov, H, W, g);
+    { NB_PROF_BEGIN(st); smooth_y_f64_kernel<<<dim3((W + GY_TX - 1) / GY_TX, (H + GY_TY - 1) / GY_TY, B * P), 256, smem2, st>>>(tmp, cov, H, W, g); NB_PROF_END("smooth_y_f64_kernel", st); }
     NB_CHECK_LAUNCH();
     return NB_OK;
 }
@@ -340,8 +340,8 @@ static int build_filter_tf(const double* cov, const void* fsig, const double* w,
     FreqW fw;
     for (int f = 0; f < NB_MAX_FREQ; ++f) fw.w[f] = f < F ? w[f] : 0.0;
     const int Wc = W / 2 + 1;
-    build_filter_kernel<T, F><<<dim3((Wc + 255) / 256, H, nOut), 256, 0, st>>>(cov, (const C2*)fsig, fw, filtFull, (T*)filtH, S,
-                                                                             sigPerTile, H, W);
+    { NB_PROF_BEGIN(st); build_filter_kernel<T, F><<<dim3((Wc + 255) / 256, H, nOut), 256, 0, st>>>(cov, (const C2*)fsig, fw, filtFull, (T*)filtH, S,
+                                                                             sigPerTile, H, W); NB_PROF_END("build_filter_kernel", st); }
     NB_CHECK_LAUNCH();
     return NB_OK;
 }
@@ -393,9 +393,9 @@ int nb_fold_filter(int prec, const double* filtFull, void* filtH, int n, int H, 
     const int Wc = W / 2 + 1;
     dim3 grid((Wc + 255) / 256, H, n);
     if (prec == NB_PREC_F64)
-        fold_filter_kernel<double><<<grid, 256, 0, st>>>(filtFull, (double*)filtH, H, W);
+        { NB_PROF_BEGIN(st); fold_filter_kernel<double><<<grid, 256, 0, st>>>(filtFull, (double*)filtH, H, W); NB_PROF_END("fold_filter_kernel", st); }
     else if (prec == NB_PREC_F32)
-        fold_filter_kernel<float><<<grid, 256, 0, st>>>(filtFull, (float*)filtH, H, W);
+        { NB_PROF_BEGIN(st); fold_filter_kernel<float><<<grid, 256, 0, st>>>(filtFull, (float*)filtH, H, W); NB_PROF_END("fold_filter_kernel", st); }
     else {
         nb_set_error("nb_fold_filter: bad precision %d", prec);
         return NB_ERR_ARG;
@@ -408,9 +408,9 @@ int nb_template_norm(int prec, const void* map, int B, int H, int W, int mode, d
                      long long* argmaxIdx, double* maxVal, double* centreVal, double* signalNorm, cudaStream_t st) {
     NB_REQUIRE(map && argmaxIdx && maxVal && signalNorm && B > 0, NB_ERR_ARG, "nb_template_norm: bad arguments");
     if (prec == NB_PREC_F64)
-        template_norm_kernel<double><<<B, 1024, 0, st>>>((const double*)map, H, W, mode, cy, cx, numer, argmaxIdx, maxVal, centreVal, signalNorm);
+        { NB_PROF_BEGIN(st); template_norm_kernel<double><<<B, 1024, 0, st>>>((const double*)map, H, W, mode, cy, cx, numer, argmaxIdx, maxVal, centreVal, signalNorm); NB_PROF_END("template_norm_kernel", st); }
     else if (prec == NB_PREC_F32)
-        template_norm_kernel<float><<<B, 1024, 0, st>>>((const float*)map, H, W, mode, cy, cx, numer, argmaxIdx, maxVal, centreVal, signalNorm);
+        { NB_PROF_BEGIN(st); template_norm_kernel<float><<<B, 1024, 0, st>>>((const float*)map, H, W, mode, cy, cx, numer, argmaxIdx, maxVal, centreVal, signalNorm); NB_PROF_END("template_norm_kernel", st); }
     else {
         nb_set_error("nb_template_norm: bad precision %d", prec);
         return NB_ERR_ARG;
@@ -423,9 +423,9 @@ int nb_plane_values_at(int prec, const void* fmaps, const void* filtH, const lon
                        int H, int W, cudaStream_t st) {
     NB_REQUIRE(fmaps && filtH && idx && out && B > 0 && F > 0, NB_ERR_ARG, "nb_plane_values_at: bad arguments");
     if (prec == NB_PREC_F64)
-        plane_values_kernel<double><<<dim3(F, B), 256, 0, st>>>((const double2*)fmaps, (const double*)filtH, idx, out, F, H, W);
+        { NB_PROF_BEGIN(st); plane_values_kernel<double><<<dim3(F, B), 256, 0, st>>>((const double2*)fmaps, (const double*)filtH, idx, out, F, H, W); NB_PROF_END("plane_values_kernel", st); }
     else if (prec == NB_PREC_F32)
-        plane_values_kernel<float><<<dim3(F, B), 256, 0, st>>>((const float2*)fmaps, (const float*)filtH, idx, out, F, H, W);
+        { NB_PROF_BEGIN(st); plane_values_kernel<float><<<dim3(F, B), 256, 0, st>>>((const float2*)fmaps, (const float*)filtH, idx, out, F, H, W); NB_PROF_END("plane_values_kernel", st); }
     else {
         nb_set_error("nb_plane_values_at: bad precision %d", prec);
         return NB_ERR_ARG;

@@ -432,11 +432,11 @@ static int cell_rms_t(const void* map, const void* wmed, int nImg, int S, int H,
     memset(&ch, 0, sizeof(ch));
     for (int i = 0; i <= ny; ++i) ch.y[i] = yChunks[i];
     for (int i = 0; i <= nx; ++i) ch.x[i] = xChunks[i];
-    cell_rms_kernel<T><<<dim3(ny * nx, nImg), CR_THREADS, sizeof(double) * (numBins + 1), st>>>(
-        (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges);
+    { NB_PROF_BEGIN(st); cell_rms_kernel<T><<<dim3(ny * nx, nImg), CR_THREADS, sizeof(double) * (numBins + 1), st>>>(
+        (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges); NB_PROF_END("cell_rms_kernel", st); }
     NB_CHECK_LAUNCH();
-    paint_rms_kernel<T><<<dim3((W + 255) / 256, H, nImg), 256, 0, st>>>((const T*)wmed, S, H, W, ch, ny, nx, ov, numBins, table,
-                                                                         edges, (T*)rms);
+    { NB_PROF_BEGIN(st); paint_rms_kernel<T><<<dim3((W + 255) / 256, H, nImg), 256, 0, st>>>((const T*)wmed, S, H, W, ch, ny, nx, ov, numBins, table,
+                                                                         edges, (T*)rms); NB_PROF_END("paint_rms_kernel", st); }
     NB_CHECK_LAUNCH();
     return NB_OK;
 }
@@ -445,11 +445,11 @@ template <typename T>
 static int snr_mask_t(void* map, void* rms, const unsigned char* ps, const unsigned char* survey, int nImg, int S, int H, int W,
                       int trim, int apodPix, int realSpace, void* sn, unsigned char* maskOut, unsigned char* scratch, cudaStream_t st) {
     if (trim > 0) {
-        edge_rows_kernel<T><<<dim3(H, nImg), 256, sizeof(int) * (W + 1), st>>>((const T*)map, ps, S, H, W, trim, scratch);
+        { NB_PROF_BEGIN(st); edge_rows_kernel<T><<<dim3(H, nImg), 256, sizeof(int) * (W + 1), st>>>((const T*)map, ps, S, H, W, trim, scratch); NB_PROF_END("edge_rows_kernel", st); }
         NB_CHECK_LAUNCH();
     }
-    edge_cols_final_kernel<T><<<dim3((W + 127) / 128, (H + EC_SEG - 1) / EC_SEG, nImg), 128, 0, st>>>(
-        (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut);
+    { NB_PROF_BEGIN(st); edge_cols_final_kernel<T><<<dim3((W + 127) / 128, (H + EC_SEG - 1) / EC_SEG, nImg), 128, 0, st>>>(
+        (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut); NB_PROF_END("edge_cols_final_kernel", st); }
     NB_CHECK_LAUNCH();
     return NB_OK;
 }
@@ -461,9 +461,9 @@ int nb_median_weights(int prec, const void* weights, void* out, int B, int F, in
     const long long HW = (long long)H * W;
     dim3 grid((unsigned)((HW + 255) / 256), B);
     if (prec == NB_PREC_F64)
-        median_weights_kernel<double><<<grid, 256, 0, st>>>((const double*)weights, (double*)out, F, HW);
+        { NB_PROF_BEGIN(st); median_weights_kernel<double><<<grid, 256, 0, st>>>((const double*)weights, (double*)out, F, HW); NB_PROF_END("median_weights_kernel", st); }
     else if (prec == NB_PREC_F32)
-        median_weights_kernel<float><<<grid, 256, 0, st>>>((const float*)weights, (float*)out, F, HW);
+        { NB_PROF_BEGIN(st); median_weights_kernel<float><<<grid, 256, 0, st>>>((const float*)weights, (float*)out, F, HW); NB_PROF_END("median_weights_kernel", st); }
     else {
         nb_set_error("nb_median_weights: bad precision %d", prec);
         return NB_ERR_ARG;
@@ -506,9 +506,9 @@ int nb_snr_from_rms(int prec, const void* map, const void* rms, void* sn, int nI
     const long long HW = (long long)H * W;
     dim3 grid((unsigned)((HW + 255) / 256), nImg);
     if (prec == NB_PREC_F64)
-        snr_from_rms_kernel<double><<<grid, 256, 0, st>>>((const double*)map, (const double*)rms, (double*)sn, HW, S);
+        { NB_PROF_BEGIN(st); snr_from_rms_kernel<double><<<grid, 256, 0, st>>>((const double*)map, (const double*)rms, (double*)sn, HW, S); NB_PROF_END("snr_from_rms_kernel", st); }
     else if (prec == NB_PREC_F32)
-        snr_from_rms_kernel<float><<<grid, 256, 0, st>>>((const float*)map, (const float*)rms, (float*)sn, HW, S);
+        { NB_PROF_BEGIN(st); snr_from_rms_kernel<float><<<grid, 256, 0, st>>>((const float*)map, (const float*)rms, (float*)sn, HW, S); NB_PROF_END("snr_from_rms_kernel", st); }
     else {
         nb_set_error("nb_snr_from_rms: bad precision %d", prec);
         return NB_ERR_ARG;

@@ -145,15 +145,15 @@ int nb_gauss_filter(int prec, const void* in, void* tmp, void* out, int B, int H
         if (smemC > 48 * 1024)                                                                                            \
             NB_CHECK_CUDA(cudaFuncSetAttribute(gauss_cols_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC)); \
         /* scipy filters axis 0 (y) first, then axis 1 (x); each pass rounds to the array dtype */                        \
-        gauss_cols_kernel<T><<<gridC, 256, smemC, st>>>((const T*)in, nullptr, (T*)tmp, H, W, gy, 0);                     \
+        { NB_PROF_BEGIN(st); gauss_cols_kernel<T><<<gridC, 256, smemC, st>>>((const T*)in, nullptr, (T*)tmp, H, W, gy, 0); NB_PROF_END("gauss_cols_kernel", st); }                     \
         NB_CHECK_LAUNCH();                                                                                                \
         if (!subtract) {                                                                                                  \
-            gauss_rows_kernel<T><<<(unsigned)((size_t)B * H), 256, sizeof(double) * W, st>>>((const T*)tmp, (T*)out, W, gx); \
+            { NB_PROF_BEGIN(st); gauss_rows_kernel<T><<<(unsigned)((size_t)B * H), 256, sizeof(double) * W, st>>>((const T*)tmp, (T*)out, W, gx); NB_PROF_END("gauss_rows_kernel", st); } \
             NB_CHECK_LAUNCH();                                                                                            \
         } else {                                                                                                          \
-            gauss_rows_kernel<T><<<(unsigned)((size_t)B * H), 256, sizeof(double) * W, st>>>((const T*)tmp, (T*)tmp, W, gx); \
+            { NB_PROF_BEGIN(st); gauss_rows_kernel<T><<<(unsigned)((size_t)B * H), 256, sizeof(double) * W, st>>>((const T*)tmp, (T*)tmp, W, gx); NB_PROF_END("gauss_rows_kernel", st); } \
             NB_CHECK_LAUNCH();                                                                                            \
-            sub_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)in, (const T*)tmp, (T*)out, n);          \
+            { NB_PROF_BEGIN(st); sub_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)in, (const T*)tmp, (T*)out, n); NB_PROF_END("sub_kernel", st); }          \
             NB_CHECK_LAUNCH();                                                                                            \
         }                                                                                                                 \
         return NB_OK;                                                                                                     \
@@ -175,7 +175,7 @@ int nb_conv2d(int prec, const void* in, const double* kern, void* out, void* pla
     {                                                                                                                     \
         if (smem > 48 * 1024)                                                                                             \
             NB_CHECK_CUDA(cudaFuncSetAttribute(conv2d_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        conv2d_kernel<T><<<grid, 256, smem, st>>>((const T*)in, kern, (T*)out, (T*)planes, F, H, W, kh, kw, scale, norm, mask); \
+        { NB_PROF_BEGIN(st); conv2d_kernel<T><<<grid, 256, smem, st>>>((const T*)in, kern, (T*)out, (T*)planes, F, H, W, kh, kw, scale, norm, mask); NB_PROF_END("conv2d_kernel", st); } \
         NB_CHECK_LAUNCH();                                                                                                \
         return NB_OK;                                                                                                     \
     }
@@ -191,13 +191,13 @@ int nb_cast(int precIn, const void* in, int precOut, void* out, long long n, cud
     if (n == 0) return NB_OK;
     const unsigned grid = (unsigned)((n + 255) / 256);
     if (precIn == NB_PREC_F32 && precOut == NB_PREC_F64)
-        cast_kernel<float, double><<<grid, 256, 0, st>>>((const float*)in, (double*)out, n);
+        { NB_PROF_BEGIN(st); cast_kernel<float, double><<<grid, 256, 0, st>>>((const float*)in, (double*)out, n); NB_PROF_END("cast_kernel", st); }
     else if (precIn == NB_PREC_F64 && precOut == NB_PREC_F32)
-        cast_kernel<double, float><<<grid, 256, 0, st>>>((const double*)in, (float*)out, n);
+        { NB_PROF_BEGIN(st); cast_kernel<double, float><<<grid, 256, 0, st>>>((const double*)in, (float*)out, n); NB_PROF_END("cast_kernel", st); }
     else if (precIn == NB_PREC_F64 && precOut == NB_PREC_F64)
-        cast_kernel<double, double><<<grid, 256, 0, st>>>((const double*)in, (double*)out, n);
+        { NB_PROF_BEGIN(st); cast_kernel<double, double><<<grid, 256, 0, st>>>((const double*)in, (double*)out, n); NB_PROF_END("cast_kernel", st); }
     else if (precIn == NB_PREC_F32 && precOut == NB_PREC_F32)
-        cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, n);
+        { NB_PROF_BEGIN(st); cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, n); NB_PROF_END("cast_kernel", st); }
     else {
         nb_set_error("nb_cast: bad precision");
         return NB_ERR_ARG;
@@ -211,9 +211,9 @@ int nb_mask_to_u8(int precIn, const void* in, unsigned char* out, long long n, c
     if (n == 0) return NB_OK;
     const unsigned grid = (unsigned)((n + 255) / 256);
     if (precIn == NB_PREC_F32)
-        mask_u8_kernel<float><<<grid, 256, 0, st>>>((const float*)in, out, n);
+        { NB_PROF_BEGIN(st); mask_u8_kernel<float><<<grid, 256, 0, st>>>((const float*)in, out, n); NB_PROF_END("mask_u8_kernel", st); }
     else if (precIn == NB_PREC_F64)
-        mask_u8_kernel<double><<<grid, 256, 0, st>>>((const double*)in, out, n);
+        { NB_PROF_BEGIN(st); mask_u8_kernel<double><<<grid, 256, 0, st>>>((const double*)in, out, n); NB_PROF_END("mask_u8_kernel", st); }
     else {
         nb_set_error("nb_mask_to_u8: bad precision");
         return NB_ERR_ARG;

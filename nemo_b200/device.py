@@ -10,6 +10,22 @@ import numpy as np
 
 _OPS = {}
 
+# bytes moved between host and device through the boundary modules (bench.py reads these per step)
+TRAFFIC = {'h2d': 0, 'd2h': 0}
+
+
+def toHost(t):
+    """Device tensor -> numpy array (synchronising copy), counted in TRAFFIC['d2h']."""
+    if t.device.type != 'cpu':
+        TRAFFIC['d2h'] += int(t.numel()) * t.element_size()
+        t = t.detach().cpu()
+    return t.numpy()
+
+
+def countH2D(t):
+    TRAFFIC['h2d'] += int(t.numel()) * t.element_size()
+    return t
+
 
 def defaultPrecision():
     return os.environ.get('NEMO_B200_PRECISION', 'f64')
@@ -53,7 +69,7 @@ class DeviceArray(object):
 
     def numpy(self):
         if self._host is None:
-            h = self.tensor.detach().cpu().numpy()
+            h = toHost(self.tensor)
             if self._dtype is not None:
                 h = h.astype(self._dtype)
             self._host = h
@@ -115,5 +131,5 @@ def gaussFilter(data, sigmaY, sigmaX, subtract=False, ops=None):
     if squeeze:
         out = out[0]
     if wasHost:
-        return out.cpu().numpy()
+        return toHost(out)
     return out

@@ -54,6 +54,8 @@ class Ops(object):
                 t = t.to(want)
             if pinned:
                 t = t.pin_memory()
+            from . import device as _device
+            _device.countH2D(t)
             return t.to(self.device, non_blocking=True)
         return t.to(want).contiguous()
 

@@ -35,9 +35,9 @@ def _asImageBatch(mapData, ops):
 def _segment(ops, imgs, threshold, sign=1.0, wantArgmax=False):
     """label + moments for a batch [B, H, W].  Returns (labels tensor, nLabels host array, table host array)."""
     labels, nLabels = ops.label4(imgs, threshold, sign=sign)
-    n = nLabels.cpu().numpy()
+    n = device.toHost(nLabels)
     nmax = int(n.max()) if len(n) else 0
-    table = ops.label_moments(imgs, labels, nmax, sign=sign).cpu().numpy()
+    table = device.toHost(ops.label_moments(imgs, labels, nmax, sign=sign))
     return labels, n, table
 
 
@@ -82,7 +82,7 @@ def getObjectPositions(mapData, threshold, findCenterOfMass=True, ops=None):
     imgs = _asImageBatch(mapData, ops)
     labels, n, table = _segment(ops, imgs, threshold)
     objIDs, objPositions, objNumPix = _positionsFromTable(table[0], int(n[0]), imgs.shape[1:], findCenterOfMass)
-    return objIDs, objPositions, objNumPix, labels[0].cpu().numpy()
+    return objIDs, objPositions, objNumPix, device.toHost(labels[0])
 
 
 # -------------------------------------------------------------------------------------------------------------
@@ -95,8 +95,8 @@ def _gatherLabels(labels, bIdx, ys, xs):
     ys = np.clip(np.nan_to_num(np.asarray(ys, dtype=np.float64)), 0, H - 1).astype(np.int64)
     xs = np.clip(np.nan_to_num(np.asarray(xs, dtype=np.float64)), 0, W - 1).astype(np.int64)
     flat = (np.asarray(bIdx, dtype=np.int64) * H + ys) * W + xs
-    idx = torch.from_numpy(flat).to(labels.device)
-    return labels.reshape(-1)[idx].cpu().numpy()
+    idx = device.countH2D(torch.from_numpy(flat)).to(labels.device)
+    return device.toHost(labels.reshape(-1)[idx])
 
 
 def findObjectsBatch(ops, snMaps, wcsList, flagMaskList, labelList, tileNameList, threshold=3.0, minObjPix=3,
@@ -155,7 +155,7 @@ def findObjectsBatch(ops, snMaps, wcsList, flagMaskList, labelList, tileNameList
     # S/N at the object positions
     yx = np.stack([cy, cx], axis=1).astype(np.float64)
     if useInterpolator == True:
-        snr = ops.spline_eval(snMaps, ops.to_device(cb, ops.torch.int32), ops.to_device(yx, ops.torch.float64), sign=sign).cpu().numpy()
+        snr = device.toHost(ops.spline_eval(snMaps, ops.to_device(cb, ops.torch.int32), ops.to_device(yx, ops.torch.float64), sign=sign))
     else:
         snr = sign * _gatherValues(snMaps, cb, np.round(cy).astype(np.int64), np.round(cx).astype(np.int64))
     pos = 0
@@ -190,7 +190,7 @@ def _gatherValues(imgs, bIdx, ys, xs):
     import torch
     B, H, W = imgs.shape
     flat = (np.asarray(bIdx, dtype=np.int64) * H + ys) * W + xs
-    return imgs.reshape(-1)[torch.from_numpy(flat).to(imgs.device)].cpu().numpy().astype(np.float64)
+    return device.toHost(imgs.reshape(-1)[device.countH2D(torch.from_numpy(flat)).to(imgs.device)]).astype(np.float64)
 
 
 def _galacticLat(ra, dec):
@@ -226,11 +226,11 @@ def _valuesAt(ops, mapLike, xs, ys, useInterpolator, sign=1.0):
         return np.zeros(0)
     if useInterpolator == True:
         yx = np.stack([np.asarray(ys, dtype=np.float64), np.asarray(xs, dtype=np.float64)], axis=1)
-        return ops.spline_eval(imgs, None, ops.to_device(yx, ops.torch.float64), sign=sign).cpu().numpy()
+        return device.toHost(ops.spline_eval(imgs, None, ops.to_device(yx, ops.torch.float64), sign=sign))
     torch = ops.torch
     yi = torch.as_tensor(np.round(np.asarray(ys)).astype(np.int64), device=imgs.device)
     xi = torch.as_tensor(np.round(np.asarray(xs)).astype(np.int64), device=imgs.device)
-    return sign * imgs[0][yi, xi].cpu().numpy().astype(np.float64)
+    return sign * device.toHost(imgs[0][yi, xi]).astype(np.float64)
 
 
 def getSNRValues(catalog, SNMap, wcs, useInterpolator=True, invertMap=False, prefix=''):

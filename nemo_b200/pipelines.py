@@ -85,7 +85,7 @@ class TileBatch(object):
     def upload(self):
         """Host (pinned) -> device copies of this batch's inputs; asynchronous on the current stream."""
         ops = self.ops
-        self.dev = {k: v.to(ops.device, non_blocking=True) for k, v in self.host.items()}
+        self.dev = {k: device.countH2D(v).to(ops.device, non_blocking=True) for k, v in self.host.items()}
         self.dev['wmed'] = ops.median_weights(self.dev['weights'])
         return self.dev
 
@@ -180,6 +180,18 @@ def filterTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow
     return catalogDict, extras
 
 
+def catalogKeys(havePhotFilter, mapUnits, measureFluxes=True):
+    """Column list of the per-(tile, scale) catalogs, the same on every rank (what catalogListToTab is asked to write)."""
+    keys = [k for k in catalogs.COLUMN_NAMES if not k.startswith('ellipse_')]   # measureShapes is not supported
+    prefixes = ['', 'fixed_'] if havePhotFilter else ['']
+    if havePhotFilter:
+        keys.append('fixed_SNR')
+    if measureFluxes:
+        for prefix in prefixes:
+            keys += [prefix + k for k in FLUX_KEYS[mapUnits]]
+    return keys
+
+
 def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measureFluxes=True, invertMap=False):
     """K9-K11 for all (tile, scale) images, then the rows of every catalog (pipelines.py:251-284)."""
     nT, S = batch.nT, len(filtersList)
@@ -213,11 +225,11 @@ def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measu
 
         def sample(imgs, idxT, sign=1.0):
             if useInterp:
-                return ops.spline_eval(imgs, idxT, yx, sign=sign).cpu().numpy()
+                return device.toHost(ops.spline_eval(imgs, idxT, yx, sign=sign))
             torch = ops.torch
             yi = torch.as_tensor(np.round(ys).astype(np.int64), device=imgs.device)
             xi = torch.as_tensor(np.round(xs).astype(np.int64), device=imgs.device)
-            return sign * imgs[idxT.long(), yi, xi].cpu().numpy().astype(np.float64)
+            return sign * device.toHost(imgs[idxT.long(), yi, xi]).astype(np.float64)
 
         vals = {}
         if photScale is not None:
@@ -255,13 +267,7 @@ def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measu
                         else:
                             r[prefix + 'fluxJy'] = 0.0
                             r[prefix + 'err_fluxJy'] = 0.0
-    keys = list(catalogs.COLUMN_NAMES)
-    prefixes = ['', 'fixed_'] if photScale is not None else ['']
-    if photScale is not None:
-        keys.append('fixed_SNR')
-    if measureFluxes:
-        for prefix in prefixes:
-            keys += [prefix + k for k in FLUX_KEYS[mapUnits]]
+    keys = catalogKeys(photScale is not None, mapUnits, measureFluxes)
     catalogDict = {}
     for o in range(nT * S):
         label = labelList[o] + "#" + tileList[o]
@@ -285,6 +291,17 @@ def _orderedFilters(parDict):
     return filtersList
 
 
+def stageTiles(config, tilesPerBatch=8, precision=None):
+    """Copies this rank's tiles into pinned host staging buffers, `tilesPerBatch` tiles per batch, and keeps them on
+    `config` so that repeated runs (source-injection iterations, benchmarks) start from pinned memory."""
+    ops = device.getOps(precision)
+    tileNames = list(config.tileNames)
+    config._staged = {'tilesPerBatch': tilesPerBatch, 'precision': ops.precision,
+                      'batches': [TileBatch(ops, tileNames[i:i + tilesPerBatch], config.tileMaps)
+                                  for i in range(0, len(tileNames), tilesPerBatch)]}
+    return config._staged['batches']
+
+
 def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=False, measureFluxes=True, invertMap=False,
                               verbose=True, tilesPerBatch=8, precision=None, comm=None):
     """Runs the map filtering and catalog construction steps for this rank's tiles and returns the optimal catalog
@@ -295,32 +312,41 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     ``photometry.findObjects`` directly for anything else.
     """
     if useCachedFilters or useCachedRMSMap:
-        raise Exception("cached filters / RMS maps: use nemo_b200.injection.InjectionRunner")
+        raise Exception("cached filters / RMS maps are not handled by the batched driver: use filters.filterMaps(useCachedFilter=True)")
     ops = device.getOps(precision)
     parDict = config.parDict
     filtersList = _orderedFilters(parDict)
     catalogDict = {}
     noiseTables = {}
-    templates = None
-    tileNames = list(config.tileNames)
-    for i in range(0, len(tileNames), tilesPerBatch):
-        names = tileNames[i:i + tilesPerBatch]
+    staged = getattr(config, '_staged', None)
+    if staged is None or staged['tilesPerBatch'] != tilesPerBatch or staged['precision'] != ops.precision:
+        batches = stageTiles(config, tilesPerBatch, precision)
+    else:
+        batches = staged['batches']
+    templates = getattr(config, '_templates', None)
+    for batch in batches:
+        names = batch.tileNames
         if verbose:
             print(">>> [rank = %d] Making filtered maps - tiles %s" % (config.rank, names))
-        batch = TileBatch(ops, names, config.tileMaps)
         if templates is None:
             templates = FilterSetTemplates(ops, filtersList, batch.mapDicts[0], tileName=names[0])
+            config._templates = templates
+        batch.upload()
         cd, extras = filterTileBatch(ops, batch, filtersList, templates, parDict,
                                      undoPixelWindow=parDict.get('undoPixelWindow', True), measureFluxes=measureFluxes,
                                      invertMap=invertMap)
+        batch.dev = None
         catalogDict.update(cd)
-        tab = extras['noiseTable'].cpu().numpy()
+        tab = device.toHost(extras['noiseTable'])
         for o in range(tab.shape[0]):
             noiseTables[filtersList[o % len(filtersList)]['label'] + "#" + names[o // len(filtersList)]] = tab[o]
     optimalCatalog = catalogs.makeOptimalCatalog(catalogDict, constraintsList=parDict.get('catalogCuts', []))
     if comm is not None and comm.size > 1:
         from . import distributed
-        optimalCatalog = distributed.allGatherCatalog(comm, optimalCatalog, filtersList, config.allTileNames)
+        havePhot = parDict.get('photFilter') is not None and any(f['label'] == parDict['photFilter'] for f in filtersList)
+        keys = catalogKeys(havePhot, templates.outputUnits, measureFluxes)
+        optimalCatalog = distributed.allGatherCatalog(comm, optimalCatalog, keys)
+        noiseTables = distributed.gatherNoiseTables(comm, noiseTables)
     config.catalogDict = catalogDict
     config.noiseTables = noiseTables
     return optimalCatalog

@@ -16,17 +16,47 @@ from . import signals_ref as signals
 from .wcs_stub import j2000ToGalactic
 
 
+def _makeRA(myRADeg):
+    """catalogs.py:295-313."""
+    hours = (myRADeg / 360) * 24
+    strHours = ("%.10f" % (hours))
+    if hours < 10:
+        sHours = "0" + strHours[0]
+    else:
+        sHours = strHours[:2]
+    mins = float(strHours[strHours.index("."):]) * 60
+    strMins = ("%.10f" % (mins))
+    if mins < 10:
+        sMins = "0" + strMins[:3]
+    else:
+        sMins = strMins[:4]
+    return (sHours + sMins)
+
+
+def _makeDec(myDecDeg):
+    """catalogs.py:316-346."""
+    text = str(float(myDecDeg))
+    mins = float(text[text.index("."):]) * 60
+    if mins < 10:
+        sMins = "0" + str(mins)[:1]
+    else:
+        sMins = str(mins)[:2]
+    if myDecDeg > 0:
+        if myDecDeg < 10:
+            sDeg = "0" + text[0]
+        else:
+            sDeg = text[:2]
+        return "+" + sDeg + sMins
+    if myDecDeg > -10:
+        sDeg = "-0" + text[1]
+    else:
+        sDeg = text[:3]
+    return str(sDeg + sMins)
+
+
 def makeName(RADeg, decDeg, prefix='ACT-CL'):
-    """catalogs.py:259-274 (IAU style JHHMM.m+DDMM, truncated not rounded)."""
-    ra = RADeg / 15.0
-    h = int(ra)
-    m = (ra - h) * 60.0
-    raStr = "%02d%04.1f" % (h, np.floor(m * 10) / 10.0)
-    sign = '+' if decDeg > 0 else '-'
-    d = abs(decDeg)
-    dd = int(d)
-    dm = int((d - dd) * 60.0)
-    return prefix + " J" + raStr + sign + "%02d%02d" % (dd, dm)
+    """catalogs.py:259-274: prefix JHHMM.m+/-DDMM, digits cut from the printed values."""
+    return prefix + " J" + _makeRA(float(RADeg)) + _makeDec(float(decDeg))
 
 
 def getObjectPositions(mapData, threshold, findCenterOfMass=True):

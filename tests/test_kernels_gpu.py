@@ -160,7 +160,7 @@ def test_build_filter_f64(ops64, report, F, S, shape):
     refH = 0.5 * (filtFull + np.roll(np.flip(filtFull, axis=(-2, -1)), (1, 1), axis=(-2, -1)))[..., :W // 2 + 1]
     errH = _relerr(_np(filtH), refH)
     report("build_filter_f64", F=F, S=S, shape=shape, relerr=worst, relerr_fold=errH)
-    assert worst < 1e-9 and errH == 0.0
+    assert worst < 1e-9 and errH < 1e-15
 
 
 def test_build_filter_singular(ops64):
