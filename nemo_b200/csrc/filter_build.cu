@@ -173,11 +173,19 @@ __global__ void __launch_bounds__(256) build_filter_kernel(const double* __restr
     const int sidx = sigPerTile ? o : (o % S);
     const int kym = (H - ky) % H, kxm = (W - kx) % W;
     const double* cv = cov + (size_t)tile * P * H * W;
-    double rhs[F], c1[P], c2[P], x1[F], x2[F];
+    double rhs[F], rhs2[F], c1[P], c2[P], x1[F], x2[F];
+    // the mirror mode -k has the conjugate template value, hence the same modulus, except on the self-conjugate
+    // columns kx = 0 and W/2 where it is a stored element of its own (equal only up to FFT rounding)
+    const bool ownMirror = (kx == 0 || kx == W / 2);
 #pragma unroll
     for (int f = 0; f < F; ++f) {
         const C2 v = fsig[(((size_t)sidx * F + f) * H + ky) * Wc + kx];
         rhs[f] = __dmul_rn(fw.w[f], hypot((double)v.x, (double)v.y));  // np.abs of a complex number is hypot
+        rhs2[f] = rhs[f];
+        if (ownMirror) {
+            const C2 vm = fsig[(((size_t)sidx * F + f) * H + kym) * Wc + kx];
+            rhs2[f] = __dmul_rn(fw.w[f], hypot((double)vm.x, (double)vm.y));
+        }
     }
 #pragma unroll
     for (int p = 0; p < P; ++p) {
@@ -185,7 +193,7 @@ __global__ void __launch_bounds__(256) build_filter_kernel(const double* __restr
         c2[p] = cv[((size_t)p * H + kym) * W + kxm];
     }
     solve_sym<F>(c1, rhs, x1);
-    solve_sym<F>(c2, rhs, x2);
+    solve_sym<F>(c2, rhs2, x2);
 #pragma unroll
     for (int f = 0; f < F; ++f) {
         filtH[(((size_t)o * F + f) * H + ky) * Wc + kx] = (T)(0.5 * __dadd_rn(x1[f], x2[f]));

@@ -5,6 +5,7 @@
 //   nb_snr_from_rms   : S/N from a cached RMS map                                     pipelines.py:216-228
 #include "nemo_b200_internal.h"
 #include <math.h>
+#include <algorithm>
 
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
@@ -146,7 +147,7 @@ __device__ double select_kth(const T* __restrict__ m, const T* __restrict__ wm, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(CR_THREADS) cell_rms_kernel(const T* __restrict__ map, const T* __restrict__ wmed, int S, int H,
+__global__ void __launch_bounds__(CR_THREADS) cell_rms_stream_kernel(const T* __restrict__ map, const T* __restrict__ wmed, int S, int H,
                                                               int W, const Chunks ch, int nx,
                                                               int ov, int numBins, double* __restrict__ table,
                                                               double* __restrict__ edges) {
@@ -287,6 +288,388 @@ __global__ void __launch_bounds__(CR_THREADS) cell_rms_kernel(const T* __restric
         }
         if (threadIdx.x == 0) tab[b] = rms;
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K6, on-chip version.  One CTA per (cell, image) loads the cell ONCE; every later pass (order statistics of the
+// weights, the two-pass mean / std and the ten clipping iterations of every weight bin) runs on data held in
+// registers (OC_PPT slots per thread) and, for what does not fit there, in shared memory.  The slots first hold
+// the order-preserving integer key of each good pixel's weight (for the percentile bin edges), then the pixel
+// value.  Cells larger than the on-chip capacity use cell_rms_stream_kernel above.
+#define OC_THREADS 512
+#define OC_WARPS (OC_THREADS / 32)
+#define OC_PPT 24
+#define OC_GROUPS 16   // order statistics resolved together by the radix select (one warp each)
+#define OC_MAXBINS 64
+
+template <typename T> struct KeyOf;
+template <> struct KeyOf<double> {
+    typedef unsigned long long type;
+    static constexpr int BITS = 64;
+    static __device__ __forceinline__ type enc(double v) { return enc_w(v); }
+    static __device__ __forceinline__ double dec(type k) { return dec_w(k); }
+    static __device__ __forceinline__ type fromValue(double v) { return (type)__double_as_longlong(v); }
+    static __device__ __forceinline__ double toValue(type k) { return __longlong_as_double((long long)k); }
+};
+template <> struct KeyOf<float> {
+    typedef unsigned int type;
+    static constexpr int BITS = 32;
+    static __device__ __forceinline__ type enc(float v) {
+        const unsigned int b = __float_as_uint(v);
+        return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    }
+    static __device__ __forceinline__ double dec(type e) {
+        const unsigned int b = (e & 0x80000000u) ? (e & 0x7fffffffu) : ~e;
+        return (double)__uint_as_float(b);
+    }
+    static __device__ __forceinline__ type fromValue(float v) { return __float_as_uint(v); }
+    static __device__ __forceinline__ double toValue(type k) { return (double)__uint_as_float(k); }
+};
+
+struct OcBinState {   // per weight bin, shared memory
+    double mean, rms, thr, pivot, prevC, prevS;
+    int done;
+    int pad;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T* __restrict__ map, const T* __restrict__ wmed, int S,
+                                                                        int H, int W, const Chunks ch, int nx, int ov, int numBins,
+                                                                        double* __restrict__ table, double* __restrict__ edges,
+                                                                        int smemSlots) {
+    typedef KeyOf<T> K;
+    typedef typename K::type key_t;
+    constexpr key_t SENT = ~(key_t)0;
+    extern __shared__ __align__(16) unsigned char oc_smem[];
+    // layout: red [OC_WARPS][numBins][3] f64 | edges [numBins + 1] f64 | state [numBins] | warpBins [OC_WARPS] u64 |
+    //         target prefix [OC_GROUPS] u64, target rank [OC_GROUPS] i64, group of target [OC_GROUPS] int, hist [OC_GROUPS][256] int |
+    //         slots [smemSlots] key_t | bins [OC_PPT * OC_THREADS + smemSlots] u8
+    double* s_red = reinterpret_cast<double*>(oc_smem);
+    double* s_edges = s_red + OC_WARPS * numBins * 3;
+    OcBinState* s_state = reinterpret_cast<OcBinState*>(s_edges + numBins + 1);
+    unsigned long long* s_warpBins = reinterpret_cast<unsigned long long*>(s_state + numBins);
+    unsigned long long* s_tprefix = s_warpBins + OC_WARPS;
+    long long* s_trank = reinterpret_cast<long long*>(s_tprefix + OC_GROUPS);
+    int* s_tgroup = reinterpret_cast<int*>(s_trank + OC_GROUPS);
+    int* s_hist = s_tgroup + OC_GROUPS;
+    key_t* s_slots = reinterpret_cast<key_t*>(s_hist + OC_GROUPS * 256);
+    unsigned char* s_bins = reinterpret_cast<unsigned char*>(s_slots + smemSlots);
+    __shared__ double s_scr[2 * CR_WARPS];
+    __shared__ int s_nGroups;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int cell = blockIdx.x, img = blockIdx.y;
+    const CellGeom g = cell_geom(ch, cell / nx, cell % nx, ov, H, W);
+    const T* m = map + (size_t)img * H * W;
+    const T* wm = wmed + (size_t)(img / S) * H * W;
+    const int cw = g.x1 - g.x0;
+    const int n = (g.y1 - g.y0) * cw;
+    constexpr int NREG = OC_PPT * OC_THREADS;
+    double* tab = table + ((size_t)img * gridDim.x + cell) * numBins;
+    double* edg = edges + ((size_t)img * gridDim.x + cell) * (numBins + 1);
+
+    key_t reg[OC_PPT];
+    // ---- load: weight keys of the good pixels ------------------------------------------------------------
+    double cnt = 0, dummy = 0, wmin = INFINITY, wmax = -INFINITY;
+    auto loadKey = [&](int e) -> key_t {
+        const int r = e / cw, c = e - r * cw;
+        const size_t off = (size_t)(g.y0 + r) * W + g.x0 + c;
+        if (m[off] == (T)0) return SENT;
+        const T w = wm[off];
+        cnt += 1.0;
+        wmin = fmin(wmin, (double)w);
+        wmax = fmax(wmax, (double)w);
+        return K::enc(w);
+    };
+#pragma unroll
+    for (int j = 0; j < OC_PPT; ++j) {
+        const int e = j * OC_THREADS + tid;
+        reg[j] = (e < n) ? loadKey(e) : SENT;
+    }
+    for (int e = NREG + tid; e < n; e += OC_THREADS) s_slots[e - NREG] = loadKey(e);
+    block_sum2(cnt, dummy, s_scr);
+    block_minmax(wmin, wmax, s_scr);
+    if (cnt == 0) {  // filters.py:446-447
+        for (int b = tid; b < numBins; b += OC_THREADS) tab[b] = 0.0;
+        for (int b = tid; b <= numBins; b += OC_THREADS) edg[b] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    const long long nGood = (long long)cnt;
+
+    // ---- bin edges: np.percentile(weights[good], b * 100 / numBins), max + 1e-6  (filters.py:450-454) -----------
+    if (tid == 0) {
+        s_edges[0] = wmin;
+        s_edges[numBins] = wmax + 1e-6;
+    }
+    if (numBins > 1 && wmin == wmax) {  // constant weights: every percentile is that constant
+        for (int b = 1 + tid; b < numBins; b += OC_THREADS) s_edges[b] = wmin;
+    } else if (numBins > 1) {
+        // skip the leading bits every key shares
+        const key_t kmin = K::enc((T)wmin), kmax = K::enc((T)wmax);
+        int nbits = 0;
+        {
+            key_t x = kmin ^ kmax;
+            while (x) {
+                ++nbits;
+                x >>= 1;
+            }
+        }
+        const int npass = (nbits + 7) / 8;
+        const key_t lowMask = (8 * npass >= K::BITS) ? SENT : (((key_t)1 << (8 * npass)) - 1);
+        const int nTargets = 2 * (numBins - 1);   // ranks lo_b, hi_b for b = 1..numBins-1, ascending
+        for (int t0 = 0; t0 < nTargets; t0 += OC_GROUPS) {
+            const int nt = min(OC_GROUPS, nTargets - t0);
+            if (tid < nt) {
+                const int t = t0 + tid, b = 1 + t / 2;
+                const double p = (double)b * (100.0 / (double)numBins);  // np.arange(0, 100, 100/numBins)[b]
+                const double q = p / 100.0;
+                const double nn = (double)nGood;
+                const double vi = nn * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0;  // numpy's virtual index, method 'linear'
+                long long lo = (long long)floor(vi), hi = lo + 1;
+                lo = max(0LL, min(lo, nGood - 1));
+                hi = max(0LL, min(hi, nGood - 1));
+                s_tprefix[tid] = (unsigned long long)(kmin & ~lowMask);
+                s_trank[tid] = (t & 1) ? hi : lo;
+            }
+            key_t maskbits = ~lowMask;
+            for (int pass = 0; pass < npass; ++pass) {
+                const int shift = 8 * (npass - 1 - pass);
+                __syncthreads();
+                // groups of targets that still share a prefix (targets ascend, so equal prefixes are adjacent)
+                if (tid == 0) {
+                    int ng = 0;
+                    for (int t = 0; t < nt; ++t) {
+                        if (t == 0 || s_tprefix[t] != s_tprefix[t - 1]) ++ng;
+                        s_tgroup[t] = ng - 1;
+                    }
+                    s_nGroups = ng;
+                }
+                for (int i = tid; i < OC_GROUPS * 256; i += OC_THREADS) s_hist[i] = 0;
+                __syncthreads();
+                const int ng = s_nGroups;
+                auto count = [&](key_t key) {
+                    int code = -1;
+                    if (key != SENT) {
+                        const unsigned long long pre = (unsigned long long)(key & maskbits);
+                        // the group whose prefix equals pre, if any (prefixes of distinct groups ascend)
+                        int loT = 0, hiT = nt - 1;
+                        while (loT < hiT) {
+                            const int mid = (loT + hiT) >> 1;
+                            if (s_tprefix[mid] < pre) loT = mid + 1; else hiT = mid;
+                        }
+                        if (s_tprefix[loT] == pre) code = s_tgroup[loT] * 256 + (int)((key >> shift) & (key_t)255);
+                    }
+                    // one shared-memory atomic per distinct (group, digit) in the warp
+                    const unsigned peers = __match_any_sync(0xffffffffu, code);
+                    if (code >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(&s_hist[code], __popc(peers));
+                };
+                (void)ng;
+#pragma unroll
+                for (int j = 0; j < OC_PPT; ++j) count(reg[j]);
+                for (int e0 = NREG; e0 < n; e0 += OC_THREADS) {   // whole warps stay converged for __match_any_sync
+                    const int e = e0 + tid;
+                    count(e < n ? s_slots[e - NREG] : SENT);
+                }
+                __syncthreads();
+                // one warp per target: locate the digit that holds its rank
+                if (wid < nt) {
+                    const int* hst = s_hist + s_tgroup[wid] * 256;
+                    int loc[8], tot = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        loc[i] = hst[lane * 8 + i];
+                        tot += loc[i];
+                    }
+                    int inc = tot;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += t;
+                    }
+                    const long long kk = s_trank[wid];
+                    const long long before = (long long)(inc - tot);
+                    const bool mine = (kk >= before) && (kk < before + tot);
+                    __syncwarp();
+                    if (mine) {
+                        long long r = kk - before;
+                        int d = 0;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (d == i && r >= loc[i]) {
+                                r -= loc[i];
+                                d = i + 1;
+                            }
+                        }
+                        if (d > 7) d = 7;
+                        s_tprefix[wid] |= ((unsigned long long)(lane * 8 + d)) << shift;
+                        s_trank[wid] = r;
+                    }
+                }
+                maskbits |= (key_t)255 << shift;
+            }
+            __syncthreads();
+            // pairs (lo, hi) of this batch -> interpolated percentiles
+            if (tid < nt && (tid & 1) == 0) {
+                const int t = t0 + tid, b = 1 + t / 2;
+                const double a = K::dec((key_t)s_tprefix[tid]);
+                const double bb = K::dec((key_t)s_tprefix[tid + 1]);
+                const double p = (double)b * (100.0 / (double)numBins);
+                const double q = p / 100.0;
+                const double nn = (double)nGood;
+                const double vi = nn * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0;
+                const double gmm = vi - floor(vi);
+                const double diff = bb - a;
+                double res = a + diff * gmm;  // numpy _lerp
+                if (gmm >= 0.5) res = bb - diff * (1.0 - gmm);
+                if (gmm == 0.0) res = a;
+                s_edges[b] = res;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    for (int b = tid; b <= numBins; b += OC_THREADS) edg[b] = s_edges[b];
+
+    // ---- bin index of every good pixel, then the slots take the pixel values -----------------------------------
+    unsigned long long present = 0ULL;
+    auto toValue = [&](key_t key, int e) -> key_t {
+        unsigned char bin = 255;
+        if (key != SENT) {
+            const double w = K::dec(key);
+            for (int b = 0; b < numBins; ++b) {
+                if (w >= s_edges[b] && w < s_edges[b + 1]) {
+                    bin = (unsigned char)b;
+                    break;
+                }
+            }
+        }
+        s_bins[e] = bin;
+        if (bin == 255) return K::fromValue((T)0);
+        present |= 1ULL << bin;
+        const int r = e / cw, c = e - r * cw;
+        return K::fromValue(m[(size_t)(g.y0 + r) * W + g.x0 + c]);
+    };
+#pragma unroll
+    for (int j = 0; j < OC_PPT; ++j) {
+        const int e = j * OC_THREADS + tid;
+        if (e < n) reg[j] = toValue(reg[j], e);
+        else reg[j] = K::fromValue((T)0);
+    }
+    for (int e = NREG + tid; e < n; e += OC_THREADS) s_slots[e - NREG] = toValue(s_slots[e - NREG], e);
+    {
+        unsigned int plo = (unsigned int)present, phi = (unsigned int)(present >> 32);
+        plo = __reduce_or_sync(0xffffffffu, plo);
+        phi = __reduce_or_sync(0xffffffffu, phi);
+        present = ((unsigned long long)phi << 32) | plo;   // bins any lane of this warp holds
+        if (lane == 0) s_warpBins[wid] = present;
+    }
+    // register copies of this thread's bin indices, four per word
+    unsigned int rbin[(OC_PPT + 3) / 4];
+#pragma unroll
+    for (int j4 = 0; j4 < (OC_PPT + 3) / 4; ++j4) {
+        unsigned int wv = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int j = j4 * 4 + i;
+            const int e = j * OC_THREADS + tid;
+            const unsigned int bv = (j < OC_PPT && e < n) ? (unsigned int)s_bins[e] : 255u;
+            wv |= bv << (8 * i);
+        }
+        rbin[j4] = wv;
+    }
+    if (tid < numBins) {
+        OcBinState st;
+        st.mean = 0.0; st.rms = 0.0; st.thr = INFINITY; st.pivot = 0.0; st.prevC = -1.0; st.prevS = 0.0; st.done = 0; st.pad = 0;
+        s_state[tid] = st;
+    }
+    __syncthreads();
+
+    // ---- sweeps: -2 mean, -1 std about the mean, 0..9 clipping iterations (filters.py:466-477) -----------------
+    for (int it = -2; it < 10; ++it) {
+        unsigned long long todo = present;
+        while (todo) {
+            const int b = __ffsll((long long)todo) - 1;
+            todo &= todo - 1;
+            if (s_state[b].done) continue;
+            const double thr = s_state[b].thr, piv = s_state[b].pivot;
+            double c0 = 0, s0 = 0, q0 = 0, c1 = 0, s1 = 0, q1 = 0;
+#pragma unroll
+            for (int j = 0; j < OC_PPT; ++j) {
+                const unsigned int bj = (rbin[j >> 2] >> (8 * (j & 3))) & 255u;
+                const double v = K::toValue(reg[j]);
+                if (bj == (unsigned int)b && fabs(v) < thr) {
+                    const double d = v - piv;
+                    if (j & 1) {
+                        c1 += 1.0; s1 += v; q1 += d * d;
+                    } else {
+                        c0 += 1.0; s0 += v; q0 += d * d;
+                    }
+                }
+            }
+            for (int e = NREG + tid; e < n; e += OC_THREADS) {
+                if (s_bins[e] == b) {
+                    const double v = K::toValue(s_slots[e - NREG]);
+                    if (fabs(v) < thr) {
+                        const double d = v - piv;
+                        c0 += 1.0; s0 += v; q0 += d * d;
+                    }
+                }
+            }
+            c0 = warp_sum(c0 + c1);
+            s0 = warp_sum(s0 + s1);
+            q0 = warp_sum(q0 + q1);
+            if (lane == 0) {
+                double* r = s_red + ((size_t)wid * numBins + b) * 3;
+                r[0] = c0; r[1] = s0; r[2] = q0;
+            }
+        }
+        __syncthreads();
+        if (tid < numBins && !s_state[tid].done) {
+            const int b = tid;
+            double c = 0, s = 0, q = 0;
+            for (int w = 0; w < OC_WARPS; ++w) {
+                if ((s_warpBins[w] >> b) & 1ULL) {
+                    const double* r = s_red + ((size_t)w * numBins + b) * 3;
+                    c += r[0]; s += r[1]; q += r[2];
+                }
+            }
+            OcBinState st = s_state[b];
+            if (it == -2) {
+                if (c == 0) {
+                    st.rms = 0.0;
+                    st.done = 1;
+                } else {
+                    st.mean = s / c;
+                    st.pivot = st.mean;
+                }
+            } else if (it == -1) {
+                st.rms = sqrt(q / c);
+                st.thr = fabs(st.mean + 3.0 * st.rms);
+            } else if (c == 0) {
+                st.done = 1;   // "if mask.sum() > 0": nothing changes now, and nothing will in later passes
+            } else {
+                const double mean = s / c;
+                const double dm = mean - st.pivot;
+                double var = q / c - dm * dm;
+                if (var < 0) var = 0;
+                // same sample as in the previous pass: a fixed point, the remaining passes change nothing
+                const bool fixed = (c == st.prevC) && (s == st.prevS);
+                st.mean = mean;
+                st.rms = sqrt(var);
+                st.pivot = mean;
+                st.thr = fabs(mean + 3.0 * st.rms);
+                st.prevC = c;
+                st.prevS = s;
+                if (fixed) st.done = 1;
+            }
+            s_state[b] = st;
+        }
+        __syncthreads();
+        bool allDone = true;
+        for (int b = 0; b < numBins; ++b) allDone = allDone && (s_state[b].done != 0);
+        if (allDone) break;
+    }
+    for (int b = tid; b < numBins; b += OC_THREADS) tab[b] = s_state[b].rms;
 }
 
 // every pixel takes the RMS of the last cell (raster order) that covers it, has rms > 0 and whose weight bin holds it
@@ -432,8 +815,25 @@ static int cell_rms_t(const void* map, const void* wmed, int nImg, int S, int H,
     memset(&ch, 0, sizeof(ch));
     for (int i = 0; i <= ny; ++i) ch.y[i] = yChunks[i];
     for (int i = 0; i <= nx; ++i) ch.x[i] = xChunks[i];
-    { NB_PROF_BEGIN(st); cell_rms_kernel<T><<<dim3(ny * nx, nImg), CR_THREADS, sizeof(double) * (numBins + 1), st>>>(
-        (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges); NB_PROF_END("cell_rms_kernel", st); }
+    // largest cell (with its overlap margins) decides between the on-chip kernel and the streaming one
+    int maxH = 0, maxW = 0;
+    for (int i = 0; i < ny; ++i) maxH = std::max(maxH, std::min(ch.y[i + 1] + ov, H) - std::max(ch.y[i] - ov, 0));
+    for (int k = 0; k < nx; ++k) maxW = std::max(maxW, std::min(ch.x[k + 1] + ov, W) - std::max(ch.x[k] - ov, 0));
+    const long long maxCell = (long long)maxH * maxW;
+    const long long nReg = (long long)OC_PPT * OC_THREADS;
+    const long long smemSlots = maxCell > nReg ? ((maxCell - nReg + 7) / 8) * 8 : 0;
+    const size_t ocBytes = sizeof(double) * ((size_t)OC_WARPS * numBins * 3 + numBins + 1) + sizeof(OcBinState) * numBins +
+                           sizeof(unsigned long long) * OC_WARPS + 16 * OC_GROUPS + sizeof(int) * OC_GROUPS +
+                           sizeof(int) * OC_GROUPS * 256 + sizeof(typename KeyOf<T>::type) * (size_t)smemSlots +
+                           (size_t)(nReg + smemSlots);
+    if (ocBytes <= 227 * 1024 && numBins <= OC_MAXBINS) {
+        NB_CHECK_CUDA(cudaFuncSetAttribute(cell_rms_onchip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ocBytes));
+        { NB_PROF_BEGIN(st); cell_rms_onchip_kernel<T><<<dim3(ny * nx, nImg), OC_THREADS, ocBytes, st>>>(
+            (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges, (int)smemSlots); NB_PROF_END("cell_rms_onchip_kernel", st); }
+    } else {
+        { NB_PROF_BEGIN(st); cell_rms_stream_kernel<T><<<dim3(ny * nx, nImg), CR_THREADS, sizeof(double) * (numBins + 1), st>>>(
+            (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges); NB_PROF_END("cell_rms_stream_kernel", st); }
+    }
     NB_CHECK_LAUNCH();
     { NB_PROF_BEGIN(st); paint_rms_kernel<T><<<dim3((W + 255) / 256, H, nImg), 256, 0, st>>>((const T*)wmed, S, H, W, ch, ny, nx, ov, numBins, table,
                                                                          edges, (T*)rms); NB_PROF_END("paint_rms_kernel", st); }

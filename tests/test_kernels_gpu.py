@@ -236,14 +236,9 @@ def _chunks(n, gridSize):
     return np.linspace(0, n, int(n / gridSize + 1), dtype=int)
 
 
-@pytest.mark.parametrize("numBins", [1, 4])
-@pytest.mark.parametrize("shape", [(256, 256), (300, 420)])
-def test_cell_rms_f64(ops64, report, numBins, shape):
-    rng = np.random.default_rng(10 + numBins)
+def _noise_case(shape, seed, constantWeights=False):
+    rng = np.random.default_rng(seed)
     H, W = shape
-    pixDeg = 0.5 / 60
-    gridArcmin = 20.0
-    gridSize = int(round((gridArcmin / 60.) / pixDeg))
     sig = 1.0 + 2.0 * (np.arange(W)[None, :] > W // 2) + 0.2 * rng.random((H, W))
     m = rng.standard_normal((H, W)) * sig
     m[rng.random((H, W)) < 0.002] += 30.0           # outliers for the clip
@@ -251,18 +246,66 @@ def test_cell_rms_f64(ops64, report, numBins, shape):
     m[:, -9:] = 0
     m[100:130, 50:200] = 0                          # a hole covering whole rows of some cells
     w1 = 1.0 / sig ** 2
+    if constantWeights:
+        w1 = np.full((H, W), 0.25)
     w2 = w1 * (0.5 + rng.random((H, W)))
     w1[m == 0] = 0
-    weights = [w1, w2]
-    ref = _oracle_noise(m, weights, pixDeg, gridArcmin, numBins if numBins > 1 else None)
-    wm = ops64.median_weights(ops64.to_device(np.array(weights)[None]))
-    assert np.array_equal(_np(wm)[0], np.median(np.array(weights), axis=0))
-    rms, table, edges = ops64.cell_rms(ops64.to_device(m[None]), wm, 1, _chunks(H, gridSize), _chunks(W, gridSize), gridSize // 2, numBins)
-    got = _np(rms)[0]
+    return m, [w1, w2] if not constantWeights else [w1]
+
+
+def _run_cell_rms(ops, m, weights, gridArcmin, numBins):
+    H, W = m.shape
+    pixDeg = 0.5 / 60
+    wm = ops.median_weights(ops.to_device(np.array(weights)[None]))
+    if gridArcmin is None:
+        yc, xc, ov = np.array([0, H]), np.array([0, W]), 0
+    else:
+        gridSize = int(round((gridArcmin / 60.) / pixDeg))
+        yc, xc, ov = _chunks(H, gridSize), _chunks(W, gridSize), gridSize // 2
+    rms, table, edges = ops.cell_rms(ops.to_device(m[None]), wm, 1, yc, xc, ov, numBins)
+    return _np(rms)[0], _np(wm)[0]
+
+
+@pytest.mark.parametrize("numBins", [1, 4, 8])
+@pytest.mark.parametrize("shape,gridArcmin", [((256, 256), 20.0), ((300, 420), 20.0), ((512, 640), 40.0), ((200, 256), None)])
+def test_cell_rms_f64(ops64, report, numBins, shape, gridArcmin):
+    """Cells of 80 x 80 (registers only), 160 x 160 (registers + shared memory) and a single whole-map cell (streaming
+    kernel), against the oracle's makeNoiseMap."""
+    m, weights = _noise_case(shape, 10 + numBins)
+    ref = _oracle_noise(m, weights, 0.5 / 60, gridArcmin, numBins if numBins > 1 else None)
+    got, wm = _run_cell_rms(ops64, m, weights, gridArcmin, numBins)
+    assert np.array_equal(wm, np.median(np.array(weights), axis=0))
     err = _relerr(got, ref)
-    report("cell_rms_f64", numBins=numBins, shape=shape, relerr=err, zeros_equal=int(np.array_equal(got == 0, ref == 0)))
+    report("cell_rms_f64", numBins=numBins, shape=shape, grid=gridArcmin, relerr=err, zeros_equal=int(np.array_equal(got == 0, ref == 0)))
     assert np.array_equal(got == 0, ref == 0)
     assert err < 1e-12
+
+
+@pytest.mark.parametrize("numBins", [1, 8])
+def test_cell_rms_constant_weights(ops64, report, numBins):
+    """All weights equal: every percentile edge collapses onto the same value and only the last bin holds pixels."""
+    m, weights = _noise_case((256, 320), 3, constantWeights=True)
+    ref = _oracle_noise(m, weights, 0.5 / 60, 20.0, numBins if numBins > 1 else None)
+    got, _ = _run_cell_rms(ops64, m, weights, 20.0, numBins)
+    assert np.array_equal(got == 0, ref == 0)
+    assert _relerr(got, ref) < 1e-12
+
+
+@pytest.mark.parametrize("numBins,gridArcmin", [(1, 20.0), (8, 40.0)])
+def test_cell_rms_f32(ops32, report, numBins, gridArcmin):
+    """fp32 storage: the oracle is fed the same fp32-rounded maps, so only the final rounding of the RMS map differs."""
+    m, weights = _noise_case((512, 512), 21)
+    m = m.astype(np.float32).astype(np.float64)
+    weights = [w.astype(np.float32).astype(np.float64) for w in weights]
+    # fp32 median of two values = their mean rounded to fp32; give the oracle that median as a single weight map
+    wmed32 = ((weights[0] + weights[1]) * 0.5).astype(np.float32).astype(np.float64)
+    ref = _oracle_noise(m, [wmed32], 0.5 / 60, gridArcmin, numBins if numBins > 1 else None)
+    got, wm = _run_cell_rms(ops32, m, weights, gridArcmin, numBins)
+    assert np.array_equal(wm.astype(np.float64), wmed32)
+    err = _relerr(got, ref)
+    report("cell_rms_f32", numBins=numBins, grid=gridArcmin, relerr=err)
+    assert np.array_equal(got == 0, ref == 0)
+    assert err < 1e-6
 
 
 @pytest.mark.parametrize("trim,realSpace", [(0, False), (24, False), (31, True), (120, False)])
