@@ -39,21 +39,71 @@ class _Row(object):
         return {k: self._t._cols[k][self._i] for k in self._t.keys()}
 
 
+class _LazyDict(dict):
+    """dict whose values may be zero-argument callables evaluated (once) on first access."""
+
+    def defer(self, key, maker):
+        dict.__setitem__(self, key, _Deferred(maker))
+
+    def put(self, key, value):
+        dict.__setitem__(self, key, value)
+
+    def isDeferred(self, key):
+        return isinstance(dict.__getitem__(self, key), _Deferred)
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if isinstance(v, _Deferred):
+            v = v.value()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def raw(self, key):
+        return dict.__getitem__(self, key)
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+
+class _Deferred(object):
+    def __init__(self, maker):
+        self.maker = maker
+        self._value = None
+
+    def value(self):
+        if self._value is None:
+            self._value = np.asarray(self.maker())
+            self.maker = None
+        return self._value
+
+    def then(self, fn):
+        """A deferred column derived from this one (row subset, reordering) without evaluating it now."""
+        return _Deferred(lambda: fn(self.value()))
+
+
 class Table(object):
     """Minimal stand-in for astropy.table.Table."""
 
     def __init__(self, names=None):
-        self._cols = {}
+        self._cols = _LazyDict()
         if names is not None:
             for n in names:
                 self._cols[n] = np.zeros(0)
+
+    def add_deferred_column(self, name, maker):
+        """Column whose values are produced by ``maker()`` the first time it is read (object names are only
+        formatted when somebody looks at them)."""
+        self._cols.defer(name, maker)
 
     def add_column(self, col, name=None):
         if isinstance(col, Column):
             name, data = col.name, col.data
         else:
             data = np.asarray(col)
-        if len(self._cols) > 0 and len(data) != len(self):
+        if any(not self._cols.isDeferred(k) for k in self._cols.keys()) and len(data) != len(self):
             raise ValueError("column length mismatch")
         self._cols[name] = np.array(data)
 
@@ -65,8 +115,11 @@ class Table(object):
         return self.keys()
 
     def __len__(self):
-        for v in self._cols.values():
-            return len(v)
+        for k in self._cols.keys():
+            if not self._cols.isDeferred(k):
+                return len(self._cols[k])
+        for k in self._cols.keys():
+            return len(self._cols[k])
         return 0
 
     def __getitem__(self, key):
@@ -75,9 +128,15 @@ class Table(object):
         if isinstance(key, (int, np.integer)):
             return _Row(self, int(key))
         out = Table()
-        for k, v in self._cols.items():
-            out._cols[k] = v[key]
+        for k in self._cols.keys():
+            out._cols.put(k, self._derived(k, lambda v: v[key]))
         return out
+
+    def _derived(self, k, fn):
+        raw = self._cols.raw(k)
+        if isinstance(raw, _Deferred):
+            return raw.then(fn)
+        return fn(raw)
 
     def __setitem__(self, key, value):
         self._cols[key] = np.asarray(value)
@@ -88,8 +147,8 @@ class Table(object):
 
     def copy(self):
         out = Table()
-        for k, v in self._cols.items():
-            out._cols[k] = v.copy()
+        for k in self._cols.keys():
+            out._cols.put(k, self._derived(k, lambda v: v.copy()))
         return out
 
     def remove_column(self, name):
@@ -99,8 +158,8 @@ class Table(object):
         if isinstance(keys, str):
             keys = [keys]
         order = np.lexsort([self._cols[k] for k in reversed(keys)])
-        for k in self._cols:
-            self._cols[k] = self._cols[k][order]
+        for k in list(self._cols.keys()):
+            self._cols.put(k, self._derived(k, lambda v: v[order]))
 
     def toRows(self):
         return [r.asDict() for r in self]
@@ -113,7 +172,11 @@ def vstack(tables):
         return out
     keys = tables[0].keys()
     for k in keys:
-        out._cols[k] = np.concatenate([t[k] if k in t.keys() else np.full(len(t), -99) for t in tables])
+        if all(k in t.keys() and t._cols.isDeferred(k) for t in tables):
+            parts = [t._cols.raw(k) for t in tables]
+            out._cols.defer(k, lambda parts=parts: np.concatenate([p.value() for p in parts]))
+        else:
+            out._cols[k] = np.concatenate([t[k] if k in t.keys() else np.full(len(t), -99) for t in tables])
     return out
 
 
@@ -152,6 +215,12 @@ def _nameDec(decDeg, longFormat):
         secsText = str(secs)
         out += secsText[:3].rjust(4, '0') if secs < 10 else secsText[:4]
     return out
+
+
+def makeNames(RADeg, decDeg, prefix='ACT-CL', longNames=False):
+    """Names of many objects at once (object array of str)."""
+    namer = makeLongName if longNames else makeName
+    return np.array([namer(r, d, prefix=prefix) for r, d in zip(np.atleast_1d(RADeg), np.atleast_1d(decDeg))], dtype=object)
 
 
 def makeName(RADeg, decDeg, prefix='ACT-CL'):

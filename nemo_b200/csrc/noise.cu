@@ -295,12 +295,19 @@ __global__ void __launch_bounds__(CR_THREADS) cell_rms_stream_kernel(const T* __
 // weights, the two-pass mean / std and the ten clipping iterations of every weight bin) runs on data held in
 // registers (OC_PPT slots per thread) and, for what does not fit there, in shared memory.  The slots first hold
 // the order-preserving integer key of each good pixel's weight (for the percentile bin edges), then the pixel
-// value.  Cells larger than the on-chip capacity use cell_rms_stream_kernel above.
+// value.  Each warp owns a contiguous run of the cell's pixels (lane-interleaved, so loads coalesce): weights
+// vary smoothly over the sky, so a warp usually meets only a few of the weight bins and skips the others.
+// Cells larger than the on-chip capacity use cell_rms_stream_kernel above.
 #define OC_THREADS 512
 #define OC_WARPS (OC_THREADS / 32)
 #define OC_PPT 24
-#define OC_GROUPS 16   // order statistics resolved together by the radix select (one warp each)
+#define OC_GROUPS 16      // order statistics resolved together by the fallback radix select (one warp each)
 #define OC_MAXBINS 64
+#define OC_MAXTARGETS (2 * (OC_MAXBINS - 1))
+#define OC_L1BITS 11
+#define OC_L1BUCKETS (1 << OC_L1BITS)
+#define OC_CANDCAP 2048   // candidate keys gathered from the buckets that hold a wanted rank
+#define OC_SEGCAP 512     // largest bucket resolved by rank counting
 
 template <typename T> struct KeyOf;
 template <> struct KeyOf<double> {
@@ -332,30 +339,63 @@ struct OcBinState {   // per weight bin, shared memory
     int pad;
 };
 
+// shared-memory carve-up shared by host (size) and device (pointers)
+template <typename KT> struct OcLayout {
+    size_t red, edges, state, warpBins, trank, tval, tuniq, usize, uoff, ucount, umin, umax, ubucket, hist, mark, cand, slots, bins, total;
+    __host__ __device__ OcLayout(int numBins, int smemSlots, int nPix) {
+        size_t o = 0;
+        red = o;      o += sizeof(double) * OC_WARPS * numBins * 3;
+        edges = o;    o += sizeof(double) * (numBins + 1);
+        state = o;    o += sizeof(OcBinState) * numBins;
+        warpBins = o; o += sizeof(unsigned long long) * OC_WARPS;
+        trank = o;    o += sizeof(long long) * OC_MAXTARGETS;
+        tval = o;     o += sizeof(unsigned long long) * OC_MAXTARGETS;
+        umin = o;     o += sizeof(unsigned long long) * OC_MAXTARGETS;
+        umax = o;     o += sizeof(unsigned long long) * OC_MAXTARGETS;
+        cand = o;     o += sizeof(KT) * OC_CANDCAP;
+        slots = o;    o += sizeof(KT) * (size_t)smemSlots;
+        tuniq = o;    o += sizeof(int) * OC_MAXTARGETS;
+        usize = o;    o += sizeof(int) * OC_MAXTARGETS;
+        uoff = o;     o += sizeof(int) * OC_MAXTARGETS;
+        ucount = o;   o += sizeof(int) * OC_MAXTARGETS;
+        ubucket = o;  o += sizeof(int) * OC_MAXTARGETS;
+        hist = o;     o += sizeof(int) * (OC_L1BUCKETS > OC_GROUPS * 256 ? OC_L1BUCKETS : OC_GROUPS * 256);
+        mark = o;     o += sizeof(short) * OC_L1BUCKETS;
+        bins = o;     o += (size_t)nPix;
+        total = (o + 15) & ~(size_t)15;
+    }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T* __restrict__ map, const T* __restrict__ wmed, int S,
                                                                         int H, int W, const Chunks ch, int nx, int ov, int numBins,
                                                                         double* __restrict__ table, double* __restrict__ edges,
-                                                                        int smemSlots) {
+                                                                        int smemSlots, int maxPix) {
     typedef KeyOf<T> K;
     typedef typename K::type key_t;
     constexpr key_t SENT = ~(key_t)0;
     extern __shared__ __align__(16) unsigned char oc_smem[];
-    // layout: red [OC_WARPS][numBins][3] f64 | edges [numBins + 1] f64 | state [numBins] | warpBins [OC_WARPS] u64 |
-    //         target prefix [OC_GROUPS] u64, target rank [OC_GROUPS] i64, group of target [OC_GROUPS] int, hist [OC_GROUPS][256] int |
-    //         slots [smemSlots] key_t | bins [OC_PPT * OC_THREADS + smemSlots] u8
-    double* s_red = reinterpret_cast<double*>(oc_smem);
-    double* s_edges = s_red + OC_WARPS * numBins * 3;
-    OcBinState* s_state = reinterpret_cast<OcBinState*>(s_edges + numBins + 1);
-    unsigned long long* s_warpBins = reinterpret_cast<unsigned long long*>(s_state + numBins);
-    unsigned long long* s_tprefix = s_warpBins + OC_WARPS;
-    long long* s_trank = reinterpret_cast<long long*>(s_tprefix + OC_GROUPS);
-    int* s_tgroup = reinterpret_cast<int*>(s_trank + OC_GROUPS);
-    int* s_hist = s_tgroup + OC_GROUPS;
-    key_t* s_slots = reinterpret_cast<key_t*>(s_hist + OC_GROUPS * 256);
-    unsigned char* s_bins = reinterpret_cast<unsigned char*>(s_slots + smemSlots);
+    const OcLayout<key_t> lay(numBins, smemSlots, maxPix);
+    double* s_red = reinterpret_cast<double*>(oc_smem + lay.red);
+    double* s_edges = reinterpret_cast<double*>(oc_smem + lay.edges);
+    OcBinState* s_state = reinterpret_cast<OcBinState*>(oc_smem + lay.state);
+    unsigned long long* s_warpBins = reinterpret_cast<unsigned long long*>(oc_smem + lay.warpBins);
+    long long* s_trank = reinterpret_cast<long long*>(oc_smem + lay.trank);
+    unsigned long long* s_tval = reinterpret_cast<unsigned long long*>(oc_smem + lay.tval);
+    unsigned long long* s_umin = reinterpret_cast<unsigned long long*>(oc_smem + lay.umin);
+    unsigned long long* s_umax = reinterpret_cast<unsigned long long*>(oc_smem + lay.umax);
+    key_t* s_cand = reinterpret_cast<key_t*>(oc_smem + lay.cand);
+    key_t* s_slots = reinterpret_cast<key_t*>(oc_smem + lay.slots);
+    int* s_tuniq = reinterpret_cast<int*>(oc_smem + lay.tuniq);
+    int* s_usize = reinterpret_cast<int*>(oc_smem + lay.usize);
+    int* s_uoff = reinterpret_cast<int*>(oc_smem + lay.uoff);
+    int* s_ucount = reinterpret_cast<int*>(oc_smem + lay.ucount);
+    int* s_ubucket = reinterpret_cast<int*>(oc_smem + lay.ubucket);
+    int* s_hist = reinterpret_cast<int*>(oc_smem + lay.hist);
+    short* s_mark = reinterpret_cast<short*>(oc_smem + lay.mark);
+    unsigned char* s_bins = oc_smem + lay.bins;
     __shared__ double s_scr[2 * CR_WARPS];
-    __shared__ int s_nGroups;
+    __shared__ int s_misc[4];   // [0] number of unique target buckets, [1] fallback flag, [2] groups (fallback)
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int cell = blockIdx.x, img = blockIdx.y;
@@ -364,7 +404,13 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     const T* wm = wmed + (size_t)(img / S) * H * W;
     const int cw = g.x1 - g.x0;
     const int n = (g.y1 - g.y0) * cw;
-    constexpr int NREG = OC_PPT * OC_THREADS;
+    // warp w owns pixels [w * CH, (w + 1) * CH); its slot (j, lane) is pixel w * CH + j * 32 + lane: j < OC_PPT in
+    // registers, the others in shared memory
+    const int CH = (((n + OC_WARPS - 1) / OC_WARPS) + 31) & ~31;
+    const int JT = CH >> 5;                                  // slots per lane
+    const int spw = smemSlots / OC_WARPS;                    // shared-memory slots per warp
+    const int e0 = wid * CH + lane;
+    key_t* mySlots = s_slots + (size_t)wid * spw + lane;
     double* tab = table + ((size_t)img * gridDim.x + cell) * numBins;
     double* edg = edges + ((size_t)img * gridDim.x + cell) * (numBins + 1);
 
@@ -372,6 +418,7 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     // ---- load: weight keys of the good pixels ------------------------------------------------------------
     double cnt = 0, dummy = 0, wmin = INFINITY, wmax = -INFINITY;
     auto loadKey = [&](int e) -> key_t {
+        if (e >= n) return SENT;
         const int r = e / cw, c = e - r * cw;
         const size_t off = (size_t)(g.y0 + r) * W + g.x0 + c;
         if (m[off] == (T)0) return SENT;
@@ -382,11 +429,8 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
         return K::enc(w);
     };
 #pragma unroll
-    for (int j = 0; j < OC_PPT; ++j) {
-        const int e = j * OC_THREADS + tid;
-        reg[j] = (e < n) ? loadKey(e) : SENT;
-    }
-    for (int e = NREG + tid; e < n; e += OC_THREADS) s_slots[e - NREG] = loadKey(e);
+    for (int j = 0; j < OC_PPT; ++j) reg[j] = (j < JT) ? loadKey(e0 + j * 32) : SENT;
+    for (int j = OC_PPT; j < JT; ++j) mySlots[(j - OC_PPT) * 32] = loadKey(e0 + j * 32);
     block_sum2(cnt, dummy, s_scr);
     block_minmax(wmin, wmax, s_scr);
     if (cnt == 0) {  // filters.py:446-447
@@ -404,127 +448,253 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     if (numBins > 1 && wmin == wmax) {  // constant weights: every percentile is that constant
         for (int b = 1 + tid; b < numBins; b += OC_THREADS) s_edges[b] = wmin;
     } else if (numBins > 1) {
-        // skip the leading bits every key shares
         const key_t kmin = K::enc((T)wmin), kmax = K::enc((T)wmax);
+        const int nTargets = 2 * (numBins - 1);   // ranks lo_b, hi_b for b = 1..numBins-1, ascending
+        // numpy's virtual index of percentile p (method 'linear'): ranks floor(vi) and floor(vi) + 1
+        auto virtualIndex = [&](int b) -> double {
+            const double p = (double)b * (100.0 / (double)numBins);  // np.arange(0, 100, 100/numBins)[b]
+            const double q = p / 100.0;
+            const double nn = (double)nGood;
+            return nn * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0;
+        };
+        for (int t = tid; t < nTargets; t += OC_THREADS) {
+            const double vi = virtualIndex(1 + t / 2);
+            long long lo = (long long)floor(vi), hi = lo + 1;
+            lo = max(0LL, min(lo, nGood - 1));
+            hi = max(0LL, min(hi, nGood - 1));
+            s_trank[t] = (t & 1) ? hi : lo;
+        }
+        // -- level 1: one histogram of the top OC_L1BITS bits of (key - kmin) ---------------------------------------
         int nbits = 0;
         {
-            key_t x = kmin ^ kmax;
+            key_t x = kmax - kmin;
             while (x) {
                 ++nbits;
                 x >>= 1;
             }
         }
-        const int npass = (nbits + 7) / 8;
-        const key_t lowMask = (8 * npass >= K::BITS) ? SENT : (((key_t)1 << (8 * npass)) - 1);
-        const int nTargets = 2 * (numBins - 1);   // ranks lo_b, hi_b for b = 1..numBins-1, ascending
-        for (int t0 = 0; t0 < nTargets; t0 += OC_GROUPS) {
-            const int nt = min(OC_GROUPS, nTargets - t0);
-            if (tid < nt) {
-                const int t = t0 + tid, b = 1 + t / 2;
-                const double p = (double)b * (100.0 / (double)numBins);  // np.arange(0, 100, 100/numBins)[b]
-                const double q = p / 100.0;
-                const double nn = (double)nGood;
-                const double vi = nn * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0;  // numpy's virtual index, method 'linear'
-                long long lo = (long long)floor(vi), hi = lo + 1;
-                lo = max(0LL, min(lo, nGood - 1));
-                hi = max(0LL, min(hi, nGood - 1));
-                s_tprefix[tid] = (unsigned long long)(kmin & ~lowMask);
-                s_trank[tid] = (t & 1) ? hi : lo;
+        const int sh1 = nbits > OC_L1BITS ? nbits - OC_L1BITS : 0;
+        for (int i = tid; i < OC_L1BUCKETS; i += OC_THREADS) {
+            s_hist[i] = 0;
+            s_mark[i] = -1;
+        }
+        if (tid == 0) s_misc[1] = 0;
+        __syncthreads();
+        auto count1 = [&](key_t key) {
+            if (key != SENT) atomicAdd(&s_hist[(int)((key - kmin) >> sh1)], 1);
+        };
+#pragma unroll
+        for (int j = 0; j < OC_PPT; ++j) count1(reg[j]);
+        for (int j = OC_PPT; j < JT; ++j) count1(mySlots[(j - OC_PPT) * 32]);
+        __syncthreads();
+        // exclusive scan of the 2048 buckets (4 per thread), in place
+        {
+            int loc[4], tot = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                loc[i] = s_hist[tid * 4 + i];
+                tot += loc[i];
             }
-            key_t maskbits = ~lowMask;
-            for (int pass = 0; pass < npass; ++pass) {
-                const int shift = 8 * (npass - 1 - pass);
-                __syncthreads();
-                // groups of targets that still share a prefix (targets ascend, so equal prefixes are adjacent)
-                if (tid == 0) {
-                    int ng = 0;
-                    for (int t = 0; t < nt; ++t) {
-                        if (t == 0 || s_tprefix[t] != s_tprefix[t - 1]) ++ng;
-                        s_tgroup[t] = ng - 1;
+            int inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            int* s_wsum = reinterpret_cast<int*>(s_scr);
+            __syncthreads();
+            if (lane == 31) s_wsum[wid] = inc;
+            __syncthreads();
+            int base = 0;
+            for (int w = 0; w < wid; ++w) base += s_wsum[w];
+            int run = base + inc - tot;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                s_hist[tid * 4 + i] = run;
+                run += loc[i];
+            }
+        }
+        __syncthreads();
+        // bucket of every target (largest bucket whose exclusive count <= rank), then the distinct buckets
+        for (int t = tid; t < nTargets; t += OC_THREADS) {
+            const int rank = (int)s_trank[t];
+            int lo = 0, hi = OC_L1BUCKETS - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_hist[mid] <= rank) lo = mid; else hi = mid - 1;
+            }
+            s_tuniq[t] = lo;                       // bucket for now
+            s_trank[t] = rank - s_hist[lo];        // rank inside the bucket
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int nu = 0, off = 0, bad = 0;
+            for (int t = 0; t < nTargets; ++t) {
+                const int bkt = s_tuniq[t];
+                if (nu == 0 || s_ubucket[nu - 1] != bkt) {   // targets ascend, so equal buckets are adjacent
+                    const int size = ((bkt + 1 < OC_L1BUCKETS) ? s_hist[bkt + 1] : (int)nGood) - s_hist[bkt];
+                    s_ubucket[nu] = bkt;
+                    s_usize[nu] = size;
+                    s_ucount[nu] = 0;
+                    s_umin[nu] = ~0ULL;
+                    s_umax[nu] = 0ULL;
+                    if (size <= OC_SEGCAP && off + size <= OC_CANDCAP) {
+                        s_uoff[nu] = off;
+                        off += size;
+                    } else {
+                        s_uoff[nu] = -1;           // too large to gather: resolved only if all its keys are equal
                     }
-                    s_nGroups = ng;
+                    s_mark[bkt] = (short)nu;
+                    ++nu;
                 }
-                for (int i = tid; i < OC_GROUPS * 256; i += OC_THREADS) s_hist[i] = 0;
+                s_tuniq[t] = nu - 1;
+            }
+            s_misc[0] = nu;
+            (void)bad;
+        }
+        __syncthreads();
+        // -- level 2: gather the keys of the wanted buckets (or their min / max when the bucket is too large) ------
+        auto gather = [&](key_t key) {
+            if (key == SENT) return;
+            const int u = s_mark[(int)((key - kmin) >> sh1)];
+            if (u < 0) return;
+            const int off = s_uoff[u];
+            if (off >= 0) {
+                s_cand[off + atomicAdd(&s_ucount[u], 1)] = key;
+            } else {
+                atomicMin(&s_umin[u], (unsigned long long)key);
+                atomicMax(&s_umax[u], (unsigned long long)key);
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < OC_PPT; ++j) gather(reg[j]);
+        for (int j = OC_PPT; j < JT; ++j) gather(mySlots[(j - OC_PPT) * 32]);
+        __syncthreads();
+        // -- one warp per target: rank counting inside its bucket ----------------------------------------------------
+        for (int t = wid; t < nTargets; t += OC_WARPS) {
+            const int u = s_tuniq[t];
+            const int off = s_uoff[u], msz = s_usize[u];
+            const int r = (int)s_trank[t];
+            if (off < 0) {
+                if (lane == 0) {
+                    if (s_umin[u] == s_umax[u]) s_tval[t] = s_umin[u];
+                    else s_misc[1] = 1;            // a large bucket of distinct keys: fall back to the radix select
+                }
+                continue;
+            }
+            for (int i = lane; i < msz; i += 32) {
+                const key_t ki = s_cand[off + i];
+                int c = 0;
+                for (int j = 0; j < msz; ++j) {
+                    const key_t kj = s_cand[off + j];
+                    c += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+                }
+                if (c == r) s_tval[t] = (unsigned long long)ki;
+            }
+        }
+        __syncthreads();
+        if (s_misc[1]) {
+            // ---- fallback: MSB-first radix select, 8 bits per pass, OC_GROUPS targets at a time ------------------------
+            int nb2 = 0;
+            {
+                key_t x = kmin ^ kmax;
+                while (x) {
+                    ++nb2;
+                    x >>= 1;
+                }
+            }
+            const int npass = (nb2 + 7) / 8;
+            const key_t lowMask = (8 * npass >= K::BITS) ? SENT : (((key_t)1 << (8 * npass)) - 1);
+            unsigned long long* s_tprefix = s_umin;   // reuse
+            int* s_tgroup = s_ucount;
+            for (int t0 = 0; t0 < nTargets; t0 += OC_GROUPS) {
+                const int nt = min(OC_GROUPS, nTargets - t0);
                 __syncthreads();
-                const int ng = s_nGroups;
-                auto count = [&](key_t key) {
-                    int code = -1;
-                    if (key != SENT) {
+                if (tid < nt) {
+                    const int t = t0 + tid;
+                    const double vi = virtualIndex(1 + t / 2);
+                    long long lo = (long long)floor(vi), hi = lo + 1;
+                    lo = max(0LL, min(lo, nGood - 1));
+                    hi = max(0LL, min(hi, nGood - 1));
+                    s_tprefix[tid] = (unsigned long long)(kmin & ~lowMask);
+                    s_trank[tid] = (t & 1) ? hi : lo;   // s_trank[0..nt) is scratch from here on
+                }
+                key_t maskbits = ~lowMask;
+                for (int pass = 0; pass < npass; ++pass) {
+                    const int shift = 8 * (npass - 1 - pass);
+                    __syncthreads();
+                    if (tid == 0) {
+                        int ng = 0;
+                        for (int t = 0; t < nt; ++t) {
+                            if (t == 0 || s_tprefix[t] != s_tprefix[t - 1]) ++ng;
+                            s_tgroup[t] = ng - 1;
+                        }
+                    }
+                    for (int i = tid; i < OC_GROUPS * 256; i += OC_THREADS) s_hist[i] = 0;
+                    __syncthreads();
+                    auto count = [&](key_t key) {
+                        if (key == SENT) return;
                         const unsigned long long pre = (unsigned long long)(key & maskbits);
-                        // the group whose prefix equals pre, if any (prefixes of distinct groups ascend)
                         int loT = 0, hiT = nt - 1;
                         while (loT < hiT) {
                             const int mid = (loT + hiT) >> 1;
                             if (s_tprefix[mid] < pre) loT = mid + 1; else hiT = mid;
                         }
-                        if (s_tprefix[loT] == pre) code = s_tgroup[loT] * 256 + (int)((key >> shift) & (key_t)255);
-                    }
-                    // one shared-memory atomic per distinct (group, digit) in the warp
-                    const unsigned peers = __match_any_sync(0xffffffffu, code);
-                    if (code >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(&s_hist[code], __popc(peers));
-                };
-                (void)ng;
+                        if (s_tprefix[loT] == pre) atomicAdd(&s_hist[s_tgroup[loT] * 256 + (int)((key >> shift) & (key_t)255)], 1);
+                    };
 #pragma unroll
-                for (int j = 0; j < OC_PPT; ++j) count(reg[j]);
-                for (int e0 = NREG; e0 < n; e0 += OC_THREADS) {   // whole warps stay converged for __match_any_sync
-                    const int e = e0 + tid;
-                    count(e < n ? s_slots[e - NREG] : SENT);
-                }
-                __syncthreads();
-                // one warp per target: locate the digit that holds its rank
-                if (wid < nt) {
-                    const int* hst = s_hist + s_tgroup[wid] * 256;
-                    int loc[8], tot = 0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        loc[i] = hst[lane * 8 + i];
-                        tot += loc[i];
-                    }
-                    int inc = tot;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= o) inc += t;
-                    }
-                    const long long kk = s_trank[wid];
-                    const long long before = (long long)(inc - tot);
-                    const bool mine = (kk >= before) && (kk < before + tot);
-                    __syncwarp();
-                    if (mine) {
-                        long long r = kk - before;
-                        int d = 0;
+                    for (int j = 0; j < OC_PPT; ++j) count(reg[j]);
+                    for (int j = OC_PPT; j < JT; ++j) count(mySlots[(j - OC_PPT) * 32]);
+                    __syncthreads();
+                    if (wid < nt) {
+                        const int* hst = s_hist + s_tgroup[wid] * 256;
+                        int loc[8], tot = 0;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            if (d == i && r >= loc[i]) {
-                                r -= loc[i];
-                                d = i + 1;
-                            }
+                            loc[i] = hst[lane * 8 + i];
+                            tot += loc[i];
                         }
-                        if (d > 7) d = 7;
-                        s_tprefix[wid] |= ((unsigned long long)(lane * 8 + d)) << shift;
-                        s_trank[wid] = r;
+                        int inc = tot;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                            if (lane >= o) inc += t;
+                        }
+                        const long long kk = s_trank[wid];
+                        const long long before = (long long)(inc - tot);
+                        if ((kk >= before) && (kk < before + tot)) {
+                            long long r = kk - before;
+                            int d = 0;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                if (d == i && r >= loc[i]) {
+                                    r -= loc[i];
+                                    d = i + 1;
+                                }
+                            }
+                            if (d > 7) d = 7;
+                            s_tprefix[wid] |= ((unsigned long long)(lane * 8 + d)) << shift;
+                            s_trank[wid] = r;
+                        }
                     }
+                    maskbits |= (key_t)255 << shift;
                 }
-                maskbits |= (key_t)255 << shift;
+                __syncthreads();
+                if (tid < nt) s_tval[t0 + tid] = s_tprefix[tid];
             }
             __syncthreads();
-            // pairs (lo, hi) of this batch -> interpolated percentiles
-            if (tid < nt && (tid & 1) == 0) {
-                const int t = t0 + tid, b = 1 + t / 2;
-                const double a = K::dec((key_t)s_tprefix[tid]);
-                const double bb = K::dec((key_t)s_tprefix[tid + 1]);
-                const double p = (double)b * (100.0 / (double)numBins);
-                const double q = p / 100.0;
-                const double nn = (double)nGood;
-                const double vi = nn * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0;
-                const double gmm = vi - floor(vi);
-                const double diff = bb - a;
-                double res = a + diff * gmm;  // numpy _lerp
-                if (gmm >= 0.5) res = bb - diff * (1.0 - gmm);
-                if (gmm == 0.0) res = a;
-                s_edges[b] = res;
-            }
-            __syncthreads();
+        }
+        // pairs (lo, hi) -> interpolated percentiles
+        for (int b = 1 + tid; b < numBins; b += OC_THREADS) {
+            const double a = K::dec((key_t)s_tval[2 * (b - 1)]);
+            const double bb = K::dec((key_t)s_tval[2 * (b - 1) + 1]);
+            const double vi = virtualIndex(b);
+            const double gmm = vi - floor(vi);
+            const double diff = bb - a;
+            double res = a + diff * gmm;  // numpy _lerp
+            if (gmm >= 0.5) res = bb - diff * (1.0 - gmm);
+            if (gmm == 0.0) res = a;
+            s_edges[b] = res;
         }
     }
     __syncthreads();
@@ -543,19 +713,15 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
                 }
             }
         }
-        s_bins[e] = bin;
+        if (e < n) s_bins[e] = bin;
         if (bin == 255) return K::fromValue((T)0);
         present |= 1ULL << bin;
         const int r = e / cw, c = e - r * cw;
         return K::fromValue(m[(size_t)(g.y0 + r) * W + g.x0 + c]);
     };
 #pragma unroll
-    for (int j = 0; j < OC_PPT; ++j) {
-        const int e = j * OC_THREADS + tid;
-        if (e < n) reg[j] = toValue(reg[j], e);
-        else reg[j] = K::fromValue((T)0);
-    }
-    for (int e = NREG + tid; e < n; e += OC_THREADS) s_slots[e - NREG] = toValue(s_slots[e - NREG], e);
+    for (int j = 0; j < OC_PPT; ++j) reg[j] = (j < JT) ? toValue(reg[j], e0 + j * 32) : K::fromValue((T)0);
+    for (int j = OC_PPT; j < JT; ++j) mySlots[(j - OC_PPT) * 32] = toValue(mySlots[(j - OC_PPT) * 32], e0 + j * 32);
     {
         unsigned int plo = (unsigned int)present, phi = (unsigned int)(present >> 32);
         plo = __reduce_or_sync(0xffffffffu, plo);
@@ -571,8 +737,8 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int j = j4 * 4 + i;
-            const int e = j * OC_THREADS + tid;
-            const unsigned int bv = (j < OC_PPT && e < n) ? (unsigned int)s_bins[e] : 255u;
+            const int e = e0 + j * 32;
+            const unsigned int bv = (j < OC_PPT && j < JT && e < n) ? (unsigned int)s_bins[e] : 255u;
             wv |= bv << (8 * i);
         }
         rbin[j4] = wv;
@@ -606,9 +772,10 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
                     }
                 }
             }
-            for (int e = NREG + tid; e < n; e += OC_THREADS) {
-                if (s_bins[e] == b) {
-                    const double v = K::toValue(s_slots[e - NREG]);
+            for (int j = OC_PPT; j < JT; ++j) {
+                const int e = e0 + j * 32;
+                if (e < n && s_bins[e] == b) {
+                    const double v = K::toValue(mySlots[(j - OC_PPT) * 32]);
                     if (fabs(v) < thr) {
                         const double d = v - piv;
                         c0 += 1.0; s0 += v; q0 += d * d;
@@ -820,16 +987,17 @@ static int cell_rms_t(const void* map, const void* wmed, int nImg, int S, int H,
     for (int i = 0; i < ny; ++i) maxH = std::max(maxH, std::min(ch.y[i + 1] + ov, H) - std::max(ch.y[i] - ov, 0));
     for (int k = 0; k < nx; ++k) maxW = std::max(maxW, std::min(ch.x[k + 1] + ov, W) - std::max(ch.x[k] - ov, 0));
     const long long maxCell = (long long)maxH * maxW;
-    const long long nReg = (long long)OC_PPT * OC_THREADS;
-    const long long smemSlots = maxCell > nReg ? ((maxCell - nReg + 7) / 8) * 8 : 0;
-    const size_t ocBytes = sizeof(double) * ((size_t)OC_WARPS * numBins * 3 + numBins + 1) + sizeof(OcBinState) * numBins +
-                           sizeof(unsigned long long) * OC_WARPS + 16 * OC_GROUPS + sizeof(int) * OC_GROUPS +
-                           sizeof(int) * OC_GROUPS * 256 + sizeof(typename KeyOf<T>::type) * (size_t)smemSlots +
-                           (size_t)(nReg + smemSlots);
-    if (ocBytes <= 227 * 1024 && numBins <= OC_MAXBINS) {
+    // warp-contiguous runs of CH pixels, OC_PPT * 32 of them in registers, the rest in shared memory
+    const long long CH = ((((maxCell + OC_WARPS - 1) / OC_WARPS) + 31) / 32) * 32;
+    const long long perWarp = CH > (long long)OC_PPT * 32 ? CH - (long long)OC_PPT * 32 : 0;
+    const long long smemSlots = perWarp * OC_WARPS;
+    const long long maxPix = ((maxCell + 15) / 16) * 16;
+    const bool fits = maxCell < (1LL << 24) && numBins <= OC_MAXBINS;
+    const size_t ocBytes = fits ? OcLayout<typename KeyOf<T>::type>(numBins, (int)smemSlots, (int)maxPix).total : (size_t)1 << 30;
+    if (ocBytes <= 226 * 1024) {
         NB_CHECK_CUDA(cudaFuncSetAttribute(cell_rms_onchip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ocBytes));
         { NB_PROF_BEGIN(st); cell_rms_onchip_kernel<T><<<dim3(ny * nx, nImg), OC_THREADS, ocBytes, st>>>(
-            (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges, (int)smemSlots); NB_PROF_END("cell_rms_onchip_kernel", st); }
+            (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges, (int)smemSlots, (int)maxPix); NB_PROF_END("cell_rms_onchip_kernel", st); }
     } else {
         { NB_PROF_BEGIN(st); cell_rms_stream_kernel<T><<<dim3(ny * nx, nImg), CR_THREADS, sizeof(double) * (numBins + 1), st>>>(
             (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges); NB_PROF_END("cell_rms_stream_kernel", st); }

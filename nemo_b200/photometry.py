@@ -149,7 +149,7 @@ def findObjectsBatch(ops, snMaps, wcsList, flagMaskList, labelList, tileNameList
     cx = np.concatenate([objs[b][2][keepMasks[b]] for b in range(B)]) if B > 0 else np.zeros(0)
     cn = np.concatenate([objs[b][3][keepMasks[b]] for b in range(B)]) if B > 0 else np.zeros(0)
     K = len(cb)
-    catalogList = [[] for _ in range(B)]
+    catalogList = [None for _ in range(B)]
     if K == 0:
         return catalogList
     # S/N at the object positions
@@ -165,25 +165,46 @@ def findObjectsBatch(ops, snMaps, wcsList, flagMaskList, labelList, tileNameList
             continue
         sl = slice(pos, pos + nb)
         pos += nb
+        keep = snr[sl] > threshold
+        if not keep.any():
+            continue
         wcs = wcsList[b]
-        ys, xs = cy[sl], cx[sl]
+        ys, xs = cy[sl][keep], cx[sl][keep]
         ra, dec = wcs.pix2wcs(xs, ys)
         ra, dec = np.atleast_1d(np.array(ra, dtype=np.float64)), np.atleast_1d(np.array(dec, dtype=np.float64))
         ra = np.where(ra < 0, 360.0 + ra, ra)
-        galLat = _galacticLat(ra, dec)
         flagMask = flagMaskList[b]
         if flagMask is not None:
             flags = np.asarray(flagMask)[np.round(ys).astype(int), np.round(xs).astype(int)]
         else:
-            flags = np.zeros(nb, dtype=int)
-        namer = catalogs.makeLongName if longNames else catalogs.makeName
-        for i in range(nb):     # id counts every object that reaches this point (photometry.py:182)
-            if snr[sl][i] > threshold:
-                catalogList[b].append({'id': i + 1, 'x': xs[i], 'y': ys[i], 'RADeg': ra[i], 'decDeg': dec[i],
-                                       'galacticLatDeg': galLat[i], 'name': namer(ra[i], dec[i], prefix=objIdent),
-                                       'numSigPix': cn[sl][i], 'template': labelList[b], 'tileName': tileNameList[b],
-                                       'SNR': float(snr[sl][i]), 'flags': flags[i]})
+            flags = np.zeros(len(ys), dtype=int)
+        # id counts every object that passed the size and ring cuts, kept or not (photometry.py:182)
+        catalogList[b] = {'id': (np.arange(nb) + 1)[keep], 'x': xs, 'y': ys, 'RADeg': ra, 'decDeg': dec,
+                          'galacticLatDeg': _galacticLat(ra, dec), 'numSigPix': cn[sl][keep], 'SNR': snr[sl][keep].astype(np.float64),
+                          'flags': flags, 'template': labelList[b], 'tileName': tileNameList[b],
+                          'objIdent': objIdent, 'longNames': longNames}
     return catalogList
+
+
+def columnsToTable(cols, extra=None, keysToWrite=None):
+    """Table from one image's column dict as made by findObjectsBatch (None -> []).  The object names are formatted
+    the first time the 'name' column is read."""
+    if cols is None:
+        return []
+    n = len(cols['x'])
+    tab = catalogs.Table()
+    ra, dec, ident, longNames = cols['RADeg'], cols['decDeg'], cols['objIdent'], cols['longNames']
+    values = dict(cols)
+    if extra is not None:
+        values.update(extra)
+    for key in (keysToWrite if keysToWrite is not None else catalogs.COLUMN_NAMES):
+        if key == 'name':
+            tab.add_deferred_column('name', lambda: catalogs.makeNames(ra, dec, prefix=ident, longNames=longNames))
+        elif key in ('template', 'tileName'):
+            tab.add_column(catalogs.Column(np.full(n, values[key], dtype=object), key))
+        elif key in values and key not in ('objIdent', 'longNames'):
+            tab.add_column(catalogs.Column(values[key], key))
+    return tab
 
 
 def _gatherValues(imgs, bIdx, ys, xs):
@@ -213,10 +234,7 @@ def findObjects(filteredMapDict, threshold=3.0, minObjPix=3, rejectBorder=10, fi
                             removeRings=removeRings, ringThresholdSigma=ringThresholdSigma, invertMap=invertMap,
                             objIdent=objIdent, longNames=longNames, useInterpolator=useInterpolator,
                             measureShapes=measureShapes)
-    catalog = cats[0]
-    if len(catalog) > 0:
-        catalog = catalogs.catalogListToTab(catalog)
-    return catalog
+    return columnsToTable(cats[0])
 
 
 # -------------------------------------------------------------------------------------------------------------

@@ -214,14 +214,20 @@ def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measu
                 photScale = s
     useInterp = parDict['useInterpolator']
     # all objects of the batch in one go: positions from (RADeg, decDeg) as the reference does (photometry.py:328)
-    flat = [(o, r) for o in range(nT * S) for r in rows[o]]
-    if len(flat) > 0 and (measureFluxes or photScale is not None):
-        xs = np.empty(len(flat))
-        ys = np.empty(len(flat))
-        for k, (o, r) in enumerate(flat):
-            xs[k], ys[k] = wcsList[o].wcs2pix(r['RADeg'], r['decDeg'])
+    owners = [o for o in range(nT * S) if rows[o] is not None]
+    extras = {o: {} for o in owners}
+    if len(owners) > 0 and (measureFluxes or photScale is not None):
+        counts = [len(rows[o]['x']) for o in owners]
+        xs, ys = [], []
+        for o in owners:
+            x, y = wcsList[o].wcs2pix(rows[o]['RADeg'], rows[o]['decDeg'])
+            xs.append(np.atleast_1d(x))
+            ys.append(np.atleast_1d(y))
+        xs, ys = np.concatenate(xs), np.concatenate(ys)
+        ownArr = np.repeat(np.array(owners, dtype=np.int32), counts)
+        snrAll = np.concatenate([rows[o]['SNR'] for o in owners])
         yx = ops.to_device(np.stack([ys, xs], axis=1), ops.torch.float64)
-        own = ops.to_device(np.array([o for o, _ in flat], dtype=np.int32), ops.torch.int32)
+        own = ops.to_device(ownArr, ops.torch.int32)
 
         def sample(imgs, idxT, sign=1.0):
             if useInterp:
@@ -233,45 +239,54 @@ def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measu
 
         vals = {}
         if photScale is not None:
-            phot = ops.to_device(np.array([(o // S) * S + photScale for o, _ in flat], dtype=np.int32), ops.torch.int32)
-            inside = np.array([int(x) > 0 and int(x) < W and int(y) > 0 and int(y) < H for x, y in zip(xs, ys)])
+            phot = ops.to_device(((ownArr // S) * S + photScale).astype(np.int32), ops.torch.int32)
+            # bounds test of getSNRValues (photometry.py:246-253): int() truncates towards zero
+            xi, yi = np.trunc(xs), np.trunc(ys)
+            inside = (xi > 0) & (xi < W) & (yi > 0) & (yi < H)
             fixedSNR = sample(sn, phot, sign=-1.0 if (invertMap and not measureFluxes) else 1.0)
             vals['fixed_SNR'] = np.where(inside, fixedSNR, 0.0)
         if measureFluxes:
             vals[''] = sample(data, own)
             if photScale is not None:
                 vals['fixed_'] = sample(data, phot)
-        for k, (o, r) in enumerate(flat):
-            if 'fixed_SNR' in vals:
-                r['fixed_SNR'] = float(vals['fixed_SNR'][k])
-            if not measureFluxes:
-                continue
+        cols = {}
+        if 'fixed_SNR' in vals:
+            cols['fixed_SNR'] = vals['fixed_SNR']
+        if measureFluxes:
             for prefix in ['', 'fixed_'] if photScale is not None else ['']:
-                v = float(vals[prefix][k])
-                snr = r[prefix + 'SNR']
+                v = vals[prefix]
+                snr = snrAll if prefix == '' else vals['fixed_SNR']
                 with np.errstate(divide='ignore', invalid='ignore'):
                     if mapUnits == 'yc':
-                        r[prefix + 'y_c'] = v / 1e-4
-                        r[prefix + 'err_y_c'] = np.float64(r[prefix + 'y_c']) / snr
+                        cols[prefix + 'y_c'] = v / 1e-4
+                        cols[prefix + 'err_y_c'] = cols[prefix + 'y_c'] / snr
                         deltaTc = maps.convertToDeltaT(v, obsFrequencyGHz=148.0)
-                        r[prefix + 'deltaT_c'] = deltaTc
-                        r[prefix + 'err_deltaT_c'] = abs(np.float64(deltaTc) / snr)
+                        cols[prefix + 'deltaT_c'] = deltaTc
+                        cols[prefix + 'err_deltaT_c'] = np.abs(deltaTc / snr)
                     else:
-                        r[prefix + 'deltaT_c'] = v
-                        r[prefix + 'err_deltaT_c'] = np.float64(v) / snr
-                        md0 = batch.mapDicts[o // S][0]
-                        nsr = md0.get('solidAngle_nsr', 0.0)
-                        if nsr > 0:
-                            r[prefix + 'fluxJy'] = photometry.deltaTToJyPerSr(r[prefix + 'deltaT_c'], md0['obsFreqGHz']) * nsr * 1.e-9
-                            r[prefix + 'err_fluxJy'] = photometry.deltaTToJyPerSr(r[prefix + 'err_deltaT_c'], md0['obsFreqGHz']) * nsr * 1.e-9
-                        else:
-                            r[prefix + 'fluxJy'] = 0.0
-                            r[prefix + 'err_fluxJy'] = 0.0
+                        cols[prefix + 'deltaT_c'] = v
+                        cols[prefix + 'err_deltaT_c'] = v / snr
+                        flux, errFlux = np.zeros(len(v)), np.zeros(len(v))
+                        lo = 0
+                        for o, cnt in zip(owners, counts):
+                            md0 = batch.mapDicts[o // S][0]
+                            nsr = md0.get('solidAngle_nsr', 0.0)
+                            if nsr > 0:
+                                sl = slice(lo, lo + cnt)
+                                flux[sl] = photometry.deltaTToJyPerSr(v[sl], md0['obsFreqGHz']) * nsr * 1.e-9
+                                errFlux[sl] = photometry.deltaTToJyPerSr(cols[prefix + 'err_deltaT_c'][sl], md0['obsFreqGHz']) * nsr * 1.e-9
+                            lo += cnt
+                        cols[prefix + 'fluxJy'] = flux
+                        cols[prefix + 'err_fluxJy'] = errFlux
+        lo = 0
+        for o, cnt in zip(owners, counts):
+            extras[o] = {k: v[lo:lo + cnt] for k, v in cols.items()}
+            lo += cnt
     keys = catalogKeys(photScale is not None, mapUnits, measureFluxes)
     catalogDict = {}
     for o in range(nT * S):
         label = labelList[o] + "#" + tileList[o]
-        catalogDict[label] = {'catalog': catalogs.catalogListToTab(rows[o], keysToWrite=keys) if len(rows[o]) > 0 else []}
+        catalogDict[label] = {'catalog': photometry.columnsToTable(rows[o], extras.get(o), keysToWrite=keys)}
     return catalogDict
 
 

@@ -291,6 +291,22 @@ def test_cell_rms_constant_weights(ops64, report, numBins):
     assert _relerr(got, ref) < 1e-12
 
 
+@pytest.mark.parametrize("gridArcmin", [20.0, 40.0])
+def test_cell_rms_clustered_weights(ops64, report, gridArcmin):
+    """Weights packed into a narrow range plus a few far outliers: the percentile buckets of the first histogram
+    level hold thousands of distinct keys, which takes the radix-select fallback inside the on-chip kernel."""
+    m, _ = _noise_case((512, 640), 5)
+    rng = np.random.default_rng(77)
+    w = 1.0 + 1e-6 * rng.random(m.shape)
+    w[rng.random(m.shape) < 0.01] = 1e6
+    ref = _oracle_noise(m, [w], 0.5 / 60, gridArcmin, 8)
+    got, _ = _run_cell_rms(ops64, m, [w], gridArcmin, 8)
+    err = _relerr(got, ref)
+    report("cell_rms_clustered", grid=gridArcmin, relerr=err)
+    assert np.array_equal(got == 0, ref == 0)
+    assert err < 1e-12
+
+
 @pytest.mark.parametrize("numBins,gridArcmin", [(1, 20.0), (8, 40.0)])
 def test_cell_rms_f32(ops32, report, numBins, gridArcmin):
     """fp32 storage: the oracle is fed the same fp32-rounded maps, so only the final rounding of the RMS map differs."""
