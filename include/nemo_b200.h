@@ -52,12 +52,14 @@ int nb_irfft2(int prec, void* spec, void* out, int B, int H, int W, double scale
               const unsigned char* mask, int maskDiv, cudaStream_t stream);
 
 /* K4: MatchedFilter.applyFilter (nemo/filters.py:851-857) followed by "* psMask" (:717):
- *   out[o] = scale * norm[o] * mask[o / S] * Re(ifft2_unnormalised(sum_f fmaps[o / S, f] * filt[o, f]))
- * fmaps [nOut / S, F, H, Wc] complex(T); filtH [nOut, F, H, Wc] real T = the filter folded onto the half plane,
+ *   out[o] = scale * norm[o] * mask[o / S] * Re(ifft2_unnormalised(sum_f fmaps[m(o), f] * filt[o, f]))
+ * with m(o) = o / S (maps of nOut / S tiles, each filtered at S scales) or, when perScale != 0, m(o) = o % S (S
+ * template spectra shared by all tiles: the normalisation pass, filters.py:653, 686).
+ * fmaps [nOut / S or S, F, H, Wc] complex(T); filtH [nOut, F, H, Wc] real T = the filter folded onto the half plane,
  * (filt(k) + filt(-k)) / 2, which is what taking the real part of the full complex inverse transform does;
  * scratch [nOut, H, Wc] complex(T).  norm / mask may be NULL. */
 int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratch, void* out, int nOut, int S,
-                    int F, int H, int W, double scale, const double* norm, const unsigned char* mask,
+                    int perScale, int F, int H, int W, double scale, const double* norm, const unsigned char* mask,
                     cudaStream_t stream);
 
 /* K8: enmap.apply_window(data, pow) and the zero restore (nemo/filters.py:101-104; pipelines.py:229-232).
@@ -93,9 +95,10 @@ int nb_template_norm(int prec, const void* map, int B, int H, int W, int mode, d
                      cudaStream_t stream);
 
 /* fRelWeights (nemo/filters.py:664-670): value at pixel idx[b] of each frequency plane of
- * Re(ifft_unnormalised(fmaps[b, f] * filtH[b, f])); out [B, F] fp64. */
+ * Re(ifft_unnormalised(fmaps[m(b), f] * filtH[b, f])); m(b) = b when S == 0, else b % S (S template spectra shared
+ * by all tiles); out [B, F] fp64. */
 int nb_plane_values_at(int prec, const void* fmaps, const void* filtH, const long long* idx, double* out, int B,
-                       int F, int H, int W, cudaStream_t stream);
+                       int S, int F, int H, int W, cudaStream_t stream);
 
 /* Per-pixel median over frequencies of the weight maps (nemo/filters.py:360-363). */
 int nb_median_weights(int prec, const void* weights, void* out, int B, int F, int H, int W, cudaStream_t stream);

@@ -30,13 +30,13 @@ _PROTOTYPES = {
     "nb_prof_report": [ctypes.c_char_p, c_ll],
     "nb_rfft2": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_ptr],
     "nb_irfft2": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr, c_int, c_ptr],
-    "nb_apply_filter": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr, c_ptr],
+    "nb_apply_filter": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr, c_ptr],
     "nb_window_deconv": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr],
     "nb_xpower_smooth": [c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_ptr],
     "nb_build_filter": [c_int, c_ptr, c_ptr, ctypes.POINTER(c_dbl), c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr],
     "nb_fold_filter": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr],
     "nb_template_norm": [c_int, c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
-    "nb_plane_values_at": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
+    "nb_plane_values_at": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr],
     "nb_median_weights": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
     "nb_cell_rms": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int), c_int,
                     c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],

@@ -108,7 +108,7 @@ fft_cols_kernel(const typename V2<T>::type* __restrict__ in, typename V2<T>::typ
 template <typename T, int N, int F>
 __global__ void __launch_bounds__(ColCfg<T, N>::THREADS)
 fft_cols_apply_kernel(const typename V2<T>::type* __restrict__ fmaps, const T* __restrict__ filt,
-                      typename V2<T>::type* __restrict__ out, int Wc, int S,
+                      typename V2<T>::type* __restrict__ out, int Wc, int S, int perScale,
                       const typename V2<T>::type* __restrict__ tw) {
     typedef ColCfg<T, N> Cfg;
     typedef typename V2<T>::type C2;
@@ -120,7 +120,7 @@ fft_cols_apply_kernel(const typename V2<T>::type* __restrict__ fmaps, const T* _
     T* s_re = smem + c * Cfg::LD;
     T* s_im = smem + (Cfg::C + c) * Cfg::LD;
     const int o = blockIdx.y;
-    const int tile = o / S;
+    const int tile = perScale ? (o % S) : (o / S);
     const size_t plane = (size_t)N * Wc;
     T re[16], im[16];
 #pragma unroll
@@ -466,7 +466,7 @@ static int fft_cols_t(const typename V2<T>::type* in, typename V2<T>::type* out,
 
 template <typename T, int F>
 static int fft_cols_apply_tf(const typename V2<T>::type* fmaps, const T* filt, typename V2<T>::type* out, int nOut,
-                             int S, int H, int Wc, cudaStream_t st) {
+                             int S, int perScale, int H, int Wc, cudaStream_t st) {
     typedef typename V2<T>::type C2;
     const void* tw;
     int rc;
@@ -476,7 +476,7 @@ static int fft_cols_apply_tf(const typename V2<T>::type* fmaps, const T* filt, t
         typedef ColCfg<T, NN> Cfg;                                                                           \
         dim3 grid((Wc + Cfg::C - 1) / Cfg::C, nOut);                                                         \
         if ((rc = set_smem(fft_cols_apply_kernel<T, NN, F>, Cfg::SMEM)) != NB_OK) return rc;                 \
-        { NB_PROF_BEGIN(st); fft_cols_apply_kernel<T, NN, F><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(fmaps, filt, out, Wc, S, (const C2*)tw); NB_PROF_END("fft_cols_apply_kernel", st); } \
+        { NB_PROF_BEGIN(st); fft_cols_apply_kernel<T, NN, F><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(fmaps, filt, out, Wc, S, perScale, (const C2*)tw); NB_PROF_END("fft_cols_apply_kernel", st); } \
     }
     NB_DISPATCH_N(H, COLS_APPLY)
 #undef COLS_APPLY
@@ -545,8 +545,8 @@ int nb_irfft2(int prec, void* spec, void* out, int B, int H, int W, double scale
     return NB_ERR_ARG;
 }
 
-int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratch, void* out, int nOut, int S, int F,
-                    int H, int W, double scale, const double* norm, const unsigned char* mask, cudaStream_t st) {
+int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratch, void* out, int nOut, int S, int perScale,
+                    int F, int H, int W, double scale, const double* norm, const unsigned char* mask, cudaStream_t st) {
     NB_REQUIRE(fmaps && filtH && scratch && out && nOut > 0 && S > 0, NB_ERR_ARG, "nb_apply_filter: bad arguments");
     NB_REQUIRE(F >= 1 && F <= NB_MAX_FREQ, NB_ERR_UNSUPPORTED, "nb_apply_filter: %d frequencies not supported (1..%d)", F, NB_MAX_FREQ);
     NB_REQUIRE(nb_fft_size_supported(H) && nb_fft_size_supported(W) && W >= 64, NB_ERR_UNSUPPORTED,
@@ -554,7 +554,7 @@ int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratc
     int rc;
     const int Wc = W / 2 + 1;
 #define APPLY_F(T, C2T, FF) \
-    rc = fft_cols_apply_tf<T, FF>((const C2T*)fmaps, (const T*)filtH, (C2T*)scratch, nOut, S, H, Wc, st)
+    rc = fft_cols_apply_tf<T, FF>((const C2T*)fmaps, (const T*)filtH, (C2T*)scratch, nOut, S, perScale, H, Wc, st)
 #define APPLY_ALL(T, C2T)                   \
     switch (F) {                            \
         case 1: APPLY_F(T, C2T, 1); break;  \

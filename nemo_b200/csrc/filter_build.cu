@@ -292,17 +292,18 @@ __global__ void __launch_bounds__(1024) template_norm_kernel(const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) plane_values_kernel(const typename V2<T>::type* __restrict__ fmaps,
                                                            const T* __restrict__ filtH, const long long* __restrict__ idx,
-                                                           double* __restrict__ out, int F, int H, int W) {
+                                                           double* __restrict__ out, int F, int H, int W, int S) {
     typedef typename V2<T>::type C2;
     const int f = blockIdx.x, b = blockIdx.y;
     const int Wc = W / 2 + 1;
     const long long p = idx[b];
     const int py = (int)(p / W), px = (int)(p % W);
-    const size_t base = ((size_t)b * F + f) * H * Wc;
+    const size_t base = ((size_t)b * F + f) * H * Wc;                        // filter of image b
+    const size_t mbase = ((size_t)(S > 0 ? b % S : b) * F + f) * H * Wc;    // its template spectrum
     double acc = 0;
     for (long long i = threadIdx.x; i < (long long)H * Wc; i += blockDim.x) {
         const int ky = (int)(i / Wc), kx = (int)(i % Wc);
-        const C2 v = fmaps[base + i];
+        const C2 v = fmaps[mbase + i];
         const double gr = (double)v.x * (double)filtH[base + i], gi = (double)v.y * (double)filtH[base + i];
         // phase 2 pi (ky py / H + kx px / W), reduced exactly in integers before the division
         const double ph = 2.0 * ((double)(((long long)ky * py) % H) / (double)H + (double)(((long long)kx * px) % W) / (double)W);
@@ -427,13 +428,13 @@ int nb_template_norm(int prec, const void* map, int B, int H, int W, int mode, d
     return NB_OK;
 }
 
-int nb_plane_values_at(int prec, const void* fmaps, const void* filtH, const long long* idx, double* out, int B, int F,
-                       int H, int W, cudaStream_t st) {
+int nb_plane_values_at(int prec, const void* fmaps, const void* filtH, const long long* idx, double* out, int B, int S,
+                       int F, int H, int W, cudaStream_t st) {
     NB_REQUIRE(fmaps && filtH && idx && out && B > 0 && F > 0, NB_ERR_ARG, "nb_plane_values_at: bad arguments");
     if (prec == NB_PREC_F64)
-        { NB_PROF_BEGIN(st); plane_values_kernel<double><<<dim3(F, B), 256, 0, st>>>((const double2*)fmaps, (const double*)filtH, idx, out, F, H, W); NB_PROF_END("plane_values_kernel", st); }
+        { NB_PROF_BEGIN(st); plane_values_kernel<double><<<dim3(F, B), 256, 0, st>>>((const double2*)fmaps, (const double*)filtH, idx, out, F, H, W, S); NB_PROF_END("plane_values_kernel", st); }
     else if (prec == NB_PREC_F32)
-        { NB_PROF_BEGIN(st); plane_values_kernel<float><<<dim3(F, B), 256, 0, st>>>((const float2*)fmaps, (const float*)filtH, idx, out, F, H, W); NB_PROF_END("plane_values_kernel", st); }
+        { NB_PROF_BEGIN(st); plane_values_kernel<float><<<dim3(F, B), 256, 0, st>>>((const float2*)fmaps, (const float*)filtH, idx, out, F, H, W, S); NB_PROF_END("plane_values_kernel", st); }
     else {
         nb_set_error("nb_plane_values_at: bad precision %d", prec);
         return NB_ERR_ARG;

@@ -341,12 +341,12 @@ struct OcBinState {   // per weight bin, shared memory
 
 // shared-memory carve-up shared by host (size) and device (pointers)
 template <typename KT> struct OcLayout {
-    size_t red, edges, state, warpBins, trank, tval, tuniq, usize, uoff, ucount, umin, umax, ubucket, hist, mark, cand, slots, bins, total;
-    __host__ __device__ OcLayout(int numBins, int smemSlots, int nPix) {
+    size_t red, edges, state, warpBins, trank, tval, tuniq, usize, uoff, ucount, umin, umax, ubucket, hist, mark, cand, slots, wstart, wrun, bins, total;
+    __host__ __device__ OcLayout(int numBins, int smemSlots) {
         size_t o = 0;
-        red = o;      o += sizeof(double) * OC_WARPS * numBins * 3;
+        red = o;      o += sizeof(double) * 2 * OC_WARPS * numBins * 3;
         edges = o;    o += sizeof(double) * (numBins + 1);
-        state = o;    o += sizeof(OcBinState) * numBins;
+        state = o;    o += sizeof(OcBinState) * OC_WARPS * numBins;
         warpBins = o; o += sizeof(unsigned long long) * OC_WARPS;
         trank = o;    o += sizeof(long long) * OC_MAXTARGETS;
         tval = o;     o += sizeof(unsigned long long) * OC_MAXTARGETS;
@@ -360,8 +360,10 @@ template <typename KT> struct OcLayout {
         ucount = o;   o += sizeof(int) * OC_MAXTARGETS;
         ubucket = o;  o += sizeof(int) * OC_MAXTARGETS;
         hist = o;     o += sizeof(int) * (OC_L1BUCKETS > OC_GROUPS * 256 ? OC_L1BUCKETS : OC_GROUPS * 256);
+        wstart = o;   o += sizeof(int) * OC_WARPS * (numBins + 1);
+        wrun = o;     o += sizeof(int) * OC_WARPS * (numBins + 1);
         mark = o;     o += sizeof(short) * OC_L1BUCKETS;
-        bins = o;     o += (size_t)nPix;
+        bins = o;     o += (size_t)smemSlots;
         total = (o + 15) & ~(size_t)15;
     }
 };
@@ -370,12 +372,12 @@ template <typename T>
 __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T* __restrict__ map, const T* __restrict__ wmed, int S,
                                                                         int H, int W, const Chunks ch, int nx, int ov, int numBins,
                                                                         double* __restrict__ table, double* __restrict__ edges,
-                                                                        int smemSlots, int maxPix) {
+                                                                        int smemSlots) {
     typedef KeyOf<T> K;
     typedef typename K::type key_t;
     constexpr key_t SENT = ~(key_t)0;
     extern __shared__ __align__(16) unsigned char oc_smem[];
-    const OcLayout<key_t> lay(numBins, smemSlots, maxPix);
+    const OcLayout<key_t> lay(numBins, smemSlots);
     double* s_red = reinterpret_cast<double*>(oc_smem + lay.red);
     double* s_edges = reinterpret_cast<double*>(oc_smem + lay.edges);
     OcBinState* s_state = reinterpret_cast<OcBinState*>(oc_smem + lay.state);
@@ -393,6 +395,8 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     int* s_ubucket = reinterpret_cast<int*>(oc_smem + lay.ubucket);
     int* s_hist = reinterpret_cast<int*>(oc_smem + lay.hist);
     short* s_mark = reinterpret_cast<short*>(oc_smem + lay.mark);
+    int* s_wstart = reinterpret_cast<int*>(oc_smem + lay.wstart);
+    int* s_wrun = reinterpret_cast<int*>(oc_smem + lay.wrun);
     unsigned char* s_bins = oc_smem + lay.bins;
     __shared__ double s_scr[2 * CR_WARPS];
     __shared__ int s_misc[4];   // [0] number of unique target buckets, [1] fallback flag, [2] groups (fallback)
@@ -403,34 +407,75 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     const T* m = map + (size_t)img * H * W;
     const T* wm = wmed + (size_t)(img / S) * H * W;
     const int cw = g.x1 - g.x0;
-    const int n = (g.y1 - g.y0) * cw;
-    // warp w owns pixels [w * CH, (w + 1) * CH); its slot (j, lane) is pixel w * CH + j * 32 + lane: j < OC_PPT in
-    // registers, the others in shared memory
-    const int CH = (((n + OC_WARPS - 1) / OC_WARPS) + 31) & ~31;
-    const int JT = CH >> 5;                                  // slots per lane
+    (void)cw;
+    // the cell is cut into 4 x 4 warp tiles of tr x tc pixels; slot i = j * 32 + lane of a warp is pixel (i / tc, i % tc)
+    // of its tile: j < OC_PPT in registers, the others in the warp's shared-memory run
+    const int Rn = g.y1 - g.y0;
+    const int tr = (Rn + 3) >> 2, tc = (cw + 3) >> 2;
+    const int JT = (tr * tc + 31) >> 5;                      // slots per lane
     const int spw = smemSlots / OC_WARPS;                    // shared-memory slots per warp
-    const int e0 = wid * CH + lane;
-    key_t* mySlots = s_slots + (size_t)wid * spw + lane;
+    const int ty0 = (wid >> 2) * tr, tx0 = (wid & 3) * tc;
+    const float rcpTc = 1.0f / (float)tc;
+    key_t* wSlots = s_slots + (size_t)wid * spw;             // this warp's run
+    unsigned char* wBins = s_bins + (size_t)wid * spw;
     double* tab = table + ((size_t)img * gridDim.x + cell) * numBins;
     double* edg = edges + ((size_t)img * gridDim.x + cell) * (numBins + 1);
+    // global offsets of this lane's slots in order (slot j is pixel j * 32 + lane of the tile), -1 outside the cell;
+    // the cursor walks the tile without a division per slot
+    int curR = 0, curC = 0;
+    auto resetCursor = [&]() {
+        curR = lane / tc;
+        curC = lane - curR * tc;
+    };
+    auto nextOffset = [&]() -> long long {
+        const int r = ty0 + curR, c = tx0 + curC;
+        const long long off = (curR < tr && r < Rn && c < cw) ? (long long)(g.y0 + r) * W + g.x0 + c : -1LL;
+        curC += 32;
+        while (curC >= tc) {
+            curC -= tc;
+            ++curR;
+        }
+        return off;
+    };
+    (void)rcpTc;
 
     key_t reg[OC_PPT];
-    // ---- load: weight keys of the good pixels ------------------------------------------------------------
+    // ---- load: weight keys of the good pixels (loads issued eight slots at a time, none depends on another) ----
     double cnt = 0, dummy = 0, wmin = INFINITY, wmax = -INFINITY;
-    auto loadKey = [&](int e) -> key_t {
-        if (e >= n) return SENT;
-        const int r = e / cw, c = e - r * cw;
-        const size_t off = (size_t)(g.y0 + r) * W + g.x0 + c;
-        if (m[off] == (T)0) return SENT;
-        const T w = wm[off];
+    auto makeKey = [&](long long off, T mv, T wv) -> key_t {
+        if (off < 0 || mv == (T)0) return SENT;
         cnt += 1.0;
-        wmin = fmin(wmin, (double)w);
-        wmax = fmax(wmax, (double)w);
-        return K::enc(w);
+        wmin = fmin(wmin, (double)wv);
+        wmax = fmax(wmax, (double)wv);
+        return K::enc(wv);
     };
+    resetCursor();
 #pragma unroll
-    for (int j = 0; j < OC_PPT; ++j) reg[j] = (j < JT) ? loadKey(e0 + j * 32) : SENT;
-    for (int j = OC_PPT; j < JT; ++j) mySlots[(j - OC_PPT) * 32] = loadKey(e0 + j * 32);
+    for (int j0 = 0; j0 < OC_PPT; j0 += 8) {
+        long long off[8];
+        T mv[8], wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            off[u] = nextOffset();
+            mv[u] = (off[u] >= 0) ? m[off[u]] : (T)0;
+            wv[u] = (off[u] >= 0) ? wm[off[u]] : (T)0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) reg[j0 + u] = makeKey(off[u], mv[u], wv[u]);
+    }
+    for (int j0 = OC_PPT; j0 < JT; j0 += 8) {
+        long long off[8];
+        T mv[8], wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            off[u] = nextOffset();
+            mv[u] = (off[u] >= 0) ? m[off[u]] : (T)0;
+            wv[u] = (off[u] >= 0) ? wm[off[u]] : (T)0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (j0 + u < JT) wSlots[(j0 + u - OC_PPT) * 32 + lane] = makeKey(off[u], mv[u], wv[u]);
+    }
     block_sum2(cnt, dummy, s_scr);
     block_minmax(wmin, wmax, s_scr);
     if (cnt == 0) {  // filters.py:446-447
@@ -485,7 +530,7 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
         };
 #pragma unroll
         for (int j = 0; j < OC_PPT; ++j) count1(reg[j]);
-        for (int j = OC_PPT; j < JT; ++j) count1(mySlots[(j - OC_PPT) * 32]);
+        for (int j = OC_PPT; j < JT; ++j) count1(wSlots[(j - OC_PPT) * 32 + lane]);
         __syncthreads();
         // exclusive scan of the 2048 buckets (4 per thread), in place
         {
@@ -568,7 +613,7 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
         };
 #pragma unroll
         for (int j = 0; j < OC_PPT; ++j) gather(reg[j]);
-        for (int j = OC_PPT; j < JT; ++j) gather(mySlots[(j - OC_PPT) * 32]);
+        for (int j = OC_PPT; j < JT; ++j) gather(wSlots[(j - OC_PPT) * 32 + lane]);
         __syncthreads();
         // -- one warp per target: rank counting inside its bucket ----------------------------------------------------
         for (int t = wid; t < nTargets; t += OC_WARPS) {
@@ -644,7 +689,7 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
                     };
 #pragma unroll
                     for (int j = 0; j < OC_PPT; ++j) count(reg[j]);
-                    for (int j = OC_PPT; j < JT; ++j) count(mySlots[(j - OC_PPT) * 32]);
+                    for (int j = OC_PPT; j < JT; ++j) count(wSlots[(j - OC_PPT) * 32 + lane]);
                     __syncthreads();
                     if (wid < nt) {
                         const int* hst = s_hist + s_tgroup[wid] * 256;
@@ -701,27 +746,93 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     for (int b = tid; b <= numBins; b += OC_THREADS) edg[b] = s_edges[b];
 
     // ---- bin index of every good pixel, then the slots take the pixel values -----------------------------------
-    unsigned long long present = 0ULL;
-    auto toValue = [&](key_t key, int e) -> key_t {
-        unsigned char bin = 255;
-        if (key != SENT) {
-            const double w = K::dec(key);
-            for (int b = 0; b < numBins; ++b) {
-                if (w >= s_edges[b] && w < s_edges[b + 1]) {
-                    bin = (unsigned char)b;
-                    break;
-                }
-            }
+    // edges ascend and edges[0] <= w < edges[numBins] for every good pixel, so the bin with edges[b] <= w < edges[b + 1]
+    // (filters.py:458) is found by bisection
+    auto binOf = [&](key_t key) -> unsigned int {
+        if (key == SENT) return 255u;
+        const double w = K::dec(key);
+        int lo = 0, hi = numBins;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (w >= s_edges[mid]) lo = mid; else hi = mid;
         }
-        if (e < n) s_bins[e] = bin;
-        if (bin == 255) return K::fromValue((T)0);
-        present |= 1ULL << bin;
-        const int r = e / cw, c = e - r * cw;
-        return K::fromValue(m[(size_t)(g.y0 + r) * W + g.x0 + c]);
+        return (unsigned int)lo;
     };
+    int* wStart = s_wstart + wid * (numBins + 1);
+    int* wRun = s_wrun + wid * (numBins + 1);
+    for (int b = lane; b <= numBins; b += 32) {
+        wStart[b] = 0;
+        wRun[b] = 0;
+    }
+    __syncwarp();
+    // register slots: bins packed four per word, values loaded in place of the keys
+    unsigned long long present = 0ULL;
+    unsigned int rbin[(OC_PPT + 3) / 4];
 #pragma unroll
-    for (int j = 0; j < OC_PPT; ++j) reg[j] = (j < JT) ? toValue(reg[j], e0 + j * 32) : K::fromValue((T)0);
-    for (int j = OC_PPT; j < JT; ++j) mySlots[(j - OC_PPT) * 32] = toValue(mySlots[(j - OC_PPT) * 32], e0 + j * 32);
+    for (int j4 = 0; j4 < (OC_PPT + 3) / 4; ++j4) rbin[j4] = 0xffffffffu;
+    resetCursor();
+#pragma unroll
+    for (int j0 = 0; j0 < OC_PPT; j0 += 8) {
+        T mv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long off = nextOffset();
+            mv[u] = (off >= 0) ? m[off] : (T)0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u;
+            const unsigned int bin = binOf(reg[j]);
+            rbin[j >> 2] = (rbin[j >> 2] & ~(255u << (8 * (j & 3)))) | (bin << (8 * (j & 3)));
+            if (bin != 255u) present |= 1ULL << bin;
+            reg[j] = K::fromValue(bin != 255u ? mv[u] : (T)0);
+        }
+    }
+    // shared-memory slots: count per bin, then rewrite the run sorted by bin so that a sweep of bin b reads only its own
+    for (int j = OC_PPT; j < JT; ++j) {
+        const unsigned int bin = binOf(wSlots[(j - OC_PPT) * 32 + lane]);
+        wBins[(j - OC_PPT) * 32 + lane] = (unsigned char)bin;
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin != 255u && lane == (__ffs(peers) - 1)) wStart[bin + 1] += __popc(peers);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        int run = 0;
+        for (int b = 0; b < numBins; ++b) {
+            const int c = wStart[b + 1];
+            wStart[b] = run;
+            wRun[b] = run;
+            run += c;
+        }
+        wStart[numBins] = run;
+    }
+    __syncwarp();
+    for (int j0 = OC_PPT; j0 < JT; j0 += 8) {
+        T mv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long off = nextOffset();
+            mv[u] = (off >= 0) ? m[off] : (T)0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (j0 + u >= JT) break;   // uniform over the warp
+            const unsigned int bin = wBins[(j0 + u - OC_PPT) * 32 + lane];
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (bin != 255u && lane == leader) {
+                base = wRun[bin];
+                wRun[bin] = base + __popc(peers);
+            }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            __syncwarp();
+            if (bin != 255u) wSlots[base + __popc(peers & ((1u << lane) - 1u))] = K::fromValue(mv[u]);
+        }
+    }
+    __syncwarp();
+    for (int b = lane; b < numBins; b += 32)
+        if (wStart[b + 1] > wStart[b]) present |= 1ULL << b;
     {
         unsigned int plo = (unsigned int)present, phi = (unsigned int)(present >> 32);
         plo = __reduce_or_sync(0xffffffffu, plo);
@@ -729,35 +840,25 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
         present = ((unsigned long long)phi << 32) | plo;   // bins any lane of this warp holds
         if (lane == 0) s_warpBins[wid] = present;
     }
-    // register copies of this thread's bin indices, four per word
-    unsigned int rbin[(OC_PPT + 3) / 4];
-#pragma unroll
-    for (int j4 = 0; j4 < (OC_PPT + 3) / 4; ++j4) {
-        unsigned int wv = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int j = j4 * 4 + i;
-            const int e = e0 + j * 32;
-            const unsigned int bv = (j < OC_PPT && j < JT && e < n) ? (unsigned int)s_bins[e] : 255u;
-            wv |= bv << (8 * i);
-        }
-        rbin[j4] = wv;
-    }
-    if (tid < numBins) {
+    // every warp keeps its own copy of the per-bin state and updates it with the same arithmetic, so one block barrier
+    // per sweep (publishing the partial sums, double-buffered) is all the synchronisation the iterations need
+    OcBinState* wState = s_state + (size_t)wid * numBins;
+    for (int b = lane; b < numBins; b += 32) {
         OcBinState st;
         st.mean = 0.0; st.rms = 0.0; st.thr = INFINITY; st.pivot = 0.0; st.prevC = -1.0; st.prevS = 0.0; st.done = 0; st.pad = 0;
-        s_state[tid] = st;
+        wState[b] = st;
     }
-    __syncthreads();
+    __syncthreads();   // s_warpBins, and the scratch the selection used, are settled
 
     // ---- sweeps: -2 mean, -1 std about the mean, 0..9 clipping iterations (filters.py:466-477) -----------------
     for (int it = -2; it < 10; ++it) {
+        double* red = s_red + (size_t)(it & 1) * OC_WARPS * numBins * 3;
         unsigned long long todo = present;
         while (todo) {
             const int b = __ffsll((long long)todo) - 1;
             todo &= todo - 1;
-            if (s_state[b].done) continue;
-            const double thr = s_state[b].thr, piv = s_state[b].pivot;
+            if (wState[b].done) continue;
+            const double thr = wState[b].thr, piv = wState[b].pivot;
             double c0 = 0, s0 = 0, q0 = 0, c1 = 0, s1 = 0, q1 = 0;
 #pragma unroll
             for (int j = 0; j < OC_PPT; ++j) {
@@ -772,71 +873,70 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
                     }
                 }
             }
-            for (int j = OC_PPT; j < JT; ++j) {
-                const int e = e0 + j * 32;
-                if (e < n && s_bins[e] == b) {
-                    const double v = K::toValue(mySlots[(j - OC_PPT) * 32]);
-                    if (fabs(v) < thr) {
-                        const double d = v - piv;
-                        c0 += 1.0; s0 += v; q0 += d * d;
-                    }
+            for (int i = wStart[b] + lane; i < wStart[b + 1]; i += 32) {
+                const double v = K::toValue(wSlots[i]);
+                if (fabs(v) < thr) {
+                    const double d = v - piv;
+                    c0 += 1.0; s0 += v; q0 += d * d;
                 }
             }
             c0 = warp_sum(c0 + c1);
             s0 = warp_sum(s0 + s1);
             q0 = warp_sum(q0 + q1);
             if (lane == 0) {
-                double* r = s_red + ((size_t)wid * numBins + b) * 3;
+                double* r = red + ((size_t)wid * numBins + b) * 3;
                 r[0] = c0; r[1] = s0; r[2] = q0;
             }
         }
         __syncthreads();
-        if (tid < numBins && !s_state[tid].done) {
-            const int b = tid;
-            double c = 0, s = 0, q = 0;
-            for (int w = 0; w < OC_WARPS; ++w) {
-                if ((s_warpBins[w] >> b) & 1ULL) {
-                    const double* r = s_red + ((size_t)w * numBins + b) * 3;
-                    c += r[0]; s += r[1]; q += r[2];
+        bool myDone = true;
+        for (int b = lane; b < numBins; b += 32) {
+            OcBinState st = wState[b];
+            if (!st.done) {
+                double c = 0, s = 0, q = 0;
+                for (int w = 0; w < OC_WARPS; ++w) {
+                    if ((s_warpBins[w] >> b) & 1ULL) {
+                        const double* r = red + ((size_t)w * numBins + b) * 3;
+                        c += r[0]; s += r[1]; q += r[2];
+                    }
                 }
-            }
-            OcBinState st = s_state[b];
-            if (it == -2) {
-                if (c == 0) {
-                    st.rms = 0.0;
-                    st.done = 1;
+                if (it == -2) {
+                    if (c == 0) {
+                        st.rms = 0.0;
+                        st.done = 1;
+                    } else {
+                        st.mean = s / c;
+                        st.pivot = st.mean;
+                    }
+                } else if (it == -1) {
+                    st.rms = sqrt(q / c);
+                    st.thr = fabs(st.mean + 3.0 * st.rms);
+                } else if (c == 0) {
+                    st.done = 1;   // "if mask.sum() > 0": nothing changes now, and nothing will in later passes
                 } else {
-                    st.mean = s / c;
-                    st.pivot = st.mean;
+                    const double mean = s / c;
+                    const double dm = mean - st.pivot;
+                    double var = q / c - dm * dm;
+                    if (var < 0) var = 0;
+                    // same sample as in the previous pass: a fixed point, the remaining passes change nothing
+                    const bool fixed = (c == st.prevC) && (s == st.prevS);
+                    st.mean = mean;
+                    st.rms = sqrt(var);
+                    st.pivot = mean;
+                    st.thr = fabs(mean + 3.0 * st.rms);
+                    st.prevC = c;
+                    st.prevS = s;
+                    if (fixed) st.done = 1;
                 }
-            } else if (it == -1) {
-                st.rms = sqrt(q / c);
-                st.thr = fabs(st.mean + 3.0 * st.rms);
-            } else if (c == 0) {
-                st.done = 1;   // "if mask.sum() > 0": nothing changes now, and nothing will in later passes
-            } else {
-                const double mean = s / c;
-                const double dm = mean - st.pivot;
-                double var = q / c - dm * dm;
-                if (var < 0) var = 0;
-                // same sample as in the previous pass: a fixed point, the remaining passes change nothing
-                const bool fixed = (c == st.prevC) && (s == st.prevS);
-                st.mean = mean;
-                st.rms = sqrt(var);
-                st.pivot = mean;
-                st.thr = fabs(mean + 3.0 * st.rms);
-                st.prevC = c;
-                st.prevS = s;
-                if (fixed) st.done = 1;
+                wState[b] = st;
             }
-            s_state[b] = st;
+            myDone = myDone && (st.done != 0);
         }
-        __syncthreads();
-        bool allDone = true;
-        for (int b = 0; b < numBins; ++b) allDone = allDone && (s_state[b].done != 0);
-        if (allDone) break;
+        __syncwarp();
+        if (__all_sync(0xffffffffu, myDone)) break;   // the same decision in every warp
     }
-    for (int b = tid; b < numBins; b += OC_THREADS) tab[b] = s_state[b].rms;
+    if (wid == 0)
+        for (int b = lane; b < numBins; b += 32) tab[b] = wState[b].rms;
 }
 
 // every pixel takes the RMS of the last cell (raster order) that covers it, has rms > 0 and whose weight bin holds it
@@ -987,17 +1087,17 @@ static int cell_rms_t(const void* map, const void* wmed, int nImg, int S, int H,
     for (int i = 0; i < ny; ++i) maxH = std::max(maxH, std::min(ch.y[i + 1] + ov, H) - std::max(ch.y[i] - ov, 0));
     for (int k = 0; k < nx; ++k) maxW = std::max(maxW, std::min(ch.x[k + 1] + ov, W) - std::max(ch.x[k] - ov, 0));
     const long long maxCell = (long long)maxH * maxW;
-    // warp-contiguous runs of CH pixels, OC_PPT * 32 of them in registers, the rest in shared memory
-    const long long CH = ((((maxCell + OC_WARPS - 1) / OC_WARPS) + 31) / 32) * 32;
+    // 4 x 4 warp tiles; OC_PPT * 32 pixels of a tile live in registers, the rest in shared memory
+    const long long tilePix = (long long)((maxH + 3) / 4) * ((maxW + 3) / 4);
+    const long long CH = ((tilePix + 31) / 32) * 32;
     const long long perWarp = CH > (long long)OC_PPT * 32 ? CH - (long long)OC_PPT * 32 : 0;
     const long long smemSlots = perWarp * OC_WARPS;
-    const long long maxPix = ((maxCell + 15) / 16) * 16;
-    const bool fits = maxCell < (1LL << 24) && numBins <= OC_MAXBINS;
-    const size_t ocBytes = fits ? OcLayout<typename KeyOf<T>::type>(numBins, (int)smemSlots, (int)maxPix).total : (size_t)1 << 30;
+    const bool fits = maxCell < (1LL << 22) && numBins <= OC_MAXBINS;
+    const size_t ocBytes = fits ? OcLayout<typename KeyOf<T>::type>(numBins, (int)smemSlots).total : (size_t)1 << 30;
     if (ocBytes <= 226 * 1024) {
         NB_CHECK_CUDA(cudaFuncSetAttribute(cell_rms_onchip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ocBytes));
         { NB_PROF_BEGIN(st); cell_rms_onchip_kernel<T><<<dim3(ny * nx, nImg), OC_THREADS, ocBytes, st>>>(
-            (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges, (int)smemSlots, (int)maxPix); NB_PROF_END("cell_rms_onchip_kernel", st); }
+            (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges, (int)smemSlots); NB_PROF_END("cell_rms_onchip_kernel", st); }
     } else {
         { NB_PROF_BEGIN(st); cell_rms_stream_kernel<T><<<dim3(ny * nx, nImg), CR_THREADS, sizeof(double) * (numBins + 1), st>>>(
             (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges); NB_PROF_END("cell_rms_stream_kernel", st); }

@@ -123,24 +123,16 @@ def buildFourierFilters(ops, fmapsNoise, templUnit, templNorm, w, outputUnits, c
     else:
         raise Exception('need to specify "outputUnits" ("yc" or "uK") in filter params')
     # filteredSignal = applyFilter(fSignalMaps) with signalNorm still 1 (filters.py:653, 686)
-    filteredSignal = ops.empty((nOut, H, W))
-    scratch = ops.empty((S if not sigPerTile else nOut, H, Wc), ops.cdtype)
     if sigPerTile:
-        ops.apply_filter(fsigN, filtH, 1, out=filteredSignal, scratch=scratch)
+        filteredSignal = ops.apply_filter(fsigN, filtH, 1)
     else:
-        for t in range(nT):
-            ops.apply_filter(fsigN, filtH[t * S:(t + 1) * S], 1, out=filteredSignal[t * S:(t + 1) * S], scratch=scratch)
+        filteredSignal = ops.apply_filter(fsigN, filtH, S, perScale=True)
     if bckSubSigmas is not None:
         filteredSignal = ops.gauss_filter(filteredSignal, bckSubSigmas[0], bckSubSigmas[1], subtract=True)
     signalNorm, argmaxIdx, maxVal, centreVal = ops.template_norm(filteredSignal, mode, cy, cx, numer)
     fRel = None
     if outputUnits == 'yc':
-        if sigPerTile:
-            planes = ops.plane_values_at(fsigN, filtH, argmaxIdx)
-        else:
-            planes = ops.empty((nOut, F), torch.float64)
-            for t in range(nT):
-                planes[t * S:(t + 1) * S] = ops.plane_values_at(fsigN, filtH[t * S:(t + 1) * S].contiguous(), argmaxIdx[t * S:(t + 1) * S].contiguous())
+        planes = ops.plane_values_at(fsigN, filtH, argmaxIdx, S=0 if sigPerTile else S)
         # fRelWeight = plane value at the argmax pixel / total signal there (filters.py:664-670)
         fRel = (planes, maxVal)
     return {'filtH': filtH, 'filtFull': filtFull, 'signalNorm': signalNorm, 'fRel': fRel, 'S': S}

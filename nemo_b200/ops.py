@@ -86,14 +86,18 @@ class Ops(object):
         self.launches += 2
         return out
 
-    def apply_filter(self, fmaps, filtH, S, scale=1.0, norm=None, mask=None, out=None, scratch=None):
-        """out[o] = scale * norm[o] * mask[o // S] * Re(ifft2(sum_f fmaps[o // S, f] * filt[o, f]))."""
+    def apply_filter(self, fmaps, filtH, S, scale=1.0, norm=None, mask=None, out=None, scratch=None, perScale=False):
+        """out[o] = scale * norm[o] * mask[o // S] * Re(ifft2(sum_f fmaps[o // S, f] * filt[o, f])); with perScale the
+        spectra are those of S templates shared by every tile, fmaps[o % S]."""
         self._check(fmaps, self.cdtype, 'fmaps')
         self._check(filtH, self.dtype, 'filtH')
         nT, F, H, Wc = fmaps.shape
         nOut = filtH.shape[0]
         W = (Wc - 1) * 2
-        if nOut != nT * S or tuple(filtH.shape[1:]) != (F, H, Wc):
+        if perScale:
+            if nT != S or nOut % S != 0 or tuple(filtH.shape[1:]) != (F, H, Wc):
+                raise _lib.NemoB200Error("apply_filter: shape mismatch fmaps %s filtH %s S %d" % (tuple(fmaps.shape), tuple(filtH.shape), S))
+        elif nOut != nT * S or tuple(filtH.shape[1:]) != (F, H, Wc):
             raise _lib.NemoB200Error("apply_filter: shape mismatch fmaps %s filtH %s S %d" % (tuple(fmaps.shape), tuple(filtH.shape), S))
         if scratch is None:
             scratch = self.empty((nOut, H, Wc), self.cdtype)
@@ -103,7 +107,7 @@ class Ops(object):
             self._check(norm, self.torch.float64, 'norm')
         if mask is not None:
             self._check(mask, self.torch.uint8, 'mask')
-        _lib.call('nb_apply_filter', self.prec, _ptr(fmaps), _ptr(filtH), _ptr(scratch), _ptr(out), nOut, int(S), F, H, W,
+        _lib.call('nb_apply_filter', self.prec, _ptr(fmaps), _ptr(filtH), _ptr(scratch), _ptr(out), nOut, int(S), 1 if perScale else 0, F, H, W,
                   float(scale), _ptr(norm), _ptr(mask), self._stream())
         self.launches += 2
         return out
@@ -179,12 +183,13 @@ class Ops(object):
         self.launches += 1
         return norm, argmax, maxVal, centre
 
-    def plane_values_at(self, fmaps, filtH, idx):
+    def plane_values_at(self, fmaps, filtH, idx, S=0):
+        """Per-frequency filtered-template values at pixel idx[b]; S > 0: fmaps holds S template spectra shared by all tiles."""
         self._check(fmaps, self.cdtype, 'fmaps')
         self._check(filtH, self.dtype, 'filtH')
-        B, F, H, Wc = fmaps.shape
+        B, F, H, Wc = filtH.shape
         out = self.empty((B, F), self.torch.float64)
-        _lib.call('nb_plane_values_at', self.prec, _ptr(fmaps), _ptr(filtH), _ptr(idx), _ptr(out), B, F, H, (Wc - 1) * 2, self._stream())
+        _lib.call('nb_plane_values_at', self.prec, _ptr(fmaps), _ptr(filtH), _ptr(idx), _ptr(out), B, int(S), F, H, (Wc - 1) * 2, self._stream())
         self.launches += 1
         return out
 
