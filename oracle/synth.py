@@ -89,19 +89,19 @@ def makeMapDict(data, weights, wcs, obsFreqGHz, beam, label, units='uK', surveyM
 
 def makeTile(shape=(1024, 1024), freqsGHz=(148.0,), noiseUK=(50.0,), beamFWHMArcmin=(1.4,), seed=1234,
              kind='clusters', numObjects=30, cmb=False, borderPix=0, psHoles=0, theta500Arcmin=2.4,
-             clusterProfile=None, dtype=np.float64):
+             clusterProfile=None, dtype=np.float64, margin=60):
     """One synthetic tile: list of per-frequency map dicts + truth table.
 
     kind = 'clusters' : Arnaud-like decrements, y0 in [0.5, 5]e-4 converted per frequency (config 1, 3-5)
            'sources'  : positive point sources, deltaT ~ lognormal(ln 600, 1.1) uK (config 2)
     borderPix > 0 zeroes a border of that width in data/weights/surveyMask (a tile with a zero edge, which
     is what edgeTrimArcmin acts on, filters.py:725-727).  psHoles punches that many 8-px-radius holes in
-    the point-source mask.
+    the point-source mask.  Objects are kept `margin` pixels away from the (zeroed) edge.
     """
     rng = np.random.default_rng(seed)
     H, W = shape
     wcs = SimpleCARWCS(shape, PIX_DEG)
-    margin = 60 + borderPix
+    margin = margin + borderPix
     xs = rng.uniform(margin, W - margin, numObjects)
     ys = rng.uniform(margin, H - margin, numObjects)
     if kind == 'clusters':

@@ -1,0 +1,151 @@
+"""
+CPU tests of the oracle (oracle/): the committed golden fixtures (tests/golden/*.npz, made by
+tests/golden/make_golden.py) and known answers for the restated third-party pieces.  The reference ships no
+golden vectors for this path, so these pin the oracle itself: if its arithmetic drifts, they fail.
+"""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+from scipy import ndimage
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+
+import make_golden  # noqa: E402
+from oracle import pixell_shim as enmap, filters_ref, photometry_ref, signals_ref, synth  # noqa: E402
+from oracle.wcs_stub import SimpleCARWCS, calcAngSepDeg, j2000ToGalactic  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.CASES.keys()))
+def test_oracle_reproduces_golden_fixture(name):
+    gold = np.load(os.path.join(HERE, 'golden', name + '.npz'))
+    mapDicts, out = make_golden.runCase(name)
+    assert list(out['input_sha256']) == list(gold['input_sha256']), "the seeded input generator changed"
+    assert np.array_equal(out['surveyMask'], gold['surveyMask'])
+    assert np.array_equal(out['segmentation'], gold['segmentation'])
+    assert int(out['numObjects']) == int(gold['numObjects'])
+    # identical machine arithmetic reproduces bit for bit; a different BLAS/FFT build may differ in the last digits
+    np.testing.assert_allclose(out['SNMap'], gold['SNMap'], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(out['data'], gold['data'], rtol=1e-9, atol=1e-9 * np.abs(gold['data']).max())
+    assert abs(float(out['signalNorm']) / float(gold['signalNorm']) - 1) < 1e-10
+    for k in gold.files:
+        if k.startswith('cat_') and k != 'cat_name':
+            np.testing.assert_allclose(out[k], gold[k], rtol=1e-8, atol=1e-10)
+    assert list(out['cat_name']) == list(gold['cat_name'])
+
+
+def test_apod_profile_matches_pixell_semantics():
+    """enmap.apod(m, 20): cosine taper over the first / last 20 samples, first sample 0, 20th exactly 1
+    (filters.py:528, 749: `apod(ones) == 1` trims 19 pixels per edge)."""
+    a = enmap.apod(np.ones((64, 80)), 20)
+    assert a[0, 40] == 0.0 and a[40, 0] == 0.0
+    assert a[19, 40] == 1.0 and a[40, 19] == 1.0 and a[18, 40] < 1.0
+    inner = (a == 1)
+    assert inner[19:-19, 19:-19].all() and inner.sum() == (64 - 38) * (80 - 38)
+    assert np.allclose(a[5, 40], 0.5 * (1 - np.cos(np.pi * 5 / 19)))
+    assert np.allclose(a, a[::-1, ::-1])
+
+
+def test_fft_conventions():
+    """enmap.fft normalises by sqrt(Npix) (Parseval holds); enmap.ifft(normalize=False) is the bare inverse sum."""
+    rng = np.random.default_rng(0)
+    m = rng.standard_normal((32, 48))
+    fm = enmap.fft(m)
+    assert np.allclose((np.abs(fm) ** 2).sum(), (m ** 2).sum())
+    assert np.allclose(enmap.ifft(fm, normalize=True).real, m)
+    assert np.allclose(enmap.ifft(fm, normalize=False).real, m * np.sqrt(32 * 48))
+
+
+def test_apply_window_known_answer():
+    """Order-0 pixel window: a single Fourier mode is scaled by sinc(fy) sinc(fx); pow=-1 undoes pow=+1."""
+    H, W = 32, 64
+    ky, kx = 3, 5
+    yy, xx = np.mgrid[:H, :W]
+    mode = np.cos(2 * np.pi * (ky * yy / H + kx * xx / W))
+    out = enmap.apply_window(mode, pow=1.0)
+    assert np.allclose(out, mode * np.sinc(ky / H) * np.sinc(kx / W))
+    rng = np.random.default_rng(1)
+    m = rng.standard_normal((H, W))
+    assert np.allclose(enmap.apply_window(enmap.apply_window(m, 1.0), -1.0), m)
+
+
+def test_wcs_stub_round_trip_and_separation():
+    wcs = SimpleCARWCS((100, 200), 0.5 / 60, crval=(10.0, -2.0))
+    x, y = wcs.wcs2pix(*wcs.pix2wcs(12.25, 80.5))
+    assert abs(x - 12.25) < 1e-9 and abs(y - 80.5) < 1e-9
+    ra, dec = wcs.getCentreWCSCoords()
+    assert abs(ra - 10.0) < 1e-12 and abs(dec + 2.0) < 1e-12
+    assert abs(calcAngSepDeg(10.0, 0.0, 10.0, 1.0) - np.degrees(np.tan(np.radians(1.0)))) < 1e-12
+    # Galactic centre and north Galactic pole (J2000)
+    l, b = j2000ToGalactic(266.40499, -28.93617)
+    assert abs(b) < 0.01 and (abs(l) < 0.01 or abs(l - 360) < 0.01)
+    l, b = j2000ToGalactic(192.85948, 27.12825)
+    assert abs(b - 90) < 0.01
+
+
+def test_names_follow_the_reference_string_slicing():
+    """catalogs.py:259-346: digits are cut from printed values, never rounded."""
+    assert photometry_ref.makeName(10.0, -1.0) == "ACT-CL J0040.0-0100"
+    assert photometry_ref.makeName(359.9999, 45.9999) == "ACT-CL J2359.9+4559"
+    assert photometry_ref.makeName(15.0 * 1.5 + 15.0 * 0.99 / 60, 0.5) == "ACT-CL J0130.9+0030"
+    assert photometry_ref.makeName(150.0, -12.51, prefix='MOCK-S') == "MOCK-S J1000.0-1230"
+
+
+def test_signal_conversions():
+    assert abs(signals_ref.fSZ(217.0)) < 0.01                    # SZ null
+    assert signals_ref.fSZ(148.0) < 0 < signals_ref.fSZ(280.0)
+    assert np.isclose(signals_ref.convertToDeltaT(1e-4, 148.0), 2.7255e6 * 1e-4 * signals_ref.fSZ(148.0), rtol=1e-3)
+    # Jy/sr conversion is linear in temperature
+    assert np.isclose(signals_ref.deltaTToJyPerSr(2.0, 150.0), 2 * signals_ref.deltaTToJyPerSr(1.0, 150.0))
+
+
+def test_make_noise_map_last_writer_wins_and_asymmetric_clip():
+    """filters.py:409-481: cells extended by half a cell, later cells overwrite earlier ones in the overlaps, the clip
+    test is |v| < |mean + 3 sigma| (not |v - mean|)."""
+    rng = np.random.default_rng(3)
+    H = W = 160
+    pixDeg = 0.5 / 60
+    data = rng.standard_normal((H, W))
+    data[:, W // 2:] *= 4.0
+    wcs = SimpleCARWCS((H, W), pixDeg)
+    md = [{'data': data, 'weights': np.ones((H, W)), 'wcs': wcs, 'flagMask': np.zeros((H, W), np.uint8), 'obsFreqGHz': 150.0,
+           'label': 'x', 'surveyMask': None, 'pointSourceMask': None}]
+    f = filters_ref.MapFilter('t', md, {'noiseParams': {'noiseGridArcmin': 20.0}})
+    rms = f.makeNoiseMap(data)
+    def clipped(cell):
+        mean, sig = cell.mean(), cell.std()
+        for _ in range(10):
+            sel = cell[np.abs(cell) < abs(mean + 3 * sig)]
+            mean, sig = sel.mean(), sel.std()
+        return sig
+
+    # cells are [40 i - 20, 40 (i + 1) + 20) along each axis, clipped to the map
+    # bottom-right pixel belongs only to the last cell
+    assert np.isclose(rms[-1, -1], clipped(data[100:, 100:]), rtol=1e-12)
+    # pixel (45, 45) lies in cells (0,0), (0,1), (1,0), (1,1): the LAST one in raster order wins
+    assert np.isclose(rms[45, 45], clipped(data[20:100, 20:100]), rtol=1e-12)
+    assert not np.isclose(rms[45, 45], clipped(data[0:60, 0:60]), rtol=1e-6)
+    # pixel (45, 65) also lies in cells (0,2), (1,2): cell (1,2) = rows [20,100), cols [60,140) wins
+    assert np.isclose(rms[45, 65], clipped(data[20:100, 60:140]), rtol=1e-12)
+    assert len(np.unique(rms)) <= 16
+
+
+def test_get_object_positions_matches_scipy_numbering():
+    rng = np.random.default_rng(5)
+    sn = ndimage.gaussian_filter(rng.standard_normal((96, 96)), 1.5) * 12
+    ids, pos, npix, seg = photometry_ref.getObjectPositions(sn, 4.0)
+    lab, n = ndimage.label(sn > 4.0)
+    assert np.array_equal(seg, lab) and ids[0] == 0 and len(ids) == n + 1
+    assert npix[0] == 0 and npix[1:].sum() == (sn > 4.0).sum()
+    com = ndimage.center_of_mass(sn, lab, np.arange(1, n + 1))
+    assert np.allclose(np.array(pos[1:]), np.array(com))
+
+
+def test_synth_is_seeded():
+    a, _ = synth.makeTile(shape=(64, 64), numObjects=2, seed=9, margin=20)
+    b, _ = synth.makeTile(shape=(64, 64), numObjects=2, seed=9, margin=20)
+    c, _ = synth.makeTile(shape=(64, 64), numObjects=2, seed=10, margin=20)
+    assert np.array_equal(a[0]['data'], b[0]['data']) and not np.array_equal(a[0]['data'], c[0]['data'])
