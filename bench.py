@@ -112,19 +112,13 @@ def algorithmicBytes(nT, F, S, H, W, E, rings=True):
     b['build_filter_kernel'] = nT * P * N * 8 + nOut * F * Nc * 2 * E + nOut * F * Nc * E
     b['fft_cols_apply_kernel'] = 2 * nOut * (F * Nc * 2 * E + F * Nc * E + Nc * 2 * E)     # templates + maps
     b['irfft_rows_kernel'] = nOut * (Nc * 2 * E + N * E) + nOut * (Nc * 2 * E + N * E + N) + nOut * (Nc * 2 * E + 2 * N * E)
-    b['template_norm_kernel'] = nOut * N * E
+    b['template_argmax_partial_kernel'] = nOut * N * E
     b['cell_rms_kernel'] = nOut * 2 * N * E
     b['paint_rms_kernel'] = nOut * 2 * N * E
     b['edge_rows_kernel'] = nOut * (N * E + 2 * N)
     b['edge_cols_final_kernel'] = nOut * (2 * N * E + 3 * N + 3 * N * E + N)
     b['fft_cols_window_kernel'] = nOut * 2 * Nc * 2 * E
-    b['label_init_img_kernel'] = nPass * nOut * (N * E + 4 * N)
-    b['label_merge_kernel'] = nPass * nOut * 8 * N
-    b['label_flatten_kernel'] = nPass * nOut * 8 * N
-    b['label_rank_kernel'] = nPass * nOut * 4 * N
-    b['label_final_kernel'] = nPass * nOut * 8 * N
-    b['moments_accum_kernel'] = nPass * nOut * (N * E + 4 * N)
-    b['moments_argmax_kernel'] = nPass * nOut * (N * E + 4 * N)
+    b['detect_scan_kernel'] = nPass * nOut * (N * E + 4 * N)      # S/N read, zeroed label image written; the rest is sparse
     return b
 
 
@@ -216,7 +210,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default='f64', choices=['f64', 'f32'])
     ap.add_argument('--tiles', type=int, default=TILES_PER_GPU, help='tiles per GPU')
-    ap.add_argument('--tiles-per-batch', type=int, default=16)
+    ap.add_argument('--tiles-per-batch', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--kernel-table', default=None, help='write the per-kernel roofline table to this file')
     args = ap.parse_args()
@@ -272,11 +266,8 @@ def main():
     torch.cuda.synchronize()
 
     def deviceStep():
-        n = 0
-        for b in batches:
-            cd, extras = pipelines.filterTileBatch(ops, b, filtersList, templates, parDict, undoPixelWindow=True)
-            n += sum(len(v['catalog']) for v in cd.values())
-        return n
+        results = pipelines.processBatches(ops, batches, filtersList, templates, parDict, upload=False, undoPixelWindow=True)
+        return sum(len(v['catalog']) for cd, _ in results for v in cd.values())
 
     for _ in range(args.warmup):
         nObj = deviceStep()

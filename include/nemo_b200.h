@@ -89,9 +89,9 @@ int nb_fold_filter(int prec, const double* filtFull, void* filtH, int n, int H, 
 /* K5: normalisation scalars (nemo/filters.py:653-670, 686-687).  For each image b of map [B, H, W]:
  * argmaxIdx[b] = np.argmax (first maximum in raster order), maxVal[b] its value, and, when mode == 1 ('yc'),
  * centreVal[b] = bicubic-spline value at (cy, cx) (RectBivariateSpline(...)(cy, cx)); mode 0 skips it.
- * signalNorm[b] = numer / (mode == 1 ? centreVal[b] : maxVal[b]). */
+ * signalNorm[b] = numer / (mode == 1 ? centreVal[b] : maxVal[b]).  scratch: B * 1024 bytes. */
 int nb_template_norm(int prec, const void* map, int B, int H, int W, int mode, double cy, double cx, double numer,
-                     long long* argmaxIdx, double* maxVal, double* centreVal, double* signalNorm,
+                     long long* argmaxIdx, double* maxVal, double* centreVal, double* signalNorm, void* scratch,
                      cudaStream_t stream);
 
 /* fRelWeights (nemo/filters.py:664-670): value at pixel idx[b] of each frequency plane of
@@ -142,6 +142,25 @@ long long nb_label4_scratch_ints(int B, int H, int W);
  * labels above maxLabels are ignored (compare nLabels to detect overflow).  v = sign * map. */
 int nb_label_moments(int prec, const void* map, double sign, const int* labels, double* table, int B, int H, int W,
                      int maxLabels, cudaStream_t stream);
+
+/* K9 + K10 in one asynchronous call, for sparse foregrounds (the usual case above a detection threshold): one dense pass
+ * over the map, then linking / numbering / moments over a compact list of the foreground pixels.  Same outputs as
+ * nb_label4 + nb_label_moments (labels [B, H, W], nLabels [B], table [B, maxLabels + 1, 8]); flags bit 0 asks for the
+ * first-arg-max columns (ndimage.maximum_position, findCenterOfMass = False).  status [B] int32 is set to 1 for an image
+ * whose foreground (> H*W/8 pixels) or component count (> 8192) exceeds the compact structures: its outputs are then
+ * invalid and the caller must use nb_label4 / nb_label_moments.  scratch: nb_detect_scratch_ints(B, H, W) int32 words. */
+int nb_detect(int prec, const void* map, double threshold, double sign, int* labels, int* nLabels, int* status,
+              double* table, int maxLabels, int* scratch, int B, int H, int W, int flags, cudaStream_t stream);
+long long nb_detect_scratch_ints(int B, int H, int W);
+
+/* Ring removal of findObjects (nemo/photometry.py:60-70, 104-105).  detTable / detN: moment table and label counts at the
+ * detection threshold; ringLabels / ringTable: segmentation and moment table at ringThresholdSigma (both from nb_detect or
+ * nb_label4 + nb_label_moments, row widths detCap + 1 and ringCap + 1).  flags [B, detCap + 1] u8 = 1 for a candidate whose
+ * position (centre of mass when posMode = 0, first maximum when 1) lies on a ring-threshold component of more than
+ * minRingPix pixels that does not contain its own centre of mass. */
+int nb_ring_flags(const double* detTable, const int* detN, int detCap, const int* ringLabels, const double* ringTable,
+                  int ringCap, int B, int H, int W, double minRingPix, int posMode, unsigned char* flags,
+                  cudaStream_t stream);
 
 /* K11: interpolate.RectBivariateSpline(arange(H), arange(W), img, kx=3, ky=3)(y, x) at K points
  * (nemo/photometry.py:76-79, 122, 243-253, 295-333; filters.py:657-660).  imgIdx [K] int32 selects the image,

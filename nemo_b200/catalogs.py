@@ -84,6 +84,11 @@ class _Deferred(object):
         return _Deferred(lambda: fn(self.value()))
 
 
+def deferred(maker):
+    """A column value for Table.fromColumns that is computed by ``maker()`` when first read."""
+    return _Deferred(maker)
+
+
 class Table(object):
     """Minimal stand-in for astropy.table.Table."""
 
@@ -92,6 +97,14 @@ class Table(object):
         if names is not None:
             for n in names:
                 self._cols[n] = np.zeros(0)
+
+    @classmethod
+    def fromColumns(cls, pairs):
+        """Table from (name, array or deferred(...)) pairs of equal length, without per-column checks."""
+        tab = cls()
+        for name, data in pairs:
+            tab._cols.put(name, data)
+        return tab
 
     def add_deferred_column(self, name, maker):
         """Column whose values are produced by ``maker()`` the first time it is read (object names are only

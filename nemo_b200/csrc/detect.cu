@@ -351,3 +351,343 @@ int nb_spline_eval(int prec, const void* img, int B, int H, int W, const int* im
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------
+// K9 + K10 fused for sparse foregrounds (nb_detect).  Above a detection threshold only ~0.1-1 % of an S/N map is
+// foreground, so only ONE dense pass is made (threshold, background moments, zeroed label image, compact list of
+// the foreground pixels); linking, root finding, ranking, labelling and the per-label moments then run over the
+// list.  Numbering is scipy's: roots are the smallest linear index of their component and are ranked in index order.
+#define DT_THREADS 256
+#define DT_ITEMS 8
+#define DT_ROOTCAP 8192
+
+struct DetectScratch {
+    int* L;          // [B, HW] parent pointers, touched only at foreground pixels
+    int* fgList;     // [B, listCap]
+    int* rootList;   // [B, DT_ROOTCAP]
+    int* fgCount;    // [B]
+    int* rootCount;  // [B]
+    int listCap;
+};
+
+__host__ __device__ inline long long detect_list_cap(int H, int W) {
+    long long c = ((long long)H * W) / 8;
+    return c < 4096 ? 4096 : c;
+}
+
+__global__ void detect_reset_kernel(int* __restrict__ fgCount, int* __restrict__ rootCount, int* __restrict__ status, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) {
+        fgCount[i] = 0;
+        rootCount[i] = 0;
+        status[i] = 0;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(DT_THREADS) detect_scan_kernel(const T* __restrict__ map, double thr, double sign,
+                                                                 int* __restrict__ labels, DetectScratch sc, double* __restrict__ table,
+                                                                 int* __restrict__ status, int H, int W, int maxLabels) {
+    const int HW = H * W;
+    const int img = blockIdx.y;
+    const T* m = map + (size_t)img * HW;
+    int* lab = labels + (size_t)img * HW;
+    int* L = sc.L + (size_t)img * HW;
+    int* list = sc.fgList + (size_t)img * sc.listCap;
+    const int lane = threadIdx.x & 31;
+    double s0 = 0, sy0 = 0, sx0 = 0, c0 = 0, mx0 = -INFINITY;
+    const int base = blockIdx.x * (DT_THREADS * DT_ITEMS) + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < DT_ITEMS; ++k) {
+        const int p = base + k * DT_THREADS;
+        const bool in = p < HW;
+        const double v = in ? sign * (double)m[p] : 0.0;
+        const bool fg = in && (v > thr);
+        if (in) lab[p] = 0;
+        if (in && !fg) {
+            const int y = p / W, x = p - y * W;
+            s0 += v;
+            sy0 += v * (double)y;
+            sx0 += v * (double)x;
+            c0 += 1.0;
+            mx0 = fmax(mx0, v);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, fg);
+        if (bal) {
+            int start = 0;
+            if (lane == 0) start = atomicAdd(&sc.fgCount[img], __popc(bal));
+            start = __shfl_sync(0xffffffffu, start, 0);
+            if (fg) {
+                const int pos = start + __popc(bal & ((1u << lane) - 1u));
+                L[p] = p;
+                if (pos < sc.listCap) list[pos] = p;
+                else status[img] = 1;
+            }
+        }
+    }
+    s0 = warp_sum(s0);
+    sy0 = warp_sum(sy0);
+    sx0 = warp_sum(sx0);
+    c0 = warp_sum(c0);
+    mx0 = warp_max(mx0);
+    __shared__ double s_b[DT_THREADS / 32][5];
+    if (lane == 0) {
+        double* r = s_b[threadIdx.x >> 5];
+        r[0] = s0; r[1] = sy0; r[2] = sx0; r[3] = c0; r[4] = mx0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c = 0, d = 0, e = -INFINITY;
+        for (int w = 0; w < DT_THREADS / 32; ++w) {
+            a += s_b[w][0]; b += s_b[w][1]; c += s_b[w][2]; d += s_b[w][3]; e = fmax(e, s_b[w][4]);
+        }
+        if (d > 0) {
+            double* tab = table + (size_t)img * (maxLabels + 1) * 8;
+            atomicAdd(tab + 0, a);
+            atomicAdd(tab + 1, b);
+            atomicAdd(tab + 2, c);
+            atomicAdd(tab + 3, d);
+            atomicMax(reinterpret_cast<unsigned long long*>(tab) + 4, enc_ordered(e));
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) detect_link_kernel(const T* __restrict__ map, double thr, double sign, DetectScratch sc, int H, int W) {
+    const int HW = H * W;
+    const int img = blockIdx.y;
+    const T* m = map + (size_t)img * HW;
+    int* L = sc.L + (size_t)img * HW;
+    const int* list = sc.fgList + (size_t)img * sc.listCap;
+    const int n = min(sc.fgCount[img], sc.listCap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = list[i];
+        const int x = p % W;
+        if (x > 0 && sign * (double)m[p - 1] > thr) uf_union(L, p, p - 1);
+        if (p >= W && sign * (double)m[p - W] > thr) uf_union(L, p, p - W);
+    }
+}
+
+__global__ void __launch_bounds__(256) detect_flatten_kernel(DetectScratch sc, int* __restrict__ status, int HW) {
+    const int img = blockIdx.y;
+    int* L = sc.L + (size_t)img * HW;
+    const int* list = sc.fgList + (size_t)img * sc.listCap;
+    int* roots = sc.rootList + (size_t)img * DT_ROOTCAP;
+    const int n = min(sc.fgCount[img], sc.listCap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = list[i];
+        const int r = uf_find(L, p);
+        if (r == p) {
+            const int pos = atomicAdd(&sc.rootCount[img], 1);
+            if (pos < DT_ROOTCAP) roots[pos] = p;
+            else status[img] = 1;
+        } else {
+            L[p] = r;  // roots are never rewritten, so concurrent finds stay valid
+        }
+    }
+}
+
+// one CTA per image: sort the roots by pixel index (bitonic, shared memory) and store -(rank + 2) at each root
+__global__ void __launch_bounds__(1024) detect_rank_kernel(DetectScratch sc, int* __restrict__ nLabels, int HW) {
+    __shared__ int s_r[DT_ROOTCAP];
+    const int img = blockIdx.x;
+    int* L = sc.L + (size_t)img * HW;
+    const int* roots = sc.rootList + (size_t)img * DT_ROOTCAP;
+    const int R = min(sc.rootCount[img], DT_ROOTCAP);
+    int n2 = 1;
+    while (n2 < R) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) s_r[i] = (i < R) ? roots[i] : 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const int a = s_r[i], b = s_r[ixj];
+                    const bool up = ((i & k) == 0);
+                    if ((a > b) == up) {
+                        s_r[i] = b;
+                        s_r[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < R; i += blockDim.x) L[s_r[i]] = -(i + 2);
+    if (threadIdx.x == 0) nLabels[img] = sc.rootCount[img];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) detect_moments_kernel(const T* __restrict__ map, double sign, DetectScratch sc,
+                                                             int* __restrict__ labels, double* __restrict__ table, int H, int W,
+                                                             int maxLabels) {
+    const int HW = H * W;
+    const int img = blockIdx.y;
+    const T* m = map + (size_t)img * HW;
+    const int* L = sc.L + (size_t)img * HW;
+    int* lab = labels + (size_t)img * HW;
+    const int* list = sc.fgList + (size_t)img * sc.listCap;
+    double* tab = table + (size_t)img * (maxLabels + 1) * 8;
+    const int n = min(sc.fgCount[img], sc.listCap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = list[i];
+        const int v0 = L[p];
+        const int l = (v0 <= -2) ? (-v0 - 1) : (-L[v0] - 1);
+        if (l < 1) continue;   // an unranked root: only when the compact structures overflowed (status is set)
+        lab[p] = l;
+        if (l <= maxLabels) {
+            const double v = sign * (double)m[p];
+            const int y = p / W, x = p - y * W;
+            double* t = tab + (size_t)l * 8;
+            atomicAdd(t + 0, v);
+            atomicAdd(t + 1, v * (double)y);
+            atomicAdd(t + 2, v * (double)x);
+            atomicAdd(t + 3, 1.0);
+            atomicMax(reinterpret_cast<unsigned long long*>(t) + 4, enc_ordered(v));
+            atomicMin(reinterpret_cast<unsigned long long*>(t) + 6, (unsigned long long)__double_as_longlong((double)p));
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) detect_argmax_kernel(const T* __restrict__ map, double sign, DetectScratch sc,
+                                                            const int* __restrict__ labels, double* __restrict__ table, int HW, int maxLabels) {
+    const int img = blockIdx.y;
+    const T* m = map + (size_t)img * HW;
+    const int* lab = labels + (size_t)img * HW;
+    const int* list = sc.fgList + (size_t)img * sc.listCap;
+    double* tab = table + (size_t)img * (maxLabels + 1) * 8;
+    const int n = min(sc.fgCount[img], sc.listCap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = list[i];
+        const int l = lab[p];
+        if (l < 1 || l > maxLabels) continue;
+        double* t = tab + (size_t)l * 8;
+        if (enc_ordered(sign * (double)m[p]) == reinterpret_cast<const unsigned long long*>(t)[4])
+            atomicMin(reinterpret_cast<unsigned long long*>(t) + 5, (unsigned long long)__double_as_longlong((double)p));
+    }
+}
+
+// first arg-max of the background (label 0), dense; only when the caller asks for maximum positions
+template <typename T>
+__global__ void __launch_bounds__(256) detect_bg_argmax_kernel(const T* __restrict__ map, double sign, const int* __restrict__ labels,
+                                                               double* __restrict__ table, int HW, int maxLabels) {
+    const int img = blockIdx.y;
+    const T* m = map + (size_t)img * HW;
+    const int* lab = labels + (size_t)img * HW;
+    double* t = table + (size_t)img * (maxLabels + 1) * 8;
+    const unsigned long long want = reinterpret_cast<const unsigned long long*>(t)[4];
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+        if (lab[p] == 0 && enc_ordered(sign * (double)m[p]) == want)
+            atomicMin(reinterpret_cast<unsigned long long*>(t) + 5, (unsigned long long)__double_as_longlong((double)p));
+    }
+}
+
+template <typename T>
+static int detect_t(const T* map, double thr, double sign, int* labels, int* nLabels, int* status, double* table, int maxLabels,
+                    int* scratch, int B, int H, int W, int flags, cudaStream_t st) {
+    const int HW = H * W;
+    DetectScratch sc;
+    sc.listCap = (int)detect_list_cap(H, W);
+    sc.L = scratch;
+    sc.fgList = sc.L + (size_t)B * HW;
+    sc.rootList = sc.fgList + (size_t)B * sc.listCap;
+    sc.fgCount = sc.rootList + (size_t)B * DT_ROOTCAP;
+    sc.rootCount = sc.fgCount + B;
+    const long long nRows = (long long)B * (maxLabels + 1);
+    { NB_PROF_BEGIN(st); detect_reset_kernel<<<(B + 255) / 256, 256, 0, st>>>(sc.fgCount, sc.rootCount, status, B); NB_PROF_END("detect_reset_kernel", st); }
+    NB_CHECK_LAUNCH();
+    { NB_PROF_BEGIN(st); moments_init_kernel<<<(unsigned)((nRows + 255) / 256), 256, 0, st>>>(table, nRows); NB_PROF_END("moments_init_kernel", st); }
+    NB_CHECK_LAUNCH();
+    dim3 gridDense((HW + DT_THREADS * DT_ITEMS - 1) / (DT_THREADS * DT_ITEMS), B);
+    { NB_PROF_BEGIN(st); detect_scan_kernel<T><<<gridDense, DT_THREADS, 0, st>>>(map, thr, sign, labels, sc, table, status, H, W, maxLabels); NB_PROF_END("detect_scan_kernel", st); }
+    NB_CHECK_LAUNCH();
+    dim3 gridSparse(64, B);
+    { NB_PROF_BEGIN(st); detect_link_kernel<T><<<gridSparse, 256, 0, st>>>(map, thr, sign, sc, H, W); NB_PROF_END("detect_link_kernel", st); }
+    NB_CHECK_LAUNCH();
+    { NB_PROF_BEGIN(st); detect_flatten_kernel<<<gridSparse, 256, 0, st>>>(sc, status, HW); NB_PROF_END("detect_flatten_kernel", st); }
+    NB_CHECK_LAUNCH();
+    { NB_PROF_BEGIN(st); detect_rank_kernel<<<B, 1024, 0, st>>>(sc, nLabels, HW); NB_PROF_END("detect_rank_kernel", st); }
+    NB_CHECK_LAUNCH();
+    { NB_PROF_BEGIN(st); detect_moments_kernel<T><<<gridSparse, 256, 0, st>>>(map, sign, sc, labels, table, H, W, maxLabels); NB_PROF_END("detect_moments_kernel", st); }
+    NB_CHECK_LAUNCH();
+    if (flags & 1) {
+        { NB_PROF_BEGIN(st); detect_argmax_kernel<T><<<gridSparse, 256, 0, st>>>(map, sign, sc, labels, table, HW, maxLabels); NB_PROF_END("detect_argmax_kernel", st); }
+        NB_CHECK_LAUNCH();
+        dim3 gridBg((HW + 256 * 8 - 1) / (256 * 8), B);
+        { NB_PROF_BEGIN(st); detect_bg_argmax_kernel<T><<<gridBg, 256, 0, st>>>(map, sign, labels, table, HW, maxLabels); NB_PROF_END("detect_bg_argmax_kernel", st); }
+        NB_CHECK_LAUNCH();
+    }
+    { NB_PROF_BEGIN(st); moments_final_kernel<<<(unsigned)((nRows + 255) / 256), 256, 0, st>>>(table, nRows); NB_PROF_END("moments_final_kernel", st); }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+// Ring removal (photometry.py:60-70, 104-105) on the device: a candidate is dropped when the ring-threshold component under its
+// position has more than minRingPix pixels and does not contain its own centre of mass.  One thread per candidate label.
+__global__ void __launch_bounds__(256) ring_flags_kernel(const double* __restrict__ detTable, const int* __restrict__ detN, int detCap,
+                                                         const int* __restrict__ ringLabels, const double* __restrict__ ringTable,
+                                                         int ringCap, int H, int W, double minRingPix, int posMode,
+                                                         unsigned char* __restrict__ flags) {
+    const int b = blockIdx.y;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o > detCap) return;
+    unsigned char out = 0;
+    if (o >= 1 && o <= detN[b]) {
+        const double* t = detTable + ((size_t)b * (detCap + 1) + o) * 8;
+        double y, x;
+        if (posMode == 0) {
+            y = t[1] / t[0];
+            x = t[2] / t[0];
+        } else {
+            y = floor(t[5] / (double)W);
+            x = t[5] - y * (double)W;
+        }
+        if (y == y && x == x) {
+            const int yi = min(max((int)y, 0), H - 1), xi = min(max((int)x, 0), W - 1);
+            const int* rl = ringLabels + (size_t)b * H * W;
+            const int r = rl[(size_t)yi * W + xi];
+            if (r > 0 && r <= ringCap) {
+                const double* rt = ringTable + ((size_t)b * (ringCap + 1) + r) * 8;
+                if (rt[3] > minRingPix) {
+                    const double ry = rt[1] / rt[0], rx = rt[2] / rt[0];
+                    const int ryi = min(max((int)ry, 0), H - 1), rxi = min(max((int)rx, 0), W - 1);
+                    if (rl[(size_t)ryi * W + rxi] != r) out = 1;
+                }
+            }
+        }
+    }
+    flags[(size_t)b * (detCap + 1) + o] = out;
+}
+
+extern "C" {
+
+int nb_ring_flags(const double* detTable, const int* detN, int detCap, const int* ringLabels, const double* ringTable, int ringCap,
+                  int B, int H, int W, double minRingPix, int posMode, unsigned char* flags, cudaStream_t st) {
+    NB_REQUIRE(detTable && detN && ringLabels && ringTable && flags && B > 0 && detCap >= 0 && ringCap >= 0, NB_ERR_ARG,
+               "nb_ring_flags: bad arguments");
+    { NB_PROF_BEGIN(st); ring_flags_kernel<<<dim3((detCap + 1 + 255) / 256, B), 256, 0, st>>>(detTable, detN, detCap, ringLabels, ringTable, ringCap, H, W, minRingPix, posMode, flags); NB_PROF_END("ring_flags_kernel", st); }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+long long nb_detect_scratch_ints(int B, int H, int W) {
+    const long long HW = (long long)H * W;
+    return (long long)B * (HW + detect_list_cap(H, W) + DT_ROOTCAP + 2);
+}
+
+int nb_detect(int prec, const void* map, double threshold, double sign, int* labels, int* nLabels, int* status, double* table,
+              int maxLabels, int* scratch, int B, int H, int W, int flags, cudaStream_t st) {
+    NB_REQUIRE(map && labels && nLabels && status && table && scratch && B > 0 && H > 0 && W > 0 && maxLabels >= 0, NB_ERR_ARG,
+               "nb_detect: bad arguments");
+    NB_REQUIRE((long long)H * W < 0x7fffffffLL, NB_ERR_UNSUPPORTED, "nb_detect: image too large");
+    if (prec == NB_PREC_F64)
+        return detect_t<double>((const double*)map, threshold, sign, labels, nLabels, status, table, maxLabels, scratch, B, H, W, flags, st);
+    if (prec == NB_PREC_F32)
+        return detect_t<float>((const float*)map, threshold, sign, labels, nLabels, status, table, maxLabels, scratch, B, H, W, flags, st);
+    nb_set_error("nb_detect: bad precision %d", prec);
+    return NB_ERR_ARG;
+}
+
+}  // extern "C"

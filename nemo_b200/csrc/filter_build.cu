@@ -218,35 +218,23 @@ __global__ void __launch_bounds__(256) fold_filter_kernel(const double* __restri
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K5.  One CTA per image: first maximum in raster order; optional spline value at (cy, cx).
-template <typename T>
-__global__ void __launch_bounds__(1024) template_norm_kernel(const T* __restrict__ map, int H, int W, int mode,
-                                                             double cy, double cx, double numer,
-                                                             long long* __restrict__ argmaxIdx, double* __restrict__ maxVal,
-                                                             double* __restrict__ centreVal, double* __restrict__ signalNorm) {
-    const int b = blockIdx.x;
-    const T* img = map + (size_t)b * H * W;
-    const long long n = (long long)H * W;
-    double best = -INFINITY;
-    long long bi = n;
-    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-        const double v = (double)img[i];
-        if (v > best) {  // strided scan visits increasing i, so the first maximum per thread is kept
-            best = v;
-            bi = i;
-        }
+// K5.  First maximum in raster order and optional spline value at (cy, cx).  Stage 1: TN_PARTS CTAs per image each reduce a
+// contiguous slice to (value, first index); stage 2: one CTA per image reduces the partials and evaluates the spline.
+#define TN_PARTS 64
+
+__device__ __forceinline__ void argmax_combine(double& best, long long& bi, double ov, long long oi) {
+    if (ov > best || (ov == best && oi < bi)) {
+        best = ov;
+        bi = oi;
     }
-    __shared__ double s_v[32];
-    __shared__ long long s_i[32];
-    __shared__ double s_centre;
+}
+
+__device__ __forceinline__ void argmax_block_reduce(double& best, long long& bi, long long n, double* s_v, long long* s_i) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, best, o);
         const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) {
-            best = ov;
-            bi = oi;
-        }
+        argmax_combine(best, bi, ov, oi);
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) {
@@ -262,15 +250,57 @@ __global__ void __launch_bounds__(1024) template_norm_kernel(const T* __restrict
         for (int o = 16; o > 0; o >>= 1) {
             const double ov = __shfl_xor_sync(0xffffffffu, best, o);
             const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) {
-                best = ov;
-                bi = oi;
-            }
+            argmax_combine(best, bi, ov, oi);
         }
-        if (lane == 0) {
-            argmaxIdx[b] = bi;
-            maxVal[b] = best;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) template_argmax_partial_kernel(const T* __restrict__ map, long long n, double* __restrict__ pVal,
+                                                                      long long* __restrict__ pIdx) {
+    const int b = blockIdx.y;
+    const T* img = map + (size_t)b * n;
+    const long long per = (n + TN_PARTS - 1) / TN_PARTS;
+    const long long i0 = (long long)blockIdx.x * per, i1 = min(i0 + per, n);
+    double best = -INFINITY;
+    long long bi = n;
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const double v = (double)img[i];
+        if (v > best) {  // strided scan visits increasing i, so the first maximum per thread is kept
+            best = v;
+            bi = i;
         }
+    }
+    __shared__ double s_v[32];
+    __shared__ long long s_i[32];
+    argmax_block_reduce(best, bi, n, s_v, s_i);
+    if (threadIdx.x == 0) {
+        pVal[(size_t)b * TN_PARTS + blockIdx.x] = best;
+        pIdx[(size_t)b * TN_PARTS + blockIdx.x] = bi;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(64) template_norm_kernel(const T* __restrict__ map, int H, int W, int mode,
+                                                           double cy, double cx, double numer, const double* __restrict__ pVal,
+                                                           const long long* __restrict__ pIdx,
+                                                           long long* __restrict__ argmaxIdx, double* __restrict__ maxVal,
+                                                           double* __restrict__ centreVal, double* __restrict__ signalNorm) {
+    const int b = blockIdx.x;
+    const T* img = map + (size_t)b * H * W;
+    const long long n = (long long)H * W;
+    double best = -INFINITY;
+    long long bi = n;
+    for (int i = threadIdx.x; i < TN_PARTS; i += blockDim.x) argmax_combine(best, bi, pVal[(size_t)b * TN_PARTS + i], pIdx[(size_t)b * TN_PARTS + i]);
+    __shared__ double s_v[32];
+    __shared__ long long s_i[32];
+    __shared__ double s_centre;
+    argmax_block_reduce(best, bi, n, s_v, s_i);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (wid == 0 && lane == 0) {
+        argmaxIdx[b] = bi;
+        maxVal[b] = best;
+        s_v[0] = best;
     }
     if (wid == 1 && mode == 1) {
         const double v = spline_eval_warp<T>(img, H, W, cy, cx, 1.0);
@@ -278,7 +308,7 @@ __global__ void __launch_bounds__(1024) template_norm_kernel(const T* __restrict
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double denom = best;
+        double denom = s_v[0];
         if (mode == 1) {
             denom = s_centre;
             if (centreVal) centreVal[b] = s_centre;
@@ -414,13 +444,21 @@ int nb_fold_filter(int prec, const double* filtFull, void* filtH, int n, int H, 
 }
 
 int nb_template_norm(int prec, const void* map, int B, int H, int W, int mode, double cy, double cx, double numer,
-                     long long* argmaxIdx, double* maxVal, double* centreVal, double* signalNorm, cudaStream_t st) {
-    NB_REQUIRE(map && argmaxIdx && maxVal && signalNorm && B > 0, NB_ERR_ARG, "nb_template_norm: bad arguments");
-    if (prec == NB_PREC_F64)
-        { NB_PROF_BEGIN(st); template_norm_kernel<double><<<B, 1024, 0, st>>>((const double*)map, H, W, mode, cy, cx, numer, argmaxIdx, maxVal, centreVal, signalNorm); NB_PROF_END("template_norm_kernel", st); }
-    else if (prec == NB_PREC_F32)
-        { NB_PROF_BEGIN(st); template_norm_kernel<float><<<B, 1024, 0, st>>>((const float*)map, H, W, mode, cy, cx, numer, argmaxIdx, maxVal, centreVal, signalNorm); NB_PROF_END("template_norm_kernel", st); }
-    else {
+                     long long* argmaxIdx, double* maxVal, double* centreVal, double* signalNorm, void* scratch,
+                     cudaStream_t st) {
+    NB_REQUIRE(map && argmaxIdx && maxVal && signalNorm && scratch && B > 0, NB_ERR_ARG, "nb_template_norm: bad arguments");
+    double* pVal = (double*)scratch;                                       // [B, TN_PARTS]
+    long long* pIdx = (long long*)(pVal + (size_t)B * TN_PARTS);           // [B, TN_PARTS]
+    const long long n = (long long)H * W;
+    if (prec == NB_PREC_F64) {
+        { NB_PROF_BEGIN(st); template_argmax_partial_kernel<double><<<dim3(TN_PARTS, B), 256, 0, st>>>((const double*)map, n, pVal, pIdx); NB_PROF_END("template_argmax_partial_kernel", st); }
+        NB_CHECK_LAUNCH();
+        { NB_PROF_BEGIN(st); template_norm_kernel<double><<<B, 64, 0, st>>>((const double*)map, H, W, mode, cy, cx, numer, pVal, pIdx, argmaxIdx, maxVal, centreVal, signalNorm); NB_PROF_END("template_norm_kernel", st); }
+    } else if (prec == NB_PREC_F32) {
+        { NB_PROF_BEGIN(st); template_argmax_partial_kernel<float><<<dim3(TN_PARTS, B), 256, 0, st>>>((const float*)map, n, pVal, pIdx); NB_PROF_END("template_argmax_partial_kernel", st); }
+        NB_CHECK_LAUNCH();
+        { NB_PROF_BEGIN(st); template_norm_kernel<float><<<B, 64, 0, st>>>((const float*)map, H, W, mode, cy, cx, numer, pVal, pIdx, argmaxIdx, maxVal, centreVal, signalNorm); NB_PROF_END("template_norm_kernel", st); }
+    } else {
         nb_set_error("nb_template_norm: bad precision %d", prec);
         return NB_ERR_ARG;
     }

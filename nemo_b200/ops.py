@@ -178,9 +178,10 @@ class Ops(object):
         maxVal = self.empty((B,), t.float64)
         centre = self.zeros((B,), t.float64)
         norm = self.empty((B,), t.float64)
+        scratch = self.empty((B * 128,), t.float64)
         _lib.call('nb_template_norm', self.prec, _ptr(maps), B, H, W, int(mode), float(cy), float(cx), float(numer), _ptr(argmax),
-                  _ptr(maxVal), _ptr(centre), _ptr(norm), self._stream())
-        self.launches += 1
+                  _ptr(maxVal), _ptr(centre), _ptr(norm), _ptr(scratch), self._stream())
+        self.launches += 2
         return norm, argmax, maxVal, centre
 
     def plane_values_at(self, fmaps, filtH, idx, S=0):
@@ -254,6 +255,42 @@ class Ops(object):
                   self._stream())
         self.launches += 6
         return labels, nLabels
+
+    DETECT_MAX_LABELS = 8192
+
+    def detect(self, maps, threshold, sign=1.0, maxLabels=None, wantArgmax=False):
+        """Threshold + 4-connected labelling + per-label moments in one asynchronous call (sparse foreground path).
+        Returns device tensors (labels, nLabels, status, table); status[b] != 0 means image b overflowed the compact
+        structures and label4 / label_moments must be used instead."""
+        self._check(maps, self.dtype, 'maps')
+        B, H, W = maps.shape
+        t = self.torch
+        if maxLabels is None:
+            maxLabels = self.DETECT_MAX_LABELS
+        labels = self.empty((B, H, W), t.int32)
+        nLabels = self.empty((B,), t.int32)
+        status = self.empty((B,), t.int32)
+        table = self.empty((B, int(maxLabels) + 1, 8), t.float64)
+        scratch = self.empty((int(_lib.load().nb_detect_scratch_ints(B, H, W)),), t.int32)
+        _lib.call('nb_detect', self.prec, _ptr(maps), float(threshold), float(sign), _ptr(labels), _ptr(nLabels), _ptr(status), _ptr(table),
+                  int(maxLabels), _ptr(scratch), B, H, W, 1 if wantArgmax else 0, self._stream())
+        self.launches += 8
+        return labels, nLabels, status, table
+
+    def ring_flags(self, detTable, detN, ringLabels, ringTable, minRingPix=30, findCenterOfMass=True):
+        """u8 [B, detCap + 1]: 1 where a candidate sits on a ring (photometry.py:60-70, 104-105); asynchronous."""
+        t = self.torch
+        self._check(detTable, t.float64, 'detTable')
+        self._check(ringTable, t.float64, 'ringTable')
+        self._check(ringLabels, t.int32, 'ringLabels')
+        self._check(detN, t.int32, 'detN')
+        B, H, W = ringLabels.shape
+        detCap, ringCap = detTable.shape[1] - 1, ringTable.shape[1] - 1
+        flags = self.empty((B, detCap + 1), t.uint8)
+        _lib.call('nb_ring_flags', _ptr(detTable), _ptr(detN), detCap, _ptr(ringLabels), _ptr(ringTable), ringCap, B, H, W,
+                  float(minRingPix), 0 if findCenterOfMass else 1, _ptr(flags), self._stream())
+        self.launches += 1
+        return flags
 
     def label_moments(self, maps, labels, maxLabels, sign=1.0):
         self._check(maps, self.dtype, 'maps')

@@ -17,6 +17,8 @@ from . import signals
 from . import wcs as _wcs
 from .device import DeviceArray
 
+MIN_RING_PIX = 30
+
 
 def _ops(mapLike, ops=None):
     if ops is not None:
@@ -32,13 +34,45 @@ def _asImageBatch(mapData, ops):
 
 
 # -------------------------------------------------------------------------------------------------------------
-def _segment(ops, imgs, threshold, sign=1.0, wantArgmax=False):
-    """label + moments for a batch [B, H, W].  Returns (labels tensor, nLabels host array, table host array)."""
+def _segmentDense(ops, imgs, threshold, sign=1.0):
+    """label + moments with the dense kernels, for images the sparse detector cannot hold."""
     labels, nLabels = ops.label4(imgs, threshold, sign=sign)
     n = device.toHost(nLabels)
     nmax = int(n.max()) if len(n) else 0
     table = device.toHost(ops.label_moments(imgs, labels, nmax, sign=sign))
     return labels, n, table
+
+
+def _launchSegments(ops, imgs, thresholds, sign=1.0, wantArgmax=False):
+    """Launches label + moments of a batch [B, H, W] at several thresholds; nothing is copied back yet."""
+    return {'ops': ops, 'imgs': imgs, 'thresholds': list(thresholds), 'sign': sign,
+            'launched': [ops.detect(imgs, thr, sign=sign, wantArgmax=wantArgmax) for thr in thresholds]}
+
+
+def _collectSegments(job):
+    """List of (labels tensor, nLabels host array, table host array), one per threshold of a _launchSegments job."""
+    ops, imgs, launched = job['ops'], job['imgs'], job['launched']
+    torch = ops.torch
+    # one synchronising copy brings the label counts and overflow flags of every threshold
+    info = device.toHost(torch.stack([torch.stack([nl, st]) for _, nl, st, _ in launched]))
+    out = []
+    for k, (labels, _, _, table) in enumerate(launched):
+        n, status = info[k, 0], info[k, 1]
+        nmax = int(n.max()) if len(n) else 0
+        if status.any() or nmax > table.shape[1] - 1:
+            out.append(_segmentDense(ops, imgs, job['thresholds'][k], sign=job['sign']))
+            continue
+        out.append((labels, n, device.toHost(table[:, :nmax + 1].contiguous())))
+    return out
+
+
+def _segmentMany(ops, imgs, thresholds, sign=1.0, wantArgmax=False):
+    return _collectSegments(_launchSegments(ops, imgs, thresholds, sign=sign, wantArgmax=wantArgmax))
+
+
+def _segment(ops, imgs, threshold, sign=1.0, wantArgmax=False):
+    """label + moments for a batch [B, H, W].  Returns (labels tensor, nLabels host array, table host array)."""
+    return _segmentMany(ops, imgs, [threshold], sign=sign, wantArgmax=wantArgmax)[0]
 
 
 def _positionArrays(table, n, shape, findCenterOfMass=True):
@@ -80,7 +114,7 @@ def getObjectPositions(mapData, threshold, findCenterOfMass=True, ops=None):
         raise Exception("Detection threshold (thresholdSigma in the config file) cannot be negative unless in forced photometry mode.")
     ops = _ops(mapData, ops)
     imgs = _asImageBatch(mapData, ops)
-    labels, n, table = _segment(ops, imgs, threshold)
+    labels, n, table = _segment(ops, imgs, threshold, wantArgmax=not findCenterOfMass)
     objIDs, objPositions, objNumPix = _positionsFromTable(table[0], int(n[0]), imgs.shape[1:], findCenterOfMass)
     return objIDs, objPositions, objNumPix, device.toHost(labels[0])
 
@@ -99,112 +133,202 @@ def _gatherLabels(labels, bIdx, ys, xs):
     return device.toHost(labels.reshape(-1)[idx])
 
 
-def findObjectsBatch(ops, snMaps, wcsList, flagMaskList, labelList, tileNameList, threshold=3.0, minObjPix=3,
-                     rejectBorder=10, findCenterOfMass=True, removeRings=True, ringThresholdSigma=0, invertMap=False,
-                     objIdent='ACT-CL', longNames=False, useInterpolator=True, measureShapes=False):
-    """findObjects for a batch of S/N maps [B, H, W] on the device; returns a list of B catalogs (lists of dicts).
-    Host synchronisations per batch: label counts, moment tables, two label gathers (rings), spline values."""
+def startFindObjectsBatch(ops, snMaps, threshold=3.0, findCenterOfMass=True, removeRings=True, ringThresholdSigma=0,
+                          invertMap=False, measureShapes=False):
+    """Launches the device work of findObjects for a batch of S/N maps [B, H, W] (thresholding, labelling and moments at
+    the detection and ring thresholds) without waiting for it; pass the result to finishFindObjectsBatch."""
     if measureShapes == True:
         raise Exception("measureShapes is not implemented in nemo_b200")
-    if threshold < 0:
+    if threshold < 0 or (removeRings == True and ringThresholdSigma < 0):
         raise Exception("Detection threshold (thresholdSigma in the config file) cannot be negative unless in forced photometry mode.")
     sign = -1.0 if invertMap == True else 1.0
-    B, H, W = snMaps.shape
-    labels, n, table = _segment(ops, snMaps, threshold, sign=sign)
-    objs = [_positionArrays(table[b], int(n[b]), (H, W), findCenterOfMass) for b in range(B)]
-    keepMasks = [o[3] > minObjPix for o in objs]
+    job = _launchSegments(ops, snMaps, [threshold, ringThresholdSigma] if removeRings == True else [threshold], sign=sign,
+                          wantArgmax=not findCenterOfMass)
+    job.update({'threshold': threshold, 'findCenterOfMass': findCenterOfMass, 'removeRings': removeRings, 'ringFlags': None})
     if removeRings == True:
-        if ringThresholdSigma < 0:
-            raise Exception("Detection threshold (thresholdSigma in the config file) cannot be negative unless in forced photometry mode.")
-        # rings: > 30 pixels at ringThresholdSigma whose centroid pixel is not one of their own (photometry.py:60-70)
-        minRingPix = 30
-        ringLabels, ringN, ringTable = _segment(ops, snMaps, ringThresholdSigma, sign=sign)
-        rb, ry, rx, rid = [], [], [], []
-        for b in range(B):
-            rIDs, rys, rxs, rNumPix = _positionArrays(ringTable[b], int(ringN[b]), (H, W), True)
-            big = rNumPix > minRingPix
-            rb.append(np.full(int(big.sum()), b, dtype=np.int64))
-            ry.append(np.trunc(rys[big]))
-            rx.append(np.trunc(rxs[big]))
-            rid.append(rIDs[big])
-        rb, ry, rx, rid = np.concatenate(rb), np.concatenate(ry), np.concatenate(rx), np.concatenate(rid)
-        at = _gatherLabels(ringLabels, rb, ry, rx)
-        bad = at != rid
-        ringBad = [set(rid[bad & (rb == b)].tolist()) for b in range(B)]
-        if any(len(r) > 0 for r in ringBad):
-            cb = np.concatenate([np.full(int(k.sum()), b, dtype=np.int64) for b, k in enumerate(keepMasks)])
-            cy = np.concatenate([np.trunc(objs[b][1][keepMasks[b]]) for b in range(B)])
-            cx = np.concatenate([np.trunc(objs[b][2][keepMasks[b]]) for b in range(B)])
-            at = _gatherLabels(ringLabels, cb, cy, cx)
-            pos = 0
-            for b in range(B):
-                k = np.where(keepMasks[b])[0]
-                if len(ringBad[b]) > 0:
-                    inRing = np.array([int(v) in ringBad[b] for v in at[pos:pos + len(k)]], dtype=bool)
-                    keepMasks[b][k[inRing]] = False
-                pos += len(k)
+        (_, detN, _, detTable), (ringLabels, _, _, ringTable) = job['launched']
+        job['ringFlags'] = ops.ring_flags(detTable, detN, ringLabels, ringTable, minRingPix=MIN_RING_PIX, findCenterOfMass=findCenterOfMass)
+    return job
 
-    cb = np.concatenate([np.full(int(k.sum()), b, dtype=np.int32) for b, k in enumerate(keepMasks)]) if B > 0 else np.zeros(0, np.int32)
-    cy = np.concatenate([objs[b][1][keepMasks[b]] for b in range(B)]) if B > 0 else np.zeros(0)
-    cx = np.concatenate([objs[b][2][keepMasks[b]] for b in range(B)]) if B > 0 else np.zeros(0)
-    cn = np.concatenate([objs[b][3][keepMasks[b]] for b in range(B)]) if B > 0 else np.zeros(0)
+
+def _collectDetections(job):
+    """(labels tensor, nLabels host, moment table host [B, nmax + 1, 8], ring flags host [B, nmax + 1] or None) of a
+    startFindObjectsBatch job.  One synchronising copy of the counts, then two small ones; the ring-threshold table never
+    leaves the device.  Images that overflowed the sparse detector are redone with the dense kernels."""
+    ops, imgs, launched, sign = job['ops'], job['imgs'], job['launched'], job['sign']
+    torch = ops.torch
+    info = device.toHost(torch.stack([torch.stack([nl, st]) for _, nl, st, _ in launched]))
+    caps = [t.shape[1] - 1 for _, _, _, t in launched]
+    overflow = any(info[k, 1].any() or int(info[k, 0].max()) > caps[k] for k in range(len(launched)))
+    if not overflow:
+        labels, _, _, table = launched[0]
+        n = info[0, 0]
+        flags = job['ringFlags']
+    else:
+        dense = []
+        for thr in job['thresholds']:
+            lab, nl = ops.label4(imgs, thr, sign=sign)
+            nmaxK = int(device.toHost(nl).max())
+            dense.append((lab, nl, ops.label_moments(imgs, lab, nmaxK, sign=sign)))
+        labels, nlDev, table = dense[0]
+        n = device.toHost(nlDev)
+        flags = None
+        if job['removeRings'] == True:
+            flags = ops.ring_flags(table, nlDev, dense[1][0], dense[1][2], minRingPix=MIN_RING_PIX, findCenterOfMass=job['findCenterOfMass'])
+    nmax = int(n.max()) if len(n) else 0
+    tableHost = device.toHost(table[:, :nmax + 1].contiguous())
+    flagsHost = device.toHost(flags[:, :nmax + 1].contiguous()) if flags is not None else None
+    return labels, n, tableHost, flagsHost
+
+
+def _flatObjects(table, n, shape, findCenterOfMass=True, minPix=None):
+    """All labels of all images of a batch as flat arrays in np.unique order, image-major: (image index, label id, y, x,
+    numPix).  Label 0 is listed for images that have background pixels, with numPix = 0, as ndimage.sum gives.  With
+    minPix only labels of more than minPix pixels are listed."""
+    W = shape[1]
+    B, K1 = table.shape[0], table.shape[1]
+    valid = np.arange(K1)[None, :] <= np.asarray(n)[:, None]
+    valid[:, 0] = table[:, 0, 3] > 0
+    if minPix is not None:
+        numAll = table[:, :, 3].copy()
+        numAll[:, 0] = 0.0
+        valid &= numAll > minPix
+    bIdx, ids = np.nonzero(valid)
+    rows = table[bIdx, ids]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        if findCenterOfMass:
+            ys = rows[:, 1] / rows[:, 0]
+            xs = rows[:, 2] / rows[:, 0]
+        else:
+            ys = np.floor_divide(rows[:, 5], W)
+            xs = np.mod(rows[:, 5], W)
+    numPix = np.where(ids == 0, 0.0, rows[:, 3])
+    return bIdx, ids, ys, xs, numPix
+
+
+def finishFindObjectsBatch(job, wcsList, flagMaskList, labelList, tileNameList, minObjPix=3, objIdent='ACT-CL', longNames=False,
+                           useInterpolator=True, extraSamples=None):
+    """Host part of findObjects for a job made by startFindObjectsBatch: positions from the moment tables, ring removal,
+    S/N at the positions, sky coordinates and flags.  Returns one flat, image-major set of columns for the whole batch
+    (see splitObjects).  extraSamples: list of (key, images [B', H, W], fn(imageIndex array) -> index into images, sign);
+    each is sampled at the positions recomputed from (RADeg, decDeg) in the same launch round as the S/N and returned in
+    flat['samples'][key] (what measureFluxes / getSNRValues read, photometry.py:243-253, 295-333)."""
+    ops, snMaps, sign = job['ops'], job['imgs'], job['sign']
+    threshold, findCenterOfMass, removeRings = job['threshold'], job['findCenterOfMass'], job['removeRings']
+    B, H, W = snMaps.shape
+    labels, n, table, ringFlags = _collectDetections(job)
+    cb, cid, cy, cx, cn = _flatObjects(table, n, (H, W), findCenterOfMass, minPix=minObjPix)
+    keep = cn > minObjPix
+    if ringFlags is not None:
+        # rings: > 30 pixels at ringThresholdSigma whose centroid pixel is not one of their own (photometry.py:60-70)
+        keep &= ringFlags[cb, cid] == 0
+    cb, cy, cx, cn = cb[keep].astype(np.int32), cy[keep], cx[keep], cn[keep]
     K = len(cb)
-    catalogList = [None for _ in range(B)]
+    flat = {'counts': np.zeros(B, dtype=np.int64), 'labels': list(labelList), 'tiles': list(tileNameList), 'objIdent': objIdent,
+            'longNames': longNames, 'cols': None, 'samples': {}}
     if K == 0:
-        return catalogList
-    # S/N at the object positions
-    yx = np.stack([cy, cx], axis=1).astype(np.float64)
+        return flat
+    # sky coordinates and flags of every candidate; positions recomputed from them for the flux measurements, as the
+    # reference's measureFluxes does (photometry.py:328)
+    perImage = np.bincount(cb, minlength=B)
+    ra, dec = np.empty(K), np.empty(K)
+    xs2, ys2 = np.empty(K), np.empty(K)
+    flags = np.zeros(K, dtype=int)
+    lo = 0
+    for b in np.nonzero(perImage)[0]:
+        sl = slice(lo, lo + perImage[b])
+        lo += perImage[b]
+        r, d = wcsList[b].pix2wcs(cx[sl], cy[sl])
+        r = np.where(np.asarray(r) < 0, 360.0 + np.asarray(r), r)
+        ra[sl], dec[sl] = r, d
+        if extraSamples:
+            xs2[sl], ys2[sl] = wcsList[b].wcs2pix(ra[sl], dec[sl])
+        if flagMaskList[b] is not None:
+            flags[sl] = np.asarray(flagMaskList[b])[np.round(cy[sl]).astype(int), np.round(cx[sl]).astype(int)]
+    # S/N at the object positions and the extra samples, all launched before the one copy back
+    samples = {}
     if useInterpolator == True:
-        snr = device.toHost(ops.spline_eval(snMaps, ops.to_device(cb, ops.torch.int32), ops.to_device(yx, ops.torch.float64), sign=sign))
+        torch = ops.torch
+        pos = np.stack([np.stack([cy, cx], axis=1), np.stack([ys2, xs2], axis=1)]) if extraSamples else np.stack([cy, cx], axis=1)[None]
+        posT = ops.to_device(pos, torch.float64)
+        idxHost = np.stack([cb] + [np.asarray(fn(cb), dtype=np.int32) for _, _, fn, _ in extraSamples]) if extraSamples else cb[None]
+        idxT = ops.to_device(np.ascontiguousarray(idxHost, dtype=np.int32), torch.int32)
+        outs = [ops.spline_eval(snMaps, idxT[0], posT[0], sign=sign)]
+        for k, (key, imgs, fn, sgn) in enumerate(extraSamples or []):
+            outs.append(ops.spline_eval(imgs, idxT[k + 1], posT[1], sign=sgn))
+        vals = device.toHost(torch.stack(outs))
+        snr = vals[0]
+        for k, (key, imgs, fn, sgn) in enumerate(extraSamples or []):
+            samples[key] = vals[k + 1]
     else:
         snr = sign * _gatherValues(snMaps, cb, np.round(cy).astype(np.int64), np.round(cx).astype(np.int64))
-    pos = 0
-    for b in range(B):
-        nb = int(keepMasks[b].sum())
-        if nb == 0:
-            continue
-        sl = slice(pos, pos + nb)
-        pos += nb
-        keep = snr[sl] > threshold
-        if not keep.any():
-            continue
-        wcs = wcsList[b]
-        ys, xs = cy[sl][keep], cx[sl][keep]
-        ra, dec = wcs.pix2wcs(xs, ys)
-        ra, dec = np.atleast_1d(np.array(ra, dtype=np.float64)), np.atleast_1d(np.array(dec, dtype=np.float64))
-        ra = np.where(ra < 0, 360.0 + ra, ra)
-        flagMask = flagMaskList[b]
-        if flagMask is not None:
-            flags = np.asarray(flagMask)[np.round(ys).astype(int), np.round(xs).astype(int)]
-        else:
-            flags = np.zeros(len(ys), dtype=int)
-        # id counts every object that passed the size and ring cuts, kept or not (photometry.py:182)
-        catalogList[b] = {'id': (np.arange(nb) + 1)[keep], 'x': xs, 'y': ys, 'RADeg': ra, 'decDeg': dec,
-                          'galacticLatDeg': _galacticLat(ra, dec), 'numSigPix': cn[sl][keep], 'SNR': snr[sl][keep].astype(np.float64),
-                          'flags': flags, 'template': labelList[b], 'tileName': tileNameList[b],
-                          'objIdent': objIdent, 'longNames': longNames}
-    return catalogList
+        for key, imgs, fn, sgn in (extraSamples or []):
+            samples[key] = sgn * _gatherValues(imgs, np.asarray(fn(cb), dtype=np.int64), np.round(ys2).astype(np.int64), np.round(xs2).astype(np.int64))
+    # id counts every object that passed the size and ring cuts, kept or not (photometry.py:182)
+    ids = np.arange(K) - (np.cumsum(perImage) - perImage)[cb] + 1
+    sel = snr > threshold
+    cb = cb[sel]
+    flat['counts'] = np.bincount(cb, minlength=B)
+    flat['owner'] = cb
+    ra, dec = ra[sel], dec[sel]
+    flat['cols'] = {'id': ids[sel], 'x': cx[sel], 'y': cy[sel], 'RADeg': ra, 'decDeg': dec, 'galacticLatDeg': _galacticLat(ra, dec),
+                    'numSigPix': cn[sel], 'SNR': snr[sel].astype(np.float64), 'flags': flags[sel]}
+    flat['samples'] = {k: v[sel] for k, v in samples.items()}
+    flat['xy2'] = (xs2[sel], ys2[sel]) if extraSamples else None
+    return flat
 
 
 def columnsToTable(cols, extra=None, keysToWrite=None):
-    """Table from one image's column dict as made by findObjectsBatch (None -> []).  The object names are formatted
-    the first time the 'name' column is read."""
+    """Table from one image's columns: dict with x, y, RADeg, decDeg, SNR, ... arrays and the scalars template, tileName,
+    objIdent, longNames (None -> [])."""
     if cols is None:
         return []
-    n = len(cols['x'])
-    tab = catalogs.Table()
-    ra, dec, ident, longNames = cols['RADeg'], cols['decDeg'], cols['objIdent'], cols['longNames']
-    values = dict(cols)
-    if extra is not None:
-        values.update(extra)
-    for key in (keysToWrite if keysToWrite is not None else catalogs.COLUMN_NAMES):
-        if key == 'name':
-            tab.add_deferred_column('name', lambda: catalogs.makeNames(ra, dec, prefix=ident, longNames=longNames))
-        elif key in ('template', 'tileName'):
-            tab.add_column(catalogs.Column(np.full(n, values[key], dtype=object), key))
-        elif key in values and key not in ('objIdent', 'longNames'):
-            tab.add_column(catalogs.Column(values[key], key))
-    return tab
+    flat = {'counts': np.array([len(cols['x'])]), 'labels': [cols['template']], 'tiles': [cols['tileName']],
+            'objIdent': cols['objIdent'], 'longNames': cols['longNames'],
+            'cols': {k: np.asarray(v) for k, v in cols.items() if k not in ('template', 'tileName', 'objIdent', 'longNames')}}
+    return splitObjects(flat, extra, keysToWrite)[0]
+
+
+def splitObjects(flat, extra=None, keysToWrite=None):
+    """Per-image tables (``[]`` where nothing was found) from the flat columns of finishFindObjectsBatch, plus optional
+    extra flat columns (fluxes).  Object names are formatted the first time a table's 'name' column is read."""
+    counts = flat['counts']
+    out = []
+    keys = keysToWrite if keysToWrite is not None else catalogs.COLUMN_NAMES
+    cols = dict(flat['cols']) if flat['cols'] is not None else {}
+    if extra:
+        cols.update(extra)
+    ident, longNames = flat['objIdent'], flat['longNames']
+    lo = 0
+    for b, cnt in enumerate(counts):
+        if cnt == 0:
+            out.append([])
+            continue
+        sl = slice(lo, lo + cnt)
+        lo += cnt
+        ordered = []
+        for key in keys:
+            if key == 'name':
+                ra, dec = cols['RADeg'][sl], cols['decDeg'][sl]
+                ordered.append((key, catalogs.deferred(lambda ra=ra, dec=dec: catalogs.makeNames(ra, dec, prefix=ident, longNames=longNames))))
+            elif key == 'template':
+                ordered.append((key, np.full(cnt, flat['labels'][b], dtype=object)))
+            elif key == 'tileName':
+                ordered.append((key, np.full(cnt, flat['tiles'][b], dtype=object)))
+            elif key in cols:
+                ordered.append((key, cols[key][sl].copy()))
+        out.append(catalogs.Table.fromColumns(ordered))
+    return out
+
+
+def findObjectsBatch(ops, snMaps, wcsList, flagMaskList, labelList, tileNameList, threshold=3.0, minObjPix=3,
+                     rejectBorder=10, findCenterOfMass=True, removeRings=True, ringThresholdSigma=0, invertMap=False,
+                     objIdent='ACT-CL', longNames=False, useInterpolator=True, measureShapes=False):
+    """findObjects for a batch of S/N maps [B, H, W] on the device; returns a list of B tables ([] where nothing was found)."""
+    job = startFindObjectsBatch(ops, snMaps, threshold=threshold, findCenterOfMass=findCenterOfMass, removeRings=removeRings,
+                                ringThresholdSigma=ringThresholdSigma, invertMap=invertMap, measureShapes=measureShapes)
+    return splitObjects(finishFindObjectsBatch(job, wcsList, flagMaskList, labelList, tileNameList, minObjPix=minObjPix,
+                                               objIdent=objIdent, longNames=longNames, useInterpolator=useInterpolator))
 
 
 def _gatherValues(imgs, bIdx, ys, xs):
@@ -234,7 +358,7 @@ def findObjects(filteredMapDict, threshold=3.0, minObjPix=3, rejectBorder=10, fi
                             removeRings=removeRings, ringThresholdSigma=ringThresholdSigma, invertMap=invertMap,
                             objIdent=objIdent, longNames=longNames, useInterpolator=useInterpolator,
                             measureShapes=measureShapes)
-    return columnsToTable(cats[0])
+    return cats[0]
 
 
 # -------------------------------------------------------------------------------------------------------------

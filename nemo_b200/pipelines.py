@@ -134,12 +134,10 @@ def _sameNoiseSetup(filtersList):
     return len(set(key(f) for f in filtersList)) == 1
 
 
-def filterTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=True, measureFluxes=True,
-                    invertMap=False, keepMaps=False):
-    """Filters every tile of `batch` at every scale of `filtersList` (Fourier matched filters with a common noise
-    set-up), detects objects and measures fluxes.  Returns (catalogDict, extras) where catalogDict maps
-    '<label>#<tileName>' -> {'catalog': Table or []} like the reference's, and extras holds the noise tables (and
-    the device maps when keepMaps)."""
+def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=True, invertMap=False):
+    """Launches, without waiting for any of it, the device work of one batch: filtering of every tile at every scale of
+    `filtersList` (Fourier matched filters with a common noise set-up), noise / S-N maps, and the thresholding,
+    labelling and moments of the detection step.  Returns the job to pass to finishTileBatch."""
     if not _sameNoiseSetup(filtersList):
         raise Exception("filters of one batch need identical noiseParams / edgeTrimArcmin / bckSub settings")
     dev = batch.dev if batch.dev is not None else batch.upload()
@@ -171,13 +169,78 @@ def filterTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow
     # K8
     if undoPixelWindow:
         engine.undoPixelWindow(ops, data)
+    # K9, K10
+    detectJob = photometry.startFindObjectsBatch(ops, sn, threshold=parDict['thresholdSigma'],
+                                                 findCenterOfMass=parDict['findCenterOfMass'], removeRings=parDict['removeRings'],
+                                                 ringThresholdSigma=parDict['ringThresholdSigma'], invertMap=invertMap,
+                                                 measureShapes=parDict['measureShapes'])
+    return {'ops': ops, 'batch': batch, 'filtersList': filtersList, 'parDict': parDict, 'mapUnits': templates.outputUnits,
+            'invertMap': invertMap, 'detectJob': detectJob, 'data': data, 'SNMap': sn, 'surveyMask': maskOut, 'RMSMap': rms,
+            'noiseTable': table, 'noiseEdges': edges, 'signalNorm': res['signalNorm'], 'fRel': res['fRel'], 'filtH': res['filtH']}
 
-    catalogDict = detectAndMeasure(ops, batch, filtersList, data, sn, templates.outputUnits, parDict,
-                                   measureFluxes=measureFluxes, invertMap=invertMap)
-    extras = {'noiseTable': table, 'noiseEdges': edges, 'signalNorm': res['signalNorm'], 'fRel': res['fRel']}
+
+def finishTileBatch(job, measureFluxes=True, keepMaps=False):
+    """Waits for a startTileBatch job and assembles its catalogs.  Returns (catalogDict, extras) where catalogDict maps
+    '<label>#<tileName>' -> {'catalog': Table or []} like the reference's, and extras holds the noise tables (and
+    the device maps when keepMaps)."""
+    catalogDict = detectAndMeasure(job['ops'], job['batch'], job['filtersList'], job['data'], job['SNMap'], job['mapUnits'],
+                                   job['parDict'], measureFluxes=measureFluxes, invertMap=job['invertMap'], detectJob=job['detectJob'])
+    extras = {'noiseTable': job['noiseTable'], 'noiseEdges': job['noiseEdges'], 'signalNorm': job['signalNorm'], 'fRel': job['fRel']}
     if keepMaps:
-        extras.update({'data': data, 'SNMap': sn, 'surveyMask': maskOut, 'RMSMap': rms, 'filtH': res['filtH']})
+        extras.update({k: job[k] for k in ('data', 'SNMap', 'surveyMask', 'RMSMap', 'filtH')})
     return catalogDict, extras
+
+
+def filterTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=True, measureFluxes=True,
+                    invertMap=False, keepMaps=False):
+    """startTileBatch + finishTileBatch for one batch."""
+    job = startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=undoPixelWindow, invertMap=invertMap)
+    return finishTileBatch(job, measureFluxes=measureFluxes, keepMaps=keepMaps)
+
+
+def processBatches(ops, batches, filtersList, templates, parDict, upload=True, undoPixelWindow=True, measureFluxes=True,
+                   invertMap=False, keepMaps=False):
+    """Runs several tile batches as a two-stage software pipeline over two CUDA streams: the device work of batch i + 1
+    (upload included) is queued before the host assembles the catalogs of batch i, so neither side waits for the other.
+    Returns the list of (catalogDict, extras), one per batch, in order."""
+    torch = ops.torch
+    if len(batches) < 2:
+        results = []
+        for b in batches:
+            if upload and b.dev is None:
+                b.upload()
+            results.append(filterTileBatch(ops, b, filtersList, templates, parDict, undoPixelWindow=undoPixelWindow,
+                                           measureFluxes=measureFluxes, invertMap=invertMap, keepMaps=keepMaps))
+            if upload:
+                b.dev = None
+        return results
+    streams = getattr(ops, '_pipeStreams', None)
+    if streams is None:
+        streams = ops._pipeStreams = [torch.cuda.Stream(device=ops.device), torch.cuda.Stream(device=ops.device)]
+    main = torch.cuda.current_stream(ops.device)
+    for st in streams:
+        st.wait_stream(main)       # templates and resident inputs were produced on the caller's stream
+    results = []
+    pending = None
+    for i, batch in enumerate(batches):
+        st = streams[i % 2]
+        with torch.cuda.stream(st):
+            if upload:
+                batch.upload()
+            job = startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=undoPixelWindow, invertMap=invertMap)
+        if pending is not None:
+            with torch.cuda.stream(pending[1]):
+                results.append(finishTileBatch(pending[0], measureFluxes=measureFluxes, keepMaps=keepMaps))
+            if upload:
+                pending[0]['batch'].dev = None
+        pending = (job, st)
+    with torch.cuda.stream(pending[1]):
+        results.append(finishTileBatch(pending[0], measureFluxes=measureFluxes, keepMaps=keepMaps))
+    if upload:
+        pending[0]['batch'].dev = None
+    for st in streams:
+        main.wait_stream(st)
+    return results
 
 
 def catalogKeys(havePhotFilter, mapUnits, measureFluxes=True):
@@ -192,7 +255,7 @@ def catalogKeys(havePhotFilter, mapUnits, measureFluxes=True):
     return keys
 
 
-def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measureFluxes=True, invertMap=False):
+def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measureFluxes=True, invertMap=False, detectJob=None):
     """K9-K11 for all (tile, scale) images, then the rows of every catalog (pipelines.py:251-284)."""
     nT, S = batch.nT, len(filtersList)
     H, W = batch.H, batch.W
@@ -200,62 +263,43 @@ def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measu
     flagList = [batch.flagMasks[o // S] for o in range(nT * S)]
     labelList = [filtersList[o % S]['label'] for o in range(nT * S)]
     tileList = [batch.tileNames[o // S] for o in range(nT * S)]
-    rows = photometry.findObjectsBatch(ops, sn, wcsList, flagList, labelList, tileList,
-                                       threshold=parDict['thresholdSigma'], minObjPix=parDict['minObjPix'],
-                                       rejectBorder=parDict['rejectBorder'], findCenterOfMass=parDict['findCenterOfMass'],
-                                       removeRings=parDict['removeRings'], ringThresholdSigma=parDict['ringThresholdSigma'],
-                                       invertMap=invertMap, objIdent=parDict['objIdent'], longNames=parDict['longNames'],
-                                       useInterpolator=parDict['useInterpolator'], measureShapes=parDict['measureShapes'])
+    if detectJob is None:
+        detectJob = photometry.startFindObjectsBatch(ops, sn, threshold=parDict['thresholdSigma'],
+                                                     findCenterOfMass=parDict['findCenterOfMass'], removeRings=parDict['removeRings'],
+                                                     ringThresholdSigma=parDict['ringThresholdSigma'], invertMap=invertMap,
+                                                     measureShapes=parDict['measureShapes'])
     photFilter = parDict.get('photFilter')
     photScale = None
     if photFilter is not None:
         for s, f in enumerate(filtersList):
             if f['label'] == photFilter:
                 photScale = s
-    useInterp = parDict['useInterpolator']
-    # all objects of the batch in one go: positions from (RADeg, decDeg) as the reference does (photometry.py:328)
-    owners = [o for o in range(nT * S) if rows[o] is not None]
-    extras = {o: {} for o in owners}
-    if len(owners) > 0 and (measureFluxes or photScale is not None):
-        counts = [len(rows[o]['x']) for o in owners]
-        xs, ys = [], []
-        for o in owners:
-            x, y = wcsList[o].wcs2pix(rows[o]['RADeg'], rows[o]['decDeg'])
-            xs.append(np.atleast_1d(x))
-            ys.append(np.atleast_1d(y))
-        xs, ys = np.concatenate(xs), np.concatenate(ys)
-        ownArr = np.repeat(np.array(owners, dtype=np.int32), counts)
-        snrAll = np.concatenate([rows[o]['SNR'] for o in owners])
-        yx = ops.to_device(np.stack([ys, xs], axis=1), ops.torch.float64)
-        own = ops.to_device(ownArr, ops.torch.int32)
-
-        def sample(imgs, idxT, sign=1.0):
-            if useInterp:
-                return device.toHost(ops.spline_eval(imgs, idxT, yx, sign=sign))
-            torch = ops.torch
-            yi = torch.as_tensor(np.round(ys).astype(np.int64), device=imgs.device)
-            xi = torch.as_tensor(np.round(xs).astype(np.int64), device=imgs.device)
-            return sign * device.toHost(imgs[idxT.long(), yi, xi]).astype(np.float64)
-
-        vals = {}
+    extraSamples = []
+    if photScale is not None:
+        photIndex = lambda o: (o // S) * S + photScale
+        extraSamples.append(('fixed_SNR', sn, photIndex, -1.0 if (invertMap and not measureFluxes) else 1.0))
+    if measureFluxes:
+        extraSamples.append(('', data, lambda o: o, 1.0))
         if photScale is not None:
-            phot = ops.to_device(((ownArr // S) * S + photScale).astype(np.int32), ops.torch.int32)
+            extraSamples.append(('fixed_', data, photIndex, 1.0))
+    flat = photometry.finishFindObjectsBatch(detectJob, wcsList, flagList, labelList, tileList, minObjPix=parDict['minObjPix'],
+                                             objIdent=parDict['objIdent'], longNames=parDict['longNames'],
+                                             useInterpolator=parDict['useInterpolator'], extraSamples=extraSamples)
+    cols = {}
+    if flat['cols'] is not None and extraSamples:
+        ownArr = flat['owner']
+        vals = flat['samples']
+        snrAll = flat['cols']['SNR']
+        if photScale is not None:
             # bounds test of getSNRValues (photometry.py:246-253): int() truncates towards zero
+            xs, ys = flat['xy2']
             xi, yi = np.trunc(xs), np.trunc(ys)
             inside = (xi > 0) & (xi < W) & (yi > 0) & (yi < H)
-            fixedSNR = sample(sn, phot, sign=-1.0 if (invertMap and not measureFluxes) else 1.0)
-            vals['fixed_SNR'] = np.where(inside, fixedSNR, 0.0)
-        if measureFluxes:
-            vals[''] = sample(data, own)
-            if photScale is not None:
-                vals['fixed_'] = sample(data, phot)
-        cols = {}
-        if 'fixed_SNR' in vals:
-            cols['fixed_SNR'] = vals['fixed_SNR']
+            cols['fixed_SNR'] = np.where(inside, vals['fixed_SNR'], 0.0)
         if measureFluxes:
             for prefix in ['', 'fixed_'] if photScale is not None else ['']:
                 v = vals[prefix]
-                snr = snrAll if prefix == '' else vals['fixed_SNR']
+                snr = snrAll if prefix == '' else cols['fixed_SNR']
                 with np.errstate(divide='ignore', invalid='ignore'):
                     if mapUnits == 'yc':
                         cols[prefix + 'y_c'] = v / 1e-4
@@ -266,27 +310,18 @@ def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measu
                     else:
                         cols[prefix + 'deltaT_c'] = v
                         cols[prefix + 'err_deltaT_c'] = v / snr
-                        flux, errFlux = np.zeros(len(v)), np.zeros(len(v))
-                        lo = 0
-                        for o, cnt in zip(owners, counts):
-                            md0 = batch.mapDicts[o // S][0]
-                            nsr = md0.get('solidAngle_nsr', 0.0)
-                            if nsr > 0:
-                                sl = slice(lo, lo + cnt)
-                                flux[sl] = photometry.deltaTToJyPerSr(v[sl], md0['obsFreqGHz']) * nsr * 1.e-9
-                                errFlux[sl] = photometry.deltaTToJyPerSr(cols[prefix + 'err_deltaT_c'][sl], md0['obsFreqGHz']) * nsr * 1.e-9
-                            lo += cnt
-                        cols[prefix + 'fluxJy'] = flux
-                        cols[prefix + 'err_fluxJy'] = errFlux
-        lo = 0
-        for o, cnt in zip(owners, counts):
-            extras[o] = {k: v[lo:lo + cnt] for k, v in cols.items()}
-            lo += cnt
+                        # Jy fluxes need the beam solid angle and frequency of the image's tile (photometry.py:336-339)
+                        nsr = np.array([batch.mapDicts[o // S][0].get('solidAngle_nsr', 0.0) for o in range(nT * S)])[ownArr]
+                        freq = np.array([batch.mapDicts[o // S][0]['obsFreqGHz'] for o in range(nT * S)], dtype=np.float64)[ownArr]
+                        flux = photometry.deltaTToJyPerSr(v, freq) * nsr * 1.e-9
+                        errFlux = photometry.deltaTToJyPerSr(cols[prefix + 'err_deltaT_c'], freq) * nsr * 1.e-9
+                        cols[prefix + 'fluxJy'] = np.where(nsr > 0, flux, 0.0)
+                        cols[prefix + 'err_fluxJy'] = np.where(nsr > 0, errFlux, 0.0)
     keys = catalogKeys(photScale is not None, mapUnits, measureFluxes)
+    tables = photometry.splitObjects(flat, cols, keysToWrite=keys)
     catalogDict = {}
     for o in range(nT * S):
-        label = labelList[o] + "#" + tileList[o]
-        catalogDict[label] = {'catalog': photometry.columnsToTable(rows[o], extras.get(o), keysToWrite=keys)}
+        catalogDict[labelList[o] + "#" + tileList[o]] = {'catalog': tables[o]}
     return catalogDict
 
 
@@ -339,18 +374,16 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     else:
         batches = staged['batches']
     templates = getattr(config, '_templates', None)
-    for batch in batches:
+    if templates is None:
+        templates = FilterSetTemplates(ops, filtersList, batches[0].mapDicts[0], tileName=batches[0].tileNames[0])
+        config._templates = templates
+    if verbose:
+        for batch in batches:
+            print(">>> [rank = %d] Making filtered maps - tiles %s" % (config.rank, batch.tileNames))
+    results = processBatches(ops, batches, filtersList, templates, parDict, upload=True,
+                             undoPixelWindow=parDict.get('undoPixelWindow', True), measureFluxes=measureFluxes, invertMap=invertMap)
+    for batch, (cd, extras) in zip(batches, results):
         names = batch.tileNames
-        if verbose:
-            print(">>> [rank = %d] Making filtered maps - tiles %s" % (config.rank, names))
-        if templates is None:
-            templates = FilterSetTemplates(ops, filtersList, batch.mapDicts[0], tileName=names[0])
-            config._templates = templates
-        batch.upload()
-        cd, extras = filterTileBatch(ops, batch, filtersList, templates, parDict,
-                                     undoPixelWindow=parDict.get('undoPixelWindow', True), measureFluxes=measureFluxes,
-                                     invertMap=invertMap)
-        batch.dev = None
         catalogDict.update(cd)
         tab = device.toHost(extras['noiseTable'])
         for o in range(tab.shape[0]):

@@ -406,6 +406,67 @@ def test_label4_and_moments(ops64, report, shape, smooth, thr):
     report("label4", shape=shape, smooth=smooth, thr=thr, nlabels=int(nLabels[0]))
 
 
+@pytest.mark.parametrize("shape,smooth,thr,sign", [((64, 64), 0.0, 2.5, 1.0), ((256, 320), 1.5, 2.0, 1.0), ((1024, 1024), 2.0, 3.0, 1.0),
+                                                    ((512, 2048), 3.0, 2.5, -1.0), ((300, 301), 1.0, 4.0, 1.0), ((1024, 1024), 0.0, 4.0, 1.0)])
+def test_detect_sparse_matches_scipy(ops64, report, shape, smooth, thr, sign):
+    """nb_detect (one dense pass + compact foreground list) against ndimage.label / center_of_mass / sum /
+    maximum_position, labels bit-exact."""
+    rng = np.random.default_rng(17)
+    B = 3
+    m = rng.standard_normal((B,) + shape)
+    if smooth > 0:
+        m = np.array([ndimage.gaussian_filter(x, smooth) for x in m])
+        m /= m.std()
+    m[2] = -5.0                                   # an image with no foreground at all
+    if sign < 0:
+        m[2] = 5.0
+    labels, nLabels, status, table = ops64.detect(ops64.to_device(m), thr, sign=sign, wantArgmax=True)
+    labels, nLabels, status, table = _np(labels), _np(nLabels), _np(status), _np(table)
+    assert not status.any()
+    for b in range(B):
+        v = sign * m[b]
+        ref, n = ndimage.label(v > thr)
+        assert nLabels[b] == n
+        assert np.array_equal(labels[b], ref), "labels differ"
+        if n == 0:
+            assert table[b, 0, 3] == v.size
+            continue
+        ids = np.arange(1, n + 1)
+        com = np.array(ndimage.center_of_mass(v, labels=ref, index=ids))
+        t = table[b]
+        gotCom = np.stack([t[ids, 1] / t[ids, 0], t[ids, 2] / t[ids, 0]], axis=1)
+        assert np.abs(gotCom - com).max() < 1e-9
+        assert np.array_equal(t[ids, 3], ndimage.sum(v > thr, labels=ref, index=ids))
+        mpos = np.array(ndimage.maximum_position(v, labels=ref, index=np.arange(0, n + 1)))
+        gotPos = np.stack([t[:n + 1, 5] // shape[1], t[:n + 1, 5] % shape[1]], axis=1)
+        assert np.array_equal(gotPos, mpos)
+        assert np.isclose(t[0, 0], v[ref == 0].sum(), rtol=1e-9, atol=1e-6) and t[0, 3] == (ref == 0).sum()
+        first = np.array([np.flatnonzero(ref.ravel() == i)[0] for i in ids])
+        assert np.array_equal(t[ids, 6], first)
+    report("detect_sparse", shape=shape, thr=thr, nlabels=int(nLabels[0]))
+
+
+def test_detect_overflow_falls_back_to_dense_path(ops64):
+    """A threshold low enough that more than H*W/8 pixels are foreground sets the status flag; photometry._segment then
+    uses the dense kernels and still agrees with scipy."""
+    from nemo_b200 import photometry
+    rng = np.random.default_rng(18)
+    m = rng.standard_normal((2, 128, 160))
+    _, _, status, _ = ops64.detect(ops64.to_device(m), 0.0)
+    assert _np(status).all()
+    labels, n, table = photometry._segment(ops64, ops64.to_device(m), 0.0)
+    for b in range(2):
+        ref, nref = ndimage.label(m[b] > 0.0)
+        assert n[b] == nref and np.array_equal(_np(labels)[b], ref)
+    # many small components (> 8192 roots) in a large image also overflow
+    big = rng.standard_normal((1, 1024, 1024))
+    _, nl, status, _ = ops64.detect(ops64.to_device(big), 1.6)
+    assert _np(status)[0] == 1 or _np(nl)[0] <= 8192
+    labels, n, table = photometry._segment(ops64, ops64.to_device(big), 1.6)
+    ref, nref = ndimage.label(big[0] > 1.6)
+    assert n[0] == nref and np.array_equal(_np(labels)[0], ref)
+
+
 def test_label4_edge_cases(ops64):
     t = ops64.torch
     for m in [np.zeros((1, 64, 64)), np.ones((1, 64, 64)), np.eye(64)[None], np.indices((64, 64)).sum(axis=0)[None] % 2.0]:
