@@ -210,7 +210,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default='f64', choices=['f64', 'f32'])
     ap.add_argument('--tiles', type=int, default=TILES_PER_GPU, help='tiles per GPU')
-    ap.add_argument('--tiles-per-batch', type=int, default=4)
+    ap.add_argument('--tiles-per-batch', type=int, default=16)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--kernel-table', default=None, help='write the per-kernel roofline table to this file')
     args = ap.parse_args()
@@ -251,6 +251,7 @@ def main():
     parDict, tileMaps, truth = bench_workloads.pointSourceConfig(numTiles=nT, shape=SHAPE, firstIndex=rank * nT)
     config = pipelines.SimpleConfig(parDict, tileMaps, rank=0, size=1)     # every rank owns all of its own tiles
     config.rank = rank
+    config.allTileNames = ['%d_%d' % (i // 4, i % 4) for i in range(world * nT)]    # the same list on every rank
     parDict = config.parDict
     ops = device.getOps(args.precision)
     F, S = 1, len(parDict['mapFilters'])
@@ -307,6 +308,8 @@ def main():
     e2e = {'value': mpixJob / tE2E, 'unit': UNIT, 'h2d_bytes_per_step': device.TRAFFIC['h2d'] // args.steps,
            'd2h_bytes_per_step': device.TRAFFIC['d2h'] // args.steps, 'ms_per_step': tE2E * 1e3, 'catalog_rows': len(cat)}
 
+    if comm is not None:
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
 

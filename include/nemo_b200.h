@@ -153,6 +153,19 @@ int nb_detect(int prec, const void* map, double threshold, double sign, int* lab
               double* table, int maxLabels, int* scratch, int B, int H, int W, int flags, cudaStream_t stream);
 long long nb_detect_scratch_ints(int B, int H, int W);
 
+/* The device side of photometry.findObjects in one asynchronous call (nemo/photometry.py:58-70, 101-105): the map is read
+ * once for the detection threshold and (haveRing != 0) the ring threshold; both foregrounds are labelled and reduced as in
+ * nb_detect; ringFlags [B, maxLabels + 1] u8 is 1 for a detection-threshold label whose position (centre of mass when
+ * posMode = 0, first maximum when 1) lies on a ring-threshold component of more than minRingPix pixels that does not contain
+ * its own centre of mass.  Outputs for the detection threshold: nLabels [B], table [B, maxLabels + 1, 8], status [B]
+ * (1 = compact structures overflowed at either threshold: use nb_label4 / nb_label_moments / nb_ring_flags), and the
+ * dense segmentation labels [B, H, W] when non-NULL.  flags bit 0: first-arg-max columns.
+ * scratch: nb_find_objects_scratch_ints(B, H, W) int32 words, 8-byte aligned. */
+int nb_find_objects(int prec, const void* map, double threshold, double ringThreshold, int haveRing, double sign,
+                    double minRingPix, int posMode, int* nLabels, int* status, double* table, unsigned char* ringFlags,
+                    int* labels, int maxLabels, int* scratch, int B, int H, int W, int flags, cudaStream_t stream);
+long long nb_find_objects_scratch_ints(int B, int H, int W);
+
 /* Ring removal of findObjects (nemo/photometry.py:60-70, 104-105).  detTable / detN: moment table and label counts at the
  * detection threshold; ringLabels / ringTable: segmentation and moment table at ringThresholdSigma (both from nb_detect or
  * nb_label4 + nb_label_moments, row widths detCap + 1 and ringCap + 1).  flags [B, detCap + 1] u8 = 1 for a candidate whose

@@ -21,6 +21,10 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC"]
 
 
+if os.environ.get("NEMO_B200_NVCC_EXTRA"):
+    NVCC_FLAGS += os.environ["NEMO_B200_NVCC_EXTRA"].split()      # experiment knobs, e.g. -DOC_THREADS=1024
+
+
 def _nvcc():
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):

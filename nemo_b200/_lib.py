@@ -47,6 +47,9 @@ _PROTOTYPES = {
     "nb_label_moments": [c_int, c_ptr, c_dbl, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
     "nb_detect": [c_int, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
     "nb_detect_scratch_ints": [c_int, c_int, c_int],
+    "nb_find_objects": [c_int, c_ptr, c_dbl, c_dbl, c_int, c_dbl, c_dbl, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int,
+                        c_int, c_int, c_ptr],
+    "nb_find_objects_scratch_ints": [c_int, c_int, c_int],
     "nb_ring_flags": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_int, c_ptr, c_ptr],
     "nb_spline_eval": [c_int, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_dbl, c_ptr],
     "nb_gauss_filter": [c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_dbl, c_dbl, c_int, c_ptr],
@@ -54,7 +57,7 @@ _PROTOTYPES = {
     "nb_cast": [c_int, c_ptr, c_int, c_ptr, c_ll, c_ptr],
     "nb_mask_to_u8": [c_int, c_ptr, c_ptr, c_ll, c_ptr],
 }
-_RESTYPES = {"nb_last_error": ctypes.c_char_p, "nb_label4_scratch_ints": c_ll, "nb_detect_scratch_ints": c_ll, "nb_prof_report": c_ll, "nb_launch_count": c_ll}
+_RESTYPES = {"nb_last_error": ctypes.c_char_p, "nb_label4_scratch_ints": c_ll, "nb_detect_scratch_ints": c_ll, "nb_find_objects_scratch_ints": c_ll, "nb_prof_report": c_ll, "nb_launch_count": c_ll}
 
 EXPORTED_SYMBOLS = sorted(_PROTOTYPES.keys())
 

@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(256) detect_moments_kernel(const T* __restrict
     const int img = blockIdx.y;
     const T* m = map + (size_t)img * HW;
     const int* L = sc.L + (size_t)img * HW;
-    int* lab = labels + (size_t)img * HW;
+    int* lab = labels ? labels + (size_t)img * HW : nullptr;
     const int* list = sc.fgList + (size_t)img * sc.listCap;
     double* tab = table + (size_t)img * (maxLabels + 1) * 8;
     const int n = min(sc.fgCount[img], sc.listCap);
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(256) detect_moments_kernel(const T* __restrict
         const int v0 = L[p];
         const int l = (v0 <= -2) ? (-v0 - 1) : (-L[v0] - 1);
         if (l < 1) continue;   // an unranked root: only when the compact structures overflowed (status is set)
-        lab[p] = l;
+        if (labels) lab[p] = l;
         if (l <= maxLabels) {
             const double v = sign * (double)m[p];
             const int y = p / W, x = p - y * W;
@@ -552,16 +552,17 @@ __global__ void __launch_bounds__(256) detect_moments_kernel(const T* __restrict
 
 template <typename T>
 __global__ void __launch_bounds__(256) detect_argmax_kernel(const T* __restrict__ map, double sign, DetectScratch sc,
-                                                            const int* __restrict__ labels, double* __restrict__ table, int HW, int maxLabels) {
+                                                            double* __restrict__ table, int HW, int maxLabels) {
     const int img = blockIdx.y;
     const T* m = map + (size_t)img * HW;
-    const int* lab = labels + (size_t)img * HW;
+    const int* L = sc.L + (size_t)img * HW;
     const int* list = sc.fgList + (size_t)img * sc.listCap;
     double* tab = table + (size_t)img * (maxLabels + 1) * 8;
     const int n = min(sc.fgCount[img], sc.listCap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int p = list[i];
-        const int l = lab[p];
+        const int v0 = L[p];
+        const int l = (v0 <= -2) ? (-v0 - 1) : (-L[v0] - 1);
         if (l < 1 || l > maxLabels) continue;
         double* t = tab + (size_t)l * 8;
         if (enc_ordered(sign * (double)m[p]) == reinterpret_cast<const unsigned long long*>(t)[4])
@@ -571,15 +572,15 @@ __global__ void __launch_bounds__(256) detect_argmax_kernel(const T* __restrict_
 
 // first arg-max of the background (label 0), dense; only when the caller asks for maximum positions
 template <typename T>
-__global__ void __launch_bounds__(256) detect_bg_argmax_kernel(const T* __restrict__ map, double sign, const int* __restrict__ labels,
+__global__ void __launch_bounds__(256) detect_bg_argmax_kernel(const T* __restrict__ map, double sign, double thr,
                                                                double* __restrict__ table, int HW, int maxLabels) {
     const int img = blockIdx.y;
     const T* m = map + (size_t)img * HW;
-    const int* lab = labels + (size_t)img * HW;
     double* t = table + (size_t)img * (maxLabels + 1) * 8;
     const unsigned long long want = reinterpret_cast<const unsigned long long*>(t)[4];
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
-        if (lab[p] == 0 && enc_ordered(sign * (double)m[p]) == want)
+        const double v = sign * (double)m[p];
+        if (!(v > thr) && enc_ordered(v) == want)
             atomicMin(reinterpret_cast<unsigned long long*>(t) + 5, (unsigned long long)__double_as_longlong((double)p));
     }
 }
@@ -613,14 +614,239 @@ static int detect_t(const T* map, double thr, double sign, int* labels, int* nLa
     { NB_PROF_BEGIN(st); detect_moments_kernel<T><<<gridSparse, 256, 0, st>>>(map, sign, sc, labels, table, H, W, maxLabels); NB_PROF_END("detect_moments_kernel", st); }
     NB_CHECK_LAUNCH();
     if (flags & 1) {
-        { NB_PROF_BEGIN(st); detect_argmax_kernel<T><<<gridSparse, 256, 0, st>>>(map, sign, sc, labels, table, HW, maxLabels); NB_PROF_END("detect_argmax_kernel", st); }
+        { NB_PROF_BEGIN(st); detect_argmax_kernel<T><<<gridSparse, 256, 0, st>>>(map, sign, sc, table, HW, maxLabels); NB_PROF_END("detect_argmax_kernel", st); }
         NB_CHECK_LAUNCH();
         dim3 gridBg((HW + 256 * 8 - 1) / (256 * 8), B);
-        { NB_PROF_BEGIN(st); detect_bg_argmax_kernel<T><<<gridBg, 256, 0, st>>>(map, sign, labels, table, HW, maxLabels); NB_PROF_END("detect_bg_argmax_kernel", st); }
+        { NB_PROF_BEGIN(st); detect_bg_argmax_kernel<T><<<gridBg, 256, 0, st>>>(map, sign, thr, table, HW, maxLabels); NB_PROF_END("detect_bg_argmax_kernel", st); }
         NB_CHECK_LAUNCH();
     }
     { NB_PROF_BEGIN(st); moments_final_kernel<<<(unsigned)((nRows + 255) / 256), 256, 0, st>>>(table, nRows); NB_PROF_END("moments_final_kernel", st); }
     NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// findObjects' device work in one call (nb_find_objects): the map is read ONCE for the detection and the ring thresholds,
+// both foregrounds are linked / numbered / reduced over their compact lists, and the ring test is evaluated per candidate.
+// No dense label image is written unless asked for.
+struct DetectPass {
+    double thr;
+    DetectScratch sc;
+    double* table;
+    int* status;
+    int maxLabels;
+};
+
+template <typename T, int NP>
+__global__ void __launch_bounds__(DT_THREADS) detect_scan_multi_kernel(const T* __restrict__ map, double sign, DetectPass p0,
+                                                                       DetectPass p1, int* __restrict__ labels0, int H, int W) {
+    const int HW = H * W;
+    const int img = blockIdx.y;
+    const T* m = map + (size_t)img * HW;
+    const int lane = threadIdx.x & 31;
+    const DetectPass* ps[2] = {&p0, &p1};
+    double acc[NP][5];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
+        acc[q][4] = -INFINITY;
+    }
+    const int base = blockIdx.x * (DT_THREADS * DT_ITEMS) + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < DT_ITEMS; ++k) {
+        const int p = base + k * DT_THREADS;
+        const bool in = p < HW;
+        const double v = in ? sign * (double)m[p] : 0.0;
+        const int y = p / W, x = p - y * W;
+        if (labels0 && in) labels0[(size_t)img * HW + p] = 0;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const DetectPass& ps_q = *ps[q];
+            const bool fg = in && (v > ps_q.thr);
+            if (in && !fg) {
+                acc[q][0] += v;
+                acc[q][1] += v * (double)y;
+                acc[q][2] += v * (double)x;
+                acc[q][3] += 1.0;
+                acc[q][4] = fmax(acc[q][4], v);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, fg);
+            if (bal) {
+                int start = 0;
+                if (lane == 0) start = atomicAdd(&ps_q.sc.fgCount[img], __popc(bal));
+                start = __shfl_sync(0xffffffffu, start, 0);
+                if (fg) {
+                    const int pos = start + __popc(bal & ((1u << lane) - 1u));
+                    ps_q.sc.L[(size_t)img * HW + p] = p;
+                    if (pos < ps_q.sc.listCap) ps_q.sc.fgList[(size_t)img * ps_q.sc.listCap + pos] = p;
+                    else ps_q.status[img] = 1;
+                }
+            }
+        }
+    }
+    __shared__ double s_b[DT_THREADS / 32][NP][5];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const double a = warp_sum(acc[q][0]), b = warp_sum(acc[q][1]), c = warp_sum(acc[q][2]), d = warp_sum(acc[q][3]);
+        const double e = warp_max(acc[q][4]);
+        if (lane == 0) {
+            double* r = s_b[threadIdx.x >> 5][q];
+            r[0] = a; r[1] = b; r[2] = c; r[3] = d; r[4] = e;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NP) {
+        const int q = threadIdx.x;
+        double a = 0, b = 0, c = 0, d = 0, e = -INFINITY;
+        for (int w = 0; w < DT_THREADS / 32; ++w) {
+            a += s_b[w][q][0]; b += s_b[w][q][1]; c += s_b[w][q][2]; d += s_b[w][q][3]; e = fmax(e, s_b[w][q][4]);
+        }
+        if (d > 0) {
+            double* tab = ps[q]->table + (size_t)img * (ps[q]->maxLabels + 1) * 8;
+            atomicAdd(tab + 0, a);
+            atomicAdd(tab + 1, b);
+            atomicAdd(tab + 2, c);
+            atomicAdd(tab + 3, d);
+            atomicMax(reinterpret_cast<unsigned long long*>(tab) + 4, enc_ordered(e));
+        }
+    }
+}
+
+// label of pixel p at a threshold whose parent array has been ranked (0 = background)
+template <typename T>
+__device__ __forceinline__ int sparse_label_at(const T* __restrict__ m, const int* __restrict__ L, int p, double thr, double sign) {
+    if (!(sign * (double)m[p] > thr)) return 0;
+    const int v0 = L[p];
+    return (v0 <= -2) ? (-v0 - 1) : (-L[v0] - 1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ring_flags_sparse_kernel(const T* __restrict__ map, double sign, const double* __restrict__ detTable,
+                                                                const int* __restrict__ detN, int detCap, double ringThr,
+                                                                const int* __restrict__ ringL, const double* __restrict__ ringTable,
+                                                                int ringCap, int H, int W, double minRingPix, int posMode,
+                                                                unsigned char* __restrict__ flags) {
+    const int b = blockIdx.y;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o > detCap) return;
+    unsigned char out = 0;
+    if (o >= 1 && o <= detN[b]) {
+        const double* t = detTable + ((size_t)b * (detCap + 1) + o) * 8;
+        double y, x;
+        if (posMode == 0) {
+            y = t[1] / t[0];
+            x = t[2] / t[0];
+        } else {
+            y = floor(t[5] / (double)W);
+            x = t[5] - y * (double)W;
+        }
+        if (y == y && x == x) {
+            const int yi = min(max((int)y, 0), H - 1), xi = min(max((int)x, 0), W - 1);
+            const T* m = map + (size_t)b * H * W;
+            const int* L = ringL + (size_t)b * H * W;
+            const int r = sparse_label_at<T>(m, L, yi * W + xi, ringThr, sign);
+            if (r > 0 && r <= ringCap) {
+                const double* rt = ringTable + ((size_t)b * (ringCap + 1) + r) * 8;
+                if (rt[3] > minRingPix) {
+                    const double ry = rt[1] / rt[0], rx = rt[2] / rt[0];
+                    const int ryi = min(max((int)ry, 0), H - 1), rxi = min(max((int)rx, 0), W - 1);
+                    if (sparse_label_at<T>(m, L, ryi * W + rxi, ringThr, sign) != r) out = 1;
+                }
+            }
+        }
+    }
+    flags[(size_t)b * (detCap + 1) + o] = out;
+}
+
+__global__ void detect_merge_status_kernel(int* __restrict__ status, const int* __restrict__ ringStatus, const int* __restrict__ ringN,
+                                           int ringCap, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B && (ringStatus[i] != 0 || ringN[i] > ringCap)) status[i] = 1;
+}
+
+static void detect_scratch_carve(DetectScratch& sc, int*& cursor, int B, int H, int W) {
+    const size_t HW = (size_t)H * W;
+    sc.listCap = (int)detect_list_cap(H, W);
+    sc.L = cursor;
+    sc.fgList = sc.L + (size_t)B * HW;
+    sc.rootList = sc.fgList + (size_t)B * sc.listCap;
+    sc.fgCount = sc.rootList + (size_t)B * DT_ROOTCAP;
+    sc.rootCount = sc.fgCount + B;
+    cursor = sc.rootCount + B;
+}
+
+template <typename T>
+static int find_objects_t(const T* map, double thr, double ringThr, int haveRing, double sign, double minRingPix, int posMode,
+                          int* nLabels, int* status, double* table, unsigned char* ringFlags, int* labels, int maxLabels, int* scratch,
+                          int B, int H, int W, int flags, cudaStream_t st) {
+    const int HW = H * W;
+    int* cursor = scratch;
+    DetectPass p[2];
+    detect_scratch_carve(p[0].sc, cursor, B, H, W);
+    p[0].thr = thr;
+    p[0].table = table;
+    p[0].status = status;
+    p[0].maxLabels = maxLabels;
+    int *ringN = nullptr, *ringStatus = nullptr;
+    const int ringCap = DT_ROOTCAP;
+    if (haveRing) {
+        detect_scratch_carve(p[1].sc, cursor, B, H, W);
+        ringN = cursor;
+        ringStatus = ringN + B;
+        cursor = ringStatus + B;
+        if ((reinterpret_cast<size_t>(cursor) & 7) != 0) ++cursor;   // the ring table holds doubles
+        p[1].thr = ringThr;
+        p[1].table = reinterpret_cast<double*>(cursor);
+        p[1].status = ringStatus;
+        p[1].maxLabels = ringCap;
+    } else {
+        p[1] = p[0];
+    }
+    const int NP = haveRing ? 2 : 1;
+    for (int q = 0; q < NP; ++q) {
+        const long long nRows = (long long)B * (p[q].maxLabels + 1);
+        { NB_PROF_BEGIN(st); detect_reset_kernel<<<(B + 255) / 256, 256, 0, st>>>(p[q].sc.fgCount, p[q].sc.rootCount, p[q].status, B); NB_PROF_END("detect_reset_kernel", st); }
+        NB_CHECK_LAUNCH();
+        { NB_PROF_BEGIN(st); moments_init_kernel<<<(unsigned)((nRows + 255) / 256), 256, 0, st>>>(p[q].table, nRows); NB_PROF_END("moments_init_kernel", st); }
+        NB_CHECK_LAUNCH();
+    }
+    dim3 gridDense((HW + DT_THREADS * DT_ITEMS - 1) / (DT_THREADS * DT_ITEMS), B);
+    if (haveRing) {
+        { NB_PROF_BEGIN(st); detect_scan_multi_kernel<T, 2><<<gridDense, DT_THREADS, 0, st>>>(map, sign, p[0], p[1], labels, H, W); NB_PROF_END("detect_scan_multi_kernel", st); }
+    } else {
+        { NB_PROF_BEGIN(st); detect_scan_multi_kernel<T, 1><<<gridDense, DT_THREADS, 0, st>>>(map, sign, p[0], p[1], labels, H, W); NB_PROF_END("detect_scan_multi_kernel", st); }
+    }
+    NB_CHECK_LAUNCH();
+    dim3 gridSparse(64, B);
+    for (int q = 0; q < NP; ++q) {
+        int* nl = (q == 0) ? nLabels : ringN;
+        { NB_PROF_BEGIN(st); detect_link_kernel<T><<<gridSparse, 256, 0, st>>>(map, p[q].thr, sign, p[q].sc, H, W); NB_PROF_END("detect_link_kernel", st); }
+        NB_CHECK_LAUNCH();
+        { NB_PROF_BEGIN(st); detect_flatten_kernel<<<gridSparse, 256, 0, st>>>(p[q].sc, p[q].status, HW); NB_PROF_END("detect_flatten_kernel", st); }
+        NB_CHECK_LAUNCH();
+        { NB_PROF_BEGIN(st); detect_rank_kernel<<<B, 1024, 0, st>>>(p[q].sc, nl, HW); NB_PROF_END("detect_rank_kernel", st); }
+        NB_CHECK_LAUNCH();
+        { NB_PROF_BEGIN(st); detect_moments_kernel<T><<<gridSparse, 256, 0, st>>>(map, sign, p[q].sc, (q == 0) ? labels : nullptr, p[q].table, H, W, p[q].maxLabels); NB_PROF_END("detect_moments_kernel", st); }
+        NB_CHECK_LAUNCH();
+    }
+    if (flags & 1) {
+        { NB_PROF_BEGIN(st); detect_argmax_kernel<T><<<gridSparse, 256, 0, st>>>(map, sign, p[0].sc, table, HW, maxLabels); NB_PROF_END("detect_argmax_kernel", st); }
+        NB_CHECK_LAUNCH();
+        dim3 gridBg((HW + 256 * 8 - 1) / (256 * 8), B);
+        { NB_PROF_BEGIN(st); detect_bg_argmax_kernel<T><<<gridBg, 256, 0, st>>>(map, sign, thr, table, HW, maxLabels); NB_PROF_END("detect_bg_argmax_kernel", st); }
+        NB_CHECK_LAUNCH();
+    }
+    for (int q = 0; q < NP; ++q) {
+        const long long nRows = (long long)B * (p[q].maxLabels + 1);
+        { NB_PROF_BEGIN(st); moments_final_kernel<<<(unsigned)((nRows + 255) / 256), 256, 0, st>>>(p[q].table, nRows); NB_PROF_END("moments_final_kernel", st); }
+        NB_CHECK_LAUNCH();
+    }
+    if (haveRing) {
+        { NB_PROF_BEGIN(st); ring_flags_sparse_kernel<T><<<dim3((maxLabels + 1 + 255) / 256, B), 256, 0, st>>>(map, sign, table, nLabels, maxLabels, ringThr, p[1].sc.L, p[1].table, ringCap, H, W, minRingPix, posMode, ringFlags); NB_PROF_END("ring_flags_sparse_kernel", st); }
+        NB_CHECK_LAUNCH();
+        { NB_PROF_BEGIN(st); detect_merge_status_kernel<<<(B + 255) / 256, 256, 0, st>>>(status, ringStatus, ringN, ringCap, B); NB_PROF_END("detect_merge_status_kernel", st); }
+        NB_CHECK_LAUNCH();
+    }
     return NB_OK;
 }
 
@@ -670,6 +896,29 @@ int nb_ring_flags(const double* detTable, const int* detN, int detCap, const int
     { NB_PROF_BEGIN(st); ring_flags_kernel<<<dim3((detCap + 1 + 255) / 256, B), 256, 0, st>>>(detTable, detN, detCap, ringLabels, ringTable, ringCap, H, W, minRingPix, posMode, flags); NB_PROF_END("ring_flags_kernel", st); }
     NB_CHECK_LAUNCH();
     return NB_OK;
+}
+
+long long nb_find_objects_scratch_ints(int B, int H, int W) {
+    const long long HW = (long long)H * W;
+    const long long perPass = (long long)B * (HW + detect_list_cap(H, W) + DT_ROOTCAP + 2);
+    return 2 * perPass + 2LL * B + 2 + 2LL * B * (DT_ROOTCAP + 1) * 8;
+}
+
+int nb_find_objects(int prec, const void* map, double threshold, double ringThreshold, int haveRing, double sign, double minRingPix,
+                    int posMode, int* nLabels, int* status, double* table, unsigned char* ringFlags, int* labels, int maxLabels,
+                    int* scratch, int B, int H, int W, int flags, cudaStream_t st) {
+    NB_REQUIRE(map && nLabels && status && table && scratch && B > 0 && H > 0 && W > 0 && maxLabels >= 0, NB_ERR_ARG,
+               "nb_find_objects: bad arguments");
+    NB_REQUIRE(!haveRing || ringFlags, NB_ERR_ARG, "nb_find_objects: ringFlags required with a ring threshold");
+    NB_REQUIRE((long long)H * W < 0x7fffffffLL, NB_ERR_UNSUPPORTED, "nb_find_objects: image too large");
+    if (prec == NB_PREC_F64)
+        return find_objects_t<double>((const double*)map, threshold, ringThreshold, haveRing, sign, minRingPix, posMode, nLabels, status,
+                                      table, ringFlags, labels, maxLabels, scratch, B, H, W, flags, st);
+    if (prec == NB_PREC_F32)
+        return find_objects_t<float>((const float*)map, threshold, ringThreshold, haveRing, sign, minRingPix, posMode, nLabels, status,
+                                     table, ringFlags, labels, maxLabels, scratch, B, H, W, flags, st);
+    nb_set_error("nb_find_objects: bad precision %d", prec);
+    return NB_ERR_ARG;
 }
 
 long long nb_detect_scratch_ints(int B, int H, int W) {

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256) median_weights_kernel(const T* __restrict
 // K6.  One CTA per (cell, image).
 #define CR_THREADS 512
 #define CR_WARPS (CR_THREADS / 32)
+#define CR_MAXWARPS 32   // scratch of the block reductions below is sized for up to 1024 threads
 
 #define NB_MAX_CHUNKS 128
 struct Chunks {  // np.linspace(0, H, n + 1, dtype=int) boundaries, passed by value
@@ -65,14 +66,14 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* s_red) 
     __syncthreads();
     if (lane == 0) {
         s_red[wid] = a;
-        s_red[CR_WARPS + wid] = b;
+        s_red[CR_MAXWARPS + wid] = b;
     }
     __syncthreads();
     double ta = 0, tb = 0;
-#pragma unroll
-    for (int i = 0; i < CR_WARPS; ++i) {
+    const int nw = blockDim.x >> 5;
+    for (int i = 0; i < nw; ++i) {
         ta += s_red[i];
-        tb += s_red[CR_WARPS + i];
+        tb += s_red[CR_MAXWARPS + i];
     }
     a = ta;
     b = tb;
@@ -85,14 +86,14 @@ __device__ __forceinline__ void block_minmax(double& mn, double& mx, double* s_r
     __syncthreads();
     if (lane == 0) {
         s_red[wid] = mn;
-        s_red[CR_WARPS + wid] = mx;
+        s_red[CR_MAXWARPS + wid] = mx;
     }
     __syncthreads();
     double ta = INFINITY, tb = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < CR_WARPS; ++i) {
+    const int nw = blockDim.x >> 5;
+    for (int i = 0; i < nw; ++i) {
         ta = fmin(ta, s_red[i]);
-        tb = fmax(tb, s_red[CR_WARPS + i]);
+        tb = fmax(tb, s_red[CR_MAXWARPS + i]);
     }
     mn = ta;
     mx = tb;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(CR_THREADS) cell_rms_stream_kernel(const T* __
                                                               int W, const Chunks ch, int nx,
                                                               int ov, int numBins, double* __restrict__ table,
                                                               double* __restrict__ edges) {
-    __shared__ double s_red[2 * CR_WARPS];
+    __shared__ double s_red[2 * CR_MAXWARPS];
     __shared__ int s_hist[256];
     __shared__ unsigned long long s_sel[2];
     extern __shared__ double s_edges[];  // numBins + 1
@@ -298,9 +299,18 @@ __global__ void __launch_bounds__(CR_THREADS) cell_rms_stream_kernel(const T* __
 // value.  Each warp owns a contiguous run of the cell's pixels (lane-interleaved, so loads coalesce): weights
 // vary smoothly over the sky, so a warp usually meets only a few of the weight bins and skips the others.
 // Cells larger than the on-chip capacity use cell_rms_stream_kernel above.
+#ifndef OC_THREADS
 #define OC_THREADS 512
+#endif
 #define OC_WARPS (OC_THREADS / 32)
-#define OC_PPT 24
+#ifndef OC_PPT
+#define OC_PPT 24         // register slots per thread (a multiple of OC_LB)
+#endif
+#ifndef OC_LB
+#define OC_LB 8           // loads issued back to back per thread
+#endif
+#define OC_TGX 4          // warp tiles across the cell
+#define OC_TGY (OC_WARPS / OC_TGX)
 #define OC_GROUPS 16      // order statistics resolved together by the fallback radix select (one warp each)
 #define OC_MAXBINS 64
 #define OC_MAXTARGETS (2 * (OC_MAXBINS - 1))
@@ -398,7 +408,7 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     int* s_wstart = reinterpret_cast<int*>(oc_smem + lay.wstart);
     int* s_wrun = reinterpret_cast<int*>(oc_smem + lay.wrun);
     unsigned char* s_bins = oc_smem + lay.bins;
-    __shared__ double s_scr[2 * CR_WARPS];
+    __shared__ double s_scr[2 * CR_MAXWARPS];
     __shared__ int s_misc[4];   // [0] number of unique target buckets, [1] fallback flag, [2] groups (fallback)
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -411,10 +421,10 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     // the cell is cut into 4 x 4 warp tiles of tr x tc pixels; slot i = j * 32 + lane of a warp is pixel (i / tc, i % tc)
     // of its tile: j < OC_PPT in registers, the others in the warp's shared-memory run
     const int Rn = g.y1 - g.y0;
-    const int tr = (Rn + 3) >> 2, tc = (cw + 3) >> 2;
+    const int tr = (Rn + OC_TGY - 1) / OC_TGY, tc = (cw + OC_TGX - 1) / OC_TGX;
     const int JT = (tr * tc + 31) >> 5;                      // slots per lane
     const int spw = smemSlots / OC_WARPS;                    // shared-memory slots per warp
-    const int ty0 = (wid >> 2) * tr, tx0 = (wid & 3) * tc;
+    const int ty0 = (wid / OC_TGX) * tr, tx0 = (wid % OC_TGX) * tc;
     const float rcpTc = 1.0f / (float)tc;
     key_t* wSlots = s_slots + (size_t)wid * spw;             // this warp's run
     unsigned char* wBins = s_bins + (size_t)wid * spw;
@@ -451,29 +461,29 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     };
     resetCursor();
 #pragma unroll
-    for (int j0 = 0; j0 < OC_PPT; j0 += 8) {
-        long long off[8];
-        T mv[8], wv[8];
+    for (int j0 = 0; j0 < OC_PPT; j0 += OC_LB) {
+        long long off[OC_LB];
+        T mv[OC_LB], wv[OC_LB];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < OC_LB; ++u) {
             off[u] = nextOffset();
             mv[u] = (off[u] >= 0) ? m[off[u]] : (T)0;
             wv[u] = (off[u] >= 0) ? wm[off[u]] : (T)0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) reg[j0 + u] = makeKey(off[u], mv[u], wv[u]);
+        for (int u = 0; u < OC_LB; ++u) reg[j0 + u] = makeKey(off[u], mv[u], wv[u]);
     }
-    for (int j0 = OC_PPT; j0 < JT; j0 += 8) {
-        long long off[8];
-        T mv[8], wv[8];
+    for (int j0 = OC_PPT; j0 < JT; j0 += OC_LB) {
+        long long off[OC_LB];
+        T mv[OC_LB], wv[OC_LB];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < OC_LB; ++u) {
             off[u] = nextOffset();
             mv[u] = (off[u] >= 0) ? m[off[u]] : (T)0;
             wv[u] = (off[u] >= 0) ? wm[off[u]] : (T)0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < OC_LB; ++u)
             if (j0 + u < JT) wSlots[(j0 + u - OC_PPT) * 32 + lane] = makeKey(off[u], mv[u], wv[u]);
     }
     block_sum2(cnt, dummy, s_scr);
@@ -534,10 +544,11 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
         __syncthreads();
         // exclusive scan of the 2048 buckets (4 per thread), in place
         {
-            int loc[4], tot = 0;
+            constexpr int PER = OC_L1BUCKETS / OC_THREADS;
+            int loc[PER], tot = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                loc[i] = s_hist[tid * 4 + i];
+            for (int i = 0; i < PER; ++i) {
+                loc[i] = s_hist[tid * PER + i];
                 tot += loc[i];
             }
             int inc = tot;
@@ -554,8 +565,8 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
             for (int w = 0; w < wid; ++w) base += s_wsum[w];
             int run = base + inc - tot;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                s_hist[tid * 4 + i] = run;
+            for (int i = 0; i < PER; ++i) {
+                s_hist[tid * PER + i] = run;
                 run += loc[i];
             }
         }
@@ -772,15 +783,15 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     for (int j4 = 0; j4 < (OC_PPT + 3) / 4; ++j4) rbin[j4] = 0xffffffffu;
     resetCursor();
 #pragma unroll
-    for (int j0 = 0; j0 < OC_PPT; j0 += 8) {
-        T mv[8];
+    for (int j0 = 0; j0 < OC_PPT; j0 += OC_LB) {
+        T mv[OC_LB];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < OC_LB; ++u) {
             const long long off = nextOffset();
             mv[u] = (off >= 0) ? m[off] : (T)0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < OC_LB; ++u) {
             const int j = j0 + u;
             const unsigned int bin = binOf(reg[j]);
             rbin[j >> 2] = (rbin[j >> 2] & ~(255u << (8 * (j & 3)))) | (bin << (8 * (j & 3)));
@@ -807,15 +818,15 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
         wStart[numBins] = run;
     }
     __syncwarp();
-    for (int j0 = OC_PPT; j0 < JT; j0 += 8) {
-        T mv[8];
+    for (int j0 = OC_PPT; j0 < JT; j0 += OC_LB) {
+        T mv[OC_LB];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < OC_LB; ++u) {
             const long long off = nextOffset();
             mv[u] = (off >= 0) ? m[off] : (T)0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < OC_LB; ++u) {
             if (j0 + u >= JT) break;   // uniform over the warp
             const unsigned int bin = wBins[(j0 + u - OC_PPT) * 32 + lane];
             const unsigned peers = __match_any_sync(0xffffffffu, bin);
@@ -851,7 +862,11 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     __syncthreads();   // s_warpBins, and the scratch the selection used, are settled
 
     // ---- sweeps: -2 mean, -1 std about the mean, 0..9 clipping iterations (filters.py:466-477) -----------------
+#ifdef OC_EXP_NOSWEEP
+    for (int it = -2; it < -2; ++it) {
+#else
     for (int it = -2; it < 10; ++it) {
+#endif
         double* red = s_red + (size_t)(it & 1) * OC_WARPS * numBins * 3;
         unsigned long long todo = present;
         while (todo) {
@@ -1088,7 +1103,7 @@ static int cell_rms_t(const void* map, const void* wmed, int nImg, int S, int H,
     for (int k = 0; k < nx; ++k) maxW = std::max(maxW, std::min(ch.x[k + 1] + ov, W) - std::max(ch.x[k] - ov, 0));
     const long long maxCell = (long long)maxH * maxW;
     // 4 x 4 warp tiles; OC_PPT * 32 pixels of a tile live in registers, the rest in shared memory
-    const long long tilePix = (long long)((maxH + 3) / 4) * ((maxW + 3) / 4);
+    const long long tilePix = (long long)((maxH + OC_TGY - 1) / OC_TGY) * ((maxW + OC_TGX - 1) / OC_TGX);
     const long long CH = ((tilePix + 31) / 32) * 32;
     const long long perWarp = CH > (long long)OC_PPT * 32 ? CH - (long long)OC_PPT * 32 : 0;
     const long long smemSlots = perWarp * OC_WARPS;

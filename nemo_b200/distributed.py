@@ -74,16 +74,30 @@ def shardTiles(tileNames, rank, size):
     return list(tileNames)[rank::size]
 
 
-def packTable(tab, keys):
-    """Table (or []) -> (numeric [n, nNum] fp64, strings [n, nStr * STR_WIDTH] u8) for a fixed column list."""
+def packTable(tab, keys, labels=None, tileNames=None):
+    """Table (or []) -> (numeric [n, nNum] fp64, strings [n, nStr * STR_WIDTH] u8) for a fixed column list.
+
+    When `labels` (filter labels) and `tileNames` are given -- lists every rank holds -- the 'template' and 'tileName'
+    columns travel as indices into them and 'name' is not sent at all (it is a function of RADeg, decDeg and is
+    re-attached, deferred, on the receiving side): the payload is then purely numeric."""
     n = len(tab)
+    coded = labels is not None and tileNames is not None
+    strKeys = [] if coded else [k for k in keys if k in ('name', 'template', 'tileName')]
     numKeys = [k for k in keys if k not in ('name', 'template', 'tileName')]
-    strKeys = [k for k in keys if k in ('name', 'template', 'tileName')]
+    if coded:
+        numKeys = numKeys + [k for k in ('template', 'tileName') if k in keys]
     num = np.zeros((n, len(numKeys)), dtype=np.float64)
     strs = np.zeros((n, len(strKeys) * STR_WIDTH), dtype=np.uint8)
     if n > 0:
         for j, k in enumerate(numKeys):
-            num[:, j] = np.asarray(tab[k], dtype=np.float64) if k in tab.keys() else -99
+            if coded and k == 'template':
+                lut = {v: i for i, v in enumerate(labels)}
+                num[:, j] = [lut[v] for v in tab[k]]
+            elif coded and k == 'tileName':
+                lut = {v: i for i, v in enumerate(tileNames)}
+                num[:, j] = [lut[v] for v in tab[k]]
+            else:
+                num[:, j] = np.asarray(tab[k], dtype=np.float64) if k in tab.keys() else -99
         for j, k in enumerate(strKeys):
             for i, s in enumerate(tab[k]):
                 b = str(s).encode()[:STR_WIDTH]
@@ -91,57 +105,77 @@ def packTable(tab, keys):
     return num, strs, numKeys, strKeys
 
 
-def unpackTable(num, strs, numKeys, strKeys):
+def unpackTable(num, strs, numKeys, strKeys, labels=None, tileNames=None, objIdent='ACT-CL', longNames=False):
     tab = catalogs.Table()
     n = num.shape[0]
     cols = {}
+    coded = labels is not None and tileNames is not None
     for j, k in enumerate(numKeys):
-        cols[k] = num[:, j].copy()
+        if coded and k == 'template':
+            cols[k] = np.array([labels[int(i)] for i in num[:, j]], dtype=object)
+        elif coded and k == 'tileName':
+            cols[k] = np.array([tileNames[int(i)] for i in num[:, j]], dtype=object)
+        else:
+            cols[k] = num[:, j].copy()
     for j, k in enumerate(strKeys):
         cols[k] = np.array([bytes(strs[i, j * STR_WIDTH:(j + 1) * STR_WIDTH]).rstrip(b'\x00').decode() for i in range(n)], dtype=object)
-    for k in list(numKeys) + list(strKeys):
-        tab.add_column(catalogs.Column(cols[k], k))
-    return tab
+    if coded and 'RADeg' in cols:
+        ra, dec = cols['RADeg'], cols['decDeg']
+        cols['name'] = catalogs.deferred(lambda: catalogs.makeNames(ra, dec, prefix=objIdent, longNames=longNames))
+    return catalogs.Table.fromColumns([(k, cols[k]) for k in (['name'] if 'name' in cols and coded else []) + list(numKeys) + list(strKeys)])
 
 
-def allGatherCatalog(comm, tab, keys):
+def allGatherCatalog(comm, tab, keys, labels=None, tileNames=None, objIdent='ACT-CL', longNames=False):
     """Every rank gets the concatenation of all ranks' catalogs, with duplicates across tiles removed (the
     reference strips them after its allgather, pipelines.py:329-331) and rows sorted by (RADeg, decDeg)."""
-    num, strs, numKeys, strKeys = packTable(tab, keys)
-    nums = comm.allGatherArrays(num)
-    strss = comm.allGatherArrays(strs)
-    num = np.concatenate(nums, axis=0)
-    strs = np.concatenate(strss, axis=0)
-    merged = unpackTable(num, strs, numKeys, strKeys)
-    ordered = catalogs.Table()
-    for k in keys:
-        ordered.add_column(catalogs.Column(merged[k], k))
+    num, strs, numKeys, strKeys = packTable(tab, keys, labels, tileNames)
+    num = np.concatenate(comm.allGatherArrays(num), axis=0)
+    if len(strKeys) > 0:
+        strs = np.concatenate(comm.allGatherArrays(strs), axis=0)
+    else:
+        strs = np.zeros((num.shape[0], 0), dtype=np.uint8)
+    merged = unpackTable(num, strs, numKeys, strKeys, labels, tileNames, objIdent, longNames)
+    ordered = catalogs.Table.fromColumns([(k, merged._cols.raw(k)) for k in keys if k in merged.keys()])
     if len(ordered) > 0:
         ordered = catalogs.removeDuplicates(ordered)
         ordered.sort(['RADeg', 'decDeg'])
     return ordered
 
 
-def gatherNoiseTables(comm, noiseTables):
+def gatherNoiseTables(comm, noiseTables, labels=None, tileNames=None):
     """{label#tile: [nCells, nBins] array} from every rank -> the union on every rank (rank 0 is the consumer in the
-    reference, pipelines.py:405-420; an all-gather costs the same for these sizes)."""
-    labels = sorted(noiseTables.keys())
-    if len(labels) > 0:
-        flat = np.stack([np.asarray(noiseTables[k], dtype=np.float64).ravel() for k in labels])
-        shape = noiseTables[labels[0]].shape
+    reference, pipelines.py:405-420; an all-gather costs the same for these sizes).  With `labels` / `tileNames` the keys
+    travel as two index columns in front of the flattened table: one numeric collective."""
+    keysSorted = sorted(noiseTables.keys())
+    coded = labels is not None and tileNames is not None
+    if len(keysSorted) > 0:
+        flat = np.stack([np.asarray(noiseTables[k], dtype=np.float64).ravel() for k in keysSorted])
+        shape = noiseTables[keysSorted[0]].shape
     else:
         flat = np.zeros((0, 0))
         shape = (0, 0)
     width = int(comm.maxOverRanks(flat.shape[1] if flat.size else 0))
     if flat.shape[1] != width:
         flat = np.zeros((0, width))
-    names = np.zeros((len(labels), STR_WIDTH * 2), dtype=np.uint8)
-    for i, s in enumerate(labels):
+    out = {}
+    if coded:
+        codes = np.zeros((flat.shape[0], 2))
+        lutL = {v: i for i, v in enumerate(labels)}
+        lutT = {v: i for i, v in enumerate(tileNames)}
+        for i, k in enumerate(keysSorted[:flat.shape[0]]):
+            lab, tile = k.split('#', 1)
+            codes[i] = (lutL[lab], lutT[tile])
+        for fl in comm.allGatherArrays(np.concatenate([codes, flat], axis=1)):
+            for row in fl:
+                key = labels[int(row[0])] + "#" + tileNames[int(row[1])]
+                out[key] = row[2:].reshape(shape) if int(np.prod(shape)) == width else row[2:].copy()
+        return out
+    names = np.zeros((len(keysSorted), STR_WIDTH * 2), dtype=np.uint8)
+    for i, s in enumerate(keysSorted):
         b = s.encode()[:STR_WIDTH * 2]
         names[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
     allFlat = comm.allGatherArrays(flat)
     allNames = comm.allGatherArrays(names)
-    out = {}
     for fl, nm in zip(allFlat, allNames):
         for i in range(fl.shape[0]):
             key = bytes(nm[i]).rstrip(b'\x00').decode()

@@ -277,6 +277,29 @@ class Ops(object):
         self.launches += 8
         return labels, nLabels, status, table
 
+    def find_objects(self, maps, threshold, ringThreshold=None, sign=1.0, minRingPix=30, findCenterOfMass=True, maxLabels=None,
+                     wantLabels=False):
+        """Device side of findObjects in one asynchronous call: returns (nLabels, status, table, ringFlags or None, labels or
+        None) as device tensors; see nb_find_objects."""
+        self._check(maps, self.dtype, 'maps')
+        B, H, W = maps.shape
+        t = self.torch
+        if maxLabels is None:
+            maxLabels = self.DETECT_MAX_LABELS
+        haveRing = ringThreshold is not None
+        nLabels = self.empty((B,), t.int32)
+        status = self.empty((B,), t.int32)
+        table = self.empty((B, int(maxLabels) + 1, 8), t.float64)
+        ringFlags = self.empty((B, int(maxLabels) + 1), t.uint8) if haveRing else None
+        labels = self.empty((B, H, W), t.int32) if wantLabels else None
+        nInts = int(_lib.load().nb_find_objects_scratch_ints(B, H, W))
+        scratch = self.empty(((nInts + 1) // 2,), t.int64)       # 8-byte aligned
+        _lib.call('nb_find_objects', self.prec, _ptr(maps), float(threshold), float(ringThreshold) if haveRing else 0.0, 1 if haveRing else 0,
+                  float(sign), float(minRingPix), 0 if findCenterOfMass else 1, _ptr(nLabels), _ptr(status), _ptr(table), _ptr(ringFlags),
+                  _ptr(labels), int(maxLabels), _ptr(scratch), B, H, W, 0 if findCenterOfMass else 1, self._stream())
+        self.launches += 14 if haveRing else 7
+        return nLabels, status, table, ringFlags, labels
+
     def ring_flags(self, detTable, detN, ringLabels, ringTable, minRingPix=30, findCenterOfMass=True):
         """u8 [B, detCap + 1]: 1 where a candidate sits on a ring (photometry.py:60-70, 104-105); asynchronous."""
         t = self.torch

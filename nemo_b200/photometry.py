@@ -142,35 +142,28 @@ def startFindObjectsBatch(ops, snMaps, threshold=3.0, findCenterOfMass=True, rem
     if threshold < 0 or (removeRings == True and ringThresholdSigma < 0):
         raise Exception("Detection threshold (thresholdSigma in the config file) cannot be negative unless in forced photometry mode.")
     sign = -1.0 if invertMap == True else 1.0
-    job = _launchSegments(ops, snMaps, [threshold, ringThresholdSigma] if removeRings == True else [threshold], sign=sign,
-                          wantArgmax=not findCenterOfMass)
-    job.update({'threshold': threshold, 'findCenterOfMass': findCenterOfMass, 'removeRings': removeRings, 'ringFlags': None})
-    if removeRings == True:
-        (_, detN, _, detTable), (ringLabels, _, _, ringTable) = job['launched']
-        job['ringFlags'] = ops.ring_flags(detTable, detN, ringLabels, ringTable, minRingPix=MIN_RING_PIX, findCenterOfMass=findCenterOfMass)
-    return job
+    dev = ops.find_objects(snMaps, threshold, ringThresholdSigma if removeRings == True else None, sign=sign,
+                           minRingPix=MIN_RING_PIX, findCenterOfMass=findCenterOfMass)
+    return {'ops': ops, 'imgs': snMaps, 'sign': sign, 'thresholds': [threshold, ringThresholdSigma] if removeRings == True else [threshold],
+            'threshold': threshold, 'findCenterOfMass': findCenterOfMass, 'removeRings': removeRings, 'dev': dev}
 
 
 def _collectDetections(job):
-    """(labels tensor, nLabels host, moment table host [B, nmax + 1, 8], ring flags host [B, nmax + 1] or None) of a
-    startFindObjectsBatch job.  One synchronising copy of the counts, then two small ones; the ring-threshold table never
-    leaves the device.  Images that overflowed the sparse detector are redone with the dense kernels."""
-    ops, imgs, launched, sign = job['ops'], job['imgs'], job['launched'], job['sign']
+    """(nLabels host, moment table host [B, nmax + 1, 8], ring flags host [B, nmax + 1] or None) of a startFindObjectsBatch job.
+    One synchronising copy of the counts, then two small ones; nothing at the ring threshold leaves the device.  Batches
+    that overflowed the sparse detector are redone with the dense kernels."""
+    ops, imgs, sign = job['ops'], job['imgs'], job['sign']
     torch = ops.torch
-    info = device.toHost(torch.stack([torch.stack([nl, st]) for _, nl, st, _ in launched]))
-    caps = [t.shape[1] - 1 for _, _, _, t in launched]
-    overflow = any(info[k, 1].any() or int(info[k, 0].max()) > caps[k] for k in range(len(launched)))
-    if not overflow:
-        labels, _, _, table = launched[0]
-        n = info[0, 0]
-        flags = job['ringFlags']
-    else:
+    nLabels, status, table, flags, _ = job['dev']
+    info = device.toHost(torch.stack([nLabels, status]))
+    n = info[0]
+    if info[1].any() or (len(n) and int(n.max()) > table.shape[1] - 1):
         dense = []
         for thr in job['thresholds']:
             lab, nl = ops.label4(imgs, thr, sign=sign)
             nmaxK = int(device.toHost(nl).max())
             dense.append((lab, nl, ops.label_moments(imgs, lab, nmaxK, sign=sign)))
-        labels, nlDev, table = dense[0]
+        _, nlDev, table = dense[0]
         n = device.toHost(nlDev)
         flags = None
         if job['removeRings'] == True:
@@ -178,7 +171,7 @@ def _collectDetections(job):
     nmax = int(n.max()) if len(n) else 0
     tableHost = device.toHost(table[:, :nmax + 1].contiguous())
     flagsHost = device.toHost(flags[:, :nmax + 1].contiguous()) if flags is not None else None
-    return labels, n, tableHost, flagsHost
+    return n, tableHost, flagsHost
 
 
 def _flatObjects(table, n, shape, findCenterOfMass=True, minPix=None):
@@ -216,7 +209,7 @@ def finishFindObjectsBatch(job, wcsList, flagMaskList, labelList, tileNameList, 
     ops, snMaps, sign = job['ops'], job['imgs'], job['sign']
     threshold, findCenterOfMass, removeRings = job['threshold'], job['findCenterOfMass'], job['removeRings']
     B, H, W = snMaps.shape
-    labels, n, table, ringFlags = _collectDetections(job)
+    n, table, ringFlags = _collectDetections(job)
     cb, cid, cy, cx, cn = _flatObjects(table, n, (H, W), findCenterOfMass, minPix=minObjPix)
     keep = cn > minObjPix
     if ringFlags is not None:

@@ -393,8 +393,10 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
         from . import distributed
         havePhot = parDict.get('photFilter') is not None and any(f['label'] == parDict['photFilter'] for f in filtersList)
         keys = catalogKeys(havePhot, templates.outputUnits, measureFluxes)
-        optimalCatalog = distributed.allGatherCatalog(comm, optimalCatalog, keys)
-        noiseTables = distributed.gatherNoiseTables(comm, noiseTables)
+        labels = [f['label'] for f in filtersList]
+        optimalCatalog = distributed.allGatherCatalog(comm, optimalCatalog, keys, labels, config.allTileNames,
+                                                      objIdent=parDict['objIdent'], longNames=parDict['longNames'])
+        noiseTables = distributed.gatherNoiseTables(comm, noiseTables, labels, config.allTileNames)
     config.catalogDict = catalogDict
     config.noiseTables = noiseTables
     return optimalCatalog

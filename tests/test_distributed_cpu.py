@@ -49,9 +49,14 @@ def _worker(rank, world, port, q):
         keys = pipelines.catalogKeys(False, 'yc', True)
         tab = _rankCatalog(rank) if rank == 0 else _rankCatalog(rank)
         # err columns are not in this toy table: the packer writes -99 for missing numeric columns
-        merged = distributed.allGatherCatalog(comm, tab, keys)
-        noise = distributed.gatherNoiseTables(comm, {'F#tile%d' % rank: np.full((4, 2), float(rank + 1))})
+        # coded form (what the pipeline uses): template / tileName as indices, names re-derived on arrival
+        labels, tileNames = ['Arnaud_M2e14_z0p4', 'other'], ['tile0', 'tile1']
+        merged = distributed.allGatherCatalog(comm, tab, keys, labels, tileNames)
+        noise = distributed.gatherNoiseTables(comm, {'F#tile%d' % rank: np.full((4, 2), float(rank + 1))}, ['F'], tileNames)
+        # plain form with string columns; one rank has nothing to contribute
         empty = distributed.allGatherCatalog(comm, [] if rank == 1 else tab, keys)
+        noise2 = distributed.gatherNoiseTables(comm, {'F#tile%d' % rank: np.full((4, 2), float(rank + 1))})
+        assert sorted(noise2.keys()) == sorted(noise.keys()) and np.array_equal(noise2['F#tile1'], noise['F#tile1'])
         result = {'n': len(merged), 'ra': list(merged['RADeg']), 'snr': list(merged['SNR']), 'names': list(merged['name']),
                   'tiles': list(merged['tileName']), 'noiseKeys': sorted(noise.keys()), 'noise1': noise['F#tile1'].tolist(),
                   'nEmpty': len(empty), 'max': comm.maxOverRanks(rank + 1.5), 'sum': comm.sumOverRanks(rank + 1.0)}

@@ -215,3 +215,45 @@ def test_batched_pipeline_matches_per_tile_oracle(report):
     assert nObj >= 6
     assert len(opt) > 0 and len(opt) <= nObj
     report("batched_pipeline", objects=nObj, optimal=len(opt))
+
+
+@pytest.mark.parametrize("findCenterOfMass", [True, False])
+def test_find_objects_ring_removal_and_options(report, findCenterOfMass):
+    """photometry.findObjects on hand-made S/N maps: detections sitting on > 30-pixel rings at ringThresholdSigma are
+    dropped (photometry.py:60-70, 104-105), others kept; centre-of-mass and maximum-position modes, invertMap, minObjPix."""
+    from scipy import ndimage
+    from nemo_b200 import photometry
+    from oracle.wcs_stub import SimpleCARWCS
+    rng = np.random.default_rng(8)
+    H, W = 256, 320
+    sn = ndimage.gaussian_filter(rng.standard_normal((H, W)), 1.2)
+    sn /= sn.std()
+    yy, xx = np.mgrid[:H, :W]
+    for cy, cx in [(60, 70), (180, 240)]:                       # two rings (artefacts around bright sources)
+        r = np.hypot(yy - cy, xx - cx)
+        sn[(r > 10) & (r < 14)] = 3.6
+        # a "detection" sitting on each ring (a peaked bump: exact ties would make scipy's maximum_position arbitrary)
+        sn = np.maximum(sn, 7.0 * np.exp(-0.5 * ((yy - cy - 0.3) ** 2 + (xx - cx - 12.2) ** 2) / 1.5 ** 2))
+    for cy, cx, a in [(120, 100, 9.0), (40, 250, 6.0), (200, 60, 12.0)]:
+        sn += a * np.exp(-0.5 * ((yy - cy) ** 2 + (xx - cx) ** 2) / 2.0 ** 2)
+    # as in a real filtered map (apodisation mask, filters.py:749-750) nothing survives near the tile edge; the GPU spline
+    # differs from FITPACK's not-a-knot spline only there (DESIGN.md section 5)
+    sn[:24, :] = 0
+    sn[-24:, :] = 0
+    sn[:, :24] = 0
+    sn[:, -24:] = 0
+    wcs = SimpleCARWCS((H, W), 0.5 / 60)
+    wcs.header['BUNIT'] = 'yc'
+    fmd = {'SNMap': sn, 'data': sn * 1e-5, 'wcs': wcs, 'surveyMask': np.ones((H, W)), 'flagMask': np.zeros((H, W), dtype=int),
+           'label': 'F', 'tileName': 'T', 'mapUnits': 'yc', 'obsFreqGHz': 148.0, 'beamSolidAngle_nsr': 0.0}
+    for kw in [dict(), dict(removeRings=False), dict(minObjPix=6), dict(invertMap=True, threshold=2.5, ringThresholdSigma=2.0)]:
+        opts = dict(threshold=4.0, minObjPix=1, findCenterOfMass=findCenterOfMass, removeRings=True, ringThresholdSigma=3,
+                    useInterpolator=True, rejectBorder=0)
+        opts.update(kw)
+        ref = photometry_ref.findObjects(fmd, **opts)
+        got = photometry.findObjects(fmd, **opts)
+        _compareCatalogs(got, ref, ['SNR'])
+        if not kw:
+            plain = photometry_ref.findObjects(fmd, **dict(opts, removeRings=False))
+            assert len(plain) == len(ref) + 2, "the two detections on the rings should be the only ones removed"
+    report("find_objects_rings", com=int(findCenterOfMass), objects=len(ref))

@@ -26,9 +26,34 @@ yc = np.linspace(0, H, int(H / grid + 1), dtype=int)
 xc = np.linspace(0, W, int(W / grid + 1), dtype=int)
 
 
+psMask = torch.ones((nT, H, W), dtype=torch.uint8, device='cuda')
+norm = torch.ones((nT,), dtype=torch.float64, device='cuda')
+state = {}
+
+
 def run():
     if args.op == 'cell_rms':
         return ops.cell_rms(maps, wmed, 1, yc, xc, grid // 2, args.bins)
+    if args.op == 'rfft2':
+        return ops.rfft2(maps, apodPix=20)
+    if args.op == 'apply':
+        if 'fm' not in state:
+            state['fm'] = ops.rfft2(maps, apodPix=20).reshape(nT, 1, H, W // 2 + 1)
+            state['filt'] = torch.rand((nT, 1, H, W // 2 + 1), device='cuda', dtype=ops.dtype)
+        return ops.apply_filter(state['fm'], state['filt'], 1, norm=norm, mask=psMask)
+    if args.op == 'window':
+        return ops.apply_window(maps.clone(), -1.0, restoreZeros=True)
+    if args.op == 'snr_mask':
+        rms = torch.ones_like(maps)
+        return ops.snr_mask(maps.clone(), rms, psMask, psMask, 1, 240, 20, False)
+    if args.op == 'filter_build':
+        if 'fm' not in state:
+            state['fm'] = ops.rfft2(maps, apodPix=20).reshape(nT, 1, H, W // 2 + 1)
+            state['fsig'] = ops.rfft2(maps[:1], apodPix=0).reshape(1, 1, H, W // 2 + 1)
+        cov = ops.xpower_smooth(state['fm'], 3.0)
+        return ops.build_filter(cov, state['fsig'], [1.0], 1, False)
+    if args.op == 'detect':
+        return ops.detect(maps / 100.0, 3.0)
     raise SystemExit("unknown op " + args.op)
 
 
