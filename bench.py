@@ -211,6 +211,7 @@ def main():
     ap.add_argument('--precision', default='f64', choices=['f64', 'f32'])
     ap.add_argument('--tiles', type=int, default=TILES_PER_GPU, help='tiles per GPU')
     ap.add_argument('--tiles-per-batch', type=int, default=16)
+    ap.add_argument('--e2e-tiles-per-batch', type=int, default=8, help='batch size of the end-to-end arm (uploads overlap compute)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--kernel-table', default=None, help='write the per-kernel roofline table to this file')
     args = ap.parse_args()
@@ -266,26 +267,40 @@ def main():
         b.upload()
     torch.cuda.synchronize()
 
-    def deviceStep():
-        results = pipelines.processBatches(ops, batches, filtersList, templates, parDict, upload=False, undoPixelWindow=True)
-        return sum(len(v['catalog']) for cd, _ in results for v in cd.values())
+    # one pipeline for the whole run: the host half of step i (catalog assembly) overlaps the device half of step i + 1,
+    # as it does in a run over many tiles; flush() inside the timed region completes the last step
+    def countObjects(res):
+        return sum(len(v['catalog']) for v in res[0].values())
 
-    for _ in range(args.warmup):
-        nObj = deviceStep()
+    def deviceSteps(n):
+        pipe = pipelines.BatchPipeline(ops, filtersList, templates, parDict, undoPixelWindow=True)
+        nObj = 0
+        for _ in range(n):
+            for b in batches:
+                out = pipe.submit(b, upload=False)
+                if out is not None:
+                    nObj += countObjects(out)
+        nObj += countObjects(pipe.flush())
+        return nObj // n
+
+    nObj = deviceSteps(args.warmup)
     sampler = ClockSampler(localRank)
     barrier()
     if rank == 0:
         sampler.start()
-    _lib.profEnable(True)
     launches0 = _lib.launchCount()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        nObj = deviceStep()
+    nObj = deviceSteps(args.steps)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = (_lib.launchCount() - launches0) // args.steps
+    # per-kernel CUDA-event times: the same steps once more, one at a time (no overlap between consecutive steps, which
+    # would stretch the individual kernel times), with the library's event timers on
+    _lib.profEnable(True)
+    for _ in range(args.steps):
+        deviceSteps(1)
     prof = _lib.profReport()
     _lib.profEnable(False)
     msStep = maxOverRanks(e0.elapsed_time(e1) / args.steps)
@@ -296,12 +311,12 @@ def main():
     for b in batches:
         b.dev = None
     for _ in range(2):
-        cat = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=args.tiles_per_batch, precision=args.precision, comm=comm)
+        cat = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=args.e2e_tiles_per_batch, precision=args.precision, comm=comm)
     barrier()
     device.TRAFFIC['h2d'] = device.TRAFFIC['d2h'] = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cat = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=args.tiles_per_batch, precision=args.precision, comm=comm)
+        cat = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=args.e2e_tiles_per_batch, precision=args.precision, comm=comm)
     torch.cuda.synchronize()
     tE2E = maxOverRanks((time.perf_counter() - t0) / args.steps)
     barrier()
@@ -337,7 +352,7 @@ def main():
     if top is not None:
         lp = top['launches_per_step']
         roofline = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
-                    'frac': top['frac'], 'traffic': None, 'peak_source': peakSrc, 'share_of_step_kernel_time': top['share'],
+                    'frac': top['frac'], 'traffic': None, 'peak_source': peakSrc, 'timed_in': 'same run, %d further steps executed one at a time with per-kernel CUDA events' % args.steps, 'share_of_step_kernel_time': top['share'],
                     'bytes_per_launch': top['algorithmic_bytes_per_step'] / lp, 'ms_per_launch': top['ms_per_step'] / lp,
                     'launches_per_step': lp}
     bpp = endToEndBytesPerPixel(F, S, E, rings=parDict['removeRings'])
@@ -358,7 +373,7 @@ def main():
             'ms_per_step': msStep, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': args.precision, 'data': 'synthetic',
             'config': {'workload': 'configs[1]: BeamMatchedFilter + S/N>4 detection on a 4096x4096 148 GHz map in 16 tiles of 1024x1024 per GPU',
-                       'tiles_per_gpu': nT, 'tile': list(SHAPE), 'freqs': F, 'scales': S, 'tiles_per_batch': args.tiles_per_batch,
+                       'tiles_per_gpu': nT, 'tile': list(SHAPE), 'freqs': F, 'scales': S, 'tiles_per_batch': args.tiles_per_batch, 'e2e_tiles_per_batch': args.e2e_tiles_per_batch,
                        'l2': 'inputs and intermediates of one step (> 1 GB) exceed the 126 MB L2; no explicit flush',
                        'objects_per_step': nObj},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'step_roofline': stepRoofline,

@@ -157,7 +157,8 @@ long long nb_detect_scratch_ints(int B, int H, int W);
  * once for the detection threshold and (haveRing != 0) the ring threshold; both foregrounds are labelled and reduced as in
  * nb_detect; ringFlags [B, maxLabels + 1] u8 is 1 for a detection-threshold label whose position (centre of mass when
  * posMode = 0, first maximum when 1) lies on a ring-threshold component of more than minRingPix pixels that does not contain
- * its own centre of mass.  Outputs for the detection threshold: nLabels [B], table [B, maxLabels + 1, 8], status [B]
+ * its own centre of mass.  Outputs for the detection threshold: nLabels [B], table [B, maxLabels + 1, 8] (row 0, the
+ * background, is left empty: findObjects never uses it), status [B]
  * (1 = compact structures overflowed at either threshold: use nb_label4 / nb_label_moments / nb_ring_flags), and the
  * dense segmentation labels [B, H, W] when non-NULL.  flags bit 0: first-arg-max columns.
  * scratch: nb_find_objects_scratch_ints(B, H, W) int32 words, 8-byte aligned. */

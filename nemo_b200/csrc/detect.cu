@@ -637,7 +637,7 @@ struct DetectPass {
     int maxLabels;
 };
 
-template <typename T, int NP>
+template <typename T, int NP, bool BG>
 __global__ void __launch_bounds__(DT_THREADS) detect_scan_multi_kernel(const T* __restrict__ map, double sign, DetectPass p0,
                                                                        DetectPass p1, int* __restrict__ labels0, int H, int W) {
     const int HW = H * W;
@@ -657,13 +657,13 @@ __global__ void __launch_bounds__(DT_THREADS) detect_scan_multi_kernel(const T* 
         const int p = base + k * DT_THREADS;
         const bool in = p < HW;
         const double v = in ? sign * (double)m[p] : 0.0;
-        const int y = p / W, x = p - y * W;
+        const int y = BG ? p / W : 0, x = BG ? p - y * W : 0;
         if (labels0 && in) labels0[(size_t)img * HW + p] = 0;
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
             const DetectPass& ps_q = *ps[q];
             const bool fg = in && (v > ps_q.thr);
-            if (in && !fg) {
+            if (BG && in && !fg) {
                 acc[q][0] += v;
                 acc[q][1] += v * (double)y;
                 acc[q][2] += v * (double)x;
@@ -684,6 +684,7 @@ __global__ void __launch_bounds__(DT_THREADS) detect_scan_multi_kernel(const T* 
             }
         }
     }
+    if constexpr (BG) {   // otherwise label 0 (background) moments are not wanted: its table row stays empty
     __shared__ double s_b[DT_THREADS / 32][NP][5];
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
@@ -709,6 +710,7 @@ __global__ void __launch_bounds__(DT_THREADS) detect_scan_multi_kernel(const T* 
             atomicAdd(tab + 3, d);
             atomicMax(reinterpret_cast<unsigned long long*>(tab) + 4, enc_ordered(e));
         }
+    }
     }
 }
 
@@ -812,9 +814,9 @@ static int find_objects_t(const T* map, double thr, double ringThr, int haveRing
     }
     dim3 gridDense((HW + DT_THREADS * DT_ITEMS - 1) / (DT_THREADS * DT_ITEMS), B);
     if (haveRing) {
-        { NB_PROF_BEGIN(st); detect_scan_multi_kernel<T, 2><<<gridDense, DT_THREADS, 0, st>>>(map, sign, p[0], p[1], labels, H, W); NB_PROF_END("detect_scan_multi_kernel", st); }
+        { NB_PROF_BEGIN(st); detect_scan_multi_kernel<T, 2, false><<<gridDense, DT_THREADS, 0, st>>>(map, sign, p[0], p[1], labels, H, W); NB_PROF_END("detect_scan_multi_kernel", st); }
     } else {
-        { NB_PROF_BEGIN(st); detect_scan_multi_kernel<T, 1><<<gridDense, DT_THREADS, 0, st>>>(map, sign, p[0], p[1], labels, H, W); NB_PROF_END("detect_scan_multi_kernel", st); }
+        { NB_PROF_BEGIN(st); detect_scan_multi_kernel<T, 1, false><<<gridDense, DT_THREADS, 0, st>>>(map, sign, p[0], p[1], labels, H, W); NB_PROF_END("detect_scan_multi_kernel", st); }
     }
     NB_CHECK_LAUNCH();
     dim3 gridSparse(64, B);
@@ -831,9 +833,6 @@ static int find_objects_t(const T* map, double thr, double ringThr, int haveRing
     }
     if (flags & 1) {
         { NB_PROF_BEGIN(st); detect_argmax_kernel<T><<<gridSparse, 256, 0, st>>>(map, sign, p[0].sc, table, HW, maxLabels); NB_PROF_END("detect_argmax_kernel", st); }
-        NB_CHECK_LAUNCH();
-        dim3 gridBg((HW + 256 * 8 - 1) / (256 * 8), B);
-        { NB_PROF_BEGIN(st); detect_bg_argmax_kernel<T><<<gridBg, 256, 0, st>>>(map, sign, thr, table, HW, maxLabels); NB_PROF_END("detect_bg_argmax_kernel", st); }
         NB_CHECK_LAUNCH();
     }
     for (int q = 0; q < NP; ++q) {

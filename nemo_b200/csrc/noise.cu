@@ -967,9 +967,23 @@ __global__ void __launch_bounds__(256) paint_rms_kernel(const T* __restrict__ wm
     const int nCells = ny * nx;
     double val = 0.0;
     bool found = false;
-    for (int i = ny - 1; i >= 0 && !found; --i) {
+    // only the chunk that holds the pixel and its two neighbours can cover it (the margins are half a chunk wide, but chunk
+    // sizes may differ by one pixel, so the test below stays exact); candidates are visited last-written first
+    int ci = min((int)(((long long)y * ny) / H), ny - 1);
+    while (ci > 0 && y < ch.y[ci]) --ci;
+    while (ci < ny - 1 && y >= ch.y[ci + 1]) ++ci;
+    int ck = min((int)(((long long)x * nx) / W), nx - 1);
+    while (ck > 0 && x < ch.x[ck]) --ck;
+    while (ck < nx - 1 && x >= ch.x[ck + 1]) ++ck;
+    // a margin wider than a neighbouring chunk would let a farther cell reach the pixel: widen the candidate range then
+    int iLo = ci, iHi = ci, kLo = ck, kHi = ck;
+    while (iLo > 0 && y < min(ch.y[iLo] + ov, H)) --iLo;
+    while (iHi < ny - 1 && y >= max(ch.y[iHi + 1] - ov, 0)) ++iHi;
+    while (kLo > 0 && x < min(ch.x[kLo] + ov, W)) --kLo;
+    while (kHi < nx - 1 && x >= max(ch.x[kHi + 1] - ov, 0)) ++kHi;
+    for (int i = iHi; i >= iLo && !found; --i) {
         if (y < max(ch.y[i] - ov, 0) || y >= min(ch.y[i + 1] + ov, H)) continue;
-        for (int k = nx - 1; k >= 0 && !found; --k) {
+        for (int k = kHi; k >= kLo && !found; --k) {
             if (x < max(ch.x[k] - ov, 0) || x >= min(ch.x[k + 1] + ov, W)) continue;
             const int cell = i * nx + k;
             const double* edg = edges + ((size_t)img * nCells + cell) * (numBins + 1);

@@ -198,48 +198,71 @@ def filterTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow
     return finishTileBatch(job, measureFluxes=measureFluxes, keepMaps=keepMaps)
 
 
-def processBatches(ops, batches, filtersList, templates, parDict, upload=True, undoPixelWindow=True, measureFluxes=True,
-                   invertMap=False, keepMaps=False):
-    """Runs several tile batches as a two-stage software pipeline over two CUDA streams: the device work of batch i + 1
-    (upload included) is queued before the host assembles the catalogs of batch i, so neither side waits for the other.
-    Returns the list of (catalogDict, extras), one per batch, in order."""
-    torch = ops.torch
-    if len(batches) < 2:
-        results = []
-        for b in batches:
-            if upload and b.dev is None:
-                b.upload()
-            results.append(filterTileBatch(ops, b, filtersList, templates, parDict, undoPixelWindow=undoPixelWindow,
-                                           measureFluxes=measureFluxes, invertMap=invertMap, keepMaps=keepMaps))
-            if upload:
-                b.dev = None
-        return results
-    streams = getattr(ops, '_pipeStreams', None)
-    if streams is None:
-        streams = ops._pipeStreams = [torch.cuda.Stream(device=ops.device), torch.cuda.Stream(device=ops.device)]
-    main = torch.cuda.current_stream(ops.device)
-    for st in streams:
-        st.wait_stream(main)       # templates and resident inputs were produced on the caller's stream
-    results = []
-    pending = None
-    for i, batch in enumerate(batches):
-        st = streams[i % 2]
+class BatchPipeline(object):
+    """Two-stage software pipeline over tile batches on two CUDA streams: ``submit(batch)`` queues the device work of that
+    batch (upload included when asked) and only then assembles the catalogs of the batch submitted before it, so the host
+    part of batch i runs while the GPU works on batch i + 1.  ``submit`` returns the (catalogDict, extras) of the previous
+    batch (None for the first one); ``flush()`` returns the last.  This is how a run over many tiles keeps both sides busy;
+    nothing is shared between batches except the read-only templates."""
+
+    def __init__(self, ops, filtersList, templates, parDict, undoPixelWindow=True, measureFluxes=True, invertMap=False,
+                 keepMaps=False):
+        self.ops, self.filtersList, self.templates, self.parDict = ops, filtersList, templates, parDict
+        self.undoPixelWindow, self.measureFluxes, self.invertMap, self.keepMaps = undoPixelWindow, measureFluxes, invertMap, keepMaps
+        torch = ops.torch
+        streams = getattr(ops, '_pipeStreams', None)
+        if streams is None:
+            streams = ops._pipeStreams = [torch.cuda.Stream(device=ops.device), torch.cuda.Stream(device=ops.device)]
+        self.streams = streams
+        self.main = torch.cuda.current_stream(ops.device)
+        for st in streams:
+            st.wait_stream(self.main)      # templates and resident inputs were produced on the caller's stream
+        self.pending = None
+        self.count = 0
+
+    def _finish(self):
+        torch = self.ops.torch
+        job, st, release = self.pending
+        self.pending = None
+        with torch.cuda.stream(st):
+            out = finishTileBatch(job, measureFluxes=self.measureFluxes, keepMaps=self.keepMaps)
+        if release:
+            job['batch'].dev = None
+        return out
+
+    def submit(self, batch, upload=True):
+        torch = self.ops.torch
+        st = self.streams[self.count % 2]
+        self.count += 1
         with torch.cuda.stream(st):
             if upload:
                 batch.upload()
-            job = startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=undoPixelWindow, invertMap=invertMap)
-        if pending is not None:
-            with torch.cuda.stream(pending[1]):
-                results.append(finishTileBatch(pending[0], measureFluxes=measureFluxes, keepMaps=keepMaps))
-            if upload:
-                pending[0]['batch'].dev = None
-        pending = (job, st)
-    with torch.cuda.stream(pending[1]):
-        results.append(finishTileBatch(pending[0], measureFluxes=measureFluxes, keepMaps=keepMaps))
-    if upload:
-        pending[0]['batch'].dev = None
-    for st in streams:
-        main.wait_stream(st)
+            job = startTileBatch(self.ops, batch, self.filtersList, self.templates, self.parDict,
+                                 undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap)
+        out = self._finish() if self.pending is not None else None
+        self.pending = (job, st, upload)
+        return out
+
+    def flush(self):
+        out = self._finish() if self.pending is not None else None
+        for st in self.streams:
+            self.main.wait_stream(st)
+        return out
+
+
+def processBatches(ops, batches, filtersList, templates, parDict, upload=True, undoPixelWindow=True, measureFluxes=True,
+                   invertMap=False, keepMaps=False):
+    """Runs several tile batches through a BatchPipeline; returns the list of (catalogDict, extras), one per batch, in order."""
+    pipe = BatchPipeline(ops, filtersList, templates, parDict, undoPixelWindow=undoPixelWindow, measureFluxes=measureFluxes,
+                         invertMap=invertMap, keepMaps=keepMaps)
+    results = []
+    for batch in batches:
+        out = pipe.submit(batch, upload=upload and batch.dev is None)
+        if out is not None:
+            results.append(out)
+    out = pipe.flush()
+    if out is not None:
+        results.append(out)
     return results
 
 
