@@ -60,10 +60,14 @@ static int get_twiddles(int prec, int N, const void** out) {
     return NB_OK;
 }
 
-// columns per CTA: keep one CTA's exchange buffer near 70 KB so 2-3 CTAs share an SM
+// columns per CTA: as many adjacent columns as fit a ~144 KB exchange buffer and 512 threads (one CTA per SM at 128
+// registers per thread), up to 16: a row of the tile is then C * sizeof(complex) contiguous bytes -- 128 B, a whole L2 line,
+// for fp64 at H = 1024 -- which is what the strided column walk needs to use DRAM bursts fully
 template <typename T, int N> struct ColCfg {
     static constexpr int BYTES_PER_COL = npad(N) * 2 * (int)sizeof(T);
-    static constexpr int CRAW = (72 * 1024) / BYTES_PER_COL;
+    static constexpr int CSMEM = (144 * 1024) / BYTES_PER_COL;
+    static constexpr int CTHR = 512 / (N / 16) > 0 ? 512 / (N / 16) : 1;
+    static constexpr int CRAW = CSMEM < CTHR ? CSMEM : CTHR;
     static constexpr int C = CRAW >= 16 ? 16 : CRAW >= 8 ? 8 : CRAW >= 4 ? 4 : CRAW >= 2 ? 2 : 1;
     static constexpr int NT = N / 16;
     static constexpr int THREADS = C * NT;
@@ -285,15 +289,8 @@ irfft_rows_kernel(const typename V2<T>::type* __restrict__ in, T* out, int H, lo
     const bool valid = row < nrows;
     T* s_re = smem + g * Cfg::LD;
     T* s_im = smem + (Cfg::RPB + g) * Cfg::LD;
-    if (valid) {
-        const C2* src = in + (size_t)row * Wc;
-        for (int k = t; k < Wc; k += NT) {
-            const C2 v = src[k];
-            s_re[spad(k)] = v.x;
-            s_im[spad(k)] = v.y;
-        }
-    }
-    __syncthreads();
+    // every thread reads its 16 spectrum samples X[k] and their mirrors X[M - k] straight from global memory (the mirrors
+    // are some other thread's samples of the same row, so they come from L1/L2): 32 independent loads in flight per thread
     T re[16], im[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -301,11 +298,19 @@ irfft_rows_kernel(const typename V2<T>::type* __restrict__ in, T* out, int H, lo
         im[q] = 0;
     }
     if (valid) {
+        const C2* src = in + (size_t)row * Wc;
+        C2 xs[16], cs[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int k = t + q * NT;
-            const T xr = s_re[spad(k)], xi = s_im[spad(k)];
-            const T cr = s_re[spad(M - k)], ci = -s_im[spad(M - k)];  // conj(X[M-k])
+            xs[q] = src[k];
+            cs[q] = src[M - k];
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int k = t + q * NT;
+            const T xr = xs[q].x, xi = xs[q].y;
+            const T cr = cs[q].x, ci = -cs[q].y;                      // conj(X[M-k])
             const C2 w = __ldg(twW + k);                               // conj -> exp(+2 pi i k / W)
             const T dr = xr - cr, di = xi - ci;
             const T a = w.x * dr + w.y * di, b = w.x * di - w.y * dr;  // conj(w) * d

@@ -82,6 +82,16 @@ class TileBatch(object):
                     fm = fm + np.asarray(m['flagMask']) * (i + 1)
             self.flagMasks.append(fm)
 
+    def refresh(self, tileMaps, keys=('data',)):
+        """Re-reads the given arrays of every tile into the pinned staging buffers (the maps changed, e.g. sources were
+        injected); masks and everything else stay as staged."""
+        import torch
+        self.mapDicts = [tileMaps[t] for t in self.tileNames]
+        for t, md in enumerate(self.mapDicts):
+            for f, m in enumerate(md):
+                for k in keys:
+                    self.host[k][t, f] = torch.from_numpy(np.ascontiguousarray(m[k]))
+
     def upload(self):
         """Host (pinned) -> device copies of this batch's inputs; asynchronous on the current stream."""
         ops = self.ops
@@ -134,10 +144,16 @@ def _sameNoiseSetup(filtersList):
     return len(set(key(f) for f in filtersList)) == 1
 
 
-def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=True, invertMap=False):
+def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=True, invertMap=False, cache=None,
+                   useCachedRMSMap=False):
     """Launches, without waiting for any of it, the device work of one batch: filtering of every tile at every scale of
     `filtersList` (Fourier matched filters with a common noise set-up), noise / S-N maps, and the thresholding,
-    labelling and moments of the detection step.  Returns the job to pass to finishTileBatch."""
+    labelling and moments of the detection step.  Returns the job to pass to finishTileBatch.
+
+    cache: {'filtH', 'signalNorm', 'RMSMap'} kept from an earlier run of the same batch (the job of that run): the filters
+    are then not rebuilt (the reference's useCachedFilters, filters.py:536, 691-696).  With useCachedRMSMap and a photFilter
+    the S/N map is made from the photFilter's cached RMS map and the pixel window is undone afterwards, as the reference's
+    source-injection path does (pipelines.py:216-232)."""
     if not _sameNoiseSetup(filtersList):
         raise Exception("filters of one batch need identical noiseParams / edgeTrimArcmin / bckSub settings")
     dev = batch.dev if batch.dev is not None else batch.upload()
@@ -156,16 +172,32 @@ def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=
     # K1: apodised input FFTs, shared by the S scales of a tile (filters.py:526-529) and by the noise estimate (:551)
     fmaps = ops.rfft2(dev['data'].reshape(nT * F, H, W), apodPix=20).reshape(nT, F, H, Wc)
     # K2, K3, K5: filters and their normalisation
-    res = engine.buildFourierFilters(ops, fmaps, templates.unit, templates.norm, templates.w, templates.outputUnits,
-                                     templates.cy, templates.cx, bckSubSigmas=bck)
+    if cache is None:
+        res = engine.buildFourierFilters(ops, fmaps, templates.unit, templates.norm, templates.w, templates.outputUnits,
+                                         templates.cy, templates.cx, bckSubSigmas=bck)
+    else:
+        res = {'filtH': cache['filtH'], 'signalNorm': cache['signalNorm'], 'fRel': cache.get('fRel')}
     # K4: apply, times the point-source mask
     filtered = engine.applyFourierFilters(ops, fmaps, res['filtH'], S, res['signalNorm'], dev['psMask'], bckSubSigmas=bck)
     del fmaps
-    # K6, K7
-    grid = engine.noiseGrid((H, W), params0['noiseParams'], pixDeg)
     trimPix = engine.trimSizePix(params0, pixDeg, realSpace=False)
-    data, sn, maskOut, rms, table, edges = engine.noiseSNAndMasks(ops, filtered, dev['wmed'], dev['psMask'], dev['surveyMask'],
-                                                                  S, grid, trimPix, 20, False)
+    photScale = None
+    if parDict.get('photFilter') is not None:
+        for i, f in enumerate(filtersList):
+            if f['label'] == parDict['photFilter']:
+                photScale = i
+    if cache is not None and useCachedRMSMap and photScale is not None:
+        # K7 with the cached noise: masks and `data` as usual, S/N = data / RMS(photFilter) where RMS > 0, else data
+        rmsPhot = cache['RMSMap'].reshape(nT, S, H, W)[:, photScale].contiguous()
+        rms = rmsPhot.repeat_interleave(S, dim=0) if S > 1 else rmsPhot.clone()
+        data, _, maskOut, rms = ops.snr_mask(filtered, rms, dev['psMask'], dev['surveyMask'], S, trimPix, 20, False)
+        sn = ops.snr_from_rms(data, rmsPhot, S)
+        table = edges = None
+    else:
+        # K6, K7
+        grid = engine.noiseGrid((H, W), params0['noiseParams'], pixDeg)
+        data, sn, maskOut, rms, table, edges = engine.noiseSNAndMasks(ops, filtered, dev['wmed'], dev['psMask'], dev['surveyMask'],
+                                                                      S, grid, trimPix, 20, False)
     # K8
     if undoPixelWindow:
         engine.undoPixelWindow(ops, data)
@@ -206,9 +238,10 @@ class BatchPipeline(object):
     nothing is shared between batches except the read-only templates."""
 
     def __init__(self, ops, filtersList, templates, parDict, undoPixelWindow=True, measureFluxes=True, invertMap=False,
-                 keepMaps=False):
+                 keepMaps=False, useCachedRMSMap=False):
         self.ops, self.filtersList, self.templates, self.parDict = ops, filtersList, templates, parDict
         self.undoPixelWindow, self.measureFluxes, self.invertMap, self.keepMaps = undoPixelWindow, measureFluxes, invertMap, keepMaps
+        self.useCachedRMSMap = useCachedRMSMap
         torch = ops.torch
         streams = getattr(ops, '_pipeStreams', None)
         if streams is None:
@@ -230,7 +263,7 @@ class BatchPipeline(object):
             job['batch'].dev = None
         return out
 
-    def submit(self, batch, upload=True):
+    def submit(self, batch, upload=True, cache=None):
         torch = self.ops.torch
         st = self.streams[self.count % 2]
         self.count += 1
@@ -238,7 +271,8 @@ class BatchPipeline(object):
             if upload:
                 batch.upload()
             job = startTileBatch(self.ops, batch, self.filtersList, self.templates, self.parDict,
-                                 undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap)
+                                 undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap, cache=cache,
+                                 useCachedRMSMap=self.useCachedRMSMap)
         out = self._finish() if self.pending is not None else None
         self.pending = (job, st, upload)
         return out
@@ -251,13 +285,14 @@ class BatchPipeline(object):
 
 
 def processBatches(ops, batches, filtersList, templates, parDict, upload=True, undoPixelWindow=True, measureFluxes=True,
-                   invertMap=False, keepMaps=False):
-    """Runs several tile batches through a BatchPipeline; returns the list of (catalogDict, extras), one per batch, in order."""
+                   invertMap=False, keepMaps=False, caches=None, useCachedRMSMap=False):
+    """Runs several tile batches through a BatchPipeline; returns the list of (catalogDict, extras), one per batch, in order.
+    caches: per-batch filter / RMS caches (see startTileBatch), or None."""
     pipe = BatchPipeline(ops, filtersList, templates, parDict, undoPixelWindow=undoPixelWindow, measureFluxes=measureFluxes,
-                         invertMap=invertMap, keepMaps=keepMaps)
+                         invertMap=invertMap, keepMaps=keepMaps, useCachedRMSMap=useCachedRMSMap)
     results = []
-    for batch in batches:
-        out = pipe.submit(batch, upload=upload and batch.dev is None)
+    for i, batch in enumerate(batches):
+        out = pipe.submit(batch, upload=upload and batch.dev is None, cache=caches[i] if caches is not None else None)
         if out is not None:
             results.append(out)
     out = pipe.flush()
@@ -376,16 +411,20 @@ def stageTiles(config, tilesPerBatch=8, precision=None):
 
 
 def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=False, measureFluxes=True, invertMap=False,
-                              verbose=True, tilesPerBatch=8, precision=None, comm=None):
+                              verbose=True, tilesPerBatch=8, precision=None, comm=None, cacheFilters=False, restage=False):
     """Runs the map filtering and catalog construction steps for this rank's tiles and returns the optimal catalog
     (highest S/N detection across filter scales), gathered over ranks when `comm` (a
     ``nemo_b200.distributed.Comm``) is given -- pipelines.py:33-109, 112-354.
 
+    cacheFilters=True keeps every batch's filters, normalisations and RMS maps on the device (``config._cache``); a later
+    call with useCachedFilters=True (and useCachedRMSMap=True) then only applies them to whatever the map dictionaries hold
+    now -- the reference's source-injection loop (maps.py:2093), where the caches are FITS files on disk.  restage=True
+    re-reads the 'data' arrays of the map dictionaries into the pinned staging buffers first (they were edited in place or
+    replaced since the tiles were staged).
+
     Only Fourier-space matched filters with a common noise set-up are batched here; use ``filters.filterMaps`` +
     ``photometry.findObjects`` directly for anything else.
     """
-    if useCachedFilters or useCachedRMSMap:
-        raise Exception("cached filters / RMS maps are not handled by the batched driver: use filters.filterMaps(useCachedFilter=True)")
     ops = device.getOps(precision)
     parDict = config.parDict
     filtersList = _orderedFilters(parDict)
@@ -396,6 +435,9 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
         batches = stageTiles(config, tilesPerBatch, precision)
     else:
         batches = staged['batches']
+        if restage:
+            for b in batches:
+                b.refresh(config.tileMaps)
     templates = getattr(config, '_templates', None)
     if templates is None:
         templates = FilterSetTemplates(ops, filtersList, batches[0].mapDicts[0], tileName=batches[0].tileNames[0])
@@ -403,11 +445,24 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     if verbose:
         for batch in batches:
             print(">>> [rank = %d] Making filtered maps - tiles %s" % (config.rank, batch.tileNames))
+    caches = None
+    if useCachedFilters:
+        caches = getattr(config, '_cache', None)
+        if caches is None or len(caches) != len(batches):
+            raise Exception("no cached filters for these tile batches: run filterMapsAndMakeCatalogs(config, cacheFilters=True) first")
+    # with a cached RMS map the pixel window is undone after the S/N map has been made (pipelines.py:171-173, 216-232); the
+    # batched path always makes the S/N map before undoing the window, so the same flag serves both cases
     results = processBatches(ops, batches, filtersList, templates, parDict, upload=True,
-                             undoPixelWindow=parDict.get('undoPixelWindow', True), measureFluxes=measureFluxes, invertMap=invertMap)
+                             undoPixelWindow=parDict.get('undoPixelWindow', True), measureFluxes=measureFluxes, invertMap=invertMap,
+                             keepMaps=cacheFilters, caches=caches, useCachedRMSMap=useCachedRMSMap)
+    if cacheFilters:
+        config._cache = [{'filtH': ex['filtH'], 'signalNorm': ex['signalNorm'], 'RMSMap': ex['RMSMap'], 'fRel': ex['fRel']}
+                         for _, ex in results]
     for batch, (cd, extras) in zip(batches, results):
         names = batch.tileNames
         catalogDict.update(cd)
+        if extras['noiseTable'] is None:
+            continue
         tab = device.toHost(extras['noiseTable'])
         for o in range(tab.shape[0]):
             noiseTables[filtersList[o % len(filtersList)]['label'] + "#" + names[o // len(filtersList)]] = tab[o]

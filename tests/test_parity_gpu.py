@@ -257,3 +257,62 @@ def test_find_objects_ring_removal_and_options(report, findCenterOfMass):
             plain = photometry_ref.findObjects(fmd, **dict(opts, removeRings=False))
             assert len(plain) == len(ref) + 2, "the two detections on the rings should be the only ones removed"
     report("find_objects_rings", com=int(findCenterOfMass), objects=len(ref))
+
+
+def test_injection_path_cached_filters_and_rms(tmp_path, report):
+    """BASELINE config 5 (reduced): sources are injected into the maps and the tiles re-filtered with the cached filters
+    and the photFilter's cached RMS map (reference maps.py:2093 -> pipelines.py:216-232), against the oracle doing the
+    reference's sequence with its own cached filter files."""
+    from nemo_b200 import pipelines
+    from oracle import pixell_shim as enmap
+    d = str(tmp_path)
+    tileMaps = {}
+    for t in range(2):
+        md, _ = synth.makeTile(shape=(256, 256), numObjects=4, kind='clusters', seed=300 + t)
+        tileMaps['tile%d' % t] = md
+    filtersList = [_arnaud('Arnaud_M2e14_z0p4', 2e14, 0.4, saveFilter=True), _arnaud('Arnaud_M6e14_z0p3', 6e14, 0.3, saveFilter=True)]
+    parDict = {'mapFilters': filtersList, 'photFilter': 'Arnaud_M2e14_z0p4', 'thresholdSigma': 4.0, 'minObjPix': 1,
+               'findCenterOfMass': True, 'useInterpolator': True, 'rejectBorder': 0}
+    config = pipelines.SimpleConfig(parDict, tileMaps)
+    pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=2, cacheFilters=True)
+    # oracle, first pass: filters and RMS maps of the real maps
+    ordered = pipelines._orderedFilters(config.parDict)
+    refRMS = {}
+    for tileName, md in tileMaps.items():
+        for f in ordered:
+            _, obj = filters_ref.filterMaps(md, _copyFilter(f), tileName, diagnosticsDir=d, selFnDir=d, returnFilter=True)
+            if f['label'] == parDict['photFilter']:
+                refRMS[tileName] = obj.RMSMap
+    # inject: a few beam-convolved decrements per tile, directly into the map arrays
+    rng = np.random.default_rng(4)
+    yy, xx = np.mgrid[:256, :256]
+    for tileName, md in tileMaps.items():
+        for _ in range(3):
+            cy, cx = rng.uniform(60, 196, 2)
+            md[0]['data'] = md[0]['data'] - 450.0 * np.exp(-0.5 * ((yy - cy) ** 2 + (xx - cx) ** 2) / 2.5 ** 2)
+    opt = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=2, useCachedFilters=True, useCachedRMSMap=True,
+                                              restage=True)
+    nObj = 0
+    for tileName, md in tileMaps.items():
+        phot = None
+        for f in ordered:
+            ref = filters_ref.filterMaps(md, _copyFilter(f), tileName, diagnosticsDir=d, selFnDir=d, useCachedFilter=True,
+                                         undoPixelWindow=False)
+            RMSMap = refRMS[tileName]
+            validMask = np.greater(RMSMap, 0)
+            SNMap = np.zeros(ref['data'].shape) + ref['data']
+            SNMap[validMask] = SNMap[validMask] / RMSMap[validMask]
+            ref['SNMap'] = SNMap
+            mask = np.equal(ref['data'], 0)
+            ref['data'] = enmap.apply_window(ref['data'], pow=-1.0)
+            ref['data'][mask] = 0
+            if f['label'] == parDict['photFilter']:
+                phot = {'SNMap': ref['SNMap'], 'data': ref['data']}
+            refCat = photometry_ref.findObjects(ref, threshold=4.0, minObjPix=1, findCenterOfMass=True, removeRings=True,
+                                                ringThresholdSigma=3, rejectBorder=0, useInterpolator=True)
+            photometry_ref.measureFluxes(refCat, ref, None, photFilteredMapDict=phot)
+            gotTab = config.catalogDict[f['label'] + "#" + tileName]['catalog']
+            _compareCatalogs(gotTab, refCat, ['SNR', 'y_c', 'err_y_c', 'fixed_SNR', 'fixed_y_c', 'deltaT_c'])
+            nObj += len(refCat)
+    assert nObj >= 8 and len(opt) >= 6
+    report("injection_cached", objects=nObj, optimal=len(opt))
