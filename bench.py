@@ -113,7 +113,9 @@ def algorithmicBytes(nT, F, S, H, W, E, rings=True):
     b['fft_cols_apply_kernel'] = 2 * nOut * (F * Nc * 2 * E + F * Nc * E + Nc * 2 * E)     # templates + maps
     b['irfft_rows_kernel'] = nOut * (Nc * 2 * E + N * E) + nOut * (Nc * 2 * E + N * E + N) + nOut * (Nc * 2 * E + 2 * N * E)
     b['template_argmax_partial_kernel'] = nOut * N * E
-    b['cell_rms_kernel'] = nOut * 2 * N * E
+    b['cell_rms_onchip_kernel'] = nOut * 2 * N * E
+    b['cell_rms_hybrid_kernel'] = nOut * 2 * N * E
+    b['cell_rms_stream_kernel'] = nOut * 2 * N * E
     b['paint_rms_kernel'] = nOut * 2 * N * E
     b['edge_rows_kernel'] = nOut * (N * E + 2 * N)
     b['edge_cols_final_kernel'] = nOut * (2 * N * E + 3 * N + 3 * N * E + N)

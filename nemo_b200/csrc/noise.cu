@@ -6,6 +6,7 @@
 #include "nemo_b200_internal.h"
 #include <math.h>
 #include <algorithm>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
@@ -349,45 +350,56 @@ struct OcBinState {   // per weight bin, shared memory
     int pad;
 };
 
-// shared-memory carve-up shared by host (size) and device (pointers)
+#define OC_SPT 32          // most shared-memory slots per lane the all-shared variant keeps track of in registers
+
+// shared-memory carve-up shared by host (size) and device (pointers).  Hybrid variant: the slots region holds the keys, then
+// the values, of the pixels that do not fit the register slots.  All-shared variant (allShared): the slots region is sized for
+// every pixel of the cell (valueSlots); while the weights are being ranked its first smemSlots entries hold keys and the
+// selection scratch sits behind them, afterwards the whole region holds the values sorted by (warp, bin).
 template <typename KT> struct OcLayout {
     size_t red, edges, state, warpBins, trank, tval, tuniq, usize, uoff, ucount, umin, umax, ubucket, hist, mark, cand, slots, wstart, wrun, bins, total;
-    __host__ __device__ OcLayout(int numBins, int smemSlots) {
+    __host__ __device__ OcLayout(int numBins, int smemSlots, int valueSlots) {
+        const bool allShared = valueSlots > 0;
         size_t o = 0;
         red = o;      o += sizeof(double) * 2 * OC_WARPS * numBins * 3;
         edges = o;    o += sizeof(double) * (numBins + 1);
         state = o;    o += sizeof(OcBinState) * OC_WARPS * numBins;
         warpBins = o; o += sizeof(unsigned long long) * OC_WARPS;
+        wstart = o;   o += sizeof(int) * OC_WARPS * (numBins + 1);
+        wrun = o;     o += sizeof(int) * OC_WARPS * (numBins + 1);
+        o = (o + 15) & ~(size_t)15;
+        slots = o;
+        const size_t slotsEnd = o + sizeof(KT) * (size_t)(allShared ? valueSlots : smemSlots);
+        o += sizeof(KT) * (size_t)smemSlots;           // the scratch follows the keys
+        o = (o + 15) & ~(size_t)15;
         trank = o;    o += sizeof(long long) * OC_MAXTARGETS;
         tval = o;     o += sizeof(unsigned long long) * OC_MAXTARGETS;
         umin = o;     o += sizeof(unsigned long long) * OC_MAXTARGETS;
         umax = o;     o += sizeof(unsigned long long) * OC_MAXTARGETS;
         cand = o;     o += sizeof(KT) * OC_CANDCAP;
-        slots = o;    o += sizeof(KT) * (size_t)smemSlots;
         tuniq = o;    o += sizeof(int) * OC_MAXTARGETS;
         usize = o;    o += sizeof(int) * OC_MAXTARGETS;
         uoff = o;     o += sizeof(int) * OC_MAXTARGETS;
         ucount = o;   o += sizeof(int) * OC_MAXTARGETS;
         ubucket = o;  o += sizeof(int) * OC_MAXTARGETS;
         hist = o;     o += sizeof(int) * (OC_L1BUCKETS > OC_GROUPS * 256 ? OC_L1BUCKETS : OC_GROUPS * 256);
-        wstart = o;   o += sizeof(int) * OC_WARPS * (numBins + 1);
-        wrun = o;     o += sizeof(int) * OC_WARPS * (numBins + 1);
         mark = o;     o += sizeof(short) * OC_L1BUCKETS;
-        bins = o;     o += (size_t)smemSlots;
+        bins = o;     o += allShared ? 0 : (size_t)smemSlots;
+        if (o < slotsEnd) o = slotsEnd;
         total = (o + 15) & ~(size_t)15;
     }
 };
 
-template <typename T>
+template <typename T, bool AS>
 __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T* __restrict__ map, const T* __restrict__ wmed, int S,
                                                                         int H, int W, const Chunks ch, int nx, int ov, int numBins,
                                                                         double* __restrict__ table, double* __restrict__ edges,
-                                                                        int smemSlots) {
+                                                                        int smemSlots, int valueSlots) {
     typedef KeyOf<T> K;
     typedef typename K::type key_t;
     constexpr key_t SENT = ~(key_t)0;
     extern __shared__ __align__(16) unsigned char oc_smem[];
-    const OcLayout<key_t> lay(numBins, smemSlots);
+    const OcLayout<key_t> lay(numBins, smemSlots, AS ? valueSlots : 0);
     double* s_red = reinterpret_cast<double*>(oc_smem + lay.red);
     double* s_edges = reinterpret_cast<double*>(oc_smem + lay.edges);
     OcBinState* s_state = reinterpret_cast<OcBinState*>(oc_smem + lay.state);
@@ -426,7 +438,7 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     const int spw = smemSlots / OC_WARPS;                    // shared-memory slots per warp
     const int ty0 = (wid / OC_TGX) * tr, tx0 = (wid % OC_TGX) * tc;
     const float rcpTc = 1.0f / (float)tc;
-    key_t* wSlots = s_slots + (size_t)wid * spw;             // this warp's run
+    key_t* wSlots = s_slots + (size_t)wid * spw;             // this warp's run (keys; values too in the hybrid variant)
     unsigned char* wBins = s_bins + (size_t)wid * spw;
     double* tab = table + ((size_t)img * gridDim.x + cell) * numBins;
     double* edg = edges + ((size_t)img * gridDim.x + cell) * (numBins + 1);
@@ -776,72 +788,147 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
         wRun[b] = 0;
     }
     __syncwarp();
-    // register slots: bins packed four per word, values loaded in place of the keys
     unsigned long long present = 0ULL;
     unsigned int rbin[(OC_PPT + 3) / 4];
 #pragma unroll
     for (int j4 = 0; j4 < (OC_PPT + 3) / 4; ++j4) rbin[j4] = 0xffffffffu;
-    resetCursor();
-#pragma unroll
-    for (int j0 = 0; j0 < OC_PPT; j0 += OC_LB) {
-        T mv[OC_LB];
-#pragma unroll
-        for (int u = 0; u < OC_LB; ++u) {
-            const long long off = nextOffset();
-            mv[u] = (off >= 0) ? m[off] : (T)0;
-        }
-#pragma unroll
-        for (int u = 0; u < OC_LB; ++u) {
-            const int j = j0 + u;
-            const unsigned int bin = binOf(reg[j]);
-            rbin[j >> 2] = (rbin[j >> 2] & ~(255u << (8 * (j & 3)))) | (bin << (8 * (j & 3)));
-            if (bin != 255u) present |= 1ULL << bin;
-            reg[j] = K::fromValue(bin != 255u ? mv[u] : (T)0);
-        }
-    }
-    // shared-memory slots: count per bin, then rewrite the run sorted by bin so that a sweep of bin b reads only its own
-    for (int j = OC_PPT; j < JT; ++j) {
-        const unsigned int bin = binOf(wSlots[(j - OC_PPT) * 32 + lane]);
-        wBins[(j - OC_PPT) * 32 + lane] = (unsigned char)bin;
+    // per-warp, per-bin counting and placement: one slot of every lane at a time; lanes that share a bin take consecutive places
+    auto countBin = [&](unsigned int bin) {
         const unsigned peers = __match_any_sync(0xffffffffu, bin);
         if (bin != 255u && lane == (__ffs(peers) - 1)) wStart[bin + 1] += __popc(peers);
         __syncwarp();
-    }
-    if (lane == 0) {
-        int run = 0;
-        for (int b = 0; b < numBins; ++b) {
-            const int c = wStart[b + 1];
-            wStart[b] = run;
-            wRun[b] = run;
-            run += c;
+    };
+    auto placeOf = [&](unsigned int bin) -> int {
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (bin != 255u && lane == leader) {
+            base = wRun[bin];
+            wRun[bin] = base + __popc(peers);
         }
-        wStart[numBins] = run;
-    }
-    __syncwarp();
-    for (int j0 = OC_PPT; j0 < JT; j0 += OC_LB) {
-        T mv[OC_LB];
-#pragma unroll
-        for (int u = 0; u < OC_LB; ++u) {
-            const long long off = nextOffset();
-            mv[u] = (off >= 0) ? m[off] : (T)0;
-        }
-#pragma unroll
-        for (int u = 0; u < OC_LB; ++u) {
-            if (j0 + u >= JT) break;   // uniform over the warp
-            const unsigned int bin = wBins[(j0 + u - OC_PPT) * 32 + lane];
-            const unsigned peers = __match_any_sync(0xffffffffu, bin);
-            const int leader = __ffs(peers) - 1;
-            int base = 0;
-            if (bin != 255u && lane == leader) {
-                base = wRun[bin];
-                wRun[bin] = base + __popc(peers);
+        base = __shfl_sync(0xffffffffu, base, leader);
+        __syncwarp();
+        return base + __popc(peers & ((1u << lane) - 1u));
+    };
+    auto prefixBins = [&]() {
+        if (lane == 0) {
+            int run = 0;
+            for (int b = 0; b < numBins; ++b) {
+                const int c = wStart[b + 1];
+                wStart[b] = run;
+                wRun[b] = run;
+                run += c;
             }
-            base = __shfl_sync(0xffffffffu, base, leader);
-            __syncwarp();
-            if (bin != 255u) wSlots[base + __popc(peers & ((1u << lane) - 1u))] = K::fromValue(mv[u]);
+            wStart[numBins] = run;
         }
+        __syncwarp();
+    };
+    if constexpr (AS) {
+        // all-shared variant: bins of every slot into registers, counts, then (the keys and the selection scratch being dead
+        // for the whole block) every value goes to its place in the warp's run of the slots region, sorted by bin
+        unsigned int sbin[OC_SPT / 4];
+#pragma unroll
+        for (int j4 = 0; j4 < OC_SPT / 4; ++j4) sbin[j4] = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < OC_PPT; ++j) {
+            const unsigned int bin = binOf(reg[j]);
+            rbin[j >> 2] = (rbin[j >> 2] & ~(255u << (8 * (j & 3)))) | (bin << (8 * (j & 3)));
+            countBin(bin);
+        }
+#pragma unroll
+        for (int jj = 0; jj < OC_SPT; ++jj) {
+            if (OC_PPT + jj < JT) {   // uniform over the warp
+                const unsigned int bin = binOf(wSlots[jj * 32 + lane]);
+                sbin[jj >> 2] = (sbin[jj >> 2] & ~(255u << (8 * (jj & 3)))) | (bin << (8 * (jj & 3)));
+                countBin(bin);
+            }
+        }
+        prefixBins();
+        __syncthreads();
+        key_t* vRun = s_slots + (size_t)wid * (valueSlots / OC_WARPS);
+        resetCursor();
+#pragma unroll
+        for (int j0 = 0; j0 < OC_PPT; j0 += OC_LB) {
+            T mv[OC_LB];
+#pragma unroll
+            for (int u = 0; u < OC_LB; ++u) {
+                const long long off = nextOffset();
+                mv[u] = (off >= 0) ? m[off] : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < OC_LB; ++u) {
+                const int j = j0 + u;
+                const unsigned int bin = (rbin[j >> 2] >> (8 * (j & 3))) & 255u;
+                const int pos = placeOf(bin);
+                if (bin != 255u) vRun[pos] = K::fromValue(mv[u]);
+            }
+        }
+#pragma unroll
+        for (int j0 = 0; j0 < OC_SPT; j0 += OC_LB) {
+            if (OC_PPT + j0 < JT) {
+                T mv[OC_LB];
+#pragma unroll
+                for (int u = 0; u < OC_LB; ++u) {
+                    const long long off = nextOffset();
+                    mv[u] = (off >= 0) ? m[off] : (T)0;
+                }
+#pragma unroll
+                for (int u = 0; u < OC_LB; ++u) {
+                    const int jj = j0 + u;
+                    if (jj < OC_SPT && OC_PPT + jj < JT) {
+                        const unsigned int bin = (sbin[jj >> 2] >> (8 * (jj & 3))) & 255u;
+                        const int pos = placeOf(bin);
+                        if (bin != 255u) vRun[pos] = K::fromValue(mv[u]);
+                    }
+                }
+            }
+        }
+        wSlots = vRun;     // the sweeps below read the sorted run
+        __syncwarp();
+    } else {
+        // hybrid variant.  Register slots: bins packed four per word, values loaded in place of the keys
+        resetCursor();
+#pragma unroll
+        for (int j0 = 0; j0 < OC_PPT; j0 += OC_LB) {
+            T mv[OC_LB];
+#pragma unroll
+            for (int u = 0; u < OC_LB; ++u) {
+                const long long off = nextOffset();
+                mv[u] = (off >= 0) ? m[off] : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < OC_LB; ++u) {
+                const int j = j0 + u;
+                const unsigned int bin = binOf(reg[j]);
+                rbin[j >> 2] = (rbin[j >> 2] & ~(255u << (8 * (j & 3)))) | (bin << (8 * (j & 3)));
+                if (bin != 255u) present |= 1ULL << bin;
+                reg[j] = K::fromValue(bin != 255u ? mv[u] : (T)0);
+            }
+        }
+        // shared-memory slots: count per bin, then rewrite the run sorted by bin so that a sweep of bin b reads only its own
+        for (int j = OC_PPT; j < JT; ++j) {
+            const unsigned int bin = binOf(wSlots[(j - OC_PPT) * 32 + lane]);
+            wBins[(j - OC_PPT) * 32 + lane] = (unsigned char)bin;
+            countBin(bin);
+        }
+        prefixBins();
+        for (int j0 = OC_PPT; j0 < JT; j0 += OC_LB) {
+            T mv[OC_LB];
+#pragma unroll
+            for (int u = 0; u < OC_LB; ++u) {
+                const long long off = nextOffset();
+                mv[u] = (off >= 0) ? m[off] : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < OC_LB; ++u) {
+                if (j0 + u >= JT) break;   // uniform over the warp
+                const unsigned int bin = wBins[(j0 + u - OC_PPT) * 32 + lane];
+                const int pos = placeOf(bin);
+                if (bin != 255u) wSlots[pos] = K::fromValue(mv[u]);
+            }
+        }
+        __syncwarp();
     }
-    __syncwarp();
     for (int b = lane; b < numBins; b += 32)
         if (wStart[b + 1] > wStart[b]) present |= 1ULL << b;
     {
@@ -875,24 +962,41 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
             if (wState[b].done) continue;
             const double thr = wState[b].thr, piv = wState[b].pivot;
             double c0 = 0, s0 = 0, q0 = 0, c1 = 0, s1 = 0, q1 = 0;
+            if constexpr (!AS) {
 #pragma unroll
-            for (int j = 0; j < OC_PPT; ++j) {
-                const unsigned int bj = (rbin[j >> 2] >> (8 * (j & 3))) & 255u;
-                const double v = K::toValue(reg[j]);
-                if (bj == (unsigned int)b && fabs(v) < thr) {
-                    const double d = v - piv;
-                    if (j & 1) {
-                        c1 += 1.0; s1 += v; q1 += d * d;
-                    } else {
-                        c0 += 1.0; s0 += v; q0 += d * d;
+                for (int j = 0; j < OC_PPT; ++j) {
+                    const unsigned int bj = (rbin[j >> 2] >> (8 * (j & 3))) & 255u;
+                    const double v = K::toValue(reg[j]);
+                    if (bj == (unsigned int)b && fabs(v) < thr) {
+                        const double d = v - piv;
+                        if (j & 1) {
+                            c1 += 1.0; s1 += v; q1 += d * d;
+                        } else {
+                            c0 += 1.0; s0 += v; q0 += d * d;
+                        }
                     }
                 }
             }
-            for (int i = wStart[b] + lane; i < wStart[b + 1]; i += 32) {
-                const double v = K::toValue(wSlots[i]);
-                if (fabs(v) < thr) {
-                    const double d = v - piv;
-                    c0 += 1.0; s0 += v; q0 += d * d;
+            {
+                const int iEnd = wStart[b + 1];
+                int i = wStart[b] + lane;
+                for (; i + 32 < iEnd; i += 64) {   // two independent chains
+                    const double v = K::toValue(wSlots[i]), v2 = K::toValue(wSlots[i + 32]);
+                    if (fabs(v) < thr) {
+                        const double d = v - piv;
+                        c0 += 1.0; s0 += v; q0 += d * d;
+                    }
+                    if (fabs(v2) < thr) {
+                        const double d = v2 - piv;
+                        c1 += 1.0; s1 += v2; q1 += d * d;
+                    }
+                }
+                if (i < iEnd) {
+                    const double v = K::toValue(wSlots[i]);
+                    if (fabs(v) < thr) {
+                        const double d = v - piv;
+                        c0 += 1.0; s0 += v; q0 += d * d;
+                    }
                 }
             }
             c0 = warp_sum(c0 + c1);
@@ -1122,11 +1226,20 @@ static int cell_rms_t(const void* map, const void* wmed, int nImg, int S, int H,
     const long long perWarp = CH > (long long)OC_PPT * 32 ? CH - (long long)OC_PPT * 32 : 0;
     const long long smemSlots = perWarp * OC_WARPS;
     const bool fits = maxCell < (1LL << 22) && numBins <= OC_MAXBINS;
-    const size_t ocBytes = fits ? OcLayout<typename KeyOf<T>::type>(numBins, (int)smemSlots).total : (size_t)1 << 30;
-    if (ocBytes <= 226 * 1024) {
-        NB_CHECK_CUDA(cudaFuncSetAttribute(cell_rms_onchip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ocBytes));
-        { NB_PROF_BEGIN(st); cell_rms_onchip_kernel<T><<<dim3(ny * nx, nImg), OC_THREADS, ocBytes, st>>>(
-            (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges, (int)smemSlots); NB_PROF_END("cell_rms_onchip_kernel", st); }
+    typedef typename KeyOf<T>::type KT;
+    // preferred: every value in shared memory, sorted by (warp, bin); else registers + shared memory; else streaming
+    const long long valueSlots = CH * OC_WARPS;
+    const size_t asBytes = (fits && perWarp / 32 <= OC_SPT) ? OcLayout<KT>(numBins, (int)smemSlots, (int)valueSlots).total : (size_t)1 << 30;
+    const size_t ocBytes = fits ? OcLayout<KT>(numBins, (int)smemSlots, 0).total : (size_t)1 << 30;
+    if (getenv("NB_DEBUG")) fprintf(stderr, "nb_cell_rms: maxCell %lld CH %lld perWarp %lld asBytes %zu ocBytes %zu fits %d\n", maxCell, CH, perWarp, asBytes, ocBytes, (int)fits);
+    if (asBytes <= 227 * 1024) {
+        NB_CHECK_CUDA(cudaFuncSetAttribute(cell_rms_onchip_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asBytes));
+        { NB_PROF_BEGIN(st); cell_rms_onchip_kernel<T, true><<<dim3(ny * nx, nImg), OC_THREADS, asBytes, st>>>(
+            (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges, (int)smemSlots, (int)valueSlots); NB_PROF_END("cell_rms_onchip_kernel", st); }
+    } else if (ocBytes <= 227 * 1024) {
+        NB_CHECK_CUDA(cudaFuncSetAttribute(cell_rms_onchip_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ocBytes));
+        { NB_PROF_BEGIN(st); cell_rms_onchip_kernel<T, false><<<dim3(ny * nx, nImg), OC_THREADS, ocBytes, st>>>(
+            (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges, (int)smemSlots, 0); NB_PROF_END("cell_rms_hybrid_kernel", st); }
     } else {
         { NB_PROF_BEGIN(st); cell_rms_stream_kernel<T><<<dim3(ny * nx, nImg), CR_THREADS, sizeof(double) * (numBins + 1), st>>>(
             (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges); NB_PROF_END("cell_rms_stream_kernel", st); }

@@ -316,3 +316,31 @@ def test_injection_path_cached_filters_and_rms(tmp_path, report):
             nObj += len(refCat)
     assert nObj >= 8 and len(opt) >= 6
     report("injection_cached", objects=nObj, optimal=len(opt))
+
+
+def test_fp32_storage_mode_against_fp64_oracle(report):
+    """precision='f32' (fp32 maps / spectra / FFT arithmetic; covariance, solve, reductions and splines in fp64) on maps that
+    are exactly representable in fp32, against the fp64 oracle on the same values: the north-star tolerances (S/N maps 1e-4,
+    positions 0.01 px) must still hold, and this test records by how much."""
+    from nemo_b200 import filters, photometry
+    mapDicts, truth = synth.makeTile(shape=(512, 512), freqsGHz=(97.8, 149.6), noiseUK=(60.0, 40.0), beamFWHMArcmin=(2.2, 1.4),
+                                     numObjects=12, kind='clusters', cmb=True, seed=11)
+    for m in mapDicts:
+        m['data'] = m['data'].astype(np.float32).astype(np.float64)
+        m['weights'] = m['weights'].astype(np.float32).astype(np.float64)
+    f = _arnaud('Arnaud_M2e14_z0p4', 2e14, 0.4, grid=40.)
+    ref = filters_ref.filterMaps(mapDicts, _copyFilter(f), 'T0')
+    f32 = _copyFilter(f)
+    f32['params']['precision'] = 'f32'
+    got = filters.filterMaps(mapDicts, f32, 'T0', verbose=False)
+    sn, snRef = np.asarray(got['SNMap'], dtype=np.float64), ref['SNMap']
+    assert np.array_equal(np.asarray(got['surveyMask']) != 0, ref['surveyMask'] != 0)
+    errSN = float(np.abs(sn - snRef).max())
+    relData = float(np.abs(np.asarray(got['data'], dtype=np.float64) - ref['data']).max() / np.abs(ref['data']).max())
+    report("fp32_mode", maxabs_dSN=errSN, rel_dData=relData)
+    assert np.allclose(sn, snRef, rtol=1e-4, atol=1e-4), "S/N maps differ: %g" % errSN
+    refCat = photometry_ref.findObjects(ref, **DETECT)
+    gotCat = photometry.findObjects(got, **DETECT)
+    assert len(gotCat) == len(refCat) and len(refCat) >= 3
+    for a, b in zip(gotCat.toRows(), refCat):
+        assert abs(a['x'] - b['x']) < 0.01 and abs(a['y'] - b['y']) < 0.01 and abs(a['SNR'] - b['SNR']) < 1e-3 * abs(b['SNR'])
