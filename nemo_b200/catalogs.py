@@ -259,8 +259,9 @@ def catalogListToTab(catalogList, keysToWrite=COLUMN_NAMES):
 
 def _crossMatchKeepBest(ra, dec, snr, radiusDeg):
     """Boolean mask of rows to remove: for every row, all rows within radiusDeg of it except the one with the highest
-    S/N (first one on ties) are dropped.  Same outcome as the reference's O(n^2) loop (catalogs.py:171-183), with the
-    neighbour search done by a k-d tree on unit vectors and the reference's separation formula as the final test."""
+    S/N (first one on ties) are dropped.  Same outcome as the reference's O(n^2) loop (catalogs.py:171-183): candidate
+    pairs come from a k-d tree on unit vectors, the reference's (tangent-plane, centred on the row) separation decides,
+    and the rule is applied to all rows at once."""
     from scipy.spatial import cKDTree
     n = len(ra)
     toRemove = np.zeros(n, dtype=bool)
@@ -268,17 +269,28 @@ def _crossMatchKeepBest(ra, dec, snr, radiusDeg):
         return toRemove
     a, d = np.radians(ra), np.radians(dec)
     xyz = np.stack([np.cos(d) * np.cos(a), np.cos(d) * np.sin(a), np.sin(d)], axis=1)
-    tree = cKDTree(xyz)
     chord = 2 * np.sin(np.radians(radiusDeg * 1.01) / 2)
-    for i, nb in enumerate(tree.query_ball_point(xyz, chord)):
-        if len(nb) < 2:
-            continue
-        nb = np.sort(np.asarray(nb))
-        rDeg = _wcs.calcAngSepDeg(ra[i], dec[i], ra[nb], dec[nb])
-        xIndices = nb[rDeg < radiusDeg]
-        if len(xIndices) > 1:
-            best = xIndices[np.argmax(snr[xIndices])]
-            toRemove[xIndices[xIndices != best]] = True
+    pairs = cKDTree(xyz).query_pairs(chord, output_type='ndarray')
+    if len(pairs) == 0:
+        return toRemove
+    # directed edges centre -> member, both directions; the separation is measured about the centre, as the reference does
+    centre = np.concatenate([pairs[:, 0], pairs[:, 1]])
+    member = np.concatenate([pairs[:, 1], pairs[:, 0]])
+    near = _wcs.calcAngSepDeg(ra[centre], dec[centre], ra[member], dec[member]) < radiusDeg
+    centre, member = centre[near], member[near]
+    if len(centre) == 0:
+        return toRemove
+    # every centre with at least one neighbour is a member of its own group
+    own = np.unique(centre)
+    centre = np.concatenate([centre, own])
+    member = np.concatenate([member, own])
+    # best member of each group: highest S/N, lowest row index on ties (np.argmax over ascending indices)
+    order = np.lexsort((member, -snr[member], centre))
+    centre, member = centre[order], member[order]
+    first = np.ones(len(centre), dtype=bool)
+    first[1:] = centre[1:] != centre[:-1]
+    best = member[np.flatnonzero(first)[np.cumsum(first) - 1]]
+    toRemove[member[member != best]] = True
     return toRemove
 
 
