@@ -38,6 +38,9 @@ int nb_fft_size_supported(int n);
  * launches; nb_prof_report synchronises the device and writes "kernel,launches,total_ms\n" lines (first-launch
  * order) into buf (host, cap bytes), returning the full length. */
 long long nb_launch_count(void); /* kernels launched by this library since it was loaded */
+/* A caller that replays a captured CUDA graph of this library's launches reports the kernels of each replay here, so
+ * that nb_launch_count keeps counting kernels that ran. */
+long long nb_launch_count_add(long long n);
 int nb_prof_enable(int on);
 long long nb_prof_report(char* buf, long long cap);
 

@@ -26,6 +26,7 @@ _PROTOTYPES = {
     "nb_device_info": [ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)],
     "nb_fft_size_supported": [c_int],
     "nb_launch_count": [],
+    "nb_launch_count_add": [c_ll],
     "nb_prof_enable": [c_int],
     "nb_prof_report": [ctypes.c_char_p, c_ll],
     "nb_rfft2": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_ptr],
@@ -57,7 +58,7 @@ _PROTOTYPES = {
     "nb_cast": [c_int, c_ptr, c_int, c_ptr, c_ll, c_ptr],
     "nb_mask_to_u8": [c_int, c_ptr, c_ptr, c_ll, c_ptr],
 }
-_RESTYPES = {"nb_last_error": ctypes.c_char_p, "nb_label4_scratch_ints": c_ll, "nb_detect_scratch_ints": c_ll, "nb_find_objects_scratch_ints": c_ll, "nb_prof_report": c_ll, "nb_launch_count": c_ll}
+_RESTYPES = {"nb_last_error": ctypes.c_char_p, "nb_label4_scratch_ints": c_ll, "nb_detect_scratch_ints": c_ll, "nb_find_objects_scratch_ints": c_ll, "nb_prof_report": c_ll, "nb_launch_count": c_ll, "nb_launch_count_add": c_ll}
 
 EXPORTED_SYMBOLS = sorted(_PROTOTYPES.keys())
 
@@ -107,9 +108,17 @@ def launchCount():
     return int(load().nb_launch_count())
 
 
+_PROF_ON = [False]
+
+
 def profEnable(on=True):
     """Starts (and clears) or stops the library's per-kernel CUDA-event timers."""
     load().nb_prof_enable(1 if on else 0)
+    _PROF_ON[0] = bool(on)
+
+
+def profEnabled():
+    return _PROF_ON[0]
 
 
 def profReport():

@@ -76,6 +76,10 @@ extern "C" {
 
 long long nb_launch_count(void) { return (long long)__atomic_load_n(&g_nb_launches, __ATOMIC_RELAXED); }
 
+long long nb_launch_count_add(long long n) {
+    return (long long)__atomic_add_fetch(&g_nb_launches, (unsigned long long)n, __ATOMIC_RELAXED);
+}
+
 int nb_prof_enable(int on) {
     std::lock_guard<std::mutex> lock(g_prof_mutex);
     for (auto& r : g_prof_recs) {

@@ -113,7 +113,14 @@ class Ops(object):
         return out
 
     def window_tables(self, H, W, power):
-        """(wy, wx) of enmap.apply_window raised to `power`, on the device (wx on the half plane)."""
+        """(wy, wx) of enmap.apply_window raised to `power`, on the device (wx on the half plane); cached."""
+        cache = self.__dict__.setdefault('_windowTables', {})
+        key = (int(H), int(W), float(power))
+        if key not in cache:
+            cache[key] = self._make_window_tables(H, W, power)
+        return cache[key]
+
+    def _make_window_tables(self, H, W, power):
         wy = np.sinc(np.fft.fftfreq(H)) ** power
         wx = (np.sinc(np.fft.fftfreq(W)) ** power)[:W // 2 + 1].copy()
         wx[W // 2] = np.sinc(0.5) ** power  # fftfreq gives -0.5 at the Nyquist column; sinc is even

@@ -230,6 +230,15 @@ def filterTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow
     return finishTileBatch(job, measureFluxes=measureFluxes, keepMaps=keepMaps)
 
 
+class _BatchView(object):
+    """The geometry of a TileBatch with other device buffers (the static inputs a captured CUDA graph reads)."""
+
+    def __init__(self, batch, dev):
+        self.dev = dev
+        self.nT, self.F, self.H, self.W = batch.nT, batch.F, batch.H, batch.W
+        self.wcsList, self.mapDicts, self.tileNames, self.flagMasks = batch.wcsList, batch.mapDicts, batch.tileNames, batch.flagMasks
+
+
 class BatchPipeline(object):
     """Two-stage software pipeline over tile batches on two CUDA streams: ``submit(batch)`` queues the device work of that
     batch (upload included when asked) and only then assembles the catalogs of the batch submitted before it, so the host
@@ -238,8 +247,12 @@ class BatchPipeline(object):
     nothing is shared between batches except the read-only templates."""
 
     def __init__(self, ops, filtersList, templates, parDict, undoPixelWindow=True, measureFluxes=True, invertMap=False,
-                 keepMaps=False, useCachedRMSMap=False):
+                 keepMaps=False, useCachedRMSMap=False, useGraphs=True):
         self.ops, self.filtersList, self.templates, self.parDict = ops, filtersList, templates, parDict
+        # the ~40 launches of a batch are captured once per (slot, shape, input buffers) into a CUDA graph and replayed:
+        # the host then spends microseconds, not a millisecond, queueing a batch.  Graphs live on the Ops object.
+        self.useGraphs = useGraphs
+        self.graphs = ops.__dict__.setdefault('_batchGraphs', {})
         self.undoPixelWindow, self.measureFluxes, self.invertMap, self.keepMaps = undoPixelWindow, measureFluxes, invertMap, keepMaps
         self.useCachedRMSMap = useCachedRMSMap
         torch = ops.torch
@@ -263,16 +276,71 @@ class BatchPipeline(object):
             job['batch'].dev = None
         return out
 
-    def submit(self, batch, upload=True, cache=None):
-        torch = self.ops.torch
-        st = self.streams[self.count % 2]
-        self.count += 1
+    def _graphEntry(self, slot, st, batch, upload):
+        """(graph, job template, static inputs, launches per replay) for this slot and batch shape, captured on first use."""
+        from . import _lib
+        ops, torch = self.ops, self.ops.torch
+        if upload:
+            ident = 'staged'
+        else:
+            ident = tuple(int(batch.dev[k].data_ptr()) for k in ('data', 'weights', 'psMask', 'surveyMask', 'wmed'))
+        key = (slot, ident, batch.nT, batch.F, batch.H, batch.W, ops.precision, id(self.templates), self.undoPixelWindow, self.invertMap,
+               repr(sorted((k, repr(v)) for k, v in self.parDict.items() if k != 'mapFilters')),
+               repr([(f['label'], repr(sorted(f['params'].items(), key=lambda kv: kv[0]))) for f in self.filtersList]))
+        entry = self.graphs.get(key)
+        if entry is not None:
+            return entry
         with torch.cuda.stream(st):
             if upload:
-                batch.upload()
-            job = startTileBatch(self.ops, batch, self.filtersList, self.templates, self.parDict,
-                                 undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap, cache=cache,
-                                 useCachedRMSMap=self.useCachedRMSMap)
+                static = {k: torch.empty(v.shape, dtype=v.dtype, device=ops.device) for k, v in batch.host.items()}
+                for k, v in batch.host.items():
+                    static[k].copy_(v, non_blocking=True)
+            else:
+                static = dict(batch.dev)
+            view = _BatchView(batch, dict(static))
+            if upload:
+                view.dev['wmed'] = ops.median_weights(static['weights'])
+            # one eager run first: twiddle tables, kernel attributes and other lazy set-up must not happen under capture
+            startTileBatch(ops, view, self.filtersList, self.templates, self.parDict, undoPixelWindow=self.undoPixelWindow,
+                           invertMap=self.invertMap)
+            st.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launchCount()
+            with torch.cuda.graph(graph, stream=st):
+                if upload:
+                    view.dev['wmed'] = ops.median_weights(static['weights'])
+                job = startTileBatch(ops, view, self.filtersList, self.templates, self.parDict,
+                                     undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap)
+            nLaunch = _lib.launchCount() - n0
+        entry = (graph, job, static, nLaunch)
+        self.graphs[key] = entry
+        return entry
+
+    def submit(self, batch, upload=True, cache=None):
+        from . import _lib
+        torch = self.ops.torch
+        slot = self.count % 2
+        st = self.streams[slot]
+        self.count += 1
+        useGraph = self.useGraphs and cache is None and not _lib.profEnabled()
+        if useGraph:
+            graph, template, static, nLaunch = self._graphEntry(slot, st, batch, upload)
+            with torch.cuda.stream(st):
+                if upload:
+                    for k, v in batch.host.items():
+                        static[k].copy_(device.countH2D(v), non_blocking=True)
+                graph.replay()
+            _lib.load().nb_launch_count_add(nLaunch)
+            job = dict(template)
+            job['batch'] = batch
+            upload = False          # nothing of the batch itself is resident
+        else:
+            with torch.cuda.stream(st):
+                if upload:
+                    batch.upload()
+                job = startTileBatch(self.ops, batch, self.filtersList, self.templates, self.parDict,
+                                     undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap, cache=cache,
+                                     useCachedRMSMap=self.useCachedRMSMap)
         out = self._finish() if self.pending is not None else None
         self.pending = (job, st, upload)
         return out
@@ -285,11 +353,12 @@ class BatchPipeline(object):
 
 
 def processBatches(ops, batches, filtersList, templates, parDict, upload=True, undoPixelWindow=True, measureFluxes=True,
-                   invertMap=False, keepMaps=False, caches=None, useCachedRMSMap=False):
+                   invertMap=False, keepMaps=False, caches=None, useCachedRMSMap=False, useGraphs=True):
     """Runs several tile batches through a BatchPipeline; returns the list of (catalogDict, extras), one per batch, in order.
     caches: per-batch filter / RMS caches (see startTileBatch), or None."""
     pipe = BatchPipeline(ops, filtersList, templates, parDict, undoPixelWindow=undoPixelWindow, measureFluxes=measureFluxes,
-                         invertMap=invertMap, keepMaps=keepMaps, useCachedRMSMap=useCachedRMSMap)
+                         invertMap=invertMap, keepMaps=keepMaps, useCachedRMSMap=useCachedRMSMap,
+                         useGraphs=useGraphs and not keepMaps)
     results = []
     for i, batch in enumerate(batches):
         out = pipe.submit(batch, upload=upload and batch.dev is None, cache=caches[i] if caches is not None else None)
