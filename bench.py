@@ -119,6 +119,7 @@ def algorithmicBytes(nT, F, S, H, W, E, rings=True):
     b['paint_rms_kernel'] = nOut * 2 * N * E
     b['edge_rows_kernel'] = nOut * (N * E + 2 * N)
     b['edge_cols_final_kernel'] = nOut * (2 * N * E + 3 * N + 3 * N * E + N)
+    b['edge_cols_final_paint_kernel'] = nOut * (2 * N * E + 3 * N + 3 * N * E + N)   # map, median weights, masks in; data, S/N, RMS, mask out
     b['fft_cols_window_kernel'] = nOut * 2 * Nc * 2 * E
     b['detect_scan_kernel'] = nPass * nOut * (N * E + 4 * N)      # S/N read, zeroed label image written; the rest is sparse
     return b

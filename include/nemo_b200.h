@@ -109,7 +109,7 @@ int nb_median_weights(int prec, const void* weights, void* out, int B, int F, in
 /* K6: MapFilter.makeNoiseMap, grid branch, default 3-sigma-clipped estimator (nemo/filters.py:409-481).
  * map [nImg, H, W] (already multiplied by psMask); wmed [nImg / S, H, W] median weights;
  * yChunks host [ny + 1], xChunks host [nx + 1] (np.linspace(..., dtype=int)); overlapPix; numBins.
- * Outputs: rms [nImg, H, W] T; table [nImg, ny * nx, numBins] fp64 cell RMS values; edges
+ * Outputs: rms [nImg, H, W] T (NULL: no painting, tables only); table [nImg, ny * nx, numBins] fp64 cell RMS values; edges
  * [nImg, ny * nx, numBins + 1] fp64 weight-bin edges (NaN for skipped cells). */
 int nb_cell_rms(int prec, const void* map, const void* wmed, int nImg, int S, int H, int W, const int* yChunks,
                 int ny, const int* xChunks, int nx, int overlapPix, int numBins, void* rms, double* table,
@@ -125,6 +125,15 @@ int nb_cell_rms(int prec, const void* map, const void* wmed, int nImg, int S, in
 int nb_snr_mask(int prec, void* map, void* rms, const unsigned char* psMask, const unsigned char* surveyMask,
                 int nImg, int S, int H, int W, int trimPix, int apodPix, int realSpace, void* sn,
                 unsigned char* maskOut, unsigned char* scratch, cudaStream_t stream);
+
+/* K6 painting fused into K7: as nb_snr_mask, but the RMS of every pixel is taken straight from the cell table of
+ * nb_cell_rms (called with rms = NULL, which skips its painting pass) instead of from a painted RMS map; rmsOut receives
+ * the painted and masked RMS map. */
+int nb_snr_mask_cells(int prec, void* map, const void* wmed, const double* table, const double* edges, const int* yChunks,
+                      int ny, const int* xChunks, int nx, int overlapPix, int numBins, const unsigned char* psMask,
+                      const unsigned char* surveyMask, int nImg, int S, int H, int W, int trimPix, int apodPix,
+                      int realSpace, void* sn, void* rmsOut, unsigned char* maskOut, unsigned char* scratch,
+                      cudaStream_t stream);
 
 /* S/N from a cached RMS map (nemo/pipelines.py:216-228): sn = where(rms > 0, map / rms, map). */
 int nb_snr_from_rms(int prec, const void* map, const void* rms, void* sn, int nImg, int S, int H, int W,

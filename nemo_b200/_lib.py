@@ -42,6 +42,8 @@ _PROTOTYPES = {
     "nb_cell_rms": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int), c_int,
                     c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "nb_snr_mask": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
+    "nb_snr_mask_cells": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int), c_int, c_int, c_int, c_ptr, c_ptr,
+                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "nb_snr_from_rms": [c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
     "nb_label4": [c_int, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr],
     "nb_label4_scratch_ints": [c_int, c_int, c_int],

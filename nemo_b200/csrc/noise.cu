@@ -1058,6 +1058,57 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
         for (int b = lane; b < numBins; b += 32) tab[b] = wState[b].rms;
 }
 
+// the RMS a pixel takes: that of the last cell (raster order) that covers it, has rms > 0 and whose weight bin holds its weight w
+// (filters.py:480-481: later cells overwrite earlier ones where they overlap); 0 when there is none
+// candidate cells along one axis for coordinate v: the chunk that holds it and every neighbour whose margin reaches it
+__device__ __forceinline__ void paint_axis_range(int v, const int* __restrict__ c, int n, int ov, int L, int& lo, int& hi) {
+    int ci = min((int)(((long long)v * n) / L), n - 1);
+    while (ci > 0 && v < c[ci]) --ci;
+    while (ci < n - 1 && v >= c[ci + 1]) ++ci;
+    lo = hi = ci;
+    while (lo > 0 && v < min(c[lo] + ov, L)) --lo;
+    while (hi < n - 1 && v >= max(c[hi + 1] - ov, 0)) ++hi;
+}
+
+// the value cell (i, k) of image img paints at weight w, or 0 when it paints nothing there.  The weight bins of a cell are
+// disjoint and ascending, so the reference's "last bin that holds w" (filters.py:455-481) is the only bin that holds it.
+__device__ __forceinline__ double paint_cell_value(double w, int cell, int img, int nCells, int numBins,
+                                                   const double* __restrict__ table, const double* __restrict__ edges) {
+    const double* edg = edges + ((size_t)img * nCells + cell) * (numBins + 1);
+    const double e0 = edg[0];
+    if (isnan(e0) || !(w >= e0) || !(w < edg[numBins])) return 0.0;
+    int lo = 0, hi = numBins;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (w >= edg[mid]) lo = mid; else hi = mid;
+    }
+    const double v = table[((size_t)img * nCells + cell) * numBins + lo];
+    return v > 0.0 ? v : 0.0;
+}
+
+__device__ __forceinline__ double paint_value_in(double w, int x, int y, int img, const Chunks& ch, int nx, int ov, int numBins,
+                                                 const double* __restrict__ table, const double* __restrict__ edges, int H, int W,
+                                                 int nCells, int iLo, int iHi, int kLo, int kHi) {
+    // candidates are visited last-written first (raster order of the cells)
+    for (int i = iHi; i >= iLo; --i) {
+        if (y < max(ch.y[i] - ov, 0) || y >= min(ch.y[i + 1] + ov, H)) continue;
+        for (int k = kHi; k >= kLo; --k) {
+            if (x < max(ch.x[k] - ov, 0) || x >= min(ch.x[k + 1] + ov, W)) continue;
+            const double v = paint_cell_value(w, i * nx + k, img, nCells, numBins, table, edges);
+            if (v > 0.0) return v;
+        }
+    }
+    return 0.0;
+}
+
+__device__ __forceinline__ double paint_value(double w, int x, int y, int img, const Chunks& ch, int ny, int nx, int ov, int numBins,
+                                              const double* __restrict__ table, const double* __restrict__ edges, int H, int W) {
+    int iLo, iHi, kLo, kHi;
+    paint_axis_range(y, ch.y, ny, ov, H, iLo, iHi);
+    paint_axis_range(x, ch.x, nx, ov, W, kLo, kHi);
+    return paint_value_in(w, x, y, img, ch, nx, ov, numBins, table, edges, H, W, ny * nx, iLo, iHi, kLo, kHi);
+}
+
 // every pixel takes the RMS of the last cell (raster order) that covers it, has rms > 0 and whose weight bin holds it
 template <typename T>
 __global__ void __launch_bounds__(256) paint_rms_kernel(const T* __restrict__ wmed, int S, int H, int W, const Chunks ch,
@@ -1068,41 +1119,7 @@ __global__ void __launch_bounds__(256) paint_rms_kernel(const T* __restrict__ wm
     const int y = blockIdx.y, img = blockIdx.z;
     if (x >= W) return;
     const double w = (double)wmed[((size_t)(img / S) * H + y) * W + x];
-    const int nCells = ny * nx;
-    double val = 0.0;
-    bool found = false;
-    // only the chunk that holds the pixel and its two neighbours can cover it (the margins are half a chunk wide, but chunk
-    // sizes may differ by one pixel, so the test below stays exact); candidates are visited last-written first
-    int ci = min((int)(((long long)y * ny) / H), ny - 1);
-    while (ci > 0 && y < ch.y[ci]) --ci;
-    while (ci < ny - 1 && y >= ch.y[ci + 1]) ++ci;
-    int ck = min((int)(((long long)x * nx) / W), nx - 1);
-    while (ck > 0 && x < ch.x[ck]) --ck;
-    while (ck < nx - 1 && x >= ch.x[ck + 1]) ++ck;
-    // a margin wider than a neighbouring chunk would let a farther cell reach the pixel: widen the candidate range then
-    int iLo = ci, iHi = ci, kLo = ck, kHi = ck;
-    while (iLo > 0 && y < min(ch.y[iLo] + ov, H)) --iLo;
-    while (iHi < ny - 1 && y >= max(ch.y[iHi + 1] - ov, 0)) ++iHi;
-    while (kLo > 0 && x < min(ch.x[kLo] + ov, W)) --kLo;
-    while (kHi < nx - 1 && x >= max(ch.x[kHi + 1] - ov, 0)) ++kHi;
-    for (int i = iHi; i >= iLo && !found; --i) {
-        if (y < max(ch.y[i] - ov, 0) || y >= min(ch.y[i + 1] + ov, H)) continue;
-        for (int k = kHi; k >= kLo && !found; --k) {
-            if (x < max(ch.x[k] - ov, 0) || x >= min(ch.x[k + 1] + ov, W)) continue;
-            const int cell = i * nx + k;
-            const double* edg = edges + ((size_t)img * nCells + cell) * (numBins + 1);
-            if (isnan(edg[0])) continue;
-            const double* tab = table + ((size_t)img * nCells + cell) * numBins;
-            // the reference writes bins in ascending order, so the last bin that holds w and has rms > 0 wins
-            for (int b = numBins - 1; b >= 0; --b) {
-                if (w >= edg[b] && w < edg[b + 1] && tab[b] > 0.0) {
-                    val = tab[b];
-                    found = true;
-                    break;
-                }
-            }
-        }
-    }
+    const double val = paint_value(w, x, y, img, ch, ny, nx, ov, numBins, table, edges, H, W);
     rms[((size_t)img * H + y) * W + x] = (T)val;
 }
 
@@ -1154,11 +1171,18 @@ __global__ void __launch_bounds__(256) edge_rows_kernel(const T* __restrict__ ma
 }
 
 #define EC_SEG 32
-template <typename T>
+struct PaintArgs {   // what edge_cols_final_kernel<T, true> needs to take the RMS straight from the cell table
+    const void* wmed;
+    const double* table;
+    const double* edges;
+    int ny, nx, ov, numBins;
+};
+
+template <typename T, bool PAINT>
 __global__ void __launch_bounds__(128) edge_cols_final_kernel(T* map, T* rms, const unsigned char* __restrict__ ps,
                                                               const unsigned char* __restrict__ survey, int S, int H, int W, int trim,
                                                               int apodPix, int realSpace, const unsigned char* __restrict__ rowAny,
-                                                              T* sn, unsigned char* __restrict__ maskOut) {
+                                                              T* sn, unsigned char* __restrict__ maskOut, PaintArgs pa, const Chunks ch) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int ys = blockIdx.y * EC_SEG, img = blockIdx.z;
     if (x >= W) return;
@@ -1170,10 +1194,20 @@ __global__ void __launch_bounds__(128) edge_cols_final_kernel(T* map, T* rms, co
         for (int d = lo; d <= hi; ++d) cnt += ra[(size_t)reflect_idx(ys + d, H) * W + x];
     }
     const int ye = min(ys + EC_SEG, H);
+    int kLo = 0, kHi = 0;
+    if constexpr (PAINT) paint_axis_range(x, ch.x, pa.nx, pa.ov, W, kLo, kHi);   // the same for every row of this column
     for (int y = ys; y < ye; ++y) {
         const size_t o = (size_t)y * W + x;
         const T m0 = map[ib + o];
-        const T r0 = rms[ib + o];
+        T r0;
+        if constexpr (PAINT) {
+            const double w = (double)reinterpret_cast<const T*>(pa.wmed)[tb + o];
+            int iLo, iHi;
+            paint_axis_range(y, ch.y, pa.ny, pa.ov, H, iLo, iHi);
+            r0 = (T)paint_value_in(w, x, y, img, ch, pa.nx, pa.ov, pa.numBins, pa.table, pa.edges, H, W, pa.ny * pa.nx, iLo, iHi, kLo, kHi);
+        } else {
+            r0 = rms[ib + o];
+        }
         const T edge = (trim > 0 && cnt > 0) ? (T)0 : (T)1;
         const T psv = (T)ps[tb + o], sv = (T)survey[tb + o];
         T snv = (r0 > (T)0) ? m0 / r0 : m0;
@@ -1245,21 +1279,32 @@ static int cell_rms_t(const void* map, const void* wmed, int nImg, int S, int H,
             (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges); NB_PROF_END("cell_rms_stream_kernel", st); }
     }
     NB_CHECK_LAUNCH();
-    { NB_PROF_BEGIN(st); paint_rms_kernel<T><<<dim3((W + 255) / 256, H, nImg), 256, 0, st>>>((const T*)wmed, S, H, W, ch, ny, nx, ov, numBins, table,
-                                                                         edges, (T*)rms); NB_PROF_END("paint_rms_kernel", st); }
-    NB_CHECK_LAUNCH();
+    if (rms) {
+        { NB_PROF_BEGIN(st); paint_rms_kernel<T><<<dim3((W + 255) / 256, H, nImg), 256, 0, st>>>((const T*)wmed, S, H, W, ch, ny, nx, ov, numBins, table,
+                                                                             edges, (T*)rms); NB_PROF_END("paint_rms_kernel", st); }
+        NB_CHECK_LAUNCH();
+    }
     return NB_OK;
 }
 
 template <typename T>
 static int snr_mask_t(void* map, void* rms, const unsigned char* ps, const unsigned char* survey, int nImg, int S, int H, int W,
-                      int trim, int apodPix, int realSpace, void* sn, unsigned char* maskOut, unsigned char* scratch, cudaStream_t st) {
+                      int trim, int apodPix, int realSpace, void* sn, unsigned char* maskOut, unsigned char* scratch, cudaStream_t st,
+                      const PaintArgs* pa = nullptr, const Chunks* chp = nullptr) {
     if (trim > 0) {
         { NB_PROF_BEGIN(st); edge_rows_kernel<T><<<dim3(H, nImg), 256, sizeof(int) * (W + 1), st>>>((const T*)map, ps, S, H, W, trim, scratch); NB_PROF_END("edge_rows_kernel", st); }
         NB_CHECK_LAUNCH();
     }
-    { NB_PROF_BEGIN(st); edge_cols_final_kernel<T><<<dim3((W + 127) / 128, (H + EC_SEG - 1) / EC_SEG, nImg), 128, 0, st>>>(
-        (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut); NB_PROF_END("edge_cols_final_kernel", st); }
+    if (pa) {
+        { NB_PROF_BEGIN(st); edge_cols_final_kernel<T, true><<<dim3((W + 127) / 128, (H + EC_SEG - 1) / EC_SEG, nImg), 128, 0, st>>>(
+            (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut, *pa, *chp); NB_PROF_END("edge_cols_final_paint_kernel", st); }
+    } else {
+        PaintArgs none = {nullptr, nullptr, nullptr, 0, 0, 0, 0};
+        Chunks ch0;
+        memset(&ch0, 0, sizeof(ch0));
+        { NB_PROF_BEGIN(st); edge_cols_final_kernel<T, false><<<dim3((W + 127) / 128, (H + EC_SEG - 1) / EC_SEG, nImg), 128, 0, st>>>(
+            (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut, none, ch0); NB_PROF_END("edge_cols_final_kernel", st); }
+    }
     NB_CHECK_LAUNCH();
     return NB_OK;
 }
@@ -1285,7 +1330,7 @@ int nb_median_weights(int prec, const void* weights, void* out, int B, int F, in
 int nb_cell_rms(int prec, const void* map, const void* wmed, int nImg, int S, int H, int W, const int* yChunks, int ny,
                 const int* xChunks, int nx, int overlapPix, int numBins, void* rms, double* table, double* edges,
                 cudaStream_t st) {
-    NB_REQUIRE(map && wmed && yChunks && xChunks && rms && table && edges && nImg > 0 && S > 0 && ny > 0 && nx > 0, NB_ERR_ARG,
+    NB_REQUIRE(map && wmed && yChunks && xChunks && table && edges && nImg > 0 && S > 0 && ny > 0 && nx > 0, NB_ERR_ARG,
                "nb_cell_rms: bad arguments");
     NB_REQUIRE(numBins >= 1 && numBins <= 64, NB_ERR_ARG, "nb_cell_rms: numBins %d out of range (1..64)", numBins);
     if (prec == NB_PREC_F64)
@@ -1308,6 +1353,29 @@ int nb_snr_mask(int prec, void* map, void* rms, const unsigned char* psMask, con
     if (prec == NB_PREC_F32)
         return snr_mask_t<float>(map, rms, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st);
     nb_set_error("nb_snr_mask: bad precision %d", prec);
+    return NB_ERR_ARG;
+}
+
+int nb_snr_mask_cells(int prec, void* map, const void* wmed, const double* table, const double* edges, const int* yChunks, int ny,
+                      const int* xChunks, int nx, int overlapPix, int numBins, const unsigned char* psMask,
+                      const unsigned char* surveyMask, int nImg, int S, int H, int W, int trimPix, int apodPix, int realSpace, void* sn,
+                      void* rmsOut, unsigned char* maskOut, unsigned char* scratch, cudaStream_t st) {
+    NB_REQUIRE(map && wmed && table && edges && yChunks && xChunks && psMask && surveyMask && sn && rmsOut && maskOut && nImg > 0 && S > 0,
+               NB_ERR_ARG, "nb_snr_mask_cells: bad arguments");
+    NB_REQUIRE(trimPix == 0 || scratch, NB_ERR_ARG, "nb_snr_mask_cells: scratch required when trimPix > 0");
+    NB_REQUIRE(trimPix >= 0 && trimPix <= H && trimPix <= W, NB_ERR_UNSUPPORTED, "nb_snr_mask_cells: trimPix %d larger than the tile", trimPix);
+    NB_REQUIRE(W <= 8192, NB_ERR_UNSUPPORTED, "nb_snr_mask_cells: tile too wide");
+    NB_REQUIRE(ny > 0 && nx > 0 && ny <= NB_MAX_CHUNKS && nx <= NB_MAX_CHUNKS, NB_ERR_UNSUPPORTED, "nb_snr_mask_cells: bad noise grid");
+    Chunks ch;
+    memset(&ch, 0, sizeof(ch));
+    for (int i = 0; i <= ny; ++i) ch.y[i] = yChunks[i];
+    for (int i = 0; i <= nx; ++i) ch.x[i] = xChunks[i];
+    PaintArgs pa = {wmed, table, edges, ny, nx, overlapPix, numBins};
+    if (prec == NB_PREC_F64)
+        return snr_mask_t<double>(map, rmsOut, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st, &pa, &ch);
+    if (prec == NB_PREC_F32)
+        return snr_mask_t<float>(map, rmsOut, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st, &pa, &ch);
+    nb_set_error("nb_snr_mask_cells: bad precision %d", prec);
     return NB_ERR_ARG;
 }
 

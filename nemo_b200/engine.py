@@ -152,8 +152,9 @@ def noiseSNAndMasks(ops, filtered, wmed, psMask, surveyMask, S, grid, trimPix, a
     """makeNoiseMap + S/N + edge trim + masks (filters.py:719-758).  `filtered` is overwritten with `data`.
     Returns (data, SNMap, surveyMaskOut u8, RMSMap, cellTable, cellEdges)."""
     yChunks, xChunks, overlapPix, numBins = grid
-    rms, table, edges = ops.cell_rms(filtered, wmed, S, yChunks, xChunks, overlapPix, numBins)
-    data, sn, maskOut, rms = ops.snr_mask(filtered, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace)
+    _, table, edges = ops.cell_rms(filtered, wmed, S, yChunks, xChunks, overlapPix, numBins, paint=False)
+    data, sn, maskOut, rms = ops.snr_mask_cells(filtered, wmed, table, edges, yChunks, xChunks, overlapPix, numBins, psMask, surveyMask,
+                                                S, trimPix, apodPix, realSpace)
     return data, sn, maskOut, rms, table, edges
 
 

@@ -210,12 +210,13 @@ class Ops(object):
         self.launches += 1
         return out
 
-    def cell_rms(self, maps, wmed, S, yChunks, xChunks, overlapPix, numBins):
+    def cell_rms(self, maps, wmed, S, yChunks, xChunks, overlapPix, numBins, paint=True):
+        """Clipped-RMS cell tables and (paint=True) the painted RMS map; with paint=False returns (None, table, edges)."""
         self._check(maps, self.dtype, 'maps')
         self._check(wmed, self.dtype, 'wmed')
         nImg, H, W = maps.shape
         ny, nx = len(yChunks) - 1, len(xChunks) - 1
-        rms = self.empty((nImg, H, W))
+        rms = self.empty((nImg, H, W)) if paint else None
         table = self.empty((nImg, ny * nx, numBins), self.torch.float64)
         edges = self.empty((nImg, ny * nx, numBins + 1), self.torch.float64)
         yc = (ctypes.c_int * (ny + 1))(*[int(v) for v in yChunks])
@@ -237,6 +238,27 @@ class Ops(object):
         scratch = self.empty((nImg, H, W), self.torch.uint8) if trimPix > 0 else None
         _lib.call('nb_snr_mask', self.prec, _ptr(maps), _ptr(rms), _ptr(psMask), _ptr(surveyMask), nImg, int(S), H, W, int(trimPix),
                   int(apodPix), 1 if realSpace else 0, _ptr(sn), _ptr(maskOut), _ptr(scratch), self._stream())
+        self.launches += 2 if trimPix > 0 else 1
+        return maps, sn, maskOut, rms
+
+    def snr_mask_cells(self, maps, wmed, table, edges, yChunks, xChunks, overlapPix, numBins, psMask, surveyMask, S, trimPix, apodPix,
+                       realSpace):
+        """snr_mask with the RMS taken straight from the cell tables (painting fused); returns (data, SNMap, mask u8, RMS map)."""
+        self._check(maps, self.dtype, 'maps')
+        self._check(wmed, self.dtype, 'wmed')
+        self._check(psMask, self.torch.uint8, 'psMask')
+        self._check(surveyMask, self.torch.uint8, 'surveyMask')
+        nImg, H, W = maps.shape
+        ny, nx = len(yChunks) - 1, len(xChunks) - 1
+        sn = self.empty((nImg, H, W))
+        rms = self.empty((nImg, H, W))
+        maskOut = self.empty((nImg, H, W), self.torch.uint8)
+        scratch = self.empty((nImg, H, W), self.torch.uint8) if trimPix > 0 else None
+        yc = (ctypes.c_int * (ny + 1))(*[int(v) for v in yChunks])
+        xc = (ctypes.c_int * (nx + 1))(*[int(v) for v in xChunks])
+        _lib.call('nb_snr_mask_cells', self.prec, _ptr(maps), _ptr(wmed), _ptr(table), _ptr(edges), yc, ny, xc, nx, int(overlapPix),
+                  int(numBins), _ptr(psMask), _ptr(surveyMask), nImg, int(S), H, W, int(trimPix), int(apodPix), 1 if realSpace else 0,
+                  _ptr(sn), _ptr(rms), _ptr(maskOut), _ptr(scratch), self._stream())
         self.launches += 2 if trimPix > 0 else 1
         return maps, sn, maskOut, rms
 
