@@ -155,7 +155,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpuIndex), '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
@@ -208,7 +208,7 @@ def runReference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default='f64', choices=['f64', 'f32'])
@@ -351,11 +351,18 @@ def main():
         table.append(row)
     table.sort(key=lambda r: -r['ms_per_step'])
     top = next((r for r in table if 'achieved_gbs' in r), None)
+    traffic, trafficSrc = None, None
+    trafficPath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if top is not None and os.path.exists(trafficPath):
+        tj = json.load(open(trafficPath))
+        ent = tj.get(args.precision, {}).get(top['kernel'])
+        if ent is not None:
+            traffic, trafficSrc = ent['dram_bytes_per_launch'], ent['source']
     roofline = None
     if top is not None:
         lp = top['launches_per_step']
         roofline = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
-                    'frac': top['frac'], 'traffic': None, 'peak_source': peakSrc, 'timed_in': 'same run, %d further steps executed one at a time with per-kernel CUDA events' % args.steps, 'share_of_step_kernel_time': top['share'],
+                    'frac': top['frac'], 'traffic': traffic, 'traffic_source': trafficSrc, 'peak_source': peakSrc, 'timed_in': 'same run, %d further steps executed one at a time with per-kernel CUDA events' % args.steps, 'share_of_step_kernel_time': top['share'],
                     'bytes_per_launch': top['algorithmic_bytes_per_step'] / lp, 'ms_per_launch': top['ms_per_step'] / lp,
                     'launches_per_step': lp}
     bpp = endToEndBytesPerPixel(F, S, E, rings=parDict['removeRings'])
