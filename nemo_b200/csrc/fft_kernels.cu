@@ -370,8 +370,18 @@ template <typename K> static int set_smem(K kernel, size_t bytes) {
                  return NB_ERR_UNSUPPORTED;                                                 \
     }
 
+static bool is_pow2_side(int n) {
+    return n == 32 || n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096;
+}
+
+// 1: power of two (direct Stockham passes); 2: any other length in 64..4096 (Bluestein passes, fft_bluestein.cu); 0: no
 int nb_fft_size_supported(int n) {
-    return (n == 32 || n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096) ? 1 : 0;
+    if (is_pow2_side(n)) return 1;
+    return (n >= 64 && n <= 4096) ? 2 : 0;
+}
+
+static bool tile_supported(int H, int W) {
+    return nb_fft_size_supported(H) != 0 && nb_fft_size_supported(W) != 0 && W >= 64 && (W % 2) == 0;
 }
 
 template <typename T>
@@ -512,52 +522,61 @@ static int fft_cols_window_t(typename V2<T>::type* data, int B, int H, int Wc, c
 // C ABI
 extern "C" {
 
+// row / column passes by side: direct when the side is a power of two, Bluestein otherwise
+static int rows_fwd(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st) {
+    if (!is_pow2_side(W)) return nb_bs_rows_fwd(prec, in, out, B, H, W, apodPix, scale, st);
+    if (prec == NB_PREC_F64) return rfft_rows_t<double>((const double*)in, (double2*)out, B, H, W, apodPix, scale, st);
+    return rfft_rows_t<float>((const float*)in, (float2*)out, B, H, W, apodPix, scale, st);
+}
+
+static int rows_inv(int prec, const void* in, void* out, int B, int H, int W, double scale, const double* norm, const unsigned char* mask,
+                    int maskDiv, const void* zeroRef, cudaStream_t st) {
+    if (maskDiv < 1) maskDiv = 1;
+    if (!is_pow2_side(W)) return nb_bs_rows_inv(prec, in, out, B, H, W, scale, norm, mask, maskDiv, zeroRef, st);
+    if (prec == NB_PREC_F64) {
+        C2RParams<double> ep = {scale, norm, mask, maskDiv, (const double*)zeroRef};
+        return irfft_rows_t<double>((const double2*)in, (double*)out, B, H, W, ep, st);
+    }
+    C2RParams<float> ep = {(float)scale, norm, mask, maskDiv, (const float*)zeroRef};
+    return irfft_rows_t<float>((const float2*)in, (float*)out, B, H, W, ep, st);
+}
+
+static int cols_plain(int prec, const void* in, void* out, int B, int H, int Wc, int dir, cudaStream_t st) {
+    if (!is_pow2_side(H)) return nb_bs_cols(prec, in, out, B, H, Wc, dir, st);
+    if (prec == NB_PREC_F64) return fft_cols_t<double>((const double2*)in, (double2*)out, B, H, Wc, dir, 1.0, st);
+    return fft_cols_t<float>((const float2*)in, (float2*)out, B, H, Wc, dir, 1.0, st);
+}
+
 int nb_rfft2(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st) {
     NB_REQUIRE(in && out && B > 0, NB_ERR_ARG, "nb_rfft2: bad arguments");
-    NB_REQUIRE(nb_fft_size_supported(H) && nb_fft_size_supported(W) && W >= 64, NB_ERR_UNSUPPORTED,
-               "nb_rfft2: tile %dx%d not supported (power-of-two sides, 64..4096)", H, W);
+    NB_REQUIRE(prec == NB_PREC_F64 || prec == NB_PREC_F32, NB_ERR_ARG, "nb_rfft2: bad precision %d", prec);
+    NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_rfft2: tile %dx%d not supported (sides 64..4096, even width)", H, W);
     int rc;
-    const int Wc = W / 2 + 1;
-    if (prec == NB_PREC_F64) {
-        if ((rc = rfft_rows_t<double>((const double*)in, (double2*)out, B, H, W, apodPix, scale, st)) != NB_OK) return rc;
-        return fft_cols_t<double>((const double2*)out, (double2*)out, B, H, Wc, -1, 1.0, st);
-    } else if (prec == NB_PREC_F32) {
-        if ((rc = rfft_rows_t<float>((const float*)in, (float2*)out, B, H, W, apodPix, scale, st)) != NB_OK) return rc;
-        return fft_cols_t<float>((const float2*)out, (float2*)out, B, H, Wc, -1, 1.0, st);
-    }
-    nb_set_error("nb_rfft2: bad precision %d", prec);
-    return NB_ERR_ARG;
+    if ((rc = rows_fwd(prec, in, out, B, H, W, apodPix, scale, st)) != NB_OK) return rc;
+    return cols_plain(prec, out, out, B, H, W / 2 + 1, -1, st);
 }
 
 int nb_irfft2(int prec, void* spec, void* out, int B, int H, int W, double scale, const double* norm,
               const unsigned char* mask, int maskDiv, cudaStream_t st) {
     NB_REQUIRE(spec && out && B > 0, NB_ERR_ARG, "nb_irfft2: bad arguments");
-    NB_REQUIRE(nb_fft_size_supported(H) && nb_fft_size_supported(W) && W >= 64, NB_ERR_UNSUPPORTED,
-               "nb_irfft2: tile %dx%d not supported (power-of-two sides, 64..4096)", H, W);
+    NB_REQUIRE(prec == NB_PREC_F64 || prec == NB_PREC_F32, NB_ERR_ARG, "nb_irfft2: bad precision %d", prec);
+    NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_irfft2: tile %dx%d not supported (sides 64..4096, even width)", H, W);
     int rc;
-    const int Wc = W / 2 + 1;
-    if (maskDiv < 1) maskDiv = 1;
-    if (prec == NB_PREC_F64) {
-        if ((rc = fft_cols_t<double>((const double2*)spec, (double2*)spec, B, H, Wc, +1, 1.0, st)) != NB_OK) return rc;
-        C2RParams<double> ep = {scale, norm, mask, maskDiv, nullptr};
-        return irfft_rows_t<double>((const double2*)spec, (double*)out, B, H, W, ep, st);
-    } else if (prec == NB_PREC_F32) {
-        if ((rc = fft_cols_t<float>((const float2*)spec, (float2*)spec, B, H, Wc, +1, 1.0, st)) != NB_OK) return rc;
-        C2RParams<float> ep = {(float)scale, norm, mask, maskDiv, nullptr};
-        return irfft_rows_t<float>((const float2*)spec, (float*)out, B, H, W, ep, st);
-    }
-    nb_set_error("nb_irfft2: bad precision %d", prec);
-    return NB_ERR_ARG;
+    if ((rc = cols_plain(prec, spec, spec, B, H, W / 2 + 1, +1, st)) != NB_OK) return rc;
+    return rows_inv(prec, spec, out, B, H, W, scale, norm, mask, maskDiv, nullptr, st);
 }
 
 int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratch, void* out, int nOut, int S, int perScale,
                     int F, int H, int W, double scale, const double* norm, const unsigned char* mask, cudaStream_t st) {
     NB_REQUIRE(fmaps && filtH && scratch && out && nOut > 0 && S > 0, NB_ERR_ARG, "nb_apply_filter: bad arguments");
+    NB_REQUIRE(prec == NB_PREC_F64 || prec == NB_PREC_F32, NB_ERR_ARG, "nb_apply_filter: bad precision %d", prec);
     NB_REQUIRE(F >= 1 && F <= NB_MAX_FREQ, NB_ERR_UNSUPPORTED, "nb_apply_filter: %d frequencies not supported (1..%d)", F, NB_MAX_FREQ);
-    NB_REQUIRE(nb_fft_size_supported(H) && nb_fft_size_supported(W) && W >= 64, NB_ERR_UNSUPPORTED,
-               "nb_apply_filter: tile %dx%d not supported (power-of-two sides, 64..4096)", H, W);
+    NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_apply_filter: tile %dx%d not supported (sides 64..4096, even width)", H, W);
     int rc;
     const int Wc = W / 2 + 1;
+    if (!is_pow2_side(H)) {
+        rc = nb_bs_cols_apply(prec, fmaps, filtH, scratch, nOut, S, perScale, F, H, Wc, st);
+    } else {
 #define APPLY_F(T, C2T, FF) \
     rc = fft_cols_apply_tf<T, FF>((const C2T*)fmaps, (const T*)filtH, (C2T*)scratch, nOut, S, perScale, H, Wc, st)
 #define APPLY_ALL(T, C2T)                   \
@@ -567,44 +586,36 @@ int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratc
         case 3: APPLY_F(T, C2T, 3); break;  \
         default: APPLY_F(T, C2T, 4); break; \
     }
-    if (prec == NB_PREC_F64) {
-        APPLY_ALL(double, double2)
-        if (rc != NB_OK) return rc;
-        C2RParams<double> ep = {scale, norm, mask, S, nullptr};
-        return irfft_rows_t<double>((const double2*)scratch, (double*)out, nOut, H, W, ep, st);
-    } else if (prec == NB_PREC_F32) {
-        APPLY_ALL(float, float2)
-        if (rc != NB_OK) return rc;
-        C2RParams<float> ep = {(float)scale, norm, mask, S, nullptr};
-        return irfft_rows_t<float>((const float2*)scratch, (float*)out, nOut, H, W, ep, st);
-    }
+        if (prec == NB_PREC_F64) {
+            APPLY_ALL(double, double2)
+        } else {
+            APPLY_ALL(float, float2)
+        }
 #undef APPLY_ALL
 #undef APPLY_F
-    nb_set_error("nb_apply_filter: bad precision %d", prec);
-    return NB_ERR_ARG;
+    }
+    if (rc != NB_OK) return rc;
+    return rows_inv(prec, scratch, out, nOut, H, W, scale, norm, mask, S, nullptr, st);
 }
 
 int nb_window_deconv(int prec, void* data, void* scratch, int B, int H, int W, const void* wy, const void* wx,
                      int restoreZeros, cudaStream_t st) {
     NB_REQUIRE(data && scratch && wy && wx && B > 0, NB_ERR_ARG, "nb_window_deconv: bad arguments");
-    NB_REQUIRE(nb_fft_size_supported(H) && nb_fft_size_supported(W) && W >= 64, NB_ERR_UNSUPPORTED,
-               "nb_window_deconv: tile %dx%d not supported (power-of-two sides, 64..4096)", H, W);
+    NB_REQUIRE(prec == NB_PREC_F64 || prec == NB_PREC_F32, NB_ERR_ARG, "nb_window_deconv: bad precision %d", prec);
+    NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_window_deconv: tile %dx%d not supported (sides 64..4096, even width)", H, W);
     int rc;
     const int Wc = W / 2 + 1;
     const double scale = 1.0 / ((double)H * (double)W);
-    if (prec == NB_PREC_F64) {
-        if ((rc = rfft_rows_t<double>((const double*)data, (double2*)scratch, B, H, W, 0, 1.0, st)) != NB_OK) return rc;
-        if ((rc = fft_cols_window_t<double>((double2*)scratch, B, H, Wc, (const double*)wy, (const double*)wx, st)) != NB_OK) return rc;
-        C2RParams<double> ep = {scale, nullptr, nullptr, 1, restoreZeros ? (const double*)data : nullptr};
-        return irfft_rows_t<double>((const double2*)scratch, (double*)data, B, H, W, ep, st);
-    } else if (prec == NB_PREC_F32) {
-        if ((rc = rfft_rows_t<float>((const float*)data, (float2*)scratch, B, H, W, 0, 1.0, st)) != NB_OK) return rc;
-        if ((rc = fft_cols_window_t<float>((float2*)scratch, B, H, Wc, (const float*)wy, (const float*)wx, st)) != NB_OK) return rc;
-        C2RParams<float> ep = {(float)scale, nullptr, nullptr, 1, restoreZeros ? (const float*)data : nullptr};
-        return irfft_rows_t<float>((const float2*)scratch, (float*)data, B, H, W, ep, st);
+    if ((rc = rows_fwd(prec, data, scratch, B, H, W, 0, 1.0, st)) != NB_OK) return rc;
+    if (!is_pow2_side(H)) {
+        rc = nb_bs_cols_window(prec, scratch, B, H, Wc, wy, wx, st);
+    } else if (prec == NB_PREC_F64) {
+        rc = fft_cols_window_t<double>((double2*)scratch, B, H, Wc, (const double*)wy, (const double*)wx, st);
+    } else {
+        rc = fft_cols_window_t<float>((float2*)scratch, B, H, Wc, (const float*)wy, (const float*)wx, st);
     }
-    nb_set_error("nb_window_deconv: bad precision %d", prec);
-    return NB_ERR_ARG;
+    if (rc != NB_OK) return rc;
+    return rows_inv(prec, scratch, data, B, H, W, scale, nullptr, nullptr, 1, restoreZeros ? data : nullptr, st);
 }
 
 }  // extern "C"

@@ -2,3 +2,14 @@
 #pragma once
 #include "common.cuh"
 #include "../../include/nemo_b200.h"
+
+// Bluestein passes for sides that are not powers of two (fft_bluestein.cu); same contracts as the power-of-two row / column
+// passes of fft_kernels.cu
+int nb_bs_length(int N);
+int nb_bs_rows_fwd(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st);
+int nb_bs_rows_inv(int prec, const void* in, void* out, int B, int H, int W, double scale, const double* norm, const unsigned char* mask,
+                   int maskDiv, const void* zeroRef, cudaStream_t st);
+int nb_bs_cols(int prec, const void* in, void* out, int B, int H, int Wc, int dir, cudaStream_t st);
+int nb_bs_cols_apply(int prec, const void* fmaps, const void* filt, void* out, int nOut, int S, int perScale, int F, int H, int Wc,
+                     cudaStream_t st);
+int nb_bs_cols_window(int prec, void* data, int B, int H, int Wc, const void* wy, const void* wx, cudaStream_t st);

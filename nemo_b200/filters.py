@@ -15,7 +15,8 @@ Differences a caller can see:
   * filter caches are FITS when astropy is importable, ``.npz`` with the same content otherwise;
   * options whose dependencies are absent raise instead of silently differing: noise methods ``model`` and
     ``max(dataMap,CMB)``, ``noiseModelCatalog``, ``noiseGridArcmin: smart``, ``RMSEstimator`` biweight/percentile,
-    ``reshapeFilter``; tiles must have power-of-two sides (64..4096).
+    ``reshapeFilter``; tile sides must lie in 64..4096 with an even width (sides that are not powers of two take the
+    slower Bluestein FFT passes).
 """
 
 import os

@@ -53,7 +53,9 @@ def test_library_is_built_for_sm_100a():
 
 def test_host_only_entry_points(lib):
     assert lib.nb_version() >= 100
-    assert lib.nb_fft_size_supported(1024) == 1 and lib.nb_fft_size_supported(1000) == 0 and lib.nb_fft_size_supported(8192) == 0
+    # 1 = power of two (direct passes), 2 = any other side in 64..4096 (Bluestein passes), 0 = unsupported
+    assert lib.nb_fft_size_supported(1024) == 1 and lib.nb_fft_size_supported(1000) == 2 and lib.nb_fft_size_supported(1031) == 2
+    assert lib.nb_fft_size_supported(8192) == 0 and lib.nb_fft_size_supported(48) == 0
     assert lib.nb_label4_scratch_ints(2, 64, 64) >= 2 * 64 * 64
     assert lib.nb_launch_count() == 0      # nothing has been launched: no GPU work happens in the CPU suite
 
@@ -62,8 +64,10 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     rc = lib.nb_rfft2(0, None, None, 1, 64, 64, 0, 1.0, None)
     assert rc < 0 and b'bad arguments' in lib.nb_last_error()
     buf = ctypes.c_void_p(16)
-    rc = lib.nb_rfft2(0, buf, buf, 1, 100, 64, 0, 1.0, None)
+    rc = lib.nb_rfft2(0, buf, buf, 1, 100, 101, 0, 1.0, None)      # odd width
     assert rc == -3 and b'not supported' in lib.nb_last_error()
+    rc = lib.nb_rfft2(0, buf, buf, 1, 5000, 64, 0, 1.0, None)
+    assert rc == -3
 
 
 def test_product_path_fails_loudly_without_cuda():

@@ -344,3 +344,21 @@ def test_fp32_storage_mode_against_fp64_oracle(report):
     assert len(gotCat) == len(refCat) and len(refCat) >= 3
     for a, b in zip(gotCat.toRows(), refCat):
         assert abs(a['x'] - b['x']) < 0.01 and abs(a['y'] - b['y']) < 0.01 and abs(a['SNR'] - b['SNR']) < 1e-3 * abs(b['SNR'])
+
+
+def test_non_power_of_two_tile_end_to_end(report):
+    """A 300 x 420 tile (real Nemo tiles are not powers of two, e.g. 1440 x 840): the whole path against the oracle."""
+    from nemo_b200 import filters, photometry
+    mapDicts, truth = synth.makeTile(shape=(300, 420), freqsGHz=(97.8, 149.6), noiseUK=(60.0, 40.0), beamFWHMArcmin=(2.2, 1.4),
+                                     numObjects=8, kind='clusters', cmb=True, seed=41, margin=50)
+    f = _arnaud('Arnaud_M2e14_z0p4', 2e14, 0.4, grid=20.)
+    ref, refObj = filters_ref.filterMaps(mapDicts, _copyFilter(f), 'T0', returnFilter=True)
+    got, gotObj = filters.filterMaps(mapDicts, _copyFilter(f), 'T0', verbose=False, returnFilter=True)
+    _compareMaps(got, ref, report, "arnaud_F2_300x420")
+    assert abs(gotObj.signalNorm / refObj.signalNorm - 1) < 1e-8
+    refCat = photometry_ref.findObjects(ref, **DETECT)
+    photometry_ref.measureFluxes(refCat, ref, None)
+    gotCat = photometry.findObjects(got, **DETECT)
+    photometry.measureFluxes(gotCat, got, None)
+    assert len(refCat) >= 3
+    _compareCatalogs(gotCat, refCat, ['SNR', 'y_c', 'err_y_c', 'deltaT_c'])
