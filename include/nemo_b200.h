@@ -12,7 +12,8 @@
  *   - prec selects the arithmetic/storage type T of maps and spectra: NB_PREC_F32 (0) or NB_PREC_F64 (1);
  *     covariances, filters-in-full-plane, reductions, tables and spline evaluations are always fp64;
  *   - real maps are [B, H, W]; half spectra are [B, H, Wc] complex(T) with Wc = W/2 + 1;
- *   - H and W must be powers of two in 64..4096 for the FFT entry points (NB_ERR_UNSUPPORTED otherwise);
+ *   - for the FFT entry points H and W must lie in 64..4096 and W must be even (NB_ERR_UNSUPPORTED otherwise); sides that
+ *     are powers of two take direct passes, any other side exact Bluestein passes (nb_fft_size_supported: 1 / 2 / 0);
  *   - every call is asynchronous on `stream` and returns 0 on success or a negative NB_ERR_* code, with a
  *     message available from nb_last_error() (thread-local).
  */
