@@ -100,9 +100,9 @@ int nb_template_norm(int prec, const void* map, int B, int H, int W, int mode, d
 
 /* fRelWeights (nemo/filters.py:664-670): value at pixel idx[b] of each frequency plane of
  * Re(ifft_unnormalised(fmaps[m(b), f] * filtH[b, f])); m(b) = b when S == 0, else b % S (S template spectra shared
- * by all tiles); out [B, F] fp64. */
+ * by all tiles); out [B, F] fp64; scratch: B * F * 16 doubles. */
 int nb_plane_values_at(int prec, const void* fmaps, const void* filtH, const long long* idx, double* out, int B,
-                       int S, int F, int H, int W, cudaStream_t stream);
+                       int S, int F, int H, int W, double* scratch, cudaStream_t stream);
 
 /* Per-pixel median over frequencies of the weight maps (nemo/filters.py:360-363). */
 int nb_median_weights(int prec, const void* weights, void* out, int B, int F, int H, int W, cudaStream_t stream);

@@ -37,7 +37,7 @@ _PROTOTYPES = {
     "nb_build_filter": [c_int, c_ptr, c_ptr, ctypes.POINTER(c_dbl), c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr],
     "nb_fold_filter": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr],
     "nb_template_norm": [c_int, c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
-    "nb_plane_values_at": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr],
+    "nb_plane_values_at": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr],
     "nb_median_weights": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
     "nb_cell_rms": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int), c_int,
                     c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],

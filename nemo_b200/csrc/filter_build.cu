@@ -318,29 +318,50 @@ __global__ void __launch_bounds__(64) template_norm_kernel(const T* __restrict__
 }
 
 // value at one pixel (py, px) of Re(sum over the full plane of G(k) e^{+2 pi i k.p / N}) for a Hermitian G given
-// on the half plane: columns 0 and W/2 count once, the others twice.  One CTA per (frequency, image).
+// on the half plane: columns 0 and W/2 count once, the others twice.  The phase separates, exp(i a ky) exp(i b kx): the
+// column factors (with the 1 / 2 weights) are tabulated once per CTA in shared memory, the row factor once per row.
+// PV_CHUNKS CTAs per (frequency, image) each take a band of rows; a second kernel adds the partial sums in a fixed order.
+#define PV_CHUNKS 16
+
 template <typename T>
-__global__ void __launch_bounds__(256) plane_values_kernel(const typename V2<T>::type* __restrict__ fmaps,
-                                                           const T* __restrict__ filtH, const long long* __restrict__ idx,
-                                                           double* __restrict__ out, int F, int H, int W, int S) {
+__global__ void __launch_bounds__(256) plane_values_partial_kernel(const typename V2<T>::type* __restrict__ fmaps,
+                                                                   const T* __restrict__ filtH, const long long* __restrict__ idx,
+                                                                   double* __restrict__ partial, int F, int H, int W, int S) {
     typedef typename V2<T>::type C2;
-    const int f = blockIdx.x, b = blockIdx.y;
+    extern __shared__ double s_col[];   // [Wc][2]: weight * (cos, sin) of 2 pi kx px / W
+    const int chunk = blockIdx.x, f = blockIdx.y, b = blockIdx.z;
     const int Wc = W / 2 + 1;
     const long long p = idx[b];
     const int py = (int)(p / W), px = (int)(p % W);
     const size_t base = ((size_t)b * F + f) * H * Wc;                        // filter of image b
     const size_t mbase = ((size_t)(S > 0 ? b % S : b) * F + f) * H * Wc;    // its template spectrum
-    double acc = 0;
-    for (long long i = threadIdx.x; i < (long long)H * Wc; i += blockDim.x) {
-        const int ky = (int)(i / Wc), kx = (int)(i % Wc);
-        const C2 v = fmaps[mbase + i];
-        const double gr = (double)v.x * (double)filtH[base + i], gi = (double)v.y * (double)filtH[base + i];
-        // phase 2 pi (ky py / H + kx px / W), reduced exactly in integers before the division
-        const double ph = 2.0 * ((double)(((long long)ky * py) % H) / (double)H + (double)(((long long)kx * px) % W) / (double)W);
+    for (int kx = threadIdx.x; kx < Wc; kx += blockDim.x) {
+        // phase reduced exactly in integers before the division
         double sn, cs;
-        sincospi(ph, &sn, &cs);
-        const double term = gr * cs - gi * sn;
-        acc += (kx == 0 || kx == W / 2) ? term : 2.0 * term;
+        sincospi(2.0 * (double)(((long long)kx * px) % W) / (double)W, &sn, &cs);
+        const double wgt = (kx == 0 || 2 * kx == W) ? 1.0 : 2.0;
+        s_col[2 * kx] = wgt * cs;
+        s_col[2 * kx + 1] = wgt * sn;
+    }
+    __syncthreads();
+    const int rows = (H + PV_CHUNKS - 1) / PV_CHUNKS;
+    const int ky0 = chunk * rows, ky1 = min(ky0 + rows, H);
+    double acc = 0;
+    for (int ky = ky0; ky < ky1; ++ky) {
+        double rs, rc;
+        sincospi(2.0 * (double)(((long long)ky * py) % H) / (double)H, &rs, &rc);
+        const C2* fm = fmaps + mbase + (size_t)ky * Wc;
+        const T* fl = filtH + base + (size_t)ky * Wc;
+        double rowRe = 0, rowIm = 0;     // sum over kx of G * colFactor
+        for (int kx = threadIdx.x; kx < Wc; kx += blockDim.x) {
+            const C2 v = fm[kx];
+            const double g = (double)fl[kx];
+            const double gr = (double)v.x * g, gi = (double)v.y * g;
+            const double cr = s_col[2 * kx], ci = s_col[2 * kx + 1];
+            rowRe += gr * cr - gi * ci;
+            rowIm += gr * ci + gi * cr;
+        }
+        acc += rowRe * rc - rowIm * rs;   // real part of (row sum) * exp(i phase_y)
     }
     __shared__ double s[8];
     acc = warp_sum(acc);
@@ -349,8 +370,16 @@ __global__ void __launch_bounds__(256) plane_values_kernel(const typename V2<T>:
     if (threadIdx.x == 0) {
         double t = 0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s[i];
-        out[(size_t)b * F + f] = t;
+        partial[((size_t)b * F + f) * PV_CHUNKS + chunk] = t;
     }
+}
+
+__global__ void plane_values_sum_kernel(const double* __restrict__ partial, double* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double t = 0;
+    for (int c = 0; c < PV_CHUNKS; ++c) t += partial[(size_t)i * PV_CHUNKS + c];
+    out[i] = t;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -467,16 +496,21 @@ int nb_template_norm(int prec, const void* map, int B, int H, int W, int mode, d
 }
 
 int nb_plane_values_at(int prec, const void* fmaps, const void* filtH, const long long* idx, double* out, int B, int S,
-                       int F, int H, int W, cudaStream_t st) {
-    NB_REQUIRE(fmaps && filtH && idx && out && B > 0 && F > 0, NB_ERR_ARG, "nb_plane_values_at: bad arguments");
-    if (prec == NB_PREC_F64)
-        { NB_PROF_BEGIN(st); plane_values_kernel<double><<<dim3(F, B), 256, 0, st>>>((const double2*)fmaps, (const double*)filtH, idx, out, F, H, W, S); NB_PROF_END("plane_values_kernel", st); }
-    else if (prec == NB_PREC_F32)
-        { NB_PROF_BEGIN(st); plane_values_kernel<float><<<dim3(F, B), 256, 0, st>>>((const float2*)fmaps, (const float*)filtH, idx, out, F, H, W, S); NB_PROF_END("plane_values_kernel", st); }
-    else {
+                       int F, int H, int W, double* scratch, cudaStream_t st) {
+    NB_REQUIRE(fmaps && filtH && idx && out && scratch && B > 0 && F > 0, NB_ERR_ARG, "nb_plane_values_at: bad arguments");
+    const size_t smem = sizeof(double) * 2 * (size_t)(W / 2 + 1);
+    NB_REQUIRE(smem <= 48 * 1024, NB_ERR_UNSUPPORTED, "nb_plane_values_at: tile too wide");
+    dim3 grid(PV_CHUNKS, F, B);
+    if (prec == NB_PREC_F64) {
+        { NB_PROF_BEGIN(st); plane_values_partial_kernel<double><<<grid, 256, smem, st>>>((const double2*)fmaps, (const double*)filtH, idx, scratch, F, H, W, S); NB_PROF_END("plane_values_partial_kernel", st); }
+    } else if (prec == NB_PREC_F32) {
+        { NB_PROF_BEGIN(st); plane_values_partial_kernel<float><<<grid, 256, smem, st>>>((const float2*)fmaps, (const float*)filtH, idx, scratch, F, H, W, S); NB_PROF_END("plane_values_partial_kernel", st); }
+    } else {
         nb_set_error("nb_plane_values_at: bad precision %d", prec);
         return NB_ERR_ARG;
     }
+    NB_CHECK_LAUNCH();
+    { NB_PROF_BEGIN(st); plane_values_sum_kernel<<<(B * F + 255) / 256, 256, 0, st>>>(scratch, out, B * F); NB_PROF_END("plane_values_sum_kernel", st); }
     NB_CHECK_LAUNCH();
     return NB_OK;
 }

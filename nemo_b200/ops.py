@@ -197,8 +197,10 @@ class Ops(object):
         self._check(filtH, self.dtype, 'filtH')
         B, F, H, Wc = filtH.shape
         out = self.empty((B, F), self.torch.float64)
-        _lib.call('nb_plane_values_at', self.prec, _ptr(fmaps), _ptr(filtH), _ptr(idx), _ptr(out), B, int(S), F, H, (Wc - 1) * 2, self._stream())
-        self.launches += 1
+        scratch = self.empty((B * F * 16,), self.torch.float64)
+        _lib.call('nb_plane_values_at', self.prec, _ptr(fmaps), _ptr(filtH), _ptr(idx), _ptr(out), B, int(S), F, H, (Wc - 1) * 2,
+                  _ptr(scratch), self._stream())
+        self.launches += 2
         return out
 
     # -- noise, S/N -------------------------------------------------------------------------------------
