@@ -8,18 +8,24 @@
 
 // ------------------------------------------------------------------------------------------------------
 // K12 row pass: one CTA per row, the row staged in shared memory as fp64
-template <typename T>
-__global__ void __launch_bounds__(256) gauss_rows_kernel(const T* in, T* out, int W, GaussW g) {
-    extern __shared__ double s_row[];
+template <typename T, bool WIDE>
+__global__ void __launch_bounds__(256) gauss_rows_kernel(const T* in, T* out, int W, GaussW g, double sigma, int rWide) {
+    extern __shared__ double s_row[];   // [W] (+ [2 r + 1] weights when WIDE)
+    const int r = WIDE ? rWide : g.r;
+    const double* wts = g.w;
+    if (WIDE) {
+        gauss_weights_smem(s_row + W, sigma, r);
+        wts = s_row + W;
+    }
     const size_t base = (size_t)blockIdx.x * W;
     for (int x = threadIdx.x; x < W; x += blockDim.x) s_row[x] = (double)in[base + x];
     __syncthreads();
     for (int x = threadIdx.x; x < W; x += blockDim.x) {
         double acc = 0;
-        if (x >= g.r && x + g.r < W) {
-            for (int d = -g.r; d <= g.r; ++d) acc += g.w[d + g.r] * s_row[x + d];
+        if (x >= r && x + r < W) {
+            for (int d = -r; d <= r; ++d) acc += wts[d + r] * s_row[x + d];
         } else {
-            for (int d = -g.r; d <= g.r; ++d) acc += g.w[d + g.r] * s_row[reflect_idx(x + d, W)];
+            for (int d = -r; d <= r; ++d) acc += wts[d + r] * s_row[reflect_idx(x + d, W)];
         }
         out[base + x] = (T)acc;
     }
@@ -28,26 +34,34 @@ __global__ void __launch_bounds__(256) gauss_rows_kernel(const T* in, T* out, in
 // K12 column pass: 32 columns x 64 rows per CTA with a reflected halo; out = subtract ? ref - smooth : smooth
 #define GC_TX 32
 #define GC_TY 64
-template <typename T>
+// TX columns per CTA: 32, or fewer when a wide halo would not fit shared memory otherwise
+template <typename T, int TX, bool WIDE>
 __global__ void __launch_bounds__(256) gauss_cols_kernel(const T* __restrict__ in, const T* ref, T* out, int H, int W, GaussW g,
-                                                         int subtract) {
-    extern __shared__ double s_t[];
-    const int x0 = blockIdx.x * GC_TX, y0 = blockIdx.y * GC_TY;
+                                                         int subtract, double sigma, int rWide) {
+    extern __shared__ double s_t[];     // [(GC_TY + 2 r)][TX] (+ [2 r + 1] weights when WIDE)
+    const int r = WIDE ? rWide : g.r;
+    const int rows = GC_TY + 2 * r;
+    const double* wts = g.w;
+    if (WIDE) {
+        gauss_weights_smem(s_t + (size_t)rows * TX, sigma, r);
+        wts = s_t + (size_t)rows * TX;
+    }
+    constexpr int TYS = 256 / TX;       // thread rows
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * GC_TY;
     const size_t plane = (size_t)blockIdx.z * H * W;
-    const int tx = threadIdx.x % GC_TX, ty = threadIdx.x / GC_TX;
-    const int rows = GC_TY + 2 * g.r;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int x = x0 + tx;
-    for (int i = ty; i < rows; i += 8) {
-        const int y = reflect_idx(y0 - g.r + i, H);
-        s_t[i * GC_TX + tx] = (x < W) ? (double)in[plane + (size_t)y * W + x] : 0.0;
+    for (int i = ty; i < rows; i += TYS) {
+        const int y = reflect_idx(y0 - r + i, H);
+        s_t[i * TX + tx] = (x < W) ? (double)in[plane + (size_t)y * W + x] : 0.0;
     }
     __syncthreads();
     if (x >= W) return;
-    for (int i = ty; i < GC_TY; i += 8) {
+    for (int i = ty; i < GC_TY; i += TYS) {
         const int y = y0 + i;
         if (y >= H) break;
         double acc = 0;
-        for (int d = 0; d <= 2 * g.r; ++d) acc += g.w[d] * s_t[(i + d) * GC_TX + tx];
+        for (int d = 0; d <= 2 * r; ++d) acc += wts[d] * s_t[(i + d) * TX + tx];
         const size_t o = plane + (size_t)y * W + x;
         // scipy rounds the smoothed map to the array dtype before maps.subtractBackground subtracts it
         out[o] = subtract ? (T)(ref[o] - (T)acc) : (T)acc;
@@ -127,40 +141,81 @@ __global__ void __launch_bounds__(256) sub_kernel(const T* a, const T* b, T* o, 
     if (i < n) o[i] = a[i] - b[i];
 }
 
+
+
+template <typename T, bool WIDE>
+static int gauss_cols_launch(const T* in, T* out, int B, int H, int W, const GaussW& g, double sigma, int r, cudaStream_t st) {
+    const size_t extra = WIDE ? sizeof(double) * (2 * (size_t)r + 1) : 0;
+    const int rows = GC_TY + 2 * r;
+#define GC_LAUNCH(TX)                                                                                                          \
+    {                                                                                                                          \
+        const size_t smem = (size_t)rows * TX * sizeof(double) + extra;                                                        \
+        if (smem <= 220 * 1024) {                                                                                              \
+            if (smem > 48 * 1024)                                                                                              \
+                NB_CHECK_CUDA(cudaFuncSetAttribute(gauss_cols_kernel<T, TX, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            dim3 grid((W + TX - 1) / TX, (H + GC_TY - 1) / GC_TY, B);                                                          \
+            { NB_PROF_BEGIN(st); gauss_cols_kernel<T, TX, WIDE><<<grid, 256, smem, st>>>(in, nullptr, out, H, W, g, 0, sigma, r); NB_PROF_END("gauss_cols_kernel", st); } \
+            NB_CHECK_LAUNCH();                                                                                                 \
+            return NB_OK;                                                                                                      \
+        }                                                                                                                      \
+    }
+    GC_LAUNCH(32)
+    GC_LAUNCH(16)
+    GC_LAUNCH(8)
+#undef GC_LAUNCH
+    nb_set_error("nb_gauss_filter: smoothing radius %d too large", r);
+    return NB_ERR_UNSUPPORTED;
+}
+
+template <typename T, bool WIDE>
+static int gauss_rows_launch(const T* in, T* out, int B, int H, int W, const GaussW& g, double sigma, int r, cudaStream_t st) {
+    const size_t smem = sizeof(double) * ((size_t)W + (WIDE ? 2 * (size_t)r + 1 : 0));
+    if (smem > 48 * 1024)
+        NB_CHECK_CUDA(cudaFuncSetAttribute(gauss_rows_kernel<T, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { NB_PROF_BEGIN(st); gauss_rows_kernel<T, WIDE><<<(unsigned)((size_t)B * H), 256, smem, st>>>(in, out, W, g, sigma, r); NB_PROF_END("gauss_rows_kernel", st); }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
+template <typename T>
+static int gauss_filter_t(const T* in, T* tmp, T* out, int B, int H, int W, double sigmaY, double sigmaX, int subtract, cudaStream_t st) {
+    // scipy filters axis 0 (y) first, then axis 1 (x); each pass rounds to the array dtype
+    const int ry = gauss_radius(sigmaY), rx = gauss_radius(sigmaX);
+    NB_REQUIRE(ry <= 4096 && rx <= 4096, NB_ERR_UNSUPPORTED, "nb_gauss_filter: smoothing scale too large");
+    GaussW gy, gx;
+    gy.r = gx.r = 0;
+    int rc;
+    if (ry <= NB_GAUSS_MAXR) {
+        if ((rc = make_gauss(sigmaY, &gy)) != NB_OK) return rc;
+        rc = gauss_cols_launch<T, false>(in, tmp, B, H, W, gy, sigmaY, ry, st);
+    } else {
+        rc = gauss_cols_launch<T, true>(in, tmp, B, H, W, gy, sigmaY, ry, st);
+    }
+    if (rc != NB_OK) return rc;
+    T* rowsOut = subtract ? tmp : out;
+    if (rx <= NB_GAUSS_MAXR) {
+        if ((rc = make_gauss(sigmaX, &gx)) != NB_OK) return rc;
+        rc = gauss_rows_launch<T, false>(tmp, rowsOut, B, H, W, gx, sigmaX, rx, st);
+    } else {
+        rc = gauss_rows_launch<T, true>(tmp, rowsOut, B, H, W, gx, sigmaX, rx, st);
+    }
+    if (rc != NB_OK) return rc;
+    if (subtract) {
+        const long long n = (long long)B * H * W;
+        { NB_PROF_BEGIN(st); sub_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, (const T*)tmp, out, n); NB_PROF_END("sub_kernel", st); }
+        NB_CHECK_LAUNCH();
+    }
+    return NB_OK;
+}
+
 extern "C" {
 
 int nb_gauss_filter(int prec, const void* in, void* tmp, void* out, int B, int H, int W, double sigmaY, double sigmaX,
                     int subtract, cudaStream_t st) {
     NB_REQUIRE(in && tmp && out && B > 0 && sigmaY > 0 && sigmaX > 0, NB_ERR_ARG, "nb_gauss_filter: bad arguments");
-    GaussW gy, gx;
-    int rc;
-    if ((rc = make_gauss(sigmaY, &gy)) != NB_OK) return rc;
-    if ((rc = make_gauss(sigmaX, &gx)) != NB_OK) return rc;
     NB_REQUIRE(W <= 16384, NB_ERR_UNSUPPORTED, "nb_gauss_filter: tile too wide");
-    const size_t smemC = (size_t)(GC_TY + 2 * gy.r) * GC_TX * sizeof(double);
-    const long long n = (long long)B * H * W;
-    dim3 gridC((W + GC_TX - 1) / GC_TX, (H + GC_TY - 1) / GC_TY, B);
-#define GAUSS(T)                                                                                                          \
-    {                                                                                                                     \
-        if (smemC > 48 * 1024)                                                                                            \
-            NB_CHECK_CUDA(cudaFuncSetAttribute(gauss_cols_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC)); \
-        /* scipy filters axis 0 (y) first, then axis 1 (x); each pass rounds to the array dtype */                        \
-        { NB_PROF_BEGIN(st); gauss_cols_kernel<T><<<gridC, 256, smemC, st>>>((const T*)in, nullptr, (T*)tmp, H, W, gy, 0); NB_PROF_END("gauss_cols_kernel", st); }                     \
-        NB_CHECK_LAUNCH();                                                                                                \
-        if (!subtract) {                                                                                                  \
-            { NB_PROF_BEGIN(st); gauss_rows_kernel<T><<<(unsigned)((size_t)B * H), 256, sizeof(double) * W, st>>>((const T*)tmp, (T*)out, W, gx); NB_PROF_END("gauss_rows_kernel", st); } \
-            NB_CHECK_LAUNCH();                                                                                            \
-        } else {                                                                                                          \
-            { NB_PROF_BEGIN(st); gauss_rows_kernel<T><<<(unsigned)((size_t)B * H), 256, sizeof(double) * W, st>>>((const T*)tmp, (T*)tmp, W, gx); NB_PROF_END("gauss_rows_kernel", st); } \
-            NB_CHECK_LAUNCH();                                                                                            \
-            { NB_PROF_BEGIN(st); sub_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)in, (const T*)tmp, (T*)out, n); NB_PROF_END("sub_kernel", st); }          \
-            NB_CHECK_LAUNCH();                                                                                            \
-        }                                                                                                                 \
-        return NB_OK;                                                                                                     \
-    }
-    if (prec == NB_PREC_F64) GAUSS(double)
-    if (prec == NB_PREC_F32) GAUSS(float)
-#undef GAUSS
+    if (prec == NB_PREC_F64) return gauss_filter_t<double>((const double*)in, (double*)tmp, (double*)out, B, H, W, sigmaY, sigmaX, subtract, st);
+    if (prec == NB_PREC_F32) return gauss_filter_t<float>((const float*)in, (float*)tmp, (float*)out, B, H, W, sigmaY, sigmaX, subtract, st);
     nb_set_error("nb_gauss_filter: bad precision %d", prec);
     return NB_ERR_ARG;
 }

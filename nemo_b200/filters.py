@@ -597,21 +597,51 @@ class RealSpaceMatchedFilter(MapFilter):
 
 
 # -------------------------------------------------------------------------------------------------------------
+# Signal templates are host-made inputs of the hot path and depend only on the tile geometry (shape and central pixel
+# scales), the beam and the model parameters -- not on the map.  The reference paints them afresh for every tile and
+# filter (~0.1 s each with the beam convolution); tiles that share a geometry reuse them here.  Entries are read-only.
+_TEMPLATE_CACHE = {}
+_TEMPLATE_CACHE_MAX = 64
+
+
+def _beamKey(beam):
+    if isinstance(beam, str):
+        return ('file', beam, os.path.getmtime(beam) if os.path.exists(beam) else None)
+    import hashlib
+    return ('profile', hashlib.sha1(np.ascontiguousarray(beam.rDeg).tobytes() + np.ascontiguousarray(beam.profile1d).tobytes()).hexdigest())
+
+
+def _cachedTemplate(key, make):
+    hit = _TEMPLATE_CACHE.get(key)
+    if hit is None:
+        hit = np.asarray(make())
+        hit.setflags(write=False)
+        if len(_TEMPLATE_CACHE) >= _TEMPLATE_CACHE_MAX:
+            _TEMPLATE_CACHE.pop(next(iter(_TEMPLATE_CACHE)))
+        _TEMPLATE_CACHE[key] = hit
+    return hit
+
+
 class BeamFilter(MapFilter):
     """Templates from ACT-style beam profiles (filters.py:1222-1233)."""
 
     def makeSignalTemplateMap(self, beamFileName, amplitude=None):
-        return signals.makeBeamModelSignalMap(np.degrees(self.radiansMap), self.wcs, beamFileName, amplitude=amplitude)
+        key = ('beam', tuple(self.shape), self.degPerPixX, self.degPerPixY, _beamKey(beamFileName), amplitude)
+        return _cachedTemplate(key, lambda: signals.makeBeamModelSignalMap(np.degrees(self.radiansMap), self.wcs, beamFileName,
+                                                                           amplitude=amplitude))
 
 
 class ArnaudModelFilter(MapFilter):
     """Templates from the Arnaud et al. (2010) GNFW profile (filters.py:1236-1252)."""
 
     def makeSignalTemplateMap(self, beamFileName, amplitude=None):
-        return signals.makeArnaudModelSignalMap(self.params['z'], self.params['M500MSun'], np.degrees(self.radiansMap),
-                                                self.wcs, beam=beamFileName,
-                                                GNFWParams=self.params.get('GNFWParams', 'default'),
-                                                amplitude=amplitude, convolveWithBeam=True)
+        gnfw = self.params.get('GNFWParams', 'default')
+        key = ('arnaud', self.params['z'], self.params['M500MSun'], repr(gnfw), tuple(self.shape), self.degPerPixX, self.degPerPixY,
+               _beamKey(beamFileName), amplitude)
+        return _cachedTemplate(key, lambda: signals.makeArnaudModelSignalMap(self.params['z'], self.params['M500MSun'],
+                                                                             np.degrees(self.radiansMap), self.wcs, beam=beamFileName,
+                                                                             GNFWParams=gnfw, amplitude=amplitude,
+                                                                             convolveWithBeam=True))
 
 
 class BattagliaModelFilter(MapFilter):

@@ -559,8 +559,10 @@ def test_spline_eval_f64(ops64, report):
     assert err < 1e-11
 
 
-@pytest.mark.parametrize("sig", [(3.0, 3.0), (7.3, 11.9), (1.0, 25.0)])
+@pytest.mark.parametrize("sig", [(3.0, 3.0), (7.3, 11.9), (1.0, 25.0), (48.0, 82.0), (130.0, 5.0)])
 def test_gauss_filter_f64(ops64, report, sig):
+    """Radii up to 127 pass scipy's weights as a kernel argument; wider ones (background-subtraction scales of tens of
+    pixels, radius 4 sigma) tabulate them in shared memory -- the reflect boundary then folds more than once."""
     rng = np.random.default_rng(15)
     x = rng.standard_normal((2, 200, 330))
     ref = np.array([ndimage.gaussian_filter(a, sig) for a in x])
@@ -569,7 +571,7 @@ def test_gauss_filter_f64(ops64, report, sig):
     err = _relerr(got, ref)
     err2 = _relerr(got2, x - ref)
     report("gauss_filter", sig=sig, relerr=err, relerr_sub=err2)
-    assert err < 1e-13 and err2 < 1e-13
+    assert err < 1e-12 and err2 < 1e-12
 
 
 @pytest.mark.parametrize("k", [(29, 29), (5, 7), (1, 1), (63, 3)])
