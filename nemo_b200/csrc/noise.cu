@@ -1161,11 +1161,19 @@ __global__ void __launch_bounds__(256) edge_rows_kernel(const T* __restrict__ ma
     __syncthreads();
     const int lo = -(trim / 2), hi = trim - 1 - trim / 2;
     unsigned char* out = rowAny + ((size_t)img * H + y) * W;
+    // zeros among the virtual positions [0, n) of the reflected row (d c b a | a b c d | d c b a ...), period 2 W; a window
+    // wider than the row folds more than once, as scipy's 'reflect' does
+    auto ext = [&](int n) -> int {
+        const int full = n / (2 * W), r = n - full * 2 * W;
+        const int part = (r <= W) ? s_pre[r] : s_pre[W] + (s_pre[W] - s_pre[2 * W - r]);
+        return full * 2 * s_pre[W] + part;
+    };
     for (int x = threadIdx.x; x < W; x += blockDim.x) {
         const int a = x + lo, b = x + hi;
-        int cnt = s_pre[min(b, W - 1) + 1] - s_pre[max(a, 0)];
-        if (a < 0) cnt += s_pre[-a];                        // indices a..-1 reflect onto 0..-a-1
-        if (b >= W) cnt += s_pre[W] - s_pre[2 * W - 1 - b];  // indices W..b reflect onto 2W-1-b..W-1
+        int cnt;
+        if (a >= 0) cnt = ext(b + 1) - ext(a);
+        else if (b < 0) cnt = ext(-a) - ext(-b - 1);     // position -k mirrors position k - 1
+        else cnt = ext(-a) + ext(b + 1);
         out[x] = cnt > 0 ? 1 : 0;
     }
 }
@@ -1346,7 +1354,7 @@ int nb_snr_mask(int prec, void* map, void* rms, const unsigned char* psMask, con
                 cudaStream_t st) {
     NB_REQUIRE(map && rms && psMask && surveyMask && sn && maskOut && nImg > 0 && S > 0, NB_ERR_ARG, "nb_snr_mask: bad arguments");
     NB_REQUIRE(trimPix == 0 || scratch, NB_ERR_ARG, "nb_snr_mask: scratch required when trimPix > 0");
-    NB_REQUIRE(trimPix >= 0 && trimPix <= H && trimPix <= W, NB_ERR_UNSUPPORTED, "nb_snr_mask: trimPix %d larger than the tile", trimPix);
+    NB_REQUIRE(trimPix >= 0, NB_ERR_ARG, "nb_snr_mask: negative trimPix %d", trimPix);
     NB_REQUIRE(W <= 8192, NB_ERR_UNSUPPORTED, "nb_snr_mask: tile too wide");
     if (prec == NB_PREC_F64)
         return snr_mask_t<double>(map, rms, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st);
@@ -1363,7 +1371,7 @@ int nb_snr_mask_cells(int prec, void* map, const void* wmed, const double* table
     NB_REQUIRE(map && wmed && table && edges && yChunks && xChunks && psMask && surveyMask && sn && rmsOut && maskOut && nImg > 0 && S > 0,
                NB_ERR_ARG, "nb_snr_mask_cells: bad arguments");
     NB_REQUIRE(trimPix == 0 || scratch, NB_ERR_ARG, "nb_snr_mask_cells: scratch required when trimPix > 0");
-    NB_REQUIRE(trimPix >= 0 && trimPix <= H && trimPix <= W, NB_ERR_UNSUPPORTED, "nb_snr_mask_cells: trimPix %d larger than the tile", trimPix);
+    NB_REQUIRE(trimPix >= 0, NB_ERR_ARG, "nb_snr_mask_cells: negative trimPix %d", trimPix);
     NB_REQUIRE(W <= 8192, NB_ERR_UNSUPPORTED, "nb_snr_mask_cells: tile too wide");
     NB_REQUIRE(ny > 0 && nx > 0 && ny <= NB_MAX_CHUNKS && nx <= NB_MAX_CHUNKS, NB_ERR_UNSUPPORTED, "nb_snr_mask_cells: bad noise grid");
     Chunks ch;

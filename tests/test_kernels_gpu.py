@@ -324,7 +324,7 @@ def test_cell_rms_f32(ops32, report, numBins, gridArcmin):
     assert err < 1e-6
 
 
-@pytest.mark.parametrize("trim,realSpace", [(0, False), (24, False), (31, True), (120, False)])
+@pytest.mark.parametrize("trim,realSpace", [(0, False), (24, False), (31, True), (120, False), (300, False), (700, False)])
 def test_snr_mask_f64(ops64, report, trim, realSpace):
     rng = np.random.default_rng(12)
     H, W = 256, 320
