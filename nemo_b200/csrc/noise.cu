@@ -506,6 +506,9 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
         return;
     }
     const long long nGood = (long long)cnt;
+#if defined(OC_EXP_STOP) && OC_EXP_STOP == 1
+    if (nGood >= 0) { if (tid == 0) tab[0] = (double)nGood; return; }
+#endif
 
     // ---- bin edges: np.percentile(weights[good], b * 100 / numBins), max + 1e-6  (filters.py:450-454) -----------
     if (tid == 0) {
@@ -767,6 +770,9 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     }
     __syncthreads();
     for (int b = tid; b <= numBins; b += OC_THREADS) edg[b] = s_edges[b];
+#if defined(OC_EXP_STOP) && OC_EXP_STOP == 2
+    if (nGood >= 0) return;
+#endif
 
     // ---- bin index of every good pixel, then the slots take the pixel values -----------------------------------
     // edges ascend and edges[0] <= w < edges[numBins] for every good pixel, so the bin with edges[b] <= w < edges[b + 1]
