@@ -87,6 +87,11 @@ int nb_xpower_smooth(int prec, const void* fmaps, double* cov, double* tmp, int 
 int nb_build_filter(int prec, const double* cov, const void* fsig, const double* w, double* filtFull, void* filtH,
                     int nOut, int S, int sigPerTile, int F, int H, int W, cudaStream_t stream);
 
+/* K2 + K3 in one kernel: the filters of nOut / S tiles at S scales straight from the map spectra, the smoothed covariance
+ * staying in shared memory (no cov / tmp arrays).  Arguments as nb_xpower_smooth + nb_build_filter. */
+int nb_build_filter_fused(int prec, const void* fmaps, const void* fsig, const double* w, double* filtFull, void* filtH,
+                          int nOut, int S, int sigPerTile, int F, int H, int W, double sigma, cudaStream_t stream);
+
 /* Fold a full-plane filter (e.g. one loaded from a cache, nemo/filters.py:784-794) onto the half plane. */
 int nb_fold_filter(int prec, const double* filtFull, void* filtH, int n, int H, int W, cudaStream_t stream);
 

@@ -35,6 +35,7 @@ _PROTOTYPES = {
     "nb_window_deconv": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr],
     "nb_xpower_smooth": [c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_ptr],
     "nb_build_filter": [c_int, c_ptr, c_ptr, ctypes.POINTER(c_dbl), c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr],
+    "nb_build_filter_fused": [c_int, c_ptr, c_ptr, ctypes.POINTER(c_dbl), c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_dbl, c_ptr],
     "nb_fold_filter": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr],
     "nb_template_norm": [c_int, c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "nb_plane_values_at": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr],

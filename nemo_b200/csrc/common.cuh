@@ -93,6 +93,7 @@ __device__ __forceinline__ double warp_max(double v) {
 
 // reflect boundary of scipy.ndimage (mode='reflect': d c b a | a b c d | d c b a)
 __host__ __device__ __forceinline__ int reflect_idx(int i, int n) {
+    if ((unsigned)i < (unsigned)n) return i;   // interior: the common case, no division
     if (n == 1) return 0;
     int p = 2 * n;
     i %= p;

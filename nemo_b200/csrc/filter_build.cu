@@ -205,6 +205,174 @@ __global__ void __launch_bounds__(256) build_filter_kernel(const double* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// K2 + K3 fused (nb_build_filter_fused): the smoothed covariance never goes to HBM.  A CTA owns a tile of up to FB_T x FB_T
+// modes of the half plane and the tile of their mirror modes -k (whose covariance the folded filter also needs; with scipy's
+// 'reflect' boundary the smoothed covariance is NOT point-symmetric near the array edges, so both are computed).  Row ky = 0 and
+// column kx = 0 are tiles of their own, which makes every tile and its mirror a contiguous rectangle of the full plane.
+// Per plane (i, j): cross power on the rectangle plus a halo of the smoothing radius, rebuilt from the half spectrum, smoothed
+// along kx then ky in shared memory; then the F x F solve for every filter scale of the tile.
+#define FB_T 32
+
+template <typename T, int F>
+__device__ __forceinline__ double cross_power_at(const typename V2<T>::type* __restrict__ base, int i, int j, int y, int x, int H,
+                                                 int W, int Wc) {
+    typedef typename V2<T>::type C2;
+    // full-plane mode (y, x): stored at (y, x) for x < Wc, else the conjugate of ((H - y) % H, W - x) -- same cross power
+    const int row = (x < Wc) ? y : (H - y) % H;
+    const int col = (x < Wc) ? x : (W - x);
+    const C2 a = base[((size_t)i * H + row) * Wc + col];
+    if (i == j) return (double)a.x * (double)a.x + (double)a.y * (double)a.y;
+    const C2 b = base[((size_t)j * H + row) * Wc + col];
+    return (double)a.x * (double)b.x + (double)a.y * (double)b.y;
+}
+
+// smoothed plane (i, j) over rows ra .. ra + nr - 1, cols ca .. ca + nc - 1 of the full plane -> s_out[nr][FB_T]
+template <typename T, int F>
+__device__ __forceinline__ void smooth_region(const typename V2<T>::type* __restrict__ base, int i, int j, int ra, int nr, int ca, int nc,
+                                              int H, int W, const GaussW& g, double* s_np, double* s_tx, double* s_out) {
+    const int Wc = W / 2 + 1;
+    const int r = g.r;
+    const int hr = nr + 2 * r, hc = nc + 2 * r;
+    for (int e = threadIdx.x; e < hr * hc; e += blockDim.x) {
+        const int rr = e / hc, cc = e - rr * hc;
+        const int y = reflect_idx(ra - r + rr, H), x = reflect_idx(ca - r + cc, W);
+        s_np[e] = cross_power_at<T, F>(base, i, j, y, x, H, W, Wc);
+    }
+    __syncthreads();
+    if (r == 12) {
+        // sigma = 3 (the reference's fixed kernelSize): register-blocked passes, every input is read from shared memory once per
+        // 8 (along kx) or 4 (along ky) outputs instead of once per output
+        constexpr int R = 12, BX = 8, BY = 4;
+        double wreg[2 * R + 1];
+#pragma unroll
+        for (int d = 0; d <= 2 * R; ++d) wreg[d] = g.w[d];
+        const int segs = (nc + BX - 1) / BX;
+        for (int task = threadIdx.x; task < hr * segs; task += blockDim.x) {
+            const int rr = task / segs, c0 = (task - rr * segs) * BX;
+            const double* src = s_np + rr * hc + c0;
+            double in[BX + 2 * R];
+#pragma unroll
+            for (int k = 0; k < BX + 2 * R; ++k) in[k] = (c0 + k < hc) ? src[k] : 0.0;
+#pragma unroll
+            for (int o = 0; o < BX; ++o) {
+                double acc = 0;
+#pragma unroll
+                for (int d = 0; d <= 2 * R; ++d) acc += wreg[d] * in[o + d];
+                if (c0 + o < nc) s_tx[rr * FB_T + c0 + o] = acc;
+            }
+        }
+        __syncthreads();
+        const int segsY = (nr + BY - 1) / BY;
+        for (int task = threadIdx.x; task < segsY * nc; task += blockDim.x) {
+            const int sy = task / nc, cc = task - sy * nc;
+            const int r0 = sy * BY;
+            double in[BY + 2 * R];
+#pragma unroll
+            for (int k = 0; k < BY + 2 * R; ++k) in[k] = (r0 + k < hr) ? s_tx[(r0 + k) * FB_T + cc] : 0.0;
+#pragma unroll
+            for (int o = 0; o < BY; ++o) {
+                double acc = 0;
+#pragma unroll
+                for (int d = 0; d <= 2 * R; ++d) acc += wreg[d] * in[o + d];
+                if (r0 + o < nr) s_out[(r0 + o) * FB_T + cc] = acc;
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    for (int e = threadIdx.x; e < hr * nc; e += blockDim.x) {
+        const int rr = e / nc, cc = e - rr * nc;
+        const double* src = s_np + rr * hc + cc;
+        double acc = 0;
+        for (int d = 0; d <= 2 * r; ++d) acc += g.w[d] * src[d];
+        s_tx[rr * FB_T + cc] = acc;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nr * nc; e += blockDim.x) {
+        const int rr = e / nc, cc = e - rr * nc;
+        double acc = 0;
+        for (int d = 0; d <= 2 * r; ++d) acc += g.w[d] * s_tx[(rr + d) * FB_T + cc];
+        s_out[rr * FB_T + cc] = acc;
+    }
+    __syncthreads();
+}
+
+template <typename T, int F>
+__global__ void __launch_bounds__(256) build_filter_fused_kernel(const typename V2<T>::type* __restrict__ fmaps,
+                                                                 const typename V2<T>::type* __restrict__ fsig, FreqW fw,
+                                                                 double* __restrict__ filtFull, T* __restrict__ filtH, int S,
+                                                                 int sigPerTile, int H, int W, GaussW g) {
+    typedef typename V2<T>::type C2;
+    constexpr int P = F * (F + 1) / 2;
+    extern __shared__ double s_fb[];
+    const int Wc = W / 2 + 1;
+    const int r = g.r;
+    double* s_np = s_fb;                                         // [(FB_T + 2r)][(FB_T + 2r)]
+    double* s_tx = s_np + (FB_T + 2 * r) * (FB_T + 2 * r);       // [(FB_T + 2r)][FB_T]
+    double* s_c1 = s_tx + (FB_T + 2 * r) * FB_T;                 // [P][FB_T][FB_T]  covariance at the tile's modes
+    double* s_c2 = s_c1 + P * FB_T * FB_T;                       // [P][FB_T][FB_T]  ... at their mirrors
+    const int tile = blockIdx.z;
+    // tile 0 along an axis is the single index 0; tile k >= 1 covers 1 + (k - 1) FB_T .. (clipped)
+    const int x0 = blockIdx.x == 0 ? 0 : 1 + (blockIdx.x - 1) * FB_T;
+    const int nx = blockIdx.x == 0 ? 1 : min(FB_T, Wc - x0);
+    const int y0 = blockIdx.y == 0 ? 0 : 1 + (blockIdx.y - 1) * FB_T;
+    const int ny = blockIdx.y == 0 ? 1 : min(FB_T, H - y0);
+    // mirror rectangle: rows (H - ky) % H, cols (W - kx) % W; ascending starts
+    const int my0 = blockIdx.y == 0 ? 0 : H - (y0 + ny - 1);
+    const int mx0 = blockIdx.x == 0 ? 0 : W - (x0 + nx - 1);
+    const C2* base = fmaps + (size_t)tile * F * H * Wc;
+    int p = 0;
+#pragma unroll
+    for (int i = 0; i < F; ++i)
+#pragma unroll
+        for (int j = i; j < F; ++j) {
+            smooth_region<T, F>(base, i, j, y0, ny, x0, nx, H, W, g, s_np, s_tx, s_c1 + p * FB_T * FB_T);
+            smooth_region<T, F>(base, i, j, my0, ny, mx0, nx, H, W, g, s_np, s_tx, s_c2 + p * FB_T * FB_T);
+            ++p;
+        }
+    for (int e = threadIdx.x; e < ny * nx; e += blockDim.x) {
+        const int ii = e / nx, jj = e - ii * nx;
+        const int ky = y0 + ii, kx = x0 + jj;
+        const int kym = (H - ky) % H, kxm = (W - kx) % W;
+        // position of the mirror mode inside the mirror rectangle (it runs backwards)
+        const int mi = (blockIdx.y == 0) ? 0 : (ny - 1 - ii), mj = (blockIdx.x == 0) ? 0 : (nx - 1 - jj);
+        double c1[P], c2[P];
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            c1[q] = s_c1[q * FB_T * FB_T + ii * FB_T + jj];
+            c2[q] = s_c2[q * FB_T * FB_T + mi * FB_T + mj];
+        }
+        const bool ownMirror = (kx == 0 || 2 * kx == W);
+        for (int sIdx = 0; sIdx < S; ++sIdx) {
+            const int o = tile * S + sIdx;
+            const int sg = sigPerTile ? o : sIdx;
+            double rhs[F], rhs2[F], x1[F], x2[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const C2 v = fsig[(((size_t)sg * F + f) * H + ky) * Wc + kx];
+                rhs[f] = __dmul_rn(fw.w[f], hypot((double)v.x, (double)v.y));
+                rhs2[f] = rhs[f];
+                if (ownMirror) {
+                    const C2 vm = fsig[(((size_t)sg * F + f) * H + kym) * Wc + kx];
+                    rhs2[f] = __dmul_rn(fw.w[f], hypot((double)vm.x, (double)vm.y));
+                }
+            }
+            solve_sym<F>(c1, rhs, x1);
+            solve_sym<F>(c2, rhs2, x2);
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                filtH[(((size_t)o * F + f) * H + ky) * Wc + kx] = (T)(0.5 * __dadd_rn(x1[f], x2[f]));
+                if (filtFull) {
+                    double* ff = filtFull + ((size_t)o * F + f) * H * W;
+                    ff[(size_t)ky * W + kx] = x1[f];
+                    if (kx > 0 && 2 * kx < W) ff[(size_t)kym * W + kxm] = x2[f];
+                }
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) fold_filter_kernel(const double* __restrict__ filtFull, T* __restrict__ filtH,
                                                           int H, int W) {
@@ -414,7 +582,49 @@ static int build_filter_tf(const double* cov, const void* fsig, const double* w,
     return NB_OK;
 }
 
+template <typename T, int F>
+static int build_filter_fused_tf(const void* fmaps, const void* fsig, const double* w, double* filtFull, void* filtH, int nOut, int S,
+                                 int sigPerTile, int H, int W, const GaussW& g, cudaStream_t st) {
+    typedef typename V2<T>::type C2;
+    constexpr int P = F * (F + 1) / 2;
+    FreqW fw;
+    for (int f = 0; f < NB_MAX_FREQ; ++f) fw.w[f] = f < F ? w[f] : 0.0;
+    const int Wc = W / 2 + 1;
+    const int side = FB_T + 2 * g.r;
+    const size_t smem = sizeof(double) * ((size_t)side * side + (size_t)side * FB_T + 2 * (size_t)P * FB_T * FB_T);
+    NB_REQUIRE(smem <= 220 * 1024, NB_ERR_UNSUPPORTED, "nb_build_filter_fused: smoothing radius %d too large", g.r);
+    if (smem > 48 * 1024)
+        NB_CHECK_CUDA(cudaFuncSetAttribute(build_filter_fused_kernel<T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(1 + (Wc - 1 + FB_T - 1) / FB_T, 1 + (H - 1 + FB_T - 1) / FB_T, nOut / S);
+    { NB_PROF_BEGIN(st); build_filter_fused_kernel<T, F><<<grid, 256, smem, st>>>((const C2*)fmaps, (const C2*)fsig, fw, filtFull, (T*)filtH, S, sigPerTile, H, W, g); NB_PROF_END("build_filter_fused_kernel", st); }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
+
 extern "C" {
+
+int nb_build_filter_fused(int prec, const void* fmaps, const void* fsig, const double* w, double* filtFull, void* filtH, int nOut,
+                          int S, int sigPerTile, int F, int H, int W, double sigma, cudaStream_t st) {
+    NB_REQUIRE(fmaps && fsig && w && filtH && nOut > 0 && S > 0 && nOut % S == 0 && (W % 2) == 0, NB_ERR_ARG,
+               "nb_build_filter_fused: bad arguments");
+    NB_REQUIRE(F >= 1 && F <= NB_MAX_FREQ, NB_ERR_UNSUPPORTED, "nb_build_filter_fused: %d frequencies not supported", F);
+    GaussW g;
+    int rc = make_gauss(sigma, &g);
+    if (rc != NB_OK) return rc;
+    NB_REQUIRE(g.r < H && g.r < W, NB_ERR_UNSUPPORTED, "nb_build_filter_fused: map smaller than the smoothing kernel");
+#define BFF(T)                                                                                                              \
+    switch (F) {                                                                                                            \
+        case 1: return build_filter_fused_tf<T, 1>(fmaps, fsig, w, filtFull, filtH, nOut, S, sigPerTile, H, W, g, st);      \
+        case 2: return build_filter_fused_tf<T, 2>(fmaps, fsig, w, filtFull, filtH, nOut, S, sigPerTile, H, W, g, st);      \
+        case 3: return build_filter_fused_tf<T, 3>(fmaps, fsig, w, filtFull, filtH, nOut, S, sigPerTile, H, W, g, st);      \
+        default: return build_filter_fused_tf<T, 4>(fmaps, fsig, w, filtFull, filtH, nOut, S, sigPerTile, H, W, g, st);     \
+    }
+    if (prec == NB_PREC_F64) { BFF(double) }
+    if (prec == NB_PREC_F32) { BFF(float) }
+#undef BFF
+    nb_set_error("nb_build_filter_fused: bad precision %d", prec);
+    return NB_ERR_ARG;
+}
 
 int nb_xpower_smooth(int prec, const void* fmaps, double* cov, double* tmp, int B, int F, int H, int W, double sigma,
                      cudaStream_t st) {

@@ -8,10 +8,15 @@ Reference arithmetic restated (nemo/filters.py): :526-529 input FFTs, :568-587 n
 :635-688 normalisation, :699/:824-859 application, :716-758 noise / S-N / masks, :101-104 pixel-window undo.
 """
 
+import os
+
 import numpy as np
 
 from . import signals
 from . import maps as nmaps
+
+
+FUSED_FILTER_BUILD = os.environ.get('NEMO_B200_FUSED_FILTER_BUILD', '0') == '1'
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -107,10 +112,17 @@ def buildFourierFilters(ops, fmapsNoise, templUnit, templNorm, w, outputUnits, c
     nS = templUnit.shape[0]
     S = nS // nT if sigPerTile else nS
     nOut = nT * S
-    cov = ops.xpower_smooth(fmapsNoise, 3.0)
     fsig = ops.rfft2(templUnit.reshape(nS * F, H, W), apodPix=0).reshape(nS, F, H, Wc)
-    filtH, filtFull = ops.build_filter(cov, fsig, w, S, sigPerTile, wantFull=wantFull)
-    del cov
+    if FUSED_FILTER_BUILD:
+        # K2 + K3 in one kernel, the covariance staying in shared memory: saves the two fp64 [nT, P, H, W] arrays, but the 12-pixel
+        # halos of its 32 x 32 tiles move more bytes through L2 than the covariance costs in HBM (0.51 ms against 0.39 ms for
+        # 16 tiles of 1024^2, F = 1), so it is off unless memory is the constraint
+        filtH, filtFull = ops.build_filter_fused(fmapsNoise, fsig, w, S, sigPerTile, sigma=3.0, wantFull=wantFull)
+    else:
+        # K2: smoothed noise covariance (filters.py:568-587); K3: per-mode solve (:624-630)
+        cov = ops.xpower_smooth(fmapsNoise, 3.0)
+        filtH, filtFull = ops.build_filter(cov, fsig, w, S, sigPerTile, wantFull=wantFull)
+        del cov
     if outputUnits == 'yc':
         tn = templNorm.reshape(nS * F, H, W).clone()
         ops.apply_window(tn, 1.0, restoreZeros=False)   # enmap.apply_window(signalMap, pow=1.0), filters.py:647

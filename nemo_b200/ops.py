@@ -167,6 +167,21 @@ class Ops(object):
         self.launches += 1
         return filtH, filtFull
 
+    def build_filter_fused(self, fmaps, fsig, w, S, sigPerTile, sigma=3.0, wantFull=False):
+        """xpower_smooth + build_filter in one kernel; the covariance never leaves the chip.  Returns (filtH, filtFull or None)."""
+        self._check(fmaps, self.cdtype, 'fmaps')
+        self._check(fsig, self.cdtype, 'fsig')
+        nT, F, H, Wc = fmaps.shape
+        W = (Wc - 1) * 2
+        nOut = nT * S
+        filtH = self.empty((nOut, F, H, Wc))
+        filtFull = self.empty((nOut, F, H, W), self.torch.float64) if wantFull else None
+        warr = (ctypes.c_double * F)(*[float(v) for v in w])
+        _lib.call('nb_build_filter_fused', self.prec, _ptr(fmaps), _ptr(fsig), warr, _ptr(filtFull), _ptr(filtH), nOut, int(S),
+                  1 if sigPerTile else 0, F, H, W, float(sigma), self._stream())
+        self.launches += 1
+        return filtH, filtFull
+
     def fold_filter(self, filtFull):
         self._check(filtFull, self.torch.float64, 'filtFull')
         shp = filtFull.shape

@@ -468,6 +468,53 @@ def _orderedFilters(parDict):
     return filtersList
 
 
+def _canBatch(filtersList):
+    """True when every filter is a Fourier-space matched filter and they share the noise set-up (what the batched kernels
+    take); anything else -- real-space filters, mixed noise parameters -- goes through the reference's per-tile loop."""
+    for f in filtersList:
+        cls = f['class'] if not isinstance(f['class'], str) else getattr(_filters, f['class'], None)
+        if cls is None or not issubclass(cls, _filters.MatchedFilter):
+            return False
+    return _sameNoiseSetup(filtersList)
+
+
+def _perTileLoop(config, filtersList, measureFluxes=True, invertMap=False, verbose=True, useCachedFilters=False):
+    """The reference's own loop (pipelines.py:179-286) over this rank's tiles and the filters, one filterMaps /
+    findObjects / measureFluxes call at a time, for filter sets the batched path does not take."""
+    parDict = config.parDict
+    photFilter = parDict.get('photFilter')
+    catalogDict = {}
+    for tileName in config.tileNames:
+        if verbose:
+            print(">>> [rank = %d] Making filtered maps - tileName = %s ..." % (config.rank, tileName))
+        photFilteredMapDict = None
+        for f in filtersList:
+            label = f['label'] + "#" + tileName
+            fCopy = {'label': f['label'], 'class': f['class'], 'params': dict(f['params'])}
+            filteredMapDict = _filters.filterMaps(config.tileMaps[tileName], fCopy, tileName,
+                                                  diagnosticsDir=getattr(config, 'diagnosticsDir', None),
+                                                  selFnDir=getattr(config, 'selFnDir', None), verbose=verbose,
+                                                  undoPixelWindow=parDict.get('undoPixelWindow', True), useCachedFilter=useCachedFilters)
+            if invertMap:
+                raise Exception("invertMap is only handled by the batched path")
+            if f['label'] == photFilter:
+                photFilteredMapDict = {'SNMap': filteredMapDict['SNMap'], 'data': filteredMapDict['data']}
+            catalog = photometry.findObjects(filteredMapDict, threshold=parDict['thresholdSigma'], minObjPix=parDict['minObjPix'],
+                                             findCenterOfMass=parDict['findCenterOfMass'], removeRings=parDict['removeRings'],
+                                             ringThresholdSigma=parDict['ringThresholdSigma'], rejectBorder=parDict['rejectBorder'],
+                                             objIdent=parDict['objIdent'], longNames=parDict['longNames'],
+                                             useInterpolator=parDict['useInterpolator'], measureShapes=parDict['measureShapes'],
+                                             verbose=False)
+            if measureFluxes:
+                photometry.measureFluxes(catalog, filteredMapDict, getattr(config, 'diagnosticsDir', None),
+                                         photFilteredMapDict=photFilteredMapDict, useInterpolator=parDict['useInterpolator'])
+            elif photFilter is not None:
+                photometry.getSNRValues(catalog, photFilteredMapDict['SNMap'], filteredMapDict['wcs'], prefix='fixed_',
+                                        useInterpolator=parDict['useInterpolator'], invertMap=invertMap)
+            catalogDict[label] = {'catalog': catalog}
+    return catalogDict
+
+
 def stageTiles(config, tilesPerBatch=8, precision=None):
     """Copies this rank's tiles into pinned host staging buffers, `tilesPerBatch` tiles per batch, and keeps them on
     `config` so that repeated runs (source-injection iterations, benchmarks) start from pinned memory."""
@@ -497,6 +544,23 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     ops = device.getOps(precision)
     parDict = config.parDict
     filtersList = _orderedFilters(parDict)
+    if not _canBatch(filtersList):
+        if cacheFilters or useCachedRMSMap:
+            raise Exception("filter caches on the device are kept by the batched (Fourier matched filter) path only")
+        catalogDict = _perTileLoop(config, filtersList, measureFluxes=measureFluxes, invertMap=invertMap, verbose=verbose,
+                                   useCachedFilters=useCachedFilters)
+        optimalCatalog = catalogs.makeOptimalCatalog(catalogDict, constraintsList=parDict.get('catalogCuts', []))
+        if comm is not None and comm.size > 1:
+            from . import distributed
+            keys = [k for k in optimalCatalog.keys()] if len(optimalCatalog) > 0 else catalogKeys(False, 'yc', measureFluxes)
+            nKeys = int(comm.maxOverRanks(len(keys)))
+            if len(keys) != nKeys:      # a rank without detections: take the longest list any rank has
+                raise Exception("ranks disagree on the catalog columns; give every rank at least one tile with detections")
+            optimalCatalog = distributed.allGatherCatalog(comm, optimalCatalog, keys, [f['label'] for f in filtersList], config.allTileNames,
+                                                          objIdent=parDict['objIdent'], longNames=parDict['longNames'])
+        config.catalogDict = catalogDict
+        config.noiseTables = {}
+        return optimalCatalog
     catalogDict = {}
     noiseTables = {}
     staged = getattr(config, '_staged', None)

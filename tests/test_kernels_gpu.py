@@ -163,6 +163,28 @@ def test_build_filter_f64(ops64, report, F, S, shape):
     assert worst < 1e-9 and errH < 1e-15
 
 
+@pytest.mark.parametrize("F,S,shape", [(1, 2, (64, 64)), (2, 2, (128, 64)), (3, 1, (64, 128)), (2, 3, (300, 420)), (4, 1, (96, 100)), (1, 1, (1024, 1024))])
+def test_build_filter_fused_matches_two_step(ops64, report, F, S, shape):
+    """nb_build_filter_fused (covariance kept in shared memory) against nb_xpower_smooth + nb_build_filter, both the folded
+    half-plane filter and the full plane, for tiles that do and do not divide into 32 x 32 blocks."""
+    rng = np.random.default_rng(23)
+    H, W = shape
+    nT = 2
+    maps = rng.standard_normal((nT, F, H, W))
+    maps[:, 1:] += maps[:, :1] * 3
+    fmaps = ops64.rfft2(ops64.to_device(maps.reshape(nT * F, H, W))).reshape(nT, F, H, W // 2 + 1)
+    templ = rng.standard_normal((S, F, H, W))
+    fsig = ops64.rfft2(ops64.to_device(templ.reshape(S * F, H, W))).reshape(S, F, H, W // 2 + 1)
+    w = rng.standard_normal(F)
+    cov = ops64.xpower_smooth(fmaps, 3.0)
+    refH, refFull = ops64.build_filter(cov, fsig, w, S, sigPerTile=False, wantFull=True)
+    gotH, gotFull = ops64.build_filter_fused(fmaps, fsig, w, S, False, sigma=3.0, wantFull=True)
+    errH = _relerr(_np(gotH), _np(refH))
+    errFull = _relerr(_np(gotFull), _np(refFull))
+    report("build_filter_fused", F=F, S=S, shape=shape, relerr_half=errH, relerr_full=errFull)
+    assert errH < 1e-11 and errFull < 1e-11
+
+
 def test_build_filter_singular(ops64):
     H, W, F = 64, 64, 2
     cov = np.zeros((1, 3, H, W))

@@ -413,3 +413,31 @@ def test_three_frequencies_half_masked_tile_and_empty_catalog(report):
     _compareCatalogs(gotCat, refCat, ['SNR'])
     assert photometry.findObjects(got, **dict(DETECT, threshold=1e6)) == []
     assert photometry_ref.findObjects(ref, **dict(DETECT, threshold=1e6)) == []
+
+
+def test_pipeline_driver_with_real_space_filters(report):
+    """filterMapsAndMakeCatalogs with a real-space filter set (BASELINE config 3 shape, reduced): the driver falls back to the
+    reference's per-tile loop over the class API; catalogs against the oracle's loop."""
+    from nemo_b200 import pipelines
+    tileMaps = {}
+    for t in range(2):
+        md, _ = synth.makeTile(shape=(256, 256), freqsGHz=(97.8, 149.6), noiseUK=(60.0, 40.0), beamFWHMArcmin=(2.2, 1.4),
+                               numObjects=6, kind='clusters', cmb=True, seed=70 + t)
+        tileMaps['tile%d' % t] = md
+    p = {'M500MSun': 2e14, 'z': 0.4, 'outputUnits': 'yc', 'bckSub': True, 'edgeTrimArcmin': 0.,
+         'noiseParams': {'method': 'dataMap', 'matchedFilterClass': 'ArnaudModelMatchedFilter', 'RADecSection': None,
+                         'kernelMaxArcmin': 7., 'symmetrize': True, 'noiseGridArcmin': 20.}}
+    f = {'label': 'ArnaudRS', 'class': 'ArnaudModelRealSpaceMatchedFilter', 'params': p}
+    parDict = {'mapFilters': [f], 'photFilter': None, 'thresholdSigma': 4.0, 'minObjPix': 1, 'findCenterOfMass': True,
+               'useInterpolator': True, 'rejectBorder': 0}
+    config = pipelines.SimpleConfig(parDict, tileMaps)
+    opt = pipelines.filterMapsAndMakeCatalogs(config, verbose=False)
+    nObj = 0
+    for tileName, md in tileMaps.items():
+        ref = filters_ref.filterMaps(md, _copyFilter(f), tileName)
+        refCat = photometry_ref.findObjects(ref, **DETECT)
+        photometry_ref.measureFluxes(refCat, ref, None)
+        _compareCatalogs(config.catalogDict['ArnaudRS#' + tileName]['catalog'], refCat, ['SNR', 'y_c', 'err_y_c'])
+        nObj += len(refCat)
+    assert nObj >= 2 and len(opt) == nObj
+    report("pipeline_real_space", objects=nObj)

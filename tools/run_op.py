@@ -50,8 +50,10 @@ def run():
         if 'fm' not in state:
             state['fm'] = ops.rfft2(maps, apodPix=20).reshape(nT, 1, H, W // 2 + 1)
             state['fsig'] = ops.rfft2(maps[:1], apodPix=0).reshape(1, 1, H, W // 2 + 1)
-        cov = ops.xpower_smooth(state['fm'], 3.0)
-        return ops.build_filter(cov, state['fsig'], [1.0], 1, False)
+        if os.environ.get('TWO_STEP'):
+            cov = ops.xpower_smooth(state['fm'], 3.0)
+            return ops.build_filter(cov, state['fsig'], [1.0], 1, False)
+        return ops.build_filter_fused(state['fm'], state['fsig'], [1.0], 1, False)
     if args.op == 'detect':
         return ops.detect(maps / 100.0, 3.0)
     raise SystemExit("unknown op " + args.op)
