@@ -188,12 +188,16 @@ class MapFilter(object):
 
     def makeRealSpaceFilterProfile(self):
         """1-d real-space profile of the filter and its angular range in arcmin (filters.py:282-304)."""
-        realSpace = fft.ifft2(self.filt).real
-        realSpace = fft.fftshift(realSpace)
-        x0 = int(realSpace.shape[2] / 2)
-        y0 = int(realSpace.shape[1] / 2)
-        normFactor = abs(realSpace[:, y0, x0:]).max()
-        prof = realSpace[:, y0, x0:] / normFactor
+        # The reference takes row H/2, columns W/2.. of fftshift(ifft2(filt).real) -- fftshift over ALL axes, the frequency
+        # axis included.  That row is row 0 of the unshifted inverse transform, i.e. the 1-d inverse transform along x of the
+        # mean over ky, so the full 2-d inverse transform is not needed.
+        filt = np.asarray(self.filt)
+        W = filt.shape[2]
+        rowCut = fft.ifft(filt.mean(axis=1), axis=-1).real
+        rowCut = fft.fftshift(rowCut, axes=0)
+        cut = rowCut[:, :W - W // 2]
+        normFactor = abs(cut).max()
+        prof = cut / normFactor
         arcminRange = np.arange(0, prof.shape[1]) * self.degPerPixX * 60.0
         return prof, arcminRange
 
