@@ -19,6 +19,20 @@
 
 using namespace nbfft;
 
+// occupancy knobs (minimum resident CTAs per SM asked of ptxas, column-tile budget)
+#ifndef FFT_ROW_MINB
+#define FFT_ROW_MINB 1
+#endif
+#ifndef FFT_COL_MINB
+#define FFT_COL_MINB 1
+#endif
+#ifndef FFT_COL_SMEM_KB
+#define FFT_COL_SMEM_KB 144
+#endif
+#ifndef FFT_COL_THREADS
+#define FFT_COL_THREADS 512
+#endif
+
 // ------------------------------------------------------------------------------------------------------
 // twiddle tables: tw[m] = exp(-2 pi i m / N), computed in long double on the host, cached per (prec, N)
 static std::mutex g_plan_mutex;
@@ -65,8 +79,8 @@ static int get_twiddles(int prec, int N, const void** out) {
 // for fp64 at H = 1024 -- which is what the strided column walk needs to use DRAM bursts fully
 template <typename T, int N> struct ColCfg {
     static constexpr int BYTES_PER_COL = npad(N) * 2 * (int)sizeof(T);
-    static constexpr int CSMEM = (144 * 1024) / BYTES_PER_COL;
-    static constexpr int CTHR = 512 / (N / 16) > 0 ? 512 / (N / 16) : 1;
+    static constexpr int CSMEM = (FFT_COL_SMEM_KB * 1024) / BYTES_PER_COL;
+    static constexpr int CTHR = FFT_COL_THREADS / (N / 16) > 0 ? FFT_COL_THREADS / (N / 16) : 1;
     static constexpr int CRAW = CSMEM < CTHR ? CSMEM : CTHR;
     static constexpr int C = CRAW >= 16 ? 16 : CRAW >= 8 ? 8 : CRAW >= 4 ? 4 : CRAW >= 2 ? 2 : 1;
     static constexpr int NT = N / 16;
@@ -80,7 +94,7 @@ template <typename T, int N> struct ColCfg {
 // ------------------------------------------------------------------------------------------------------
 // column kernels
 template <typename T, int N, int DIR>
-__global__ void __launch_bounds__(ColCfg<T, N>::THREADS)
+__global__ void __launch_bounds__(ColCfg<T, N>::THREADS, FFT_COL_MINB)
 fft_cols_kernel(const typename V2<T>::type* __restrict__ in, typename V2<T>::type* __restrict__ out, int Wc,
                 const typename V2<T>::type* __restrict__ tw, T scale) {
     typedef ColCfg<T, N> Cfg;
@@ -110,7 +124,7 @@ fft_cols_kernel(const typename V2<T>::type* __restrict__ in, typename V2<T>::typ
 
 // out[o] = inverse column FFT of sum_f fmaps[o / S, f] * filt[o, f]      (filt real, folded half plane)
 template <typename T, int N, int F>
-__global__ void __launch_bounds__(ColCfg<T, N>::THREADS)
+__global__ void __launch_bounds__(ColCfg<T, N>::THREADS, FFT_COL_MINB)
 fft_cols_apply_kernel(const typename V2<T>::type* __restrict__ fmaps, const T* __restrict__ filt,
                       typename V2<T>::type* __restrict__ out, int Wc, int S, int perScale,
                       const typename V2<T>::type* __restrict__ tw) {
@@ -157,7 +171,7 @@ fft_cols_apply_kernel(const typename V2<T>::type* __restrict__ fmaps, const T* _
 
 // in place: forward column FFT, multiply by wy[ky] * wx[kx], inverse column FFT (un-normalised: gains a factor N)
 template <typename T, int N>
-__global__ void __launch_bounds__(ColCfg<T, N>::THREADS)
+__global__ void __launch_bounds__(ColCfg<T, N>::THREADS, FFT_COL_MINB)
 fft_cols_window_kernel(typename V2<T>::type* __restrict__ data, int Wc, const T* __restrict__ wy,
                        const T* __restrict__ wx, const typename V2<T>::type* __restrict__ tw) {
     typedef ColCfg<T, N> Cfg;
@@ -207,7 +221,7 @@ template <typename T, int W> struct RowCfg {
 };
 
 template <typename T, int W>
-__global__ void __launch_bounds__(RowCfg<T, W>::THREADS)
+__global__ void __launch_bounds__(RowCfg<T, W>::THREADS, FFT_ROW_MINB)
 rfft_rows_kernel(const T* __restrict__ in, typename V2<T>::type* __restrict__ out, int H, long long nrows,
                  NbTaper tp, T scale, const typename V2<T>::type* __restrict__ twM,
                  const typename V2<T>::type* __restrict__ twW) {
@@ -276,7 +290,7 @@ template <typename T> struct C2RParams {
 };
 
 template <typename T, int W>
-__global__ void __launch_bounds__(RowCfg<T, W>::THREADS)
+__global__ void __launch_bounds__(RowCfg<T, W>::THREADS, FFT_ROW_MINB)
 irfft_rows_kernel(const typename V2<T>::type* __restrict__ in, T* out, int H, long long nrows, C2RParams<T> ep,
                   const typename V2<T>::type* __restrict__ twM, const typename V2<T>::type* __restrict__ twW) {
     typedef RowCfg<T, W> Cfg;
