@@ -9,7 +9,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libnemo_b200.so")
+LIBPATH = os.environ.get("NEMO_B200_LIB") or os.path.join(HERE, "libnemo_b200.so")   # the override is for kernel experiments
 
 PREC_F32 = 0
 PREC_F64 = 1

@@ -108,10 +108,8 @@ static int get_bs_tables(int prec, int N, BsTables* out) {
     for (int m = 0; m < M; ++m) {
         br[m] /= (long double)M;
         bi[m] /= (long double)M;
-        const long double a = 2.0L * pi * (long double)m / (long double)M;
-        tr[m] = cosl(a);
-        ti[m] = -sinl(a);
     }
+    nb_fill_pass_twiddles(M, 16, tr, ti);     // pass tables of the M-point transforms (fft.cuh), 16 values per thread
     BsTables t;
     t.M = M;
     int rc;

@@ -20,8 +20,11 @@
 using namespace nbfft;
 
 // occupancy knobs (minimum resident CTAs per SM asked of ptxas, column-tile budget)
+#ifndef FFT_ROW_V
+#define FFT_ROW_V 8         // complex values per thread of the row passes: 8 halves the registers of 16 and doubles the resident warps
+#endif
 #ifndef FFT_ROW_MINB
-#define FFT_ROW_MINB 1
+#define FFT_ROW_MINB (FFT_ROW_V == 8 ? 3 : 2)   // resident CTAs per SM asked of ptxas (256 threads each)
 #endif
 #ifndef FFT_COL_MINB
 #define FFT_COL_MINB 1
@@ -70,6 +73,64 @@ static int get_twiddles(int prec, int N, const void** out) {
         NB_CHECK_CUDA(cudaMemcpy(d, h.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
     }
     g_twiddles[key] = d;
+    *out = d;
+    return NB_OK;
+}
+
+// pass twiddle tables (fft.cuh: pass_tw_offset) of an N-point transform carried V values per thread, cached per (prec, N, V)
+static std::map<std::pair<int, int>, void*> g_pass_twiddles;
+
+void nb_fill_pass_twiddles(int N, int V, std::vector<long double>& re, std::vector<long double>& im) {
+    const long double twopi = 6.283185307179586476925286766559005768L;
+    re.assign(pass_tw_total(N, V), 1.0L);
+    im.assign(pass_tw_total(N, V), 0.0L);
+    for (int Ns = 1; Ns < N;) {
+        const int R = (N / Ns) >= V ? V : (N / Ns);
+        if (Ns > 1) {
+            const int off = pass_tw_offset(N, V, Ns);
+            for (int r = 1; r < R; ++r)
+                for (int k = 0; k < Ns; ++k) {
+                    const long double a = twopi * (long double)(r * k) / (long double)(Ns * R);
+                    re[off + (r - 1) * Ns + k] = cosl(a);
+                    im[off + (r - 1) * Ns + k] = -sinl(a);
+                }
+        }
+        Ns *= R;
+    }
+}
+
+static int get_pass_twiddles(int prec, int N, int V, const void** out) {
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto key = std::make_pair((prec * 64 + dev) * 32 + V, N);
+    auto it = g_pass_twiddles.find(key);
+    if (it != g_pass_twiddles.end()) {
+        *out = it->second;
+        return NB_OK;
+    }
+    std::vector<long double> re, im;
+    nb_fill_pass_twiddles(N, V, re, im);
+    const size_t n = re.size();
+    void* d = nullptr;
+    if (prec == NB_PREC_F64) {
+        std::vector<double2> h(n);
+        for (size_t m = 0; m < n; ++m) {
+            h[m].x = (double)re[m];
+            h[m].y = (double)im[m];
+        }
+        NB_CHECK_CUDA(cudaMalloc(&d, sizeof(double2) * n));
+        NB_CHECK_CUDA(cudaMemcpy(d, h.data(), sizeof(double2) * n, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float2> h(n);
+        for (size_t m = 0; m < n; ++m) {
+            h[m].x = (float)re[m];
+            h[m].y = (float)im[m];
+        }
+        NB_CHECK_CUDA(cudaMalloc(&d, sizeof(float2) * n));
+        NB_CHECK_CUDA(cudaMemcpy(d, h.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    }
+    g_pass_twiddles[key] = d;
     *out = d;
     return NB_OK;
 }
@@ -209,10 +270,11 @@ fft_cols_window_kernel(typename V2<T>::type* __restrict__ data, int Wc, const T*
 }
 
 // ------------------------------------------------------------------------------------------------------
-// row kernels.  W real samples per row, M = W/2 complex points, NT = M/16 threads per row.
+// row kernels.  W real samples per row, M = W/2 complex points, NT = M/V threads per row.
 template <typename T, int W> struct RowCfg {
+    static constexpr int V = FFT_ROW_V;
     static constexpr int M = W / 2;
-    static constexpr int NT = M / 16;
+    static constexpr int NT = M / V;
     static constexpr int LD = npad(M) + 2;
     // rows per CTA: aim for 256 threads
     static constexpr int RPB = (256 / NT) > 0 ? (256 / NT) : 1;
@@ -227,7 +289,7 @@ rfft_rows_kernel(const T* __restrict__ in, typename V2<T>::type* __restrict__ ou
                  const typename V2<T>::type* __restrict__ twW) {
     typedef RowCfg<T, W> Cfg;
     typedef typename V2<T>::type C2;
-    constexpr int M = Cfg::M, NT = Cfg::NT, Wc = M + 1;
+    constexpr int M = Cfg::M, NT = Cfg::NT, Wc = M + 1, V = Cfg::V;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
     const int g = threadIdx.x / NT, t = threadIdx.x % NT;
@@ -235,13 +297,13 @@ rfft_rows_kernel(const T* __restrict__ in, typename V2<T>::type* __restrict__ ou
     const bool valid = row < nrows;
     T* s_re = smem + g * Cfg::LD;
     T* s_im = smem + (Cfg::RPB + g) * Cfg::LD;
-    T re[16], im[16];
+    T re[V], im[V];
     if (valid) {
         const C2* src = reinterpret_cast<const C2*>(in + (size_t)row * W);
         const int y = (int)(row % H);
         const T ay = (tp.n > 0) ? taper_at<T>(tp, y, H) : (T)1;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
+        for (int q = 0; q < V; ++q) {
             const int n = t + q * NT;
             C2 v = src[n];
             if (tp.n > 0) {
@@ -253,7 +315,7 @@ rfft_rows_kernel(const T* __restrict__ in, typename V2<T>::type* __restrict__ ou
         }
     } else {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
+        for (int q = 0; q < V; ++q) {
             re[q] = 0;
             im[q] = 0;
         }
@@ -266,7 +328,7 @@ rfft_rows_kernel(const T* __restrict__ in, typename V2<T>::type* __restrict__ ou
         C2* dst = out + (size_t)row * Wc;
         const T h = (T)0.5;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
+        for (int q = 0; q < V; ++q) {
             const int k = t + q * NT;
             const int kc = (M - k) & (M - 1);
             const T zr = re[q], zi = im[q];
@@ -295,7 +357,7 @@ irfft_rows_kernel(const typename V2<T>::type* __restrict__ in, T* out, int H, lo
                   const typename V2<T>::type* __restrict__ twM, const typename V2<T>::type* __restrict__ twW) {
     typedef RowCfg<T, W> Cfg;
     typedef typename V2<T>::type C2;
-    constexpr int M = Cfg::M, NT = Cfg::NT, Wc = M + 1;
+    constexpr int M = Cfg::M, NT = Cfg::NT, Wc = M + 1, V = Cfg::V;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
     const int g = threadIdx.x / NT, t = threadIdx.x % NT;
@@ -304,24 +366,24 @@ irfft_rows_kernel(const typename V2<T>::type* __restrict__ in, T* out, int H, lo
     T* s_re = smem + g * Cfg::LD;
     T* s_im = smem + (Cfg::RPB + g) * Cfg::LD;
     // every thread reads its 16 spectrum samples X[k] and their mirrors X[M - k] straight from global memory (the mirrors
-    // are some other thread's samples of the same row, so they come from L1/L2): 32 independent loads in flight per thread
-    T re[16], im[16];
+    // are some other thread's samples of the same row, so they come from L1/L2): 2 V independent loads in flight per thread
+    T re[V], im[V];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
+    for (int q = 0; q < V; ++q) {
         re[q] = 0;
         im[q] = 0;
     }
     if (valid) {
         const C2* src = in + (size_t)row * Wc;
-        C2 xs[16], cs[16];
+        C2 xs[V], cs[V];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
+        for (int q = 0; q < V; ++q) {
             const int k = t + q * NT;
             xs[q] = src[k];
             cs[q] = src[M - k];
         }
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
+        for (int q = 0; q < V; ++q) {
             const int k = t + q * NT;
             const T xr = xs[q].x, xi = xs[q].y;
             const T cr = cs[q].x, ci = -cs[q].y;                      // conj(X[M-k])
@@ -342,7 +404,7 @@ irfft_rows_kernel(const typename V2<T>::type* __restrict__ in, T* out, int H, lo
         const unsigned char* mrow = ep.mask ? ep.mask + ((size_t)(img / ep.maskDiv) * H + (row % H)) * W : nullptr;
         const C2* zrow = ep.zeroRef ? reinterpret_cast<const C2*>(ep.zeroRef + (size_t)row * W) : nullptr;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
+        for (int q = 0; q < V; ++q) {
             const int n = t + q * NT;
             T a = re[q] * f, b = im[q] * f;
             if (mrow) {
@@ -411,7 +473,7 @@ static int rfft_rows_t(const T* in, typename V2<T>::type* out, int B, int H, int
     if (apodPix > 0) tp.a[apodPix - 1] = 1.0;  // np.linspace end point is exact; cos(pi) = -1 exactly
     const void *twM, *twW;
     int rc;
-    if ((rc = get_twiddles(prec_of<T>(), W / 2, &twM)) != NB_OK) return rc;
+    if ((rc = get_pass_twiddles(prec_of<T>(), W / 2, FFT_ROW_V, &twM)) != NB_OK) return rc;
     if ((rc = get_twiddles(prec_of<T>(), W, &twW)) != NB_OK) return rc;
     const long long nrows = (long long)B * H;
 #define ROWS_FWD(WW)                                                                                          \
@@ -442,7 +504,7 @@ static int irfft_rows_t(const typename V2<T>::type* in, T* out, int B, int H, in
     typedef typename V2<T>::type C2;
     const void *twM, *twW;
     int rc;
-    if ((rc = get_twiddles(prec_of<T>(), W / 2, &twM)) != NB_OK) return rc;
+    if ((rc = get_pass_twiddles(prec_of<T>(), W / 2, FFT_ROW_V, &twM)) != NB_OK) return rc;
     if ((rc = get_twiddles(prec_of<T>(), W, &twW)) != NB_OK) return rc;
     const long long nrows = (long long)B * H;
 #define ROWS_INV(WW)                                                                                          \
@@ -474,7 +536,7 @@ static int fft_cols_t(const typename V2<T>::type* in, typename V2<T>::type* out,
     typedef typename V2<T>::type C2;
     const void* tw;
     int rc;
-    if ((rc = get_twiddles(prec_of<T>(), H, &tw)) != NB_OK) return rc;
+    if ((rc = get_pass_twiddles(prec_of<T>(), H, 16, &tw)) != NB_OK) return rc;
 #define COLS(NN)                                                                                             \
     {                                                                                                        \
         typedef ColCfg<T, NN> Cfg;                                                                           \
@@ -499,7 +561,7 @@ static int fft_cols_apply_tf(const typename V2<T>::type* fmaps, const T* filt, t
     typedef typename V2<T>::type C2;
     const void* tw;
     int rc;
-    if ((rc = get_twiddles(prec_of<T>(), H, &tw)) != NB_OK) return rc;
+    if ((rc = get_pass_twiddles(prec_of<T>(), H, 16, &tw)) != NB_OK) return rc;
 #define COLS_APPLY(NN)                                                                                       \
     {                                                                                                        \
         typedef ColCfg<T, NN> Cfg;                                                                           \
@@ -518,7 +580,7 @@ static int fft_cols_window_t(typename V2<T>::type* data, int B, int H, int Wc, c
     typedef typename V2<T>::type C2;
     const void* tw;
     int rc;
-    if ((rc = get_twiddles(prec_of<T>(), H, &tw)) != NB_OK) return rc;
+    if ((rc = get_pass_twiddles(prec_of<T>(), H, 16, &tw)) != NB_OK) return rc;
 #define COLS_WIN(NN)                                                                                         \
     {                                                                                                        \
         typedef ColCfg<T, NN> Cfg;                                                                           \

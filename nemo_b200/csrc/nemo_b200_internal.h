@@ -2,6 +2,10 @@
 #pragma once
 #include "common.cuh"
 #include "../../include/nemo_b200.h"
+#include <vector>
+
+// pass twiddle tables of the shared-memory FFT (layout: fft.cuh pass_tw_offset), in long double (fft_kernels.cu)
+void nb_fill_pass_twiddles(int N, int V, std::vector<long double>& re, std::vector<long double>& im);
 
 // Bluestein passes for sides that are not powers of two (fft_bluestein.cu); same contracts as the power-of-two row / column
 // passes of fft_kernels.cu
