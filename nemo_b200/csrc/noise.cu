@@ -437,48 +437,39 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     const int JT = (tr * tc + 31) >> 5;                      // slots per lane
     const int spw = smemSlots / OC_WARPS;                    // shared-memory slots per warp
     const int ty0 = (wid / OC_TGX) * tr, tx0 = (wid % OC_TGX) * tc;
-    const float rcpTc = 1.0f / (float)tc;
     key_t* wSlots = s_slots + (size_t)wid * spw;             // this warp's run (keys; values too in the hybrid variant)
     unsigned char* wBins = s_bins + (size_t)wid * spw;
     double* tab = table + ((size_t)img * gridDim.x + cell) * numBins;
     double* edg = edges + ((size_t)img * gridDim.x + cell) * (numBins + 1);
-    // global offsets of this lane's slots in order (slot j is pixel j * 32 + lane of the tile), -1 outside the cell;
-    // the cursor walks the tile without a division per slot
-    int curR = 0, curC = 0;
-    auto resetCursor = [&]() {
-        curR = lane / tc;
-        curC = lane - curR * tc;
+    // global offset of this lane's slot j (pixel i = j * 32 + lane of the warp's tile, row i / tc, column i % tc), -1 outside the
+    // cell.  The division is a multiply-high by ceil(2^32 / tc), exact while i * tc < 2^32 (tiles hold < 2^18 pixels).
+    const unsigned int tcMagic = tc > 1 ? 0xFFFFFFFFu / (unsigned int)tc + 1u : 0u;
+    const int tileBase = (g.y0 + ty0) * W + g.x0 + tx0;
+    const int rowsLeft = min(tr, Rn - ty0), colsLeft = cw - tx0;     // rows / columns of the tile that lie inside the cell
+    auto offsetOf = [&](int j) -> int {
+        const unsigned int i = (unsigned int)(j * 32 + lane);
+        const int r = tc > 1 ? (int)__umulhi(i, tcMagic) : (int)i;
+        const int c = (int)i - r * tc;
+        return (r < rowsLeft && c < colsLeft) ? tileBase + r * W + c : -1;
     };
-    auto nextOffset = [&]() -> long long {
-        const int r = ty0 + curR, c = tx0 + curC;
-        const long long off = (curR < tr && r < Rn && c < cw) ? (long long)(g.y0 + r) * W + g.x0 + c : -1LL;
-        curC += 32;
-        while (curC >= tc) {
-            curC -= tc;
-            ++curR;
-        }
-        return off;
-    };
-    (void)rcpTc;
 
     key_t reg[OC_PPT];
     // ---- load: weight keys of the good pixels (loads issued eight slots at a time, none depends on another) ----
     double cnt = 0, dummy = 0, wmin = INFINITY, wmax = -INFINITY;
-    auto makeKey = [&](long long off, T mv, T wv) -> key_t {
+    auto makeKey = [&](int off, T mv, T wv) -> key_t {
         if (off < 0 || mv == (T)0) return SENT;
         cnt += 1.0;
         wmin = fmin(wmin, (double)wv);
         wmax = fmax(wmax, (double)wv);
         return K::enc(wv);
     };
-    resetCursor();
 #pragma unroll
     for (int j0 = 0; j0 < OC_PPT; j0 += OC_LB) {
-        long long off[OC_LB];
+        int off[OC_LB];
         T mv[OC_LB], wv[OC_LB];
 #pragma unroll
         for (int u = 0; u < OC_LB; ++u) {
-            off[u] = nextOffset();
+            off[u] = offsetOf(j0 + u);
             mv[u] = (off[u] >= 0) ? m[off[u]] : (T)0;
             wv[u] = (off[u] >= 0) ? wm[off[u]] : (T)0;
         }
@@ -486,11 +477,11 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
         for (int u = 0; u < OC_LB; ++u) reg[j0 + u] = makeKey(off[u], mv[u], wv[u]);
     }
     for (int j0 = OC_PPT; j0 < JT; j0 += OC_LB) {
-        long long off[OC_LB];
+        int off[OC_LB];
         T mv[OC_LB], wv[OC_LB];
 #pragma unroll
         for (int u = 0; u < OC_LB; ++u) {
-            off[u] = nextOffset();
+            off[u] = offsetOf(j0 + u);
             mv[u] = (off[u] >= 0) ? m[off[u]] : (T)0;
             wv[u] = (off[u] >= 0) ? wm[off[u]] : (T)0;
         }
@@ -852,13 +843,12 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
         prefixBins();
         __syncthreads();
         key_t* vRun = s_slots + (size_t)wid * (valueSlots / OC_WARPS);
-        resetCursor();
 #pragma unroll
         for (int j0 = 0; j0 < OC_PPT; j0 += OC_LB) {
             T mv[OC_LB];
 #pragma unroll
             for (int u = 0; u < OC_LB; ++u) {
-                const long long off = nextOffset();
+                const int off = offsetOf(j0 + u);
                 mv[u] = (off >= 0) ? m[off] : (T)0;
             }
 #pragma unroll
@@ -875,7 +865,7 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
                 T mv[OC_LB];
 #pragma unroll
                 for (int u = 0; u < OC_LB; ++u) {
-                    const long long off = nextOffset();
+                    const int off = offsetOf(OC_PPT + j0 + u);
                     mv[u] = (off >= 0) ? m[off] : (T)0;
                 }
 #pragma unroll
@@ -893,13 +883,12 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
         __syncwarp();
     } else {
         // hybrid variant.  Register slots: bins packed four per word, values loaded in place of the keys
-        resetCursor();
 #pragma unroll
         for (int j0 = 0; j0 < OC_PPT; j0 += OC_LB) {
             T mv[OC_LB];
 #pragma unroll
             for (int u = 0; u < OC_LB; ++u) {
-                const long long off = nextOffset();
+                const int off = offsetOf(j0 + u);
                 mv[u] = (off >= 0) ? m[off] : (T)0;
             }
 #pragma unroll
@@ -922,7 +911,7 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
             T mv[OC_LB];
 #pragma unroll
             for (int u = 0; u < OC_LB; ++u) {
-                const long long off = nextOffset();
+                const int off = offsetOf(j0 + u);
                 mv[u] = (off >= 0) ? m[off] : (T)0;
             }
 #pragma unroll
@@ -954,6 +943,9 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
     }
     __syncthreads();   // s_warpBins, and the scratch the selection used, are settled
 
+    int nbp = 1;                             // bins per round of the reduction below (a power of two), lanes per bin, lane's group
+    while (nbp < numBins && nbp < 32) nbp <<= 1;
+    const int lpb = 32 / nbp, sub = lane / nbp;
     // ---- sweeps: -2 mean, -1 std about the mean, 0..9 clipping iterations (filters.py:466-477) -----------------
 #ifdef OC_EXP_NOSWEEP
     for (int it = -2; it < -2; ++it) {
@@ -1014,17 +1006,28 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
             }
         }
         __syncthreads();
+        // per-bin totals: the lanes of a warp share the bins and the warps' partial sums between them (nbp bins x lpb groups of
+        // warps), then combine by butterfly -- the same additions in every warp, so every copy of the state stays bit-identical
         bool myDone = true;
-        for (int b = lane; b < numBins; b += 32) {
-            OcBinState st = wState[b];
-            if (!st.done) {
-                double c = 0, s = 0, q = 0;
-                for (int w = 0; w < OC_WARPS; ++w) {
+        for (int b0 = 0; b0 < numBins; b0 += 32) {
+            const int b = b0 + (lane & (nbp - 1));
+            const bool live = b < numBins && !wState[b].done;
+            double c = 0, s = 0, q = 0;
+            if (live) {
+                for (int w = sub; w < OC_WARPS; w += lpb) {
                     if ((s_warpBins[w] >> b) & 1ULL) {
                         const double* r = red + ((size_t)w * numBins + b) * 3;
                         c += r[0]; s += r[1]; q += r[2];
                     }
                 }
+            }
+            for (int o = nbp; o < 32; o <<= 1) {
+                c += __shfl_xor_sync(0xffffffffu, c, o);
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                q += __shfl_xor_sync(0xffffffffu, q, o);
+            }
+            if (live && sub == 0) {
+                OcBinState st = wState[b];
                 if (it == -2) {
                     if (c == 0) {
                         st.rms = 0.0;
@@ -1054,8 +1057,8 @@ __global__ void __launch_bounds__(OC_THREADS, 1) cell_rms_onchip_kernel(const T*
                     if (fixed) st.done = 1;
                 }
                 wState[b] = st;
+                myDone = myDone && (st.done != 0);
             }
-            myDone = myDone && (st.done != 0);
         }
         __syncwarp();
         if (__all_sync(0xffffffffu, myDone)) break;   // the same decision in every warp
