@@ -214,7 +214,7 @@ def main():
     ap.add_argument('--precision', default='f64', choices=['f64', 'f32'])
     ap.add_argument('--tiles', type=int, default=TILES_PER_GPU, help='tiles per GPU')
     ap.add_argument('--tiles-per-batch', type=int, default=16)
-    ap.add_argument('--e2e-tiles-per-batch', type=int, default=8, help='batch size of the end-to-end arm (uploads overlap compute)')
+    ap.add_argument('--e2e-tiles-per-batch', default='2,4', help='batch sizes of the end-to-end arm (uploads overlap compute): one size, or a list that is mirrored at the end (2,4 -> 2,4,4,...,4,2)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--kernel-table', default=None, help='write the per-kernel roofline table to this file')
     args = ap.parse_args()
@@ -227,6 +227,8 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    e2eBatch = [int(v) for v in str(args.e2e_tiles_per_batch).split(',')]
+    e2eBatch = e2eBatch[0] if len(e2eBatch) == 1 else e2eBatch
 
     import numpy as np
     import torch
@@ -314,12 +316,12 @@ def main():
     for b in batches:
         b.dev = None
     for _ in range(2):
-        cat = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=args.e2e_tiles_per_batch, precision=args.precision, comm=comm)
+        cat = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=e2eBatch, precision=args.precision, comm=comm)
     barrier()
     device.TRAFFIC['h2d'] = device.TRAFFIC['d2h'] = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cat = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=args.e2e_tiles_per_batch, precision=args.precision, comm=comm)
+        cat = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=e2eBatch, precision=args.precision, comm=comm)
     torch.cuda.synchronize()
     tE2E = maxOverRanks((time.perf_counter() - t0) / args.steps)
     barrier()
@@ -383,7 +385,7 @@ def main():
             'ms_per_step': msStep, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': args.precision, 'data': 'synthetic',
             'config': {'workload': 'configs[1]: BeamMatchedFilter + S/N>4 detection on a 4096x4096 148 GHz map in 16 tiles of 1024x1024 per GPU',
-                       'tiles_per_gpu': nT, 'tile': list(SHAPE), 'freqs': F, 'scales': S, 'tiles_per_batch': args.tiles_per_batch, 'e2e_tiles_per_batch': args.e2e_tiles_per_batch,
+                       'tiles_per_gpu': nT, 'tile': list(SHAPE), 'freqs': F, 'scales': S, 'tiles_per_batch': args.tiles_per_batch, 'e2e_tiles_per_batch': e2eBatch,
                        'l2': 'inputs and intermediates of one step (> 1 GB) exceed the 126 MB L2; no explicit flush',
                        'objects_per_step': nObj},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'step_roofline': stepRoofline,

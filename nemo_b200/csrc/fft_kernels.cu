@@ -146,9 +146,12 @@ template <typename T, int N> struct ColCfg {
     static constexpr int C = CRAW >= 16 ? 16 : CRAW >= 8 ? 8 : CRAW >= 4 ? 4 : CRAW >= 2 ? 2 : 1;
     static constexpr int NT = N / 16;
     static constexpr int THREADS = C * NT;
-    // column stride in shared memory: == 32/C (mod 32) words so a warp's C x (32/C) accesses spread over banks
-    static constexpr int TV = (32 / C) > 0 ? (32 / C) : 1;
-    static constexpr int LD = npad(N) + ((TV - npad(N)) % 32 + 32) % 32;
+    // column stride in shared memory.  One access phase serves 128 bytes: BANKS = 32 floats or 16 doubles (a warp of doubles
+    // takes two phases of 16 lanes).  Lanes run over the C columns first, then over BANKS / C consecutive positions, so a
+    // stride == BANKS / C (mod BANKS) elements gives every lane of a phase its own bank
+    static constexpr int BANKS = 128 / (int)sizeof(T);
+    static constexpr int TV = (BANKS / C) > 0 ? (BANKS / C) : 1;
+    static constexpr int LD = npad(N) + ((TV - npad(N)) % BANKS + BANKS) % BANKS;
     static constexpr size_t SMEM = (size_t)2 * C * LD * sizeof(T);
 };
 

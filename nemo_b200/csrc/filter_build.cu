@@ -85,6 +85,117 @@ __global__ void __launch_bounds__(256) smooth_y_f64_kernel(const double* __restr
     }
 }
 
+// Register-blocked versions of the two passes for a radius known at compile time (sigma = 3 -> radius 12, the only
+// value K2 uses): a thread computes RB = 8 consecutive outputs along the smoothing axis from RB + 2 R inputs it reads once,
+// with the weights in registers -- 4 shared-memory reads per output instead of 25 (the plain kernels above were bound by
+// the shared-memory pipe at ~80 % of its peak).  Same products in the same order, so the results are bit-identical.
+#define GS_RB 8
+__host__ __device__ constexpr int gs_pad(int i) { return i + (i >> 3); }   // one pad word per 8: lanes 8 apart hit different banks
+
+template <typename T, int F, int R>
+__global__ void __launch_bounds__(512) xpower_smooth_x_rb_kernel(const typename V2<T>::type* __restrict__ fmaps,
+                                                                 double* __restrict__ tmp, int H, int W, GaussW g) {
+    typedef typename V2<T>::type C2;
+    constexpr int P = F * (F + 1) / 2;
+    extern __shared__ double s_np[];  // [P][gs_pad(W + 2 R) + 1], position x + R holds kx = x, reflected halos on both sides
+    const int LD = gs_pad(W + 2 * R) + 1;
+    const int ky = blockIdx.x, b = blockIdx.y;
+    const int Wc = W / 2 + 1;
+    const int kym = (H - ky) % H;
+    const C2* base = fmaps + (size_t)b * F * H * Wc;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        const int row = (x < Wc) ? ky : kym;
+        const int col = (x < Wc) ? x : (W - x);
+        double re[F], im[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            const C2 v = base[((size_t)f * H + row) * Wc + col];
+            re[f] = (double)v.x;
+            im[f] = (double)v.y;
+        }
+        int p = 0;
+#pragma unroll
+        for (int i = 0; i < F; ++i)
+#pragma unroll
+            for (int j = i; j < F; ++j) {
+                s_np[p * LD + gs_pad(x + R)] = re[i] * re[j] + im[i] * im[j];
+                ++p;
+            }
+    }
+    __syncthreads();
+    for (int h = threadIdx.x; h < 2 * R * P; h += blockDim.x) {     // scipy 'reflect': position -1 - h mirrors h, W + h mirrors W - 1 - h
+        const int p = h / (2 * R), k = h % (2 * R);
+        double* s = s_np + p * LD;
+        if (k < R) s[gs_pad(R - 1 - k)] = s[gs_pad(R + k)];
+        else s[gs_pad(W + R + (k - R))] = s[gs_pad(W + R - 1 - (k - R))];
+    }
+    __syncthreads();
+    double w[2 * R + 1];
+#pragma unroll
+    for (int d = 0; d <= 2 * R; ++d) w[d] = g.w[d];
+    double* out = tmp + ((size_t)b * P * H + ky) * W;
+    for (int x0 = threadIdx.x * GS_RB; x0 < W; x0 += blockDim.x * GS_RB) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const double* s = s_np + p * LD;
+            double acc[GS_RB];
+#pragma unroll
+            for (int o = 0; o < GS_RB; ++o) acc[o] = 0;
+#pragma unroll
+            for (int d = 0; d < GS_RB + 2 * R; ++d) {
+                const double v = s[gs_pad(x0 + d)];
+#pragma unroll
+                for (int o = 0; o < GS_RB; ++o)
+                    if (d - o >= 0 && d - o <= 2 * R) acc[o] += w[d - o] * v;
+            }
+            double* dst = out + (size_t)p * H * W + x0;
+            if (x0 + GS_RB <= W) {
+#pragma unroll
+                for (int o = 0; o < GS_RB; o += 2) *reinterpret_cast<double2*>(dst + o) = make_double2(acc[o], acc[o + 1]);
+            } else {
+#pragma unroll
+                for (int o = 0; o < GS_RB; ++o)
+                    if (x0 + o < W) dst[o] = acc[o];
+            }
+        }
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(512) smooth_y_rb_kernel(const double* __restrict__ in, double* __restrict__ out, int H, int W, GaussW g) {
+    constexpr int TY = 16 * GS_RB;     // rows per CTA: 16 thread rows x 8 outputs
+    extern __shared__ double s_t[];    // [TY + 2 R][32]
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * TY;
+    const size_t plane = (size_t)blockIdx.z * H * W;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x = x0 + tx;
+    for (int i = ty; i < TY + 2 * R; i += 16) {
+        const int y = reflect_idx(y0 - R + i, H);
+        s_t[i * 32 + tx] = (x < W) ? in[plane + (size_t)y * W + x] : 0.0;
+    }
+    __syncthreads();
+    if (x >= W) return;
+    double w[2 * R + 1];
+#pragma unroll
+    for (int d = 0; d <= 2 * R; ++d) w[d] = g.w[d];
+    double acc[GS_RB];
+#pragma unroll
+    for (int o = 0; o < GS_RB; ++o) acc[o] = 0;
+    const int i0 = ty * GS_RB;
+#pragma unroll
+    for (int d = 0; d < GS_RB + 2 * R; ++d) {
+        const double v = s_t[(i0 + d) * 32 + tx];
+#pragma unroll
+        for (int o = 0; o < GS_RB; ++o)
+            if (d - o >= 0 && d - o <= 2 * R) acc[o] += w[d - o] * v;
+    }
+#pragma unroll
+    for (int o = 0; o < GS_RB; ++o) {
+        const int y = y0 + i0 + o;
+        if (y < H) out[plane + (size_t)y * W + x] = acc[o];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // K3.  Solve the F x F system with partial pivoting (LAPACK-style); an exactly zero pivot marks the matrix
 // singular and yields zeros, which is what the reference's "except: continue" leaves in self.filt.
@@ -555,6 +666,21 @@ template <typename T, int F>
 static int xpower_smooth_tf(const void* fmaps, double* cov, double* tmp, int B, int H, int W, const GaussW& g, cudaStream_t st) {
     typedef typename V2<T>::type C2;
     constexpr int P = F * (F + 1) / 2;
+    constexpr int R = 12;     // gauss_radius(3.0): the register-blocked kernels are compiled for it
+    if (g.r == R && W >= 2 * R && (W % 2) == 0) {
+        const size_t smem = (size_t)P * (gs_pad(W + 2 * R) + 1) * sizeof(double);
+        NB_REQUIRE(smem <= 200 * 1024, NB_ERR_UNSUPPORTED, "nb_xpower_smooth: F=%d, W=%d needs too much shared memory", F, W);
+        if (smem > 48 * 1024)
+            NB_CHECK_CUDA(cudaFuncSetAttribute(xpower_smooth_x_rb_kernel<T, F, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int threads = ((W + GS_RB - 1) / GS_RB + 31) / 32 * 32;
+        if (threads > 512) threads = 512;
+        { NB_PROF_BEGIN(st); xpower_smooth_x_rb_kernel<T, F, R><<<dim3(H, B), threads, smem, st>>>((const C2*)fmaps, tmp, H, W, g); NB_PROF_END("xpower_smooth_x_kernel", st); }
+        NB_CHECK_LAUNCH();
+        const size_t smem2 = (size_t)(16 * GS_RB + 2 * R) * 32 * sizeof(double);
+        { NB_PROF_BEGIN(st); smooth_y_rb_kernel<R><<<dim3((W + 31) / 32, (H + 16 * GS_RB - 1) / (16 * GS_RB), B * P), 512, smem2, st>>>(tmp, cov, H, W, g); NB_PROF_END("smooth_y_f64_kernel", st); }
+        NB_CHECK_LAUNCH();
+        return NB_OK;
+    }
     const size_t smem = (size_t)P * W * sizeof(double);
     NB_REQUIRE(smem <= 200 * 1024, NB_ERR_UNSUPPORTED, "nb_xpower_smooth: F=%d, W=%d needs too much shared memory", F, W);
     if (smem > 48 * 1024)

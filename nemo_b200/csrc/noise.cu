@@ -1187,7 +1187,7 @@ __global__ void __launch_bounds__(256) edge_rows_kernel(const T* __restrict__ ma
     }
 }
 
-#define EC_SEG 32
+#define EC_SEG 64
 struct PaintArgs {   // what edge_cols_final_kernel<T, true> needs to take the RMS straight from the cell table
     const void* wmed;
     const double* table;
@@ -1213,6 +1213,10 @@ __global__ void __launch_bounds__(128) edge_cols_final_kernel(T* map, T* rms, co
     const int ye = min(ys + EC_SEG, H);
     int kLo = 0, kHi = 0;
     if constexpr (PAINT) paint_axis_range(x, ch.x, pa.nx, pa.ov, W, kLo, kHi);   // the same for every row of this column
+    // the last-written candidate cell (iHi, kHi) always covers the pixel and nearly always paints it; while the rows of this
+    // column stay in the same cell and the weight stays in the same bin of it, the value is the one found for the row above
+    int cacheI = -1;
+    double cacheLo = 0.0, cacheHi = 0.0, cacheVal = 0.0;
     for (int y = ys; y < ye; ++y) {
         const size_t o = (size_t)y * W + x;
         const T m0 = map[ib + o];
@@ -1221,7 +1225,32 @@ __global__ void __launch_bounds__(128) edge_cols_final_kernel(T* map, T* rms, co
             const double w = (double)reinterpret_cast<const T*>(pa.wmed)[tb + o];
             int iLo, iHi;
             paint_axis_range(y, ch.y, pa.ny, pa.ov, H, iLo, iHi);
-            r0 = (T)paint_value_in(w, x, y, img, ch, pa.nx, pa.ov, pa.numBins, pa.table, pa.edges, H, W, pa.ny * pa.nx, iLo, iHi, kLo, kHi);
+            if (iHi == cacheI && w >= cacheLo && w < cacheHi) {
+                r0 = (T)cacheVal;
+            } else {
+                const int nCells = pa.ny * pa.nx, cell = iHi * pa.nx + kHi;
+                const double* edg = pa.edges + ((size_t)img * nCells + cell) * (pa.numBins + 1);
+                const double e0 = edg[0];
+                double val = 0.0;
+                cacheI = -1;
+                if (!isnan(e0) && w >= e0 && w < edg[pa.numBins]) {
+                    int lob = 0, hib = pa.numBins;
+                    while (hib - lob > 1) {
+                        const int mid = (lob + hib) >> 1;
+                        if (w >= edg[mid]) lob = mid; else hib = mid;
+                    }
+                    val = pa.table[((size_t)img * nCells + cell) * pa.numBins + lob];
+                    if (val > 0.0) {
+                        cacheI = iHi;
+                        cacheLo = edg[lob];
+                        cacheHi = edg[lob + 1];
+                        cacheVal = val;
+                    }
+                }
+                if (!(val > 0.0))   // the first candidate paints nothing here: the general search over all candidates
+                    val = paint_value_in(w, x, y, img, ch, pa.nx, pa.ov, pa.numBins, pa.table, pa.edges, H, W, nCells, iLo, iHi, kLo, kHi);
+                r0 = (T)val;
+            }
         } else {
             r0 = rms[ib + o];
         }

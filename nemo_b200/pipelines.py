@@ -520,10 +520,51 @@ def stageTiles(config, tilesPerBatch=8, precision=None):
     `config` so that repeated runs (source-injection iterations, benchmarks) start from pinned memory."""
     ops = device.getOps(precision)
     tileNames = list(config.tileNames)
-    config._staged = {'tilesPerBatch': tilesPerBatch, 'precision': ops.precision,
-                      'batches': [TileBatch(ops, tileNames[i:i + tilesPerBatch], config.tileMaps)
-                                  for i in range(0, len(tileNames), tilesPerBatch)]}
+    config._staged = {'tilesPerBatch': _batchKey(tilesPerBatch), 'precision': ops.precision,
+                      'batches': [TileBatch(ops, tileNames[i:j], config.tileMaps)
+                                  for i, j in _batchBounds(len(tileNames), tilesPerBatch)]}
     return config._staged['batches']
+
+
+def _batchKey(tilesPerBatch):
+    return int(tilesPerBatch) if isinstance(tilesPerBatch, (int, np.integer)) else tuple(int(v) for v in tilesPerBatch)
+
+
+def _batchBounds(numTiles, tilesPerBatch):
+    """[(first, last + 1)] of the batches.  tilesPerBatch: a batch size, or a sequence of sizes -- the last size repeats until
+    the tiles run out, except that the list is mirrored at the end when it starts small: [2, 4] gives 2, 4, 4, ..., 4, 2.  A
+    small first batch starts the device work sooner (nothing overlaps its upload), a small last one shortens the tail that
+    no upload overlaps."""
+    if isinstance(tilesPerBatch, (int, np.integer)):
+        sizes = [int(tilesPerBatch)] * ((numTiles + int(tilesPerBatch) - 1) // int(tilesPerBatch))
+    else:
+        head = [int(v) for v in tilesPerBatch]
+        if not head or min(head) < 1:
+            raise Exception("tilesPerBatch needs positive batch sizes")
+        tail = head[:-1][::-1]
+        sizes = []
+        left = numTiles - sum(tail)
+        for v in head:
+            if left <= 0:
+                break
+            sizes.append(min(v, left))
+            left -= sizes[-1]
+        while left > 0:
+            sizes.append(min(head[-1], left))
+            left -= sizes[-1]
+        left = numTiles - sum(sizes)
+        for v in tail:
+            if left <= 0:
+                break
+            sizes.append(min(v, left))
+            left -= sizes[-1]
+    bounds, first = [], 0
+    for v in sizes:
+        if first >= numTiles:
+            break
+        bounds.append((first, min(first + v, numTiles)))
+        first += v
+    return bounds
 
 
 def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=False, measureFluxes=True, invertMap=False,
@@ -564,7 +605,7 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     catalogDict = {}
     noiseTables = {}
     staged = getattr(config, '_staged', None)
-    if staged is None or staged['tilesPerBatch'] != tilesPerBatch or staged['precision'] != ops.precision:
+    if staged is None or staged['tilesPerBatch'] != _batchKey(tilesPerBatch) or staged['precision'] != ops.precision:
         batches = stageTiles(config, tilesPerBatch, precision)
     else:
         batches = staged['batches']

@@ -195,7 +195,7 @@ def test_batched_pipeline_matches_per_tile_oracle(report):
     parDict = {'mapFilters': filtersList, 'photFilter': 'Arnaud_M2e14_z0p4', 'thresholdSigma': 4.0, 'minObjPix': 1,
                'findCenterOfMass': True, 'useInterpolator': True, 'rejectBorder': 0}
     config = pipelines.SimpleConfig(parDict, tileMaps)
-    opt = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=2)
+    opt = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=[1, 2])     # batches of 1 and 2 tiles
     # oracle: the reference's loop order (pipelines.py:179-286)
     ordered = pipelines._orderedFilters(config.parDict)
     assert ordered[0]['label'] == 'Arnaud_M2e14_z0p4'
