@@ -183,13 +183,18 @@ def vstack(tables):
     out = Table()
     if not tables:
         return out
-    keys = tables[0].keys()
-    for k in keys:
-        if all(k in t.keys() and t._cols.isDeferred(k) for t in tables):
-            parts = [t._cols.raw(k) for t in tables]
+    cols = [t._cols for t in tables]
+    lengths = None
+    for k in tables[0].keys():
+        if all(k in c and c.isDeferred(k) for c in cols):
+            parts = [c.raw(k) for c in cols]
             out._cols.defer(k, lambda parts=parts: np.concatenate([p.value() for p in parts]))
+        elif all(k in c for c in cols):
+            out._cols.put(k, np.concatenate([c[k] for c in cols]))
         else:
-            out._cols[k] = np.concatenate([t[k] if k in t.keys() else np.full(len(t), -99) for t in tables])
+            if lengths is None:
+                lengths = [len(t) for t in tables]
+            out._cols.put(k, np.concatenate([c[k] if k in c else np.full(m, -99) for c, m in zip(cols, lengths)]))
     return out
 
 
@@ -257,20 +262,42 @@ def catalogListToTab(catalogList, keysToWrite=COLUMN_NAMES):
     return tab
 
 
+def _candidatePairs(ra, dec, radiusDeg):
+    """Index pairs (i, j), each once, that may lie within radiusDeg of each other: a superset cut on |d dec| and |d RA|
+    (a great-circle or tangent-plane separation below the radius implies both), found by a sweep over the declination-sorted
+    rows with searchsorted -- no tree to build."""
+    n = len(ra)
+    order = np.argsort(dec, kind='stable')
+    ds = dec[order]
+    hi = np.searchsorted(ds, ds + radiusDeg, side='right')      # rows order[i + 1 : hi[i]] are within the declination window of row i
+    idx = np.arange(n)
+    cnt = hi - (idx + 1)
+    total = int(cnt.sum())
+    if total == 0:
+        return np.zeros((0, 2), dtype=np.intp)
+    first = np.repeat(idx, cnt)
+    start = np.cumsum(cnt) - cnt
+    second = first + 1 + (np.arange(total) - np.repeat(start, cnt))
+    i, j = order[first], order[second]
+    dRA = np.abs(ra[i] - ra[j])
+    dRA = np.minimum(dRA, 360.0 - dRA)
+    cosMin = np.cos(np.radians(min(max(abs(ds[0]), abs(ds[-1])) + radiusDeg, 90.0)))     # smallest cos(dec) any pair can see
+    if cosMin > 1e-6:
+        keep = dRA <= radiusDeg / cosMin * 1.0001
+        i, j = i[keep], j[keep]
+    return np.stack([i, j], axis=1)
+
+
 def _crossMatchKeepBest(ra, dec, snr, radiusDeg):
     """Boolean mask of rows to remove: for every row, all rows within radiusDeg of it except the one with the highest
     S/N (first one on ties) are dropped.  Same outcome as the reference's O(n^2) loop (catalogs.py:171-183): candidate
-    pairs come from a k-d tree on unit vectors, the reference's (tangent-plane, centred on the row) separation decides,
+    pairs come from a declination-sorted sweep, the reference's (tangent-plane, centred on the row) separation decides,
     and the rule is applied to all rows at once."""
-    from scipy.spatial import cKDTree
     n = len(ra)
     toRemove = np.zeros(n, dtype=bool)
     if n < 2:
         return toRemove
-    a, d = np.radians(ra), np.radians(dec)
-    xyz = np.stack([np.cos(d) * np.cos(a), np.cos(d) * np.sin(a), np.sin(d)], axis=1)
-    chord = 2 * np.sin(np.radians(radiusDeg * 1.01) / 2)
-    pairs = cKDTree(xyz).query_pairs(chord, output_type='ndarray')
+    pairs = _candidatePairs(ra, dec, radiusDeg * 1.01)
     if len(pairs) == 0:
         return toRemove
     # directed edges centre -> member, both directions; the separation is measured about the centre, as the reference does

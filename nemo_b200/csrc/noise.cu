@@ -1188,6 +1188,7 @@ __global__ void __launch_bounds__(256) edge_rows_kernel(const T* __restrict__ ma
 }
 
 #define EC_SEG 64
+#define EC_UNR 4      // rows whose loads are issued together
 struct PaintArgs {   // what edge_cols_final_kernel<T, true> needs to take the RMS straight from the cell table
     const void* wmed;
     const double* table;
@@ -1217,60 +1218,89 @@ __global__ void __launch_bounds__(128) edge_cols_final_kernel(T* map, T* rms, co
     // column stay in the same cell and the weight stays in the same bin of it, the value is the one found for the row above
     int cacheI = -1;
     double cacheLo = 0.0, cacheHi = 0.0, cacheVal = 0.0;
-    for (int y = ys; y < ye; ++y) {
-        const size_t o = (size_t)y * W + x;
-        const T m0 = map[ib + o];
-        T r0;
-        if constexpr (PAINT) {
-            const double w = (double)reinterpret_cast<const T*>(pa.wmed)[tb + o];
-            int iLo, iHi;
-            paint_axis_range(y, ch.y, pa.ny, pa.ov, H, iLo, iHi);
-            if (iHi == cacheI && w >= cacheLo && w < cacheHi) {
-                r0 = (T)cacheVal;
+    // rows are taken EC_UNR at a time with all their loads issued before any store: map and rms are read and written in place,
+    // so the compiler must keep every load behind the previous row's stores and a row-by-row loop pays a full memory latency
+    // per row
+    for (int yb = ys; yb < ye; yb += EC_UNR) {
+        T m0v[EC_UNR], wv[EC_UNR], rv[EC_UNR];
+        unsigned char psv8[EC_UNR], sv8[EC_UNR], raIn[EC_UNR], raOut[EC_UNR];
+#pragma unroll
+        for (int u = 0; u < EC_UNR; ++u) {
+            const int y = yb + u;
+            const bool ok = y < ye;
+            const size_t o = (size_t)(ok ? y : ys) * W + x;
+            m0v[u] = map[ib + o];
+            if constexpr (PAINT) {
+                wv[u] = reinterpret_cast<const T*>(pa.wmed)[tb + o];
+                rv[u] = (T)0;
             } else {
-                const int nCells = pa.ny * pa.nx, cell = iHi * pa.nx + kHi;
-                const double* edg = pa.edges + ((size_t)img * nCells + cell) * (pa.numBins + 1);
-                const double e0 = edg[0];
-                double val = 0.0;
-                cacheI = -1;
-                if (!isnan(e0) && w >= e0 && w < edg[pa.numBins]) {
-                    int lob = 0, hib = pa.numBins;
-                    while (hib - lob > 1) {
-                        const int mid = (lob + hib) >> 1;
-                        if (w >= edg[mid]) lob = mid; else hib = mid;
-                    }
-                    val = pa.table[((size_t)img * nCells + cell) * pa.numBins + lob];
-                    if (val > 0.0) {
-                        cacheI = iHi;
-                        cacheLo = edg[lob];
-                        cacheHi = edg[lob + 1];
-                        cacheVal = val;
-                    }
-                }
-                if (!(val > 0.0))   // the first candidate paints nothing here: the general search over all candidates
-                    val = paint_value_in(w, x, y, img, ch, pa.nx, pa.ov, pa.numBins, pa.table, pa.edges, H, W, nCells, iLo, iHi, kLo, kHi);
-                r0 = (T)val;
+                wv[u] = (T)0;
+                rv[u] = rms[ib + o];
             }
-        } else {
-            r0 = rms[ib + o];
+            psv8[u] = ps[tb + o];
+            sv8[u] = survey[tb + o];
+            raIn[u] = 0;
+            raOut[u] = 0;
+            if (trim > 0 && ok && y + 1 < ye) {   // the rows that enter / leave the window when it slides down from row y
+                raIn[u] = ra[(size_t)reflect_idx(y + 1 + hi, H) * W + x];
+                raOut[u] = ra[(size_t)reflect_idx(y + lo, H) * W + x];
+            }
         }
-        const T edge = (trim > 0 && cnt > 0) ? (T)0 : (T)1;
-        const T psv = (T)ps[tb + o], sv = (T)survey[tb + o];
-        T snv = (r0 > (T)0) ? m0 / r0 : m0;
-        T d = m0 * edge;
-        const T sm1 = edge * sv * psv;
-        if (!realSpace) d = d * sm1;
-        const bool apodOk = (apodPix <= 0) || (x >= apodPix - 1 && x <= W - apodPix && y >= apodPix - 1 && y <= H - apodPix);
-        const T mo = apodOk ? sm1 : (T)0;
-        snv = snv * mo;
-        if (snv != snv) snv = (T)0;
-        map[ib + o] = d;
-        sn[ib + o] = snv;
-        rms[ib + o] = r0 * mo;
-        maskOut[ib + o] = (mo != (T)0) ? 1 : 0;
-        if (trim > 0 && y + 1 < ye) {  // slide the window down by one row
-            cnt += ra[(size_t)reflect_idx(y + 1 + hi, H) * W + x];
-            cnt -= ra[(size_t)reflect_idx(y + lo, H) * W + x];
+#pragma unroll
+        for (int u = 0; u < EC_UNR; ++u) {
+            const int y = yb + u;
+            if (y >= ye) break;
+            const size_t o = (size_t)y * W + x;
+            const T m0 = m0v[u];
+            T r0;
+            if constexpr (PAINT) {
+                const double w = (double)wv[u];
+                int iLo, iHi;
+                paint_axis_range(y, ch.y, pa.ny, pa.ov, H, iLo, iHi);
+                if (iHi == cacheI && w >= cacheLo && w < cacheHi) {
+                    r0 = (T)cacheVal;
+                } else {
+                    const int nCells = pa.ny * pa.nx, cell = iHi * pa.nx + kHi;
+                    const double* edg = pa.edges + ((size_t)img * nCells + cell) * (pa.numBins + 1);
+                    const double e0 = edg[0];
+                    double val = 0.0;
+                    cacheI = -1;
+                    if (!isnan(e0) && w >= e0 && w < edg[pa.numBins]) {
+                        int lob = 0, hib = pa.numBins;
+                        while (hib - lob > 1) {
+                            const int mid = (lob + hib) >> 1;
+                            if (w >= edg[mid]) lob = mid; else hib = mid;
+                        }
+                        val = pa.table[((size_t)img * nCells + cell) * pa.numBins + lob];
+                        if (val > 0.0) {
+                            cacheI = iHi;
+                            cacheLo = edg[lob];
+                            cacheHi = edg[lob + 1];
+                            cacheVal = val;
+                        }
+                    }
+                    if (!(val > 0.0))   // the first candidate paints nothing here: the general search over all candidates
+                        val = paint_value_in(w, x, y, img, ch, pa.nx, pa.ov, pa.numBins, pa.table, pa.edges, H, W, nCells, iLo, iHi, kLo, kHi);
+                    r0 = (T)val;
+                }
+            } else {
+                r0 = rv[u];
+            }
+            const T edge = (trim > 0 && cnt > 0) ? (T)0 : (T)1;
+            const T psv = (T)psv8[u], sv = (T)sv8[u];
+            T snv = (r0 > (T)0) ? m0 / r0 : m0;
+            T d = m0 * edge;
+            const T sm1 = edge * sv * psv;
+            if (!realSpace) d = d * sm1;
+            const bool apodOk = (apodPix <= 0) || (x >= apodPix - 1 && x <= W - apodPix && y >= apodPix - 1 && y <= H - apodPix);
+            const T mo = apodOk ? sm1 : (T)0;
+            snv = snv * mo;
+            if (snv != snv) snv = (T)0;
+            map[ib + o] = d;
+            sn[ib + o] = snv;
+            rms[ib + o] = r0 * mo;
+            maskOut[ib + o] = (mo != (T)0) ? 1 : 0;
+            cnt += (int)raIn[u] - (int)raOut[u];      // slide the window down by one row
         }
     }
 }

@@ -251,3 +251,29 @@ def test_batch_bounds_cover_all_tiles_in_order():
     assert _batchKey([2, 4]) == _batchKey((2, 4)) == (2, 4) and _batchKey(8) == 8
     with pytest.raises(Exception):
         _batchBounds(4, [0, 2])
+
+
+def test_cross_match_equals_the_quadratic_rule():
+    """The sweep-based cross-match removes exactly the rows the reference's O(n^2) loop removes (catalogs.py:171-183),
+    including across RA = 0 and at high declination."""
+    from nemo_b200 import catalogs, wcs
+
+    def brute(ra, dec, snr, r):
+        rem = np.zeros(len(ra), bool)
+        for i in range(len(ra)):
+            m = np.flatnonzero(wcs.calcAngSepDeg(ra[i], dec[i], ra, dec) < r)
+            if len(m) > 1:
+                best = m[np.argmax(snr[m])]
+                rem[m[m != best]] = True
+        return rem
+
+    for seed, dec0, ra0 in [(0, 0.0, 0.0), (1, 60.0, 10.0), (2, -30.0, 359.0)]:
+        rng = np.random.default_rng(seed)
+        n = 500
+        ra = (rng.uniform(0, 1.5, n) + ra0) % 360.0
+        dec = rng.uniform(-0.8, 0.8, n) + dec0
+        snr = rng.uniform(4, 50, n)
+        got = catalogs._crossMatchKeepBest(ra, dec, snr, catalogs.XMATCH_RADIUS_DEG)
+        want = brute(ra, dec, snr, catalogs.XMATCH_RADIUS_DEG)
+        assert want.sum() > 20
+        assert np.array_equal(got, want)
