@@ -214,7 +214,8 @@ def main():
     ap.add_argument('--precision', default='f64', choices=['f64', 'f32'])
     ap.add_argument('--tiles', type=int, default=TILES_PER_GPU, help='tiles per GPU')
     ap.add_argument('--tiles-per-batch', type=int, default=16)
-    ap.add_argument('--e2e-tiles-per-batch', default='2,4', help='batch sizes of the end-to-end arm (uploads overlap compute): one size, or a list that is mirrored at the end (2,4 -> 2,4,4,...,4,2)')
+    ap.add_argument('--e2e-tiles-per-batch', default='4', help='batch sizes of the end-to-end arm (uploads overlap compute): one size, or a list that is mirrored at the end (2,4 -> 2,4,4,...,4,2)')
+    ap.add_argument('--pipeline-depth', type=int, default=2, help='batches in flight on the device behind the one whose catalogs the host assembles (device-resident arm)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--kernel-table', default=None, help='write the per-kernel roofline table to this file')
     args = ap.parse_args()
@@ -278,14 +279,14 @@ def main():
         return sum(len(v['catalog']) for v in res[0].values())
 
     def deviceSteps(n):
-        pipe = pipelines.BatchPipeline(ops, filtersList, templates, parDict, undoPixelWindow=True)
+        pipe = pipelines.BatchPipeline(ops, filtersList, templates, parDict, undoPixelWindow=True, depth=args.pipeline_depth)
         nObj = 0
         for _ in range(n):
             for b in batches:
                 out = pipe.submit(b, upload=False)
                 if out is not None:
                     nObj += countObjects(out)
-        nObj += countObjects(pipe.flush())
+        nObj += sum(countObjects(out) for out in pipe.flush())
         return nObj // n
 
     nObj = deviceSteps(args.warmup)

@@ -247,7 +247,7 @@ class BatchPipeline(object):
     nothing is shared between batches except the read-only templates."""
 
     def __init__(self, ops, filtersList, templates, parDict, undoPixelWindow=True, measureFluxes=True, invertMap=False,
-                 keepMaps=False, useCachedRMSMap=False, useGraphs=True):
+                 keepMaps=False, useCachedRMSMap=False, useGraphs=True, depth=2):
         self.ops, self.filtersList, self.templates, self.parDict = ops, filtersList, templates, parDict
         # the ~40 launches of a batch are captured once per (slot, shape, input buffers) into a CUDA graph and replayed:
         # the host then spends microseconds, not a millisecond, queueing a batch.  Graphs live on the Ops object.
@@ -255,21 +255,26 @@ class BatchPipeline(object):
         self.graphs = ops.__dict__.setdefault('_batchGraphs', {})
         self.undoPixelWindow, self.measureFluxes, self.invertMap, self.keepMaps = undoPixelWindow, measureFluxes, invertMap, keepMaps
         self.useCachedRMSMap = useCachedRMSMap
+        # `depth` batches may be queued on the device while the host assembles the catalogs of the oldest one: with two, the
+        # upload of batch i + 2 is already in the copy queue when the host starts waiting for batch i, so the copy engine
+        # never waits for the host.  Every slot has its own stream (and its own input buffers when it uploads).
+        self.depth = max(1, int(depth))
         torch = ops.torch
         streams = getattr(ops, '_pipeStreams', None)
         if streams is None:
-            streams = ops._pipeStreams = [torch.cuda.Stream(device=ops.device), torch.cuda.Stream(device=ops.device)]
-        self.streams = streams
+            streams = ops._pipeStreams = []
+        while len(streams) < self.depth + 1:
+            streams.append(torch.cuda.Stream(device=ops.device))
+        self.streams = streams[:self.depth + 1]
         self.main = torch.cuda.current_stream(ops.device)
-        for st in streams:
+        for st in self.streams:
             st.wait_stream(self.main)      # templates and resident inputs were produced on the caller's stream
-        self.pending = None
+        self.pending = []
         self.count = 0
 
     def _finish(self):
         torch = self.ops.torch
-        job, st, release = self.pending
-        self.pending = None
+        job, st, release = self.pending.pop(0)
         with torch.cuda.stream(st):
             out = finishTileBatch(job, measureFluxes=self.measureFluxes, keepMaps=self.keepMaps)
         if release:
@@ -317,9 +322,11 @@ class BatchPipeline(object):
         return entry
 
     def submit(self, batch, upload=True, cache=None):
+        """Queues the device work of `batch`; returns the (catalogDict, extras) of the oldest queued batch once more than
+        `depth` - 1 others are in flight behind it, else None."""
         from . import _lib
         torch = self.ops.torch
-        slot = self.count % 2
+        slot = self.count % len(self.streams)
         st = self.streams[slot]
         self.count += 1
         useGraph = self.useGraphs and cache is None and not _lib.profEnabled()
@@ -341,32 +348,34 @@ class BatchPipeline(object):
                 job = startTileBatch(self.ops, batch, self.filtersList, self.templates, self.parDict,
                                      undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap, cache=cache,
                                      useCachedRMSMap=self.useCachedRMSMap)
-        out = self._finish() if self.pending is not None else None
-        self.pending = (job, st, upload)
-        return out
+        self.pending.append((job, st, upload))
+        # a slot's buffers (graph outputs, static inputs) are reused by the batch submitted len(streams) calls later, so at
+        # most `depth` jobs may stay unread
+        return self._finish() if len(self.pending) > self.depth else None
 
     def flush(self):
-        out = self._finish() if self.pending is not None else None
+        """The results of every batch still in flight, oldest first (a list; empty when nothing is pending)."""
+        outs = []
+        while self.pending:
+            outs.append(self._finish())
         for st in self.streams:
             self.main.wait_stream(st)
-        return out
+        return outs
 
 
 def processBatches(ops, batches, filtersList, templates, parDict, upload=True, undoPixelWindow=True, measureFluxes=True,
-                   invertMap=False, keepMaps=False, caches=None, useCachedRMSMap=False, useGraphs=True):
+                   invertMap=False, keepMaps=False, caches=None, useCachedRMSMap=False, useGraphs=True, depth=2):
     """Runs several tile batches through a BatchPipeline; returns the list of (catalogDict, extras), one per batch, in order.
     caches: per-batch filter / RMS caches (see startTileBatch), or None."""
     pipe = BatchPipeline(ops, filtersList, templates, parDict, undoPixelWindow=undoPixelWindow, measureFluxes=measureFluxes,
                          invertMap=invertMap, keepMaps=keepMaps, useCachedRMSMap=useCachedRMSMap,
-                         useGraphs=useGraphs and not keepMaps)
+                         useGraphs=useGraphs and not keepMaps, depth=depth)
     results = []
     for i, batch in enumerate(batches):
         out = pipe.submit(batch, upload=upload and batch.dev is None, cache=caches[i] if caches is not None else None)
         if out is not None:
             results.append(out)
-    out = pipe.flush()
-    if out is not None:
-        results.append(out)
+    results.extend(pipe.flush())
     return results
 
 
