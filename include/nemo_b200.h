@@ -109,6 +109,11 @@ int nb_template_norm(int prec, const void* map, int B, int H, int W, int mode, d
 int nb_plane_values_at(int prec, const void* fmaps, const void* filtH, const long long* idx, double* out, int B,
                        int S, int F, int H, int W, double* scratch, cudaStream_t stream);
 
+/* Maps as they are on disk (FITS BITPIX -32; the reference's MapDict.loadTile hands such arrays to MapFilter, nemo/maps.py:83-180,
+ * nemo/filters.py:157-164, and numpy widens them in the first arithmetic operation) uploaded as float32 and widened on the
+ * device: out[i] = (double) in[i], n elements.  Exact; halves the host-to-device bytes of a tile. */
+int nb_widen_f32(const float* in, double* out, long long n, cudaStream_t stream);
+
 /* Per-pixel median over frequencies of the weight maps (nemo/filters.py:360-363). */
 int nb_median_weights(int prec, const void* weights, void* out, int B, int F, int H, int W, cudaStream_t stream);
 

@@ -1146,11 +1146,15 @@ __global__ void __launch_bounds__(256) edge_rows_kernel(const T* __restrict__ ma
     const unsigned char* p = ps + ((size_t)(img / S) * H + y) * W;
     const int per = (W + blockDim.x - 1) / blockDim.x;
     const int b0 = threadIdx.x * per, b1 = min(b0 + per, W);
+    // zero flags with coalesced loads first, then every thread scans its own run of them in shared memory
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        const T a = m[x] + (T)(1 - (int)p[x]);
+        s_pre[x + 1] = (a == (T)0) ? 1 : 0;
+    }
+    __syncthreads();
     int local = 0;
     for (int x = b0; x < b1; ++x) {
-        const T a = m[x] + (T)(1 - (int)p[x]);
-        const int z = (a == (T)0) ? 1 : 0;
-        local += z;
+        local += s_pre[x + 1];
         s_pre[x + 1] = local;  // local inclusive, offset added below
     }
     s_part[threadIdx.x] = local;
@@ -1385,7 +1389,31 @@ static int snr_mask_t(void* map, void* rms, const unsigned char* ps, const unsig
     return NB_OK;
 }
 
+__global__ void __launch_bounds__(256) widen_f32_kernel(const float4* __restrict__ in, double4* __restrict__ out, long long n4,
+                                                        const float* __restrict__ tailIn, double* __restrict__ tailOut, int nTail) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        const float4 v = in[i];
+        double4 o;
+        o.x = (double)v.x; o.y = (double)v.y; o.z = (double)v.z; o.w = (double)v.w;
+        out[i] = o;
+    }
+    if (i < nTail) tailOut[i] = (double)tailIn[i];
+}
+
 extern "C" {
+
+int nb_widen_f32(const float* in, double* out, long long n, cudaStream_t st) {
+    NB_REQUIRE(in && out && n > 0, NB_ERR_ARG, "nb_widen_f32: bad arguments");
+    NB_REQUIRE(((size_t)in % 16) == 0 && ((size_t)out % 16) == 0, NB_ERR_ARG, "nb_widen_f32: buffers must be 16-byte aligned");
+    const long long n4 = n / 4;
+    const int nTail = (int)(n - 4 * n4);
+    const long long threads = n4 > nTail ? n4 : nTail;
+    { NB_PROF_BEGIN(st); widen_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const float4*)in, (double4*)out, n4, in + 4 * n4,
+                                                                                           out + 4 * n4, nTail); NB_PROF_END("widen_f32_kernel", st); }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
+}
 
 int nb_median_weights(int prec, const void* weights, void* out, int B, int F, int H, int W, cudaStream_t st) {
     NB_REQUIRE(weights && out && B > 0 && F >= 1 && F <= NB_MAX_FREQ, NB_ERR_ARG, "nb_median_weights: bad arguments");

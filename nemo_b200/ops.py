@@ -219,6 +219,16 @@ class Ops(object):
         return out
 
     # -- noise, S/N -------------------------------------------------------------------------------------
+    def widen(self, x):
+        """float32 device tensor -> float64 tensor of the same shape (maps uploaded in their on-disk format)."""
+        torch = self.torch
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            raise Exception("widen expects a contiguous float32 tensor")
+        out = torch.empty(x.shape, dtype=torch.float64, device=x.device)
+        _lib.call('nb_widen_f32', _ptr(x), _ptr(out), x.numel(), self._stream())
+        self.launches += 1
+        return out
+
     def median_weights(self, weights):
         self._check(weights, self.dtype, 'weights')
         B, F, H, W = weights.shape

@@ -228,14 +228,21 @@ def finishFindObjectsBatch(job, wcsList, flagMaskList, labelList, tileNameList, 
     xs2, ys2 = np.empty(K), np.empty(K)
     flags = np.zeros(K, dtype=int)
     lo = 0
+    wcsParams = _wcs.batchParams(wcsList)
+    if wcsParams is not None:      # every image on a CARWCS: all positions in one expression
+        ra, dec = _wcs.batchPix2wcs(wcsParams, cb, cx, cy)
+        ra = np.where(ra < 0, 360.0 + ra, ra)
+        if extraSamples:
+            xs2, ys2 = _wcs.batchWcs2pix(wcsParams, cb, ra, dec)
     for b in np.nonzero(perImage)[0]:
         sl = slice(lo, lo + perImage[b])
         lo += perImage[b]
-        r, d = wcsList[b].pix2wcs(cx[sl], cy[sl])
-        r = np.where(np.asarray(r) < 0, 360.0 + np.asarray(r), r)
-        ra[sl], dec[sl] = r, d
-        if extraSamples:
-            xs2[sl], ys2[sl] = wcsList[b].wcs2pix(ra[sl], dec[sl])
+        if wcsParams is None:
+            r, d = wcsList[b].pix2wcs(cx[sl], cy[sl])
+            r = np.where(np.asarray(r) < 0, 360.0 + np.asarray(r), r)
+            ra[sl], dec[sl] = r, d
+            if extraSamples:
+                xs2[sl], ys2[sl] = wcsList[b].wcs2pix(ra[sl], dec[sl])
         if flagMaskList[b] is not None:
             flags[sl] = np.asarray(flagMaskList[b])[np.round(cy[sl]).astype(int), np.round(cx[sl]).astype(int)]
     # S/N at the object positions and the extra samples, all launched before the one copy back

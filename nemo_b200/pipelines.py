@@ -56,8 +56,13 @@ class TileBatch(object):
         F = len(self.mapDicts[0])
         H, W = self.mapDicts[0][0]['data'].shape
         self.nT, self.F, self.H, self.W = nT, F, H, W
-        data = torch.empty((nT, F, H, W), dtype=ops.dtype, pin_memory=pinned)
-        weights = torch.empty((nT, F, H, W), dtype=ops.dtype, pin_memory=pinned)
+        # maps that arrive as float32 (the on-disk format: FITS BITPIX -32) are staged and uploaded as float32 and widened on
+        # the device -- exact, and half the host-to-device bytes; anything else is staged in the compute type
+        def stageType(key):
+            allF32 = all(np.asarray(m[key]).dtype == np.float32 for md in self.mapDicts for m in md)
+            return torch.float32 if allF32 else ops.dtype
+        data = torch.empty((nT, F, H, W), dtype=stageType('data'), pin_memory=pinned)
+        weights = torch.empty((nT, F, H, W), dtype=stageType('weights'), pin_memory=pinned)
         survey = torch.empty((nT, H, W), dtype=torch.uint8, pin_memory=pinned)
         ps = torch.empty((nT, H, W), dtype=torch.uint8, pin_memory=pinned)
         for t, md in enumerate(self.mapDicts):
@@ -80,7 +85,7 @@ class TileBatch(object):
             for i, m in enumerate(md):
                 if m.get('flagMask') is not None:
                     fm = fm + np.asarray(m['flagMask']) * (i + 1)
-            self.flagMasks.append(fm)
+            self.flagMasks.append(fm if fm.any() else None)      # an all-zero mask flags nothing: no per-object look-up
 
     def refresh(self, tileMaps, keys=('data',)):
         """Re-reads the given arrays of every tile into the pinned staging buffers (the maps changed, e.g. sources were
@@ -96,8 +101,17 @@ class TileBatch(object):
         """Host (pinned) -> device copies of this batch's inputs; asynchronous on the current stream."""
         ops = self.ops
         self.dev = {k: device.countH2D(v).to(ops.device, non_blocking=True) for k, v in self.host.items()}
+        widenStaged(ops, self.dev)
         self.dev['wmed'] = ops.median_weights(self.dev['weights'])
         return self.dev
+
+
+def widenStaged(ops, dev):
+    """float32-staged maps / weights of a device dictionary -> the compute type, in place in the dictionary."""
+    for k in ('data', 'weights'):
+        if dev[k].dtype != ops.dtype:
+            dev[k] = ops.widen(dev[k])
+    return dev
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -286,7 +300,7 @@ class BatchPipeline(object):
         from . import _lib
         ops, torch = self.ops, self.ops.torch
         if upload:
-            ident = 'staged'
+            ident = ('staged', str(batch.host['data'].dtype), str(batch.host['weights'].dtype))
         else:
             ident = tuple(int(batch.dev[k].data_ptr()) for k in ('data', 'weights', 'psMask', 'surveyMask', 'wmed'))
         key = (slot, ident, batch.nT, batch.F, batch.H, batch.W, ops.precision, id(self.templates), self.undoPixelWindow, self.invertMap,
@@ -304,7 +318,8 @@ class BatchPipeline(object):
                 static = dict(batch.dev)
             view = _BatchView(batch, dict(static))
             if upload:
-                view.dev['wmed'] = ops.median_weights(static['weights'])
+                widenStaged(ops, view.dev)
+                view.dev['wmed'] = ops.median_weights(view.dev['weights'])
             # one eager run first: twiddle tables, kernel attributes and other lazy set-up must not happen under capture
             startTileBatch(ops, view, self.filtersList, self.templates, self.parDict, undoPixelWindow=self.undoPixelWindow,
                            invertMap=self.invertMap)
@@ -313,7 +328,9 @@ class BatchPipeline(object):
             n0 = _lib.launchCount()
             with torch.cuda.graph(graph, stream=st):
                 if upload:
-                    view.dev['wmed'] = ops.median_weights(static['weights'])
+                    view.dev.update(static)          # the widening of float32-staged maps is part of the captured work
+                    widenStaged(ops, view.dev)
+                    view.dev['wmed'] = ops.median_weights(view.dev['weights'])
                 job = startTileBatch(ops, view, self.filtersList, self.templates, self.parDict,
                                      undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap)
             nLaunch = _lib.launchCount() - n0

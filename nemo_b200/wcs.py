@@ -56,6 +56,27 @@ class CARWCS(object):
         return min(ra0, ra1), max(ra0, ra1), min(dec0, dec1), max(dec0, dec1)
 
 
+def batchParams(wcsList):
+    """Per-image (crval1, crval2, crpix1, crpix2, pixDeg) arrays when every wcs of the list is a CARWCS, else None: the batched
+    driver then converts the positions of all images of a batch with one expression (same arithmetic as the methods)."""
+    if not all(type(w) is CARWCS for w in wcsList):
+        return None
+    return (np.array([w.crval[0] for w in wcsList]), np.array([w.crval[1] for w in wcsList]),
+            np.array([w.crpix[0] for w in wcsList]), np.array([w.crpix[1] for w in wcsList]),
+            np.array([w.pixDeg for w in wcsList]))
+
+
+def batchPix2wcs(params, owner, x, y):
+    v0, v1, p0, p1, pd = (a[owner] for a in params)
+    return v0 - (np.asarray(x, dtype=np.float64) - p0) * pd, v1 + (np.asarray(y, dtype=np.float64) - p1) * pd
+
+
+def batchWcs2pix(params, owner, RADeg, decDeg):
+    v0, v1, p0, p1, pd = (a[owner] for a in params)
+    dra = (np.asarray(RADeg, dtype=np.float64) - v0 + 180.0) % 360.0 - 180.0
+    return p0 - dra / pd, p1 + (np.asarray(decDeg, dtype=np.float64) - v1) / pd
+
+
 def calcAngSepDeg(RADeg1, decDeg1, RADeg2, decDeg2):
     """Tangent-plane angular separation (what astCoords.calcAngSepDeg returns), degrees."""
     a0, d0 = np.radians(RADeg1), np.radians(decDeg1)

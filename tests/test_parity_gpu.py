@@ -441,3 +441,33 @@ def test_pipeline_driver_with_real_space_filters(report):
         nObj += len(refCat)
     assert nObj >= 2 and len(opt) == nObj
     report("pipeline_real_space", objects=nObj)
+
+
+def test_float32_host_tiles_are_widened_exactly(report):
+    """Tiles handed over as float32 (the on-disk format) are staged and uploaded as float32 and widened on the device: the
+    catalogs equal those of the same values handed over as float64."""
+    from nemo_b200 import pipelines
+    import torch
+    tiles32, tiles64 = {}, {}
+    for t in range(3):
+        md, _ = synth.makeTile(shape=(256, 256), numObjects=6, kind='clusters', seed=300 + t)
+        m32 = [dict(m, data=np.asarray(m['data'], dtype=np.float32), weights=np.asarray(m['weights'], dtype=np.float32)) for m in md]
+        tiles32['tile%d' % t] = m32
+        tiles64['tile%d' % t] = [dict(m, data=np.asarray(m['data'], dtype=np.float64), weights=np.asarray(m['weights'], dtype=np.float64))
+                                 for m in m32]
+    parDict = {'mapFilters': [_arnaud('Arnaud_M2e14_z0p4', 2e14, 0.4)], 'photFilter': None, 'thresholdSigma': 4.0, 'minObjPix': 1,
+               'findCenterOfMass': True, 'useInterpolator': True, 'rejectBorder': 0}
+    c32 = pipelines.SimpleConfig(parDict, tiles32)
+    c64 = pipelines.SimpleConfig(parDict, tiles64)
+    opt32 = pipelines.filterMapsAndMakeCatalogs(c32, verbose=False, tilesPerBatch=2)
+    opt64 = pipelines.filterMapsAndMakeCatalogs(c64, verbose=False, tilesPerBatch=2)
+    assert c32._staged['batches'][0].host['data'].dtype == torch.float32
+    assert c64._staged['batches'][0].host['data'].dtype == torch.float64
+    assert c32._staged['batches'][0].h2dBytes < 0.6 * c64._staged['batches'][0].h2dBytes
+    assert len(opt32) == len(opt64) and len(opt64) >= 3
+    # the widening is exact, so the two runs see the same doubles; the per-object moments are accumulated with atomics (their
+    # order varies from run to run), hence a last-digits tolerance rather than bit equality
+    for k in ['x', 'y', 'SNR', 'y_c', 'RADeg', 'decDeg']:
+        assert np.allclose(np.asarray(opt32[k], dtype=float), np.asarray(opt64[k], dtype=float), rtol=1e-12, atol=1e-12), k
+    assert np.array_equal(np.asarray(opt32['numSigPix'], dtype=float), np.asarray(opt64['numSigPix'], dtype=float))
+    report("float32-staged tiles: %d objects equal (1e-12) to the float64-staged run" % len(opt64))
