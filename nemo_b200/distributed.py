@@ -42,21 +42,34 @@ class Comm(object):
 
     def allGatherArrays(self, arr):
         """All ranks contribute a 2-D array with the same number of columns and dtype; returns the list of every
-        rank's array, in rank order."""
+        rank's array, in rank order.
+
+        One collective in the usual case: every rank sends a fixed-capacity byte buffer whose first eight bytes carry its row
+        count.  The capacity (kept per row size, the same on every rank because every rank sees every count) only grows: when
+        some rank has more rows than fit, all ranks see that in the gathered headers, double the capacity and repeat."""
         torch, dist = self.torch, self.dist
         arr = np.ascontiguousarray(arr)
-        ncols = arr.shape[1]
-        count = torch.tensor([arr.shape[0]], dtype=torch.int64, device=self.device)
-        counts = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(self.size)]
-        dist.all_gather(counts, count)
-        counts = [int(c.item()) for c in counts]
-        nmax = max(max(counts), 1)
-        buf = torch.zeros((nmax, ncols), dtype=torch.from_numpy(arr[:0]).dtype, device=self.device)
-        if arr.shape[0] > 0:
-            buf[:arr.shape[0]] = torch.from_numpy(arr).to(self.device)
-        out = [torch.empty_like(buf) for _ in range(self.size)]
-        dist.all_gather(out, buf)
-        return [o[:n].cpu().numpy() for o, n in zip(out, counts)]
+        n, ncols = arr.shape
+        rowBytes = ncols * arr.dtype.itemsize
+        caps = self.__dict__.setdefault('_gatherCaps', {})
+        cap = caps.get(rowBytes, 256)
+        raw = arr.view(np.uint8).reshape(-1) if arr.size else np.zeros(0, dtype=np.uint8)
+        while True:
+            host = np.zeros(8 + cap * rowBytes, dtype=np.uint8)
+            host[:8] = np.frombuffer(np.int64(n).tobytes(), dtype=np.uint8)
+            m = min(n, cap) * rowBytes
+            host[8:8 + m] = raw[:m]
+            buf = torch.from_numpy(host).to(self.device)
+            out = torch.empty(self.size * host.size, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(out, buf)
+            got = out.cpu().numpy().reshape(self.size, host.size)
+            counts = [int(np.frombuffer(got[r, :8].tobytes(), dtype=np.int64)[0]) for r in range(self.size)]
+            if max(counts) <= cap:
+                caps[rowBytes] = cap
+                return [np.frombuffer(got[r, 8:8 + c * rowBytes].tobytes(), dtype=arr.dtype).reshape(c, ncols) for r, c in enumerate(counts)]
+            while cap < max(counts):
+                cap *= 2
+            caps[rowBytes] = cap
 
     def maxOverRanks(self, value):
         t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.device)
@@ -105,6 +118,12 @@ def packTable(tab, keys, labels=None, tileNames=None):
     return num, strs, numKeys, strKeys
 
 
+def _objectArray(values):
+    out = np.empty(len(values), dtype=object)
+    out[:] = list(values)
+    return out
+
+
 def unpackTable(num, strs, numKeys, strKeys, labels=None, tileNames=None, objIdent='ACT-CL', longNames=False):
     tab = catalogs.Table()
     n = num.shape[0]
@@ -112,9 +131,9 @@ def unpackTable(num, strs, numKeys, strKeys, labels=None, tileNames=None, objIde
     coded = labels is not None and tileNames is not None
     for j, k in enumerate(numKeys):
         if coded and k == 'template':
-            cols[k] = np.array([labels[int(i)] for i in num[:, j]], dtype=object)
+            cols[k] = _objectArray(labels)[num[:, j].astype(np.intp)]
         elif coded and k == 'tileName':
-            cols[k] = np.array([tileNames[int(i)] for i in num[:, j]], dtype=object)
+            cols[k] = _objectArray(tileNames)[num[:, j].astype(np.intp)]
         else:
             cols[k] = num[:, j].copy()
     for j, k in enumerate(strKeys):

@@ -46,6 +46,13 @@ def _worker(rank, world, port, q):
         mine = distributed.shardTiles(tiles, rank, world)
         counts = comm.allGatherArrays(np.array([[len(mine)]], dtype=np.float64))
         assert sum(int(c[0, 0]) for c in counts) == len(tiles)
+        # more rows on one rank than the gather buffer holds at first (256): the capacity grows on every rank alike, and
+        # ragged and empty contributions come back exact
+        big = np.arange((700 if rank == 1 else 0) * 3, dtype=np.float64).reshape(-1, 3) + rank
+        parts = comm.allGatherArrays(big)
+        assert [p.shape for p in parts] == [(0, 3), (700, 3)] and np.array_equal(parts[1], np.arange(2100.0).reshape(-1, 3) + 1)
+        parts = comm.allGatherArrays(np.full((2 + rank, 5), 7 + rank, dtype=np.uint8))
+        assert [p.shape for p in parts] == [(2, 5), (3, 5)] and parts[1].dtype == np.uint8 and int(parts[1][2, 4]) == 8
         keys = pipelines.catalogKeys(False, 'yc', True)
         tab = _rankCatalog(rank) if rank == 0 else _rankCatalog(rank)
         # err columns are not in this toy table: the packer writes -99 for missing numeric columns
