@@ -52,7 +52,7 @@ class Comm(object):
         n, ncols = arr.shape
         rowBytes = ncols * arr.dtype.itemsize
         caps = self.__dict__.setdefault('_gatherCaps', {})
-        cap = caps.get(rowBytes, 256)
+        cap = caps.get(rowBytes, max(4, 65536 // max(rowBytes, 1)))       # rows; about 64 KB to begin with
         raw = arr.view(np.uint8).reshape(-1) if arr.size else np.zeros(0, dtype=np.uint8)
         while True:
             host = np.zeros(8 + cap * rowBytes, dtype=np.uint8)
