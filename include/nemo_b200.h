@@ -117,6 +117,14 @@ int nb_widen_f32(const float* in, double* out, long long n, cudaStream_t stream)
 /* Per-pixel median over frequencies of the weight maps (nemo/filters.py:360-363). */
 int nb_median_weights(int prec, const void* weights, void* out, int B, int F, int H, int W, cudaStream_t stream);
 
+/* MapFilter.makeNoiseMap, noiseGridArcmin = "smart" (nemo/filters.py:366-407): numBins - 1 whole-map bins between the smallest
+ * and the largest median weight (np.linspace edges, strict inequalities on both sides), 3-sigma-clipped standard deviation of the
+ * non-zero map values of each bin, painted to every pixel of the bin when > 0.
+ * map [nImg, H, W]; wmed [nImg / S, H, W].  Outputs: rms [nImg, H, W] T; table [nImg, numBins - 1] fp64 bin RMS values (NULL: not
+ * wanted); edges [nImg / S, numBins] fp64.  scratch: 16 * (nImg / S) + 80 * nImg * max(numBins - 1, 1) + 4 * nImg + 64 bytes. */
+int nb_smart_rms(int prec, const void* map, const void* wmed, int nImg, int S, int H, int W, int numBins, void* rms, double* table,
+                 double* edges, void* scratch, cudaStream_t stream);
+
 /* K6: MapFilter.makeNoiseMap, grid branch, default 3-sigma-clipped estimator (nemo/filters.py:409-481).
  * map [nImg, H, W] (already multiplied by psMask); wmed [nImg / S, H, W] median weights;
  * yChunks host [ny + 1], xChunks host [nx + 1] (np.linspace(..., dtype=int)); overlapPix; numBins.

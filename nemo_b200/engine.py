@@ -22,11 +22,17 @@ FUSED_FILTER_BUILD = os.environ.get('NEMO_B200_FUSED_FILTER_BUILD', '0') == '1'
 # ------------------------------------------------------------------------------------------------------
 # host-side parameter logic
 def noiseGrid(shape, noiseParams, pixDeg):
-    """(yChunks, xChunks, overlapPix, numBins) of MapFilter.makeNoiseMap's grid branch (filters.py:412-429)."""
-    if noiseParams.get('noiseGridArcmin') == "smart":
-        raise Exception("noiseGridArcmin = 'smart' is not implemented in nemo_b200 (grid or None only)")
+    """(yChunks, xChunks, overlapPix, numBins) of MapFilter.makeNoiseMap's grid branch (filters.py:412-429), or
+    ('smart', numBins) for its 'smart' branch (:366-372)."""
     if 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] in ['biweight', 'percentile']:
         raise Exception("RMSEstimator '%s' is not implemented in nemo_b200 (default 3-sigma clipping only)" % noiseParams['RMSEstimator'])
+    if noiseParams.get('noiseGridArcmin') == "smart":
+        # whole-map weight bins instead of grid cells (filters.py:366-372): ('smart', numBins)
+        try:
+            numBins = noiseParams['numNoiseBins']
+        except Exception:
+            raise Exception("Need to give numNoiseBins in noiseParams when using noiseGridArcmin = 'smart'")
+        return ('smart', int(numBins))
     if 'noiseGridArcmin' not in noiseParams.keys() or noiseParams['noiseGridArcmin'] is None:
         overlapPix = 0
         numXChunks = 1
@@ -163,6 +169,10 @@ def applyFourierFilters(ops, fmaps, filtH, S, signalNorm, psMask, bckSubSigmas=N
 def noiseSNAndMasks(ops, filtered, wmed, psMask, surveyMask, S, grid, trimPix, apodPix, realSpace):
     """makeNoiseMap + S/N + edge trim + masks (filters.py:719-758).  `filtered` is overwritten with `data`.
     Returns (data, SNMap, surveyMaskOut u8, RMSMap, cellTable, cellEdges)."""
+    if grid[0] == 'smart':
+        rms, table, edges = ops.smart_rms(filtered, wmed, S, grid[1])
+        data, sn, maskOut, rms = ops.snr_mask(filtered, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace)
+        return data, sn, maskOut, rms, table, edges
     yChunks, xChunks, overlapPix, numBins = grid
     _, table, edges = ops.cell_rms(filtered, wmed, S, yChunks, xChunks, overlapPix, numBins, paint=False)
     data, sn, maskOut, rms = ops.snr_mask_cells(filtered, wmed, table, edges, yChunks, xChunks, overlapPix, numBins, psMask, surveyMask,

@@ -14,7 +14,7 @@ Differences a caller can see:
     preprocessed exactly as the reference does;
   * filter caches are FITS when astropy is importable, ``.npz`` with the same content otherwise;
   * options whose dependencies are absent raise instead of silently differing: noise methods ``model`` and
-    ``max(dataMap,CMB)``, ``noiseModelCatalog``, ``noiseGridArcmin: smart``, ``RMSEstimator`` biweight/percentile,
+    ``max(dataMap,CMB)``, ``noiseModelCatalog``, ``RMSEstimator`` biweight/percentile,
     ``reshapeFilter``; tile sides must lie in 64..4096 with an even width (sides that are not powers of two take the
     slower Bluestein FFT passes).
 """
@@ -209,7 +209,10 @@ class MapFilter(object):
         if t.dim() == 2:
             t = t.unsqueeze(0)
         grid = engine.noiseGrid(self.shape, self.params['noiseParams'], self.wcs.getPixelSizeDeg())
-        rms, table, edges = ops.cell_rms(t.contiguous(), dev['wmed'], 1, *grid)
+        if grid[0] == 'smart':
+            rms, table, edges = ops.smart_rms(t.contiguous(), dev['wmed'], 1, grid[1])
+        else:
+            rms, table, edges = ops.cell_rms(t.contiguous(), dev['wmed'], 1, *grid)
         self.noiseTable = (table, edges)
         return rms[0].cpu().numpy()
 

@@ -253,6 +253,24 @@ class Ops(object):
         self.launches += 2
         return rms, table, edges
 
+    def smart_rms(self, maps, wmed, S, numBins):
+        """RMS map of the 'smart' noise option: whole-map weight bins.  Returns (rms [nImg, H, W], table [nImg, numBins - 1],
+        edges [nImg / S, numBins])."""
+        self._check(maps, self.dtype, 'maps')
+        self._check(wmed, self.dtype, 'wmed')
+        torch = self.torch
+        nImg, H, W = maps.shape
+        numBins = int(numBins)
+        nb = max(numBins - 1, 1)
+        rms = self.empty((nImg, H, W))
+        table = self.zeros((nImg, nb), torch.float64)
+        edges = self.empty((nImg // int(S), numBins), torch.float64)
+        scratch = self.empty((16 * (nImg // int(S)) + 80 * nImg * nb + 4 * nImg + 64,), torch.uint8)
+        _lib.call('nb_smart_rms', self.prec, _ptr(maps), _ptr(wmed), nImg, int(S), H, W, numBins, _ptr(rms), _ptr(table), _ptr(edges),
+                  _ptr(scratch), self._stream())
+        self.launches += 28 if numBins > 1 else 4
+        return rms, table[:, :numBins - 1], edges
+
     def snr_mask(self, maps, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace):
         """In place on maps / rms; returns (data, SNMap, surveyMaskOut u8, rms)."""
         self._check(maps, self.dtype, 'maps')

@@ -88,10 +88,39 @@ class MapFilter(object):
     def makeNoiseMap(self, mapData):
         medWeights = np.median(np.array([m['weights'] for m in self.unfilteredMapsDictList]), axis=0)
         noiseParams = self.params['noiseParams']
-        if noiseParams.get('noiseGridArcmin') == "smart":
-            raise Exception("oracle: noiseGridArcmin 'smart' not restated")
         if 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] in ['biweight', 'percentile']:
             raise Exception("oracle: only the default 3-sigma clipped RMS estimator is restated")
+        if noiseParams.get('noiseGridArcmin') == "smart":
+            # 'smart' branch (filters.py:366-407): numBins - 1 whole-map bins between the smallest and the largest median weight,
+            # strict inequalities on both sides (a pixel whose weight equals an edge is in no bin)
+            try:
+                numBins = noiseParams['numNoiseBins']
+            except Exception:
+                raise Exception("Need to give numNoiseBins in noiseParams when using noiseGridArcmin = 'smart'")
+            binEdges = np.linspace(medWeights.min(), medWeights.max(), numBins)
+            RMSMap = np.zeros(medWeights.shape)
+            apodMask = np.not_equal(mapData, 0)
+            for i in range(len(binEdges) - 1):
+                binMin = binEdges[i]
+                binMax = binEdges[i + 1]
+                weightMask = np.logical_and(medWeights > binMin, medWeights < binMax)
+                chunkValues = mapData[weightMask]
+                goodAreaMask = np.greater_equal(apodMask[weightMask], 1.0)
+                if np.not_equal(chunkValues, 0).sum() != 0:
+                    chunkMean = np.mean(chunkValues[goodAreaMask])
+                    chunkRMS = np.std(chunkValues[goodAreaMask])
+                    sigmaClip = 3.0
+                    for c in range(10):
+                        mask = np.less(abs(chunkValues), abs(chunkMean + sigmaClip * chunkRMS))
+                        mask = np.logical_and(goodAreaMask, mask)
+                        if mask.sum() > 0:
+                            chunkMean = np.mean(chunkValues[mask])
+                            chunkRMS = np.std(chunkValues[mask])
+                else:
+                    chunkRMS = 0.
+                if chunkRMS > 0:
+                    RMSMap[weightMask] = chunkRMS
+            return RMSMap
         if 'noiseGridArcmin' not in noiseParams.keys() or noiseParams['noiseGridArcmin'] is None:
             overlapPix = 0
             numXChunks = 1

@@ -329,6 +329,38 @@ def test_cell_rms_clustered_weights(ops64, report, gridArcmin):
     assert err < 1e-12
 
 
+@pytest.mark.parametrize("numBins", [2, 6, 100])
+@pytest.mark.parametrize("shape", [(256, 256), (300, 420)])
+def test_smart_noise_bins_f64(ops64, report, numBins, shape):
+    """noiseGridArcmin = 'smart' (filters.py:366-407): whole-map weight bins with np.linspace edges and strict inequalities,
+    3-sigma clipped, against the oracle.  The case has zeroed regions, outliers and pixels whose weight sits exactly on the
+    first and last edge (the extremes), which belong to no bin."""
+    m, weights = _noise_case(shape, 40 + numBins)
+    ref = _oracle_noise(m, weights, 0.5 / 60, "smart", numBins)
+    wm = ops64.median_weights(ops64.to_device(np.array(weights)[None]))
+    rms, table, edges = ops64.smart_rms(ops64.to_device(m[None]), wm, 1, numBins)
+    got = _np(rms)[0]
+    medW = np.median(np.array(weights), axis=0)
+    assert np.array_equal(_np(edges)[0], np.linspace(medW.min(), medW.max(), numBins))
+    err = _relerr(got, ref)
+    report("smart_rms_f64", numBins=numBins, shape=shape, relerr=err, painted=float((ref > 0).mean()))
+    assert np.array_equal(got == 0, ref == 0)
+    assert (ref > 0).mean() > 0.5
+    assert err < 1e-11
+    # the table holds the values painted
+    assert set(np.unique(got[got > 0])) <= set(_np(table)[0].tolist())
+
+
+def test_smart_noise_constant_weights(ops64):
+    """All weights equal: every edge coincides, no pixel lies strictly between two edges, the noise map is zero."""
+    m, weights = _noise_case((256, 320), 3, constantWeights=True)
+    weights = [np.full(m.shape, 0.25)]
+    ref = _oracle_noise(m, weights, 0.5 / 60, "smart", 8)
+    wm = ops64.median_weights(ops64.to_device(np.array(weights)[None]))
+    rms, _, _ = ops64.smart_rms(ops64.to_device(m[None]), wm, 1, 8)
+    assert not ref.any() and not _np(rms).any()
+
+
 @pytest.mark.parametrize("numBins,gridArcmin", [(1, 20.0), (8, 40.0)])
 def test_cell_rms_f32(ops32, report, numBins, gridArcmin):
     """fp32 storage: the oracle is fed the same fp32-rounded maps, so only the final rounding of the RMS map differs."""

@@ -149,3 +149,36 @@ def test_synth_is_seeded():
     b, _ = synth.makeTile(shape=(64, 64), numObjects=2, seed=9, margin=20)
     c, _ = synth.makeTile(shape=(64, 64), numObjects=2, seed=10, margin=20)
     assert np.array_equal(a[0]['data'], b[0]['data']) and not np.array_equal(a[0]['data'], c[0]['data'])
+
+
+def test_smart_noise_branch_known_answers():
+    """noiseGridArcmin = 'smart' (filters.py:366-407): numBins - 1 bins between the extreme weights, strict inequalities (the
+    extreme-weight pixels and anything exactly on an edge stay unpainted), clipped standard deviation per bin."""
+    from oracle import filters_ref
+    from oracle.wcs_stub import SimpleCARWCS
+    rng = np.random.default_rng(3)
+    H, W = 64, 96
+    w = np.empty((H, W))
+    w[:, :32], w[:, 32:64], w[:, 64:] = 1.0, 2.0, 3.0
+    w[0, 0], w[0, 95] = 0.5, 4.0                       # extremes: edges = linspace(0.5, 4, 3) = [0.5, 2.25, 4]
+    m = rng.standard_normal((H, W)) * np.where(w <= 2.0, 1.0, 5.0)
+    m[5, 5] = 0.0                                      # a zero pixel is not a sample but is painted
+    md = [{'data': m, 'weights': w, 'wcs': SimpleCARWCS(m.shape, 0.5 / 60), 'flagMask': np.zeros(m.shape, np.uint8), 'obsFreqGHz': 150.0,
+           'label': 'x', 'surveyMask': None, 'pointSourceMask': None}]
+    f = filters_ref.MapFilter('t', md, {'noiseParams': {'noiseGridArcmin': 'smart', 'numNoiseBins': 3}})
+    rms = f.makeNoiseMap(m)
+    assert rms[0, 0] == 0 and rms[0, 95] == 0          # on the first / last edge: in no bin
+    lowBin, highBin = (w > 0.5) & (w < 2.25), (w > 2.25) & (w < 4.0)
+    assert len(np.unique(rms[lowBin])) == 1 and len(np.unique(rms[highBin])) == 1
+    assert rms[5, 5] == rms[6, 6] > 0
+    assert abs(rms[6, 6] - 1.0) < 0.1 and abs(rms[6, 80] - 5.0) < 0.5
+
+    def clipped(v):
+        mean, std = v.mean(), v.std()
+        for _ in range(10):
+            k = np.abs(v) < abs(mean + 3 * std)
+            mean, std = v[k].mean(), v[k].std()
+        return std
+    assert np.isclose(rms[6, 6], clipped(m[lowBin & (m != 0)]), rtol=1e-14)
+    with pytest.raises(Exception):
+        filters_ref.MapFilter('t', md, {'noiseParams': {'noiseGridArcmin': 'smart'}}).makeNoiseMap(m)

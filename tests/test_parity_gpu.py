@@ -471,3 +471,34 @@ def test_float32_host_tiles_are_widened_exactly(report):
         assert np.allclose(np.asarray(opt32[k], dtype=float), np.asarray(opt64[k], dtype=float), rtol=1e-12, atol=1e-12), k
     assert np.array_equal(np.asarray(opt32['numSigPix'], dtype=float), np.asarray(opt64['numSigPix'], dtype=float))
     report("float32-staged tiles: %d objects equal (1e-12) to the float64-staged run" % len(opt64))
+
+
+def test_smart_noise_option_end_to_end(report):
+    """noiseGridArcmin: 'smart' with numNoiseBins (the reference's examples/sources/PS_S18d_f220_202006.yml set-up, 'dataMap'
+    noise): whole-map weight bins instead of grid cells, through filterMaps and through the batched driver."""
+    from nemo_b200 import filters, photometry, pipelines
+    tileMaps = {}
+    for t in range(2):
+        md, _ = synth.makeTile(shape=(256, 256), freqsGHz=(148.0,), noiseUK=(100.0,), numObjects=12, kind='sources', seed=700 + t,
+                               borderPix=20)
+        yy, xx = np.mgrid[0:256, 0:256]
+        md[0]['weights'] = md[0]['weights'] * (0.7 + 0.3 * np.sin(yy / 40.0) * np.cos(xx / 55.0))
+        tileMaps['t%d' % t] = md
+    f = _beam(grid='smart', numBins=12, edgeTrimArcmin=0.0)
+    for name, md in tileMaps.items():
+        ref = filters_ref.filterMaps(md, _copyFilter(f), name)
+        got = filters.filterMaps(md, _copyFilter(f), name, verbose=False)
+        _compareMaps(got, ref, report, "beam_smart_" + name)
+        assert (ref['SNMap'] != 0).mean() > 0.5
+    parDict = {'mapFilters': [f], 'photFilter': None, 'thresholdSigma': 4.0, 'minObjPix': 1, 'findCenterOfMass': True,
+               'useInterpolator': True, 'rejectBorder': 0}
+    config = pipelines.SimpleConfig(parDict, tileMaps)
+    pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=2)
+    nObj = 0
+    for name, md in tileMaps.items():
+        ref = filters_ref.filterMaps(md, _copyFilter(f), name)
+        refCat = photometry_ref.findObjects(ref, **DETECT)
+        photometry_ref.measureFluxes(refCat, ref, None)
+        _compareCatalogs(config.catalogDict[f['label'] + "#" + name]['catalog'], refCat, ['SNR', 'deltaT_c'])
+        nObj += len(refCat)
+    assert nObj >= 6
