@@ -169,7 +169,7 @@ def applyFourierFilters(ops, fmaps, filtH, S, signalNorm, psMask, bckSubSigmas=N
 def noiseSNAndMasks(ops, filtered, wmed, psMask, surveyMask, S, grid, trimPix, apodPix, realSpace):
     """makeNoiseMap + S/N + edge trim + masks (filters.py:719-758).  `filtered` is overwritten with `data`.
     Returns (data, SNMap, surveyMaskOut u8, RMSMap, cellTable, cellEdges)."""
-    if grid[0] == 'smart':
+    if isinstance(grid[0], str) and grid[0] == 'smart':
         rms, table, edges = ops.smart_rms(filtered, wmed, S, grid[1])
         data, sn, maskOut, rms = ops.snr_mask(filtered, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace)
         return data, sn, maskOut, rms, table, edges

@@ -209,7 +209,7 @@ class MapFilter(object):
         if t.dim() == 2:
             t = t.unsqueeze(0)
         grid = engine.noiseGrid(self.shape, self.params['noiseParams'], self.wcs.getPixelSizeDeg())
-        if grid[0] == 'smart':
+        if isinstance(grid[0], str) and grid[0] == 'smart':
             rms, table, edges = ops.smart_rms(t.contiguous(), dev['wmed'], 1, grid[1])
         else:
             rms, table, edges = ops.cell_rms(t.contiguous(), dev['wmed'], 1, *grid)
