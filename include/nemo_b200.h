@@ -125,6 +125,14 @@ int nb_median_weights(int prec, const void* weights, void* out, int B, int F, in
 int nb_smart_rms(int prec, const void* map, const void* wmed, int nImg, int S, int H, int W, int numBins, void* rms, double* table,
                  double* edges, void* scratch, cudaStream_t stream);
 
+/* completeness.getRMSTab (nemo/completeness.py:981-999): map area per distinct noise level of an RMS map.
+ * rms [nImg, H, W] T (the masked RMS maps of nb_snr_mask*); mask [nImg, H, W] u8 (the area mask = surveyMaskOut); rowArea
+ * [nImg / S, H] fp64 pixel area of every row (maps.getPixelAreaArcmin2Map / 3600); cand [nImg, K] fp64 the levels to look for,
+ * ascending, padded with +inf (the values of the noise tables).  Outputs: area [nImg, K] fp64 = sum of rowArea * mask over the
+ * pixels at each level; total [nImg] fp64 = masked area; miss [nImg] i32 = non-zero RMS pixels whose value is not in cand. */
+int nb_rms_area_table(int prec, const void* rms, const unsigned char* mask, const double* rowArea, int nImg, int S, int H, int W,
+                      const double* cand, int K, double* area, double* total, int* miss, cudaStream_t stream);
+
 /* K6: MapFilter.makeNoiseMap, grid branch, default 3-sigma-clipped estimator (nemo/filters.py:409-481).
  * map [nImg, H, W] (already multiplied by psMask); wmed [nImg / S, H, W] median weights;
  * yChunks host [ny + 1], xChunks host [nx + 1] (np.linspace(..., dtype=int)); overlapPix; numBins.

@@ -282,6 +282,61 @@ static int smart_rms_t(const void* map, const void* wmed, int nImg, int S, int H
     return NB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// completeness.getRMSTab (nemo/completeness.py:981-999): map area per distinct noise level.  The levels of an RMS map are the
+// values its cells / bins painted, so the caller passes them sorted (cand [nImg, K], padded with +inf) and every pixel finds
+// its own by bisection; a warp's 32 neighbouring pixels share one or two levels, so they combine before the atomics.
+// area[img, k] += rowArea[img / S, y] * mask[p]; total[img] = masked area of the image; miss[img] counts non-zero RMS values
+// that are not in the list (none, when the list came from the noise tables).
+template <typename T>
+__global__ void __launch_bounds__(256) rms_area_kernel(const T* __restrict__ rms, const unsigned char* __restrict__ mask,
+                                                       const double* __restrict__ rowArea, int S, int H, int W,
+                                                       const double* __restrict__ cand, int K, double* __restrict__ area,
+                                                       double* __restrict__ total, int* __restrict__ miss) {
+    extern __shared__ double s_cand[];
+    const int img = blockIdx.y, y = blockIdx.x;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) s_cand[i] = cand[(size_t)img * K + i];
+    __syncthreads();
+    const double ra = rowArea[(size_t)(img / S) * H + y];
+    const T* r = rms + ((size_t)img * H + y) * W;
+    const unsigned char* mk = mask + ((size_t)img * H + y) * W;
+    const int lane = threadIdx.x & 31;
+    double tot = 0;
+    for (int x0 = 0; x0 < W; x0 += blockDim.x) {       // uniform trip count: the shuffles need every lane
+        const int x = x0 + threadIdx.x;
+        int idx = -1;
+        double a = 0;
+        if (x < W) {
+            const double v = (double)r[x];
+            a = ra * (double)mk[x];
+            tot += a;
+            if (v != 0.0) {
+                int lo = 0, hi = K;                    // first candidate >= v
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_cand[mid] < v) lo = mid + 1; else hi = mid;
+                }
+                if (lo < K && s_cand[lo] == v) idx = lo;
+                else atomicAdd(&miss[img], 1);
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, idx >= 0);
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const int k = __shfl_sync(0xffffffffu, idx, leader);
+            const bool mine = idx == k;
+            const unsigned grp = __ballot_sync(0xffffffffu, mine);
+            double aa = mine ? a : 0.0;
+            for (int o = 16; o > 0; o >>= 1) aa += __shfl_xor_sync(0xffffffffu, aa, o);
+            if (lane == leader) atomicAdd(&area[(size_t)img * K + k], aa);
+            todo &= ~grp;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) atomicAdd(&total[img], tot);
+}
+
 extern "C" {
 
 int nb_smart_rms(int prec, const void* map, const void* wmed, int nImg, int S, int H, int W, int numBins, void* rms, double* table,
@@ -292,6 +347,28 @@ int nb_smart_rms(int prec, const void* map, const void* wmed, int nImg, int S, i
     if (prec == NB_PREC_F32) return smart_rms_t<float>(map, wmed, nImg, S, H, W, numBins, rms, table, edges, scratch, st);
     nb_set_error("nb_smart_rms: bad precision %d", prec);
     return NB_ERR_ARG;
+}
+
+int nb_rms_area_table(int prec, const void* rms, const unsigned char* mask, const double* rowArea, int nImg, int S, int H, int W,
+                      const double* cand, int K, double* area, double* total, int* miss, cudaStream_t st) {
+    NB_REQUIRE(rms && mask && rowArea && cand && area && total && miss && nImg > 0 && S > 0 && K > 0, NB_ERR_ARG, "nb_rms_area_table: bad arguments");
+    NB_REQUIRE(K <= 16384, NB_ERR_UNSUPPORTED, "nb_rms_area_table: more than 16384 noise levels per image");
+    NB_CHECK_CUDA(cudaMemsetAsync(area, 0, sizeof(double) * (size_t)nImg * K, st));
+    NB_CHECK_CUDA(cudaMemsetAsync(total, 0, sizeof(double) * nImg, st));
+    NB_CHECK_CUDA(cudaMemsetAsync(miss, 0, sizeof(int) * nImg, st));
+    const size_t smem = sizeof(double) * (size_t)K;
+    if (prec == NB_PREC_F64) {
+        if (smem > 48 * 1024) NB_CHECK_CUDA(cudaFuncSetAttribute(rms_area_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { NB_PROF_BEGIN(st); rms_area_kernel<double><<<dim3(H, nImg), 256, smem, st>>>((const double*)rms, mask, rowArea, S, H, W, cand, K, area, total, miss); NB_PROF_END("rms_area_kernel", st); }
+    } else if (prec == NB_PREC_F32) {
+        if (smem > 48 * 1024) NB_CHECK_CUDA(cudaFuncSetAttribute(rms_area_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { NB_PROF_BEGIN(st); rms_area_kernel<float><<<dim3(H, nImg), 256, smem, st>>>((const float*)rms, mask, rowArea, S, H, W, cand, K, area, total, miss); NB_PROF_END("rms_area_kernel", st); }
+    } else {
+        nb_set_error("nb_rms_area_table: bad precision %d", prec);
+        return NB_ERR_ARG;
+    }
+    NB_CHECK_LAUNCH();
+    return NB_OK;
 }
 
 }  // extern "C"

@@ -200,3 +200,25 @@ def gatherNoiseTables(comm, noiseTables, labels=None, tileNames=None):
             key = bytes(nm[i]).rstrip(b'\x00').decode()
             out[key] = fl[i].reshape(shape) if int(np.prod(shape)) == fl.shape[1] else fl[i]
     return out
+
+
+def gatherRMSTabs(comm, RMSTabs, labels, tileNames):
+    """{label#tile: (y0RMS, areaDeg2)} from every rank -> the union on every rank (the reference gathers its per-tile RMSTab
+    objects to rank 0, pipelines.py:395-405).  Rows travel as (label index, tile index, y0RMS, areaDeg2): one collective."""
+    lutL = {v: i for i, v in enumerate(labels)}
+    lutT = {v: i for i, v in enumerate(tileNames)}
+    rows = [np.zeros((0, 4))]
+    for key in sorted(RMSTabs.keys()):
+        lab, tile = key.split('#', 1)
+        values, areas = RMSTabs[key]
+        rows.append(np.stack([np.full(len(values), lutL[lab], dtype=np.float64), np.full(len(values), lutT[tile], dtype=np.float64),
+                              np.asarray(values, dtype=np.float64), np.asarray(areas, dtype=np.float64)], axis=1))
+    out = {}
+    for part in comm.allGatherArrays(np.concatenate(rows, axis=0)):
+        if part.shape[0] == 0:
+            continue
+        code = part[:, 0].astype(np.int64) * len(tileNames) + part[:, 1].astype(np.int64)
+        for c in np.unique(code):
+            sel = code == c
+            out[labels[int(c) // len(tileNames)] + "#" + tileNames[int(c) % len(tileNames)]] = (part[sel, 2].copy(), part[sel, 3].copy())
+    return out

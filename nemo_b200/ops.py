@@ -271,6 +271,23 @@ class Ops(object):
         self.launches += 28 if numBins > 1 else 4
         return rms, table[:, :numBins - 1], edges
 
+    def rms_area_table(self, rms, mask, rowArea, S, cand):
+        """Area per noise level: rms [nImg, H, W], mask u8 [nImg, H, W], rowArea [nImg / S, H] f64, cand [nImg, K] f64 ascending,
+        +inf padded.  Returns (area [nImg, K], total [nImg], miss [nImg] i32)."""
+        self._check(rms, self.dtype, 'rms')
+        self._check(mask, self.torch.uint8, 'mask')
+        self._check(rowArea, self.torch.float64, 'rowArea')
+        self._check(cand, self.torch.float64, 'cand')
+        nImg, H, W = rms.shape
+        K = cand.shape[1]
+        area = self.empty((nImg, K), self.torch.float64)
+        total = self.empty((nImg,), self.torch.float64)
+        miss = self.empty((nImg,), self.torch.int32)
+        _lib.call('nb_rms_area_table', self.prec, _ptr(rms), _ptr(mask), _ptr(rowArea), nImg, int(S), H, W, _ptr(cand), K, _ptr(area),
+                  _ptr(total), _ptr(miss), self._stream())
+        self.launches += 1
+        return area, total, miss
+
     def snr_mask(self, maps, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace):
         """In place on maps / rms; returns (data, SNMap, surveyMaskOut u8, rms)."""
         self._check(maps, self.dtype, 'maps')

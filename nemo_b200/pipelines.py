@@ -75,7 +75,12 @@ class TileBatch(object):
                 weights[t, f] = torch.from_numpy(np.ascontiguousarray(m['weights']))
             survey[t] = torch.from_numpy(_filters._maskToU8(md[0].get('surveyMask'), (H, W)))
             ps[t] = torch.from_numpy(_filters._maskToU8(md[0].get('pointSourceMask'), (H, W)))
-        self.host = {'data': data, 'weights': weights, 'surveyMask': survey, 'psMask': ps}
+        # pixel area (deg^2) of every row of every tile: input of the noise level / area tables (completeness.getRMSTab)
+        from . import completeness
+        rowArea = torch.empty((nT, H), dtype=torch.float64, pin_memory=pinned)
+        for t, md in enumerate(self.mapDicts):
+            rowArea[t] = torch.from_numpy(completeness.rowAreasDeg2((H, W), md[0]['wcs']))
+        self.host = {'data': data, 'weights': weights, 'surveyMask': survey, 'psMask': ps, 'rowArea': rowArea}
         self.h2dBytes = sum(int(v.numel()) * v.element_size() for v in self.host.values())
         self.dev = None
         self.wcsList = [md[0]['wcs'] for md in self.mapDicts]
@@ -159,7 +164,7 @@ def _sameNoiseSetup(filtersList):
 
 
 def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=True, invertMap=False, cache=None,
-                   useCachedRMSMap=False):
+                   useCachedRMSMap=False, rmsTables=False):
     """Launches, without waiting for any of it, the device work of one batch: filtering of every tile at every scale of
     `filtersList` (Fourier matched filters with a common noise set-up), noise / S-N maps, and the thresholding,
     labelling and moments of the detection step.  Returns the job to pass to finishTileBatch.
@@ -212,6 +217,11 @@ def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=
         grid = engine.noiseGrid((H, W), params0['noiseParams'], pixDeg)
         data, sn, maskOut, rms, table, edges = engine.noiseSNAndMasks(ops, filtered, dev['wmed'], dev['psMask'], dev['surveyMask'],
                                                                       S, grid, trimPix, 20, False)
+    # noise level versus area (completeness.getRMSTab) of every image, while its RMS map is on the device
+    rmsTabJob = None
+    if rmsTables and table is not None:
+        from . import completeness
+        rmsTabJob = completeness.startRMSTables(ops, rms, maskOut, dev['rowArea'], S, table)
     # K8
     if undoPixelWindow:
         engine.undoPixelWindow(ops, data)
@@ -222,7 +232,8 @@ def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=
                                                  measureShapes=parDict['measureShapes'])
     return {'ops': ops, 'batch': batch, 'filtersList': filtersList, 'parDict': parDict, 'mapUnits': templates.outputUnits,
             'invertMap': invertMap, 'detectJob': detectJob, 'data': data, 'SNMap': sn, 'surveyMask': maskOut, 'RMSMap': rms,
-            'noiseTable': table, 'noiseEdges': edges, 'signalNorm': res['signalNorm'], 'fRel': res['fRel'], 'filtH': res['filtH']}
+            'noiseTable': table, 'noiseEdges': edges, 'signalNorm': res['signalNorm'], 'fRel': res['fRel'], 'filtH': res['filtH'],
+            'rmsTabJob': rmsTabJob}
 
 
 def finishTileBatch(job, measureFluxes=True, keepMaps=False):
@@ -232,6 +243,9 @@ def finishTileBatch(job, measureFluxes=True, keepMaps=False):
     catalogDict = detectAndMeasure(job['ops'], job['batch'], job['filtersList'], job['data'], job['SNMap'], job['mapUnits'],
                                    job['parDict'], measureFluxes=measureFluxes, invertMap=job['invertMap'], detectJob=job['detectJob'])
     extras = {'noiseTable': job['noiseTable'], 'noiseEdges': job['noiseEdges'], 'signalNorm': job['signalNorm'], 'fRel': job['fRel']}
+    if job.get('rmsTabJob') is not None:
+        from . import completeness
+        extras['RMSTabs'] = completeness.finishRMSTables(job['rmsTabJob'])      # [(y0RMS, areaDeg2)] per image
     if keepMaps:
         extras.update({k: job[k] for k in ('data', 'SNMap', 'surveyMask', 'RMSMap', 'filtH')})
     return catalogDict, extras
@@ -261,7 +275,8 @@ class BatchPipeline(object):
     nothing is shared between batches except the read-only templates."""
 
     def __init__(self, ops, filtersList, templates, parDict, undoPixelWindow=True, measureFluxes=True, invertMap=False,
-                 keepMaps=False, useCachedRMSMap=False, useGraphs=True, depth=2):
+                 keepMaps=False, useCachedRMSMap=False, useGraphs=True, depth=2, rmsTables=False):
+        self.rmsTables = rmsTables
         self.ops, self.filtersList, self.templates, self.parDict = ops, filtersList, templates, parDict
         # the ~40 launches of a batch are captured once per (slot, shape, input buffers) into a CUDA graph and replayed:
         # the host then spends microseconds, not a millisecond, queueing a batch.  Graphs live on the Ops object.
@@ -303,7 +318,7 @@ class BatchPipeline(object):
             ident = ('staged', str(batch.host['data'].dtype), str(batch.host['weights'].dtype))
         else:
             ident = tuple(int(batch.dev[k].data_ptr()) for k in ('data', 'weights', 'psMask', 'surveyMask', 'wmed'))
-        key = (slot, ident, batch.nT, batch.F, batch.H, batch.W, ops.precision, id(self.templates), self.undoPixelWindow, self.invertMap,
+        key = (slot, ident, batch.nT, batch.F, batch.H, batch.W, ops.precision, id(self.templates), self.undoPixelWindow, self.invertMap, self.rmsTables,
                repr(sorted((k, repr(v)) for k, v in self.parDict.items() if k != 'mapFilters')),
                repr([(f['label'], repr(sorted(f['params'].items(), key=lambda kv: kv[0]))) for f in self.filtersList]))
         entry = self.graphs.get(key)
@@ -322,7 +337,7 @@ class BatchPipeline(object):
                 view.dev['wmed'] = ops.median_weights(view.dev['weights'])
             # one eager run first: twiddle tables, kernel attributes and other lazy set-up must not happen under capture
             startTileBatch(ops, view, self.filtersList, self.templates, self.parDict, undoPixelWindow=self.undoPixelWindow,
-                           invertMap=self.invertMap)
+                           invertMap=self.invertMap, rmsTables=self.rmsTables)
             st.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launchCount()
@@ -332,7 +347,7 @@ class BatchPipeline(object):
                     widenStaged(ops, view.dev)
                     view.dev['wmed'] = ops.median_weights(view.dev['weights'])
                 job = startTileBatch(ops, view, self.filtersList, self.templates, self.parDict,
-                                     undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap)
+                                     undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap, rmsTables=self.rmsTables)
             nLaunch = _lib.launchCount() - n0
         entry = (graph, job, static, nLaunch)
         self.graphs[key] = entry
@@ -364,7 +379,7 @@ class BatchPipeline(object):
                     batch.upload()
                 job = startTileBatch(self.ops, batch, self.filtersList, self.templates, self.parDict,
                                      undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap, cache=cache,
-                                     useCachedRMSMap=self.useCachedRMSMap)
+                                     useCachedRMSMap=self.useCachedRMSMap, rmsTables=self.rmsTables)
         self.pending.append((job, st, upload))
         # a slot's buffers (graph outputs, static inputs) are reused by the batch submitted len(streams) calls later, so at
         # most `depth` jobs may stay unread
@@ -381,12 +396,12 @@ class BatchPipeline(object):
 
 
 def processBatches(ops, batches, filtersList, templates, parDict, upload=True, undoPixelWindow=True, measureFluxes=True,
-                   invertMap=False, keepMaps=False, caches=None, useCachedRMSMap=False, useGraphs=True, depth=2):
+                   invertMap=False, keepMaps=False, caches=None, useCachedRMSMap=False, useGraphs=True, depth=2, rmsTables=False):
     """Runs several tile batches through a BatchPipeline; returns the list of (catalogDict, extras), one per batch, in order.
     caches: per-batch filter / RMS caches (see startTileBatch), or None."""
     pipe = BatchPipeline(ops, filtersList, templates, parDict, undoPixelWindow=undoPixelWindow, measureFluxes=measureFluxes,
                          invertMap=invertMap, keepMaps=keepMaps, useCachedRMSMap=useCachedRMSMap,
-                         useGraphs=useGraphs and not keepMaps, depth=depth)
+                         useGraphs=useGraphs and not keepMaps, depth=depth, rmsTables=rmsTables)
     results = []
     for i, batch in enumerate(batches):
         out = pipe.submit(batch, upload=upload and batch.dev is None, cache=caches[i] if caches is not None else None)
@@ -594,7 +609,8 @@ def _batchBounds(numTiles, tilesPerBatch):
 
 
 def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=False, measureFluxes=True, invertMap=False,
-                              verbose=True, tilesPerBatch=8, precision=None, comm=None, cacheFilters=False, restage=False):
+                              verbose=True, tilesPerBatch=8, precision=None, comm=None, cacheFilters=False, restage=False,
+                              makeRMSTables=False):
     """Runs the map filtering and catalog construction steps for this rank's tiles and returns the optimal catalog
     (highest S/N detection across filter scales), gathered over ranks when `comm` (a
     ``nemo_b200.distributed.Comm``) is given -- pipelines.py:33-109, 112-354.
@@ -627,6 +643,7 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
                                                           objIdent=parDict['objIdent'], longNames=parDict['longNames'])
         config.catalogDict = catalogDict
         config.noiseTables = {}
+        config.RMSTabs = {}
         return optimalCatalog
     catalogDict = {}
     noiseTables = {}
@@ -654,13 +671,16 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     # batched path always makes the S/N map before undoing the window, so the same flag serves both cases
     results = processBatches(ops, batches, filtersList, templates, parDict, upload=True,
                              undoPixelWindow=parDict.get('undoPixelWindow', True), measureFluxes=measureFluxes, invertMap=invertMap,
-                             keepMaps=cacheFilters, caches=caches, useCachedRMSMap=useCachedRMSMap)
+                             keepMaps=cacheFilters, caches=caches, useCachedRMSMap=useCachedRMSMap, rmsTables=makeRMSTables)
     if cacheFilters:
         config._cache = [{'filtH': ex['filtH'], 'signalNorm': ex['signalNorm'], 'RMSMap': ex['RMSMap'], 'fRel': ex['fRel']}
                          for _, ex in results]
+    RMSTabs = {}
     for batch, (cd, extras) in zip(batches, results):
         names = batch.tileNames
         catalogDict.update(cd)
+        for o, tab in enumerate(extras.get('RMSTabs') or []):
+            RMSTabs[filtersList[o % len(filtersList)]['label'] + "#" + names[o // len(filtersList)]] = tab
         if extras['noiseTable'] is None:
             continue
         tab = device.toHost(extras['noiseTable'])
@@ -675,6 +695,10 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
         optimalCatalog = distributed.allGatherCatalog(comm, optimalCatalog, keys, labels, config.allTileNames,
                                                       objIdent=parDict['objIdent'], longNames=parDict['longNames'])
         noiseTables = distributed.gatherNoiseTables(comm, noiseTables, labels, config.allTileNames)
+    if makeRMSTables and comm is not None and comm.size > 1:
+        from . import distributed
+        RMSTabs = distributed.gatherRMSTabs(comm, RMSTabs, [f['label'] for f in filtersList], config.allTileNames)
     config.catalogDict = catalogDict
     config.noiseTables = noiseTables
+    config.RMSTabs = RMSTabs      # {'<label>#<tileName>': (y0RMS ascending, areaDeg2)} -- completeness.getRMSTab per tile and filter
     return optimalCatalog

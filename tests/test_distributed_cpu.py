@@ -64,6 +64,10 @@ def _worker(rank, world, port, q):
         empty = distributed.allGatherCatalog(comm, [] if rank == 1 else tab, keys)
         noise2 = distributed.gatherNoiseTables(comm, {'F#tile%d' % rank: np.full((4, 2), float(rank + 1))})
         assert sorted(noise2.keys()) == sorted(noise.keys()) and np.array_equal(noise2['F#tile1'], noise['F#tile1'])
+        tabs = distributed.gatherRMSTabs(comm, {'Arnaud_M2e14_z0p4#tile%d' % rank: (np.arange(3 + rank) + 1.0, np.full(3 + rank, 0.5 + rank))},
+                                         labels, tileNames)
+        assert sorted(tabs.keys()) == ['Arnaud_M2e14_z0p4#tile0', 'Arnaud_M2e14_z0p4#tile1']
+        assert np.array_equal(tabs['Arnaud_M2e14_z0p4#tile1'][0], [1.0, 2.0, 3.0, 4.0]) and np.array_equal(tabs['Arnaud_M2e14_z0p4#tile1'][1], [1.5] * 4)
         result = {'n': len(merged), 'ra': list(merged['RADeg']), 'snr': list(merged['SNR']), 'names': list(merged['name']),
                   'tiles': list(merged['tileName']), 'noiseKeys': sorted(noise.keys()), 'noise1': noise['F#tile1'].tolist(),
                   'nEmpty': len(empty), 'max': comm.maxOverRanks(rank + 1.5), 'sum': comm.sumOverRanks(rank + 1.0)}

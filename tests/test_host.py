@@ -277,3 +277,31 @@ def test_cross_match_equals_the_quadratic_rule():
         want = brute(ra, dec, snr, catalogs.XMATCH_RADIUS_DEG)
         assert want.sum() > 20
         assert np.array_equal(got, want)
+
+
+def test_row_areas_match_the_reference_pixel_area_map():
+    """completeness.rowAreasDeg2 (vectorised) against the oracle's restatement of maps.getPixelAreaArcmin2Map, and the
+    oracle's getRMSTab on a hand-made map."""
+    from nemo_b200 import completeness
+    from nemo_b200.wcs import CARWCS
+    from oracle import completeness_ref
+    from oracle.wcs_stub import SimpleCARWCS
+    shape = (48, 80)
+    for crval in [(10.0, 0.0), (200.0, -52.0)]:
+        ref = completeness_ref.getPixelAreaArcmin2Map(shape, SimpleCARWCS(shape, 0.5 / 60, crval=crval))
+        got = completeness.rowAreasDeg2(shape, CARWCS(shape, 0.5 / 60, crval=crval))
+        assert ref.shape == shape and np.array_equal(ref[:, 0], ref[:, -1])
+        assert np.allclose(got * 3600.0, ref[:, 0], rtol=1e-13, atol=0)
+        assert np.allclose(completeness.getPixelAreaArcmin2Map(shape, CARWCS(shape, 0.5 / 60, crval=crval)), ref, rtol=1e-13, atol=0)
+    rms = np.zeros(shape)
+    rms[:, :40], rms[:, 40:] = 2.0, 1.0
+    rms[:4] = 0.0
+    area = (rms > 0).astype(np.uint8)
+    values, areas = completeness_ref.getRMSTab(rms, area, SimpleCARWCS(shape, 0.5 / 60))
+    assert list(values) == [1.0, 2.0] and abs(areas[0] - areas[1]) < 1e-15
+    assert np.isclose(areas.sum(), 44 * 80 * (0.5 / 60) ** 2, rtol=1e-4)
+    area[:4] = 1                                         # masked-in area without a noise level: the reference refuses (tol 0.003 deg^2)
+    rmsBig, areaBig = np.zeros((600, 600)), np.ones((600, 600), np.uint8)
+    rmsBig[:300] = 1.0
+    with pytest.raises(Exception):
+        completeness_ref.getRMSTab(rmsBig, areaBig, SimpleCARWCS((600, 600), 0.5 / 60))

@@ -502,3 +502,41 @@ def test_smart_noise_option_end_to_end(report):
         _compareCatalogs(config.catalogDict[f['label'] + "#" + name]['catalog'], refCat, ['SNR', 'deltaT_c'])
         nObj += len(refCat)
     assert nObj >= 6
+
+
+def test_rms_area_tables_match_reference_getRMSTab(report):
+    """completeness.getRMSTab (nemo/completeness.py:981-999): noise level versus area of a filtered tile, from the class API
+    (grid and 'smart' noise) and from the batched driver (makeRMSTables), against the oracle's np.unique / boolean-sum version
+    on the oracle's own RMS map and area mask."""
+    from nemo_b200 import filters, pipelines, completeness
+    from oracle import completeness_ref
+    tileMaps = {}
+    for t in range(3):
+        md, _ = synth.makeTile(shape=(256, 256), freqsGHz=(148.0,), noiseUK=(100.0,), numObjects=8, kind='sources', seed=900 + t,
+                               borderPix=24)
+        yy, xx = np.mgrid[0:256, 0:256]
+        md[0]['weights'] = md[0]['weights'] * (0.7 + 0.3 * np.sin(yy / 33.0 + t) * np.cos(xx / 47.0))
+        tileMaps['t%d' % t] = md
+    for f in [_beam(grid=20., numBins=4), _beam(grid='smart', numBins=9)]:
+        for name, md in tileMaps.items():
+            ref, refObj = filters_ref.filterMaps(md, _copyFilter(f), name, returnFilter=True)
+            got, gotObj = filters.filterMaps(md, _copyFilter(f), name, verbose=False, returnFilter=True)
+            # the reference makes its table from the masked RMS map and the area mask the filter step wrote
+            values, areas = completeness_ref.getRMSTab(refObj.RMSMap, ref['surveyMask'], md[0]['wcs'])
+            tab = completeness.getRMSTab(gotObj.RMSMap, got['surveyMask'], md[0]['wcs'], gotObj.noiseTable[0])
+            assert len(tab) == len(values)
+            assert np.allclose(np.asarray(tab['y0RMS']), values, rtol=1e-11, atol=0)
+            assert np.allclose(np.asarray(tab['areaDeg2']), areas, rtol=1e-11, atol=0)
+            assert len(values) >= 3
+        parDict = {'mapFilters': [f], 'photFilter': None, 'thresholdSigma': 4.0, 'minObjPix': 1, 'findCenterOfMass': True,
+                   'useInterpolator': True, 'rejectBorder': 0}
+        config = pipelines.SimpleConfig(parDict, tileMaps)
+        pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=2, makeRMSTables=True)
+        assert sorted(config.RMSTabs.keys()) == sorted(f['label'] + "#" + n for n in tileMaps)
+        for name, md in tileMaps.items():
+            ref, refObj = filters_ref.filterMaps(md, _copyFilter(f), name, returnFilter=True)
+            values, areas = completeness_ref.getRMSTab(refObj.RMSMap, ref['surveyMask'], md[0]['wcs'])
+            bv, ba = config.RMSTabs[f['label'] + "#" + name]
+            assert len(bv) == len(values)
+            assert np.allclose(bv, values, rtol=1e-11, atol=0) and np.allclose(ba, areas, rtol=1e-11, atol=0)
+        report("rms_area_tables %s: %d levels in the last tile, %.3f deg2" % (f['params']['noiseParams']['noiseGridArcmin'], len(values), areas.sum()))
