@@ -12,6 +12,7 @@
 #include "nemo_b200_internal.h"
 #include <math.h>
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -91,6 +92,49 @@ static int get_bs_tables(int prec, int N, BsTables* out) {
     }
     const int M = nb_bs_length(N);
     const long double pi = 3.141592653589793238462643383279502884L;
+    // 2-3-5-7-smooth lengths: mixed-radix plan and pass tables instead of the chirp tables (bhat stays null, see bluestein_run)
+    {
+        std::vector<int> radices;
+        int rest = N;
+        for (int f : {7, 5, 3}) while (rest % f == 0) { radices.push_back(f); rest /= f; }
+        while (rest % 4 == 0) { radices.push_back(4); rest /= 4; }
+        if (rest % 2 == 0) { radices.push_back(2); rest /= 2; }
+        if (rest == 1 && !getenv("NEMO_B200_FORCE_BLUESTEIN")) {
+            std::vector<int> plan(1 + 2 * radices.size());
+            std::vector<long double> tr, ti;
+            plan[0] = (int)radices.size();
+            int Ns = 1;
+            for (size_t p = 0; p < radices.size(); ++p) {
+                const int R = radices[p];
+                plan[1 + 2 * p] = R;
+                plan[2 + 2 * p] = (int)tr.size();
+                if (Ns > 1) {
+                    for (int r = 1; r < R; ++r)
+                        for (int k = 0; k < Ns; ++k) {
+                            const long double a = 2.0L * pi * (long double)((long long)r * k) / (long double)((long long)Ns * R);
+                            tr.push_back(cosl(a));
+                            ti.push_back(-sinl(a));
+                        }
+                }
+                Ns *= R;
+            }
+            if (tr.empty()) { tr.push_back(1.0L); ti.push_back(0.0L); }
+            BsTables t;
+            t.M = M;
+            t.bhat = nullptr;
+            int rc;
+            if (prec == NB_PREC_F64) rc = upload_c2<double>(tr, ti, &t.tw);
+            else rc = upload_c2<float>(tr, ti, &t.tw);
+            if (rc != NB_OK) return rc;
+            void* d = nullptr;
+            NB_CHECK_CUDA(cudaMalloc(&d, sizeof(int) * plan.size()));
+            NB_CHECK_CUDA(cudaMemcpy(d, plan.data(), sizeof(int) * plan.size(), cudaMemcpyHostToDevice));
+            t.chirp = d;
+            g_bs_tables[key] = t;
+            *out = t;
+            return NB_OK;
+        }
+    }
     std::vector<long double> cr(N), ci(N), br(M, 0.0L), bi(M, 0.0L), tr(M), ti(M);
     for (int n = 0; n < N; ++n) {
         const long long r = ((long long)n * n) % (2LL * N);   // n^2 mod 2N keeps the phase exact
@@ -128,6 +172,160 @@ static int get_bs_tables(int prec, int N, BsTables* out) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Lengths whose only prime factors are 2, 3, 5 and 7 (1440 x 840 survey tiles: 2^5 3^2 5 and 2^3 3 5 7) do not need the chirp
+// detour: a mixed-radix Stockham transform of length N itself, passes of radix 7 / 5 / 3 / 4 / 2 through the group's shared
+// memory (two regions of N values inside the buffer Bluestein's M >= 2 N - 1 points need, so the kernels and their launch
+// geometry are shared), about a sixth of the arithmetic.  Pass with sub-transform length Ns and radix R, butterfly j < N / R,
+// k = j mod Ns: inputs x[j + r N / R] times exp(-2 pi i r k / (Ns R)), a natural-order DFT of size R, outputs to
+// (j - k) R + k + r Ns.  Twiddles per pass as a block [R - 1][Ns]; the plan (number of passes, then radix and table offset
+// of each) sits in device memory.
+template <int R> __device__ __forceinline__ constexpr double mix_cos(int m) {
+    return R == 3 ? (m == 0 ? 1.0 : -0.5)
+         : R == 5 ? (m == 0 ? 1.0 : (m == 1 || m == 4) ? 0.30901699437494745 : -0.8090169943749475)
+                  : (m == 0 ? 1.0 : (m == 1 || m == 6) ? 0.6234898018587335 : (m == 2 || m == 5) ? -0.2225209339563144 : -0.9009688679024191);
+}
+template <int R> __device__ __forceinline__ constexpr double mix_sin(int m) {
+    return R == 3 ? (m == 0 ? 0.0 : m == 1 ? 0.8660254037844386 : -0.8660254037844386)
+         : R == 5 ? (m == 0 ? 0.0 : m == 1 ? 0.9510565162951535 : m == 2 ? 0.5877852522924731 : m == 3 ? -0.5877852522924731 : -0.9510565162951535)
+                  : (m == 0 ? 0.0 : m == 1 ? 0.7818314824680298 : m == 2 ? 0.9749279121818236 : m == 3 ? 0.4338837391175581
+                     : m == 4 ? -0.4338837391175581 : m == 5 ? -0.9749279121818236 : -0.7818314824680298);
+}
+
+// natural-order DFT of R values in registers, DIR = -1 forward, +1 inverse (no scaling)
+template <typename T, int R, int DIR>
+__device__ __forceinline__ void dft_small(T (&xr)[R], T (&xi)[R]) {
+    if constexpr (R == 2) {
+        const T ar = xr[0], ai = xi[0];
+        xr[0] = ar + xr[1]; xi[0] = ai + xi[1];
+        xr[1] = ar - xr[1]; xi[1] = ai - xi[1];
+    } else if constexpr (R == 4) {
+        const T s02r = xr[0] + xr[2], s02i = xi[0] + xi[2], d02r = xr[0] - xr[2], d02i = xi[0] - xi[2];
+        const T s13r = xr[1] + xr[3], s13i = xi[1] + xi[3], d13r = xr[1] - xr[3], d13i = xi[1] - xi[3];
+        xr[0] = s02r + s13r; xi[0] = s02i + s13i;
+        xr[2] = s02r - s13r; xi[2] = s02i - s13i;
+        // forward: X1 = d02 - i d13, X3 = d02 + i d13; inverse the other way round
+        if (DIR < 0) {
+            xr[1] = d02r + d13i; xi[1] = d02i - d13r;
+            xr[3] = d02r - d13i; xi[3] = d02i + d13r;
+        } else {
+            xr[1] = d02r - d13i; xi[1] = d02i + d13r;
+            xr[3] = d02r + d13i; xi[3] = d02i - d13r;
+        }
+    } else {
+        constexpr int Hh = (R - 1) / 2;
+        T spr[Hh], spi[Hh], smr[Hh], smi[Hh];
+#pragma unroll
+        for (int r = 1; r <= Hh; ++r) {
+            spr[r - 1] = xr[r] + xr[R - r]; spi[r - 1] = xi[r] + xi[R - r];
+            smr[r - 1] = xr[r] - xr[R - r]; smi[r - 1] = xi[r] - xi[R - r];
+        }
+        const T x0r = xr[0], x0i = xi[0];
+        T t0r = x0r, t0i = x0i;
+#pragma unroll
+        for (int r = 0; r < Hh; ++r) {
+            t0r += spr[r];
+            t0i += spi[r];
+        }
+        xr[0] = t0r; xi[0] = t0i;
+#pragma unroll
+        for (int k = 1; k <= Hh; ++k) {
+            T ar = x0r, ai = x0i, br = 0, bi = 0;
+#pragma unroll
+            for (int r = 1; r <= Hh; ++r) {
+                const T c = (T)mix_cos<R>((r * k) % R), sn = (T)mix_sin<R>((r * k) % R);
+                ar += c * spr[r - 1]; ai += c * spi[r - 1];
+                br += sn * smr[r - 1]; bi += sn * smi[r - 1];
+            }
+            // forward: X[k] = A - i B, X[R - k] = A + i B; inverse the other way round
+            if (DIR < 0) {
+                xr[k] = ar + bi; xi[k] = ai - br;
+                xr[R - k] = ar - bi; xi[R - k] = ai + br;
+            } else {
+                xr[k] = ar - bi; xi[k] = ai + br;
+                xr[R - k] = ar + bi; xi[R - k] = ai - br;
+            }
+        }
+    }
+}
+
+template <typename T, int R, int DIR>
+__device__ __forceinline__ void mix_pass(const T* __restrict__ aR, const T* __restrict__ aI, T* __restrict__ bR, T* __restrict__ bI,
+                                         const typename V2<T>::type* __restrict__ tw, const int N, const int Ns, const int t, const int NT) {
+    typedef typename V2<T>::type C2;
+    const int nb = N / R;
+    for (int j = t; j < nb; j += NT) {
+        const int k = j % Ns;
+        T xr[R], xi[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            xr[r] = aR[j + r * nb];
+            xi[r] = aI[j + r * nb];
+        }
+        if (Ns > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                const C2 w = __ldg(tw + (r - 1) * Ns + k);
+                const T wr = w.x, wi = (DIR < 0) ? w.y : -w.y;
+                const T ur = xr[r], ui = xi[r];
+                xr[r] = ur * wr - ui * wi;
+                xi[r] = ur * wi + ui * wr;
+            }
+        }
+        dft_small<T, R, DIR>(xr, xi);
+        const int j0 = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            bR[j0 + r * Ns] = xr[r];
+            bI[j0 + r * Ns] = xi[r];
+        }
+    }
+}
+
+// same contract as bluestein_run below
+template <typename T, int M, int DIR, class Sync>
+__device__ __forceinline__ void mixed_run(T (&re)[16], T (&im)[16], const int t, T* s_re, T* s_im,
+                                          const typename V2<T>::type* __restrict__ mtw, const int* __restrict__ plan, const int N,
+                                          Sync sync) {
+    constexpr int NT = M / 16;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int n = t + q * NT;
+        if (n < N) {
+            s_re[n] = re[q];
+            s_im[n] = im[q];
+        }
+    }
+    sync();
+    T *aR = s_re, *aI = s_im, *bR = s_re + N, *bI = s_im + N;
+    const int nPass = plan[0];
+    int Ns = 1;
+    for (int p = 0; p < nPass; ++p) {
+        const int R = plan[1 + 2 * p];
+        const typename V2<T>::type* tw = mtw + plan[2 + 2 * p];
+        switch (R) {
+            case 2: mix_pass<T, 2, DIR>(aR, aI, bR, bI, tw, N, Ns, t, NT); break;
+            case 3: mix_pass<T, 3, DIR>(aR, aI, bR, bI, tw, N, Ns, t, NT); break;
+            case 4: mix_pass<T, 4, DIR>(aR, aI, bR, bI, tw, N, Ns, t, NT); break;
+            case 5: mix_pass<T, 5, DIR>(aR, aI, bR, bI, tw, N, Ns, t, NT); break;
+            default: mix_pass<T, 7, DIR>(aR, aI, bR, bI, tw, N, Ns, t, NT); break;
+        }
+        sync();
+        T* x = aR; aR = bR; bR = x;
+        x = aI; aI = bI; bI = x;
+        Ns *= R;
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int n = t + q * NT;
+        if (n < N) {
+            re[q] = aR[n];
+            im[q] = aI[n];
+        }
+    }
+    sync();    // the caller may reuse the buffer straight away
+}
+
+// ------------------------------------------------------------------------------------------------------
 // The transform of one line held by a thread group: on entry re/im[q] = x[t + q * NT] for indices < N, 0 beyond; on exit
 // re/im[q] = X[t + q * NT] for indices < N (undefined beyond).  DIR = -1: X[k] = sum x[n] exp(-2 pi i n k / N);
 // DIR = +1: the un-normalised inverse sum.  s_re / s_im: npad(M) words each, private to the group.
@@ -138,6 +336,10 @@ __device__ __forceinline__ void bluestein_run(T (&re)[16], T (&im)[16], const in
                                               const typename V2<T>::type* __restrict__ bhat, const int N, Sync sync) {
     typedef typename V2<T>::type C2;
     constexpr int NT = M / 16;
+    if (bhat == nullptr) {   // a 2-3-5-7-smooth length: tw holds the mixed-radix pass tables, chirp points to the plan
+        mixed_run<T, M, DIR>(re, im, t, s_re, s_im, tw, reinterpret_cast<const int*>(chirp), N, sync);
+        return;
+    }
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
         const int n = t + q * NT;
