@@ -15,8 +15,8 @@ Differences a caller can see:
   * filter caches are FITS when astropy is importable, ``.npz`` with the same content otherwise;
   * options whose dependencies are absent raise instead of silently differing: noise methods ``model`` and
     ``max(dataMap,CMB)``, ``noiseModelCatalog``, ``RMSEstimator`` biweight/percentile,
-    ``reshapeFilter``; tile sides must lie in 64..4096 with an even width (sides that are not powers of two take the
-    slower Bluestein FFT passes).
+    ``reshapeFilter``; tile sides must lie in 64..4096 with an even width (sides that are not powers of two take
+    mixed-radix passes when their prime factors are 2, 3, 5, 7, the slower Bluestein passes otherwise).
 """
 
 import os
