@@ -142,6 +142,13 @@ int nb_cell_rms(int prec, const void* map, const void* wmed, int nImg, int S, in
                 int ny, const int* xChunks, int nx, int overlapPix, int numBins, void* rms, double* table,
                 double* edges, cudaStream_t stream);
 
+/* nb_cell_rms with the RMS estimator of noiseParams['RMSEstimator'] (nemo/filters.py:460-479): 0 = 3-sigma clipped standard
+ * deviation (the default, what nb_cell_rms does), 1 = 'percentile' = np.percentile(abs(binValues), 68.3).  Estimators other
+ * than 0 run on the streaming kernel (exact order statistics by radix select over the cell). */
+int nb_cell_rms_est(int prec, const void* map, const void* wmed, int nImg, int S, int H, int W, const int* yChunks, int ny,
+                    const int* xChunks, int nx, int overlapPix, int numBins, int estimator, void* rms, double* table, double* edges,
+                    cudaStream_t stream);
+
 /* K7: S/N map, edge trim and final masks (nemo/filters.py:716-758 Fourier class, :1112-1161 real-space class).
  * In: map [nImg, H, W] (filtered * psMask), rms [nImg, H, W], psMask / surveyMask u8 [nImg / S, H, W].
  * edgeCheck = rank_filter(|map + (1 - psMask)|, 0, size = (trimPix, trimPix)) > 0 (all ones when trimPix = 0);

@@ -45,6 +45,8 @@ _PROTOTYPES = {
     "nb_median_weights": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
     "nb_cell_rms": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int), c_int,
                     c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
+    "nb_cell_rms_est": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int), c_int,
+                        c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "nb_snr_mask": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "nb_snr_mask_cells": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int), c_int, c_int, c_int, c_ptr, c_ptr,
                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],

@@ -148,11 +148,52 @@ __device__ double select_kth(const T* __restrict__ m, const T* __restrict__ wm, 
     return dec_w(prefix);
 }
 
+// k-th smallest (0-based) |value| among the good pixels of the cell whose weight lies in [wlo, whi): the same radix select on
+// the bit pattern of |v| (non-negative doubles order like their bits) -- the 'percentile' RMS estimator (filters.py:464-465)
+template <typename T>
+__device__ double select_kth_abs(const T* __restrict__ m, const T* __restrict__ wm, int W, CellGeom g, long long k, double wlo, double whi,
+                                 int* s_hist, unsigned long long* s_sel) {
+    unsigned long long prefix = 0, maskbits = 0;
+    const int cw = g.x1 - g.x0;
+    const int n = (g.y1 - g.y0) * cw;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            const int r = e / cw, c = e - r * cw;
+            const size_t off = (size_t)(g.y0 + r) * W + g.x0 + c;
+            const double v = (double)m[off], w = (double)wm[off];
+            if (v != 0.0 && w >= wlo && w < whi) {
+                const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(v));
+                if ((key & maskbits) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 255ULL)], 1);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long kk = (long long)s_sel[1];
+            if (pass == 0) kk = k;
+            int d = 0;
+            for (; d < 255; ++d) {
+                if (kk < s_hist[d]) break;
+                kk -= s_hist[d];
+            }
+            s_sel[0] = prefix | ((unsigned long long)d << shift);
+            s_sel[1] = (unsigned long long)kk;
+        }
+        __syncthreads();
+        prefix = s_sel[0];
+        maskbits |= 0xFFULL << shift;
+    }
+    __syncthreads();
+    return __longlong_as_double((long long)prefix);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(CR_THREADS) cell_rms_stream_kernel(const T* __restrict__ map, const T* __restrict__ wmed, int S, int H,
                                                               int W, const Chunks ch, int nx,
                                                               int ov, int numBins, double* __restrict__ table,
-                                                              double* __restrict__ edges) {
+                                                              double* __restrict__ edges, int estimator) {
     __shared__ double s_red[2 * CR_MAXWARPS];
     __shared__ int s_hist[256];
     __shared__ unsigned long long s_sel[2];
@@ -235,7 +276,25 @@ __global__ void __launch_bounds__(CR_THREADS) cell_rms_stream_kernel(const T* __
         }
         block_sum2(c0, s0, s_red);
         double rms = 0.0;
-        if (c0 > 0) {
+        if (estimator == 1) {
+            // np.percentile(abs(binValues), 68.3) (filters.py:464-465); an empty bin gives nan there, which paints nothing
+            if (c0 > 0) {
+                const double q = 68.3 / 100.0;
+                const double vi = c0 * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0;   // numpy's virtual index, method 'linear'
+                const double fl = floor(vi);
+                long long klo = (long long)fl, khi = klo + 1;
+                const long long nn = (long long)c0;
+                klo = klo < 0 ? 0 : (klo > nn - 1 ? nn - 1 : klo);
+                khi = khi < 0 ? 0 : (khi > nn - 1 ? nn - 1 : khi);
+                const double gmm = vi - fl;
+                const double a = select_kth_abs<T>(m, wm, W, g, klo, lo, hi, s_hist, s_sel);
+                const double bb = (khi == klo) ? a : select_kth_abs<T>(m, wm, W, g, khi, lo, hi, s_hist, s_sel);
+                const double diff = bb - a;
+                rms = a + diff * gmm;           // numpy _lerp
+                if (gmm >= 0.5) rms = bb - diff * (1.0 - gmm);
+                if (gmm == 0.0) rms = a;
+            }
+        } else if (c0 > 0) {
             double mean = s0 / c0;
             double q0 = 0, d0 = 0;
             for (int e = threadIdx.x; e < n; e += blockDim.x) {
@@ -1146,15 +1205,11 @@ __global__ void __launch_bounds__(256) edge_rows_kernel(const T* __restrict__ ma
     const unsigned char* p = ps + ((size_t)(img / S) * H + y) * W;
     const int per = (W + blockDim.x - 1) / blockDim.x;
     const int b0 = threadIdx.x * per, b1 = min(b0 + per, W);
-    // zero flags with coalesced loads first, then every thread scans its own run of them in shared memory
-    for (int x = threadIdx.x; x < W; x += blockDim.x) {
-        const T a = m[x] + (T)(1 - (int)p[x]);
-        s_pre[x + 1] = (a == (T)0) ? 1 : 0;
-    }
-    __syncthreads();
     int local = 0;
     for (int x = b0; x < b1; ++x) {
-        local += s_pre[x + 1];
+        const T a = m[x] + (T)(1 - (int)p[x]);
+        const int z = (a == (T)0) ? 1 : 0;
+        local += z;
         s_pre[x + 1] = local;  // local inclusive, offset added below
     }
     s_part[threadIdx.x] = local;
@@ -1323,7 +1378,8 @@ __global__ void __launch_bounds__(256) snr_from_rms_kernel(const T* __restrict__
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
 static int cell_rms_t(const void* map, const void* wmed, int nImg, int S, int H, int W, const int* yChunks, int ny,
-                      const int* xChunks, int nx, int ov, int numBins, void* rms, double* table, double* edges, cudaStream_t st) {
+                      const int* xChunks, int nx, int ov, int numBins, void* rms, double* table, double* edges, cudaStream_t st,
+                      int estimator = 0) {
     NB_REQUIRE(ny <= NB_MAX_CHUNKS && nx <= NB_MAX_CHUNKS, NB_ERR_UNSUPPORTED, "nb_cell_rms: more than %d noise cells per axis", NB_MAX_CHUNKS);
     Chunks ch;
     memset(&ch, 0, sizeof(ch));
@@ -1339,7 +1395,7 @@ static int cell_rms_t(const void* map, const void* wmed, int nImg, int S, int H,
     const long long CH = ((tilePix + 31) / 32) * 32;
     const long long perWarp = CH > (long long)OC_PPT * 32 ? CH - (long long)OC_PPT * 32 : 0;
     const long long smemSlots = perWarp * OC_WARPS;
-    const bool fits = maxCell < (1LL << 22) && numBins <= OC_MAXBINS;
+    const bool fits = maxCell < (1LL << 22) && numBins <= OC_MAXBINS && estimator == 0;    // other estimators: streaming kernel
     typedef typename KeyOf<T>::type KT;
     // preferred: every value in shared memory, sorted by (warp, bin); else registers + shared memory; else streaming
     const long long valueSlots = CH * OC_WARPS;
@@ -1356,7 +1412,7 @@ static int cell_rms_t(const void* map, const void* wmed, int nImg, int S, int H,
             (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges, (int)smemSlots, 0); NB_PROF_END("cell_rms_hybrid_kernel", st); }
     } else {
         { NB_PROF_BEGIN(st); cell_rms_stream_kernel<T><<<dim3(ny * nx, nImg), CR_THREADS, sizeof(double) * (numBins + 1), st>>>(
-            (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges); NB_PROF_END("cell_rms_stream_kernel", st); }
+            (const T*)map, (const T*)wmed, S, H, W, ch, nx, ov, numBins, table, edges, estimator); NB_PROF_END("cell_rms_stream_kernel", st); }
     }
     NB_CHECK_LAUNCH();
     if (rms) {
@@ -1442,6 +1498,21 @@ int nb_cell_rms(int prec, const void* map, const void* wmed, int nImg, int S, in
     if (prec == NB_PREC_F32)
         return cell_rms_t<float>(map, wmed, nImg, S, H, W, yChunks, ny, xChunks, nx, overlapPix, numBins, rms, table, edges, st);
     nb_set_error("nb_cell_rms: bad precision %d", prec);
+    return NB_ERR_ARG;
+}
+
+int nb_cell_rms_est(int prec, const void* map, const void* wmed, int nImg, int S, int H, int W, const int* yChunks, int ny,
+                    const int* xChunks, int nx, int overlapPix, int numBins, int estimator, void* rms, double* table, double* edges,
+                    cudaStream_t st) {
+    NB_REQUIRE(map && wmed && yChunks && xChunks && table && edges && nImg > 0 && S > 0 && ny > 0 && nx > 0, NB_ERR_ARG,
+               "nb_cell_rms_est: bad arguments");
+    NB_REQUIRE(numBins >= 1 && numBins <= 64, NB_ERR_ARG, "nb_cell_rms_est: numBins %d out of range (1..64)", numBins);
+    NB_REQUIRE(estimator == 0 || estimator == 1, NB_ERR_UNSUPPORTED, "nb_cell_rms_est: estimator %d not implemented (0 clip, 1 percentile)", estimator);
+    if (prec == NB_PREC_F64)
+        return cell_rms_t<double>(map, wmed, nImg, S, H, W, yChunks, ny, xChunks, nx, overlapPix, numBins, rms, table, edges, st, estimator);
+    if (prec == NB_PREC_F32)
+        return cell_rms_t<float>(map, wmed, nImg, S, H, W, yChunks, ny, xChunks, nx, overlapPix, numBins, rms, table, edges, st, estimator);
+    nb_set_error("nb_cell_rms_est: bad precision %d", prec);
     return NB_ERR_ARG;
 }
 

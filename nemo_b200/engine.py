@@ -22,11 +22,16 @@ FUSED_FILTER_BUILD = os.environ.get('NEMO_B200_FUSED_FILTER_BUILD', '0') == '1'
 # ------------------------------------------------------------------------------------------------------
 # host-side parameter logic
 def noiseGrid(shape, noiseParams, pixDeg):
-    """(yChunks, xChunks, overlapPix, numBins) of MapFilter.makeNoiseMap's grid branch (filters.py:412-429), or
+    """(yChunks, xChunks, overlapPix, numBins, estimator) of MapFilter.makeNoiseMap's grid branch (filters.py:412-429), or
     ('smart', numBins) for its 'smart' branch (:366-372)."""
-    if 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] in ['biweight', 'percentile']:
-        raise Exception("RMSEstimator '%s' is not implemented in nemo_b200 (default 3-sigma clipping only)" % noiseParams['RMSEstimator'])
+    estimator = 'clip'
+    if 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] == 'biweight':
+        raise Exception("RMSEstimator 'biweight' is not implemented in nemo_b200 (astropy's biweight_scale; 3-sigma clipping and 'percentile' are)")
+    if 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] == 'percentile':
+        estimator = 'percentile'
     if noiseParams.get('noiseGridArcmin') == "smart":
+        if estimator != 'clip':
+            raise Exception("RMSEstimator '%s' with noiseGridArcmin 'smart' is not implemented in nemo_b200" % estimator)
         # whole-map weight bins instead of grid cells (filters.py:366-372): ('smart', numBins)
         try:
             numBins = noiseParams['numNoiseBins']
@@ -45,7 +50,7 @@ def noiseGrid(shape, noiseParams, pixDeg):
     yChunks = np.linspace(0, shape[0], int(numYChunks + 1), dtype=int)
     xChunks = np.linspace(0, shape[1], int(numXChunks + 1), dtype=int)
     numBins = noiseParams['numNoiseBins'] if 'numNoiseBins' in noiseParams.keys() else 1
-    return yChunks, xChunks, overlapPix, int(numBins)
+    return yChunks, xChunks, overlapPix, int(numBins), estimator
 
 
 def trimSizePix(params, pixDeg, realSpace):
@@ -173,8 +178,8 @@ def noiseSNAndMasks(ops, filtered, wmed, psMask, surveyMask, S, grid, trimPix, a
         rms, table, edges = ops.smart_rms(filtered, wmed, S, grid[1])
         data, sn, maskOut, rms = ops.snr_mask(filtered, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace)
         return data, sn, maskOut, rms, table, edges
-    yChunks, xChunks, overlapPix, numBins = grid
-    _, table, edges = ops.cell_rms(filtered, wmed, S, yChunks, xChunks, overlapPix, numBins, paint=False)
+    yChunks, xChunks, overlapPix, numBins, estimator = grid
+    _, table, edges = ops.cell_rms(filtered, wmed, S, yChunks, xChunks, overlapPix, numBins, estimator=estimator, paint=False)
     data, sn, maskOut, rms = ops.snr_mask_cells(filtered, wmed, table, edges, yChunks, xChunks, overlapPix, numBins, psMask, surveyMask,
                                                 S, trimPix, apodPix, realSpace)
     return data, sn, maskOut, rms, table, edges

@@ -14,7 +14,7 @@ Differences a caller can see:
     preprocessed exactly as the reference does;
   * filter caches are FITS when astropy is importable, ``.npz`` with the same content otherwise;
   * options whose dependencies are absent raise instead of silently differing: noise methods ``model`` and
-    ``max(dataMap,CMB)``, ``noiseModelCatalog``, ``RMSEstimator`` biweight/percentile,
+    ``max(dataMap,CMB)``, ``noiseModelCatalog``, ``RMSEstimator`` biweight,
     ``reshapeFilter``; tile sides must lie in 64..4096 with an even width (sides that are not powers of two take
     mixed-radix passes when their prime factors are 2, 3, 5, 7, the slower Bluestein passes otherwise).
 """

@@ -237,8 +237,11 @@ class Ops(object):
         self.launches += 1
         return out
 
-    def cell_rms(self, maps, wmed, S, yChunks, xChunks, overlapPix, numBins, paint=True):
-        """Clipped-RMS cell tables and (paint=True) the painted RMS map; with paint=False returns (None, table, edges)."""
+    ESTIMATORS = {'clip': 0, 'percentile': 1}
+
+    def cell_rms(self, maps, wmed, S, yChunks, xChunks, overlapPix, numBins, estimator='clip', paint=True):
+        """Cell RMS tables (estimator 'clip': 3-sigma clipped standard deviation; 'percentile': 68.3th percentile of |v|) and
+        (paint=True) the painted RMS map; with paint=False returns (None, table, edges)."""
         self._check(maps, self.dtype, 'maps')
         self._check(wmed, self.dtype, 'wmed')
         nImg, H, W = maps.shape
@@ -248,9 +251,15 @@ class Ops(object):
         edges = self.empty((nImg, ny * nx, numBins + 1), self.torch.float64)
         yc = (ctypes.c_int * (ny + 1))(*[int(v) for v in yChunks])
         xc = (ctypes.c_int * (nx + 1))(*[int(v) for v in xChunks])
-        _lib.call('nb_cell_rms', self.prec, _ptr(maps), _ptr(wmed), nImg, int(S), H, W, yc, ny, xc, nx, int(overlapPix), int(numBins),
-                  _ptr(rms), _ptr(table), _ptr(edges), self._stream())
-        self.launches += 2
+        if estimator not in self.ESTIMATORS:
+            raise Exception("RMSEstimator '%s' is not implemented in nemo_b200 (clip, percentile)" % estimator)
+        if estimator == 'clip':
+            _lib.call('nb_cell_rms', self.prec, _ptr(maps), _ptr(wmed), nImg, int(S), H, W, yc, ny, xc, nx, int(overlapPix), int(numBins),
+                      _ptr(rms), _ptr(table), _ptr(edges), self._stream())
+        else:
+            _lib.call('nb_cell_rms_est', self.prec, _ptr(maps), _ptr(wmed), nImg, int(S), H, W, yc, ny, xc, nx, int(overlapPix),
+                      int(numBins), self.ESTIMATORS[estimator], _ptr(rms), _ptr(table), _ptr(edges), self._stream())
+        self.launches += 2 if paint else 1
         return rms, table, edges
 
     def smart_rms(self, maps, wmed, S, numBins):

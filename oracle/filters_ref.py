@@ -88,8 +88,11 @@ class MapFilter(object):
     def makeNoiseMap(self, mapData):
         medWeights = np.median(np.array([m['weights'] for m in self.unfilteredMapsDictList]), axis=0)
         noiseParams = self.params['noiseParams']
-        if 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] in ['biweight', 'percentile']:
-            raise Exception("oracle: only the default 3-sigma clipped RMS estimator is restated")
+        if 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] == 'biweight':
+            raise Exception("oracle: the biweight estimator needs astropy.stats.biweight_scale, absent here")
+        percentileEstimator = 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] == 'percentile'
+        if percentileEstimator and noiseParams.get('noiseGridArcmin') == "smart":
+            raise Exception("oracle: percentile estimator restated for the grid branch only")
         if noiseParams.get('noiseGridArcmin') == "smart":
             # 'smart' branch (filters.py:366-407): numBins - 1 whole-map bins between the smallest and the largest median weight,
             # strict inequalities on both sides (a pixel whose weight equals an edge is in no bin)
@@ -156,7 +159,10 @@ class MapFilter(object):
                     binMax = binEdges[b + 1]
                     binMask = np.logical_and(weightValues >= binMin, weightValues < binMax)
                     binValues = chunkValues[binMask * goodAreaMask]
-                    if np.not_equal(binValues, 0).sum() != 0:
+                    if percentileEstimator:
+                        # filters.py:464-465; an empty bin gives nan (with a numpy warning), which paints nothing
+                        chunkRMS = np.percentile(abs(binValues), 68.3) if len(binValues) > 0 else np.nan
+                    elif np.not_equal(binValues, 0).sum() != 0:
                         chunkMean = np.mean(binValues)
                         chunkRMS = np.std(binValues)
                         sigmaClip = 3.0

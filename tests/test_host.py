@@ -94,13 +94,16 @@ def test_product_never_imports_the_oracle():
 def test_noise_grid_and_trim_follow_the_reference():
     from nemo_b200 import engine
     pixDeg = 0.5 / 60
-    yc, xc, ov, nb = engine.noiseGrid((1024, 1024), {'method': 'dataMap', 'noiseGridArcmin': 40.0, 'numNoiseBins': 8}, pixDeg)
-    assert ov == 40 and nb == 8 and len(yc) == 13 and yc[0] == 0 and yc[-1] == 1024
+    yc, xc, ov, nb, est = engine.noiseGrid((1024, 1024), {'method': 'dataMap', 'noiseGridArcmin': 40.0, 'numNoiseBins': 8}, pixDeg)
+    assert ov == 40 and nb == 8 and len(yc) == 13 and yc[0] == 0 and yc[-1] == 1024 and est == 'clip'
     assert list(yc) == list(np.linspace(0, 1024, int(1024 / 80 + 1), dtype=int))
-    yc, xc, ov, nb = engine.noiseGrid((300, 420), {'method': 'dataMap'}, pixDeg)
-    assert list(yc) == [0, 300] and list(xc) == [0, 420] and ov == 0 and nb == 1
+    yc, xc, ov, nb, est = engine.noiseGrid((300, 420), {'method': 'dataMap', 'RMSEstimator': 'percentile'}, pixDeg)
+    assert list(yc) == [0, 300] and list(xc) == [0, 420] and ov == 0 and nb == 1 and est == 'percentile'
+    assert engine.noiseGrid((64, 64), {'noiseGridArcmin': 'smart', 'numNoiseBins': 12}, pixDeg) == ('smart', 12)
     with pytest.raises(Exception):
-        engine.noiseGrid((64, 64), {'noiseGridArcmin': 'smart'}, pixDeg)
+        engine.noiseGrid((64, 64), {'noiseGridArcmin': 'smart'}, pixDeg)                 # numNoiseBins is required (filters.py:367-370)
+    with pytest.raises(Exception):
+        engine.noiseGrid((64, 64), {'noiseGridArcmin': 'smart', 'numNoiseBins': 4, 'RMSEstimator': 'percentile'}, pixDeg)
     with pytest.raises(Exception):
         engine.noiseGrid((64, 64), {'noiseGridArcmin': 20., 'RMSEstimator': 'biweight'}, pixDeg)
     # filters.py:728-735: edgeTrimArcmin 0 means three noise cells

@@ -241,7 +241,7 @@ def test_plane_values_at_f64(ops64, report):
 
 
 # ----------------------------------------------------------------------------------------------------------
-def _oracle_noise(mapData, weightsList, pixDeg, gridArcmin, numBins):
+def _oracle_noise(mapData, weightsList, pixDeg, gridArcmin, numBins, estimator=None):
     from oracle import filters_ref
     from oracle.wcs_stub import SimpleCARWCS
     wcs = SimpleCARWCS(mapData.shape, pixDeg)
@@ -250,6 +250,8 @@ def _oracle_noise(mapData, weightsList, pixDeg, gridArcmin, numBins):
     params = {'noiseParams': {'noiseGridArcmin': gridArcmin}}
     if numBins is not None:
         params['noiseParams']['numNoiseBins'] = numBins
+    if estimator is not None:
+        params['noiseParams']['RMSEstimator'] = estimator
     f = filters_ref.MapFilter('t', md, params)
     return f.makeNoiseMap(mapData)
 
@@ -327,6 +329,24 @@ def test_cell_rms_clustered_weights(ops64, report, gridArcmin):
     report("cell_rms_clustered", grid=gridArcmin, relerr=err)
     assert np.array_equal(got == 0, ref == 0)
     assert err < 1e-12
+
+
+@pytest.mark.parametrize("numBins,shape,gridArcmin", [(1, (256, 256), 20.0), (4, (300, 420), 20.0), (8, (512, 640), 40.0)])
+def test_cell_rms_percentile_estimator(ops64, report, numBins, shape, gridArcmin):
+    """RMSEstimator: 'percentile' (filters.py:464-465): np.percentile(abs(binValues), 68.3) per cell and weight bin, exact
+    order statistics by radix select, against the oracle."""
+    m, weights = _noise_case(shape, 60 + numBins)
+    ref = _oracle_noise(m, weights, 0.5 / 60, gridArcmin, numBins if numBins > 1 else None, estimator='percentile')
+    H, W = m.shape
+    gridSize = int(round((gridArcmin / 60.) / (0.5 / 60)))
+    yc, xc, ov = _chunks(H, gridSize), _chunks(W, gridSize), gridSize // 2
+    wm = ops64.median_weights(ops64.to_device(np.array(weights)[None]))
+    rms, table, edges = ops64.cell_rms(ops64.to_device(m[None]), wm, 1, yc, xc, ov, numBins, estimator='percentile')
+    got = _np(rms)[0]
+    err = _relerr(got, ref)
+    report("cell_rms_percentile", numBins=numBins, shape=shape, relerr=err)
+    assert np.array_equal(got == 0, ref == 0)
+    assert err < 1e-14
 
 
 @pytest.mark.parametrize("numBins", [2, 6, 100])

@@ -540,3 +540,31 @@ def test_rms_area_tables_match_reference_getRMSTab(report):
             assert len(bv) == len(values)
             assert np.allclose(bv, values, rtol=1e-11, atol=0) and np.allclose(ba, areas, rtol=1e-11, atol=0)
         report("rms_area_tables %s: %d levels in the last tile, %.3f deg2" % (f['params']['noiseParams']['noiseGridArcmin'], len(values), areas.sum()))
+
+
+def test_percentile_rms_estimator_end_to_end(report):
+    """noiseParams RMSEstimator: 'percentile' through filterMaps and the batched driver."""
+    from nemo_b200 import filters, pipelines
+    tileMaps = {}
+    for t in range(2):
+        md, _ = synth.makeTile(shape=(256, 256), freqsGHz=(148.0,), noiseUK=(100.0,), numObjects=10, kind='sources', seed=800 + t,
+                               borderPix=20)
+        tileMaps['t%d' % t] = md
+    f = _beam(grid=20., numBins=2, edgeTrimArcmin=0.0)
+    f['params']['noiseParams']['RMSEstimator'] = 'percentile'
+    for name, md in tileMaps.items():
+        ref = filters_ref.filterMaps(md, _copyFilter(f), name)
+        got = filters.filterMaps(md, _copyFilter(f), name, verbose=False)
+        _compareMaps(got, ref, report, "beam_percentile_" + name)
+    parDict = {'mapFilters': [f], 'photFilter': None, 'thresholdSigma': 4.0, 'minObjPix': 1, 'findCenterOfMass': True,
+               'useInterpolator': True, 'rejectBorder': 0}
+    config = pipelines.SimpleConfig(parDict, tileMaps)
+    pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=2)
+    nObj = 0
+    for name, md in tileMaps.items():
+        ref = filters_ref.filterMaps(md, _copyFilter(f), name)
+        refCat = photometry_ref.findObjects(ref, **DETECT)
+        photometry_ref.measureFluxes(refCat, ref, None)
+        _compareCatalogs(config.catalogDict[f['label'] + "#" + name]['catalog'], refCat, ['SNR', 'deltaT_c'])
+        nObj += len(refCat)
+    assert nObj >= 4
