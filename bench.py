@@ -242,6 +242,7 @@ def main():
     torch.cuda.set_device(localRank)
     comm = None
     if world > 1:
+        distributed.bindProcessToDeviceCpus(localRank)     # pinned staging buffers next to this rank's GPU
         import torch.distributed as dist
         dist.init_process_group(backend='nccl', device_id=torch.device('cuda', localRank))
         comm = distributed.Comm()

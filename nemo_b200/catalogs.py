@@ -288,6 +288,53 @@ def _candidatePairs(ra, dec, radiusDeg):
     return np.stack([i, j], axis=1)
 
 
+def _candidatePairsGrid(ra, dec, radiusDeg):
+    """The same superset of close pairs as _candidatePairs, from a hash of the sky into cells one radius high and one radius
+    (at the largest |dec| present) wide: a pair within the radius lies in the same or in adjacent cells.  The number of
+    candidates then follows the local density, not the number of rows in a declination strip -- with thousands of rows from
+    many overlapping tiles the strip sweep generates hundreds of thousands of pairs.  Returns None when the cells would wrap
+    onto themselves in RA (near a pole); the caller falls back to the strip sweep."""
+    n = len(ra)
+    cosMin = np.cos(np.radians(min(np.abs(dec).max() + radiusDeg, 90.0)))
+    if cosMin <= 1e-6:
+        return None
+    cellRA = radiusDeg / cosMin * 1.0001
+    NX = int(np.floor(360.0 / cellRA))
+    if NX < 4:
+        return None
+    cellRA = 360.0 / NX                                  # cells tile the circle exactly; still >= the radius in RA
+    ix = np.minimum((np.mod(ra, 360.0) / cellRA).astype(np.int64), NX - 1)
+    iy = np.floor((dec + 90.0) / radiusDeg).astype(np.int64)
+    key = iy * NX + ix
+    order = np.argsort(key, kind='stable')
+    ks = key[order]
+    idx = np.arange(n)
+    out = []
+    # every unordered pair of cells once: the cell itself (rows after the current one), its east neighbour, and the three cells
+    # of the row above; RA neighbours wrap around
+    for dy, dx in ((0, 0), (0, 1), (1, -1), (1, 0), (1, 1)):
+        if dy == 0 and dx == 0:
+            lo = idx + 1
+            hi = np.searchsorted(ks, ks, side='right')
+        else:
+            nkey = (iy[order] + dy) * NX + np.mod(ix[order] + dx, NX)
+            if dx != 0 and NX < 3:
+                continue
+            lo = np.searchsorted(ks, nkey, side='left')
+            hi = np.searchsorted(ks, nkey, side='right')
+        cnt = np.maximum(hi - lo, 0)
+        total = int(cnt.sum())
+        if total == 0:
+            continue
+        first = np.repeat(idx, cnt)
+        start = np.cumsum(cnt) - cnt
+        second = np.repeat(lo, cnt) + (np.arange(total) - np.repeat(start, cnt))
+        out.append(np.stack([order[first], order[second]], axis=1))
+    if not out:
+        return np.zeros((0, 2), dtype=np.intp)
+    return np.concatenate(out, axis=0)
+
+
 def _crossMatchKeepBest(ra, dec, snr, radiusDeg):
     """Boolean mask of rows to remove: for every row, all rows within radiusDeg of it except the one with the highest
     S/N (first one on ties) are dropped.  Same outcome as the reference's O(n^2) loop (catalogs.py:171-183): candidate
@@ -297,7 +344,9 @@ def _crossMatchKeepBest(ra, dec, snr, radiusDeg):
     toRemove = np.zeros(n, dtype=bool)
     if n < 2:
         return toRemove
-    pairs = _candidatePairs(ra, dec, radiusDeg * 1.01)
+    pairs = _candidatePairsGrid(ra, dec, radiusDeg * 1.01)
+    if pairs is None:
+        pairs = _candidatePairs(ra, dec, radiusDeg * 1.01)
     if len(pairs) == 0:
         return toRemove
     # directed edges centre -> member, both directions; the separation is measured about the centre, as the reference does

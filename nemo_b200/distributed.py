@@ -82,6 +82,30 @@ class Comm(object):
         return float(t.item())
 
 
+def bindProcessToDeviceCpus(deviceIndex):
+    """Pins this process to the CPU cores NVML lists as local to GPU `deviceIndex` (same NUMA node / PCIe root), so that the pinned
+    staging buffers it allocates afterwards are first-touched next to the GPU that will read them.  With eight ranks uploading
+    at once, host memory placement decides the copy bandwidth each gets.  Returns the core list, or None when NVML or the
+    affinity call is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+        index = int(visible.split(',')[deviceIndex]) if visible and all(v.strip().isdigit() for v in visible.split(',')) else deviceIndex
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        nCpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (nCpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < nCpu]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def shardTiles(tileNames, rank, size):
     """Round-robin split of tiles over ranks; all scales of a tile stay on one rank."""
     return list(tileNames)[rank::size]

@@ -38,5 +38,22 @@ p = {'M500MSun': 2e14, 'z': 0.4, 'outputUnits': 'yc', 'bckSub': True, 'edgeTrimA
                      'symmetrize': True, 'noiseGridArcmin': 20.}}
 out = filters.filterMaps(md, {'label': 'RS', 'class': 'ArnaudModelRealSpaceMatchedFilter', 'params': p}, 'T', verbose=False)
 print("real-space ok")
+# this round's additions: 'smart' noise bins, percentile estimator, noise level / area tables, float32-staged tiles, a 2-3-5-7-smooth
+# side (mixed-radix passes) next to a side with a large prime factor (Bluestein passes)
+md, _ = synth.makeTile(shape=(120, 106), numObjects=2, kind='sources', seed=4, margin=30)      # 120 = 5 * 3 * 8, 106 = 2 * 53
+yy, xx = np.mgrid[0:120, 0:106]
+md[0]['weights'] = md[0]['weights'] * (0.7 + 0.3 * np.sin(yy / 20.0) * np.cos(xx / 25.0))
+for noise in [{'method': 'dataMap', 'noiseGridArcmin': 'smart', 'numNoiseBins': 7},
+              {'method': 'dataMap', 'noiseGridArcmin': 10., 'numNoiseBins': 2, 'RMSEstimator': 'percentile'}]:
+    f = {'label': 'B', 'class': 'BeamMatchedFilter', 'params': {'outputUnits': 'uK', 'edgeTrimArcmin': 0., 'noiseParams': noise}}
+    out, obj = filters.filterMaps(md, copy.deepcopy(f), 'T', verbose=False, returnFilter=True)
+    from nemo_b200 import completeness
+    tab = completeness.getRMSTab(obj.RMSMap, out['surveyMask'], md[0]['wcs'], obj.noiseTable[0])
+    print("noise option ok:", noise['noiseGridArcmin'], len(tab), "levels")
+tiles32 = {k: [dict(m, data=np.asarray(m['data'], dtype=np.float32), weights=np.asarray(m['weights'], dtype=np.float32)) for m in v]
+           for k, v in tileMaps.items()}
+cfg32 = pipelines.SimpleConfig(par, tiles32)
+opt = pipelines.filterMapsAndMakeCatalogs(cfg32, verbose=False, tilesPerBatch=[1, 2], makeRMSTables=True)
+print("float32-staged batches + RMS tables ok", len(opt), len(cfg32.RMSTabs))
 torch.cuda.synchronize()
 print("ALL OK")

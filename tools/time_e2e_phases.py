@@ -10,6 +10,7 @@ rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_S
 torch.cuda.set_device(local)
 comm = None
 if world > 1:
+    print('rank', rank, 'cpus', distributed.bindProcessToDeviceCpus(local)) if os.environ.get('BIND', '1') == '1' else None
     torch.distributed.init_process_group(backend='nccl', device_id=torch.device('cuda', local))
     comm = distributed.Comm()
 parDict, tileMaps, truth = bench_workloads.pointSourceConfig(numTiles=16, firstIndex=16 * rank)
