@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(512) xpower_smooth_x_rb_kernel(const typename 
                                                                  double* __restrict__ tmp, int H, int W, GaussW g) {
     typedef typename V2<T>::type C2;
     constexpr int P = F * (F + 1) / 2;
-    extern __shared__ double s_np[];  // [P][gs_pad(W + 2 R) + 1], position x + R holds kx = x, reflected halos on both sides
-    const int LD = gs_pad(W + 2 * R) + 1;
+    extern __shared__ double s_np[];  // [P][LD], position x + R holds kx = x, reflected halos on both sides (W rounded up to 8)
+    const int LD = gs_pad((W + GS_RB - 1) / GS_RB * GS_RB + 2 * R) + 1;   // the last thread of a row reads a full block of 8 + 2 R inputs
     const int ky = blockIdx.x, b = blockIdx.y;
     const int Wc = W / 2 + 1;
     const int kym = (H - ky) % H;
@@ -668,7 +668,7 @@ static int xpower_smooth_tf(const void* fmaps, double* cov, double* tmp, int B, 
     constexpr int P = F * (F + 1) / 2;
     constexpr int R = 12;     // gauss_radius(3.0): the register-blocked kernels are compiled for it
     if (g.r == R && W >= 2 * R && (W % 2) == 0) {
-        const size_t smem = (size_t)P * (gs_pad(W + 2 * R) + 1) * sizeof(double);
+        const size_t smem = (size_t)P * (gs_pad((W + GS_RB - 1) / GS_RB * GS_RB + 2 * R) + 1) * sizeof(double);
         NB_REQUIRE(smem <= 200 * 1024, NB_ERR_UNSUPPORTED, "nb_xpower_smooth: F=%d, W=%d needs too much shared memory", F, W);
         if (smem > 48 * 1024)
             NB_CHECK_CUDA(cudaFuncSetAttribute(xpower_smooth_x_rb_kernel<T, F, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
