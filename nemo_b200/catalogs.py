@@ -344,7 +344,10 @@ def _crossMatchKeepBest(ra, dec, snr, radiusDeg):
     toRemove = np.zeros(n, dtype=bool)
     if n < 2:
         return toRemove
-    pairs = _candidatePairsGrid(ra, dec, radiusDeg * 1.01)
+    # the strip sweep is the cheaper one until the strips get crowded (its candidates grow with n^2 / declination range)
+    pairs = None
+    if float(n) * n * radiusDeg / max(float(dec.max() - dec.min()), radiusDeg) > 5e4:
+        pairs = _candidatePairsGrid(ra, dec, radiusDeg * 1.01)
     if pairs is None:
         pairs = _candidatePairs(ra, dec, radiusDeg * 1.01)
     if len(pairs) == 0:

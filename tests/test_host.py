@@ -280,6 +280,17 @@ def test_cross_match_equals_the_quadratic_rule():
         want = brute(ra, dec, snr, catalogs.XMATCH_RADIUS_DEG)
         assert want.sum() > 20
         assert np.array_equal(got, want)
+        # both candidate generators (declination sweep for small catalogs, sky grid hash for crowded ones) hold every close pair
+        sep = lambda p: wcs.calcAngSepDeg(ra[p[:, 0]], dec[p[:, 0]], ra[p[:, 1]], dec[p[:, 1]])
+        close = set()
+        for i in range(n):
+            for j in np.flatnonzero(wcs.calcAngSepDeg(ra[i], dec[i], ra, dec) < catalogs.XMATCH_RADIUS_DEG):
+                if j != i:
+                    close.add((min(i, int(j)), max(i, int(j))))
+        for gen in (catalogs._candidatePairs, catalogs._candidatePairsGrid):
+            pairs = gen(ra, dec, catalogs.XMATCH_RADIUS_DEG * 1.01)
+            have = set((min(int(a), int(b)), max(int(a), int(b))) for a, b in pairs)
+            assert close <= have and len(have) == len(pairs)
 
 
 def test_row_areas_match_the_reference_pixel_area_map():
