@@ -1,0 +1,157 @@
+"""
+Runs the REFERENCE's own code (``/root/reference/nemo/filters.py`` and ``photometry.py``, unmodified, imported from where they
+lie) on the seeded tiles of the golden cases and stores its outputs in ``ref_<case>.npz``.  These fixtures pin the oracle
+(``tests/test_oracle.py::test_oracle_matches_reference_run``) and the CUDA path (``tests/test_golden_gpu.py``) against what the
+reference computes -- not against a restatement of it.
+
+    python tests/golden/make_reference_golden.py        # needs /root/reference; the fixtures travel, the reference does not
+
+What is the reference's and what is not.  The reference cannot be imported as a package here: astLib, astropy, pixell, pyccl,
+mahotas, mpi4py, matplotlib and its own compiled ``nemoCython`` are absent, and this fork assigns ``enmap = None``
+(nemo/filters.py:22-27), so even with every dependency present its Fourier filter could not run.  The generator therefore
+
+  * puts stand-in modules (``unittest.mock``) in ``sys.modules`` for the absent third-party packages, so that the reference's
+    source files import unchanged;
+  * hands the reference the things the hot path needs from those packages: ``enmap.fft / ifft / apod / apply_window``
+    (``oracle/pixell_shim.py``), a CAR ``astWCS.WCS`` and ``astCoords.calcAngSepDeg`` (``oracle/wcs_stub.py``) -- the published
+    behaviour of pixell / astLib, restated -- and the five CODATA constants ``signals.fSZ`` reads from ``astropy.constants``;
+  * gives its filter classes the signal TEMPLATE maps as inputs (``makeSignalTemplateMap`` is overridden to return the arrays the
+    oracle's painter makes): template painting needs pixell / nemoCython and is an input of the path.
+
+Everything else that runs is the reference's own code: ``filters.filterMaps``, ``MapFilter.__init__ / makeRadiansMap /
+makeNoiseMap``, ``MatchedFilter.buildAndApply / applyFilter`` (noise covariance, smoothing, the per-mode solve, normalisation,
+S/N, edge trimming, masks), ``photometry.getObjectPositions``, with the real numpy / scipy underneath.
+"""
+
+import importlib
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import types
+from unittest import mock
+
+import numpy as np
+import scipy, scipy.ndimage, scipy.interpolate, scipy.stats, scipy.optimize, scipy.integrate, scipy.special, scipy.signal  # noqa: F401,E401
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+REF = '/root/reference/nemo'
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Any import of an absent third-party package resolves to a MagicMock module."""
+    NAMES = ('astLib', 'astropy', 'pixell', 'pyccl', 'mahotas', 'mpi4py', 'pylab', 'matplotlib', 'colorcet', 'nemoCython', 'PIL',
+             'healpy', 'numba', 'cmocean', 'shapely', 'requests', 'zCluster', 'IPython', 'cycler', 'pyximport')
+
+    def find_spec(self, name, path, target=None):
+        if name.split('.')[0] in self.NAMES or name == 'nemo.nemoCython':
+            return importlib.machinery.ModuleSpec(name, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = mock.MagicMock(name=spec.name)
+        m.__name__, m.__path__, m.__spec__, m.__all__ = spec.name, [], spec, []
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+def loadReference():
+    """(filters, photometry) modules of the reference, executed from their own source files."""
+    from oracle import pixell_shim, wcs_stub
+    sys.meta_path.insert(0, _StubFinder())
+    pkg = types.ModuleType('nemo')
+    pkg.__path__ = [REF]
+    pkg.__version__ = 'reference'
+    sys.modules['nemo'] = pkg
+    refFilters = importlib.import_module('nemo.filters')
+    refPhotometry = importlib.import_module('nemo.photometry')
+    refMaps = importlib.import_module('nemo.maps')
+    shim = types.SimpleNamespace(fft=pixell_shim.fft, ifft=pixell_shim.ifft, apod=pixell_shim.apod, apply_window=pixell_shim.apply_window)
+    coords = types.SimpleNamespace(calcAngSepDeg=wcs_stub.calcAngSepDeg)
+    for mod in (refFilters, refPhotometry, refMaps):
+        mod.enmap = shim
+        mod.astCoords = coords
+    # astropy.constants (CODATA 2018), read by the reference's signals.fSZ (nemo/signals.py:364-369)
+    refSignals = importlib.import_module('nemo.signals')
+    val = lambda v: types.SimpleNamespace(value=v)
+    refSignals.constants = types.SimpleNamespace(h=val(6.62607015e-34), k_B=val(1.380649e-23), sigma_T=val(6.6524587321e-29),
+                                                 m_e=val(9.1093837015e-31), c=val(299792458.0), pc=val(3.0856775814913674e16),
+                                                 M_sun=val(1.988409870698051e30))
+    return refFilters, refPhotometry
+
+
+class RefMapDict(dict):
+    """What the reference's filter classes expect of maps.MapDict: a dict with copy() and preprocess() (FITS I/O there; the tiles
+    are already in memory here)."""
+
+    def copy(self):
+        return RefMapDict(self)
+
+    def preprocess(self, tileName='PRIMARY', diagnosticsDir=None):
+        return None
+
+
+def runCase(refFilters, refPhotometry, name, tmpDir):
+    from oracle import filters_ref
+    import copy
+    import make_golden
+    case = make_golden.CASES[name]
+    mapDicts, _ = make_golden.runCase(name)          # the same seeded tile the oracle fixture was made from
+    f = copy.deepcopy(case['filter'])
+    # the oracle object only paints the templates (inputs of the path)
+    oracleObj = getattr(filters_ref, f['class'])(f['label'], mapDicts, copy.deepcopy(f['params']), tileName='T0')
+
+    class RefFilter(refFilters.MatchedFilter):
+        def makeSignalTemplateMap(self, beamFileName, amplitude=None):
+            return oracleObj.makeSignalTemplateMap(beamFileName, amplitude=amplitude)
+
+    refFilters.RefFilter = RefFilter
+    refMaps = []
+    for m in mapDicts:
+        d = RefMapDict(m)
+        d['wcs'].AWCS = None            # MapFilter.__init__ keeps it for pixell; nothing on this path reads it
+        refMaps.append(d)
+    fRef = {'label': f['label'], 'class': 'RefFilter', 'params': copy.deepcopy(f['params'])}
+    os.makedirs(os.path.join(tmpDir, 'T0'), exist_ok=True)
+    out, obj = refFilters.filterMaps(refMaps, fRef, 'T0', diagnosticsDir=tmpDir, selFnDir=tmpDir, verbose=False,
+                                     undoPixelWindow=True, returnFilter=True)
+    ids, pos, numPix, seg = refPhotometry.getObjectPositions(out['SNMap'], 4.0, findCenterOfMass=True)
+    # the other branches of the reference's makeNoiseMap (filters.py:366-407 'smart', :464-465 'percentile'), on the filtered map
+    noise = {}
+    for key, noiseParams in (('smart', {'method': 'dataMap', 'noiseGridArcmin': 'smart', 'numNoiseBins': 6}),
+                             ('percentile', {'method': 'dataMap', 'noiseGridArcmin': 20., 'numNoiseBins': 2 if name.startswith('beam') else 1,
+                                             'RMSEstimator': 'percentile'})):   # constant weights leave bins empty, and np.percentile([]) raises
+        saved = obj.params['noiseParams']
+        obj.params['noiseParams'] = noiseParams
+        noise['noise_' + key] = np.asarray(obj.makeNoiseMap(np.asarray(out['SNMap']) * 3.0 + 0.0))
+        obj.params['noiseParams'] = saved
+    return {'data': np.asarray(out['data']), 'SNMap': np.asarray(out['SNMap']), 'surveyMask': np.asarray(out['surveyMask']),
+            'signalNorm': np.float64(obj.signalNorm), 'filt': np.asarray(obj.filt),
+            'objIDs': np.asarray(ids), 'objPositions': np.asarray(pos, dtype=np.float64).reshape(-1, 2), 'objNumPix': np.asarray(numPix),
+            'segmentationMap': np.asarray(seg, dtype=np.int32),
+            'fRelKeys': np.array(sorted(obj.fRelWeights.keys()), dtype=np.float64),
+            'fRelValues': np.array([obj.fRelWeights[k] for k in sorted(obj.fRelWeights.keys())], dtype=np.float64), **noise}
+
+
+def main():
+    import tempfile
+    sys.path.insert(0, HERE)
+    import make_golden
+    refFilters, refPhotometry = loadReference()
+    tmpDir = tempfile.mkdtemp()
+    for name in make_golden.CASES:
+        res = runCase(refFilters, refPhotometry, name, tmpDir)
+        # compact: S/N and data as float64 (they are the contract), the filter as a checksum plus a few samples
+        filt = res.pop('filt')
+        res['filtSample'] = filt[:, ::16, ::16].copy()
+        np.savez_compressed(os.path.join(HERE, 'ref_%s.npz' % name), **res)
+        print("%s: reference run stored (%d labels above S/N 4, signalNorm %.6g)" % (name, len(res['objIDs']) - 1, float(res['signalNorm'])))
+
+
+if __name__ == '__main__':
+    main()

@@ -2,7 +2,8 @@
 The CUDA path against the committed golden fixtures (tests/golden/*.npz, produced by the oracle with
 tests/golden/make_golden.py): S/N maps within 1e-4, survey masks and segmentation labels bit-exact, catalog identical
 above the S/N cut with positions within 0.01 px.  Inputs are regenerated from their seeds and checked against the
-recorded checksums; the oracle's filtering code is not run here.
+recorded checksums; the oracle's filtering code is not run here.  The same outputs are also checked against the fixtures
+ref_<case>.npz, which hold what the REFERENCE's own source files computed for these tiles (tests/golden/make_reference_golden.py).
 """
 
 import os
@@ -52,3 +53,40 @@ def test_cuda_path_matches_golden_fixture(name, report):
     if 'fRelWeights' in gold.files:
         for freq, wgt in gold['fRelWeights']:
             assert abs(obj.fRelWeights[float(freq)] - wgt) < 1e-8
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.CASES.keys()))
+def test_cuda_path_matches_reference_run(name, report):
+    """The CUDA path against runs of the reference's own code (nemo/filters.py, nemo/photometry.py imported from /root/reference
+    when the fixture was made): S/N map within 1e-4, filtered map, area mask and labels, object positions within 0.01 px, the
+    'smart' and 'percentile' noise maps."""
+    from nemo_b200 import filters, photometry
+    ref = np.load(os.path.join(HERE, 'golden', 'ref_' + name + '.npz'))
+    case = make_golden.CASES[name]
+    from oracle import synth
+    mapDicts, _ = synth.makeTile(**case['tile'])
+    if name == 'beam_f148_128_bins':
+        rng = np.random.default_rng(99)
+        mapDicts[0]['weights'] = mapDicts[0]['weights'] * (0.6 + 0.8 * rng.random(mapDicts[0]['weights'].shape))
+    got, obj = filters.filterMaps(mapDicts, make_golden.copyFilter(case['filter']), 'T0', verbose=False, returnFilter=True)
+    sn = np.asarray(got['SNMap'])
+    assert np.array_equal(np.asarray(got['surveyMask']) != 0, ref['surveyMask'] != 0)
+    assert np.allclose(sn, ref['SNMap'], rtol=1e-4, atol=1e-4)
+    errData = float(np.abs(np.asarray(got['data']) - ref['data']).max() / np.abs(ref['data']).max())
+    assert errData < 1e-4
+    assert abs(obj.signalNorm / float(ref['signalNorm']) - 1) < 1e-8
+    ids, pos, numPix, seg = photometry.getObjectPositions(got['SNMap'], 4.0)
+    assert np.array_equal(seg, ref['segmentationMap']) and np.array_equal(ids, ref['objIDs'])
+    assert np.array_equal(np.asarray(numPix, dtype=np.float64), np.asarray(ref['objNumPix'], dtype=np.float64))
+    p = np.asarray(pos, dtype=np.float64).reshape(-1, 2)
+    assert np.abs(p[1:] - ref['objPositions'][1:]).max() < 0.01          # entry 0 is the background label
+    # the other noise estimators, on the map the fixture used (3 x the reference's S/N map)
+    for key, noiseParams in (('smart', {'method': 'dataMap', 'noiseGridArcmin': 'smart', 'numNoiseBins': 6}),
+                             ('percentile', {'method': 'dataMap', 'noiseGridArcmin': 20., 'numNoiseBins': 2 if name.startswith('beam') else 1,
+                                             'RMSEstimator': 'percentile'})):
+        params = dict(make_golden.copyFilter(case['filter'])['params'], noiseParams=noiseParams)
+        f = filters.MapFilter('t', mapDicts, params)
+        rms = f.makeNoiseMap(ref['SNMap'] * 3.0 + 0.0)
+        assert np.array_equal(rms == 0, ref['noise_' + key] == 0), key
+        assert np.allclose(rms, ref['noise_' + key], rtol=1e-10, atol=0), key
+    report("reference_run_" + name, maxabs_dSN=float(np.abs(sn - ref['SNMap']).max()), rel_dData=errData, labels=int(len(ids) - 1))

@@ -182,3 +182,36 @@ def test_smart_noise_branch_known_answers():
     assert np.isclose(rms[6, 6], clipped(m[lowBin & (m != 0)]), rtol=1e-14)
     with pytest.raises(Exception):
         filters_ref.MapFilter('t', md, {'noiseParams': {'noiseGridArcmin': 'smart'}}).makeNoiseMap(m)
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.CASES.keys()))
+def test_oracle_matches_reference_run(name):
+    """The fixtures ref_<case>.npz hold what the REFERENCE's own source files computed for the golden tiles
+    (tests/golden/make_reference_golden.py: nemo/filters.py and nemo/photometry.py imported unmodified from /root/reference, the
+    absent third-party packages replaced by the shims, the template maps given as inputs).  The oracle must reproduce them bit
+    for bit: filtered map, S/N map, area mask, normalisation, relative frequency weights, labels, positions and pixel counts,
+    and the 'smart' and 'percentile' branches of makeNoiseMap."""
+    from oracle import filters_ref, photometry_ref
+    ref = np.load(os.path.join(HERE, 'golden', 'ref_' + name + '.npz'))
+    mapDicts, out = make_golden.runCase(name)
+    assert np.array_equal(out['data'], ref['data'])
+    assert np.array_equal(out['SNMap'], ref['SNMap'])
+    assert np.array_equal(out['surveyMask'] != 0, ref['surveyMask'] != 0)
+    assert float(out['signalNorm']) == float(ref['signalNorm'])
+    if 'fRelWeights' in out:
+        assert np.array_equal(out['fRelWeights'][np.argsort(out['fRelWeights'][:, 0]), 1], ref['fRelValues'])
+    ids, pos, numPix, seg = photometry_ref.getObjectPositions(out['SNMap'], 4.0)
+    assert np.array_equal(seg, ref['segmentationMap']) and np.array_equal(ids, ref['objIDs'])
+    assert np.array_equal(np.asarray(pos, dtype=np.float64).reshape(-1, 2), ref['objPositions'], equal_nan=True)
+    assert np.array_equal(numPix, ref['objNumPix'])
+    assert len(ids) - 1 >= 3
+    case = make_golden.CASES[name]
+    for key, noiseParams in (('smart', {'method': 'dataMap', 'noiseGridArcmin': 'smart', 'numNoiseBins': 6}),
+                             ('percentile', {'method': 'dataMap', 'noiseGridArcmin': 20., 'numNoiseBins': 2 if name.startswith('beam') else 1,
+                                             'RMSEstimator': 'percentile'})):   # constant weights leave bins empty, and np.percentile([]) raises
+        params = dict(make_golden.copyFilter(case['filter'])['params'], noiseParams=noiseParams)
+        f = filters_ref.MapFilter('t', mapDicts, params)
+        got = f.makeNoiseMap(out['SNMap'] * 3.0 + 0.0)
+        assert np.array_equal(got, ref['noise_' + key]), key
+        if name.startswith('beam') or key == 'percentile':      # constant weights have no 'smart' bins: all zero, as the reference
+            assert (got > 0).mean() > 0.3
