@@ -20,7 +20,8 @@ mahotas, mpi4py, matplotlib and its own compiled ``nemoCython`` are absent, and 
 
 Everything else that runs is the reference's own code: ``filters.filterMaps``, ``MapFilter.__init__ / makeRadiansMap /
 makeNoiseMap``, ``MatchedFilter.buildAndApply / applyFilter`` (noise covariance, smoothing, the per-mode solve, normalisation,
-S/N, edge trimming, masks), ``photometry.getObjectPositions``, with the real numpy / scipy underneath.
+S/N, edge trimming, masks), ``photometry.getObjectPositions / findObjects / measureFluxes`` and ``catalogs.catalogListToTab / makeName`` (with a plain column table
+standing in for ``astropy.table``), with the real numpy / scipy underneath.
 """
 
 import importlib
@@ -72,16 +73,23 @@ def loadReference():
     refPhotometry = importlib.import_module('nemo.photometry')
     refMaps = importlib.import_module('nemo.maps')
     shim = types.SimpleNamespace(fft=pixell_shim.fft, ifft=pixell_shim.ifft, apod=pixell_shim.apod, apply_window=pixell_shim.apply_window)
-    coords = types.SimpleNamespace(calcAngSepDeg=wcs_stub.calcAngSepDeg)
-    for mod in (refFilters, refPhotometry, refMaps):
+    coords = types.SimpleNamespace(calcAngSepDeg=wcs_stub.calcAngSepDeg,
+                                   convertCoords=lambda a, b, ra, dec, epoch: wcs_stub.j2000ToGalactic(ra, dec))
+    from nemo_b200 import catalogs as hostTables        # a column table with astropy's add_column / row assignment (pure Python)
+    tables = types.SimpleNamespace(Table=hostTables.Table, Column=hostTables.Column)
+    refCatalogs = importlib.import_module('nemo.catalogs')
+    for mod in (refFilters, refPhotometry, refMaps, refCatalogs):
         mod.enmap = shim
         mod.astCoords = coords
+        mod.atpy = tables
     # astropy.constants (CODATA 2018), read by the reference's signals.fSZ (nemo/signals.py:364-369)
     refSignals = importlib.import_module('nemo.signals')
-    val = lambda v: types.SimpleNamespace(value=v)
-    refSignals.constants = types.SimpleNamespace(h=val(6.62607015e-34), k_B=val(1.380649e-23), sigma_T=val(6.6524587321e-29),
-                                                 m_e=val(9.1093837015e-31), c=val(299792458.0), pc=val(3.0856775814913674e16),
-                                                 M_sun=val(1.988409870698051e30))
+    val = lambda v, cgs=None: types.SimpleNamespace(value=v, cgs=types.SimpleNamespace(value=cgs))
+    consts = types.SimpleNamespace(h=val(6.62607015e-34, 6.62607015e-27), k_B=val(1.380649e-23, 1.380649e-16), sigma_T=val(6.6524587321e-29),
+                                   m_e=val(9.1093837015e-31), c=val(299792458.0, 29979245800.0), pc=val(3.0856775814913674e16),
+                                   M_sun=val(1.988409870698051e30))
+    refSignals.constants = consts
+    refPhotometry.constants = consts          # photometry.deltaTToJyPerSr reads the cgs values (nemo/photometry.py:465-467)
     return refFilters, refPhotometry
 
 
@@ -121,6 +129,17 @@ def runCase(refFilters, refPhotometry, name, tmpDir):
     out, obj = refFilters.filterMaps(refMaps, fRef, 'T0', diagnosticsDir=tmpDir, selFnDir=tmpDir, verbose=False,
                                      undoPixelWindow=True, returnFilter=True)
     ids, pos, numPix, seg = refPhotometry.getObjectPositions(out['SNMap'], 4.0, findCenterOfMass=True)
+    # the reference's findObjects / measureFluxes on its own filtered maps (ring removal, spline S/N, names, fluxes)
+    import make_golden as mg
+    cat = refPhotometry.findObjects(out, threshold=mg.DETECT['threshold'], minObjPix=mg.DETECT['minObjPix'],
+                                    rejectBorder=mg.DETECT['rejectBorder'], findCenterOfMass=mg.DETECT['findCenterOfMass'],
+                                    removeRings=mg.DETECT['removeRings'], ringThresholdSigma=mg.DETECT['ringThresholdSigma'],
+                                    useInterpolator=mg.DETECT['useInterpolator'], verbose=False)
+    refPhotometry.measureFluxes(cat, out, tmpDir, useInterpolator=mg.DETECT['useInterpolator'])
+    catalog = {}
+    for k in cat.keys():
+        col = np.asarray(cat[k])
+        catalog['refcat_' + k] = col.astype(str) if col.dtype == object or col.dtype.kind in 'US' else col.astype(np.float64)
     # the other branches of the reference's makeNoiseMap (filters.py:366-407 'smart', :464-465 'percentile'), on the filtered map
     noise = {}
     for key, noiseParams in (('smart', {'method': 'dataMap', 'noiseGridArcmin': 'smart', 'numNoiseBins': 6}),
@@ -135,7 +154,7 @@ def runCase(refFilters, refPhotometry, name, tmpDir):
             'objIDs': np.asarray(ids), 'objPositions': np.asarray(pos, dtype=np.float64).reshape(-1, 2), 'objNumPix': np.asarray(numPix),
             'segmentationMap': np.asarray(seg, dtype=np.int32),
             'fRelKeys': np.array(sorted(obj.fRelWeights.keys()), dtype=np.float64),
-            'fRelValues': np.array([obj.fRelWeights[k] for k in sorted(obj.fRelWeights.keys())], dtype=np.float64), **noise}
+            'fRelValues': np.array([obj.fRelWeights[k] for k in sorted(obj.fRelWeights.keys())], dtype=np.float64), **noise, **catalog}
 
 
 def main():

@@ -80,6 +80,18 @@ def test_cuda_path_matches_reference_run(name, report):
     assert np.array_equal(np.asarray(numPix, dtype=np.float64), np.asarray(ref['objNumPix'], dtype=np.float64))
     p = np.asarray(pos, dtype=np.float64).reshape(-1, 2)
     assert np.abs(p[1:] - ref['objPositions'][1:]).max() < 0.01          # entry 0 is the background label
+    # the catalog of the reference's findObjects + measureFluxes on its own maps
+    cat = photometry.findObjects(got, **make_golden.DETECT)
+    photometry.measureFluxes(cat, got, None)
+    assert len(cat) == len(ref['refcat_RADeg'])
+    assert list(cat['name']) == list(ref['refcat_name'])
+    pixDeg = mapDicts[0]['wcs'].getPixelSizeDeg()
+    assert np.abs(np.asarray(cat['RADeg'], dtype=float) - ref['refcat_RADeg']).max() < 0.01 * pixDeg
+    assert np.abs(np.asarray(cat['decDeg'], dtype=float) - ref['refcat_decDeg']).max() < 0.01 * pixDeg
+    assert np.array_equal(np.asarray(cat['numSigPix'], dtype=float), ref['refcat_numSigPix'])
+    for k in [k[7:] for k in ref.files if k.startswith('refcat_')]:
+        if k not in ('name', 'template', 'tileName', 'RADeg', 'decDeg', 'numSigPix'):
+            np.testing.assert_allclose(np.asarray(cat[k], dtype=np.float64), ref['refcat_' + k], rtol=1e-4, atol=1e-9, err_msg=k)
     # the other noise estimators, on the map the fixture used (3 x the reference's S/N map)
     for key, noiseParams in (('smart', {'method': 'dataMap', 'noiseGridArcmin': 'smart', 'numNoiseBins': 6}),
                              ('percentile', {'method': 'dataMap', 'noiseGridArcmin': 20., 'numNoiseBins': 2 if name.startswith('beam') else 1,

@@ -190,7 +190,8 @@ def test_oracle_matches_reference_run(name):
     (tests/golden/make_reference_golden.py: nemo/filters.py and nemo/photometry.py imported unmodified from /root/reference, the
     absent third-party packages replaced by the shims, the template maps given as inputs).  The oracle must reproduce them bit
     for bit: filtered map, S/N map, area mask, normalisation, relative frequency weights, labels, positions and pixel counts,
-    and the 'smart' and 'percentile' branches of makeNoiseMap."""
+    the catalog of findObjects + measureFluxes (names, sky positions, S/N, pixel counts, flags, fluxes) and the 'smart' and
+    'percentile' branches of makeNoiseMap."""
     from oracle import filters_ref, photometry_ref
     ref = np.load(os.path.join(HERE, 'golden', 'ref_' + name + '.npz'))
     mapDicts, out = make_golden.runCase(name)
@@ -205,6 +206,17 @@ def test_oracle_matches_reference_run(name):
     assert np.array_equal(np.asarray(pos, dtype=np.float64).reshape(-1, 2), ref['objPositions'], equal_nan=True)
     assert np.array_equal(numPix, ref['objNumPix'])
     assert len(ids) - 1 >= 3
+    # the reference's findObjects / measureFluxes / makeName on its own filtered maps: the catalog, column by column
+    refKeys = [k[7:] for k in ref.files if k.startswith('refcat_')]
+    assert len(ref['refcat_RADeg']) == int(out['numObjects']) >= 3
+    for k in refKeys:
+        if k in ('template', 'tileName'):
+            continue
+        if ref['refcat_' + k].dtype.kind in 'US':
+            assert list(ref['refcat_' + k]) == list(out['cat_' + k]), k
+        else:
+            assert np.array_equal(ref['refcat_' + k], out['cat_' + k]), k
+    assert {'name', 'RADeg', 'decDeg', 'SNR', 'numSigPix', 'flags', 'galacticLatDeg', 'deltaT_c', 'err_deltaT_c'} <= set(refKeys)
     case = make_golden.CASES[name]
     for key, noiseParams in (('smart', {'method': 'dataMap', 'noiseGridArcmin': 'smart', 'numNoiseBins': 6}),
                              ('percentile', {'method': 'dataMap', 'noiseGridArcmin': 20., 'numNoiseBins': 2 if name.startswith('beam') else 1,
