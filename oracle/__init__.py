@@ -23,8 +23,9 @@ fixtures BIT FOR BIT (``tests/test_oracle.py::test_oracle_matches_reference_run`
 normalisation, relative weights, labels, positions, and every column of the catalogs), and the CUDA path is tested against the same fixtures
 (``tests/test_golden_gpu.py``).  Still restated from published behaviour only: pixell ``enmap.fft/ifft/apod/apply_window`` and the
 astLib CAR WCS and J2000 -> Galactic rotation (pinned by the known-answer tests in ``tests/test_oracle.py``), the
-signal-template painters and the real-space filter (whose kernel construction deletes the in-memory maps in this fork,
-nemo/filters.py:919-923, so it cannot run on arrays).  The scipy / numpy calls the reference makes (``ndimage.label``, ``center_of_mass``,
+signal-template painters and the real-space filter's kernel construction (it deletes the in-memory maps in this fork,
+nemo/filters.py:919-923, so it cannot run on arrays; the filter's ``applyFilter``, ``catalogs.makeOptimalCatalog`` and
+``maps.getPixelAreaArcmin2Map`` do run and are pinned by ``tests/golden/ref_misc.npz``).  The scipy / numpy calls the reference makes (``ndimage.label``, ``center_of_mass``,
 ``gaussian_filter``, ``rank_filter``, ``convolve``, ``RectBivariateSpline``, ``np.linalg.inv``, ``np.percentile``) are called
 here for real, so those are the reference's arithmetic exactly.
 """

@@ -157,6 +157,60 @@ def runCase(refFilters, refPhotometry, name, tmpDir):
             'fRelValues': np.array([obj.fRelWeights[k] for k in sorted(obj.fRelWeights.keys())], dtype=np.float64), **noise, **catalog}
 
 
+def miscInputs():
+    """Seeded inputs of the stand-alone pieces (also read by the tests): a two-frequency cube and kernel for the real-space
+    filter's applyFilter, two overlapping catalogs for the cross-scale merge."""
+    from oracle.wcs_stub import SimpleCARWCS
+    rng = np.random.default_rng(2024)
+    shape = (96, 120)
+    wcs = SimpleCARWCS(shape, 0.5 / 60.0, crval=(30.0, -20.0))
+    cube = rng.standard_normal((2,) + shape) * np.array([60.0, 40.0])[:, None, None]
+    yy, xx = np.mgrid[-4:5, -4:5]
+    kern = np.stack([np.exp(-(xx ** 2 + yy ** 2) / (2 * s ** 2)) - 0.4 * np.exp(-(xx ** 2 + yy ** 2) / (2 * (2 * s) ** 2)) for s in (1.2, 1.8)])
+    kern[1] *= -0.3
+    n = 40
+    ra = 30.0 + rng.uniform(-0.4, 0.4, n)
+    dec = -20.0 + rng.uniform(-0.3, 0.3, n)
+    snr = rng.uniform(4, 30, n)
+    catA = {'RADeg': ra, 'decDeg': dec, 'SNR': snr}
+    keep = rng.random(n) < 0.7                                   # the second scale re-detects most objects, slightly shifted
+    catB = {'RADeg': ra[keep] + rng.normal(0, 0.002, keep.sum()), 'decDeg': dec[keep] + rng.normal(0, 0.002, keep.sum()),
+            'SNR': snr[keep] * rng.uniform(0.6, 1.5, keep.sum())}
+    extra = {'RADeg': 30.0 + rng.uniform(-0.4, 0.4, 6), 'decDeg': -20.0 + rng.uniform(-0.3, 0.3, 6), 'SNR': rng.uniform(4, 9, 6)}
+    catB = {k: np.concatenate([catB[k], extra[k]]) for k in catB}
+    return {'shape': shape, 'wcs': wcs, 'cube': cube, 'kern': kern, 'catA': catA, 'catB': catB,
+            'applyRADeg': 30.0, 'applyDecDeg': -20.0, 'bckSubScaleArcmin': 3.0, 'signalNorm': 0.37}
+
+
+def runMisc(refFilters):
+    """Stand-alone pieces of the reference: RealSpaceMatchedFilter.applyFilter (maps.subtractBackground / smoothMap +
+    ndimage.convolve, nemo/filters.py:1172-1218), catalogs.makeOptimalCatalog (nemo/catalogs.py:149-189) and
+    maps.getPixelAreaArcmin2Map (nemo/maps.py:1461-1482)."""
+    from nemo_b200 import catalogs as hostTables
+    refCatalogs = importlib.import_module('nemo.catalogs')
+    refMaps = importlib.import_module('nemo.maps')
+    refCatalogs.atpy.vstack = hostTables.vstack
+    inp = miscInputs()
+    obj = object.__new__(refFilters.RealSpaceMatchedFilter)
+    obj.params = {'bckSub': True}
+    obj.wcs, obj.kern2d, obj.signalNorm = inp['wcs'], inp['kern'], inp['signalNorm']
+    obj.applyRACentre, obj.applyDecCentre, obj.bckSubScaleArcmin = inp['applyRADeg'], inp['applyDecDeg'], inp['bckSubScaleArcmin']
+    obj.unfilteredMapsDictList = [{'obsFreqGHz': 97.8}, {'obsFreqGHz': 149.6}]
+    filtered = obj.applyFilter(inp['cube'].copy(), calcFRelWeights=True)
+    obj.params = {'bckSub': False}
+    filteredNoBck = obj.applyFilter(inp['cube'].copy())
+
+    def table(cols):
+        return hostTables.Table.fromColumns([(k, np.array(v)) for k, v in cols.items()])
+    merged = refCatalogs.makeOptimalCatalog({'A#t': {'catalog': table(inp['catA'])}, 'B#t': {'catalog': table(inp['catB'])}})
+    area = refMaps.getPixelAreaArcmin2Map(inp['shape'], inp['wcs'])
+    return {'rs_filtered': filtered, 'rs_filteredNoBck': filteredNoBck,
+            'rs_fRel': np.array([obj.fRelWeights[97.8], obj.fRelWeights[149.6]]),
+            'opt_RADeg': np.asarray(merged['RADeg'], dtype=np.float64), 'opt_decDeg': np.asarray(merged['decDeg'], dtype=np.float64),
+            'opt_SNR': np.asarray(merged['SNR'], dtype=np.float64), 'pixAreaArcmin2Rows': np.asarray(area)[:, 0].copy(),
+            'pixAreaConstantAlongRows': np.array(np.array_equal(np.asarray(area)[:, :1] * np.ones((1, inp['shape'][1])), area))}
+
+
 def main():
     import tempfile
     sys.path.insert(0, HERE)
@@ -170,6 +224,9 @@ def main():
         res['filtSample'] = filt[:, ::16, ::16].copy()
         np.savez_compressed(os.path.join(HERE, 'ref_%s.npz' % name), **res)
         print("%s: reference run stored (%d labels above S/N 4, signalNorm %.6g)" % (name, len(res['objIDs']) - 1, float(res['signalNorm'])))
+    misc = runMisc(refFilters)
+    np.savez_compressed(os.path.join(HERE, 'ref_misc.npz'), **misc)
+    print("misc: real-space applyFilter, makeOptimalCatalog (%d rows kept), pixel areas stored" % len(misc['opt_SNR']))
 
 
 if __name__ == '__main__':

@@ -102,3 +102,30 @@ def test_cuda_path_matches_reference_run(name, report):
         assert np.array_equal(rms == 0, ref['noise_' + key] == 0), key
         assert np.allclose(rms, ref['noise_' + key], rtol=1e-10, atol=0), key
     report("reference_run_" + name, maxabs_dSN=float(np.abs(sn - ref['SNMap']).max()), rel_dData=errData, labels=int(len(ids) - 1))
+
+
+def test_real_space_apply_matches_reference_run(report):
+    """RealSpaceMatchedFilter.applyFilter on the device (Gaussian high-pass K12 + kernel convolution K13) against what the
+    reference's own applyFilter (nemo/filters.py:1172-1218, with maps.subtractBackground / smoothMap) computed for the seeded
+    cube and kernel of ref_misc.npz."""
+    import make_reference_golden as mrg
+    from nemo_b200 import filters, device
+    from nemo_b200.wcs import CARWCS
+    ref = np.load(os.path.join(HERE, 'golden', 'ref_misc.npz'))
+    inp = mrg.miscInputs()
+    obj = object.__new__(filters.RealSpaceMatchedFilter)
+    obj.ops = device.getOps('f64')
+    obj.params = {'bckSub': True}
+    obj.wcs = CARWCS(inp['shape'], 0.5 / 60.0, crval=(30.0, -20.0))
+    obj.kern2d, obj.signalNorm = inp['kern'], inp['signalNorm']
+    obj.applyRACentre, obj.applyDecCentre, obj.bckSubScaleArcmin = inp['applyRADeg'], inp['applyDecDeg'], inp['bckSubScaleArcmin']
+    obj.unfilteredMapsDictList = [{'obsFreqGHz': 97.8}, {'obsFreqGHz': 149.6}]
+    got = obj.applyFilter(inp['cube'].copy(), calcFRelWeights=True)
+    scale = np.abs(ref['rs_filtered']).max()
+    err = float(np.abs(got - ref['rs_filtered']).max() / scale)
+    assert err < 1e-12
+    assert np.allclose([obj.fRelWeights[97.8], obj.fRelWeights[149.6]], ref['rs_fRel'], rtol=1e-10, atol=0)
+    obj.params = {'bckSub': False}
+    errNo = float(np.abs(obj.applyFilter(inp['cube'].copy()) - ref['rs_filteredNoBck']).max() / np.abs(ref['rs_filteredNoBck']).max())
+    assert errNo < 1e-12
+    report("reference_run_real_space_apply", rel_err=err, rel_err_no_bck=errNo)

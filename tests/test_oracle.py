@@ -227,3 +227,36 @@ def test_oracle_matches_reference_run(name):
         assert np.array_equal(got, ref['noise_' + key]), key
         if name.startswith('beam') or key == 'percentile':      # constant weights have no 'smart' bins: all zero, as the reference
             assert (got > 0).mean() > 0.3
+
+
+def test_standalone_pieces_match_reference_run():
+    """ref_misc.npz: the reference's RealSpaceMatchedFilter.applyFilter (Gaussian high-pass + kernel convolution,
+    nemo/filters.py:1172-1218), catalogs.makeOptimalCatalog (nemo/catalogs.py:149-189) and maps.getPixelAreaArcmin2Map
+    (nemo/maps.py:1461-1482), run from their own source files on seeded inputs; the oracle and the host-side merge reproduce
+    them."""
+    import make_reference_golden as mrg
+    from oracle import filters_ref, completeness_ref
+    from nemo_b200 import catalogs, completeness
+    from nemo_b200.wcs import CARWCS
+    ref = np.load(os.path.join(HERE, 'golden', 'ref_misc.npz'))
+    inp = mrg.miscInputs()
+    obj = object.__new__(filters_ref.RealSpaceMatchedFilter)
+    obj.params = {'bckSub': True}
+    obj.wcs, obj.kern2d, obj.signalNorm = inp['wcs'], inp['kern'], inp['signalNorm']
+    obj.applyRACentre, obj.applyDecCentre, obj.bckSubScaleArcmin = inp['applyRADeg'], inp['applyDecDeg'], inp['bckSubScaleArcmin']
+    obj.unfilteredMapsDictList = [{'obsFreqGHz': 97.8}, {'obsFreqGHz': 149.6}]
+    assert np.array_equal(obj.applyFilter(inp['cube'].copy(), calcFRelWeights=True), ref['rs_filtered'])
+    assert np.array_equal(np.array([obj.fRelWeights[97.8], obj.fRelWeights[149.6]]), ref['rs_fRel'])
+    obj.params = {'bckSub': False}
+    assert np.array_equal(obj.applyFilter(inp['cube'].copy()), ref['rs_filteredNoBck'])
+    # pixel areas
+    area = completeness_ref.getPixelAreaArcmin2Map(inp['shape'], inp['wcs'])
+    assert bool(ref['pixAreaConstantAlongRows']) and np.array_equal(area[:, 0], ref['pixAreaArcmin2Rows'])
+    wcs = CARWCS(inp['shape'], 0.5 / 60.0, crval=(30.0, -20.0))
+    assert np.allclose(completeness.rowAreasDeg2(inp['shape'], wcs) * 3600.0, ref['pixAreaArcmin2Rows'], rtol=1e-13, atol=0)
+    # cross-scale merge: same rows, same order
+    table = lambda cols: catalogs.Table.fromColumns([(k, np.array(v)) for k, v in cols.items()])
+    merged = catalogs.makeOptimalCatalog({'A#t': {'catalog': table(inp['catA'])}, 'B#t': {'catalog': table(inp['catB'])}})
+    assert len(merged) == len(ref['opt_SNR']) and 30 < len(merged) < len(inp['catA']['SNR']) + len(inp['catB']['SNR'])
+    for k in ('RADeg', 'decDeg', 'SNR'):
+        assert np.array_equal(np.asarray(merged[k], dtype=np.float64), ref['opt_' + k]), k
