@@ -182,6 +182,51 @@ def miscInputs():
             'applyRADeg': 30.0, 'applyDecDeg': -20.0, 'bckSubScaleArcmin': 3.0, 'signalNorm': 0.37}
 
 
+PHOT_SECOND_SCALE = {'label': 'Arnaud_M8e14_z0p2', 'class': 'ArnaudModelMatchedFilter',
+                     'params': {'M500MSun': 8e14, 'z': 0.2, 'noiseParams': {'method': 'dataMap', 'noiseGridArcmin': 20.},
+                                'outputUnits': 'yc', 'edgeTrimArcmin': 0.}}
+
+
+def runPhotFilter(refFilters, refPhotometry, tmpDir):
+    """The photFilter flow of the inner loop (nemo/pipelines.py:238-284) with the reference's own functions: the golden Arnaud
+    tile filtered at its own scale (the reference filter) and at a second scale; the second scale's catalog gets fixed_SNR from
+    the reference filter's S/N map (getSNRValues, prefix 'fixed_') and fixed_ fluxes (measureFluxes with photFilteredMapDict)."""
+    from oracle import filters_ref
+    import copy
+    import make_golden
+    mapDicts, _ = make_golden.runCase('arnaud_f148_128')
+    outs = []
+    for f in (make_golden.CASES['arnaud_f148_128']['filter'], PHOT_SECOND_SCALE):
+        f = copy.deepcopy(f)
+        oracleObj = getattr(filters_ref, f['class'])(f['label'], mapDicts, copy.deepcopy(f['params']), tileName='T0')
+
+        class RefFilter(refFilters.MatchedFilter):
+            def makeSignalTemplateMap(self, beamFileName, amplitude=None, _o=oracleObj):
+                return _o.makeSignalTemplateMap(beamFileName, amplitude=amplitude)
+        refFilters.RefFilter = RefFilter
+        refMaps = []
+        for m in mapDicts:
+            d = RefMapDict(m)
+            d['wcs'].AWCS = None
+            refMaps.append(d)
+        os.makedirs(os.path.join(tmpDir, 'T0'), exist_ok=True)
+        outs.append(refFilters.filterMaps(refMaps, {'label': f['label'], 'class': 'RefFilter', 'params': copy.deepcopy(f['params'])}, 'T0',
+                                          diagnosticsDir=tmpDir, selFnDir=tmpDir, verbose=False, undoPixelWindow=True))
+    phot = {'SNMap': outs[0]['SNMap'], 'data': outs[0]['data']}
+    mg = make_golden
+    cat = refPhotometry.findObjects(outs[1], threshold=mg.DETECT['threshold'], minObjPix=mg.DETECT['minObjPix'],
+                                    rejectBorder=mg.DETECT['rejectBorder'], findCenterOfMass=mg.DETECT['findCenterOfMass'],
+                                    removeRings=mg.DETECT['removeRings'], ringThresholdSigma=mg.DETECT['ringThresholdSigma'],
+                                    useInterpolator=mg.DETECT['useInterpolator'], verbose=False)
+    refPhotometry.getSNRValues(cat, phot['SNMap'], outs[1]['wcs'], prefix='fixed_', useInterpolator=mg.DETECT['useInterpolator'])
+    refPhotometry.measureFluxes(cat, outs[1], tmpDir, photFilteredMapDict=phot, useInterpolator=mg.DETECT['useInterpolator'])
+    res = {}
+    for k in cat.keys():
+        col = np.asarray(cat[k])
+        res['phot_' + k] = col.astype(str) if col.dtype == object or col.dtype.kind in 'US' else col.astype(np.float64)
+    return res
+
+
 def runMisc(refFilters):
     """Stand-alone pieces of the reference: RealSpaceMatchedFilter.applyFilter (maps.subtractBackground / smoothMap +
     ndimage.convolve, nemo/filters.py:1172-1218), catalogs.makeOptimalCatalog (nemo/catalogs.py:149-189) and
@@ -225,6 +270,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, 'ref_%s.npz' % name), **res)
         print("%s: reference run stored (%d labels above S/N 4, signalNorm %.6g)" % (name, len(res['objIDs']) - 1, float(res['signalNorm'])))
     misc = runMisc(refFilters)
+    misc.update(runPhotFilter(refFilters, refPhotometry, tmpDir))
     np.savez_compressed(os.path.join(HERE, 'ref_misc.npz'), **misc)
     print("misc: real-space applyFilter, makeOptimalCatalog (%d rows kept), pixel areas stored" % len(misc['opt_SNR']))
 

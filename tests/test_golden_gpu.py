@@ -129,3 +129,27 @@ def test_real_space_apply_matches_reference_run(report):
     errNo = float(np.abs(obj.applyFilter(inp['cube'].copy()) - ref['rs_filteredNoBck']).max() / np.abs(ref['rs_filteredNoBck']).max())
     assert errNo < 1e-12
     report("reference_run_real_space_apply", rel_err=err, rel_err_no_bck=errNo)
+
+
+def test_phot_filter_flow_matches_reference_run(report):
+    """The batched driver with a photFilter (reference filter first, fixed_SNR and fixed_ fluxes for the other scale) against the
+    reference's own findObjects + getSNRValues + measureFluxes on that tile (ref_misc.npz phot_*)."""
+    import copy
+    import make_reference_golden as mrg
+    from nemo_b200 import pipelines
+    ref = np.load(os.path.join(HERE, 'golden', 'ref_misc.npz'))
+    mapDicts, _ = make_golden.runCase('arnaud_f148_128')
+    f0, f1 = copy.deepcopy(make_golden.CASES['arnaud_f148_128']['filter']), copy.deepcopy(mrg.PHOT_SECOND_SCALE)
+    parDict = {'mapFilters': [f1, f0], 'photFilter': f0['label'], 'thresholdSigma': make_golden.DETECT['threshold'],
+               'minObjPix': make_golden.DETECT['minObjPix'], 'findCenterOfMass': True, 'useInterpolator': True, 'rejectBorder': 0,
+               'removeRings': True, 'ringThresholdSigma': make_golden.DETECT['ringThresholdSigma']}
+    config = pipelines.SimpleConfig(parDict, {'T0': mapDicts})
+    pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=1)
+    cat = config.catalogDict[f1['label'] + '#T0']['catalog']
+    assert len(cat) == len(ref['phot_SNR'])
+    assert list(cat['name']) == list(ref['phot_name'])
+    for k in [k[5:] for k in ref.files if k.startswith('phot_')]:
+        if k in ('name', 'template', 'tileName'):
+            continue
+        np.testing.assert_allclose(np.asarray(cat[k], dtype=np.float64), ref['phot_' + k], rtol=1e-4, atol=1e-9, err_msg=k)
+    report("reference_run_phot_filter", rows=len(cat), max_rel_fixed_SNR=float(np.abs(np.asarray(cat['fixed_SNR'], dtype=float) / ref['phot_fixed_SNR'] - 1).max()))

@@ -260,3 +260,27 @@ def test_standalone_pieces_match_reference_run():
     assert len(merged) == len(ref['opt_SNR']) and 30 < len(merged) < len(inp['catA']['SNR']) + len(inp['catB']['SNR'])
     for k in ('RADeg', 'decDeg', 'SNR'):
         assert np.array_equal(np.asarray(merged[k], dtype=np.float64), ref['opt_' + k]), k
+
+
+def test_phot_filter_flow_matches_reference_run():
+    """ref_misc.npz phot_*: the reference's findObjects + getSNRValues(prefix='fixed_') + measureFluxes(photFilteredMapDict=...) on a
+    second filter scale of the golden Arnaud tile (the flow of nemo/pipelines.py:238-284); the oracle reproduces every column."""
+    import copy
+    import make_reference_golden as mrg
+    from oracle import filters_ref, photometry_ref
+    ref = np.load(os.path.join(HERE, 'golden', 'ref_misc.npz'))
+    mapDicts, _ = make_golden.runCase('arnaud_f148_128')
+    outs = [filters_ref.filterMaps(mapDicts, copy.deepcopy(f), 'T0') for f in (make_golden.CASES['arnaud_f148_128']['filter'], mrg.PHOT_SECOND_SCALE)]
+    phot = {'SNMap': outs[0]['SNMap'], 'data': outs[0]['data']}
+    cat = photometry_ref.findObjects(outs[1], **make_golden.DETECT)
+    photometry_ref.getSNRValues(cat, phot['SNMap'], outs[1]['wcs'], prefix='fixed_', useInterpolator=True)
+    photometry_ref.measureFluxes(cat, outs[1], None, photFilteredMapDict=phot, useInterpolator=True)
+    assert len(cat) == len(ref['phot_SNR']) >= 3
+    for k in [k[5:] for k in ref.files if k.startswith('phot_')]:
+        if k in ('template', 'tileName'):
+            continue
+        col = [row[k] for row in cat]
+        if ref['phot_' + k].dtype.kind in 'US':
+            assert [str(v) for v in col] == list(ref['phot_' + k]), k
+        else:
+            assert np.array_equal(np.array(col, dtype=np.float64), ref['phot_' + k]), k
