@@ -111,9 +111,9 @@ class TileBatch(object):
         return self.dev
 
 
-def widenStaged(ops, dev):
+def widenStaged(ops, dev, keys=('data', 'weights')):
     """float32-staged maps / weights of a device dictionary -> the compute type, in place in the dictionary."""
-    for k in ('data', 'weights'):
+    for k in keys:
         if dev[k].dtype != ops.dtype:
             dev[k] = ops.widen(dev[k])
     return dev
@@ -310,7 +310,7 @@ class BatchPipeline(object):
             job['batch'].dev = None
         return out
 
-    def _graphEntry(self, slot, st, batch, upload):
+    def _graphEntry(self, slot, st, batch, upload, cache=None):
         """(graph, job template, static inputs, launches per replay) for this slot and batch shape, captured on first use."""
         from . import _lib
         ops, torch = self.ops, self.ops.torch
@@ -318,7 +318,11 @@ class BatchPipeline(object):
             ident = ('staged', str(batch.host['data'].dtype), str(batch.host['weights'].dtype))
         else:
             ident = tuple(int(batch.dev[k].data_ptr()) for k in ('data', 'weights', 'psMask', 'surveyMask', 'wmed'))
-        key = (slot, ident, batch.nT, batch.F, batch.H, batch.W, ops.precision, id(self.templates), self.undoPixelWindow, self.invertMap, self.rmsTables,
+        # cached filters / RMS maps (the source-injection loop) are device buffers that persist between calls: part of the key
+        cacheIdent = None
+        if cache is not None:
+            cacheIdent = (self.useCachedRMSMap,) + tuple(int(cache[k].data_ptr()) for k in ('filtH', 'signalNorm', 'RMSMap') if cache.get(k) is not None)
+        key = (slot, ident, cacheIdent, batch.nT, batch.F, batch.H, batch.W, ops.precision, id(self.templates), self.undoPixelWindow, self.invertMap, self.rmsTables,
                repr(sorted((k, repr(v)) for k, v in self.parDict.items() if k != 'mapFilters')),
                repr([(f['label'], repr(sorted(f['params'].items(), key=lambda kv: kv[0]))) for f in self.filtersList]))
         entry = self.graphs.get(key)
@@ -332,22 +336,25 @@ class BatchPipeline(object):
             else:
                 static = dict(batch.dev)
             view = _BatchView(batch, dict(static))
+            photInList = self.parDict.get('photFilter') is not None and any(f['label'] == self.parDict['photFilter'] for f in self.filtersList)
+            needWeights = not (cache is not None and self.useCachedRMSMap and photInList and not self.rmsTables)
             if upload:
-                widenStaged(ops, view.dev)
-                view.dev['wmed'] = ops.median_weights(view.dev['weights'])
+                widenStaged(ops, view.dev) if needWeights else widenStaged(ops, view.dev, keys=('data',))
+                view.dev['wmed'] = ops.median_weights(view.dev['weights']) if needWeights else None
             # one eager run first: twiddle tables, kernel attributes and other lazy set-up must not happen under capture
             startTileBatch(ops, view, self.filtersList, self.templates, self.parDict, undoPixelWindow=self.undoPixelWindow,
-                           invertMap=self.invertMap, rmsTables=self.rmsTables)
+                           invertMap=self.invertMap, rmsTables=self.rmsTables, cache=cache, useCachedRMSMap=self.useCachedRMSMap)
             st.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launchCount()
             with torch.cuda.graph(graph, stream=st):
                 if upload:
                     view.dev.update(static)          # the widening of float32-staged maps is part of the captured work
-                    widenStaged(ops, view.dev)
-                    view.dev['wmed'] = ops.median_weights(view.dev['weights'])
+                    widenStaged(ops, view.dev) if needWeights else widenStaged(ops, view.dev, keys=('data',))
+                    view.dev['wmed'] = ops.median_weights(view.dev['weights']) if needWeights else None
                 job = startTileBatch(ops, view, self.filtersList, self.templates, self.parDict,
-                                     undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap, rmsTables=self.rmsTables)
+                                     undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap, rmsTables=self.rmsTables,
+                                     cache=cache, useCachedRMSMap=self.useCachedRMSMap)
             nLaunch = _lib.launchCount() - n0
         entry = (graph, job, static, nLaunch)
         self.graphs[key] = entry
@@ -361,12 +368,18 @@ class BatchPipeline(object):
         slot = self.count % len(self.streams)
         st = self.streams[slot]
         self.count += 1
-        useGraph = self.useGraphs and cache is None and not _lib.profEnabled()
+        useGraph = self.useGraphs and not _lib.profEnabled()
+        # with cached filters AND a cached RMS map nothing reads the weights (they only feed the noise estimate): a realisation of
+        # the injection loop uploads its maps and masks, not the weight maps
+        photInList = self.parDict.get('photFilter') is not None and any(f['label'] == self.parDict['photFilter'] for f in self.filtersList)
+        skipKeys = ('weights', 'rowArea') if (cache is not None and self.useCachedRMSMap and photInList and not self.rmsTables) else ()
         if useGraph:
-            graph, template, static, nLaunch = self._graphEntry(slot, st, batch, upload)
+            graph, template, static, nLaunch = self._graphEntry(slot, st, batch, upload, cache)
             with torch.cuda.stream(st):
                 if upload:
                     for k, v in batch.host.items():
+                        if k in skipKeys:
+                            continue
                         static[k].copy_(device.countH2D(v), non_blocking=True)
                 graph.replay()
             _lib.load().nb_launch_count_add(nLaunch)
