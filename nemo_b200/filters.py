@@ -71,6 +71,9 @@ def _maskToU8(m, shape):
     return np.ascontiguousarray(np.not_equal(m, 0), dtype=np.uint8)
 
 
+_RADIANS_MAPS = {}
+
+
 class MapFilter(object):
     """Base class: prepares the maps of one tile on the device and provides the noise-map machinery."""
 
@@ -174,11 +177,21 @@ class MapFilter(object):
         ra1, dec1 = self.wcs.pix2wcs(x0 + 1, y0 + 1)
         self.degPerPixX = _wcs.calcAngSepDeg(ra0, dec0, ra1, dec0)
         self.degPerPixY = _wcs.calcAngSepDeg(ra0, dec0, ra0, dec1)
-        xRadRange = np.array([np.arange(int(np.floor(-shape[1] / 2)), int(shape[1] / 2), dtype=np.float64)
-                              * np.radians(self.degPerPixX)] * shape[0])
-        yRadRange = np.array([np.arange(int(np.floor(-shape[0] / 2)), int(shape[0] / 2), dtype=np.float64)
-                              * np.radians(self.degPerPixY)] * shape[1]).transpose()
-        self.radiansMap = np.sqrt(xRadRange ** 2 + yRadRange ** 2)
+        # a function of the tile shape and the two central pixel scales only: tiles of one geometry (and the nested filter of a
+        # real-space kernel build) share one read-only array
+        key = (tuple(shape), float(self.degPerPixX), float(self.degPerPixY))
+        cached = _RADIANS_MAPS.get(key)
+        if cached is None:
+            xRadRange = np.array([np.arange(int(np.floor(-shape[1] / 2)), int(shape[1] / 2), dtype=np.float64)
+                                  * np.radians(self.degPerPixX)] * shape[0])
+            yRadRange = np.array([np.arange(int(np.floor(-shape[0] / 2)), int(shape[0] / 2), dtype=np.float64)
+                                  * np.radians(self.degPerPixY)] * shape[1]).transpose()
+            cached = np.sqrt(xRadRange ** 2 + yRadRange ** 2)
+            cached.setflags(write=False)
+            if len(_RADIANS_MAPS) >= 8:
+                _RADIANS_MAPS.pop(next(iter(_RADIANS_MAPS)))
+            _RADIANS_MAPS[key] = cached
+        self.radiansMap = cached
 
     def buildAndApply(self):
         raise Exception("Called a base filter class without a buildAndApply() function implemented.")
@@ -462,11 +475,29 @@ class RealSpaceMatchedFilter(MapFilter):
         mask = np.less(arcminRange, kernelMaxArcmin)
         if 'symmetrize' in self.params['noiseParams'].keys() and self.params['noiseParams']['symmetrize'] == True:
             rRadians = np.radians(arcminRange / 60.)
+            # The interpolated profile is zero beyond the last radius below kernelMaxArcmin, so only a window around the tile
+            # centre can hold the peak and the kernel: evaluating it there gives the same kern2d as the reference's full-map
+            # evaluation (filters.py:955-960) for a hundredth of the work.
+            rmap = matchedFilter.radiansMap
+            yc, xc = int(np.argmin(rmap[:, 0])), int(np.argmin(rmap[0, :]))
+            rMax = rRadians[mask].max() if mask.any() else 0.0
+            rows, cols = np.flatnonzero(rmap[:, xc] <= rMax), np.flatnonzero(rmap[yc, :] <= rMax)
+            pad = rIndex + 2
+            wy0, wy1 = max(rows.min() - pad, 0), min(rows.max() + pad + 1, rmap.shape[0])
+            wx0, wx1 = max(cols.min() - pad, 0), min(cols.max() + pad + 1, rmap.shape[1])
             profile2d = []
             for i in range(prof.shape[0]):
                 r2p = interpolate.interp1d(rRadians[mask], prof[i, mask], bounds_error=False, fill_value=0.0)
-                profile2d.append(r2p(matchedFilter.radiansMap))
+                profile2d.append(r2p(rmap[wy0:wy1, wx0:wx1]))
             profile2d = np.array(profile2d)
+            z, y, x = np.where(abs(profile2d) == abs(profile2d).max())
+            y, x = y[0], x[0]
+            if abs(profile2d).max() > 0 and y - rIndex >= 0 and x - rIndex >= 0 and y + rIndex <= profile2d.shape[1] and x + rIndex <= profile2d.shape[2]:
+                windowed = True
+            else:      # degenerate profile or a kernel that leaves the window: the full map, as the reference
+                windowed = False
+                profile2d = np.array([interpolate.interp1d(rRadians[mask], prof[i, mask], bounds_error=False, fill_value=0.0)(rmap)
+                                      for i in range(prof.shape[0])])
         else:
             profile2d = fft.ifft2(matchedFilter.filt).real
             profile2d = fft.fftshift(profile2d)
