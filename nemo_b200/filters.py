@@ -466,6 +466,8 @@ class RealSpaceMatchedFilter(MapFilter):
             matchedFilterClass = globals()[matchedFilterClass]
         matchedFilter = matchedFilterClass(kernelLabel, kernelUnfilteredMapsDictList, self.params, tileName=self.tileName,
                                            diagnosticsDir=None, selFnDir=None)
+        if RADecSection is None and len(matchedFilter.unfilteredMapsDictList) == len(self.unfilteredMapsDictList):
+            matchedFilter._dev = self._stage()      # the noise region is the whole tile: the same arrays, already on the device
         matchedFilter.buildAndApply()
         self.matchedFilter = matchedFilter
 
@@ -531,11 +533,13 @@ class RealSpaceMatchedFilter(MapFilter):
                 raise Exception('need to specify "outputUnits" ("yc" or "uK") in filter params')
             signalMaps.append(signalMap)
         signalMaps = np.array(signalMaps)
-        filteredSignal = self.applyFilter(signalMaps, calcFRelWeights=True)
+        # applyFilter(signalMaps, calcFRelWeights=True) followed by .max() (filters.py:1029-1035), with the maximum, its position
+        # and the per-frequency values there found on the device: a few numbers come back instead of F + 1 maps
+        peak = self._filteredSignalPeak(signalMaps)
         if self.params['outputUnits'] == 'yc':
-            self.signalNorm = y0 / filteredSignal.max()
+            self.signalNorm = y0 / peak
         else:
-            self.signalNorm = 1.0 / filteredSignal.max()
+            self.signalNorm = 1.0 / peak
 
         if self.filterFileName is not None:
             header = {'SIGNORM': self.signalNorm, 'APP_RA': self.applyRACentre, 'APP_DEC': self.applyDecCentre}
@@ -569,13 +573,16 @@ class RealSpaceMatchedFilter(MapFilter):
             self.loadFilter()
 
         # Apply the kernel to the *raw* tile (filters.py:1106-1110)
-        raw = []
+        raw, staged = [], True
         for mapDict in self.unfilteredMapsDictList:
             if hasattr(mapDict, 'loadTile'):
                 raw.append(mapDict.loadTile('mapFileName', tileName=self.tileName))
+                staged = False
             else:
+                staged = staged and mapDict.get('rawData') is None
                 raw.append(mapDict['rawData'] if mapDict.get('rawData') is not None else mapDict['data'])
-        rawT = ops.to_device(np.array(raw)[None])
+        # in-memory tiles without a separate raw map: what was staged IS the raw tile
+        rawT = dev['data'] if staged else ops.to_device(np.array(raw)[None])
         normT = ops.to_device(np.array([self.signalNorm], dtype=np.float64), ops.torch.float64)
         filteredMap = self._applyOnDevice(rawT, normT, dev['psMask'])
 
@@ -613,6 +620,25 @@ class RealSpaceMatchedFilter(MapFilter):
             cubeT = ops.gauss_filter(cubeT.contiguous(), sy, sx, subtract=True)
         kernT = ops.to_device(self.kern2d, ops.torch.float64)
         return ops.conv2d(cubeT.contiguous(), kernT, norm=normT, mask=psMask, wantPlanes=wantPlanes)
+
+    def _filteredSignalPeak(self, signalMaps):
+        """max of the filtered signal templates (signalNorm still 1) and, as applyFilter(..., calcFRelWeights=True) does, the
+        relative weight of every frequency plane at that pixel (filters.py:1204-1212)."""
+        ops = self.ops
+        cubeT = device.asTensor(signalMaps, ops)
+        if cubeT.dim() == 3:
+            cubeT = cubeT.unsqueeze(0)
+        normT = ops.to_device(np.array([self.signalNorm], dtype=np.float64), ops.torch.float64)
+        out, planes = self._applyOnDevice(cubeT, normT, None, wantPlanes=True)
+        _, argmaxIdx, maxVal, _ = ops.template_norm(out.contiguous(), 0, 0.0, 0.0, 1.0)
+        idx = int(device.toHost(argmaxIdx)[0])
+        vals = device.toHost(planes[0].reshape(planes.shape[1], -1)[:, idx].contiguous())
+        peak = float(device.toHost(maxVal)[0])
+        self.fRelWeights = {}
+        totalSignal = vals.sum()
+        for v, mapDict in zip(vals, self.unfilteredMapsDictList):
+            self.fRelWeights[mapDict['obsFreqGHz']] = v / totalSignal
+        return peak
 
     def applyFilter(self, mapDataToFilter, calcFRelWeights=False):
         """Applies the kernel to a cube [F, H, W] (filters.py:1172-1218).  Returns a numpy array."""
