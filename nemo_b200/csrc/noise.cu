@@ -1212,19 +1212,21 @@ __global__ void __launch_bounds__(256) edge_rows_kernel(const T* __restrict__ ma
         local += z;
         s_pre[x + 1] = local;  // local inclusive, offset added below
     }
-    s_part[threadIdx.x] = local;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int i = 0; i < (int)blockDim.x; ++i) {
-            const int t = s_part[i];
-            s_part[i] = run;
-            run += t;
-        }
-        s_pre[0] = 0;
+    // exclusive scan of the per-thread counts over the block: shuffles inside a warp, the warp totals through shared memory (a
+    // single thread walking all 256 partial counts cost more than the loads of the row)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
     }
+    if (lane == 31) s_part[wid] = inc;
+    if (threadIdx.x == 0) s_pre[0] = 0;
     __syncthreads();
-    const int offv = s_part[threadIdx.x];
+    int base = 0;
+    for (int w = 0; w < wid; ++w) base += s_part[w];
+    const int offv = base + inc - local;
     for (int x = b0; x < b1; ++x) s_pre[x + 1] += offv;
     __syncthreads();
     const int lo = -(trim / 2), hi = trim - 1 - trim / 2;
@@ -1239,7 +1241,8 @@ __global__ void __launch_bounds__(256) edge_rows_kernel(const T* __restrict__ ma
     for (int x = threadIdx.x; x < W; x += blockDim.x) {
         const int a = x + lo, b = x + hi;
         int cnt;
-        if (a >= 0) cnt = ext(b + 1) - ext(a);
+        if (a >= 0 && b < W) cnt = s_pre[b + 1] - s_pre[a];       // window inside the row: no reflection, no divisions
+        else if (a >= 0) cnt = ext(b + 1) - ext(a);
         else if (b < 0) cnt = ext(-a) - ext(-b - 1);     // position -k mirrors position k - 1
         else cnt = ext(-a) + ext(b + 1);
         out[x] = cnt > 0 ? 1 : 0;
