@@ -1265,6 +1265,17 @@ __global__ void __launch_bounds__(128) edge_cols_final_kernel(T* map, T* rms, co
                                                               T* sn, unsigned char* __restrict__ maskOut, PaintArgs pa, const Chunks ch) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int ys = blockIdx.y * EC_SEG, img = blockIdx.z;
+    // candidate cell rows of every row of this segment: the same for all columns, so found once per block (the search divides)
+    __shared__ short s_iLo[EC_SEG], s_iHi[EC_SEG];
+    if constexpr (PAINT) {
+        for (int r = threadIdx.x; r < EC_SEG; r += blockDim.x) {
+            int a = 0, b = 0;
+            if (ys + r < H) paint_axis_range(ys + r, ch.y, pa.ny, pa.ov, H, a, b);
+            s_iLo[r] = (short)a;
+            s_iHi[r] = (short)b;
+        }
+        __syncthreads();
+    }
     if (x >= W) return;
     const size_t ib = (size_t)img * H * W, tb = (size_t)(img / S) * H * W;
     const unsigned char* ra = rowAny + ib;
@@ -1317,8 +1328,7 @@ __global__ void __launch_bounds__(128) edge_cols_final_kernel(T* map, T* rms, co
             T r0;
             if constexpr (PAINT) {
                 const double w = (double)wv[u];
-                int iLo, iHi;
-                paint_axis_range(y, ch.y, pa.ny, pa.ov, H, iLo, iHi);
+                const int iLo = s_iLo[y - ys], iHi = s_iHi[y - ys];
                 if (iHi == cacheI && w >= cacheLo && w < cacheHi) {
                     r0 = (T)cacheVal;
                 } else {
