@@ -2,22 +2,27 @@
 """
 bench.py -- throughput of the per-tile filter -> noise/S-N -> detect -> photometry hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload dr5|ptsrc]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): a 4096 x 4096 synthetic 148 GHz map in 16 tiles of 1024 x 1024 per GPU,
-BeamMatchedFilter (noiseGridArcmin 40, numNoiseBins 8, uK), S/N > 4 detection, ring removal, spline photometry
-(bench_workloads.pointSourceConfig).  One step = one pass of the whole path over the rank's 16 tiles.  Tiles are
-independent, so with N ranks every rank filters its own 16 tiles (weak scaling) and the only collective is the
-catalog / noise-table gather at the end of the end-to-end step.
+Workload (default, BASELINE.json configs[3]): an ACT-DR5-scale cluster search -- 280 tiles of 840 x 1440 pixels at 149.6 + 97.8
+GHz, the 16 Arnaud_M*_z* matched-filter scales of the reference's examples/ACT-DR5-clusters/DR5ClusterSearch.yml with photFilter
+Arnaud_M2e14_z0p4, S/N > 4 detection, ring removal, spline photometry (bench_workloads.dr5Config).  Tiles are sharded over the
+GPUs: 35 tiles per GPU (280 at 8 GPUs), weak scaling.  One step = one pass of the whole path over the rank's 35 tiles x 16
+scales.  Tiles are independent, so there is no collective on the data path; the end-to-end step ends with the catalog /
+noise-table gathers.  `--workload ptsrc` runs configs[1] (16 tiles of 1024 x 1024, BeamMatchedFilter, last round's bench line).
 
-Metric: filtered+detected Mpix/s per filter scale = tiles * H * W * S / step time (whole job, all ranks).
+Metric: filtered+detected Mpix/s per filter scale = tiles * H * W * S / step time: every (pixel, scale) pair that was filtered
+and searched counts once (whole job, all ranks).
   value : inputs resident in HBM when the timed region starts (CUDA events, max over ranks)
   e2e   : pipelines.filterMapsAndMakeCatalogs from pinned HOST buffers to the host catalog, copies inside the timed region
+  e2e_from_pageable : the same with the numpy -> pinned staging copy of every tile inside the timed region as well
   roofline     : the kernel with the largest share of the step, algorithmic bytes / its CUDA-event time vs measured HBM peak
   cpu_baseline : the numpy/scipy oracle (the reference's arithmetic) on a bounded sample of the same tiles, on the host cores
 
---impl reference times that CPU path alone (all host cores, one tile per worker process per step).
+--impl reference times that CPU path alone on all host cores: one tile per worker process per step and, for the 16-scale
+workload, the photFilter plus one further scale per step (the reference shares nothing between scales, so its cost per scale
+is the same for every scale; 16 scales would take a minute per step).
 """
 
 import argparse
@@ -33,29 +38,51 @@ if ROOT not in sys.path:
 
 METRIC = "filtered+detected Mpix/s per filter scale"
 UNIT = "Mpix/s"
-SHAPE = (1024, 1024)
-TILES_PER_GPU = 16
+
+WORKLOADS = {
+    'dr5': {'shape': (840, 1440), 'tiles': 35, 'freqs': 2, 'scales': 16, 'cpu_scales': 2, 'tiles_per_batch': 8,
+            'name': "configs[3]: ACT-DR5-scale cluster search, 840x1440 tiles at 149.6+97.8 GHz, 16 Arnaud_M*_z* filter scales "
+                    "(ArnaudModelMatchedFilter, photFilter Arnaud_M2e14_z0p4), S/N>4 detection; 35 tiles per GPU (280 tiles at 8 GPUs)"},
+    'ptsrc': {'shape': (1024, 1024), 'tiles': 16, 'freqs': 1, 'scales': 1, 'cpu_scales': 1, 'tiles_per_batch': 16,
+              'name': "configs[1]: BeamMatchedFilter + S/N>4 detection on a 4096x4096 148 GHz map, 16 tiles of 1024x1024 per GPU"},
+}
+
+
+def makeWorkload(kind, numTiles, firstIndex):
+    import bench_workloads
+    if kind == 'dr5':
+        return bench_workloads.dr5Config(numTiles=numTiles, firstIndex=firstIndex)
+    return bench_workloads.pointSourceConfig(numTiles=numTiles, shape=WORKLOADS[kind]['shape'], firstIndex=firstIndex)
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU baseline (the oracle): one tile per worker process
-def _cpuTile(index):
-    """Worker: regenerates tile `index` (same seed as the GPU arm) and runs the reference arithmetic on it."""
+# CPU arm (the oracle): one tile per worker process
+def _cpuTile(job):
+    """Worker: regenerates tile `index` (same seed as the GPU arm) and runs the reference arithmetic on it for the filters
+    `scaleIdx` of the ordered list, in the reference's loop order (pipelines.py:179-286: photFilter first)."""
+    kind, index, scaleIdx = job
     os.environ.setdefault('OMP_NUM_THREADS', '1')
-    import bench_workloads
     from oracle import filters_ref, photometry_ref
-    parDict, tileMaps, _ = bench_workloads.pointSourceConfig(numTiles=1, shape=SHAPE, firstIndex=index)
+    from nemo_b200 import pipelines
+    parDict, tileMaps, _ = makeWorkload(kind, 1, index)
+    parDict = dict(pipelines.SimpleConfig.DEFAULTS, **parDict)
     name, mapDicts = next(iter(tileMaps.items()))
-    f = parDict['mapFilters'][0]
+    ordered = pipelines._orderedFilters(parDict)
     t0 = time.perf_counter()
-    filtered = filters_ref.filterMaps(mapDicts, {'label': f['label'], 'class': f['class'], 'params': dict(f['params'])}, name)
-    cat = photometry_ref.findObjects(filtered, threshold=parDict['thresholdSigma'], minObjPix=parDict['minObjPix'],
-                                     rejectBorder=parDict['rejectBorder'], findCenterOfMass=parDict['findCenterOfMass'],
-                                     removeRings=parDict['removeRings'], ringThresholdSigma=parDict['ringThresholdSigma'],
-                                     objIdent=parDict['objIdent'], longNames=parDict['longNames'],
-                                     useInterpolator=parDict['useInterpolator'])
-    photometry_ref.measureFluxes(cat, filtered, None, useInterpolator=parDict['useInterpolator'])
-    return time.perf_counter() - t0, len(cat)
+    phot, nObj = None, 0
+    for s in scaleIdx:
+        f = ordered[s]
+        filtered = filters_ref.filterMaps(mapDicts, {'label': f['label'], 'class': f['class'], 'params': dict(f['params'])}, name)
+        if f['label'] == parDict.get('photFilter'):
+            phot = {'SNMap': filtered['SNMap'], 'data': filtered['data']}
+        cat = photometry_ref.findObjects(filtered, threshold=parDict['thresholdSigma'], minObjPix=parDict['minObjPix'],
+                                         rejectBorder=parDict['rejectBorder'], findCenterOfMass=parDict['findCenterOfMass'],
+                                         removeRings=parDict['removeRings'], ringThresholdSigma=parDict['ringThresholdSigma'],
+                                         objIdent=parDict['objIdent'], longNames=parDict['longNames'],
+                                         useInterpolator=parDict['useInterpolator'])
+        photometry_ref.measureFluxes(cat, filtered, None, photFilteredMapDict=phot, useInterpolator=parDict['useInterpolator'])
+        nObj += len(cat)
+    return time.perf_counter() - t0, nObj
 
 
 def _cpuPool(cores):
@@ -66,62 +93,75 @@ def _cpuPool(cores):
     return mp.get_context('spawn').Pool(cores)
 
 
-def cpuBaseline(cores=None, tiles=None, steps=1, warmup=0):
-    """Times the oracle over `tiles` tiles per step spread over `cores` worker processes (the reference's MPI-over-tiles
-    split, startUp.py:390-404).  Tile generation happens inside the workers but outside their timers; the step time
-    is the slowest worker's summed compute time (what an MPI job's wall clock would be)."""
+def cpuBaseline(kind, cores=None, steps=1, warmup=0):
+    """Times the oracle over one tile per worker process per step on `cores` processes (the reference's MPI-over-tiles split,
+    startUp.py:390-404).  Tile generation happens inside the workers but outside their timers; the step time is the slowest
+    worker's compute time (what an MPI job's wall clock would be)."""
+    wl = WORKLOADS[kind]
     cores = cores or os.cpu_count() or 1
-    tiles = tiles or cores
-    pool = _cpuPool(min(cores, tiles))
+    tiles = cores
+    S, nS = wl['scales'], wl['cpu_scales']
+    pool = _cpuPool(cores)
     try:
         times = []
         nObj = 0
         for it in range(warmup + steps):
-            res = pool.map(_cpuTile, [i % TILES_PER_GPU for i in range(tiles)], chunksize=1)
-            # wall of the step: tiles are dealt round-robin to `cores` workers
-            perWorker = [0.0] * min(cores, tiles)
-            for i, (dt, n) in enumerate(res):
-                perWorker[i % len(perWorker)] += dt
+            # the photFilter (index 0 of the ordered list) and the next of the other scales in rotation
+            scaleIdx = [0] + [1 + (it * (nS - 1) + k) % (S - 1) for k in range(nS - 1)] if S > 1 else [0]
+            res = pool.map(_cpuTile, [(kind, i % wl['tiles'], scaleIdx) for i in range(tiles)], chunksize=1)
             if it >= warmup:
-                times.append(max(perWorker))
+                times.append(max(dt for dt, _ in res))
                 nObj = sum(n for _, n in res)
     finally:
         pool.close()
         pool.join()
     tStep = sum(times) / len(times)
-    mpix = tiles * SHAPE[0] * SHAPE[1] / 1e6
-    return {'value': mpix / tStep, 'unit': UNIT, 'cores': min(cores, tiles), 'kind': 'port',
-            'sample': "%d of the workload's 1024x1024 tiles per step, one per worker process, %d step(s); numpy/scipy oracle "
-                      "(np.fft for pixell, vectorised np.linalg.inv), %.2f s per step, %d objects" % (tiles, steps, tStep, nObj)}, tStep
+    H, W = wl['shape']
+    mpix = tiles * H * W * nS / 1e6
+    sample = ("%d of the workload's %dx%d tiles per step, one per worker process, %d of its %d filter scales per tile (photFilter + "
+              "%d in rotation; the reference shares nothing between scales), %d step(s); numpy/scipy oracle (np.fft for pixell, "
+              "vectorised np.linalg.inv), %.2f s per step, %d objects" % (tiles, H, W, nS, S, nS - 1, steps, tStep, nObj))
+    return {'value': mpix / tStep, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}, tStep
 
 
 # ------------------------------------------------------------------------------------------------------
-def algorithmicBytes(nT, F, S, H, W, E, rings=True):
+def algorithmicBytes(nT, F, S, H, W, E, rings=True, yc=True):
     """Algorithmic HBM bytes per step of every kernel of the batched Fourier path: own inputs read once + own outputs
-    written once (SURVEY.md 8d / DESIGN.md), E = bytes per real (8 for f64, 4 for f32), complex = 2E."""
+    written once (SURVEY.md 8d / DESIGN.md), E = bytes per real (8 for f64, 4 for f32), complex = 2E.  Keyed by the names the
+    library's event timers report; kernels that serve several passes are charged the sum of those passes."""
     N, Nc = H * W, H * (W // 2 + 1)
     P = F * (F + 1) // 2
     nOut = nT * S
     nPass = 2 if rings else 1
+    nTpl = S * F
+    rowFwd = N * E + Nc * 2 * E               # per image: real rows in, half spectrum out
+    rowInv = Nc * 2 * E + N * E
+    col = 2 * Nc * 2 * E                      # half spectrum in and out
+    fwdImgs = nT * F + nTpl + (2 * nTpl if yc else 0) + nOut         # maps, unit templates, (windowed) norm templates, window undo
+    plainColImgs = nT * F + nTpl + (nTpl if yc else 0)
+    windowColImgs = nOut + (nTpl if yc else 0)
+    applyBytes = 2 * nOut * (F * Nc * E + Nc * 2 * E) + (nT * F + nTpl) * Nc * 2 * E     # filters in, product out; spectra once
+    invBytes = 2 * nOut * rowInv + nOut * N + nOut * rowInv + nOut * N * E + (nTpl * rowInv if yc else 0)   # + mask, + zero reference
     b = {}
-    imgsFwd = nT * F + S * F + nOut          # data, unit templates, pixel-window undo
-    b['rfft_rows_kernel'] = imgsFwd * (N * E + Nc * 2 * E)
-    b['fft_cols_kernel'] = (nT * F + S * F) * 2 * Nc * 2 * E
-    b['xpower_smooth_x_kernel'] = nT * (F * Nc * 2 * E + P * N * 8)
-    b['smooth_y_f64_kernel'] = nT * P * N * 8 * 2
-    b['build_filter_kernel'] = nT * P * N * 8 + nOut * F * Nc * 2 * E + nOut * F * Nc * E
-    b['fft_cols_apply_kernel'] = 2 * nOut * (F * Nc * 2 * E + F * Nc * E + Nc * 2 * E)     # templates + maps
-    b['irfft_rows_kernel'] = nOut * (Nc * 2 * E + N * E) + nOut * (Nc * 2 * E + N * E + N) + nOut * (Nc * 2 * E + 2 * N * E)
+    for rows in ('rfft_rows_kernel', 'bs_rows_fwd_kernel', 'sfft_rows_fwd_kernel'):
+        b[rows] = fwdImgs * rowFwd
+    for rows in ('irfft_rows_kernel', 'bs_rows_inv_kernel', 'sfft_rows_inv_kernel'):
+        b[rows] = invBytes
+    b['fft_cols_kernel'] = plainColImgs * col
+    b['fft_cols_window_kernel'] = windowColImgs * col
+    b['fft_cols_apply_kernel'] = applyBytes
+    b['bs_cols_kernel'] = b['sfft_cols_kernel'] = plainColImgs * col + windowColImgs * col + applyBytes
+    b['xpower_smooth_x_kernel'] = b['xpower_smooth_x_rb_kernel'] = nT * (F * Nc * 2 * E + P * N * 8)
+    b['smooth_y_f64_kernel'] = b['smooth_y_rb_kernel'] = nT * P * N * 8 * 2
+    b['build_filter_kernel'] = nT * P * N * 8 + nTpl * Nc * 2 * E + nOut * F * Nc * E
     b['template_argmax_partial_kernel'] = nOut * N * E
-    b['cell_rms_onchip_kernel'] = nOut * 2 * N * E
-    b['cell_rms_hybrid_kernel'] = nOut * 2 * N * E
-    b['cell_rms_stream_kernel'] = nOut * 2 * N * E
-    b['paint_rms_kernel'] = nOut * 2 * N * E
+    b['plane_values_partial_kernel'] = nOut * F * Nc * E + nTpl * Nc * 2 * E
+    for k6 in ('cell_rms_onchip_kernel', 'cell_rms_hybrid_kernel', 'cell_rms_stream_kernel', 'cell_rms_kernel', 'paint_rms_kernel'):
+        b[k6] = nOut * N * E + nT * N * E      # every image's map; the median weights of its tile
     b['edge_rows_kernel'] = nOut * (N * E + 2 * N)
     b['edge_cols_final_kernel'] = nOut * (2 * N * E + 3 * N + 3 * N * E + N)
     b['edge_cols_final_paint_kernel'] = nOut * (2 * N * E + 3 * N + 3 * N * E + N)   # map, median weights, masks in; data, S/N, RMS, mask out
-    b['fft_cols_window_kernel'] = nOut * 2 * Nc * 2 * E
-    b['detect_scan_kernel'] = nPass * nOut * (N * E + 4 * N)      # S/N read, zeroed label image written; the rest is sparse
+    b['detect_scan_kernel'] = b['detect_scan_multi_kernel'] = nOut * (N * E)         # S/N read once for both thresholds; the rest is sparse
     return b
 
 
@@ -188,18 +228,28 @@ class ClockSampler(object):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+L2_NOTE = 'GPU arm: inputs and intermediates of one batch (> 1 GB) exceed the 126 MB L2, no explicit flush; CPU arm: not applicable'
+
+
+def workloadConfig(kind, args=None):
+    """The `config` object both arms print (same `workload` string, so the driver can tell they ran the same thing)."""
+    wl = WORKLOADS[kind]
+    return {'workload': wl['name'], 'tile': list(wl['shape']), 'freqs': wl['freqs'], 'scales': wl['scales'],
+            'tiles_per_gpu': args.tiles if args is not None and args.tiles else wl['tiles']}
+
+
 # ------------------------------------------------------------------------------------------------------
 def runReference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    base, tStep = cpuBaseline(cores=cores, tiles=min(cores, TILES_PER_GPU), steps=args.steps, warmup=args.warmup)
+    base, tStep = cpuBaseline(args.workload, cores=cores, steps=args.steps, warmup=args.warmup)
+    cfg = workloadConfig(args.workload, args)
+    cfg['l2'] = L2_NOTE
     line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': tStep * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': 'configs[1]: BeamMatchedFilter + S/N>4 detection, 1024x1024 tiles of a 4096x4096 148 GHz map',
-                       'tile': list(SHAPE), 'freqs': 1, 'scales': 1, 'tiles_per_step': min(cores, TILES_PER_GPU)},
-            'cpu_baseline': base,
+            'dtype': 'f64', 'data': 'synthetic', 'config': cfg, 'cpu_baseline': base,
+            'run': {'cpu_tiles_per_step': cores, 'cpu_scales_per_step': WORKLOADS[args.workload]['cpu_scales']},
             'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -208,33 +258,40 @@ def runReference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='dr5', choices=sorted(WORKLOADS))
     ap.add_argument('--precision', default='f64', choices=['f64', 'f32'])
-    ap.add_argument('--tiles', type=int, default=TILES_PER_GPU, help='tiles per GPU')
-    ap.add_argument('--tiles-per-batch', type=int, default=16)
-    ap.add_argument('--e2e-tiles-per-batch', default='4', help='batch sizes of the end-to-end arm (uploads overlap compute): one size, or a list that is mirrored at the end (2,4 -> 2,4,4,...,4,2)')
+    ap.add_argument('--tiles', type=int, default=None, help='tiles per GPU (default: the workload\'s)')
+    ap.add_argument('--tiles-per-batch', type=int, default=None)
+    ap.add_argument('--e2e-tiles-per-batch', default=None, help='batch sizes of the end-to-end arm (uploads overlap compute): one size, or a list that is mirrored at the end (2,4 -> 2,4,4,...,4,2)')
     ap.add_argument('--pipeline-depth', type=int, default=2, help='batches in flight on the device behind the one whose catalogs the host assembles (device-resident arm)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-f32-host', action='store_true', help='skip the extra end-to-end arm with float32 host tiles')
+    ap.add_argument('--no-extra-e2e', action='store_true', help='skip the extra end-to-end arms (pageable host tiles; float32 host tiles)')
     ap.add_argument('--kernel-table', default=None, help='write the per-kernel roofline table to this file')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     localRank = int(os.environ.get('LOCAL_RANK', '0'))
+    wl = WORKLOADS[args.workload]
+    if args.tiles is None:
+        args.tiles = wl['tiles']
     if args.impl == 'reference':
         runReference(args, rank)
         return
     if args.warmup < 3:
         args.warmup = 3
-    e2eBatch = [int(v) for v in str(args.e2e_tiles_per_batch).split(',')]
-    e2eBatch = e2eBatch[0] if len(e2eBatch) == 1 else e2eBatch
+    tilesPerBatch = args.tiles_per_batch or wl['tiles_per_batch']
+    if args.e2e_tiles_per_batch is None:
+        e2eBatch = [2, 4, tilesPerBatch] if args.workload == 'dr5' else 4
+    else:
+        e2eBatch = [int(v) for v in str(args.e2e_tiles_per_batch).split(',')]
+        e2eBatch = e2eBatch[0] if len(e2eBatch) == 1 else e2eBatch
 
     import numpy as np
     import torch
-    import bench_workloads
     from nemo_b200 import _lib, device, pipelines, distributed
 
     if not torch.cuda.is_available():
@@ -255,22 +312,26 @@ def main():
     def maxOverRanks(v):
         return comm.maxOverRanks(v) if comm is not None else v
 
-    H, W = SHAPE
+    H, W = wl['shape']
     nT = args.tiles
-    parDict, tileMaps, truth = bench_workloads.pointSourceConfig(numTiles=nT, shape=SHAPE, firstIndex=rank * nT)
+    parDict, tileMaps, truth = makeWorkload(args.workload, nT, rank * nT)
     config = pipelines.SimpleConfig(parDict, tileMaps, rank=0, size=1)     # every rank owns all of its own tiles
     config.rank = rank
-    config.allTileNames = ['%d_%d' % (i // 4, i % 4) for i in range(world * nT)]    # the same list on every rank
+    import bench_workloads
+    if args.workload == 'dr5':
+        config.allTileNames = [bench_workloads.dr5TileName(i) for i in range(world * nT)]    # the same list on every rank
+    else:
+        config.allTileNames = ['%d_%d' % (i // 4, i % 4) for i in range(world * nT)]
     parDict = config.parDict
     ops = device.getOps(args.precision)
-    F, S = 1, len(parDict['mapFilters'])
+    F, S = wl['freqs'], len(parDict['mapFilters'])
     E = 8 if args.precision == 'f64' else 4
     filtersList = pipelines._orderedFilters(parDict)
+    outputUnits = filtersList[0]['params']['outputUnits']
 
     # ---- device-resident arm ---------------------------------------------------------------------------
-    batches = pipelines.stageTiles(config, args.tiles_per_batch, args.precision)
-    templates = pipelines.FilterSetTemplates(ops, filtersList, batches[0].mapDicts[0])
-    config._templates = templates
+    batches = pipelines.stageTiles(config, tilesPerBatch, args.precision)
+    templatesList = [pipelines.templatesFor(config, ops, filtersList, b) for b in batches]
     for b in batches:
         b.upload()
     torch.cuda.synchronize()
@@ -280,12 +341,13 @@ def main():
     def countObjects(res):
         return sum(len(v['catalog']) for v in res[0].values())
 
-    def deviceSteps(n):
-        pipe = pipelines.BatchPipeline(ops, filtersList, templates, parDict, undoPixelWindow=True, depth=args.pipeline_depth)
+    def deviceSteps(n, serialize=False):
+        pipe = pipelines.BatchPipeline(ops, filtersList, templatesList[0], parDict, undoPixelWindow=True, depth=args.pipeline_depth,
+                                       serialize=serialize)
         nObj = 0
         for _ in range(n):
-            for b in batches:
-                out = pipe.submit(b, upload=False)
+            for b, tpl in zip(batches, templatesList):
+                out = pipe.submit(b, upload=False, templates=tpl)
                 if out is not None:
                     nObj += countObjects(out)
         nObj += sum(countObjects(out) for out in pipe.flush())
@@ -304,11 +366,12 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = (_lib.launchCount() - launches0) // args.steps
-    # per-kernel CUDA-event times: the same steps once more, one at a time (no overlap between consecutive steps, which
-    # would stretch the individual kernel times), with the library's event timers on
+    # per-kernel CUDA-event times: the same steps once more with the library's event timers on, every batch waited for before
+    # the next is queued (kernels of batches running side by side on the pipeline's streams would stretch each other's times)
+    profSteps = min(args.steps, 5)
     _lib.profEnable(True)
-    for _ in range(args.steps):
-        deviceSteps(1)
+    for _ in range(profSteps):
+        deviceSteps(1, serialize=True)
     prof = _lib.profReport()
     _lib.profEnable(False)
     msStep = maxOverRanks(e0.elapsed_time(e1) / args.steps)
@@ -318,43 +381,41 @@ def main():
     # ---- end-to-end arm: pinned host buffers -> host catalog through the public driver ------------------------
     for b in batches:
         b.dev = None
-    for _ in range(2):
-        cat = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=e2eBatch, precision=args.precision, comm=comm)
-    barrier()
-    device.TRAFFIC['h2d'] = device.TRAFFIC['d2h'] = 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cat = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=e2eBatch, precision=args.precision, comm=comm)
-    torch.cuda.synchronize()
-    tE2E = maxOverRanks((time.perf_counter() - t0) / args.steps)
-    barrier()
-    e2e = {'value': mpixJob / tE2E, 'unit': UNIT, 'h2d_bytes_per_step': device.TRAFFIC['h2d'] // args.steps,
-           'd2h_bytes_per_step': device.TRAFFIC['d2h'] // args.steps, 'ms_per_step': tE2E * 1e3, 'catalog_rows': len(cat)}
 
-    # the same arm with the tiles held as float32 on the host, the format survey maps have on disk (FITS BITPIX -32): staged and
-    # uploaded as float32, widened to float64 on the device, everything after that unchanged.  Reported beside `e2e`, which stays
-    # the float64-host number.
-    e2eF32 = None
-    if args.precision == 'f64' and not args.no_f32_host:
-        tileMaps32 = {name: [dict(m, data=np.asarray(m['data'], dtype=np.float32), weights=np.asarray(m['weights'], dtype=np.float32))
-                             for m in md] for name, md in tileMaps.items()}
-        config32 = pipelines.SimpleConfig(parDict, tileMaps32, rank=0, size=1)
-        config32.rank = rank
-        config32.allTileNames = config.allTileNames
-        config32._templates = templates
+    def e2eArm(cfg, restage=False, steps=args.steps):
         for _ in range(2):
-            cat32 = pipelines.filterMapsAndMakeCatalogs(config32, verbose=False, tilesPerBatch=e2eBatch, precision=args.precision, comm=comm)
+            cat = pipelines.filterMapsAndMakeCatalogs(cfg, verbose=False, tilesPerBatch=e2eBatch, precision=args.precision, comm=comm,
+                                                      restage=restage, restageKeys=('data', 'weights'))
         barrier()
         device.TRAFFIC['h2d'] = device.TRAFFIC['d2h'] = 0
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            cat32 = pipelines.filterMapsAndMakeCatalogs(config32, verbose=False, tilesPerBatch=e2eBatch, precision=args.precision, comm=comm)
+        for _ in range(steps):
+            cat = pipelines.filterMapsAndMakeCatalogs(cfg, verbose=False, tilesPerBatch=e2eBatch, precision=args.precision, comm=comm,
+                                                      restage=restage, restageKeys=('data', 'weights'))
         torch.cuda.synchronize()
-        t32 = maxOverRanks((time.perf_counter() - t0) / args.steps)
+        t = maxOverRanks((time.perf_counter() - t0) / steps)
         barrier()
-        e2eF32 = {'value': mpixJob / t32, 'unit': UNIT, 'h2d_bytes_per_step': device.TRAFFIC['h2d'] // args.steps,
-                  'd2h_bytes_per_step': device.TRAFFIC['d2h'] // args.steps, 'ms_per_step': t32 * 1e3, 'catalog_rows': len(cat32),
-                  'note': 'host tiles float32 (as on disk), widened to float64 on the device; compute unchanged'}
+        return {'value': mpixJob / t, 'unit': UNIT, 'h2d_bytes_per_step': device.TRAFFIC['h2d'] // steps,
+                'd2h_bytes_per_step': device.TRAFFIC['d2h'] // steps, 'ms_per_step': t * 1e3, 'catalog_rows': len(cat)}
+
+    e2e = e2eArm(config)
+    e2ePageable = e2eF32 = None
+    if not args.no_extra_e2e:
+        # the numpy -> pinned staging copy of every tile inside the timed region too (restage: each batch's maps and weights are
+        # copied into its pinned buffers right before it is submitted, under the device work of the batch before it)
+        e2ePageable = e2eArm(config, restage=True, steps=max(2, args.steps // 2))
+        e2ePageable['note'] = 'tiles start as pageable numpy arrays: staging copy into pinned buffers inside the timed region'
+        if args.precision == 'f64':
+            # tiles held as float32 on the host, the format survey maps have on disk (FITS BITPIX -32): staged and uploaded as
+            # float32, widened to float64 on the device, everything after that unchanged
+            tileMaps32 = {name: [dict(m, data=np.asarray(m['data'], dtype=np.float32), weights=np.asarray(m['weights'], dtype=np.float32))
+                                 for m in md] for name, md in tileMaps.items()}
+            config32 = pipelines.SimpleConfig(parDict, tileMaps32, rank=0, size=1)
+            config32.rank = rank
+            config32.allTileNames = config.allTileNames
+            config32._templates = config._templates
+            e2eF32 = e2eArm(config32, steps=max(2, args.steps // 2))
+            e2eF32['note'] = 'host tiles float32 (as on disk), widened to float64 on the device; compute unchanged'
 
     if comm is not None:
         torch.distributed.destroy_process_group()
@@ -368,12 +429,12 @@ def main():
         peaks = json.load(open(peakPath))
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peakSrc = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
-    algo = algorithmicBytes(nT, F, S, H, W, E, rings=parDict['removeRings'])
+    algo = algorithmicBytes(nT, F, S, H, W, E, rings=parDict['removeRings'], yc=(outputUnits == 'yc'))
     table = []
-    totalKernelMs = sum(ms for _, ms in prof.values()) / args.steps
+    totalKernelMs = sum(ms for _, ms in prof.values()) / profSteps
     for name, (cnt, ms) in prof.items():
-        msK = ms / args.steps
-        row = {'kernel': name, 'launches_per_step': cnt / args.steps, 'ms_per_step': msK, 'share': msK / totalKernelMs}
+        msK = ms / profSteps
+        row = {'kernel': name, 'launches_per_step': cnt / profSteps, 'ms_per_step': msK, 'share': msK / totalKernelMs}
         if name in algo:
             row['algorithmic_bytes_per_step'] = algo[name]
             row['achieved_gbs'] = algo[name] / (msK * 1e-3) / 1e9
@@ -385,14 +446,18 @@ def main():
     trafficPath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if top is not None and os.path.exists(trafficPath):
         tj = json.load(open(trafficPath))
-        ent = tj.get(args.precision, {}).get(top['kernel'])
+        ent = tj.get(args.workload, {}).get(args.precision, {}).get(top['kernel'])
         if ent is not None:
-            traffic, trafficSrc = ent['dram_bytes_per_launch'], ent['source']
+            # ncu captured one launch of some batch size: scale to the bytes one average launch of this run moves
+            traffic = ent['dram_bytes_per_launch'] * (top['algorithmic_bytes_per_step'] / top['launches_per_step']) / ent['algorithmic_bytes_per_launch']
+            trafficSrc = ent['source']
     roofline = None
     if top is not None:
         lp = top['launches_per_step']
         roofline = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
-                    'frac': top['frac'], 'traffic': traffic, 'traffic_source': trafficSrc, 'peak_source': peakSrc, 'timed_in': 'same run, %d further steps executed one at a time with per-kernel CUDA events' % args.steps, 'share_of_step_kernel_time': top['share'],
+                    'frac': top['frac'], 'traffic': traffic, 'traffic_source': trafficSrc, 'peak_source': peakSrc,
+                    'timed_in': 'same run, %d further steps with per-kernel CUDA events, one batch at a time' % profSteps,
+                    'share_of_step_kernel_time': top['share'],
                     'bytes_per_launch': top['algorithmic_bytes_per_step'] / lp, 'ms_per_launch': top['ms_per_step'] / lp,
                     'launches_per_step': lp}
     bpp = endToEndBytesPerPixel(F, S, E, rings=parDict['removeRings'])
@@ -401,23 +466,21 @@ def main():
     stepRoofline['kernel_ms_per_step'] = totalKernelMs
     if args.kernel_table:
         with open(args.kernel_table, 'w') as fh:
-            json.dump({'precision': args.precision, 'tiles': nT, 'shape': SHAPE, 'F': F, 'S': S, 'ms_per_step': msStep,
+            json.dump({'workload': args.workload, 'precision': args.precision, 'tiles': nT, 'shape': [H, W], 'F': F, 'S': S, 'ms_per_step': msStep,
                        'kernel_ms_per_step': totalKernelMs, 'peak_gbs': peak, 'kernels': table, 'step': stepRoofline}, fh, indent=1)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        cpu, _ = cpuBaseline(cores=cores, tiles=min(cores, TILES_PER_GPU), steps=1, warmup=0)
+        cpu, _ = cpuBaseline(args.workload, cores=os.cpu_count() or 1, steps=1, warmup=0)
 
+    cfg = workloadConfig(args.workload, args)
+    cfg['l2'] = L2_NOTE
+    run = {'tiles_per_batch': tilesPerBatch, 'e2e_tiles_per_batch': e2eBatch, 'objects_per_step': nObj}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': msStep, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': args.precision, 'data': 'synthetic',
-            'config': {'workload': 'configs[1]: BeamMatchedFilter + S/N>4 detection on a 4096x4096 148 GHz map in 16 tiles of 1024x1024 per GPU',
-                       'tiles_per_gpu': nT, 'tile': list(SHAPE), 'freqs': F, 'scales': S, 'tiles_per_batch': args.tiles_per_batch, 'e2e_tiles_per_batch': e2eBatch,
-                       'l2': 'inputs and intermediates of one step (> 1 GB) exceed the 126 MB L2; no explicit flush',
-                       'objects_per_step': nObj},
-            'clocks': clocks, 'e2e': e2e, 'e2e_f32_host': e2eF32, 'gpu_launches': int(launches), 'roofline': roofline, 'step_roofline': stepRoofline,
-            'cpu_baseline': cpu}
+            'dtype': args.precision, 'data': 'synthetic', 'config': cfg, 'run': run,
+            'clocks': clocks, 'e2e': e2e, 'e2e_from_pageable': e2ePageable, 'e2e_f32_host': e2eF32, 'gpu_launches': int(launches),
+            'roofline': roofline, 'step_roofline': stepRoofline, 'cpu_baseline': cpu}
     print(json.dumps(line))
 
 

@@ -50,6 +50,11 @@ def noiseGrid(shape, noiseParams, pixDeg):
     yChunks = np.linspace(0, shape[0], int(numYChunks + 1), dtype=int)
     xChunks = np.linspace(0, shape[1], int(numXChunks + 1), dtype=int)
     numBins = noiseParams['numNoiseBins'] if 'numNoiseBins' in noiseParams.keys() else 1
+    # the kernels take the percentile list np.arange(0, 100, 100 / numBins) (filters.py:450) to have numBins entries; floating-point
+    # steps give one more for a few values (29, 31, 58, ...), where the reference ends up with numBins + 1 bins
+    if len(np.arange(0, 100, 100. / numBins)) != int(numBins):
+        raise Exception("numNoiseBins = %d: np.arange(0, 100, 100 / numBins) has %d entries, so the reference makes %d weight bins; "
+                        "use a neighbouring value" % (numBins, len(np.arange(0, 100, 100. / numBins)), len(np.arange(0, 100, 100. / numBins))))
     return yChunks, xChunks, overlapPix, int(numBins), estimator
 
 

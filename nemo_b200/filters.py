@@ -64,6 +64,30 @@ def filterMaps(unfilteredMapsDictList, filterParams, tileName, diagnosticsDir='.
 
 
 # -------------------------------------------------------------------------------------------------------------
+_SOLID_ANGLES = {}
+
+
+def beamSolidAngle_nsr(mapDict):
+    """Beam solid angle (nsr) of a map dictionary as MapFilter.__init__ finds it (filters.py:180-196): the 'solidAngle_nsr' key,
+    else the 'solid angle = ... nsr' line of the beam profile file, else 0 (no Jy fluxes).  Used by the class API and by the
+    batched driver, so that both report the same fluxJy."""
+    if 'solidAngle_nsr' in mapDict.keys():
+        return mapDict['solidAngle_nsr']
+    beamFileName = mapDict.get('beamFileName')
+    if not isinstance(beamFileName, str):
+        return 0.0
+    key = (beamFileName, os.path.getmtime(beamFileName))
+    if key not in _SOLID_ANGLES:
+        solidAngle_nsr = 0.0
+        with open(beamFileName, "r") as inFile:
+            for line in inFile.readlines():
+                if line.find("solid angle") != -1:
+                    solidAngle_nsr = float(line.split("=")[1].split()[0])
+                    break
+        _SOLID_ANGLES[key] = solidAngle_nsr
+    return _SOLID_ANGLES[key]
+
+
 def _maskToU8(m, shape):
     if m is None:
         return np.ones(shape, dtype=np.uint8)
@@ -108,18 +132,7 @@ class MapFilter(object):
 
         self.beamSolidAnglesDict = {}
         for mapDict in self.unfilteredMapsDictList:
-            if 'solidAngle_nsr' in mapDict.keys():
-                solidAngle_nsr = mapDict['solidAngle_nsr']
-            elif isinstance(mapDict.get('beamFileName'), str):
-                solidAngle_nsr = 0.0
-                with open(mapDict['beamFileName'], "r") as inFile:
-                    for line in inFile.readlines():
-                        if line.find("solid angle") != -1:
-                            solidAngle_nsr = float(line.split("=")[1].split()[0])
-                            break
-            else:
-                solidAngle_nsr = 0.0
-            self.beamSolidAnglesDict[mapDict['obsFreqGHz']] = solidAngle_nsr
+            self.beamSolidAnglesDict[mapDict['obsFreqGHz']] = beamSolidAngle_nsr(mapDict)
 
         self.apodPix = 20
         for mapDict in self.unfilteredMapsDictList:
@@ -700,12 +713,26 @@ class ArnaudModelFilter(MapFilter):
 
     def makeSignalTemplateMap(self, beamFileName, amplitude=None):
         gnfw = self.params.get('GNFWParams', 'default')
+        # the reference paints the cluster at wcs.getCentreWCSCoords() (filters.py:1244-1250), which is where the normalisation
+        # spline is evaluated (:655-662); that is pixel (W/2, H/2) of radiansMap for a WCS whose centre is an integer pixel and
+        # half a pixel away from it for e.g. astWCS's (NAXIS/2 in FITS counting) convention
+        cRADeg, cDecDeg = self.wcs.getCentreWCSCoords()
+        cx, cy = self.wcs.wcs2pix(cRADeg, cDecDeg)
         key = ('arnaud', self.params['z'], self.params['M500MSun'], repr(gnfw), tuple(self.shape), self.degPerPixX, self.degPerPixY,
-               _beamKey(beamFileName), amplitude)
-        return _cachedTemplate(key, lambda: signals.makeArnaudModelSignalMap(self.params['z'], self.params['M500MSun'],
-                                                                             np.degrees(self.radiansMap), self.wcs, beam=beamFileName,
-                                                                             GNFWParams=gnfw, amplitude=amplitude,
-                                                                             convolveWithBeam=True))
+               float(cx), float(cy), _beamKey(beamFileName), amplitude)
+
+        def make():
+            beamDegreesMap = np.degrees(self.radiansMap)
+            if float(cx) == int(self.shape[1] / 2) and float(cy) == int(self.shape[0] / 2):
+                degreesMap = beamDegreesMap
+            else:
+                xDeg = (np.arange(self.shape[1], dtype=np.float64) - cx) * self.degPerPixX
+                yDeg = (np.arange(self.shape[0], dtype=np.float64) - cy) * self.degPerPixY
+                degreesMap = np.sqrt(xDeg[None, :] ** 2 + yDeg[:, None] ** 2)
+            return signals.makeArnaudModelSignalMap(self.params['z'], self.params['M500MSun'], degreesMap, self.wcs, beam=beamFileName,
+                                                    GNFWParams=gnfw, amplitude=amplitude, convolveWithBeam=True,
+                                                    beamDegreesMap=beamDegreesMap)
+        return _cachedTemplate(key, make)
 
 
 class BattagliaModelFilter(MapFilter):

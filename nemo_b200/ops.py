@@ -465,5 +465,9 @@ class Ops(object):
 
     def scale_mask(self, maps, scale=1.0, norm=None, mask=None):
         """maps * scale * norm[b] * mask[b] via a 1x1 convolution (keeps all arithmetic in the library)."""
-        one = self.to_device(np.ones((1, 1, 1)), self.torch.float64)
+        # the 1 x 1 kernel is made once per Ops on the device: a host-to-device copy from pageable memory is not allowed while a
+        # stream is being captured into a CUDA graph (the batched bckSub path runs under capture)
+        one = getattr(self, '_unitKernel', None)
+        if one is None:
+            one = self._unitKernel = self.torch.ones((1, 1, 1), dtype=self.torch.float64, device=self.device)
         return self.conv2d(maps.unsqueeze(1).contiguous(), one, scale=scale, norm=norm, mask=mask)

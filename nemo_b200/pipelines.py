@@ -44,6 +44,25 @@ class SimpleConfig(object):
 
 
 # ------------------------------------------------------------------------------------------------------
+def tileGeometry(mapDicts):
+    """What the filters, templates and noise grid of a tile depend on besides its pixels: (H, W, degPerPixX, degPerPixY,
+    pixel size, centre pixel x, y).  The reference rebuilds radiansMap, the pixel scales and the signal templates for every tile
+    (filters.py:214-239, 617, 642-646); degPerPixX goes with cos(dec), so CAR tiles at different declinations have different
+    filters.  Tiles with equal geometry share templates; a batch never mixes geometries."""
+    wcs = mapDicts[0]['wcs']
+    H, W = mapDicts[0]['data'].shape
+    x0, y0 = int(W / 2), int(H / 2)
+    ra0, dec0 = wcs.pix2wcs(x0, y0)
+    ra1, dec1 = wcs.pix2wcs(x0 + 1, y0 + 1)
+    cRADeg, cDecDeg = wcs.getCentreWCSCoords()
+    cx, cy = wcs.wcs2pix(cRADeg, cDecDeg)
+    # rounded so that tiles of one declination row, whose pixel scales and centres agree to the last few bits only (their RA
+    # offsets round differently), land in one group: 1e-12 relative on the scales, 1e-6 pixel on the centre
+    sig = lambda v: float('%.12e' % v)
+    return (int(H), int(W), sig(_wcs.calcAngSepDeg(ra0, dec0, ra1, dec0)), sig(_wcs.calcAngSepDeg(ra0, dec0, ra0, dec1)),
+            sig(wcs.getPixelSizeDeg()), round(float(cx), 6), round(float(cy), 6))
+
+
 class TileBatch(object):
     """Maps of nT tiles resident on the device: data / weights [nT, F, H, W], masks u8 [nT, H, W], median weights."""
 
@@ -56,6 +75,11 @@ class TileBatch(object):
         F = len(self.mapDicts[0])
         H, W = self.mapDicts[0][0]['data'].shape
         self.nT, self.F, self.H, self.W = nT, F, H, W
+        self.geometry = tileGeometry(self.mapDicts[0])
+        for md in self.mapDicts[1:]:
+            if tuple(md[0]['data'].shape) == (H, W) and tileGeometry(md) != self.geometry:
+                raise Exception("tiles of one batch need the same geometry (shape, pixel scales at the tile centre): "
+                                "stageTiles groups tiles by geometry")
         # maps that arrive as float32 (the on-disk format: FITS BITPIX -32) are staged and uploaded as float32 and widened on
         # the device -- exact, and half the host-to-device bytes; anything else is staged in the compute type
         def stageType(key):
@@ -124,7 +148,11 @@ class FilterSetTemplates(object):
     """Host-made signal templates of a list of Fourier filters for one tile geometry, uploaded once and reused for
     every tile with the same shape and pixel scale (template maps are inputs to the hot path)."""
 
+    _serial = 0
+
     def __init__(self, ops, filtersList, mapDicts, tileName='PRIMARY'):
+        FilterSetTemplates._serial += 1
+        self.serial = FilterSetTemplates._serial      # never reused, unlike id(): CUDA-graph caches key on it
         self.filtersList = filtersList
         self.S = len(filtersList)
         unit, norm = [], []
@@ -147,8 +175,10 @@ class FilterSetTemplates(object):
             unit.append([obj.makeSignalTemplateMap(m['beamFileName']) for m in mapDicts])
             amps = engine.normAmplitudes(mapDicts, f['params'])
             if amps is not None:
-                norm.append([obj.makeSignalTemplateMap(m['beamFileName'], amplitude=a) for m, a in zip(mapDicts, amps)])
-        self.geometry = (obj.shape, obj.degPerPixX, obj.degPerPixY)
+                # makeSignalTemplateMap(beam, amplitude=a) scales the 1-D profile by a before painting and convolving, all linear:
+                # a times the unit template to rounding, at none of the painting cost
+                norm.append([u * a for u, a in zip(unit[-1], amps)])
+        self.geometry = tileGeometry(mapDicts)
         self.unit = ops.to_device(np.array(unit))
         self.norm = ops.to_device(np.array(norm)) if len(norm) > 0 else None
         wcs = mapDicts[0]['wcs']
@@ -163,6 +193,27 @@ def _sameNoiseSetup(filtersList):
     return len(set(key(f) for f in filtersList)) == 1
 
 
+def _filtersKey(filtersList):
+    return repr([(f['label'], f['class'] if isinstance(f['class'], str) else f['class'].__name__,
+                  repr(sorted(f['params'].items(), key=lambda kv: kv[0]))) for f in filtersList])
+
+
+def _beamsKey(mapDicts):
+    return tuple((m['obsFreqGHz'], m.get('units'), _filters._beamKey(m['beamFileName'])) for m in mapDicts)
+
+
+def templatesFor(config, ops, filtersList, batch):
+    """The FilterSetTemplates of a batch, built once per (tile geometry, beams, filter set, precision) and kept on `config`."""
+    cache = getattr(config, '_templates', None)
+    if not isinstance(cache, dict):
+        cache = config._templates = {}
+    key = (batch.geometry, _beamsKey(batch.mapDicts[0]), _filtersKey(filtersList), ops.precision)
+    hit = cache.get(key)
+    if hit is None:
+        hit = cache[key] = FilterSetTemplates(ops, filtersList, batch.mapDicts[0], tileName=batch.tileNames[0])
+    return hit
+
+
 def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=True, invertMap=False, cache=None,
                    useCachedRMSMap=False, rmsTables=False):
     """Launches, without waiting for any of it, the device work of one batch: filtering of every tile at every scale of
@@ -175,6 +226,8 @@ def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=
     source-injection path does (pipelines.py:216-232)."""
     if not _sameNoiseSetup(filtersList):
         raise Exception("filters of one batch need identical noiseParams / edgeTrimArcmin / bckSub settings")
+    if getattr(batch, 'geometry', None) is not None and templates.geometry != batch.geometry:
+        raise Exception("signal templates were made for another tile geometry %s than this batch's %s" % (templates.geometry, batch.geometry))
     dev = batch.dev if batch.dev is not None else batch.upload()
     nT, F, H, W, S = batch.nT, batch.F, batch.H, batch.W, len(filtersList)
     Wc = W // 2 + 1
@@ -242,7 +295,19 @@ def finishTileBatch(job, measureFluxes=True, keepMaps=False):
     the device maps when keepMaps)."""
     catalogDict = detectAndMeasure(job['ops'], job['batch'], job['filtersList'], job['data'], job['SNMap'], job['mapUnits'],
                                    job['parDict'], measureFluxes=measureFluxes, invertMap=job['invertMap'], detectJob=job['detectJob'])
-    extras = {'noiseTable': job['noiseTable'], 'noiseEdges': job['noiseEdges'], 'signalNorm': job['signalNorm'], 'fRel': job['fRel']}
+    # small per-image results go to the host here, on the job's stream and before its pipeline slot is reused: with CUDA graphs the
+    # device tensors are the graph's static outputs, which the batch submitted three submits later overwrites
+    def host(v):
+        if v is None:
+            return None
+        if isinstance(v, tuple):
+            return tuple(host(x) for x in v)
+        return device.toHost(v) if hasattr(v, 'device') and not isinstance(v, np.ndarray) else v
+    extras = {'noiseTable': host(job['noiseTable']), 'noiseEdges': host(job['noiseEdges'])}
+    if keepMaps:      # filter caches stay on the device (no graphs in that mode)
+        extras.update({'signalNorm': job['signalNorm'], 'fRel': job['fRel']})
+    else:
+        extras.update({'signalNorm': host(job['signalNorm']), 'fRel': host(job['fRel'])})
     if job.get('rmsTabJob') is not None:
         from . import completeness
         extras['RMSTabs'] = completeness.finishRMSTables(job['rmsTabJob'])      # [(y0RMS, areaDeg2)] per image
@@ -265,6 +330,7 @@ class _BatchView(object):
         self.dev = dev
         self.nT, self.F, self.H, self.W = batch.nT, batch.F, batch.H, batch.W
         self.wcsList, self.mapDicts, self.tileNames, self.flagMasks = batch.wcsList, batch.mapDicts, batch.tileNames, batch.flagMasks
+        self.geometry = getattr(batch, 'geometry', None)
 
 
 class BatchPipeline(object):
@@ -275,8 +341,9 @@ class BatchPipeline(object):
     nothing is shared between batches except the read-only templates."""
 
     def __init__(self, ops, filtersList, templates, parDict, undoPixelWindow=True, measureFluxes=True, invertMap=False,
-                 keepMaps=False, useCachedRMSMap=False, useGraphs=True, depth=2, rmsTables=False):
+                 keepMaps=False, useCachedRMSMap=False, useGraphs=True, depth=2, rmsTables=False, serialize=False):
         self.rmsTables = rmsTables
+        self.serialize = serialize      # wait for every batch's device work before queueing the next (per-kernel timing runs)
         self.ops, self.filtersList, self.templates, self.parDict = ops, filtersList, templates, parDict
         # the ~40 launches of a batch are captured once per (slot, shape, input buffers) into a CUDA graph and replayed:
         # the host then spends microseconds, not a millisecond, queueing a batch.  Graphs live on the Ops object.
@@ -310,10 +377,11 @@ class BatchPipeline(object):
             job['batch'].dev = None
         return out
 
-    def _graphEntry(self, slot, st, batch, upload, cache=None):
+    def _graphEntry(self, slot, st, batch, upload, cache=None, templates=None):
         """(graph, job template, static inputs, launches per replay) for this slot and batch shape, captured on first use."""
         from . import _lib
         ops, torch = self.ops, self.ops.torch
+        templates = self.templates if templates is None else templates
         if upload:
             ident = ('staged', str(batch.host['data'].dtype), str(batch.host['weights'].dtype))
         else:
@@ -322,9 +390,9 @@ class BatchPipeline(object):
         cacheIdent = None
         if cache is not None:
             cacheIdent = (self.useCachedRMSMap,) + tuple(int(cache[k].data_ptr()) for k in ('filtH', 'signalNorm', 'RMSMap') if cache.get(k) is not None)
-        key = (slot, ident, cacheIdent, batch.nT, batch.F, batch.H, batch.W, ops.precision, id(self.templates), self.undoPixelWindow, self.invertMap, self.rmsTables,
+        key = (slot, ident, cacheIdent, batch.nT, batch.F, batch.H, batch.W, ops.precision, templates.serial, self.undoPixelWindow, self.invertMap, self.rmsTables,
                repr(sorted((k, repr(v)) for k, v in self.parDict.items() if k != 'mapFilters')),
-               repr([(f['label'], repr(sorted(f['params'].items(), key=lambda kv: kv[0]))) for f in self.filtersList]))
+               _filtersKey(self.filtersList))
         entry = self.graphs.get(key)
         if entry is not None:
             return entry
@@ -342,7 +410,7 @@ class BatchPipeline(object):
                 widenStaged(ops, view.dev) if needWeights else widenStaged(ops, view.dev, keys=('data',))
                 view.dev['wmed'] = ops.median_weights(view.dev['weights']) if needWeights else None
             # one eager run first: twiddle tables, kernel attributes and other lazy set-up must not happen under capture
-            startTileBatch(ops, view, self.filtersList, self.templates, self.parDict, undoPixelWindow=self.undoPixelWindow,
+            startTileBatch(ops, view, self.filtersList, templates, self.parDict, undoPixelWindow=self.undoPixelWindow,
                            invertMap=self.invertMap, rmsTables=self.rmsTables, cache=cache, useCachedRMSMap=self.useCachedRMSMap)
             st.synchronize()
             graph = torch.cuda.CUDAGraph()
@@ -352,15 +420,15 @@ class BatchPipeline(object):
                     view.dev.update(static)          # the widening of float32-staged maps is part of the captured work
                     widenStaged(ops, view.dev) if needWeights else widenStaged(ops, view.dev, keys=('data',))
                     view.dev['wmed'] = ops.median_weights(view.dev['weights']) if needWeights else None
-                job = startTileBatch(ops, view, self.filtersList, self.templates, self.parDict,
+                job = startTileBatch(ops, view, self.filtersList, templates, self.parDict,
                                      undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap, rmsTables=self.rmsTables,
                                      cache=cache, useCachedRMSMap=self.useCachedRMSMap)
             nLaunch = _lib.launchCount() - n0
-        entry = (graph, job, static, nLaunch)
+        entry = (graph, job, static, nLaunch, templates)      # the templates the graph reads stay alive with it
         self.graphs[key] = entry
         return entry
 
-    def submit(self, batch, upload=True, cache=None):
+    def submit(self, batch, upload=True, cache=None, templates=None):
         """Queues the device work of `batch`; returns the (catalogDict, extras) of the oldest queued batch once more than
         `depth` - 1 others are in flight behind it, else None."""
         from . import _lib
@@ -374,7 +442,7 @@ class BatchPipeline(object):
         photInList = self.parDict.get('photFilter') is not None and any(f['label'] == self.parDict['photFilter'] for f in self.filtersList)
         skipKeys = ('weights', 'rowArea') if (cache is not None and self.useCachedRMSMap and photInList and not self.rmsTables) else ()
         if useGraph:
-            graph, template, static, nLaunch = self._graphEntry(slot, st, batch, upload, cache)
+            graph, template, static, nLaunch, _ = self._graphEntry(slot, st, batch, upload, cache, templates)
             with torch.cuda.stream(st):
                 if upload:
                     for k, v in batch.host.items():
@@ -390,9 +458,11 @@ class BatchPipeline(object):
             with torch.cuda.stream(st):
                 if upload:
                     batch.upload()
-                job = startTileBatch(self.ops, batch, self.filtersList, self.templates, self.parDict,
+                job = startTileBatch(self.ops, batch, self.filtersList, self.templates if templates is None else templates, self.parDict,
                                      undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap, cache=cache,
                                      useCachedRMSMap=self.useCachedRMSMap, rmsTables=self.rmsTables)
+        if self.serialize:
+            st.synchronize()
         self.pending.append((job, st, upload))
         # a slot's buffers (graph outputs, static inputs) are reused by the batch submitted len(streams) calls later, so at
         # most `depth` jobs may stay unread
@@ -409,15 +479,23 @@ class BatchPipeline(object):
 
 
 def processBatches(ops, batches, filtersList, templates, parDict, upload=True, undoPixelWindow=True, measureFluxes=True,
-                   invertMap=False, keepMaps=False, caches=None, useCachedRMSMap=False, useGraphs=True, depth=2, rmsTables=False):
+                   invertMap=False, keepMaps=False, caches=None, useCachedRMSMap=False, useGraphs=True, depth=2, rmsTables=False,
+                   beforeSubmit=None):
     """Runs several tile batches through a BatchPipeline; returns the list of (catalogDict, extras), one per batch, in order.
-    caches: per-batch filter / RMS caches (see startTileBatch), or None."""
-    pipe = BatchPipeline(ops, filtersList, templates, parDict, undoPixelWindow=undoPixelWindow, measureFluxes=measureFluxes,
+    caches: per-batch filter / RMS caches (see startTileBatch), or None.  templates: one FilterSetTemplates, or one per batch.
+    beforeSubmit(batch): host work to do right before a batch is queued (re-staging its maps); it runs while the device
+    works on the batches queued before it."""
+    pipe = BatchPipeline(ops, filtersList, templates[0] if isinstance(templates, (list, tuple)) else templates, parDict,
+                         undoPixelWindow=undoPixelWindow, measureFluxes=measureFluxes,
                          invertMap=invertMap, keepMaps=keepMaps, useCachedRMSMap=useCachedRMSMap,
                          useGraphs=useGraphs and not keepMaps, depth=depth, rmsTables=rmsTables)
+    perBatch = isinstance(templates, (list, tuple))
     results = []
     for i, batch in enumerate(batches):
-        out = pipe.submit(batch, upload=upload and batch.dev is None, cache=caches[i] if caches is not None else None)
+        if beforeSubmit is not None:
+            beforeSubmit(batch)
+        out = pipe.submit(batch, upload=upload and batch.dev is None, cache=caches[i] if caches is not None else None,
+                          templates=templates[i] if perBatch else None)
         if out is not None:
             results.append(out)
     results.extend(pipe.flush())
@@ -492,7 +570,7 @@ def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measu
                         cols[prefix + 'deltaT_c'] = v
                         cols[prefix + 'err_deltaT_c'] = v / snr
                         # Jy fluxes need the beam solid angle and frequency of the image's tile (photometry.py:336-339)
-                        nsr = np.array([batch.mapDicts[o // S][0].get('solidAngle_nsr', 0.0) for o in range(nT * S)])[ownArr]
+                        nsr = np.array([_filters.beamSolidAngle_nsr(batch.mapDicts[o // S][0]) for o in range(nT * S)], dtype=np.float64)[ownArr]
                         freq = np.array([batch.mapDicts[o // S][0]['obsFreqGHz'] for o in range(nT * S)], dtype=np.float64)[ownArr]
                         flux = photometry.deltaTToJyPerSr(v, freq) * nsr * 1.e-9
                         errFlux = photometry.deltaTToJyPerSr(cols[prefix + 'err_deltaT_c'], freq) * nsr * 1.e-9
@@ -573,10 +651,15 @@ def stageTiles(config, tilesPerBatch=8, precision=None):
     """Copies this rank's tiles into pinned host staging buffers, `tilesPerBatch` tiles per batch, and keeps them on
     `config` so that repeated runs (source-injection iterations, benchmarks) start from pinned memory."""
     ops = device.getOps(precision)
-    tileNames = list(config.tileNames)
-    config._staged = {'tilesPerBatch': _batchKey(tilesPerBatch), 'precision': ops.precision,
-                      'batches': [TileBatch(ops, tileNames[i:j], config.tileMaps)
-                                  for i, j in _batchBounds(len(tileNames), tilesPerBatch)]}
+    # tiles of one geometry (shape and pixel scales at the tile centre: CAR tiles of one declination row) form the batches;
+    # groups keep the order in which their first tile appears
+    groups = {}
+    for name in config.tileNames:
+        groups.setdefault((tileGeometry(config.tileMaps[name]), len(config.tileMaps[name])), []).append(name)
+    batches = []
+    for names in groups.values():
+        batches += [TileBatch(ops, names[i:j], config.tileMaps) for i, j in _batchBounds(len(names), tilesPerBatch)]
+    config._staged = {'tilesPerBatch': _batchKey(tilesPerBatch), 'precision': ops.precision, 'batches': batches}
     return config._staged['batches']
 
 
@@ -623,7 +706,7 @@ def _batchBounds(numTiles, tilesPerBatch):
 
 def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=False, measureFluxes=True, invertMap=False,
                               verbose=True, tilesPerBatch=8, precision=None, comm=None, cacheFilters=False, restage=False,
-                              makeRMSTables=False):
+                              makeRMSTables=False, restageKeys=('data',)):
     """Runs the map filtering and catalog construction steps for this rank's tiles and returns the optimal catalog
     (highest S/N detection across filter scales), gathered over ranks when `comm` (a
     ``nemo_b200.distributed.Comm``) is given -- pipelines.py:33-109, 112-354.
@@ -631,8 +714,9 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     cacheFilters=True keeps every batch's filters, normalisations and RMS maps on the device (``config._cache``); a later
     call with useCachedFilters=True (and useCachedRMSMap=True) then only applies them to whatever the map dictionaries hold
     now -- the reference's source-injection loop (maps.py:2093), where the caches are FITS files on disk.  restage=True
-    re-reads the 'data' arrays of the map dictionaries into the pinned staging buffers first (they were edited in place or
-    replaced since the tiles were staged).
+    re-reads the `restageKeys` arrays ('data'; 'weights') of the map dictionaries into the pinned staging buffers (they were
+    edited in place or replaced since the tiles were staged), batch by batch, each right before it is queued so that the copy
+    runs under the device work of the batches before it.
 
     Only Fourier-space matched filters with a common noise set-up are batched here; use ``filters.filterMaps`` +
     ``photometry.findObjects`` directly for anything else.
@@ -665,13 +749,9 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
         batches = stageTiles(config, tilesPerBatch, precision)
     else:
         batches = staged['batches']
-        if restage:
-            for b in batches:
-                b.refresh(config.tileMaps)
-    templates = getattr(config, '_templates', None)
-    if templates is None:
-        templates = FilterSetTemplates(ops, filtersList, batches[0].mapDicts[0], tileName=batches[0].tileNames[0])
-        config._templates = templates
+    beforeSubmit = (lambda b: b.refresh(config.tileMaps, keys=restageKeys)) if restage else None
+    templatesList = [templatesFor(config, ops, filtersList, b) for b in batches]
+    templates = templatesList[0]
     if verbose:
         for batch in batches:
             print(">>> [rank = %d] Making filtered maps - tiles %s" % (config.rank, batch.tileNames))
@@ -682,9 +762,10 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
             raise Exception("no cached filters for these tile batches: run filterMapsAndMakeCatalogs(config, cacheFilters=True) first")
     # with a cached RMS map the pixel window is undone after the S/N map has been made (pipelines.py:171-173, 216-232); the
     # batched path always makes the S/N map before undoing the window, so the same flag serves both cases
-    results = processBatches(ops, batches, filtersList, templates, parDict, upload=True,
+    results = processBatches(ops, batches, filtersList, templatesList, parDict, upload=True,
                              undoPixelWindow=parDict.get('undoPixelWindow', True), measureFluxes=measureFluxes, invertMap=invertMap,
-                             keepMaps=cacheFilters, caches=caches, useCachedRMSMap=useCachedRMSMap, rmsTables=makeRMSTables)
+                             keepMaps=cacheFilters, caches=caches, useCachedRMSMap=useCachedRMSMap, rmsTables=makeRMSTables,
+                             beforeSubmit=beforeSubmit)
     if cacheFilters:
         config._cache = [{'filtH': ex['filtH'], 'signalNorm': ex['signalNorm'], 'RMSMap': ex['RMSMap'], 'fRel': ex['fRel']}
                          for _, ex in results]
@@ -696,7 +777,7 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
             RMSTabs[filtersList[o % len(filtersList)]['label'] + "#" + names[o // len(filtersList)]] = tab
         if extras['noiseTable'] is None:
             continue
-        tab = device.toHost(extras['noiseTable'])
+        tab = extras['noiseTable']
         for o in range(tab.shape[0]):
             noiseTables[filtersList[o % len(filtersList)]['label'] + "#" + names[o // len(filtersList)]] = tab[o]
     optimalCatalog = catalogs.makeOptimalCatalog(catalogDict, constraintsList=parDict.get('catalogCuts', []))

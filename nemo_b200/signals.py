@@ -143,9 +143,10 @@ def makeArnaudModelProfile(z, M500, GNFWParams='default'):
 
 
 def makeArnaudModelSignalMap(z, M500, degreesMap, wcs, beam=None, GNFWParams='default', amplitude=None,
-                             maxSizeDeg=15.0, convolveWithBeam=True):
+                             maxSizeDeg=15.0, convolveWithBeam=True, beamDegreesMap=None):
     """Arnaud-model cluster template centred where degreesMap is zero, optionally convolved with the beam on the
-    periodic tile grid."""
+    periodic tile grid.  beamDegreesMap: distance map whose zero is the integer pixel (H/2, W/2), for the beam kernel (so that the
+    convolution does not move the cluster) when degreesMap is centred elsewhere; default degreesMap."""
     tckP = makeArnaudModelProfile(z, M500, GNFWParams=GNFWParams)['tckP']
     rDeg = np.linspace(0.0, maxSizeDeg, 5000)
     profile1d = interpolate.splev(rDeg, tckP, ext=1)
@@ -156,7 +157,7 @@ def makeArnaudModelSignalMap(z, M500, degreesMap, wcs, beam=None, GNFWParams='de
     if convolveWithBeam:
         if beam is None:
             raise Exception("No beam supplied.")
-        beamMap = makeBeamModelSignalMap(degreesMap, wcs, beam)
+        beamMap = makeBeamModelSignalMap(degreesMap if beamDegreesMap is None else beamDegreesMap, wcs, beam)
         beamMap = beamMap / beamMap.sum()
         signalMap = np.fft.ifft2(np.fft.fft2(signalMap) * np.fft.fft2(np.fft.ifftshift(beamMap))).real
     return signalMap

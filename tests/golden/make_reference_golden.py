@@ -256,6 +256,48 @@ def runMisc(refFilters):
             'pixAreaConstantAlongRows': np.array(np.array_equal(np.asarray(area)[:, :1] * np.ones((1, inp['shape'][1])), area))}
 
 
+def runBigCase(refFilters, refPhotometry, name, tmpDir):
+    """A full-size case (big_cases.BIG_CASES) through the reference's filterMaps / getObjectPositions / findObjects / getSNRValues
+    / measureFluxes in its loop order (nemo/pipelines.py:179-286), stored in compact form."""
+    from oracle import filters_ref
+    import copy
+    import big_cases
+    case = big_cases.BIG_CASES[name]
+    mapDicts = case['tile']()
+    res, phot = {}, None
+    for i, f in enumerate(case['filters']):
+        f = copy.deepcopy(f)
+        oracleObj = getattr(filters_ref, f['class'])(f['label'], mapDicts, copy.deepcopy(f['params']), tileName='T0')
+
+        class RefFilter(refFilters.MatchedFilter):
+            def makeSignalTemplateMap(self, beamFileName, amplitude=None, _o=oracleObj):
+                return _o.makeSignalTemplateMap(beamFileName, amplitude=amplitude)
+        refFilters.RefFilter = RefFilter
+        refMaps = []
+        for m in mapDicts:
+            d = RefMapDict(m)
+            d['wcs'].AWCS = None
+            refMaps.append(d)
+        os.makedirs(os.path.join(tmpDir, 'T0'), exist_ok=True)
+        out, obj = refFilters.filterMaps(refMaps, {'label': f['label'], 'class': 'RefFilter', 'params': copy.deepcopy(f['params'])}, 'T0',
+                                         diagnosticsDir=tmpDir, selFnDir=tmpDir, verbose=False, undoPixelWindow=True, returnFilter=True)
+        if f['label'] == case['photFilter']:
+            phot = {'SNMap': out['SNMap'], 'data': out['data']}
+        D = big_cases.DETECT
+        seg = refPhotometry.getObjectPositions(out['SNMap'], D['threshold'], findCenterOfMass=True)[3]
+        cat = refPhotometry.findObjects(out, threshold=D['threshold'], minObjPix=D['minObjPix'], rejectBorder=D['rejectBorder'],
+                                        findCenterOfMass=D['findCenterOfMass'], removeRings=D['removeRings'],
+                                        ringThresholdSigma=D['ringThresholdSigma'], useInterpolator=D['useInterpolator'], verbose=False)
+        if phot is not None:
+            refPhotometry.getSNRValues(cat, phot['SNMap'], out['wcs'], prefix='fixed_', useInterpolator=D['useInterpolator'])
+        refPhotometry.measureFluxes(cat, out, tmpDir, photFilteredMapDict=phot, useInterpolator=D['useInterpolator'])
+        res.update(big_cases.compact('s%d_' % i, out['data'], out['SNMap'], out['surveyMask'], seg, obj.signalNorm))
+        res.update(big_cases.catalogColumns('s%d_cat_' % i, cat))
+        if obj.fRelWeights:
+            res['s%d_fRel' % i] = np.array([obj.fRelWeights[k] for k in sorted(obj.fRelWeights.keys())], dtype=np.float64)
+    return res
+
+
 def main():
     import tempfile
     sys.path.insert(0, HERE)
@@ -269,6 +311,12 @@ def main():
         res['filtSample'] = filt[:, ::16, ::16].copy()
         np.savez_compressed(os.path.join(HERE, 'ref_%s.npz' % name), **res)
         print("%s: reference run stored (%d labels above S/N 4, signalNorm %.6g)" % (name, len(res['objIDs']) - 1, float(res['signalNorm'])))
+    import big_cases
+    for name in big_cases.BIG_CASES:
+        res = runBigCase(refFilters, refPhotometry, name, tmpDir)
+        path = os.path.join(HERE, 'ref_big_%s.npz' % name)
+        np.savez_compressed(path, **res)
+        print("%s: reference run stored (%d rows in the first catalog, %.0f kB)" % (name, len(res['s0_cat_RADeg']), os.path.getsize(path) / 1e3))
     misc = runMisc(refFilters)
     misc.update(runPhotFilter(refFilters, refPhotometry, tmpDir))
     np.savez_compressed(os.path.join(HERE, 'ref_misc.npz'), **misc)

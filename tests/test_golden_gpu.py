@@ -153,3 +153,70 @@ def test_phot_filter_flow_matches_reference_run(report):
             continue
         np.testing.assert_allclose(np.asarray(cat[k], dtype=np.float64), ref['phot_' + k], rtol=1e-4, atol=1e-9, err_msg=k)
     report("reference_run_phot_filter", rows=len(cat), max_rel_fixed_SNR=float(np.abs(np.asarray(cat['fixed_SNR'], dtype=float) / ref['phot_fixed_SNR'] - 1).max()))
+
+
+@pytest.mark.parametrize("name", ['arnaud_f148_1024', 'dr5_f150_f098_840x1440'])
+def test_cuda_path_matches_full_size_reference_run(name, report):
+    """BASELINE-size tiles against runs of the reference's own code (ref_big_<case>.npz, compact form, tests/golden/big_cases.py):
+    configs[0] -- one 1024 x 1024 tile, ArnaudModelMatchedFilter -- and one 840 x 1440 two-frequency tile of configs[3] at
+    declination -42.5 (x pixel scale 0.74 of y) with the photFilter flow of nemo/pipelines.py:238-284.  Class API, reference loop
+    order; S/N within 1e-4, masks and labels bit-exact, catalogs identical with positions within 0.01 px."""
+    import copy
+    import big_cases
+    from nemo_b200 import filters, photometry
+    ref = np.load(os.path.join(HERE, 'golden', 'ref_big_' + name + '.npz'))
+    case = big_cases.BIG_CASES[name]
+    mapDicts = case['tile']()
+    D = big_cases.DETECT
+    phot = None
+    for i, f in enumerate(case['filters']):
+        got, obj = filters.filterMaps(mapDicts, copy.deepcopy(f), 'T0', verbose=False, returnFilter=True)
+        if f['label'] == case['photFilter']:
+            phot = {'SNMap': got['SNMap'], 'data': got['data']}
+        seg = photometry.getObjectPositions(got['SNMap'], D['threshold'])[3]
+        cat = photometry.findObjects(got, **D)
+        if phot is not None:
+            photometry.getSNRValues(cat, phot['SNMap'], got['wcs'], prefix='fixed_', useInterpolator=D['useInterpolator'])
+        photometry.measureFluxes(cat, got, None, photFilteredMapDict=phot, useInterpolator=D['useInterpolator'])
+        prefix = 's%d_' % i
+        rec = big_cases.compact(prefix, got['data'], got['SNMap'], got['surveyMask'], seg, obj.signalNorm)
+        big_cases.compareCompact(rec, ref, prefix)
+        assert len(cat) == len(ref[prefix + 'cat_RADeg']) >= 20
+        assert list(cat['name']) == list(ref[prefix + 'cat_name'])
+        pixDeg = mapDicts[0]['wcs'].getPixelSizeDeg()         # the reference's table keeps sky positions, not x / y
+        assert np.abs(np.asarray(cat['RADeg'], dtype=float) - ref[prefix + 'cat_RADeg']).max() < 0.01 * pixDeg
+        assert np.abs(np.asarray(cat['decDeg'], dtype=float) - ref[prefix + 'cat_decDeg']).max() < 0.01 * pixDeg
+        assert np.array_equal(np.asarray(cat['numSigPix'], dtype=float), ref[prefix + 'cat_numSigPix'])
+        for k in [k[len(prefix) + 4:] for k in ref.files if k.startswith(prefix + 'cat_')]:
+            if k not in ('name', 'template', 'tileName', 'RADeg', 'decDeg', 'numSigPix'):
+                np.testing.assert_allclose(np.asarray(cat[k], dtype=np.float64), ref[prefix + 'cat_' + k], rtol=1e-4, atol=1e-9, err_msg=k)
+        if prefix + 'fRel' in ref.files:
+            gotRel = np.array([obj.fRelWeights[k] for k in sorted(obj.fRelWeights.keys())])
+            assert np.abs(gotRel - ref[prefix + 'fRel']).max() < 1e-8
+        report("reference_run_big_%s_%d" % (name, i), maxabs_dSN_sub=float(np.abs(rec[prefix + 'SN_sub'] - ref[prefix + 'SN_sub']).max()), rows=len(cat))
+
+
+def test_batched_driver_matches_full_size_reference_run(report):
+    """The same configs[3] tile through the batched driver (pipelines.filterMapsAndMakeCatalogs: K1-K11 over tile x scale
+    images, CUDA graphs): its per-(tile, scale) catalogs against the reference run's, fixed_ columns included."""
+    import big_cases
+    from nemo_b200 import pipelines
+    name = 'dr5_f150_f098_840x1440'
+    ref = np.load(os.path.join(HERE, 'golden', 'ref_big_' + name + '.npz'))
+    case = big_cases.BIG_CASES[name]
+    parDict = {'mapFilters': case['filters'], 'photFilter': case['photFilter'], 'thresholdSigma': 4.0, 'minObjPix': 1,
+               'findCenterOfMass': True, 'useInterpolator': True, 'rejectBorder': 0}
+    config = pipelines.SimpleConfig(parDict, {'T0': case['tile']()})
+    opt = pipelines.filterMapsAndMakeCatalogs(config, verbose=False)
+    for i, f in enumerate(case['filters']):
+        prefix = 's%d_cat_' % i
+        cat = config.catalogDict[f['label'] + '#T0']['catalog']
+        assert len(cat) == len(ref[prefix + 'RADeg'])
+        assert list(cat['name']) == list(ref[prefix + 'name'])
+        for k in [k[len(prefix):] for k in ref.files if k.startswith(prefix)]:
+            if k in ('name', 'template', 'tileName'):
+                continue
+            tol = dict(rtol=0, atol=0.01 * 0.5 / 60) if k in ('RADeg', 'decDeg') else dict(rtol=1e-4, atol=1e-9)
+            np.testing.assert_allclose(np.asarray(cat[k], dtype=np.float64), ref[prefix + k], err_msg=k, **tol)
+    assert len(opt) >= 20
+    report("batched_reference_run_big", optimal=len(opt))

@@ -284,3 +284,29 @@ def test_phot_filter_flow_matches_reference_run():
             assert [str(v) for v in col] == list(ref['phot_' + k]), k
         else:
             assert np.array_equal(np.array(col, dtype=np.float64), ref['phot_' + k]), k
+
+
+@pytest.mark.parametrize("name", ['arnaud_f148_1024', 'dr5_f150_f098_840x1440'])
+def test_oracle_matches_full_size_reference_run(name):
+    """BASELINE-size tiles: configs[0] (1024 x 1024, ArnaudModelMatchedFilter) and one 840 x 1440 two-frequency tile of configs[3]
+    with the photFilter flow.  ref_big_<case>.npz holds, in compact form (tests/golden/big_cases.py), what the REFERENCE's own
+    filters.py / photometry.py computed for them; the oracle must reproduce it bit for bit, catalogs included."""
+    sys.path.insert(0, os.path.join(HERE, 'golden'))
+    import big_cases
+    ref = np.load(os.path.join(HERE, 'golden', 'ref_big_' + name + '.npz'))
+    _, out = big_cases.runOracle(name)
+    for i, f in enumerate(big_cases.BIG_CASES[name]['filters']):
+        prefix = 's%d_' % i
+        big_cases.compareCompact(out, ref, prefix, exact=True)
+        catKeys = [k for k in ref.files if k.startswith(prefix + 'cat_')]
+        assert len(ref[prefix + 'cat_RADeg']) >= 20
+        assert prefix + 'cat_y_c' in catKeys and (i == 0 or prefix + 'cat_fixed_SNR' in catKeys or big_cases.BIG_CASES[name]['photFilter'] is None)
+        for k in catKeys:
+            if k.endswith('cat_template') or k.endswith('cat_tileName'):
+                continue
+            if ref[k].dtype.kind in 'US':
+                assert list(ref[k]) == list(out[k]), k
+            else:
+                assert np.array_equal(ref[k], out[k]), k
+        if prefix + 'fRel' in ref.files:
+            assert np.array_equal(ref[prefix + 'fRel'], out[prefix + 'fRel'])

@@ -568,3 +568,157 @@ def test_percentile_rms_estimator_end_to_end(report):
         _compareCatalogs(config.catalogDict[f['label'] + "#" + name]['catalog'], refCat, ['SNR', 'deltaT_c'])
         nObj += len(refCat)
     assert nObj >= 4
+
+
+def test_dr5_tile_all_sixteen_scales_against_oracle(report):
+    """BASELINE configs[3] at full size: one 840 x 1440 two-frequency tile through the batched driver at all 16 Arnaud_M*_z*
+    scales with photFilter Arnaud_M2e14_z0p4, every per-scale catalog against the oracle in the reference's loop order."""
+    import bench_workloads
+    from nemo_b200 import pipelines
+    parDict, tileMaps, _ = bench_workloads.dr5Config(numTiles=1, firstIndex=57)       # third declination row
+    config = pipelines.SimpleConfig(parDict, tileMaps)
+    opt = pipelines.filterMapsAndMakeCatalogs(config, verbose=False)
+    ordered = pipelines._orderedFilters(config.parDict)
+    assert len(ordered) == 16 and ordered[0]['label'] == 'Arnaud_M2e14_z0p4'
+    nObj = 0
+    for tileName, md in tileMaps.items():
+        phot = None
+        for f in ordered:
+            ref = filters_ref.filterMaps(md, _copyFilter(f), tileName)
+            if f['label'] == parDict['photFilter']:
+                phot = {'SNMap': ref['SNMap'], 'data': ref['data']}
+            refCat = photometry_ref.findObjects(ref, **dict(DETECT, objIdent='ACT-CL'))
+            photometry_ref.measureFluxes(refCat, ref, None, photFilteredMapDict=phot)
+            _compareCatalogs(config.catalogDict[f['label'] + "#" + tileName]['catalog'], refCat,
+                             ['SNR', 'y_c', 'err_y_c', 'fixed_SNR', 'fixed_y_c', 'deltaT_c'])
+            nObj += len(refCat)
+    assert nObj >= 16 * 15 and len(opt) >= 15
+    report("dr5_sixteen_scales", objects=nObj, optimal=len(opt))
+
+
+def test_tiles_at_two_declinations_get_their_own_filters(report):
+    """CAR tiles at different declinations have different x pixel scales, hence different radiansMap, templates, filters and
+    normalisation (filters.py:214-239, 617, 642-646).  Four tiles, two at dec 0 and two at dec -50, interleaved: the batched driver
+    groups them by geometry and every catalog matches the per-tile oracle."""
+    from nemo_b200 import pipelines
+    from nemo_b200.wcs import CARWCS
+    tileMaps = {}
+    for t, dec in enumerate([0.0, -50.0, 0.0, -50.0]):
+        md, _ = synth.makeTile(shape=(256, 320), freqsGHz=(97.8, 149.6), noiseUK=(60.0, 40.0), beamFWHMArcmin=(2.2, 1.4),
+                               numObjects=6, kind='clusters', seed=300 + t)
+        wcs = CARWCS((256, 320), 0.5 / 60, crval=(20.0 + t, dec))
+        for m in md:
+            m['wcs'] = wcs
+        tileMaps['tile%d' % t] = md
+    filtersList = [_arnaud('Arnaud_M2e14_z0p4', 2e14, 0.4, grid=20.), _arnaud('Arnaud_M8e14_z0p2', 8e14, 0.2, grid=20.)]
+    parDict = {'mapFilters': filtersList, 'photFilter': 'Arnaud_M2e14_z0p4', 'thresholdSigma': 4.0, 'minObjPix': 1,
+               'findCenterOfMass': True, 'useInterpolator': True, 'rejectBorder': 0}
+    config = pipelines.SimpleConfig(parDict, tileMaps)
+    pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=4)
+    assert [b.tileNames for b in config._staged['batches']] == [['tile0', 'tile2'], ['tile1', 'tile3']]
+    assert len(config._templates) == 2
+    norms = {}
+    nObj = 0
+    for tileName, md in tileMaps.items():
+        phot = None
+        for f in pipelines._orderedFilters(config.parDict):
+            ref, refObj = filters_ref.filterMaps(md, _copyFilter(f), tileName, returnFilter=True)
+            norms[(tileName, f['label'])] = refObj.signalNorm
+            if f['label'] == parDict['photFilter']:
+                phot = {'SNMap': ref['SNMap'], 'data': ref['data']}
+            refCat = photometry_ref.findObjects(ref, **DETECT)
+            photometry_ref.measureFluxes(refCat, ref, None, photFilteredMapDict=phot)
+            _compareCatalogs(config.catalogDict[f['label'] + "#" + tileName]['catalog'], refCat, ['SNR', 'y_c', 'fixed_SNR', 'fixed_y_c'])
+            nObj += len(refCat)
+    # the two geometries really differ: the normalisation moves by far more than the comparison tolerance
+    assert abs(norms[('tile1', 'Arnaud_M2e14_z0p4')] / norms[('tile0', 'Arnaud_M2e14_z0p4')] - 1) > 0.02
+    # a batch that mixes geometries is refused instead of silently taking tile 0's
+    with pytest.raises(Exception):
+        pipelines.TileBatch(pipelines.device.getOps(None), ['tile0', 'tile1'], tileMaps)
+    report("two_declinations", objects=nObj)
+
+
+def test_graph_slots_do_not_leak_between_batches(report):
+    """Seven batches through three pipeline slots with CUDA graphs: the noise tables of every tile equal those of a run
+    without graphs (a slot's graph outputs are overwritten by the batch that reuses it, so they are copied out per batch)."""
+    from nemo_b200 import pipelines
+    tileMaps = {}
+    for t in range(7):
+        md, _ = synth.makeTile(shape=(128, 160), freqsGHz=(148.0,), noiseUK=(40.0 + 7 * t,), numObjects=3, kind='sources', seed=400 + t, margin=30)
+        tileMaps['tile%d' % t] = md
+    parDict = {'mapFilters': [_beam('Beam', grid=10., numBins=2)], 'photFilter': None, 'thresholdSigma': 4.0, 'minObjPix': 1,
+               'findCenterOfMass': True, 'useInterpolator': True, 'rejectBorder': 0}
+    config = pipelines.SimpleConfig(parDict, tileMaps)
+    pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=1)
+    withGraphs = {k: np.array(v) for k, v in config.noiseTables.items()}
+    ops = pipelines.device.getOps(None)
+    batches = config._staged['batches']
+    templates = [pipelines.templatesFor(config, ops, pipelines._orderedFilters(config.parDict), b) for b in batches]
+    for b in batches:
+        b.dev = None
+    results = pipelines.processBatches(ops, batches, pipelines._orderedFilters(config.parDict), templates, config.parDict, useGraphs=False)
+    assert len(withGraphs) == 7
+    for b, (_, extras) in zip(batches, results):
+        key = 'Beam#' + b.tileNames[0]
+        assert np.array_equal(withGraphs[key], np.asarray(extras['noiseTable'])[0]), key
+    tabs = [withGraphs['Beam#tile%d' % t] for t in range(7)]
+    assert all(not np.array_equal(tabs[0], t) for t in tabs[1:])
+    report("graph_slots", batches=7)
+
+
+def test_batched_driver_reads_solid_angle_from_beam_file(tmp_path, report):
+    """outputUnits uK with beams given as ACT-style profile files that carry a 'solid angle = ... nsr' line and no
+    solidAngle_nsr key in the map dictionary: the batched driver and the class API report the same fluxJy (filters.py:180-196,
+    photometry.py:336-339)."""
+    from nemo_b200 import pipelines, filters, photometry, signals
+    md, _ = synth.makeTile(shape=(192, 192), freqsGHz=(148.0,), noiseUK=(80.0,), numObjects=5, kind='sources', seed=77, margin=40)
+    beam = signals.gaussianBeam(1.4)
+    path = str(tmp_path / "beam_profile.txt")
+    with open(path, "w") as fh:
+        fh.write("# solid angle = 188.1 nsr\n")
+        for r, p in zip(beam.rDeg, beam.profile1d):
+            fh.write("%.8e %.8e\n" % (r, p))
+    for m in md:
+        m.pop('solidAngle_nsr', None)
+        m['beamFileName'] = path
+        m['beam'] = path
+    f = _beam('Beam', grid=20.)
+    parDict = {'mapFilters': [f], 'photFilter': None, 'thresholdSigma': 4.0, 'minObjPix': 1, 'findCenterOfMass': True,
+               'useInterpolator': True, 'rejectBorder': 0}
+    config = pipelines.SimpleConfig(parDict, {'T0': md})
+    pipelines.filterMapsAndMakeCatalogs(config, verbose=False)
+    batched = config.catalogDict['Beam#T0']['catalog']
+    got = filters.filterMaps(md, _copyFilter(f), 'T0', verbose=False)
+    assert got['beamSolidAngle_nsr'] == 188.1
+    cat = photometry.findObjects(got, **DETECT)
+    photometry.measureFluxes(cat, got, None)
+    assert len(cat) == len(batched) >= 3
+    assert np.all(np.asarray(cat['fluxJy'], dtype=float) != 0)
+    np.testing.assert_allclose(np.asarray(batched['fluxJy'], dtype=float), np.asarray(cat['fluxJy'], dtype=float), rtol=1e-9)
+    np.testing.assert_allclose(np.asarray(batched['err_fluxJy'], dtype=float), np.asarray(cat['err_fluxJy'], dtype=float), rtol=1e-9)
+    report("beam_file_solid_angle", objects=len(cat))
+
+
+def test_batched_driver_with_background_subtraction(report):
+    """bckSub in the batched driver (Gaussian high-pass of the filtered map and of the filtered template, filters.py:655-659,
+    853-856), with CUDA graphs: catalogs against the per-tile oracle."""
+    from nemo_b200 import pipelines
+    tileMaps = {}
+    for t in range(2):
+        md, _ = synth.makeTile(shape=(256, 256), freqsGHz=(148.0,), noiseUK=(50.0,), numObjects=5, kind='clusters', cmb=True, seed=500 + t)
+        tileMaps['tile%d' % t] = md
+    f = _arnaud('Arnaud_M2e14_z0p4', 2e14, 0.4, grid=20., bckSub=True, bckSubScaleArcmin=6.0)
+    parDict = {'mapFilters': [f], 'photFilter': None, 'thresholdSigma': 4.0, 'minObjPix': 1, 'findCenterOfMass': True,
+               'useInterpolator': True, 'rejectBorder': 0}
+    config = pipelines.SimpleConfig(parDict, tileMaps)
+    for _ in range(2):          # the second call replays the captured graphs
+        pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=1)
+    nObj = 0
+    for tileName, md in tileMaps.items():
+        ref = filters_ref.filterMaps(md, _copyFilter(f), tileName)
+        refCat = photometry_ref.findObjects(ref, **DETECT)
+        photometry_ref.measureFluxes(refCat, ref, None)
+        _compareCatalogs(config.catalogDict[f['label'] + "#" + tileName]['catalog'], refCat, ['SNR', 'y_c', 'deltaT_c'])
+        nObj += len(refCat)
+    assert nObj >= 4
+    report("batched_bcksub", objects=nObj)
