@@ -13,6 +13,7 @@
 #include "fft.cuh"
 #include "nemo_b200_internal.h"
 #include <math.h>
+#include <stdlib.h>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -602,7 +603,13 @@ static int fft_cols_window_t(typename V2<T>::type* data, int B, int H, int Wc, c
 extern "C" {
 
 // row / column passes by side: direct when the side is a power of two, Bluestein otherwise
+static bool use_sfft(int n) {
+    static const bool off = getenv("NEMO_B200_NO_SFFT") != nullptr;      // the run-time-plan passes of fft_bluestein*.cu instead
+    return !off && nb_sfft_supported(n) != 0;
+}
+
 static int rows_fwd(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st) {
+    if (use_sfft(W)) return nb_sfft_rows_fwd(prec, in, out, B, H, W, apodPix, scale, st);
     if (!is_pow2_side(W)) return nb_bs_rows_fwd(prec, in, out, B, H, W, apodPix, scale, st);
     if (prec == NB_PREC_F64) return rfft_rows_t<double>((const double*)in, (double2*)out, B, H, W, apodPix, scale, st);
     return rfft_rows_t<float>((const float*)in, (float2*)out, B, H, W, apodPix, scale, st);
@@ -611,6 +618,7 @@ static int rows_fwd(int prec, const void* in, void* out, int B, int H, int W, in
 static int rows_inv(int prec, const void* in, void* out, int B, int H, int W, double scale, const double* norm, const unsigned char* mask,
                     int maskDiv, const void* zeroRef, cudaStream_t st) {
     if (maskDiv < 1) maskDiv = 1;
+    if (use_sfft(W)) return nb_sfft_rows_inv(prec, in, out, B, H, W, scale, norm, mask, maskDiv, zeroRef, st);
     if (!is_pow2_side(W)) return nb_bs_rows_inv(prec, in, out, B, H, W, scale, norm, mask, maskDiv, zeroRef, st);
     if (prec == NB_PREC_F64) {
         C2RParams<double> ep = {scale, norm, mask, maskDiv, (const double*)zeroRef};
@@ -621,6 +629,7 @@ static int rows_inv(int prec, const void* in, void* out, int B, int H, int W, do
 }
 
 static int cols_plain(int prec, const void* in, void* out, int B, int H, int Wc, int dir, cudaStream_t st) {
+    if (use_sfft(H)) return prec == NB_PREC_F64 ? nb_sfft_cols_f64(in, out, B, H, Wc, dir, st) : nb_sfft_cols_f32(in, out, B, H, Wc, dir, st);
     if (!is_pow2_side(H)) return nb_bs_cols(prec, in, out, B, H, Wc, dir, st);
     if (prec == NB_PREC_F64) return fft_cols_t<double>((const double2*)in, (double2*)out, B, H, Wc, dir, 1.0, st);
     return fft_cols_t<float>((const float2*)in, (float2*)out, B, H, Wc, dir, 1.0, st);
@@ -653,7 +662,10 @@ int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratc
     NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_apply_filter: tile %dx%d not supported (sides 64..4096, even width)", H, W);
     int rc;
     const int Wc = W / 2 + 1;
-    if (!is_pow2_side(H)) {
+    if (use_sfft(H)) {
+        rc = prec == NB_PREC_F64 ? nb_sfft_cols_apply_f64(fmaps, filtH, scratch, nOut, S, perScale, F, H, Wc, st)
+                                 : nb_sfft_cols_apply_f32(fmaps, filtH, scratch, nOut, S, perScale, F, H, Wc, st);
+    } else if (!is_pow2_side(H)) {
         rc = nb_bs_cols_apply(prec, fmaps, filtH, scratch, nOut, S, perScale, F, H, Wc, st);
     } else {
 #define APPLY_F(T, C2T, FF) \
@@ -686,7 +698,9 @@ int nb_window_deconv(int prec, void* data, void* scratch, int B, int H, int W, c
     const int Wc = W / 2 + 1;
     const double scale = 1.0 / ((double)H * (double)W);
     if ((rc = rows_fwd(prec, data, scratch, B, H, W, 0, 1.0, st)) != NB_OK) return rc;
-    if (!is_pow2_side(H)) {
+    if (use_sfft(H)) {
+        rc = prec == NB_PREC_F64 ? nb_sfft_cols_window_f64(scratch, B, H, Wc, wy, wx, st) : nb_sfft_cols_window_f32(scratch, B, H, Wc, wy, wx, st);
+    } else if (!is_pow2_side(H)) {
         rc = nb_bs_cols_window(prec, scratch, B, H, Wc, wy, wx, st);
     } else if (prec == NB_PREC_F64) {
         rc = fft_cols_window_t<double>((double2*)scratch, B, H, Wc, (const double*)wy, (const double*)wx, st);

@@ -17,3 +17,16 @@ int nb_bs_cols(int prec, const void* in, void* out, int B, int H, int Wc, int di
 int nb_bs_cols_apply(int prec, const void* fmaps, const void* filt, void* out, int nOut, int S, int perScale, int F, int H, int Wc,
                      cudaStream_t st);
 int nb_bs_cols_window(int prec, void* data, int B, int H, int Wc, const void* wy, const void* wx, cudaStream_t st);
+
+// compile-time mixed-radix passes for the 2-3-5-7-smooth sides listed in sfft_host.cuh (sfft_rows.cu, sfft_cols_f64/f32.cu);
+// same contracts again
+int nb_sfft_supported(int n);
+int nb_sfft_rows_fwd(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st);
+int nb_sfft_rows_inv(int prec, const void* in, void* out, int B, int H, int W, double scale, const double* norm, const unsigned char* mask,
+                     int maskDiv, const void* zeroRef, cudaStream_t st);
+int nb_sfft_cols_f64(const void* in, void* out, int B, int H, int Wc, int dir, cudaStream_t st);
+int nb_sfft_cols_f32(const void* in, void* out, int B, int H, int Wc, int dir, cudaStream_t st);
+int nb_sfft_cols_apply_f64(const void* fmaps, const void* filt, void* out, int nOut, int S, int perScale, int F, int H, int Wc, cudaStream_t st);
+int nb_sfft_cols_apply_f32(const void* fmaps, const void* filt, void* out, int nOut, int S, int perScale, int F, int H, int Wc, cudaStream_t st);
+int nb_sfft_cols_window_f64(void* data, int B, int H, int Wc, const void* wy, const void* wx, cudaStream_t st);
+int nb_sfft_cols_window_f32(void* data, int B, int H, int Wc, const void* wy, const void* wx, cudaStream_t st);

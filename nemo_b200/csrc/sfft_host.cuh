@@ -1,0 +1,43 @@
+// Host side shared by the sfft translation units: the list of lengths with a compile-time plan, and their twiddle tables.
+#pragma once
+#include "sfft.cuh"
+#include <map>
+#include <mutex>
+#include <vector>
+
+// X(N, R0, R1, R2, NT,  C0, C1, C2, CNT): length; pass radices and threads per transform of the ROW passes (about N / R
+// threads, a thread does one butterfly per pass; two row pairs per CTA); pass radices and threads per column of the COLUMN
+// passes (about N / 2R threads, two butterflies per pass and at most 16 values per thread: a CTA of 4 columns is then small
+// enough in threads and registers for two CTAs per SM, one loading while the other computes)
+#define SFFT_FOR_SIZES(X) \
+    X(1440, 10, 12, 12, 144,  10, 12, 12, 144) \
+    X(840, 7, 10, 12, 120,    7, 8, 15, 60)    \
+    X(420, 5, 7, 12, 84,      5, 7, 12, 42)    \
+    X(320, 5, 8, 8, 64,       5, 8, 8, 32)     \
+    X(300, 5, 6, 10, 60,      5, 6, 10, 30)
+
+// knobs for experiments (tools/build_variant.sh)
+#ifndef SFFT_ROW_G
+#define SFFT_ROW_G 2          // row pairs per CTA
+#endif
+#ifndef SFFT_ROW_MINB
+#define SFFT_ROW_MINB 2       // resident CTAs per SM asked of ptxas
+#endif
+#ifndef SFFT_COL_C
+#define SFFT_COL_C 4          // adjacent columns per CTA
+#endif
+#ifndef SFFT_COL_MINB
+#define SFFT_COL_MINB 2
+#endif
+
+// pass twiddles of a plan (layout: sfft::Plan::twOffset), cached per (precision, device, radices)
+int nb_sfft_twiddles(int prec, int R0, int R1, int R2, const void** out);
+
+template <class PL> static inline int sfft_tw(int prec, const void** out) {
+    return nb_sfft_twiddles(prec, PL::radix(0), PL::radix(1), PL::NP > 2 ? PL::radix(2) : 1, out);
+}
+
+template <typename K> static inline int sfft_set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) NB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return NB_OK;
+}

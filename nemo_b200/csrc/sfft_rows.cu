@@ -1,0 +1,328 @@
+// Row passes of the 2-D real FFT for widths with a compile-time mixed-radix plan (sfft.cuh): real rows -> half spectra with the
+// cosine taper and 1/sqrt(HW) fused into load / store (K1), half spectra -> real rows with signalNorm, scale, mask and
+// zero-restore fused into the store (K4, K8).  Two real rows ride one complex transform of length W.
+#include "sfft_host.cuh"
+#include <math.h>
+
+using namespace sfft;
+
+// ------------------------------------------------------------------------------------------------------
+static std::mutex g_sfft_mutex;
+static std::map<std::vector<int>, void*> g_sfft_tw;
+
+int nb_sfft_twiddles(int prec, int R0, int R1, int R2, const void** out) {
+    std::lock_guard<std::mutex> lock(g_sfft_mutex);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::vector<int> key = {prec, dev, R0, R1, R2};
+    auto it = g_sfft_tw.find(key);
+    if (it != g_sfft_tw.end()) {
+        *out = it->second;
+        return NB_OK;
+    }
+    const long double twopi = 6.283185307179586476925286766559005768L;
+    std::vector<long double> re, im;
+    int Ns = R0;
+    for (int R : {R1, R2}) {
+        if (R <= 1) break;
+        for (int r = 1; r < R; ++r)
+            for (int k = 0; k < Ns; ++k) {
+                const long double a = twopi * (long double)((long long)r * k) / (long double)((long long)Ns * R);
+                re.push_back(cosl(a));
+                im.push_back(-sinl(a));
+            }
+        Ns *= R;
+    }
+    void* d = nullptr;
+    if (prec == NB_PREC_F64) {
+        std::vector<double2> h(re.size());
+        for (size_t i = 0; i < re.size(); ++i) { h[i].x = (double)re[i]; h[i].y = (double)im[i]; }
+        NB_CHECK_CUDA(cudaMalloc(&d, sizeof(double2) * h.size()));
+        NB_CHECK_CUDA(cudaMemcpy(d, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float2> h(re.size());
+        for (size_t i = 0; i < re.size(); ++i) { h[i].x = (float)re[i]; h[i].y = (float)im[i]; }
+        NB_CHECK_CUDA(cudaMalloc(&d, sizeof(float2) * h.size()));
+        NB_CHECK_CUDA(cudaMemcpy(d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
+    }
+    g_sfft_tw[key] = d;
+    *out = d;
+    return NB_OK;
+}
+
+int nb_sfft_supported(int n) {
+#define SFFT_CASE(NN, R0, R1, R2, NT, CR0, CR1, CR2, CNT) if (n == NN) return 1;
+    SFFT_FOR_SIZES(SFFT_CASE)
+#undef SFFT_CASE
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int N, int G> struct SRowCfg {
+    static constexpr int LD = N + 2;
+    static constexpr size_t SMEM = (size_t)2 * G * LD * sizeof(T);
+};
+
+template <typename T, class PL, int NT, int G>
+__global__ void __launch_bounds__(NT * G, SFFT_ROW_MINB)
+sfft_rows_fwd_kernel(const T* __restrict__ in, typename V2<T>::type* __restrict__ out, int H, long long nrows, NbTaper tp, T scale,
+                     const typename V2<T>::type* __restrict__ tw) {
+    typedef typename V2<T>::type C2;
+    typedef SRowCfg<T, PL::N, G> Cfg;
+    typedef Stage<PL, NT, 0> S0;
+    typedef typename Last<PL, NT>::S SL;
+    constexpr int W = PL::N, Wc = W / 2 + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
+    const int g = threadIdx.x / NT, t = threadIdx.x % NT;
+    const long long r0 = ((long long)blockIdx.x * G + g) * 2, r1 = r0 + 1;
+    T* s_re = smem + g * Cfg::LD;
+    T* s_im = smem + (G + g) * Cfg::LD;
+    const bool v0 = r0 < nrows, v1 = r1 < nrows;
+    const T ay0 = (v0 && tp.n > 0) ? taper_at<T>(tp, (int)(r0 % H), H) : (T)1;
+    const T ay1 = (v1 && tp.n > 0) ? taper_at<T>(tp, (int)(r1 % H), H) : (T)1;
+    const T* row0 = in + (size_t)(v0 ? r0 : 0) * W;
+    const T* row1 = in + (size_t)(v1 ? r1 : 0) * W;
+    T xr[S0::REGS], xi[S0::REGS];
+#pragma unroll
+    for (int i = 0; i < S0::IT; ++i) {
+        const int j = t + i * NT;
+#pragma unroll
+        for (int r = 0; r < S0::R; ++r) {
+            T a = 0, b = 0;
+            if (S0::IT * NT == S0::NB || j < S0::NB) {
+                const int n = j + r * S0::NB;
+                a = row0[n];
+                b = row1[n];
+                if (tp.n > 0) {
+                    const T ax = taper_at<T>(tp, n, W);
+                    a *= ay0 * ax;
+                    b *= ay1 * ax;
+                }
+            }
+            xr[i * S0::R + r] = v0 ? a : (T)0;
+            xi[i * S0::R + r] = v1 ? b : (T)0;
+        }
+    }
+    run_from<PL, T, NT, -1, 0>(xr, xi, t, s_re, s_im, tw, BlockSync(), [&](auto& yr, auto& yi) {
+#pragma unroll
+        for (int i = 0; i < SL::IT; ++i) {
+            const int j = t + i * NT;
+            if (SL::IT * NT > SL::NB && j >= SL::NB) continue;
+#pragma unroll
+            for (int r = 0; r < SL::R; ++r) {
+                s_re[j + r * SL::NB] = yr[i * SL::R + r];
+                s_im[j + r * SL::NB] = yi[i * SL::R + r];
+            }
+        }
+    });
+    __syncthreads();
+    // A = (Z + conj(Zc)) / 2,  B = (Z - conj(Zc)) / (2 i),  Zc = Z[W - k]
+    const T h = (T)0.5 * scale;
+    C2* o0 = out + (size_t)r0 * Wc;
+    C2* o1 = out + (size_t)r1 * Wc;
+    for (int k = t; k < Wc; k += NT) {
+        const int kc = (k == 0) ? 0 : W - k;
+        const T zr = s_re[k], zi = s_im[k];
+        const T cr = s_re[kc], ci = -s_im[kc];
+        if (v0) o0[k] = mk2<T>(h * (zr + cr), h * (zi + ci));
+        if (v1) o1[k] = mk2<T>(h * (zi - ci), -h * (zr - cr));
+    }
+}
+
+template <typename T> struct SC2RParams {
+    T scale;
+    const double* norm;
+    const unsigned char* mask;
+    int maskDiv;
+    const T* zeroRef;
+};
+
+template <typename T, class PL, int NT, int G>
+__global__ void __launch_bounds__(NT * G, SFFT_ROW_MINB)
+sfft_rows_inv_kernel(const typename V2<T>::type* __restrict__ in, T* out, int H, long long nrows, SC2RParams<T> ep,
+                     const typename V2<T>::type* __restrict__ tw) {
+    typedef typename V2<T>::type C2;
+    typedef SRowCfg<T, PL::N, G> Cfg;
+    typedef Stage<PL, NT, 0> S0;
+    typedef typename Last<PL, NT>::S SL;
+    constexpr int W = PL::N, Wc = W / 2 + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
+    const int g = threadIdx.x / NT, t = threadIdx.x % NT;
+    const long long r0 = ((long long)blockIdx.x * G + g) * 2, r1 = r0 + 1;
+    T* s_re = smem + g * Cfg::LD;
+    T* s_im = smem + (G + g) * Cfg::LD;
+    const bool v0 = r0 < nrows, v1 = r1 < nrows;
+    // what the store epilogue needs from global memory -- the mask bytes and which pixels of the zero reference (possibly the
+    // output itself: in-place window undo) are zero -- is requested now, together with the spectra: read after the transform it
+    // would cost every CTA a second exposed memory latency.  Kept as packed bytes / one bit per register slot.
+    static_assert(SL::REGS <= 32, "one bit per register slot");
+    constexpr int MW = (SL::REGS + 3) / 4;
+    unsigned mpack[2][MW];
+    unsigned zbits[2] = {0u, 0u};
+    const unsigned H32 = (unsigned)H;
+    unsigned imgOf[2], yOf[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const unsigned row = (unsigned)(rr == 0 ? r0 : r1);       // fewer than 2^32 rows in a batch (checked by the host)
+        imgOf[rr] = row / H32;
+        yOf[rr] = row - imgOf[rr] * H32;
+#pragma unroll
+        for (int w = 0; w < MW; ++w) mpack[rr][w] = 0x01010101u;
+        if (!(rr == 0 ? v0 : v1)) continue;
+        const unsigned char* mrow = ep.mask ? ep.mask + ((size_t)(imgOf[rr] / (unsigned)ep.maskDiv) * H + yOf[rr]) * W : nullptr;
+        const T* zrow = ep.zeroRef ? ep.zeroRef + (size_t)row * W : nullptr;
+        if (mrow) {
+#pragma unroll
+            for (int i = 0; i < SL::IT; ++i) {
+                const int j = t + i * NT;
+#pragma unroll
+                for (int r = 0; r < SL::R; ++r) {
+                    const int q = i * SL::R + r;
+                    const unsigned m = (SL::IT * NT == SL::NB || j < SL::NB) ? (unsigned)mrow[j + r * SL::NB] : 1u;
+                    mpack[rr][q >> 2] = (mpack[rr][q >> 2] & ~(0xffu << (8 * (q & 3)))) | (m << (8 * (q & 3)));
+                }
+            }
+        }
+        if (zrow) {
+#pragma unroll
+            for (int i = 0; i < SL::IT; ++i) {
+                const int j = t + i * NT;
+#pragma unroll
+                for (int r = 0; r < SL::R; ++r) {
+                    if ((SL::IT * NT == SL::NB || j < SL::NB) && zrow[j + r * SL::NB] == (T)0) zbits[rr] |= 1u << (i * SL::R + r);
+                }
+            }
+        }
+    }
+    // the two half spectra, read once and coalesced, become the full Hermitian input Z = A + i B in the exchange buffer
+    {
+        const C2* a0 = in + (size_t)(v0 ? r0 : 0) * Wc;
+        const C2* b0 = in + (size_t)(v1 ? r1 : 0) * Wc;
+        constexpr int KT = (Wc + NT - 1) / NT;
+        C2 av[KT], bv[KT];
+#pragma unroll
+        for (int i = 0; i < KT; ++i) {      // every load in flight before the first store
+            const int k = t + i * NT;
+            av[i] = (v0 && k < Wc) ? a0[k] : mk2<T>(0, 0);
+            bv[i] = (v1 && k < Wc) ? b0[k] : mk2<T>(0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < KT; ++i) {
+            const int k = t + i * NT;
+            if (k >= Wc) continue;
+            const C2 a = av[i], b = bv[i];
+            s_re[k] = a.x - b.y;
+            s_im[k] = a.y + b.x;
+            if (k > 0 && 2 * k < W) {   // Z[W - k] = conj(A[k]) + i conj(B[k])
+                s_re[W - k] = a.x + b.y;
+                s_im[W - k] = b.x - a.y;
+            }
+        }
+    }
+    __syncthreads();
+    T xr[S0::REGS], xi[S0::REGS];
+    stage_gather<PL, T, NT, 0>(xr, xi, t, s_re, s_im);
+    __syncthreads();
+    run_from<PL, T, NT, +1, 0>(xr, xi, t, s_re, s_im, tw, BlockSync(), [&](auto& yr, auto& yi) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const long long row = rr == 0 ? r0 : r1;
+            if (row >= nrows) continue;
+            T f = ep.scale;
+            if (ep.norm) f *= (T)ep.norm[imgOf[rr]];
+            T* orow = out + (size_t)row * W;
+#pragma unroll
+            for (int i = 0; i < SL::IT; ++i) {
+                const int j = t + i * NT;
+                if (SL::IT * NT > SL::NB && j >= SL::NB) continue;
+#pragma unroll
+                for (int r = 0; r < SL::R; ++r) {
+                    const int q = i * SL::R + r;
+                    T v = (rr == 0 ? yr[q] : yi[q]) * f;
+                    if (ep.mask) v *= (T)((mpack[rr][q >> 2] >> (8 * (q & 3))) & 0xffu);
+                    if ((zbits[rr] >> q) & 1u) v = 0;
+                    orow[j + r * SL::NB] = v;
+                }
+            }
+        }
+    });
+}
+
+static void sfft_fill_taper(NbTaper& tp, int apodPix) {
+    tp.n = apodPix;
+    for (int i = 0; i < apodPix; ++i) tp.a[i] = (apodPix == 1) ? 0.0 : 0.5 * (1.0 - cos(M_PI * (double)i / (double)(apodPix - 1)));
+    if (apodPix > 0) tp.a[apodPix - 1] = 1.0;
+}
+
+template <typename T>
+static int sfft_rows_fwd_t(const T* in, typename V2<T>::type* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st) {
+    typedef typename V2<T>::type C2;
+    NB_REQUIRE(apodPix >= 0 && apodPix <= NB_MAX_TAPER && 2 * apodPix <= H && 2 * apodPix <= W, NB_ERR_ARG, "apodPix %d out of range", apodPix);
+    NbTaper tp;
+    sfft_fill_taper(tp, apodPix);
+    const int prec = sizeof(T) == 8 ? NB_PREC_F64 : NB_PREC_F32;
+    const long long nrows = (long long)B * H;
+    const long long npairs = (nrows + 1) / 2;
+    constexpr int G = SFFT_ROW_G;
+    int rc;
+    const void* tw;
+#define SFFT_CASE(NN, R0, R1, R2, NT, CR0, CR1, CR2, CNT)                                                                              \
+    if (W == NN) {                                                                                                        \
+        typedef Plan<NN, R0, R1, R2> PL;                                                                                  \
+        typedef SRowCfg<T, NN, G> Cfg;                                                                                    \
+        if ((rc = sfft_tw<PL>(prec, &tw)) != NB_OK) return rc;                                                            \
+        if ((rc = sfft_set_smem(sfft_rows_fwd_kernel<T, PL, NT, G>, Cfg::SMEM)) != NB_OK) return rc;                      \
+        const unsigned grid = (unsigned)((npairs + G - 1) / G);                                                           \
+        { NB_PROF_BEGIN(st); sfft_rows_fwd_kernel<T, PL, NT, G><<<grid, NT * G, Cfg::SMEM, st>>>(in, out, H, nrows, tp, (T)scale, (const C2*)tw); NB_PROF_END("sfft_rows_fwd_kernel", st); } \
+        NB_CHECK_LAUNCH();                                                                                                \
+        return NB_OK;                                                                                                     \
+    }
+    SFFT_FOR_SIZES(SFFT_CASE)
+#undef SFFT_CASE
+    nb_set_error("sfft: width %d has no compile-time plan", W);
+    return NB_ERR_UNSUPPORTED;
+}
+
+template <typename T>
+static int sfft_rows_inv_t(const typename V2<T>::type* in, T* out, int B, int H, int W, SC2RParams<T> ep, cudaStream_t st) {
+    typedef typename V2<T>::type C2;
+    const int prec = sizeof(T) == 8 ? NB_PREC_F64 : NB_PREC_F32;
+    const long long nrows = (long long)B * H;
+    NB_REQUIRE(nrows < (1LL << 31), NB_ERR_ARG, "sfft: %lld rows in one call (at most 2^31 - 1)", nrows);
+    const long long npairs = (nrows + 1) / 2;
+    constexpr int G = SFFT_ROW_G;
+    int rc;
+    const void* tw;
+#define SFFT_CASE(NN, R0, R1, R2, NT, CR0, CR1, CR2, CNT)                                                                              \
+    if (W == NN) {                                                                                                        \
+        typedef Plan<NN, R0, R1, R2> PL;                                                                                  \
+        typedef SRowCfg<T, NN, G> Cfg;                                                                                    \
+        if ((rc = sfft_tw<PL>(prec, &tw)) != NB_OK) return rc;                                                            \
+        if ((rc = sfft_set_smem(sfft_rows_inv_kernel<T, PL, NT, G>, Cfg::SMEM)) != NB_OK) return rc;                      \
+        const unsigned grid = (unsigned)((npairs + G - 1) / G);                                                           \
+        { NB_PROF_BEGIN(st); sfft_rows_inv_kernel<T, PL, NT, G><<<grid, NT * G, Cfg::SMEM, st>>>(in, out, H, nrows, ep, (const C2*)tw); NB_PROF_END("sfft_rows_inv_kernel", st); } \
+        NB_CHECK_LAUNCH();                                                                                                \
+        return NB_OK;                                                                                                     \
+    }
+    SFFT_FOR_SIZES(SFFT_CASE)
+#undef SFFT_CASE
+    nb_set_error("sfft: width %d has no compile-time plan", W);
+    return NB_ERR_UNSUPPORTED;
+}
+
+int nb_sfft_rows_fwd(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st) {
+    if (prec == NB_PREC_F64) return sfft_rows_fwd_t<double>((const double*)in, (double2*)out, B, H, W, apodPix, scale, st);
+    return sfft_rows_fwd_t<float>((const float*)in, (float2*)out, B, H, W, apodPix, scale, st);
+}
+
+int nb_sfft_rows_inv(int prec, const void* in, void* out, int B, int H, int W, double scale, const double* norm, const unsigned char* mask,
+                     int maskDiv, const void* zeroRef, cudaStream_t st) {
+    if (prec == NB_PREC_F64) {
+        SC2RParams<double> ep = {scale, norm, mask, maskDiv < 1 ? 1 : maskDiv, (const double*)zeroRef};
+        return sfft_rows_inv_t<double>((const double2*)in, (double*)out, B, H, W, ep, st);
+    }
+    SC2RParams<float> ep = {(float)scale, norm, mask, maskDiv < 1 ? 1 : maskDiv, (const float*)zeroRef};
+    return sfft_rows_inv_t<float>((const float2*)in, (float*)out, B, H, W, ep, st);
+}

@@ -444,7 +444,7 @@ def test_snr_mask_f64(ops64, report, trim, realSpace):
 
 
 # ----------------------------------------------------------------------------------------------------------
-NONPOW2 = [(96, 100), (300, 420), (420, 300), (257, 1024), (1024, 330), (840, 1440), (1031, 1032)]
+NONPOW2 = [(96, 100), (300, 420), (420, 300), (257, 1024), (1024, 330), (840, 1440), (1440, 840), (256, 320), (320, 300), (1031, 1032)]
 
 
 @pytest.mark.parametrize("shape", NONPOW2)
@@ -464,7 +464,7 @@ def test_rfft2_irfft2_any_size_f64(ops64, report, shape):
     assert err < 1e-11 and err2 < 1e-11
 
 
-@pytest.mark.parametrize("shape", [(300, 420), (257, 1024), (1024, 330)])
+@pytest.mark.parametrize("shape", [(300, 420), (257, 1024), (1024, 330), (840, 1440), (320, 256)])
 def test_apply_filter_and_window_any_size_f64(ops64, report, shape):
     rng = np.random.default_rng(32)
     H, W = shape
@@ -663,3 +663,20 @@ def test_conv2d_f64(ops64, report, k):
     errP = _relerr(_np(planes)[1, 0], ndimage.convolve(x[1, 0], kern[0]))
     report("conv2d", k=k, relerr=err, relerr_plane=errP)
     assert err < 1e-12 and errP < 1e-12
+
+
+@pytest.mark.parametrize("shape", [(840, 1440), (300, 420)])
+def test_rfft2_irfft2_smooth_size_f32(ops32, report, shape):
+    """The compile-time mixed-radix passes in fp32 storage mode (sides 2-3-5-7-smooth with a plan in sfft_host.cuh)."""
+    rng = np.random.default_rng(33)
+    H, W = shape
+    x = rng.standard_normal((2, H, W)).astype(np.float32)
+    got = _np(ops32.rfft2(ops32.to_device(x), apodPix=20))
+    from oracle import pixell_shim as enmap
+    ref = (np.fft.rfft2(enmap.apod(x.astype(np.float64), 20)) / np.sqrt(H * W))
+    err = _relerr(got, ref)
+    spec = ops32.to_device(np.fft.rfft2(x.astype(np.float64)).astype(np.complex64), ops32.cdtype)
+    back = _np(ops32.irfft2(spec, W, scale=1.0 / (H * W)))
+    err2 = _relerr(back, x)
+    report("rfft2_smooth_f32", shape=shape, relerr=err, relerr_inverse=err2)
+    assert err < 2e-5 and err2 < 2e-5
