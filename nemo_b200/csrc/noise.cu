@@ -40,24 +40,7 @@ __global__ void __launch_bounds__(256) median_weights_kernel(const T* __restrict
 #define CR_WARPS (CR_THREADS / 32)
 #define CR_MAXWARPS 32   // scratch of the block reductions below is sized for up to 1024 threads
 
-#define NB_MAX_CHUNKS 128
-struct Chunks {  // np.linspace(0, H, n + 1, dtype=int) boundaries, passed by value
-    int y[NB_MAX_CHUNKS + 1];
-    int x[NB_MAX_CHUNKS + 1];
-};
-
-struct CellGeom {
-    int y0, y1, x0, x1;
-};
-
-__device__ __forceinline__ CellGeom cell_geom(const Chunks& ch, int i, int k, int ov, int H, int W) {
-    CellGeom g;
-    g.y0 = max(ch.y[i] - ov, 0);
-    g.y1 = min(ch.y[i + 1] + ov, H);
-    g.x0 = max(ch.x[k] - ov, 0);
-    g.x1 = min(ch.x[k + 1] + ov, W);
-    return g;
-}
+#include "noise_cells.cuh"
 
 // block-wide sum of two doubles; result valid in every thread
 __device__ __forceinline__ void block_sum2(double& a, double& b, double* s_red) {
@@ -1398,6 +1381,18 @@ static int cell_rms_t(const void* map, const void* wmed, int nImg, int S, int H,
     memset(&ch, 0, sizeof(ch));
     for (int i = 0; i <= ny; ++i) ch.y[i] = yChunks[i];
     for (int i = 0; i <= nx; ++i) ch.x[i] = xChunks[i];
+    static const bool noOneBin = getenv("NEMO_B200_NO_ONEBIN") != nullptr;      // the on-chip kernel for one bin as well (comparison runs)
+    if (numBins == 1 && estimator == 0 && !noOneBin && nb_onebin_supported(H, W, yChunks, ny, xChunks, nx, ov)) {
+        const int prec = sizeof(T) == 8 ? NB_PREC_F64 : NB_PREC_F32;
+        int rc = nb_cell_rms_onebin(prec, map, wmed, nImg, S, H, W, ch, ny, nx, ov, table, edges, st);
+        if (rc != NB_OK) return rc;
+        if (rms) {
+            { NB_PROF_BEGIN(st); paint_rms_kernel<T><<<dim3((W + 255) / 256, H, nImg), 256, 0, st>>>((const T*)wmed, S, H, W, ch, ny, nx, ov, numBins, table,
+                                                                                 edges, (T*)rms); NB_PROF_END("paint_rms_kernel", st); }
+            NB_CHECK_LAUNCH();
+        }
+        return NB_OK;
+    }
     // largest cell (with its overlap margins) decides between the on-chip kernel and the streaming one
     int maxH = 0, maxW = 0;
     for (int i = 0; i < ny; ++i) maxH = std::max(maxH, std::min(ch.y[i + 1] + ov, H) - std::max(ch.y[i] - ov, 0));

@@ -305,6 +305,42 @@ def test_cell_rms_f64(ops64, report, numBins, shape, gridArcmin):
     assert err < 1e-12
 
 
+@pytest.mark.parametrize("case", ["offset_mean", "two_noise_levels", "heavy_tails", "bright_sources", "mostly_masked"])
+def test_cell_rms_one_bin_hard_cases(ops64, report, case):
+    """One weight bin per cell (zone moments + list-based clipping passes, noise_onebin.cu) on maps that leave the easy regime: a
+    mean far from zero (pivoted sums), cells straddling a 20x jump of the noise level (the list of values above t_lo overflows:
+    sweeping passes), heavy tails and bright sources (thresholds that fall below t_lo: the cell is swept again), and a map that
+    is mostly zero.  Same answer as the oracle's makeNoiseMap in every case."""
+    rng = np.random.default_rng(500 + ["offset_mean", "two_noise_levels", "heavy_tails", "bright_sources", "mostly_masked"].index(case))
+    H, W = 420, 520
+    m = rng.standard_normal((H, W))
+    if case == "offset_mean":
+        m = 50.0 + m
+    elif case == "two_noise_levels":
+        m[:, W // 2 + 17:] *= 20.0
+        m[H // 2 + 5:, :] *= 3.0
+    elif case == "heavy_tails":
+        m = rng.standard_t(1.5, size=(H, W))
+    elif case == "bright_sources":
+        yy, xx = np.mgrid[0:H, 0:W]
+        for _ in range(12):
+            y0, x0 = rng.integers(0, H), rng.integers(0, W)
+            m += rng.uniform(50, 3000) * np.exp(-((yy - y0) ** 2 + (xx - x0) ** 2) / (2 * 3.0 ** 2))
+    elif case == "mostly_masked":
+        m[rng.random((H, W)) < 0.97] = 0
+        m[:, 100:300] = 0
+    m[:7, :] = 0
+    m[:, -5:] = 0
+    w = 1.0 + rng.random((H, W))
+    for gridArcmin in (20.0, 40.0):
+        ref = _oracle_noise(m, [w], 0.5 / 60, gridArcmin, None)
+        got, _ = _run_cell_rms(ops64, m, [w], gridArcmin, 1)
+        err = _relerr(got, ref)
+        report("cell_rms_one_bin_" + case, grid=gridArcmin, relerr=err)
+        assert np.array_equal(got == 0, ref == 0)
+        assert err < 1e-11
+
+
 @pytest.mark.parametrize("numBins", [1, 8])
 def test_cell_rms_constant_weights(ops64, report, numBins):
     """All weights equal: every percentile edge collapses onto the same value and only the last bin holds pixels."""
