@@ -28,6 +28,18 @@
 #define OB_THREADS 256
 #define OB_WARPS (OB_THREADS / 32)
 #define OB_CAP 3072            // list entries per cell (shared memory: 24 KB of doubles)
+#ifndef OB_TLO
+#define OB_TLO 0.65           // t_lo as a fraction of the sweeping pass's threshold
+#endif
+#ifndef OB_MINB
+#define OB_MINB 4
+#endif
+#ifndef OB_U
+#define OB_U 8              // loads in flight per thread of a sweeping pass
+#endif
+#ifndef OB_ZU
+#define OB_ZU 4             // loads of map and weights in flight per thread of the zone pass
+#endif
 #define OB_ZT 5                // doubles per zone block: count, sum d, sum d^2, min weight, max weight (good pixels)
 
 // zone z of an axis with chunk boundaries c[0..n] and overlap ov: even z = 2 i is the core of cell i, odd z = 2 i + 1 the margin
@@ -39,89 +51,118 @@ __device__ __forceinline__ int zone_lo(const int* __restrict__ c, int n, int ov,
     return (z & 1) ? c[i + 1] - ov : c[i] + ov;
 }
 
+// loads the compiler may neither drop nor move under a later condition (it would turn "load map, load weight" into "load map,
+// test, load weight": two memory latencies in a row)
+__device__ __forceinline__ double ob_ldg(const double* q) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(q));
+    return v;
+}
+__device__ __forceinline__ float ob_ldg(const float* q) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(q));
+    return v;
+}
+
 __device__ __forceinline__ double ob_pivot(double centre) { return (centre - centre == 0.0) ? centre : 0.0; }   // finite, else 0
 
+// One CTA per chunk (i, k) takes the four zone blocks (2 i, 2 i + 1) x (2 k, 2 k + 1): the chunk's core, the margins it shares with
+// its right and lower neighbours and the corner between them, one after the other.
 template <typename T>
 __global__ void __launch_bounds__(OB_THREADS) zone_moments_kernel(const T* __restrict__ map, const T* __restrict__ wmed, int S, int H, int W,
                                                                   const Chunks ch, int ny, int nx, int ov, double* __restrict__ zoneTab) {
-    __shared__ double s_red[OB_WARPS][OB_ZT];
-    const int zx = blockIdx.x, zy = blockIdx.y, img = blockIdx.z;
-    const int y0 = zone_lo(ch.y, ny, ov, H, zy), y1 = zone_lo(ch.y, ny, ov, H, zy + 1);
-    const int x0 = zone_lo(ch.x, nx, ov, W, zx), x1 = zone_lo(ch.x, nx, ov, W, zx + 1);
+    __shared__ double s_red[4][OB_ZT][OB_WARPS];
+    const int ck = blockIdx.x, ci = blockIdx.y, img = blockIdx.z;
+    const int nZy = 2 * ny - 1, nZx = 2 * nx - 1;
     const T* m = map + (size_t)img * H * W;
     const T* wm = wmed + (size_t)(img / S) * H * W;
     const double p = ob_pivot((double)m[(size_t)(H / 2) * W + W / 2]);
-    const int bw = x1 - x0, n = (y1 - y0) * bw;
-    const unsigned int magic = bw > 1 ? 0xFFFFFFFFu / (unsigned int)bw + 1u : 0u;     // e / bw by multiply-high, exact for e * bw < 2^32
-    double cnt = 0, s1 = 0, s2 = 0, wmin = INFINITY, wmax = -INFINITY;
-    constexpr int U = 4;
-    for (int e0 = threadIdx.x; e0 < n; e0 += U * OB_THREADS) {
-        T v[U], w[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int e = e0 + u * OB_THREADS;
-            v[u] = (T)0;
-            w[u] = (T)0;
-            if (e < n) {
-                const int r = bw > 1 ? (int)__umulhi((unsigned int)e, magic) : e;
-                const size_t off = (size_t)(y0 + r) * W + x0 + (e - r * bw);
-                v[u] = m[off];
-                w[u] = wm[off];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (v[u] != (T)0) {           // good pixel (filters.py:444); slots past the end hold 0
-                const double d = (double)v[u] - p;
-                cnt += 1.0;
-                s1 += d;
-                s2 += d * d;
-                wmin = fmin(wmin, (double)w[u]);
-                wmax = fmax(wmax, (double)w[u]);
-            }
-        }
-    }
-    cnt = warp_sum(cnt);
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    wmin = warp_min(wmin);
-    wmax = warp_max(wmax);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) {
-        s_red[wid][0] = cnt;
-        s_red[wid][1] = s1;
-        s_red[wid][2] = s2;
-        s_red[wid][3] = wmin;
-        s_red[wid][4] = wmax;
+#pragma unroll 1
+    for (int sub = 0; sub < 4; ++sub) {
+        const int zy = 2 * ci + (sub >> 1), zx = 2 * ck + (sub & 1);
+        double cnt = 0, s1 = 0, s2 = 0, wmin = INFINITY, wmax = -INFINITY;
+        if (zy < nZy && zx < nZx) {
+            const int y0 = zone_lo(ch.y, ny, ov, H, zy), y1 = zone_lo(ch.y, ny, ov, H, zy + 1);
+            const int x0 = zone_lo(ch.x, nx, ov, W, zx), x1 = zone_lo(ch.x, nx, ov, W, zx + 1);
+            const int bw = x1 - x0, n = (y1 - y0) * bw;
+            if (n > 0) {
+                // pixel e of the block sits at offset e + (e / bw) (W - bw) from its first pixel: 32-bit arithmetic, the division a
+                // multiply-high (exact for e * bw < 2^32); loads are unconditional (index clamped), slots past the end count as 0
+                const unsigned int magic = bw > 1 ? 0xFFFFFFFFu / (unsigned int)bw + 1u : 0u;
+                const unsigned int skip = (unsigned int)(W - bw), last = (unsigned int)(n - 1);
+                const T* mb = m + y0 * W + x0;
+                const T* wb = wm + y0 * W + x0;
+                constexpr int U = OB_ZU;
+                int icnt = 0;
+                for (unsigned int e0 = threadIdx.x; e0 <= last; e0 += U * OB_THREADS) {
+                    T v[U], w[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const unsigned int e = min(e0 + u * OB_THREADS, last);
+                        const unsigned int r = bw > 1 ? __umulhi(e, magic) : e;
+                        const unsigned int off = e + r * skip;
+                        v[u] = ob_ldg(mb + off);        // both loads of all U slots are in flight before the first use
+                        w[u] = ob_ldg(wb + off);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const bool good = (e0 + u * OB_THREADS <= last) && v[u] != (T)0;         // filters.py:444
+                        const double wv = (double)w[u];
+                        if (good) {
+                            const double d = (double)v[u] - p;
+                            ++icnt;
+                            s1 += d;
+                            s2 += d * d;
+                            wmin = wv < wmin ? wv : wmin;
+                            wmax = wv > wmax ? wv : wmax;
+                        }
+                    }
+                }
+                cnt = (double)icnt;
+            }
+        }
+        cnt = warp_sum(cnt);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        wmin = warp_min(wmin);
+        wmax = warp_max(wmax);
+        if (lane == 0) {
+            s_red[sub][0][wid] = cnt;
+            s_red[sub][1][wid] = s1;
+            s_red[sub][2][wid] = s2;
+            s_red[sub][3][wid] = wmin;
+            s_red[sub][4][wid] = wmax;
+        }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < OB_WARPS; ++w) {
-            cnt += s_red[w][0];
-            s1 += s_red[w][1];
-            s2 += s_red[w][2];
-            wmin = fmin(wmin, s_red[w][3]);
-            wmax = fmax(wmax, s_red[w][4]);
+    if (threadIdx.x < 4 * OB_ZT) {
+        const int sub = threadIdx.x / OB_ZT, q = threadIdx.x % OB_ZT;
+        const int zy = 2 * ci + (sub >> 1), zx = 2 * ck + (sub & 1);
+        if (zy < nZy && zx < nZx) {
+            double acc = s_red[sub][q][0];
+            for (int w = 1; w < OB_WARPS; ++w) {
+                const double t = s_red[sub][q][w];
+                acc = q < 3 ? acc + t : (q == 3 ? fmin(acc, t) : fmax(acc, t));
+            }
+            zoneTab[(((size_t)img * nZy + zy) * nZx + zx) * OB_ZT + q] = acc;
         }
-        double* z = zoneTab + (((size_t)img * gridDim.y + zy) * gridDim.x + zx) * OB_ZT;
-        z[0] = cnt;
-        z[1] = s1;
-        z[2] = s2;
-        z[3] = wmin;
-        z[4] = wmax;
     }
 }
 
-struct ObSums {
-    double n, s, q;
-};
+#ifdef OB_STATS
+__device__ unsigned long long g_ob_stats[4];     // cells, sweeping passes, list passes, list overflows
+#define OB_COUNT(i) do { if (threadIdx.x == 0) atomicAdd(&g_ob_stats[i], 1ULL); } while (0)
+#else
+#define OB_COUNT(i) do { } while (0)
+#endif
 
 template <typename T>
-__global__ void __launch_bounds__(OB_THREADS) cell_clip_kernel(const T* __restrict__ map, int H, int W, const Chunks ch, int ny, int nx, int ov,
+__global__ void __launch_bounds__(OB_THREADS, OB_MINB) cell_clip_kernel(const T* __restrict__ map, int H, int W, const Chunks ch, int ny, int nx, int ov,
                                                                const double* __restrict__ zoneTab, double* __restrict__ table,
                                                                double* __restrict__ edges) {
     __shared__ T s_tail[OB_CAP];
-    __shared__ double s_red[OB_WARPS][6];
+    __shared__ double s_red[OB_WARPS][3];
     __shared__ double s_pub[8];
     __shared__ int s_cnt;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -187,101 +228,113 @@ __global__ void __launch_bounds__(OB_THREADS) cell_clip_kernel(const T* __restri
     const double p = (mean - mean == 0.0) ? mean : 0.0;        // pivot of everything that follows
     const int cw = g.x1 - g.x0, nPix = (g.y1 - g.y0) * cw;
     const unsigned int magic = cw > 1 ? 0xFFFFFFFFu / (unsigned int)cw + 1u : 0u;
-    const T* m0 = m + (size_t)g.y0 * W + g.x0;
+    const unsigned int skip = (unsigned int)(W - cw), lastPix = (unsigned int)(nPix - 1);
+    const T* m0 = m + g.y0 * W + g.x0;
+    OB_COUNT(0);
     double prevN = n0;
     int it = 0;
     bool done = false;
-    while (it < 10 && !done) {       // filters.py:473
-        // ---- a pass that sweeps the cell: moments below t_lo, moments of [t_lo, thr), list of everything from t_lo up ----
-        const double thr = fabs(mean + 3.0 * rms);
-        if (!(thr == thr)) break;    // nan: no pass can select anything, nothing changes any more
-        const double tlo = 0.75 * thr;
-        if (tid == 0) s_cnt = 0;
-        __syncthreads();
-        double nb = 0, sb = 0, qb = 0, nm = 0, sm = 0, qm = 0;
-        constexpr int U = 8;
-        for (int eb = 0; eb < nPix; eb += U * OB_THREADS) {      // warp-uniform trip count: the list append ballots
+    // moments (count, sum d, sum d^2 about p) of the good values with |v| < t; with LIST also appends the good values that
+    // fail the test to s_tail (count in s_cnt, entries past OB_CAP dropped).  Block-wide result in every thread.
+    auto sweep = [&](const double t, const bool list, double& nb, double& sb, double& qb) {
+        constexpr int U = OB_U;
+        int icnt = 0;
+        sb = 0;
+        qb = 0;
+        for (int eb = 0; eb < nPix; eb += U * OB_THREADS) {      // warp-uniform trip count: the append uses warp collectives
             T v[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int e = eb + tid + u * OB_THREADS;
-                v[u] = (T)0;
-                if (e < nPix) {
-                    const int r = cw > 1 ? (int)__umulhi((unsigned int)e, magic) : e;
-                    v[u] = m0[(size_t)r * W + (e - r * cw)];
-                }
+                const unsigned int e = min((unsigned int)(eb + tid + u * OB_THREADS), lastPix);      // clamped, unconditional loads; 32-bit offsets
+                const unsigned int r = cw > 1 ? __umulhi(e, magic) : e;
+                v[u] = ob_ldg(m0 + (e + r * skip));
             }
+            unsigned int tmask = 0;          // which of this thread's U values go to the list
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const double dv = (double)v[u];
-                const double a = fabs(dv), d = dv - p;
-                const bool good = v[u] != (T)0;
-                const bool below = a < tlo;
+                const bool good = (eb + tid + u * OB_THREADS < nPix) && v[u] != (T)0;
+                const bool below = fabs(dv) < t;
                 if (good && below) {
-                    nb += 1.0;
+                    const double d = dv - p;
+                    ++icnt;
                     sb += d;
                     qb += d * d;
                 }
-                const bool inTail = good && !below;
-                if (inTail && a < thr) {
-                    nm += 1.0;
-                    sm += d;
-                    qm += d * d;
+                tmask |= ((good && !below) ? 1u : 0u) << u;
+            }
+            if (list) {
+                // one shared-memory atomic per warp and batch: list slots by a warp scan of the per-thread counts
+                const int c = __popc(tmask);
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int q = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += q;
                 }
-                const unsigned int bal = __ballot_sync(0xffffffffu, inTail);
-                if (bal) {
-                    const int leader = __ffs(bal) - 1;
+                const int total = __shfl_sync(0xffffffffu, inc, 31);
+                if (total) {
                     int base = 0;
-                    if (lane == leader) base = atomicAdd(&s_cnt, __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, leader);
-                    if (inTail) {
-                        const int idx = base + __popc(bal & ((1u << lane) - 1u));
-                        if (idx < OB_CAP) s_tail[idx] = v[u];
+                    if (lane == 31) base = atomicAdd(&s_cnt, total);
+                    base = __shfl_sync(0xffffffffu, base, 31);
+                    int idx = base + inc - c;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if ((tmask >> u) & 1u) {
+                            if (idx < OB_CAP) s_tail[idx] = v[u];
+                            ++idx;
+                        }
                     }
                 }
             }
         }
-        nb = warp_sum(nb);
+        nb = warp_sum((double)icnt);
         sb = warp_sum(sb);
         qb = warp_sum(qb);
-        nm = warp_sum(nm);
-        sm = warp_sum(sm);
-        qm = warp_sum(qm);
         if (lane == 0) {
             s_red[wid][0] = nb;
             s_red[wid][1] = sb;
             s_red[wid][2] = qb;
-            s_red[wid][3] = nm;
-            s_red[wid][4] = sm;
-            s_red[wid][5] = qm;
         }
         __syncthreads();
-        nb = sb = qb = nm = sm = qm = 0;
+        nb = sb = qb = 0;
 #pragma unroll
         for (int w = 0; w < OB_WARPS; ++w) {
             nb += s_red[w][0];
             sb += s_red[w][1];
             qb += s_red[w][2];
-            nm += s_red[w][3];
-            sm += s_red[w][4];
-            qm += s_red[w][5];
         }
-        const int nTail = s_cnt;
-        {
-            const double n = nb + nm;
-            if (n > 0) {                 // "if mask.sum() > 0" (filters.py:475)
-                const double e1 = (sb + sm) / n, e2 = (qb + qm) / n;
-                double var = e2 - e1 * e1;
-                if (var <= e2 * (n * 8.9e-16)) var = 0.0;
-                mean = p + e1;
-                rms = sqrt(var);
-            }
-            if (n == prevN || n == 0) done = true;     // same sample as the pass before (or none): the fixed point
-            prevN = n > 0 ? n : prevN;
+    };
+    // one clipping pass given the moments of its sample (filters.py:474-477); the same in every thread that calls it
+    auto update = [&](const double n, const double sd, const double qd) {
+        if (n > 0) {                 // "if mask.sum() > 0"
+            const double e1 = sd / n, e2 = qd / n;
+            double var = e2 - e1 * e1;
+            if (var <= e2 * (n * 8.9e-16)) var = 0.0;
+            mean = p + e1;
+            rms = sqrt(var);
         }
+        if (n == prevN || n == 0) done = true;     // same sample as the pass before (or none): the fixed point
+        prevN = n > 0 ? n : prevN;
         ++it;
-        if (nTail > OB_CAP) {            // list incomplete: the next pass sweeps again
-            __syncthreads();             // (everyone has read s_cnt before it is reset)
+    };
+    while (it < 10 && !done) {       // filters.py:473
+        const double thr = fabs(mean + 3.0 * rms);
+        if (!(thr == thr)) break;    // nan: no pass can select anything, nothing changes any more
+        // ---- sweep the cell: moments below t_lo, list of everything from t_lo up ------------------------------------------
+        const double tlo = OB_TLO * thr;
+        OB_COUNT(1);
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        double nb, sb, qb;
+        sweep(tlo, true, nb, sb, qb);
+        const int nTail = s_cnt;
+        __syncthreads();             // everyone has read s_cnt and s_red
+        if (nTail > OB_CAP) {        // list incomplete: this pass directly, the next one sweeps again
+            OB_COUNT(3);
+            sweep(thr, false, nb, sb, qb);
+            __syncthreads();
+            update(nb, sb, qb);
             continue;
         }
         // ---- passes that only need the list (one warp, no barrier), while their thresholds stay at or above t_lo ----------
@@ -293,6 +346,7 @@ __global__ void __launch_bounds__(OB_THREADS) cell_clip_kernel(const T* __restri
                     break;
                 }
                 if (t < tlo) break;
+                OB_COUNT(2);
                 double nt = 0, st = 0, qt = 0;
                 for (int e = lane; e < nTail; e += 32) {
                     const double dv = (double)s_tail[e];
@@ -306,17 +360,7 @@ __global__ void __launch_bounds__(OB_THREADS) cell_clip_kernel(const T* __restri
                 nt = warp_sum(nt);
                 st = warp_sum(st);
                 qt = warp_sum(qt);
-                const double n = nb + nt;
-                if (n > 0) {
-                    const double e1 = (sb + st) / n, e2 = (qb + qt) / n;
-                    double var = e2 - e1 * e1;
-                    if (var <= e2 * (n * 8.9e-16)) var = 0.0;
-                    mean = p + e1;
-                    rms = sqrt(var);
-                }
-                if (n == prevN || n == 0) done = true;
-                prevN = n > 0 ? n : prevN;
-                ++it;
+                update(nb + nt, sb + st, qb + qt);
             }
             if (lane == 0) {
                 s_pub[0] = mean;
@@ -379,16 +423,28 @@ template <typename T>
 static int onebin_t(const T* map, const T* wmed, int nImg, int S, int H, int W, const Chunks& ch, int ny, int nx, int ov, double* table,
                     double* edges, cudaStream_t st) {
     const int nZy = 2 * ny - 1, nZx = 2 * nx - 1;
-    NB_REQUIRE(nImg <= 65535 && nZy <= 65535, NB_ERR_UNSUPPORTED, "nb_cell_rms: more than 65535 images in one call");
+    NB_REQUIRE(nImg <= 65535, NB_ERR_UNSUPPORTED, "nb_cell_rms: more than 65535 images in one call");
     double* zoneTab = nullptr;
     int rc = ob_scratch(st, sizeof(double) * OB_ZT * (size_t)nImg * nZy * nZx, &zoneTab);
     if (rc != NB_OK) return rc;
-    { NB_PROF_BEGIN(st); zone_moments_kernel<T><<<dim3(nZx, nZy, nImg), OB_THREADS, 0, st>>>(map, wmed, S, H, W, ch, ny, nx, ov, zoneTab); NB_PROF_END("zone_moments_kernel", st); }
+    { NB_PROF_BEGIN(st); zone_moments_kernel<T><<<dim3(nx, ny, nImg), OB_THREADS, 0, st>>>(map, wmed, S, H, W, ch, ny, nx, ov, zoneTab); NB_PROF_END("zone_moments_kernel", st); }
     NB_CHECK_LAUNCH();
     { NB_PROF_BEGIN(st); cell_clip_kernel<T><<<dim3(ny * nx, nImg), OB_THREADS, 0, st>>>(map, H, W, ch, ny, nx, ov, zoneTab, table, edges); NB_PROF_END("cell_clip_kernel", st); }
     NB_CHECK_LAUNCH();
     return NB_OK;
 }
+
+#ifdef OB_STATS
+extern "C" int nb_onebin_stats(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_ob_stats, sizeof(unsigned long long) * 4);
+    if (reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_ob_stats, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 int nb_cell_rms_onebin(int prec, const void* map, const void* wmed, int nImg, int S, int H, int W, const Chunks& ch, int ny, int nx, int ov,
                        double* table, double* edges, cudaStream_t st) {
