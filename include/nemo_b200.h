@@ -133,6 +133,14 @@ int nb_smart_rms(int prec, const void* map, const void* wmed, int nImg, int S, i
 int nb_rms_area_table(int prec, const void* rms, const unsigned char* mask, const double* rowArea, int nImg, int S, int H, int W,
                       const double* cand, int K, double* area, double* total, int* miss, cudaStream_t stream);
 
+/* catalogs.makeOptimalCatalog / removeDuplicates (nemo/catalogs.py:171-183, 520-565; nemo/pipelines.py:329-331): which rows of a
+ * stacked catalog lose to a higher-S/N detection of the same object.  raDeg, decDeg, snr [n] fp64 (device).  For every centre row
+ * c in [firstCentre, firstCentre + numCentres): the rows within radiusDeg of c by astCoords.calcAngSepDeg(c, row) (c included); if
+ * more than one, all but the highest-S/N one (lowest index on ties) get toRemove = 1.  toRemove [n] u8 must be zeroed by the
+ * caller; calls over disjoint centre ranges (ranks of a multi-GPU run) are combined by OR. */
+int nb_xmatch_keep_best(const double* raDeg, const double* decDeg, const double* snr, int n, int firstCentre, int numCentres,
+                        double radiusDeg, unsigned char* toRemove, cudaStream_t stream);
+
 /* K6: MapFilter.makeNoiseMap, grid branch, default 3-sigma-clipped estimator (nemo/filters.py:409-481).
  * map [nImg, H, W] (already multiplied by psMask); wmed [nImg / S, H, W] median weights;
  * yChunks host [ny + 1], xChunks host [nx + 1] (np.linspace(..., dtype=int)); overlapPix; numBins.

@@ -373,24 +373,44 @@ def _crossMatchKeepBest(ra, dec, snr, radiusDeg):
     return toRemove
 
 
-def makeOptimalCatalog(catalogDict, constraintsList=[]):
+def crossMatchKeepBest(ra, dec, snr, radiusDeg, ops=None, comm=None):
+    """Boolean mask of the rows that lose to a higher-S/N row (see _crossMatchKeepBest).  With `ops` (nemo_b200.ops.Ops) the rule is
+    evaluated on the device (nb_xmatch_keep_best: every centre against every row).  With `comm` as well (all ranks hold the same
+    rows) the ranks share the centres and combine their masks with one all-reduce."""
+    if ops is None:
+        return _crossMatchKeepBest(ra, dec, snr, radiusDeg)
+    from . import device
+    n = len(ra)
+    if n < 2:
+        return np.zeros(n, dtype=bool)
+    if comm is not None and comm.size > 1:
+        per = (n + comm.size - 1) // comm.size
+        first = min(comm.rank * per, n)
+        mask = ops.xmatch_keep_best(ra, dec, snr, radiusDeg, first, min(per, n - first))
+        mask = comm.maxReduceDevice(mask)
+    else:
+        mask = ops.xmatch_keep_best(ra, dec, snr, radiusDeg)
+    return device.toHost(mask) != 0
+
+
+def makeOptimalCatalog(catalogDict, constraintsList=[], ops=None):
     """Keeps, for every group of detections within XMATCH_RADIUS_DEG of each other across filters, the one with
-    the highest S/N; sorted by (RADeg, decDeg)  (catalogs.py:149-189)."""
+    the highest S/N; sorted by (RADeg, decDeg)  (catalogs.py:149-189).  ops: evaluate the cross-match on the device."""
     allCatalogs = [catalogDict[key]['catalog'] for key in catalogDict.keys() if len(catalogDict[key]['catalog']) > 0]
     if len(allCatalogs) == 0:
         return Table(names=('SNR', 'RADeg', 'decDeg'))
     allCat = vstack(allCatalogs)
     ra, dec, snr = allCat['RADeg'].astype(float), allCat['decDeg'].astype(float), allCat['SNR'].astype(float)
-    merged = allCat[~_crossMatchKeepBest(ra, dec, snr, XMATCH_RADIUS_DEG)]
+    merged = allCat[~crossMatchKeepBest(ra, dec, snr, XMATCH_RADIUS_DEG, ops=ops)]
     merged.sort(['RADeg', 'decDeg'])
     if constraintsList:
         raise Exception("catalogCuts constraints are not supported yet")
     return merged
 
 
-def removeDuplicates(tab):
+def removeDuplicates(tab, ops=None, comm=None):
     """Drops lower-S/N duplicates of the same object found in overlapping tiles (catalogs.py:520-565)."""
     if len(tab) < 2:
         return tab
     ra, dec, snr = tab['RADeg'].astype(float), tab['decDeg'].astype(float), tab['SNR'].astype(float)
-    return tab[~_crossMatchKeepBest(ra, dec, snr, XMATCH_RADIUS_DEG)]
+    return tab[~crossMatchKeepBest(ra, dec, snr, XMATCH_RADIUS_DEG, ops=ops, comm=comm)]

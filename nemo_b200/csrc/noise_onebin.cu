@@ -93,31 +93,34 @@ __global__ void __launch_bounds__(OB_THREADS) zone_moments_kernel(const T* __res
                 const unsigned int skip = (unsigned int)(W - bw), last = (unsigned int)(n - 1);
                 const T* mb = m + y0 * W + x0;
                 const T* wb = wm + y0 * W + x0;
-                constexpr int U = OB_ZU;
                 int icnt = 0;
-                for (unsigned int e0 = threadIdx.x; e0 <= last; e0 += U * OB_THREADS) {
+                auto take = [&](const T v, const T w) {
+                    if (v != (T)0) {          // good pixel (filters.py:444)
+                        const double d = (double)v - p, wv = (double)w;
+                        ++icnt;
+                        s1 += d;
+                        s2 += d * d;
+                        wmin = wv < wmin ? wv : wmin;
+                        wmax = wv > wmax ? wv : wmax;
+                    }
+                };
+                auto offsetOf = [&](const unsigned int e) { return e + (bw > 1 ? __umulhi(e, magic) : e) * skip; };
+                constexpr int U = OB_ZU;
+                unsigned int e0 = threadIdx.x;
+                for (; e0 + (U - 1) * OB_THREADS <= last; e0 += U * OB_THREADS) {     // full batches: U loads of each array in flight
                     T v[U], w[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const unsigned int e = min(e0 + u * OB_THREADS, last);
-                        const unsigned int r = bw > 1 ? __umulhi(e, magic) : e;
-                        const unsigned int off = e + r * skip;
-                        v[u] = ob_ldg(mb + off);        // both loads of all U slots are in flight before the first use
+                        const unsigned int off = offsetOf(e0 + u * OB_THREADS);
+                        v[u] = ob_ldg(mb + off);
                         w[u] = ob_ldg(wb + off);
                     }
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const bool good = (e0 + u * OB_THREADS <= last) && v[u] != (T)0;         // filters.py:444
-                        const double wv = (double)w[u];
-                        if (good) {
-                            const double d = (double)v[u] - p;
-                            ++icnt;
-                            s1 += d;
-                            s2 += d * d;
-                            wmin = wv < wmin ? wv : wmin;
-                            wmax = wv > wmax ? wv : wmax;
-                        }
-                    }
+                    for (int u = 0; u < U; ++u) take(v[u], w[u]);
+                }
+                for (; e0 <= last; e0 += OB_THREADS) {      // what is left (thin zone blocks never reach the loop above)
+                    const unsigned int off = offsetOf(e0);
+                    take(ob_ldg(mb + off), ob_ldg(wb + off));
                 }
                 cnt = (double)icnt;
             }

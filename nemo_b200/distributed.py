@@ -76,6 +76,11 @@ class Comm(object):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def maxReduceDevice(self, t):
+        """Element-wise maximum of a device tensor over ranks, in place (the OR of u8 masks): one all-reduce."""
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t
+
     def sumOverRanks(self, value):
         t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.device)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
@@ -168,7 +173,7 @@ def unpackTable(num, strs, numKeys, strKeys, labels=None, tileNames=None, objIde
     return catalogs.Table.fromColumns([(k, cols[k]) for k in (['name'] if 'name' in cols and coded else []) + list(numKeys) + list(strKeys)])
 
 
-def allGatherCatalog(comm, tab, keys, labels=None, tileNames=None, objIdent='ACT-CL', longNames=False):
+def allGatherCatalog(comm, tab, keys, labels=None, tileNames=None, objIdent='ACT-CL', longNames=False, ops=None):
     """Every rank gets the concatenation of all ranks' catalogs, with duplicates across tiles removed (the
     reference strips them after its allgather, pipelines.py:329-331) and rows sorted by (RADeg, decDeg)."""
     num, strs, numKeys, strKeys = packTable(tab, keys, labels, tileNames)
@@ -180,7 +185,9 @@ def allGatherCatalog(comm, tab, keys, labels=None, tileNames=None, objIdent='ACT
     merged = unpackTable(num, strs, numKeys, strKeys, labels, tileNames, objIdent, longNames)
     ordered = catalogs.Table.fromColumns([(k, merged._cols.raw(k)) for k in keys if k in merged.keys()])
     if len(ordered) > 0:
-        ordered = catalogs.removeDuplicates(ordered)
+        # every rank holds the same gathered rows: with `ops` the ranks share the cross-match (each takes 1 / size of the centres
+        # on its GPU, one all-reduce of the byte mask) instead of every rank repeating the whole of it on the host
+        ordered = catalogs.removeDuplicates(ordered, ops=ops, comm=comm if ops is not None else None)
         ordered.sort(['RADeg', 'decDeg'])
     return ordered
 

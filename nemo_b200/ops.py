@@ -297,6 +297,19 @@ class Ops(object):
         self.launches += 1
         return area, total, miss
 
+    def xmatch_keep_best(self, RADeg, decDeg, SNR, radiusDeg, firstCentre=0, numCentres=None):
+        """catalogs.makeOptimalCatalog's decision for host columns RADeg, decDeg, SNR [n]: device u8 mask [n], 1 where a row loses
+        to a higher-S/N row within radiusDeg of some centre in [firstCentre, firstCentre + numCentres) (default: all rows)."""
+        ra = self.to_device(np.ascontiguousarray(RADeg, dtype=np.float64), self.torch.float64)
+        dec = self.to_device(np.ascontiguousarray(decDeg, dtype=np.float64), self.torch.float64)
+        snr = self.to_device(np.ascontiguousarray(SNR, dtype=np.float64), self.torch.float64)
+        n = int(ra.shape[0])
+        toRemove = self.zeros((n,), self.torch.uint8)
+        _lib.call('nb_xmatch_keep_best', _ptr(ra), _ptr(dec), _ptr(snr), n, int(firstCentre), int(n if numCentres is None else numCentres),
+                  float(radiusDeg), _ptr(toRemove), self._stream())
+        self.launches += 1
+        return toRemove
+
     def snr_mask(self, maps, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace):
         """In place on maps / rms; returns (data, SNMap, surveyMaskOut u8, rms)."""
         self._check(maps, self.dtype, 'maps')

@@ -780,14 +780,14 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
         tab = extras['noiseTable']
         for o in range(tab.shape[0]):
             noiseTables[filtersList[o % len(filtersList)]['label'] + "#" + names[o // len(filtersList)]] = tab[o]
-    optimalCatalog = catalogs.makeOptimalCatalog(catalogDict, constraintsList=parDict.get('catalogCuts', []))
+    optimalCatalog = catalogs.makeOptimalCatalog(catalogDict, constraintsList=parDict.get('catalogCuts', []), ops=ops)
     if comm is not None and comm.size > 1:
         from . import distributed
         havePhot = parDict.get('photFilter') is not None and any(f['label'] == parDict['photFilter'] for f in filtersList)
         keys = catalogKeys(havePhot, templates.outputUnits, measureFluxes)
         labels = [f['label'] for f in filtersList]
         optimalCatalog = distributed.allGatherCatalog(comm, optimalCatalog, keys, labels, config.allTileNames,
-                                                      objIdent=parDict['objIdent'], longNames=parDict['longNames'])
+                                                      objIdent=parDict['objIdent'], longNames=parDict['longNames'], ops=ops)
         noiseTables = distributed.gatherNoiseTables(comm, noiseTables, labels, config.allTileNames)
     if makeRMSTables and comm is not None and comm.size > 1:
         from . import distributed

@@ -716,3 +716,32 @@ def test_rfft2_irfft2_smooth_size_f32(ops32, report, shape):
     err2 = _relerr(back, x)
     report("rfft2_smooth_f32", shape=shape, relerr=err, relerr_inverse=err2)
     assert err < 2e-5 and err2 < 2e-5
+
+
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,spread", [(1, 1.0), (2, 0.001), (300, 0.3), (5000, 1.5), (20000, 6.0)])
+def test_xmatch_keep_best_matches_host_rule(ops64, report, n, spread):
+    """nb_xmatch_keep_best (every centre against every row on the device) against the host rule of catalogs._crossMatchKeepBest,
+    itself tested against the reference's quadratic loop (test_host.py) and pinned to a reference run (ref_misc.npz opt_*):
+    crowded fields, equal S/N values (lowest row index wins), rows across RA = 0, and the centres split into three ranges whose
+    masks are OR-ed, as the ranks of a multi-GPU run do."""
+    from nemo_b200 import catalogs
+    rng = np.random.default_rng(n)
+    nObj = max(1, n // 9)
+    ra0 = (359.8 + rng.random(nObj) * spread) % 360.0
+    dec0 = -42.0 + rng.random(nObj) * spread
+    pick = rng.integers(0, nObj, n)
+    ra = (ra0[pick] + rng.normal(0, 0.006, n)) % 360.0
+    dec = dec0[pick] + rng.normal(0, 0.006, n)
+    snr = np.round(4 + rng.random(n) * 6, 1)          # one decimal: plenty of ties
+    want = catalogs._crossMatchKeepBest(ra, dec, snr, catalogs.XMATCH_RADIUS_DEG)
+    got = _np(ops64.xmatch_keep_best(ra, dec, snr, catalogs.XMATCH_RADIUS_DEG)) != 0
+    assert np.array_equal(got, want)
+    parts = np.zeros(n, dtype=bool)
+    per = (n + 2) // 3
+    for r in range(3):
+        first = min(r * per, n)
+        parts |= _np(ops64.xmatch_keep_best(ra, dec, snr, catalogs.XMATCH_RADIUS_DEG, first, min(per, n - first))) != 0
+    assert np.array_equal(parts, want)
+    assert np.array_equal(catalogs.crossMatchKeepBest(ra, dec, snr, catalogs.XMATCH_RADIUS_DEG, ops=ops64), want)
+    report("xmatch_keep_best", n=n, removed=int(want.sum()))

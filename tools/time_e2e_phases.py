@@ -13,11 +13,19 @@ if world > 1:
     print('rank', rank, 'cpus', distributed.bindProcessToDeviceCpus(local)) if os.environ.get('BIND', '1') == '1' else None
     torch.distributed.init_process_group(backend='nccl', device_id=torch.device('cuda', local))
     comm = distributed.Comm()
-parDict, tileMaps, truth = bench_workloads.pointSourceConfig(numTiles=16, firstIndex=16 * rank)
+if os.environ.get('WORKLOAD', 'dr5') == 'dr5':
+    nT = int(os.environ.get('TILES', 35))
+    parDict, tileMaps, truth = bench_workloads.dr5Config(numTiles=nT, firstIndex=nT * rank)
+    allNames = [bench_workloads.dr5TileName(i) for i in range(world * nT)]
+    defaultTb = [2, 4, 8]
+else:
+    parDict, tileMaps, truth = bench_workloads.pointSourceConfig(numTiles=16, firstIndex=16 * rank)
+    allNames = ['%d_%d' % (i // 4, i % 4) for i in range(world * 16)]
+    defaultTb = [4]
 config = pipelines.SimpleConfig(parDict, tileMaps)
 config.rank = rank
-config.allTileNames = ['%d_%d' % (i // 4, i % 4) for i in range(world * 16)]
-tb = [int(v) for v in sys.argv[1].split(',')] if len(sys.argv) > 1 else [4]
+config.allTileNames = allNames
+tb = [int(v) for v in sys.argv[1].split(',')] if len(sys.argv) > 1 else defaultTb
 tb = tb[0] if len(tb) == 1 else tb
 acc = {}
 def timed(mod, name):
@@ -32,9 +40,10 @@ for _ in range(3):
     pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=tb, comm=comm)
 for mod, name in [(pipelines, 'processBatches'), (catalogs, 'makeOptimalCatalog'), (device, 'toHost'), (pipelines, 'finishTileBatch'),
                   (distributed, 'allGatherCatalog'), (distributed, 'gatherNoiseTables'), (distributed, 'packTable'),
-                  (distributed, 'unpackTable'), (catalogs, 'removeDuplicates'), (distributed.Comm, 'allGatherArrays')]:
+                  (distributed, 'unpackTable'), (catalogs, 'removeDuplicates'), (distributed.Comm, 'allGatherArrays'),
+                  (pipelines, 'templatesFor'), (pipelines, 'startTileBatch'), (pipelines, 'detectAndMeasure')]:
     timed(mod, name)
-torch.cuda.synchronize(); n = 20
+torch.cuda.synchronize(); n = int(os.environ.get('STEPS', 5))
 if comm is not None: comm.barrier()
 t0 = time.perf_counter()
 for _ in range(n):
