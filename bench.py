@@ -158,6 +158,8 @@ def algorithmicBytes(nT, F, S, H, W, E, rings=True, yc=True):
     b['plane_values_partial_kernel'] = nOut * F * Nc * E + nTpl * Nc * 2 * E
     for k6 in ('cell_rms_onchip_kernel', 'cell_rms_hybrid_kernel', 'cell_rms_stream_kernel', 'cell_rms_kernel', 'paint_rms_kernel'):
         b[k6] = nOut * N * E + nT * N * E      # every image's map; the median weights of its tile
+    b['zone_moments_kernel'] = nOut * N * E + nT * N * E     # one-bin K6: map once + the tile's median weights; then the map once more
+    b['cell_clip_kernel'] = nOut * N * E
     b['edge_rows_kernel'] = nOut * (N * E + 2 * N)
     b['edge_cols_final_kernel'] = nOut * (2 * N * E + 3 * N + 3 * N * E + N)
     b['edge_cols_final_paint_kernel'] = nOut * (2 * N * E + 3 * N + 3 * N * E + N)   # map, median weights, masks in; data, S/N, RMS, mask out
@@ -381,6 +383,12 @@ def main():
     # ---- end-to-end arm: pinned host buffers -> host catalog through the public driver ------------------------
     for b in batches:
         b.dev = None
+    # the device-resident arm's CUDA graphs (and the memory pools their outputs live in) are not needed any more
+    del batches
+    ops.__dict__.pop('_batchGraphs', None)
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
 
     def e2eArm(cfg, restage=False, steps=args.steps):
         for _ in range(2):
@@ -475,7 +483,8 @@ def main():
 
     cfg = workloadConfig(args.workload, args)
     cfg['l2'] = L2_NOTE
-    run = {'tiles_per_batch': tilesPerBatch, 'e2e_tiles_per_batch': e2eBatch, 'objects_per_step': nObj}
+    run = {'tiles_per_batch': tilesPerBatch, 'e2e_tiles_per_batch': e2eBatch, 'objects_per_step': nObj,
+           'hbm_peak_gb': torch.cuda.max_memory_allocated() / 1e9}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': msStep, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': args.precision, 'data': 'synthetic', 'config': cfg, 'run': run,

@@ -57,8 +57,9 @@ def tileGeometry(mapDicts):
     cRADeg, cDecDeg = wcs.getCentreWCSCoords()
     cx, cy = wcs.wcs2pix(cRADeg, cDecDeg)
     # rounded so that tiles of one declination row, whose pixel scales and centres agree to the last few bits only (their RA
-    # offsets round differently), land in one group: 1e-12 relative on the scales, 1e-6 pixel on the centre
-    sig = lambda v: float('%.12e' % v)
+    # offsets round differently: the separations come out 1e-12 apart), land in one group: 1e-9 relative on the scales, 1e-6
+    # pixel on the centre
+    sig = lambda v: float('%.8e' % v)
     return (int(H), int(W), sig(_wcs.calcAngSepDeg(ra0, dec0, ra1, dec0)), sig(_wcs.calcAngSepDeg(ra0, dec0, ra0, dec1)),
             sig(wcs.getPixelSizeDeg()), round(float(cx), 6), round(float(cy), 6))
 
@@ -415,7 +416,12 @@ class BatchPipeline(object):
             st.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launchCount()
-            with torch.cuda.graph(graph, stream=st):
+            # graphs of one slot run one after the other on the slot's stream, so they capture into one memory pool: the
+            # intermediates of a batch shape reuse those of the shapes captured before it (each graph keeps only its outputs)
+            pools = ops.__dict__.setdefault('_graphPools', {})
+            if slot not in pools:
+                pools[slot] = torch.cuda.graph_pool_handle()
+            with torch.cuda.graph(graph, pool=pools[slot], stream=st):
                 if upload:
                     view.dev.update(static)          # the widening of float32-staged maps is part of the captured work
                     widenStaged(ops, view.dev) if needWeights else widenStaged(ops, view.dev, keys=('data',))

@@ -3,12 +3,13 @@ import os, sys, time, cProfile, pstats, io
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench_workloads
 from nemo_b200 import pipelines, device, photometry
-parDict, tileMaps, truth = bench_workloads.pointSourceConfig(numTiles=16)
+nT = int(os.environ.get('TILES', 8))
+parDict, tileMaps, truth = (bench_workloads.dr5Config(numTiles=nT) if os.environ.get('WORKLOAD', 'dr5') == 'dr5' else bench_workloads.pointSourceConfig(numTiles=nT))
 config = pipelines.SimpleConfig(parDict, tileMaps)
 parDict = config.parDict
 ops = device.getOps('f64')
 filtersList = pipelines._orderedFilters(parDict)
-batches = pipelines.stageTiles(config, 16, 'f64')
+batches = pipelines.stageTiles(config, nT, 'f64')
 templates = pipelines.FilterSetTemplates(ops, filtersList, batches[0].mapDicts[0])
 for b in batches: b.upload()
 b = batches[0]
