@@ -11,9 +11,10 @@
  *     "host"; nothing is allocated behind the caller's back except FFT twiddle tables cached per (N, prec);
  *   - prec selects the arithmetic/storage type T of maps and spectra: NB_PREC_F32 (0) or NB_PREC_F64 (1);
  *     covariances, filters-in-full-plane, reductions, tables and spline evaluations are always fp64;
- *   - real maps are [B, H, W]; half spectra are [B, H, Wc] complex(T) with Wc = W/2 + 1;
- *   - for the FFT entry points H and W must lie in 64..4096 and W must be even (NB_ERR_UNSUPPORTED otherwise); sides that
- *     are powers of two take direct passes, any other side exact Bluestein passes (nb_fft_size_supported: 1 / 2 / 0);
+ *   - real maps are [B, H, W]; half spectra are [B, H, Wc] complex(T) with Wc = W/2 + 1 (integer division: odd widths too);
+ *   - for the FFT entry points H and W must lie in 64..4096 (NB_ERR_UNSUPPORTED otherwise); sides that are powers of two take
+ *     direct passes, sides with prime factors 2, 3, 5, 7 that have a compiled plan mixed-radix passes, any other side -- odd
+ *     ones included -- exact Bluestein passes (nb_fft_size_supported: 1 / 2 / 0);
  *   - every call is asynchronous on `stream` and returns 0 on success or a negative NB_ERR_* code, with a
  *     message available from nb_last_error() (thread-local).
  */

@@ -461,7 +461,7 @@ int nb_fft_size_supported(int n) {
 }
 
 static bool tile_supported(int H, int W) {
-    return nb_fft_size_supported(H) != 0 && nb_fft_size_supported(W) != 0 && W >= 64 && (W % 2) == 0;
+    return nb_fft_size_supported(H) != 0 && nb_fft_size_supported(W) != 0;     // odd widths: Bluestein rows, Wc = (W + 1) / 2
 }
 
 template <typename T>
@@ -638,7 +638,7 @@ static int cols_plain(int prec, const void* in, void* out, int B, int H, int Wc,
 int nb_rfft2(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st) {
     NB_REQUIRE(in && out && B > 0, NB_ERR_ARG, "nb_rfft2: bad arguments");
     NB_REQUIRE(prec == NB_PREC_F64 || prec == NB_PREC_F32, NB_ERR_ARG, "nb_rfft2: bad precision %d", prec);
-    NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_rfft2: tile %dx%d not supported (sides 64..4096, even width)", H, W);
+    NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_rfft2: tile %dx%d not supported (sides 64..4096)", H, W);
     int rc;
     if ((rc = rows_fwd(prec, in, out, B, H, W, apodPix, scale, st)) != NB_OK) return rc;
     return cols_plain(prec, out, out, B, H, W / 2 + 1, -1, st);
@@ -648,7 +648,7 @@ int nb_irfft2(int prec, void* spec, void* out, int B, int H, int W, double scale
               const unsigned char* mask, int maskDiv, cudaStream_t st) {
     NB_REQUIRE(spec && out && B > 0, NB_ERR_ARG, "nb_irfft2: bad arguments");
     NB_REQUIRE(prec == NB_PREC_F64 || prec == NB_PREC_F32, NB_ERR_ARG, "nb_irfft2: bad precision %d", prec);
-    NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_irfft2: tile %dx%d not supported (sides 64..4096, even width)", H, W);
+    NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_irfft2: tile %dx%d not supported (sides 64..4096)", H, W);
     int rc;
     if ((rc = cols_plain(prec, spec, spec, B, H, W / 2 + 1, +1, st)) != NB_OK) return rc;
     return rows_inv(prec, spec, out, B, H, W, scale, norm, mask, maskDiv, nullptr, st);
@@ -659,7 +659,7 @@ int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratc
     NB_REQUIRE(fmaps && filtH && scratch && out && nOut > 0 && S > 0, NB_ERR_ARG, "nb_apply_filter: bad arguments");
     NB_REQUIRE(prec == NB_PREC_F64 || prec == NB_PREC_F32, NB_ERR_ARG, "nb_apply_filter: bad precision %d", prec);
     NB_REQUIRE(F >= 1 && F <= NB_MAX_FREQ, NB_ERR_UNSUPPORTED, "nb_apply_filter: %d frequencies not supported (1..%d)", F, NB_MAX_FREQ);
-    NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_apply_filter: tile %dx%d not supported (sides 64..4096, even width)", H, W);
+    NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_apply_filter: tile %dx%d not supported (sides 64..4096)", H, W);
     int rc;
     const int Wc = W / 2 + 1;
     if (use_sfft(H)) {
@@ -693,7 +693,7 @@ int nb_window_deconv(int prec, void* data, void* scratch, int B, int H, int W, c
                      int restoreZeros, cudaStream_t st) {
     NB_REQUIRE(data && scratch && wy && wx && B > 0, NB_ERR_ARG, "nb_window_deconv: bad arguments");
     NB_REQUIRE(prec == NB_PREC_F64 || prec == NB_PREC_F32, NB_ERR_ARG, "nb_window_deconv: bad precision %d", prec);
-    NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_window_deconv: tile %dx%d not supported (sides 64..4096, even width)", H, W);
+    NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_window_deconv: tile %dx%d not supported (sides 64..4096)", H, W);
     int rc;
     const int Wc = W / 2 + 1;
     const double scale = 1.0 / ((double)H * (double)W);

@@ -286,8 +286,8 @@ __global__ void __launch_bounds__(256) build_filter_kernel(const double* __restr
     const double* cv = cov + (size_t)tile * P * H * W;
     double rhs[F], rhs2[F], c1[P], c2[P], x1[F], x2[F];
     // the mirror mode -k has the conjugate template value, hence the same modulus, except on the self-conjugate
-    // columns kx = 0 and W/2 where it is a stored element of its own (equal only up to FFT rounding)
-    const bool ownMirror = (kx == 0 || kx == W / 2);
+    // columns kx = 0 and (even W) W/2 where it is a stored element of its own (equal only up to FFT rounding)
+    const bool ownMirror = (kx == 0 || 2 * kx == W);
 #pragma unroll
     for (int f = 0; f < F; ++f) {
         const C2 v = fsig[(((size_t)sidx * F + f) * H + ky) * Wc + kx];
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) build_filter_kernel(const double* __restr
         if (filtFull) {
             double* ff = filtFull + ((size_t)o * F + f) * H * W;
             ff[(size_t)ky * W + kx] = x1[f];
-            if (kx > 0 && kx < W / 2) ff[(size_t)kym * W + kxm] = x2[f];
+            if (kx > 0 && 2 * kx != W) ff[(size_t)kym * W + kxm] = x2[f];
         }
     }
 }
@@ -754,7 +754,7 @@ int nb_build_filter_fused(int prec, const void* fmaps, const void* fsig, const d
 
 int nb_xpower_smooth(int prec, const void* fmaps, double* cov, double* tmp, int B, int F, int H, int W, double sigma,
                      cudaStream_t st) {
-    NB_REQUIRE(fmaps && cov && tmp && B > 0 && H > 0 && W > 0 && (W % 2) == 0, NB_ERR_ARG, "nb_xpower_smooth: bad arguments");
+    NB_REQUIRE(fmaps && cov && tmp && B > 0 && H > 0 && W > 0, NB_ERR_ARG, "nb_xpower_smooth: bad arguments");
     NB_REQUIRE(F >= 1 && F <= NB_MAX_FREQ, NB_ERR_UNSUPPORTED, "nb_xpower_smooth: %d frequencies not supported", F);
     GaussW g;
     int rc = make_gauss(sigma, &g);
@@ -776,7 +776,7 @@ int nb_xpower_smooth(int prec, const void* fmaps, double* cov, double* tmp, int 
 
 int nb_build_filter(int prec, const double* cov, const void* fsig, const double* w, double* filtFull, void* filtH,
                     int nOut, int S, int sigPerTile, int F, int H, int W, cudaStream_t st) {
-    NB_REQUIRE(cov && fsig && w && filtH && nOut > 0 && S > 0 && (W % 2) == 0, NB_ERR_ARG, "nb_build_filter: bad arguments");
+    NB_REQUIRE(cov && fsig && w && filtH && nOut > 0 && S > 0, NB_ERR_ARG, "nb_build_filter: bad arguments");
     NB_REQUIRE(F >= 1 && F <= NB_MAX_FREQ, NB_ERR_UNSUPPORTED, "nb_build_filter: %d frequencies not supported", F);
 #define BF(T)                                                                                             \
     switch (F) {                                                                                          \
@@ -793,7 +793,7 @@ int nb_build_filter(int prec, const double* cov, const void* fsig, const double*
 }
 
 int nb_fold_filter(int prec, const double* filtFull, void* filtH, int n, int H, int W, cudaStream_t st) {
-    NB_REQUIRE(filtFull && filtH && n > 0 && (W % 2) == 0, NB_ERR_ARG, "nb_fold_filter: bad arguments");
+    NB_REQUIRE(filtFull && filtH && n > 0, NB_ERR_ARG, "nb_fold_filter: bad arguments");
     const int Wc = W / 2 + 1;
     dim3 grid((Wc + 255) / 256, H, n);
     if (prec == NB_PREC_F64)

@@ -124,7 +124,7 @@ def buildFourierFilters(ops, fmapsNoise, templUnit, templNorm, w, outputUnits, c
     """
     torch = ops.torch
     nT, F, H, Wc = fmapsNoise.shape
-    W = (Wc - 1) * 2
+    W = int(templUnit.shape[-1])          # (odd widths: Wc = (W + 1) / 2, so the width is not implied by Wc)
     nS = templUnit.shape[0]
     S = nS // nT if sigPerTile else nS
     nOut = nT * S
@@ -133,10 +133,10 @@ def buildFourierFilters(ops, fmapsNoise, templUnit, templNorm, w, outputUnits, c
         # K2 + K3 in one kernel, the covariance staying in shared memory: saves the two fp64 [nT, P, H, W] arrays, but the 12-pixel
         # halos of its 32 x 32 tiles move more bytes through L2 than the covariance costs in HBM (0.51 ms against 0.39 ms for
         # 16 tiles of 1024^2, F = 1), so it is off unless memory is the constraint
-        filtH, filtFull = ops.build_filter_fused(fmapsNoise, fsig, w, S, sigPerTile, sigma=3.0, wantFull=wantFull)
+        filtH, filtFull = ops.build_filter_fused(fmapsNoise, fsig, w, S, sigPerTile, sigma=3.0, wantFull=wantFull, W=W)
     else:
         # K2: smoothed noise covariance (filters.py:568-587); K3: per-mode solve (:624-630)
-        cov = ops.xpower_smooth(fmapsNoise, 3.0)
+        cov = ops.xpower_smooth(fmapsNoise, 3.0, W=W)
         filtH, filtFull = ops.build_filter(cov, fsig, w, S, sigPerTile, wantFull=wantFull)
         del cov
     if outputUnits == 'yc':
@@ -152,25 +152,26 @@ def buildFourierFilters(ops, fmapsNoise, templUnit, templNorm, w, outputUnits, c
         raise Exception('need to specify "outputUnits" ("yc" or "uK") in filter params')
     # filteredSignal = applyFilter(fSignalMaps) with signalNorm still 1 (filters.py:653, 686)
     if sigPerTile:
-        filteredSignal = ops.apply_filter(fsigN, filtH, 1)
+        filteredSignal = ops.apply_filter(fsigN, filtH, 1, W=W)
     else:
-        filteredSignal = ops.apply_filter(fsigN, filtH, S, perScale=True)
+        filteredSignal = ops.apply_filter(fsigN, filtH, S, perScale=True, W=W)
     if bckSubSigmas is not None:
         filteredSignal = ops.gauss_filter(filteredSignal, bckSubSigmas[0], bckSubSigmas[1], subtract=True)
     signalNorm, argmaxIdx, maxVal, centreVal = ops.template_norm(filteredSignal, mode, cy, cx, numer)
     fRel = None
     if outputUnits == 'yc':
-        planes = ops.plane_values_at(fsigN, filtH, argmaxIdx, S=0 if sigPerTile else S)
+        planes = ops.plane_values_at(fsigN, filtH, argmaxIdx, S=0 if sigPerTile else S, W=W)
         # fRelWeight = plane value at the argmax pixel / total signal there (filters.py:664-670)
         fRel = (planes, maxVal)
     return {'filtH': filtH, 'filtFull': filtFull, 'signalNorm': signalNorm, 'fRel': fRel, 'S': S}
 
 
-def applyFourierFilters(ops, fmaps, filtH, S, signalNorm, psMask, bckSubSigmas=None):
-    """MatchedFilter.applyFilter (filters.py:824-859) for every (tile, scale), times psMask (:717)."""
+def applyFourierFilters(ops, fmaps, filtH, S, signalNorm, psMask, bckSubSigmas=None, W=None):
+    """MatchedFilter.applyFilter (filters.py:824-859) for every (tile, scale), times psMask (:717).  W: the map width when it
+    is odd (or always); by default that of psMask, else the even width that goes with the half spectra."""
     if bckSubSigmas is None:
-        return ops.apply_filter(fmaps, filtH, S, norm=signalNorm, mask=psMask)
-    m = ops.apply_filter(fmaps, filtH, S)
+        return ops.apply_filter(fmaps, filtH, S, norm=signalNorm, mask=psMask, W=W)
+    m = ops.apply_filter(fmaps, filtH, S, W=W if W is not None else (int(psMask.shape[-1]) if psMask is not None else None))
     m = ops.gauss_filter(m, bckSubSigmas[0], bckSubSigmas[1], subtract=True)
     maskFull = psMask if S == 1 or psMask is None else psMask.repeat_interleave(S, dim=0)
     return ops.scale_mask(m, norm=signalNorm, mask=maskFull)

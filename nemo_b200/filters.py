@@ -15,8 +15,8 @@ Differences a caller can see:
   * filter caches are FITS when astropy is importable, ``.npz`` with the same content otherwise;
   * options whose dependencies are absent raise instead of silently differing: noise methods ``model`` and
     ``max(dataMap,CMB)``, ``noiseModelCatalog``, ``RMSEstimator`` biweight,
-    ``reshapeFilter``; tile sides must lie in 64..4096 with an even width (sides that are not powers of two take
-    mixed-radix passes when their prime factors are 2, 3, 5, 7, the slower Bluestein passes otherwise).
+    ``reshapeFilter``; tile sides must lie in 64..4096 (sides that are not powers of two take mixed-radix passes when
+    their prime factors are 2, 3, 5, 7, the slower Bluestein passes otherwise -- odd sides included).
 """
 
 import os
@@ -339,7 +339,7 @@ class MatchedFilter(MapFilter):
             self.params['savePlots'] = False
 
         filteredMap = engine.applyFourierFilters(ops, fMapsToFilter, self._filtHT, 1, self._signalNormT, dev['psMask'],
-                                                 bckSubSigmas=self._bckSubSigmas())
+                                                 bckSubSigmas=self._bckSubSigmas(), W=self.shape[1])
         del fMapsToFilter
 
         if self.params['outputUnits'] == 'yc':
@@ -420,7 +420,7 @@ class MatchedFilter(MapFilter):
             fMaps = ops.rfft2(device.asTensor(mapDataToFilter, ops).reshape(F, H, W).contiguous(),
                               apodPix=self.apodPix).reshape(1, F, H, W // 2 + 1)
         normT = ops.to_device(np.array([self.signalNorm], dtype=np.float64), ops.torch.float64)
-        out = engine.applyFourierFilters(ops, fMaps, self._filtHT, 1, normT, None, bckSubSigmas=self._bckSubSigmas())
+        out = engine.applyFourierFilters(ops, fMaps, self._filtHT, 1, normT, None, bckSubSigmas=self._bckSubSigmas(), W=W)
         return out[0].cpu().numpy()
 
 

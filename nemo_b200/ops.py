@@ -59,6 +59,17 @@ class Ops(object):
             return t.to(self.device, non_blocking=True)
         return t.to(want).contiguous()
 
+    @staticmethod
+    def _width(Wc, W=None, like=None):
+        """Map width that goes with half spectra of Wc columns: given, or that of a real array `like`, else the even one."""
+        if W is None and like is not None:
+            W = int(like.shape[-1])
+        if W is None:
+            return (Wc - 1) * 2
+        if int(W) // 2 + 1 != Wc:
+            raise _lib.NemoB200Error("width %d does not go with half spectra of %d columns" % (W, Wc))
+        return int(W)
+
     def _check(self, t, dtype, name):
         if t.dtype != dtype or not t.is_contiguous() or t.device != self.device:
             raise _lib.NemoB200Error("%s must be a contiguous %s tensor on %s (got %s, contiguous=%s, %s)"
@@ -86,14 +97,14 @@ class Ops(object):
         self.launches += 2
         return out
 
-    def apply_filter(self, fmaps, filtH, S, scale=1.0, norm=None, mask=None, out=None, scratch=None, perScale=False):
+    def apply_filter(self, fmaps, filtH, S, scale=1.0, norm=None, mask=None, out=None, scratch=None, perScale=False, W=None):
         """out[o] = scale * norm[o] * mask[o // S] * Re(ifft2(sum_f fmaps[o // S, f] * filt[o, f])); with perScale the
         spectra are those of S templates shared by every tile, fmaps[o % S]."""
         self._check(fmaps, self.cdtype, 'fmaps')
         self._check(filtH, self.dtype, 'filtH')
         nT, F, H, Wc = fmaps.shape
         nOut = filtH.shape[0]
-        W = (Wc - 1) * 2
+        W = self._width(Wc, W, mask)
         if perScale:
             if nT != S or nOut % S != 0 or tuple(filtH.shape[1:]) != (F, H, Wc):
                 raise _lib.NemoB200Error("apply_filter: shape mismatch fmaps %s filtH %s S %d" % (tuple(fmaps.shape), tuple(filtH.shape), S))
@@ -123,7 +134,8 @@ class Ops(object):
     def _make_window_tables(self, H, W, power):
         wy = np.sinc(np.fft.fftfreq(H)) ** power
         wx = (np.sinc(np.fft.fftfreq(W)) ** power)[:W // 2 + 1].copy()
-        wx[W // 2] = np.sinc(0.5) ** power  # fftfreq gives -0.5 at the Nyquist column; sinc is even
+        if W % 2 == 0:
+            wx[W // 2] = np.sinc(0.5) ** power  # fftfreq gives -0.5 at the Nyquist column; sinc is even
         return self.to_device(wy), self.to_device(wx)
 
     def apply_window(self, data, power, restoreZeros=False, tables=None, scratch=None):
@@ -141,10 +153,10 @@ class Ops(object):
         return data
 
     # -- filter construction ---------------------------------------------------------------------------
-    def xpower_smooth(self, fmaps, sigma=3.0):
+    def xpower_smooth(self, fmaps, sigma=3.0, W=None):
         self._check(fmaps, self.cdtype, 'fmaps')
         B, F, H, Wc = fmaps.shape
-        W = (Wc - 1) * 2
+        W = self._width(Wc, W)
         P = F * (F + 1) // 2
         cov = self.empty((B, P, H, W), self.torch.float64)
         tmp = self.empty((B, P, H, W), self.torch.float64)
@@ -167,12 +179,12 @@ class Ops(object):
         self.launches += 1
         return filtH, filtFull
 
-    def build_filter_fused(self, fmaps, fsig, w, S, sigPerTile, sigma=3.0, wantFull=False):
+    def build_filter_fused(self, fmaps, fsig, w, S, sigPerTile, sigma=3.0, wantFull=False, W=None):
         """xpower_smooth + build_filter in one kernel; the covariance never leaves the chip.  Returns (filtH, filtFull or None)."""
         self._check(fmaps, self.cdtype, 'fmaps')
         self._check(fsig, self.cdtype, 'fsig')
         nT, F, H, Wc = fmaps.shape
-        W = (Wc - 1) * 2
+        W = self._width(Wc, W)
         nOut = nT * S
         filtH = self.empty((nOut, F, H, Wc))
         filtFull = self.empty((nOut, F, H, W), self.torch.float64) if wantFull else None
@@ -206,14 +218,14 @@ class Ops(object):
         self.launches += 2
         return norm, argmax, maxVal, centre
 
-    def plane_values_at(self, fmaps, filtH, idx, S=0):
+    def plane_values_at(self, fmaps, filtH, idx, S=0, W=None):
         """Per-frequency filtered-template values at pixel idx[b]; S > 0: fmaps holds S template spectra shared by all tiles."""
         self._check(fmaps, self.cdtype, 'fmaps')
         self._check(filtH, self.dtype, 'filtH')
         B, F, H, Wc = filtH.shape
         out = self.empty((B, F), self.torch.float64)
         scratch = self.empty((B * F * 16,), self.torch.float64)
-        _lib.call('nb_plane_values_at', self.prec, _ptr(fmaps), _ptr(filtH), _ptr(idx), _ptr(out), B, int(S), F, H, (Wc - 1) * 2,
+        _lib.call('nb_plane_values_at', self.prec, _ptr(fmaps), _ptr(filtH), _ptr(idx), _ptr(out), B, int(S), F, H, self._width(Wc, W),
                   _ptr(scratch), self._stream())
         self.launches += 2
         return out

@@ -251,7 +251,7 @@ def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=
     else:
         res = {'filtH': cache['filtH'], 'signalNorm': cache['signalNorm'], 'fRel': cache.get('fRel')}
     # K4: apply, times the point-source mask
-    filtered = engine.applyFourierFilters(ops, fmaps, res['filtH'], S, res['signalNorm'], dev['psMask'], bckSubSigmas=bck)
+    filtered = engine.applyFourierFilters(ops, fmaps, res['filtH'], S, res['signalNorm'], dev['psMask'], bckSubSigmas=bck, W=batch.W)
     del fmaps
     trimPix = engine.trimSizePix(params0, pixDeg, realSpace=False)
     photScale = None

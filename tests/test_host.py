@@ -64,10 +64,11 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     rc = lib.nb_rfft2(0, None, None, 1, 64, 64, 0, 1.0, None)
     assert rc < 0 and b'bad arguments' in lib.nb_last_error()
     buf = ctypes.c_void_p(16)
-    rc = lib.nb_rfft2(0, buf, buf, 1, 100, 101, 0, 1.0, None)      # odd width
+    rc = lib.nb_rfft2(0, buf, buf, 1, 100, 63, 0, 1.0, None)       # a side below 64
     assert rc == -3 and b'not supported' in lib.nb_last_error()
     rc = lib.nb_rfft2(0, buf, buf, 1, 5000, 64, 0, 1.0, None)
     assert rc == -3
+    assert lib.nb_fft_size_supported(1033) == 2 and lib.nb_fft_size_supported(1024) == 1 and lib.nb_fft_size_supported(4097) == 0
 
 
 def test_product_path_fails_loudly_without_cuda():

@@ -112,7 +112,7 @@ def test_window_deconv_f64(ops64, report, shape):
 
 
 # ----------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("F,shape", [(1, (64, 128)), (2, (128, 64)), (3, (64, 64)), (2, (512, 512))])
+@pytest.mark.parametrize("F,shape", [(1, (64, 128)), (2, (128, 64)), (3, (64, 64)), (2, (512, 512)), (2, (97, 131)), (1, (300, 421))])
 def test_xpower_smooth_f64(ops64, report, F, shape):
     rng = np.random.default_rng(6)
     H, W = shape
@@ -120,7 +120,7 @@ def test_xpower_smooth_f64(ops64, report, F, shape):
     maps[:, 1:] += maps[:, :1] * 5  # correlated frequencies
     fm = np.fft.fft2(maps) / np.sqrt(H * W)
     fmaps = ops64.rfft2(ops64.to_device(maps.reshape(2 * F, H, W))).reshape(2, F, H, W // 2 + 1)
-    cov = _np(ops64.xpower_smooth(fmaps, 3.0))
+    cov = _np(ops64.xpower_smooth(fmaps, 3.0, W=W))
     p = 0
     worst = 0.0
     for i in range(F):
@@ -133,7 +133,7 @@ def test_xpower_smooth_f64(ops64, report, F, shape):
     assert worst < 1e-12
 
 
-@pytest.mark.parametrize("F,S,shape", [(1, 2, (64, 64)), (2, 2, (128, 64)), (3, 1, (64, 128))])
+@pytest.mark.parametrize("F,S,shape", [(1, 2, (64, 64)), (2, 2, (128, 64)), (3, 1, (64, 128)), (2, 2, (97, 131))])
 def test_build_filter_f64(ops64, report, F, S, shape):
     rng = np.random.default_rng(7)
     H, W = shape
@@ -142,7 +142,7 @@ def test_build_filter_f64(ops64, report, F, S, shape):
     maps[:, 1:] += maps[:, :1] * 3
     fm = np.fft.fft2(maps) / np.sqrt(H * W)
     fmaps = ops64.rfft2(ops64.to_device(maps.reshape(nT * F, H, W))).reshape(nT, F, H, W // 2 + 1)
-    covT = ops64.xpower_smooth(fmaps, 3.0)
+    covT = ops64.xpower_smooth(fmaps, 3.0, W=W)
     templ = rng.standard_normal((S, F, H, W))
     fsigT = ops64.rfft2(ops64.to_device(templ.reshape(S * F, H, W))).reshape(S, F, H, W // 2 + 1)
     w = rng.standard_normal(F)
@@ -223,9 +223,10 @@ def test_template_norm_f64(ops64, report, mode):
     report("template_norm", mode=mode, ok=1)
 
 
-def test_plane_values_at_f64(ops64, report):
+@pytest.mark.parametrize("H,W", [(64, 128), (97, 131)])
+def test_plane_values_at_f64(ops64, report, H, W):
     rng = np.random.default_rng(9)
-    B, F, H, W = 2, 2, 64, 128
+    B, F = 2, 2
     maps = rng.standard_normal((B, F, H, W))
     filt = rng.random((B, F, H, W))
     fm = np.fft.fft2(maps) / np.sqrt(H * W)
@@ -234,7 +235,7 @@ def test_plane_values_at_f64(ops64, report):
     ref = np.array([[cube[b, f].flatten()[idx[b]] for f in range(F)] for b in range(B)])
     fmaps = ops64.rfft2(ops64.to_device(maps.reshape(B * F, H, W))).reshape(B, F, H, W // 2 + 1)
     filtH = ops64.fold_filter(ops64.to_device(filt))
-    got = _np(ops64.plane_values_at(fmaps, filtH, ops64.to_device(idx, ops64.torch.int64)))
+    got = _np(ops64.plane_values_at(fmaps, filtH, ops64.to_device(idx, ops64.torch.int64), W=W))
     err = _relerr(got, ref)
     report("plane_values_at", relerr=err)
     assert err < 1e-11
@@ -480,7 +481,8 @@ def test_snr_mask_f64(ops64, report, trim, realSpace):
 
 
 # ----------------------------------------------------------------------------------------------------------
-NONPOW2 = [(96, 100), (300, 420), (420, 300), (257, 1024), (1024, 330), (840, 1440), (1440, 840), (256, 320), (320, 300), (1031, 1032)]
+NONPOW2 = [(96, 100), (300, 420), (420, 300), (257, 1024), (1024, 330), (840, 1440), (1440, 840), (256, 320), (320, 300), (1031, 1032),
+           (1031, 1033), (301, 421), (128, 65), (840, 1441)]      # odd widths: Wc = (W + 1) / 2, no Nyquist column
 
 
 @pytest.mark.parametrize("shape", NONPOW2)
@@ -494,13 +496,14 @@ def test_rfft2_irfft2_any_size_f64(ops64, report, shape):
     ref = (np.fft.rfft2(enmap.apod(x, 20)) / np.sqrt(H * W))
     err = _relerr(got, ref)
     spec = ops64.to_device(np.fft.rfft2(x), ops64.cdtype)
+    assert got.shape[-1] == W // 2 + 1 == spec.shape[-1]
     back = _np(ops64.irfft2(spec, W, scale=1.0 / (H * W)))
     err2 = _relerr(back, x)
     report("rfft2_any_size", shape=shape, relerr=err, relerr_inverse=err2)
     assert err < 1e-11 and err2 < 1e-11
 
 
-@pytest.mark.parametrize("shape", [(300, 420), (257, 1024), (1024, 330), (840, 1440), (320, 256)])
+@pytest.mark.parametrize("shape", [(300, 420), (257, 1024), (1024, 330), (840, 1440), (320, 256), (301, 421), (1031, 1033)])
 def test_apply_filter_and_window_any_size_f64(ops64, report, shape):
     rng = np.random.default_rng(32)
     H, W = shape

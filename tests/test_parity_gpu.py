@@ -364,6 +364,35 @@ def test_non_power_of_two_tile_end_to_end(report):
     _compareCatalogs(gotCat, refCat, ['SNR', 'y_c', 'err_y_c', 'deltaT_c'])
 
 
+def test_odd_sided_tile_end_to_end(report):
+    """A 301 x 421 tile (the reference's autotiler produces arbitrary sides, maps.py:691-791): odd width -> (W + 1) / 2 spectrum
+    columns and no Nyquist column.  Beam filter on two frequencies (its template is painted on radiansMap by the oracle and the
+    product alike; the oracle's simplified Arnaud painter centres on radiansMap too, while the product follows the reference and
+    paints at wcs.getCentreWCSCoords(), half a pixel away on an odd side).  Class API against the oracle, and the batched driver
+    against the same catalog."""
+    from nemo_b200 import filters, photometry, pipelines
+    mapDicts, truth = synth.makeTile(shape=(301, 421), freqsGHz=(97.8, 149.6), noiseUK=(60.0, 40.0), beamFWHMArcmin=(2.2, 1.4),
+                                     numObjects=14, kind='sources', cmb=True, seed=43, margin=50)
+    f = _beam(edgeTrimArcmin=5.0)
+    ref, refObj = filters_ref.filterMaps(mapDicts, _copyFilter(f), 'T0', returnFilter=True)
+    got, gotObj = filters.filterMaps(mapDicts, _copyFilter(f), 'T0', verbose=False, returnFilter=True)
+    _compareMaps(got, ref, report, "beam_F2_301x421")
+    assert abs(gotObj.signalNorm / refObj.signalNorm - 1) < 1e-8
+    refCat = photometry_ref.findObjects(ref, **DETECT)
+    photometry_ref.measureFluxes(refCat, ref, None)
+    gotCat = photometry.findObjects(got, **DETECT)
+    photometry.measureFluxes(gotCat, got, None)
+    assert len(refCat) >= 3
+    _compareCatalogs(gotCat, refCat, ['SNR', 'deltaT_c', 'err_deltaT_c'])
+    parDict = {'mapFilters': [_copyFilter(f)], 'photFilter': None, 'thresholdSigma': DETECT['threshold'], 'minObjPix': DETECT['minObjPix'],
+               'findCenterOfMass': DETECT['findCenterOfMass'], 'useInterpolator': DETECT['useInterpolator'],
+               'rejectBorder': DETECT['rejectBorder'], 'removeRings': DETECT['removeRings'],
+               'ringThresholdSigma': DETECT['ringThresholdSigma']}
+    config = pipelines.SimpleConfig(parDict, {'T0': mapDicts})
+    pipelines.filterMapsAndMakeCatalogs(config, verbose=False)
+    _compareCatalogs(config.catalogDict[f['label'] + '#T0']['catalog'], refCat, ['SNR', 'deltaT_c', 'err_deltaT_c'])
+
+
 def test_bench_workload_parity_at_full_tile_size(report):
     """The workload bench.py measures (BASELINE configs[1]: 1024 x 1024 tiles, Beam filter, 8 weight bins, S/N > 4) through
     the batched, graph-replayed pipeline, against the oracle on two of its tiles: catalogs identical, noise tables equal."""
