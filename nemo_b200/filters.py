@@ -12,7 +12,8 @@ Differences a caller can see:
     ``pointSourceMask``, ``flagMask``, ``wcs``, ``obsFreqGHz``, ``units``, ``beamFileName`` (a path or a
     ``signals.BeamProfile``); objects with a ``preprocess`` method (the reference's ``maps.MapDict``) are
     preprocessed exactly as the reference does;
-  * filter caches are FITS when astropy is importable, ``.npz`` with the same content otherwise;
+  * filter caches, RMS maps and area masks are FITS files in the reference's layout, written and read by ``nemo_b200.fitsio``
+    (astropy is not needed; tile compression is not implemented, the images are plain HDUs of the same pixel type);
   * options whose dependencies are absent raise instead of silently differing: noise methods ``model`` and
     ``max(dataMap,CMB)``, ``noiseModelCatalog``, ``RMSEstimator`` biweight,
     ``reshapeFilter``; tile sides must lie in 64..4096 (sides that are not powers of two take mixed-radix passes when
@@ -257,26 +258,18 @@ class MapFilter(object):
         return None
 
     def _saveFilterFile(self, arr, header):
-        os.makedirs(os.path.dirname(self.filterFileName), exist_ok=True)
-        try:
-            import astropy.io.fits as pyfits
-            img = pyfits.PrimaryHDU()
-            for k, v in header.items():
-                img.header[k] = v
-            img.data = arr
-            img.writeto(self.filterFileName, overwrite=True)
-        except ImportError:
-            np.savez(self.filterFileName[:-5] + ".npz", data=arr, headerKeys=np.array(list(header.keys())),
-                     headerVals=np.array([float(v) for v in header.values()]))
+        """The reference's filter cache (filters.py:767-777): primary HDU = the filter, SIGNORM / RW<n>_GHZ / RW<n> keywords."""
+        from . import fitsio
+        os.makedirs(os.path.dirname(self.filterFileName) or '.', exist_ok=True)
+        fitsio.writeImage(self.filterFileName, np.asarray(arr), header)
 
     def _readFilterFile(self):
+        from . import fitsio
         path = self._cachePath()
-        if path.endswith(".npz"):
+        if path.endswith(".npz"):           # caches written by earlier versions of this package
             with np.load(path) as z:
                 return z['data'], {str(k): float(v) for k, v in zip(z['headerKeys'], z['headerVals'])}
-        import astropy.io.fits as pyfits
-        with pyfits.open(path) as img:
-            return img[0].data, dict(img[0].header)
+        return fitsio.readImage(path)
 
 
 # -------------------------------------------------------------------------------------------------------------
@@ -375,14 +368,13 @@ class MatchedFilter(MapFilter):
                 'beamSolidAngle_nsr': beamSolidAngle_nsr, 'label': self.label, 'tileName': self.tileName}
 
     def _saveRMSMap(self, rmsT):
+        """filters.py:760-762: selFnDir/<tile>/RMSMap_<label>#<tile>.fits with the tile's WCS (float32, as the reference's
+        RICE_1 file holds; written uncompressed, see nemo_b200/fitsio.py)."""
+        from . import fitsio
         outDir = self.selFnDir + os.path.sep + self.tileName
         os.makedirs(outDir, exist_ok=True)
-        path = outDir + os.path.sep + "RMSMap_%s#%s" % (self.label, self.tileName)
-        try:
-            import astropy.io.fits as pyfits
-            pyfits.CompImageHDU(np.array(rmsT.cpu().numpy(), dtype=np.float32), compression_type='RICE_1').writeto(path + ".fits", overwrite=True)
-        except ImportError:
-            np.save(path + ".npy", rmsT.cpu().numpy())
+        fitsio.saveFITS(outDir + os.path.sep + "RMSMap_%s#%s.fits" % (self.label, self.tileName), rmsT.cpu().numpy(), self.wcs,
+                        compressionType="RICE_1")
 
     def loadFilter(self):
         """Loads a previously saved filter (filters.py:784-794)."""

@@ -290,10 +290,12 @@ def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=
             'rmsTabJob': rmsTabJob}
 
 
-def finishTileBatch(job, measureFluxes=True, keepMaps=False):
+def finishTileBatch(job, measureFluxes=True, keepMaps=False, collect=()):
     """Waits for a startTileBatch job and assembles its catalogs.  Returns (catalogDict, extras) where catalogDict maps
     '<label>#<tileName>' -> {'catalog': Table or []} like the reference's, and extras holds the noise tables (and
-    the device maps when keepMaps)."""
+    the device maps when keepMaps).  collect: 'areaMask' and / or 'RMSMap' -- host copies, per tile, of the area mask (uint8) and
+    the RMS map (float32) of the first filter of the list (the photFilter when there is one), for the selFn/ files the reference
+    writes (pipelines.py:266-267, 336; filters.py:760-762)."""
     catalogDict = detectAndMeasure(job['ops'], job['batch'], job['filtersList'], job['data'], job['SNMap'], job['mapUnits'],
                                    job['parDict'], measureFluxes=measureFluxes, invertMap=job['invertMap'], detectJob=job['detectJob'])
     # small per-image results go to the host here, on the job's stream and before its pipeline slot is reused: with CUDA graphs the
@@ -314,6 +316,14 @@ def finishTileBatch(job, measureFluxes=True, keepMaps=False):
         extras['RMSTabs'] = completeness.finishRMSTables(job['rmsTabJob'])      # [(y0RMS, areaDeg2)] per image
     if keepMaps:
         extras.update({k: job[k] for k in ('data', 'SNMap', 'surveyMask', 'RMSMap', 'filtH')})
+    S = len(job['filtersList'])
+    names = job['batch'].tileNames
+    if 'areaMask' in collect:
+        first = device.toHost(job['surveyMask'][::S].contiguous())
+        extras['areaMask'] = {name: first[i] for i, name in enumerate(names)}
+    if 'RMSMap' in collect:
+        first = device.toHost(job['RMSMap'][::S].to(job['ops'].torch.float32).contiguous())
+        extras['RMSMapFirst'] = {name: first[i] for i, name in enumerate(names)}
     return catalogDict, extras
 
 
@@ -342,8 +352,9 @@ class BatchPipeline(object):
     nothing is shared between batches except the read-only templates."""
 
     def __init__(self, ops, filtersList, templates, parDict, undoPixelWindow=True, measureFluxes=True, invertMap=False,
-                 keepMaps=False, useCachedRMSMap=False, useGraphs=True, depth=2, rmsTables=False, serialize=False):
+                 keepMaps=False, useCachedRMSMap=False, useGraphs=True, depth=2, rmsTables=False, serialize=False, collect=()):
         self.rmsTables = rmsTables
+        self.collect = tuple(collect)
         self.serialize = serialize      # wait for every batch's device work before queueing the next (per-kernel timing runs)
         self.ops, self.filtersList, self.templates, self.parDict = ops, filtersList, templates, parDict
         # the ~40 launches of a batch are captured once per (slot, shape, input buffers) into a CUDA graph and replayed:
@@ -373,7 +384,7 @@ class BatchPipeline(object):
         torch = self.ops.torch
         job, st, release = self.pending.pop(0)
         with torch.cuda.stream(st):
-            out = finishTileBatch(job, measureFluxes=self.measureFluxes, keepMaps=self.keepMaps)
+            out = finishTileBatch(job, measureFluxes=self.measureFluxes, keepMaps=self.keepMaps, collect=self.collect)
         if release:
             job['batch'].dev = None
         return out
@@ -486,7 +497,7 @@ class BatchPipeline(object):
 
 def processBatches(ops, batches, filtersList, templates, parDict, upload=True, undoPixelWindow=True, measureFluxes=True,
                    invertMap=False, keepMaps=False, caches=None, useCachedRMSMap=False, useGraphs=True, depth=2, rmsTables=False,
-                   beforeSubmit=None):
+                   beforeSubmit=None, collect=()):
     """Runs several tile batches through a BatchPipeline; returns the list of (catalogDict, extras), one per batch, in order.
     caches: per-batch filter / RMS caches (see startTileBatch), or None.  templates: one FilterSetTemplates, or one per batch.
     beforeSubmit(batch): host work to do right before a batch is queued (re-staging its maps); it runs while the device
@@ -494,7 +505,7 @@ def processBatches(ops, batches, filtersList, templates, parDict, upload=True, u
     pipe = BatchPipeline(ops, filtersList, templates[0] if isinstance(templates, (list, tuple)) else templates, parDict,
                          undoPixelWindow=undoPixelWindow, measureFluxes=measureFluxes,
                          invertMap=invertMap, keepMaps=keepMaps, useCachedRMSMap=useCachedRMSMap,
-                         useGraphs=useGraphs and not keepMaps, depth=depth, rmsTables=rmsTables)
+                         useGraphs=useGraphs and not keepMaps, depth=depth, rmsTables=rmsTables, collect=collect)
     perBatch = isinstance(templates, (list, tuple))
     results = []
     for i, batch in enumerate(batches):
@@ -669,6 +680,30 @@ def stageTiles(config, tilesPerBatch=8, precision=None):
     return config._staged['batches']
 
 
+def _writeSelFnMaps(config, batches, results, label, comm=None):
+    """The area mask (multi-extension, one per tile) and the RMS maps of filter `label` under config.selFnDir."""
+    import os
+    from . import fitsio
+    selFnDir = getattr(config, 'selFnDir', None)
+    if selFnDir is None:
+        raise Exception("writeAreaMask / writeRMSMaps need config.selFnDir")
+    os.makedirs(selFnDir, exist_ok=True)
+    wcsOf = {name: b.wcsList[i] for b in batches for i, name in enumerate(b.tileNames)}
+    masks, count = [], 0
+    for _, extras in results:
+        for name, m in (extras.get('areaMask') or {}).items():
+            masks.append((name, m, wcsOf[name]))
+        for name, rms in (extras.get('RMSMapFirst') or {}).items():
+            os.makedirs(selFnDir + os.path.sep + name, exist_ok=True)
+            fitsio.saveFITS(selFnDir + os.path.sep + name + os.path.sep + "RMSMap_%s#%s.fits" % (label, name), rms, wcsOf[name],
+                            compressionType='RICE_1')
+            count += 1
+    if masks:
+        multi = comm is not None and comm.size > 1
+        fitsio.writeMEF(selFnDir + os.path.sep + ("areaMask_rank%d.fits" % comm.rank if multi else "areaMask.fits"), masks,
+                        compressionType='PLIO_1')
+
+
 def _batchKey(tilesPerBatch):
     return int(tilesPerBatch) if isinstance(tilesPerBatch, (int, np.integer)) else tuple(int(v) for v in tilesPerBatch)
 
@@ -712,7 +747,7 @@ def _batchBounds(numTiles, tilesPerBatch):
 
 def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=False, measureFluxes=True, invertMap=False,
                               verbose=True, tilesPerBatch=8, precision=None, comm=None, cacheFilters=False, restage=False,
-                              makeRMSTables=False, restageKeys=('data',)):
+                              makeRMSTables=False, restageKeys=('data',), writeAreaMask=False, writeRMSMaps=False):
     """Runs the map filtering and catalog construction steps for this rank's tiles and returns the optimal catalog
     (highest S/N detection across filter scales), gathered over ranks when `comm` (a
     ``nemo_b200.distributed.Comm``) is given -- pipelines.py:33-109, 112-354.
@@ -723,6 +758,10 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     re-reads the `restageKeys` arrays ('data'; 'weights') of the map dictionaries into the pinned staging buffers (they were
     edited in place or replaced since the tiles were staged), batch by batch, each right before it is queued so that the copy
     runs under the device work of the batches before it.
+
+    writeAreaMask / writeRMSMaps (need ``config.selFnDir``): this rank's ``areaMask.fits`` (one extension per tile; with several
+    ranks ``areaMask_rank<r>.fits``) and ``<tile>/RMSMap_<filter>#<tile>.fits`` of the first filter of the list (the photFilter when
+    there is one), as the reference writes them (pipelines.py:266-267, 336; filters.py:760-762) -- see nemo_b200/fitsio.py.
 
     Only Fourier-space matched filters with a common noise set-up are batched here; use ``filters.filterMaps`` +
     ``photometry.findObjects`` directly for anything else.
@@ -771,7 +810,10 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     results = processBatches(ops, batches, filtersList, templatesList, parDict, upload=True,
                              undoPixelWindow=parDict.get('undoPixelWindow', True), measureFluxes=measureFluxes, invertMap=invertMap,
                              keepMaps=cacheFilters, caches=caches, useCachedRMSMap=useCachedRMSMap, rmsTables=makeRMSTables,
-                             beforeSubmit=beforeSubmit)
+                             beforeSubmit=beforeSubmit,
+                             collect=(('areaMask',) if writeAreaMask else ()) + (('RMSMap',) if writeRMSMaps else ()))
+    if writeAreaMask or writeRMSMaps:
+        _writeSelFnMaps(config, batches, results, filtersList[0]['label'], comm)
     if cacheFilters:
         config._cache = [{'filtH': ex['filtH'], 'signalNorm': ex['signalNorm'], 'RMSMap': ex['RMSMap'], 'fRel': ex['fRel']}
                          for _, ex in results]

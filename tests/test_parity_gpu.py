@@ -160,6 +160,39 @@ def test_cached_filter_round_trip(tmp_path, report):
     report("cached_filter", ok=1)
 
 
+def test_files_are_written_in_the_reference_layout(tmp_path, report):
+    """The FITS files other parts of Nemo read back (nemo_b200.fitsio): the filter cache with SIGNORM / RW<n> keywords
+    (filters.py:767-794) holds exactly the filter and normalisation of the object that wrote it; the class API's RMSMap file
+    (filters.py:760-762) and the batched driver's RMSMap / areaMask files (pipelines.py:266-267, 336) hold the maps the filter
+    step returned, with the tile's WCS keywords."""
+    from nemo_b200 import filters, fitsio, pipelines
+    mapDicts, truth = synth.makeTile(shape=(256, 320), freqsGHz=(97.8, 149.6), noiseUK=(60.0, 40.0), beamFWHMArcmin=(2.2, 1.4),
+                                     numObjects=6, kind='clusters', cmb=True, seed=23)
+    f = _arnaud(saveFilter=True, saveRMSMap=True)
+    d = str(tmp_path)
+    got, obj = filters.filterMaps(mapDicts, _copyFilter(f), 'T0', diagnosticsDir=d, selFnDir=d, verbose=False, returnFilter=True)
+    assert obj.filterFileName.endswith('.fits') and os.path.exists(obj.filterFileName)
+    filt, header = fitsio.readImage(obj.filterFileName)
+    assert filt.dtype == np.float64 and filt.shape == (2, 256, 320) and np.array_equal(filt, np.asarray(obj.filt))
+    assert header['SIGNORM'] == obj.signalNorm
+    assert {header['RW1_GHZ']: header['RW1'], header['RW2_GHZ']: header['RW2']} == {float(k): float(v) for k, v in obj.fRelWeights.items()}
+    rms, h = fitsio.readImage(os.path.join(d, 'T0', 'RMSMap_%s#T0.fits' % f['label']))
+    assert rms.dtype == np.float32 and h['CTYPE1'] == 'RA---CAR' and h['NAXIS1'] == 320
+    sn, data = np.asarray(got['SNMap']), np.asarray(got['data'])
+    # the class API's file holds the masked RMS map of the filter step: S/N x RMS gives back the (window-convolved) map wherever
+    # the S/N is non-zero, so check it through the batched driver's copy, which also exposes that map
+    parDict = {'mapFilters': [_copyFilter(_arnaud())], 'photFilter': None, 'thresholdSigma': 4.0, 'minObjPix': 1, 'rejectBorder': 0}
+    config = pipelines.SimpleConfig(parDict, {'T0': mapDicts})
+    config.selFnDir = os.path.join(d, 'batched')
+    pipelines.filterMapsAndMakeCatalogs(config, verbose=False, writeAreaMask=True, writeRMSMaps=True)
+    rmsB, hB = fitsio.readImage(os.path.join(config.selFnDir, 'T0', 'RMSMap_%s#T0.fits' % f['label']))
+    assert np.array_equal(rmsB, rms) and hB['CRVAL1'] == h['CRVAL1']
+    area, hA = fitsio.readImage(os.path.join(config.selFnDir, 'areaMask.fits'), extName='T0')
+    assert area.dtype == np.uint8 and np.array_equal(area != 0, np.asarray(got['surveyMask']) != 0) and hA['EXTNAME'] == 'T0'
+    assert np.array_equal(rms > 0, (area != 0) & (rms > 0)) and (rms > 0).sum() > 0.5 * rms.size
+    report("reference_layout_files", ok=1)
+
+
 def test_real_space_matched_filter_two_frequency(report):
     """BASELINE config 3 (one reduced tile): 90 + 150 GHz real-space kernel, symmetrised, bckSub."""
     from nemo_b200 import filters, photometry
