@@ -134,6 +134,20 @@ int nb_smart_rms(int prec, const void* map, const void* wmed, int nImg, int S, i
 int nb_rms_area_table(int prec, const void* rms, const unsigned char* mask, const double* rowArea, int nImg, int S, int H, int W,
                       const double* cand, int K, double* area, double* total, int* miss, cudaStream_t stream);
 
+/* maps.makeModelImage (nemo/maps.py:1734-1899) with maps.makeDegreesDistanceMap (:2414-2471) and signals.makeBeamModelSignalMap
+ * (nemo/signals.py:587-619): out[img] = base[img] (or 0 when base is NULL) + sum over the image's objects, in list order, of
+ * amplitude * profile(r), r = sqrt(((y - y0) yPixScale)^2 + ((x - x0) xPixScale)^2) inside the object's box [minX, maxX) x
+ * [minY, maxY), the profile interpolated linearly as numpy.interp does (0 beyond its last radius).  obj [nObj, 10] fp64: x0, y0,
+ * xPixScale, yPixScale, amplitude, minX, maxX, minY, maxY, profile index; objStart [nImg + 1] i32: objects of image img are
+ * obj[objStart[img] .. objStart[img + 1]); profR, profV [nProf, nR] fp64 ascending radii (degrees) and profile values.  The pixel
+ * window (and for clusters the beam) are applied afterwards with nb_window_deconv / nb_apply_filter. */
+int nb_paint_objects(int prec, const void* base, void* out, int nImg, int H, int W, const double* obj, const int* objStart,
+                     const double* profR, const double* profV, int nProf, int nR, cudaStream_t stream);
+
+/* out[i] = a[i] + b[i mod nB], i < n: a model image (or one per tile, broadcast over nothing when nB = n) added to the maps it is
+ * injected into (nemo/maps.py:2093 sourceInjectionTest: mapDict['data'] = data + modelMap). */
+int nb_add_maps(int prec, const void* a, const void* b, void* out, long long n, long long nB, cudaStream_t stream);
+
 /* catalogs.makeOptimalCatalog / removeDuplicates (nemo/catalogs.py:171-183, 520-565; nemo/pipelines.py:329-331): which rows of a
  * stacked catalog lose to a higher-S/N detection of the same object.  raDeg, decDeg, snr [n] fp64 (device).  For every centre row
  * c in [firstCentre, firstCentre + numCentres): the rows within radiusDeg of c by astCoords.calcAngSepDeg(c, row) (c included); if

@@ -41,6 +41,8 @@ _PROTOTYPES = {
     "nb_plane_values_at": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr],
     "nb_widen_f32": [c_ptr, c_ptr, c_ll, c_ptr],
     "nb_rms_area_table": [c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
+    "nb_paint_objects": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr],
+    "nb_add_maps": [c_int, c_ptr, c_ptr, c_ptr, c_ll, c_ll, c_ptr],
     "nb_xmatch_keep_best": [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr],
     "nb_smart_rms": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "nb_median_weights": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],

@@ -373,6 +373,24 @@ def _crossMatchKeepBest(ra, dec, snr, radiusDeg):
     return toRemove
 
 
+def withinImage(RADeg, decDeg, shape, wcs, mask=None):
+    """Boolean selection of the positions catalogs.getCatalogWithinImage keeps (catalogs.py:874-892): 0 <= x < W - 1 and
+    0 <= y < H - 1, and mask == 1 at the rounded pixel when a mask is given."""
+    x, y = wcs.wcs2pix(np.asarray(RADeg, dtype=np.float64), np.asarray(decDeg, dtype=np.float64))
+    x, y = np.atleast_1d(np.asarray(x, dtype=np.float64)), np.atleast_1d(np.asarray(y, dtype=np.float64))
+    with np.errstate(invalid='ignore'):
+        sel = (x >= 0) & (x < shape[1] - 1) & (y >= 0) & (y < shape[0] - 1)
+    if mask is not None:
+        idx = np.flatnonzero(sel)
+        sel[idx] = np.asarray(mask)[np.rint(y[idx]).astype(int), np.rint(x[idx]).astype(int)] == 1
+    return sel
+
+
+def getCatalogWithinImage(tab, shape, wcs, mask=None):
+    """The subset of the catalog inside the image (catalogs.py:855-892)."""
+    return tab[withinImage(tab['RADeg'], tab['decDeg'], shape, wcs, mask=mask)]
+
+
 def crossMatchKeepBest(ra, dec, snr, radiusDeg, ops=None, comm=None):
     """Boolean mask of the rows that lose to a higher-S/N row (see _crossMatchKeepBest).  With `ops` (nemo_b200.ops.Ops) the rule is
     evaluated on the device (nb_xmatch_keep_best: every centre against every row).  With `comm` as well (all ranks hold the same

@@ -309,6 +309,39 @@ class Ops(object):
         self.launches += 1
         return area, total, miss
 
+    def paint_objects(self, shape, objects, objStart, profR, profV, base=None):
+        """Model images [nImg, H, W]: objects [nObj, 10] fp64 (x0, y0, xPixScale, yPixScale, amplitude, minX, maxX, minY, maxY, profile
+        index; host array or device tensor), objStart [nImg + 1] i32, profile tables profR / profV [nProf, nR] fp64; added to `base`
+        [nImg, H, W] when given."""
+        t = self.torch
+        nImg, H, W = shape
+        obj = objects if hasattr(objects, 'data_ptr') else self.to_device(np.ascontiguousarray(objects, dtype=np.float64).reshape(-1, 10), t.float64)
+        start = objStart if hasattr(objStart, 'data_ptr') else self.to_device(np.ascontiguousarray(objStart, dtype=np.int32), t.int32)
+        pr = profR if hasattr(profR, 'data_ptr') else self.to_device(np.ascontiguousarray(np.atleast_2d(profR), dtype=np.float64), t.float64)
+        pv = profV if hasattr(profV, 'data_ptr') else self.to_device(np.ascontiguousarray(np.atleast_2d(profV), dtype=np.float64), t.float64)
+        if tuple(pr.shape) != tuple(pv.shape) or int(start.shape[0]) != nImg + 1:
+            raise _lib.NemoB200Error("paint_objects: profile tables %s / %s or objStart %s do not fit" % (tuple(pr.shape), tuple(pv.shape), tuple(start.shape)))
+        if obj.shape[0] == 0:
+            obj = self.zeros((1, 10), t.float64)
+        if base is not None:
+            self._check(base, self.dtype, 'base')
+        out = self.empty((nImg, H, W))
+        _lib.call('nb_paint_objects', self.prec, _ptr(base), _ptr(out), int(nImg), int(H), int(W), _ptr(obj), _ptr(start), _ptr(pr), _ptr(pv),
+                  int(pr.shape[0]), int(pr.shape[1]), self._stream())
+        self.launches += 1
+        return out
+
+    def add_maps(self, a, b):
+        """a + b, b broadcast over the leading axes of a (a model image per tile added to every frequency map of the tile...)."""
+        self._check(a, self.dtype, 'a')
+        self._check(b, self.dtype, 'b')
+        if a.numel() % b.numel() != 0:
+            raise _lib.NemoB200Error("add_maps: sizes %d and %d do not fit" % (a.numel(), b.numel()))
+        out = self.empty(tuple(a.shape))
+        _lib.call('nb_add_maps', self.prec, _ptr(a), _ptr(b), _ptr(out), int(a.numel()), int(b.numel()), self._stream())
+        self.launches += 1
+        return out
+
     def xmatch_keep_best(self, RADeg, decDeg, SNR, radiusDeg, firstCentre=0, numCentres=None):
         """catalogs.makeOptimalCatalog's decision for host columns RADeg, decDeg, SNR [n]: device u8 mask [n], 1 where a row loses
         to a higher-S/N row within radiusDeg of some centre in [firstCentre, firstCentre + numCentres) (default: all rows)."""

@@ -75,9 +75,13 @@ def subtractBackground(data, wcs, RADeg='centre', decDeg='centre', smoothScaleDe
 class BeamProfile(object):
     """Tabulated radial beam (signals.py:82-137 with profile1d/rDeg given directly)."""
 
-    def __init__(self, profile1d, rDeg):
+    def __init__(self, profile1d=None, rDeg=None, beamFileName=None):
+        if beamFileName is not None:        # two-column text file: degrees, response (signals.py:107-122)
+            beamData = np.loadtxt(beamFileName).transpose()
+            profile1d, rDeg = beamData[1], beamData[0]
         self.profile1d = np.asarray(profile1d, dtype=np.float64)
         self.rDeg = np.asarray(rDeg, dtype=np.float64)
+        self.FWHMArcmin = self.rDeg[np.argmin(abs(self.profile1d - 0.5))] * 60 * 2      # signals.py:136
 
 
 def gaussianBeam(FWHMArcmin, maxDeg=0.5, n=1800):

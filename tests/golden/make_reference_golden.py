@@ -256,6 +256,63 @@ def runMisc(refFilters):
             'pixAreaConstantAlongRows': np.array(np.array_equal(np.asarray(area)[:, :1] * np.ones((1, inp['shape'][1])), area))}
 
 
+def paintInputs():
+    """Seeded inputs of the model-image painter (also read by the tests): a 300 x 420 tile at declination -35, a Gaussian beam
+    written to a two-column text file (the ACT beam-profile format BeamProfile reads, nemo/signals.py:107-127), and a catalog of
+    60 sources of either sign, some outside the tile and some on its rim, with S/N values for the minSNR cut."""
+    from oracle.wcs_stub import SimpleCARWCS
+    from oracle import signals_ref
+    rng = np.random.default_rng(4242)
+    shape = (300, 420)
+    wcs = SimpleCARWCS(shape, 0.5 / 60.0, crval=(52.0, -35.0))
+    n = 60
+    x = rng.uniform(-15, shape[1] + 15, n)
+    y = rng.uniform(-15, shape[0] + 15, n)
+    x[:4] = [0.3, shape[1] - 1.4, 200.5, 17.0]
+    y[:4] = [150.2, 40.0, shape[0] - 1.2, 0.1]
+    ra, dec = wcs.pix2wcs(x, y)
+    beam = signals_ref.gaussianBeam(1.4)
+    return {'shape': shape, 'wcs': wcs, 'beamRDeg': beam.rDeg, 'beamProfile': beam.profile1d,
+            'catalog': {'RADeg': np.asarray(ra), 'decDeg': np.asarray(dec), 'deltaT_c': rng.uniform(-400, 900, n), 'SNR': rng.uniform(2, 40, n)},
+            'validAreaSection': [30, 390, 20, 270], 'minSNR': 5.0}
+
+
+def writeBeamFile(path, rDeg, profile1d):
+    with open(path, 'w') as fh:
+        for r, p in zip(rDeg, profile1d):
+            fh.write("%.17g %.17g\n" % (r, p))
+
+
+def runPaint(tmpDir):
+    """maps.makeModelImage of the reference (nemo/maps.py:1734-1899), point-source branch: makeDegreesDistanceMap per source,
+    signals.makeBeamModelSignalMap, sum in catalog order, enmap.apply_window; once over the whole tile and once with
+    validAreaSection and a minSNR cut."""
+    from nemo_b200 import catalogs as hostTables
+    refMaps = importlib.import_module('nemo.maps')
+    refSignals = importlib.import_module('nemo.signals')
+    # BeamProfile also derives the beam transform with pixell's curvedsky (None in this fork, nemo/signals.py:125); the
+    # point-source painter never reads it
+    refSignals.curvedsky = types.SimpleNamespace(profile2harm=lambda prof, r: np.ones(2))
+    inp = paintInputs()
+    beamPath = os.path.join(tmpDir, 'beam_f150.txt')
+    writeBeamFile(beamPath, inp['beamRDeg'], inp['beamProfile'])
+    tab = hostTables.Table.fromColumns([(k, np.array(v)) for k, v in inp['catalog'].items()])
+
+    class AstWCSLike(type(inp['wcs'])):
+        """astWCS.WCS.wcs2pix returns a list of [x, y] pairs when given sequences (which is how catalogs.getCatalogWithinImage
+        and the validAreaSection cut index its result); the stub returns the two coordinate arrays."""
+
+        def wcs2pix(self, RADeg, decDeg):
+            x, y = super().wcs2pix(RADeg, decDeg)
+            return (x, y) if np.ndim(RADeg) == 0 else np.stack([np.asarray(x), np.asarray(y)], axis=1).tolist()
+    wcs = AstWCSLike(inp['shape'], inp['wcs'].pixDeg, crval=inp['wcs'].crval)
+    full = refMaps.makeModelImage(inp['shape'], wcs, tab, beamPath, applyPixelWindow=True)
+    noWindow = refMaps.makeModelImage(inp['shape'], wcs, tab, beamPath, applyPixelWindow=False)
+    cut = refMaps.makeModelImage(inp['shape'], wcs, tab, beamPath, applyPixelWindow=True,
+                                 validAreaSection=inp['validAreaSection'], minSNR=inp['minSNR'])
+    return {'paint_full': np.asarray(full), 'paint_noWindow': np.asarray(noWindow), 'paint_cut': np.asarray(cut)}
+
+
 def runBigCase(refFilters, refPhotometry, name, tmpDir):
     """A full-size case (big_cases.BIG_CASES) through the reference's filterMaps / getObjectPositions / findObjects / getSNRValues
     / measureFluxes in its loop order (nemo/pipelines.py:179-286), stored in compact form."""
@@ -304,6 +361,11 @@ def main():
     import make_golden
     refFilters, refPhotometry = loadReference()
     tmpDir = tempfile.mkdtemp()
+    paint = runPaint(tmpDir)
+    np.savez_compressed(os.path.join(HERE, 'ref_paint.npz'), **paint)
+    print("paint: maps.makeModelImage stored (%d non-zero pixels)" % int((paint['paint_full'] != 0).sum()))
+    if '--only-paint' in sys.argv:
+        return
     for name in make_golden.CASES:
         res = runCase(refFilters, refPhotometry, name, tmpDir)
         # compact: S/N and data as float64 (they are the contract), the filter as a checksum plus a few samples

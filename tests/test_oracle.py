@@ -310,3 +310,19 @@ def test_oracle_matches_full_size_reference_run(name):
                 assert np.array_equal(ref[k], out[k]), k
         if prefix + 'fRel' in ref.files:
             assert np.array_equal(ref[prefix + 'fRel'], out[prefix + 'fRel'])
+
+
+def test_model_image_painter_matches_reference_run():
+    """oracle/maps_ref.makeModelImage (point-source branch) against the reference's own maps.makeModelImage run on the same
+    catalog (tests/golden/ref_paint.npz): identical arrays, with and without the pixel window, validAreaSection and S/N cut."""
+    import make_reference_golden as gen
+    from oracle import maps_ref, signals_ref
+    inp = gen.paintInputs()
+    ref = np.load(os.path.join(HERE, 'golden', 'ref_paint.npz'))
+    beam = signals_ref.BeamProfile(profile1d=inp['beamProfile'], rDeg=inp['beamRDeg'])
+    assert np.array_equal(maps_ref.makeModelImage(inp['shape'], inp['wcs'], inp['catalog'], beam), ref['paint_full'])
+    assert np.array_equal(maps_ref.makeModelImage(inp['shape'], inp['wcs'], inp['catalog'], beam, applyPixelWindow=False), ref['paint_noWindow'])
+    assert np.array_equal(maps_ref.makeModelImage(inp['shape'], inp['wcs'], inp['catalog'], beam, validAreaSection=inp['validAreaSection'],
+                                                  minSNR=inp['minSNR']), ref['paint_cut'])
+    far = dict(inp['catalog'], RADeg=inp['catalog']['RADeg'] + 90.0)
+    assert maps_ref.makeModelImage(inp['shape'], inp['wcs'], far, beam) is None
