@@ -117,10 +117,10 @@ def _beamTimesWindow(ops, shape, wcs, beam, applyPixelWindow):
 
 
 def paintModelImages(ops, shape, wcsList, catalogList, beamList, obsFreqGHzList=None, GNFWParams='default', applyPixelWindow=True,
-                     override=None, validAreaSection=None, minSNR=-99, TCMBAlpha=0, base=None):
+                     override=None, validAreaSection=None, minSNR=-99, TCMBAlpha=0, base=None, out=None):
     """makeModelImage for a batch of images on the device: image i is painted on wcsList[i] from catalogList[i] with beam
     beamList[i] (and converted to delta T at obsFreqGHzList[i] for cluster catalogs).  Returns a device tensor [nImg, H, W]
-    (base + model when `base` [nImg, H, W] is given) and the number of objects painted per image."""
+    (base + model when `base` [nImg, H, W] is given; written to `out` when given) and the number of objects painted per image."""
     H, W = shape
     nImg = len(catalogList)
     rows, starts, profR, profV, profIndex = [], [0], [], [], {}
@@ -187,7 +187,8 @@ def paintModelImages(ops, shape, wcsList, catalogList, beamList, obsFreqGHzList=
             tabV[k, len(r) - 1:] = np.concatenate([[profV[k][-1]], np.zeros(nR - len(r))])
     objects = np.concatenate(rows, axis=0) if rows else np.zeros((0, 10))
     needPost = cluster or applyPixelWindow
-    model = ops.paint_objects((nImg, H, W), objects, np.array(starts, dtype=np.int32), tabR, tabV, base=None if needPost else base)
+    model = ops.paint_objects((nImg, H, W), objects, np.array(starts, dtype=np.int32), tabR, tabV, base=None if needPost else base,
+                              out=None if (needPost or out is None) else out.reshape(nImg, H, W))
     if cluster:
         # beam convolution on the periodic tile grid and the pixel window in one Fourier multiplication
         mult = ops.torch.stack([_beamTimesWindow(ops, shape, wcsList[i], signals._asBeam(beamList[i]), applyPixelWindow) for i in range(nImg)])
@@ -197,7 +198,10 @@ def paintModelImages(ops, shape, wcsList, catalogList, beamList, obsFreqGHzList=
     elif applyPixelWindow:
         model = ops.apply_window(model, 1.0, restoreZeros=False)
     if needPost and base is not None:
-        model = ops.add_maps(base, model)
+        model = ops.add_maps(base.reshape(nImg, H, W), model, out=None if out is None else out.reshape(nImg, H, W))
+    elif needPost and out is not None:
+        out.reshape(nImg, H, W).copy_(model)
+        model = out.reshape(nImg, H, W)
     return model, counts
 
 

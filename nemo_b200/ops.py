@@ -309,7 +309,7 @@ class Ops(object):
         self.launches += 1
         return area, total, miss
 
-    def paint_objects(self, shape, objects, objStart, profR, profV, base=None):
+    def paint_objects(self, shape, objects, objStart, profR, profV, base=None, out=None):
         """Model images [nImg, H, W]: objects [nObj, 10] fp64 (x0, y0, xPixScale, yPixScale, amplitude, minX, maxX, minY, maxY, profile
         index; host array or device tensor), objStart [nImg + 1] i32, profile tables profR / profV [nProf, nR] fp64; added to `base`
         [nImg, H, W] when given."""
@@ -325,19 +325,25 @@ class Ops(object):
             obj = self.zeros((1, 10), t.float64)
         if base is not None:
             self._check(base, self.dtype, 'base')
-        out = self.empty((nImg, H, W))
+        if out is None:
+            out = self.empty((nImg, H, W))
+        else:
+            self._check(out, self.dtype, 'out')
         _lib.call('nb_paint_objects', self.prec, _ptr(base), _ptr(out), int(nImg), int(H), int(W), _ptr(obj), _ptr(start), _ptr(pr), _ptr(pv),
                   int(pr.shape[0]), int(pr.shape[1]), self._stream())
         self.launches += 1
         return out
 
-    def add_maps(self, a, b):
+    def add_maps(self, a, b, out=None):
         """a + b, b broadcast over the leading axes of a (a model image per tile added to every frequency map of the tile...)."""
         self._check(a, self.dtype, 'a')
         self._check(b, self.dtype, 'b')
         if a.numel() % b.numel() != 0:
             raise _lib.NemoB200Error("add_maps: sizes %d and %d do not fit" % (a.numel(), b.numel()))
-        out = self.empty(tuple(a.shape))
+        if out is None:
+            out = self.empty(tuple(a.shape))
+        else:
+            self._check(out, self.dtype, 'out')
         _lib.call('nb_add_maps', self.prec, _ptr(a), _ptr(b), _ptr(out), int(a.numel()), int(b.numel()), self._stream())
         self.launches += 1
         return out

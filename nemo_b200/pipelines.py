@@ -127,6 +127,35 @@ class TileBatch(object):
                 for k in keys:
                     self.host[k][t, f] = torch.from_numpy(np.ascontiguousarray(m[k]))
 
+    def inject(self, catalogs, override=None, GNFWParams='default', applyPixelWindow=True, minSNR=-99, validAreaSection=None):
+        """The painter half of the source-injection loop on the device (maps.py:2093: mapDict['data'] = data + modelMap, with
+        modelMap = maps.makeModelImage(...) per frequency map): the tiles' maps stay resident as uploaded, a model image of
+        catalogs[tileName] is painted for every (tile, frequency) -- each map's own beam; cluster catalogs converted to delta T at
+        the map's frequency -- and their sum goes to a second resident buffer that the filter step then reads.  Nothing but the
+        catalogs crosses the host-device link.  catalogs: {tileName: catalog}; tiles without an entry get an unmodified copy."""
+        from . import maps
+        ops = self.ops
+        if self.dev is None:
+            self.upload()
+        if getattr(self, 'devOriginal', None) is None:
+            self.devOriginal = self.dev['data']
+            self.devInjected = ops.empty(tuple(self.devOriginal.shape))
+        nT, F, H, W = self.nT, self.F, self.H, self.W
+        empty = {'RADeg': np.zeros(0), 'decDeg': np.zeros(0), 'deltaT_c': np.zeros(0)}
+        wcsList, catList, beamList, freqList = [], [], [], []
+        for t, name in enumerate(self.tileNames):
+            for f in range(F):
+                m = self.mapDicts[t][f]
+                wcsList.append(self.wcsList[t])
+                catList.append(catalogs.get(name, empty))
+                beamList.append(m.get('beamFileName', m.get('beam')))
+                freqList.append(m.get('obsFreqGHz'))
+        _, counts = maps.paintModelImages(ops, (H, W), wcsList, catList, beamList, freqList, GNFWParams=GNFWParams,
+                                          applyPixelWindow=applyPixelWindow, override=override, validAreaSection=validAreaSection,
+                                          minSNR=minSNR, base=self.devOriginal.reshape(nT * F, H, W), out=self.devInjected)
+        self.dev['data'] = self.devInjected
+        return counts
+
     def upload(self):
         """Host (pinned) -> device copies of this batch's inputs; asynchronous on the current stream."""
         ops = self.ops
@@ -445,14 +474,19 @@ class BatchPipeline(object):
         self.graphs[key] = entry
         return entry
 
-    def submit(self, batch, upload=True, cache=None, templates=None):
+    def submit(self, batch, upload=True, cache=None, templates=None, prepare=None):
         """Queues the device work of `batch`; returns the (catalogDict, extras) of the oldest queued batch once more than
-        `depth` - 1 others are in flight behind it, else None."""
+        `depth` - 1 others are in flight behind it, else None.  prepare(batch): device work to queue on the slot's stream
+        before the batch itself (painting injected sources into its resident maps)."""
         from . import _lib
         torch = self.ops.torch
         slot = self.count % len(self.streams)
         st = self.streams[slot]
         self.count += 1
+        if prepare is not None:
+            with torch.cuda.stream(st):
+                prepare(batch)
+            upload = upload and batch.dev is None
         useGraph = self.useGraphs and not _lib.profEnabled()
         # with cached filters AND a cached RMS map nothing reads the weights (they only feed the noise estimate): a realisation of
         # the injection loop uploads its maps and masks, not the weight maps
@@ -497,7 +531,7 @@ class BatchPipeline(object):
 
 def processBatches(ops, batches, filtersList, templates, parDict, upload=True, undoPixelWindow=True, measureFluxes=True,
                    invertMap=False, keepMaps=False, caches=None, useCachedRMSMap=False, useGraphs=True, depth=2, rmsTables=False,
-                   beforeSubmit=None, collect=()):
+                   beforeSubmit=None, collect=(), prepare=None):
     """Runs several tile batches through a BatchPipeline; returns the list of (catalogDict, extras), one per batch, in order.
     caches: per-batch filter / RMS caches (see startTileBatch), or None.  templates: one FilterSetTemplates, or one per batch.
     beforeSubmit(batch): host work to do right before a batch is queued (re-staging its maps); it runs while the device
@@ -512,7 +546,7 @@ def processBatches(ops, batches, filtersList, templates, parDict, upload=True, u
         if beforeSubmit is not None:
             beforeSubmit(batch)
         out = pipe.submit(batch, upload=upload and batch.dev is None, cache=caches[i] if caches is not None else None,
-                          templates=templates[i] if perBatch else None)
+                          templates=templates[i] if perBatch else None, prepare=prepare)
         if out is not None:
             results.append(out)
     results.extend(pipe.flush())
@@ -747,7 +781,8 @@ def _batchBounds(numTiles, tilesPerBatch):
 
 def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=False, measureFluxes=True, invertMap=False,
                               verbose=True, tilesPerBatch=8, precision=None, comm=None, cacheFilters=False, restage=False,
-                              makeRMSTables=False, restageKeys=('data',), writeAreaMask=False, writeRMSMaps=False):
+                              makeRMSTables=False, restageKeys=('data',), writeAreaMask=False, writeRMSMaps=False,
+                              injectCatalogs=None, injectOptions=None):
     """Runs the map filtering and catalog construction steps for this rank's tiles and returns the optimal catalog
     (highest S/N detection across filter scales), gathered over ranks when `comm` (a
     ``nemo_b200.distributed.Comm``) is given -- pipelines.py:33-109, 112-354.
@@ -758,6 +793,11 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     re-reads the `restageKeys` arrays ('data'; 'weights') of the map dictionaries into the pinned staging buffers (they were
     edited in place or replaced since the tiles were staged), batch by batch, each right before it is queued so that the copy
     runs under the device work of the batches before it.
+
+    injectCatalogs = {tileName: catalog} paints model sources or clusters into the tiles ON THE DEVICE before they are filtered
+    (TileBatch.inject: the painter of the source-injection loop, maps.py:1734-1899, 2093) -- the maps stay resident from one
+    call to the next and only the catalogs travel; injectOptions: override / GNFWParams / minSNR / validAreaSection /
+    applyPixelWindow of makeModelImage.  An empty dict restores the original maps.
 
     writeAreaMask / writeRMSMaps (need ``config.selFnDir``): this rank's ``areaMask.fits`` (one extension per tile; with several
     ranks ``areaMask_rank<r>.fits``) and ``<tile>/RMSMap_<filter>#<tile>.fits`` of the first filter of the list (the photFilter when
@@ -795,6 +835,12 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     else:
         batches = staged['batches']
     beforeSubmit = (lambda b: b.refresh(config.tileMaps, keys=restageKeys)) if restage else None
+    prepare = None
+    if injectCatalogs is not None:
+        if restage:
+            raise Exception("injectCatalogs paints into the maps resident on the device; restage re-uploads them -- use one or the other")
+        opts = dict(injectOptions or {})
+        prepare = lambda b: b.inject(injectCatalogs, **opts)
     templatesList = [templatesFor(config, ops, filtersList, b) for b in batches]
     templates = templatesList[0]
     if verbose:
@@ -810,7 +856,7 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     results = processBatches(ops, batches, filtersList, templatesList, parDict, upload=True,
                              undoPixelWindow=parDict.get('undoPixelWindow', True), measureFluxes=measureFluxes, invertMap=invertMap,
                              keepMaps=cacheFilters, caches=caches, useCachedRMSMap=useCachedRMSMap, rmsTables=makeRMSTables,
-                             beforeSubmit=beforeSubmit,
+                             beforeSubmit=beforeSubmit, prepare=prepare,
                              collect=(('areaMask',) if writeAreaMask else ()) + (('RMSMap',) if writeRMSMaps else ()))
     if writeAreaMask or writeRMSMaps:
         _writeSelFnMaps(config, batches, results, filtersList[0]['label'], comm)

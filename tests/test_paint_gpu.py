@@ -100,3 +100,57 @@ def test_cluster_model_image_matches_oracle_painter(report):
         err = np.abs(got - ref).max() / np.abs(ref).max()
         report("paint_clusters_oracle", override=int(bool(kw)), relerr=err)
         assert err < 1e-11
+
+
+def test_device_injection_equals_host_injection(report):
+    """The source-injection loop (maps.py:2093) both ways: models painted by the oracle into the host maps, re-staged and
+    re-filtered with the cached filters and RMS maps -- and the same catalogs handed to the driver, which paints them into the
+    resident maps on the device (TileBatch.inject).  Same recovered catalogs; a second realisation starts from the original maps
+    again, and an empty dict restores them."""
+    from oracle import synth, maps_ref, signals_ref
+    from nemo_b200 import pipelines
+    tileMaps = {}
+    for t in range(3):
+        md, _ = synth.makeTile(shape=(256, 320), numObjects=3, kind='sources', seed=500 + t, freqsGHz=(148.0,), noiseUK=(80.0,))
+        tileMaps['tile%d' % t] = md
+    f = {'label': 'Beam', 'class': 'BeamMatchedFilter',
+         'params': {'noiseParams': {'method': 'dataMap', 'noiseGridArcmin': 20.}, 'outputUnits': 'uK', 'edgeTrimArcmin': 0.}}
+    parDict = {'mapFilters': [f], 'photFilter': 'Beam', 'thresholdSigma': 5.0, 'minObjPix': 1, 'rejectBorder': 0}
+    config = pipelines.SimpleConfig(parDict, tileMaps)
+    pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=2, cacheFilters=True)
+    original = {k: md[0]['data'].copy() for k, md in tileMaps.items()}
+    rng = np.random.default_rng(77)
+    keys = ['RADeg', 'decDeg', 'SNR', 'deltaT_c', 'x', 'y']
+
+    def realisation():
+        cats = {}
+        for k, md in tileMaps.items():
+            x, y = rng.uniform(40, 280, 12), rng.uniform(40, 216, 12)
+            ra, dec = md[0]['wcs'].pix2wcs(x, y)
+            cats[k] = {'RADeg': np.asarray(ra), 'decDeg': np.asarray(dec), 'deltaT_c': rng.uniform(900, 2500, 12)}
+        return cats
+    for it in range(2):
+        cats = realisation()
+        got = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=2, useCachedFilters=True, useCachedRMSMap=True,
+                                                  injectCatalogs=cats)
+        for k, md in tileMaps.items():
+            beam = md[0]['beamFileName']
+            ob = signals_ref.BeamProfile(profile1d=beam.profile1d, rDeg=beam.rDeg)
+            md[0]['data'] = original[k] + maps_ref.makeModelImage(original[k].shape, md[0]['wcs'], cats[k], ob)
+        want = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=2, useCachedFilters=True, useCachedRMSMap=True,
+                                                   restage=True)
+        for b in config._staged['batches']:       # the re-staged upload replaced the resident maps: drop them for the next round
+            b.dev, b.devOriginal = None, None
+        assert len(got) == len(want) >= 30
+        for key in keys:
+            np.testing.assert_allclose(np.asarray(got[key], dtype=float), np.asarray(want[key], dtype=float), rtol=1e-9, atol=1e-9, err_msg=key)
+        report("device_injection", realisation=it, rows=len(got))
+    for k, md in tileMaps.items():
+        md[0]['data'] = original[k]
+    plain = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=2, useCachedFilters=True, useCachedRMSMap=True, restage=True)
+    for b in config._staged['batches']:
+        b.dev, b.devOriginal = None, None
+    restored = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=2, useCachedFilters=True, useCachedRMSMap=True,
+                                                   injectCatalogs={})
+    assert len(restored) == len(plain)
+    np.testing.assert_allclose(np.asarray(restored['SNR'], dtype=float), np.asarray(plain['SNR'], dtype=float), rtol=1e-12)

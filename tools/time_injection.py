@@ -42,8 +42,9 @@ for _ in range(n):
     torch.cuda.synchronize(); t2 = time.perf_counter()
     tInject += t1 - t0; tStage += ts - t1; tRun += t2 - ts
 mpix = nT * 1024 * 1024 / 1e6
-print("per realisation, %d tiles: host copy into the pinned buffers %.2f ms; upload + re-filter + detect + catalogs %.2f ms = %.0f Mpix/s; %d rows"
-      % (nT, tStage / n * 1e3, tRun / n * 1e3, mpix / (tRun / n), len(cat)))
+print("host painter: per realisation, %d tiles: painting on the host %.2f ms; host copy into the pinned buffers %.2f ms; upload + re-filter + detect + "
+      "catalogs %.2f ms; %.2f ms in all = %.0f Mpix/s; %d rows"
+      % (nT, tInject / n * 1e3, tStage / n * 1e3, tRun / n * 1e3, (tInject + tStage + tRun) / n * 1e3, mpix / ((tInject + tStage + tRun) / n), len(cat)))
 if os.environ.get('PROFILE'):
     import cProfile, pstats, io
     pr = cProfile.Profile(); pr.enable()
@@ -51,3 +52,31 @@ if os.environ.get('PROFILE'):
         cat = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=4, useCachedFilters=True, useCachedRMSMap=True)
     torch.cuda.synchronize(); pr.disable()
     s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats('cumulative').print_stats(28); print(s.getvalue()[:5000])
+
+# ---- the same loop with the painter on the device: maps resident, only the catalogs travel ---------------------------------
+for b in batches:
+    b.dev, b.devOriginal = None, None
+for k, md in tileMaps.items():
+    np.copyto(md[0]['data'], original[k])
+def mockCatalogs():
+    cats = {}
+    for k, md in tileMaps.items():
+        ra, dec = md[0]['wcs'].pix2wcs(rng.uniform(100, 900, 50), rng.uniform(100, 900, 50))
+        cats[k] = {'RADeg': np.asarray(ra), 'decDeg': np.asarray(dec), 'deltaT_c': rng.uniform(300, 900, 50)}
+    return cats
+for _ in range(3):
+    pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=4, useCachedFilters=True, useCachedRMSMap=True, injectCatalogs=mockCatalogs())
+torch.cuda.synchronize()
+N = int(os.environ.get('REALISATIONS', 100))
+from nemo_b200 import device
+device.TRAFFIC['h2d'] = device.TRAFFIC['d2h'] = 0
+t0 = time.perf_counter()
+rows = 0
+for _ in range(N):
+    cat = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=4, useCachedFilters=True, useCachedRMSMap=True,
+                                              injectCatalogs=mockCatalogs())
+    rows += len(cat)
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / N
+print("device painter: %d realisations x %d tiles, %.2f ms per realisation = %.0f Mpix/s; %.1f kB host-to-device and %.1f kB device-to-host per "
+      "realisation; %d rows per realisation" % (N, nT, dt * 1e3, mpix / dt, device.TRAFFIC['h2d'] / N / 1e3, device.TRAFFIC['d2h'] / N / 1e3, rows // N))
