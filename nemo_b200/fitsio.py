@@ -261,3 +261,52 @@ def saveFITS(outputFileName, mapData, wcs, compressionType=None, version=None):
     if compressionType is not None:
         arr = np.array(arr, dtype=np.uint8 if compressionType == 'PLIO_1' else np.float32)
     writeImage(outputFileName, arr, header)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Binary tables of float64 columns: the QFit.fits file of signals.fitQ (nemo/signals.py:1086-1117: one table per tile with columns
+# Q, theta500Arcmin, z, as astropy's table_to_hdu writes them)
+def writeTableMEF(path, tables):
+    """tables: list of (extName, {column name: 1-d array}, header dict).  Every column is written as float64 (TFORM 'D')."""
+    if os.path.exists(path):
+        os.remove(path)
+    with open(path, 'wb') as fh:
+        head = ''.join([_card('SIMPLE', True, 'conforms to FITS standard'), _card('BITPIX', 8), _card('NAXIS', 0), _card('EXTEND', True),
+                        'END'.ljust(80)]).encode('ascii')
+        fh.write(head + b' ' * (-len(head) % BLOCK))
+        for extName, cols, header in tables:
+            names = list(cols.keys())
+            arrs = [np.asarray(cols[k], dtype=np.float64).ravel() for k in names]
+            n = len(arrs[0]) if arrs else 0
+            if any(len(a) != n for a in arrs):
+                raise ValueError("columns of table %s differ in length" % extName)
+            cards = [_card('XTENSION', 'BINTABLE', 'binary table extension'), _card('BITPIX', 8), _card('NAXIS', 2),
+                     _card('NAXIS1', 8 * len(names), 'length of dimension 1'), _card('NAXIS2', n, 'length of dimension 2'),
+                     _card('PCOUNT', 0), _card('GCOUNT', 1), _card('TFIELDS', len(names)), _card('EXTNAME', extName)]
+            for i, k in enumerate(names, start=1):
+                cards += [_card('TTYPE%d' % i, k), _card('TFORM%d' % i, 'D')]
+            for key, value in _headerItems(header):
+                cards.append(_card(key, value))
+            cards.append('END'.ljust(80))
+            head = ''.join(cards).encode('ascii')
+            fh.write(head + b' ' * (-len(head) % BLOCK))
+            body = np.ascontiguousarray(np.stack(arrs, axis=1) if names else np.zeros((0, 0)), dtype='>f8').tobytes()
+            fh.write(body)
+            fh.write(b'\0' * (-len(body) % BLOCK))
+
+
+def readTable(path, extName):
+    """({column: float64 array}, header) of the binary-table extension named `extName` (columns of TFORM 'D' only)."""
+    with open(path, 'rb') as fh:
+        while True:
+            header, _ = _readHeader(fh)
+            if header is None:
+                raise OSError("no table '%s' in %s" % (extName, path))
+            nBytes, _ = _dataBytes(header)
+            if str(header.get('XTENSION', '')).strip() == 'BINTABLE' and str(header.get('EXTNAME', '')).strip() == extName:
+                nCols, nRows = int(header['TFIELDS']), int(header['NAXIS2'])
+                if any(str(header['TFORM%d' % i]).strip() not in ('D', '1D') for i in range(1, nCols + 1)):
+                    raise OSError("table '%s' has columns that are not float64" % extName)
+                raw = np.frombuffer(fh.read(8 * nCols * nRows), dtype='>f8').reshape(nRows, nCols)
+                return {str(header['TTYPE%d' % i]).strip(): raw[:, i - 1].astype(np.float64) for i in range(1, nCols + 1)}, header
+            fh.seek(nBytes + (-nBytes % BLOCK), 1)

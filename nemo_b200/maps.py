@@ -117,10 +117,12 @@ def _beamTimesWindow(ops, shape, wcs, beam, applyPixelWindow):
 
 
 def paintModelImages(ops, shape, wcsList, catalogList, beamList, obsFreqGHzList=None, GNFWParams='default', applyPixelWindow=True,
-                     override=None, validAreaSection=None, minSNR=-99, TCMBAlpha=0, base=None, out=None):
+                     override=None, validAreaSection=None, minSNR=-99, TCMBAlpha=0, base=None, out=None, maxSizeDeg=None):
     """makeModelImage for a batch of images on the device: image i is painted on wcsList[i] from catalogList[i] with beam
     beamList[i] (and converted to delta T at obsFreqGHzList[i] for cluster catalogs).  Returns a device tensor [nImg, H, W]
-    (base + model when `base` [nImg, H, W] is given; written to `out` when given) and the number of objects painted per image."""
+    (base + model when `base` [nImg, H, W] is given; written to `out` when given) and the number of objects painted per image.
+    maxSizeDeg: paint clusters out to this radius instead of makeModelImage's 5 theta500 (signals.makeArnaudModelSignalMap's own
+    default is 15 degrees, which is what the filter templates and signals.fitQ use)."""
     H, W = shape
     nImg = len(catalogList)
     rows, starts, profR, profV, profIndex = [], [0], [], [], {}
@@ -155,7 +157,7 @@ def paintModelImages(ops, shape, wcsList, catalogList, beamList, obsFreqGHzList=
                 key = ('A10', float(zs[j]), float(Ms[j]), repr(GNFWParams))
                 if key not in profIndex:
                     prof = signals.makeArnaudModelProfile(zs[j], Ms[j], GNFWParams=GNFWParams)
-                    size = 5 * (prof['theta500Arcmin'] / 60)
+                    size = 5 * (prof['theta500Arcmin'] / 60) if maxSizeDeg is None else float(maxSizeDeg)
                     rDeg = np.linspace(0.0, size, 5000)
                     profIndex[key] = (len(profR), size)
                     profR.append(rDeg)

@@ -890,3 +890,103 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     config.noiseTables = noiseTables
     config.RMSTabs = RMSTabs      # {'<label>#<tileName>': (y0RMS ascending, areaDeg2)} -- completeness.getRMSTab per tile and filter
     return optimalCatalog
+
+
+# ------------------------------------------------------------------------------------------------------
+def fitQ(config, precision=None, tilesPerBatch=4, verbose=False, y0=2e-04, scales=None):
+    """signals.fitQ (nemo/signals.py:864-1125) for this rank's tiles: model clusters of ~55 angular sizes are painted at the tile
+    centre (beam-convolved, pixel window applied), filtered with the tile's reference (photFilter) filter, and the peak of the
+    filtered signal -- a bicubic spline at the centre -- relative to the input y0 is Q(theta500).  Everything per-pixel runs on
+    the device: the painter (nb_paint_objects + one Fourier multiplication for beam and window), K1 on the models, K2/K3/K5 for
+    the tile's filter, K4 for every (tile, size), and the spline of K5.  Model spectra are shared by the tiles of one geometry.
+
+    Returns {tileName: Table with columns Q, theta500Arcmin, z, sorted by theta500Arcmin}; with ``config.selFnDir`` set the
+    tables are also written to ``selFnDir/QFit.fits`` as one binary-table extension per tile with ZDEPQ / TILENAME keywords,
+    the layout the reference writes (:1086-1117) and signals.QFit reads.  scales: (zRange, MRange) to use instead of
+    signals.fitQScales -- the reference scale must come first."""
+    import os
+    ops = device.getOps(precision)
+    torch = ops.torch
+    parDict = config.parDict
+    ref = None
+    for f in parDict['mapFilters']:
+        if f['label'] == parDict.get('photFilter'):
+            ref = f
+    if ref is None:
+        raise Exception("couldn't find filter that matches photFilter")
+    className = ref['class'] if isinstance(ref['class'], str) else ref['class'].__name__
+    if className.find("Arnaud") == -1:
+        raise Exception("Signal model for Q calculation should be 'Arnaud' ('Battaglia' needs pyccl)")
+    if className.find("RealSpace") != -1:
+        raise Exception("fitQ with a real-space reference filter goes through the class API (filters.RealSpaceMatchedFilter.applyFilter)")
+    refEntry = {'label': ref['label'], 'class': ref['class'], 'params': dict(ref['params'])}
+    zRange, MRange = scales if scales is not None else signals.fitQScales(ref['params']['M500MSun'], ref['params']['z'])
+    nS = len(zRange)
+    GNFWParams = ref['params'].get('GNFWParams', parDict.get('GNFWParams', 'default'))
+    staged = stageTiles(config, tilesPerBatch, precision)
+    QTabDict = {}
+    spectraByGeometry = {}
+    for batch in staged:
+        nT, F, H, W = batch.nT, batch.F, batch.H, batch.W
+        Wc = W // 2 + 1
+        templates = templatesFor(config, ops, [refEntry], batch)
+        dev = batch.dev if batch.dev is not None else batch.upload()
+        md0 = batch.mapDicts[0]
+        # model spectra of every size and frequency, once per geometry (signals.py:1029-1055: makeSignalModelMap at the tile
+        # centre with amplitude y0 -> delta T, beam-convolved, enmap.apply_window, enmap.fft)
+        key = (batch.geometry, _beamsKey(md0), repr(GNFWParams), nS, float(MRange[-1]))
+        if key not in spectraByGeometry:
+            wcs0 = batch.wcsList[0]
+            ra0, dec0 = wcs0.getCentreWCSCoords()
+            wcsList, cats, beams, freqs = [], [], [], []
+            for z, M in zip(zRange, MRange):
+                for m in md0:
+                    wcsList.append(wcs0)
+                    cats.append({'RADeg': np.array([ra0]), 'decDeg': np.array([dec0]), 'true_y_c': np.array([y0 / 1e-4]),
+                                 'true_M500c': np.array([M / 1e14]), 'redshift': np.array([z])})
+                    beams.append(m['beamFileName'])
+                    freqs.append(None if m.get('units') == 'yc' else m['obsFreqGHz'])
+            model, _ = maps.paintModelImages(ops, (H, W), wcsList, cats, beams, freqs, GNFWParams=GNFWParams, applyPixelWindow=True,
+                                              maxSizeDeg=15.0)
+            spectraByGeometry[key] = ops.rfft2(model, apodPix=0).reshape(nS, F, H, Wc)
+            del model
+        spectra = spectraByGeometry[key]
+        # the tiles' reference filters (filters.py:524-696), then every size through every tile's filter
+        params0 = refEntry['params']
+        bck = None
+        if 'bckSub' in params0.keys() and 'bckSubScaleArcmin' in params0.keys() and params0['bckSub'] == True:
+            bck = maps.smoothScalesPix(batch.wcsList[0], smoothScaleDeg=params0['bckSubScaleArcmin'] / 60.)
+        fmaps = ops.rfft2(dev['data'].reshape(nT * F, H, W), apodPix=20).reshape(nT, F, H, Wc)
+        res = engine.buildFourierFilters(ops, fmaps, templates.unit, templates.norm, templates.w, templates.outputUnits,
+                                         templates.cy, templates.cx, bckSubSigmas=bck)
+        del fmaps
+        for t, tileName in enumerate(batch.tileNames):
+            filt = res['filtH'][t].unsqueeze(0).expand(nS, F, H, Wc).contiguous()
+            norm = res['signalNorm'][t].reshape(1).expand(nS).contiguous()
+            filtered = engine.applyFourierFilters(ops, spectra, filt, 1, norm, None, bckSubSigmas=bck, W=W)
+            _, _, _, centre = ops.template_norm(filtered, 1, templates.cy, templates.cx, 1.0)
+            peak = device.toHost(centre)
+            del filt, filtered
+            Q, theta, zs = [], [], []
+            for v, z, M in zip(peak, zRange, MRange):
+                if v not in Q:                        # signals.py:1068
+                    Q.append(float(v))
+                    theta.append(signals.calcTheta500Arcmin(z, M))
+                    zs.append(z)
+            Q = np.array(Q)
+            if abs(1 - Q[0] / y0) > 1e-6:
+                raise Exception("Q[0]/y0 outside tolerance")
+            Q = Q / y0
+            order = np.argsort(np.array(theta), kind='stable')
+            QTabDict[tileName] = catalogs.Table.fromColumns([('Q', Q[order]), ('theta500Arcmin', np.array(theta)[order]),
+                                                             ('z', np.array(zs)[order])])
+            if verbose:
+                print("... fitted Q in tile %s" % (tileName))
+    selFnDir = getattr(config, 'selFnDir', None)
+    if selFnDir is not None:
+        from . import fitsio
+        os.makedirs(selFnDir, exist_ok=True)
+        fitsio.writeTableMEF(selFnDir + os.path.sep + "QFit.fits",
+                             [(name, {k: np.asarray(tab[k]) for k in ('Q', 'theta500Arcmin', 'z')}, {'NEMOVER': 'nemo_b200', 'ZDEPQ': 0, 'TILENAME': name})
+                              for name, tab in QTabDict.items()])
+    return QTabDict

@@ -161,3 +161,34 @@ def makeArnaudModelSignalMap(z, M500, degreesMap, wcs, beam=None, GNFWParams='de
         beamMap = beamMap / beamMap.sum()
         signalMap = np.fft.ifft2(np.fft.fft2(signalMap) * np.fft.fft2(np.fft.ifftshift(beamMap))).real
     return signalMap
+
+
+# ------------------------------------------------------------------------------------------------------
+# Filter mismatch function Q (reference nemo/signals.py:864-1125 fitQ)
+def calcM500FromTheta500Arcmin(theta500Arcmin, z, Om0=0.3, H0=70.0):
+    """M500 (MSun) of a cluster of angular size theta500 at redshift z: the inverse of calcTheta500Arcmin, as signals.fitQ does it
+    (signals.py:907-912: R500 = tan(theta500) D_A, M500 = 4/3 pi R500^3 500 rho_crit(z))."""
+    G = 4.30091e-9  # Mpc (km/s)^2 / MSun
+    Ez = np.sqrt(Om0 * (1 + z) ** 3 + (1 - Om0))
+    rhoCrit = 3 * (H0 * Ez) ** 2 / (8 * np.pi * G)
+    DC = integrate.quad(lambda zz: 1.0 / np.sqrt(Om0 * (1 + zz) ** 3 + (1 - Om0)), 0, z)[0] * (_C_LIGHT / 1e3) / H0
+    R500Mpc = np.tan(np.radians(theta500Arcmin / 60.0)) * (DC / (1 + z))
+    return (4 / 3.0) * np.pi * R500Mpc ** 3 * 500 * rhoCrit
+
+
+def fitQScales(refM500MSun, refz):
+    """(zRange, MRange) of the scales signals.fitQ filters for an Arnaud-profile reference filter (no redshift dependence of the
+    profile shape, zDepQ = 0; signals.py:898-915): the reference scale first, then 54 sizes from 0.1' to 50' at log spacing
+    0.05055349, each at a redshift that keeps the mass sensible."""
+    theta500Arcmin_wanted = np.power(10, np.arange(np.log10(0.1), np.log10(50), 0.05055349))
+    zRange_wanted = [2.0] * 10 + [1.0] * 10 + [0.6] * 10 + [0.3] * 10 + [0.1] * 10 + [0.07] * 4
+    MRange = [refM500MSun] + [calcM500FromTheta500Arcmin(t, z) for t, z in zip(theta500Arcmin_wanted, zRange_wanted)]
+    zRange = [refz] + zRange_wanted[:len(theta500Arcmin_wanted)]
+    return zRange, MRange
+
+
+def fitQ(config, **kwargs):
+    """The filter mismatch function Q on a grid of cluster sizes for every tile (signals.py:864-1125); see
+    nemo_b200.pipelines.fitQ, which runs it on the GPU."""
+    from . import pipelines
+    return pipelines.fitQ(config, **kwargs)

@@ -166,3 +166,63 @@ def makeArnaudModelProfile(z, M500, GNFWParams='default'):
     thetaDegRange = bRange * (theta500Arcmin / 60.)
     tckP = interpolate.splrep(thetaDegRange, cylPProfile)
     return {'tckP': tckP, 'theta500Arcmin': theta500Arcmin, 'rDeg': thetaDegRange}
+
+
+# ------------------------------------------------------------------------------------------------------
+# signals.fitQ (nemo/signals.py:864-1125), Arnaud profile (zDepQ = 0)
+def calcM500FromTheta500Arcmin(theta500Arcmin, z, Om0=0.3, H0=70.0):
+    """signals.py:907-912 with the flat LCDM of calcTheta500Arcmin above instead of pyccl."""
+    from scipy import integrate
+    G = 4.30091e-9
+    Ez = np.sqrt(Om0 * (1 + z) ** 3 + (1 - Om0))
+    rhoCrit = 3 * (H0 * Ez) ** 2 / (8 * np.pi * G)
+    DC = integrate.quad(lambda zz: 1.0 / np.sqrt(Om0 * (1 + zz) ** 3 + (1 - Om0)), 0, z)[0] * (299792458.0 / 1e3) / H0
+    R500Mpc = np.tan(np.radians(theta500Arcmin / 60.0)) * (DC / (1 + z))
+    return (4 / 3.0) * np.pi * R500Mpc ** 3 * 500 * rhoCrit
+
+
+def fitQScales(refM500MSun, refz):
+    """signals.py:898-915."""
+    theta500Arcmin_wanted = np.power(10, np.arange(np.log10(0.1), np.log10(50), 0.05055349))
+    zRange_wanted = [2.0] * 10 + [1.0] * 10 + [0.6] * 10 + [0.3] * 10 + [0.1] * 10 + [0.07] * 4
+    MRange = [refM500MSun]
+    zRange = [refz]
+    for theta500Arcmin, z in zip(theta500Arcmin_wanted, zRange_wanted):
+        MRange.append(calcM500FromTheta500Arcmin(theta500Arcmin, z))
+        zRange.append(z)
+    return zRange, MRange
+
+
+def fitQTile(filterObj, mapDicts, zRange, MRange, y0=2e-04):
+    """The per-tile body of signals.fitQ (signals.py:1029-1083) for a Fourier-space reference filter object of
+    oracle/filters_ref.py (already built: filt and signalNorm set): (Q, theta500Arcmin, z) sorted by theta500Arcmin."""
+    import copy
+    from scipy import interpolate as _interp
+    from . import pixell_shim as enmap
+    wcs = filterObj.wcs
+    RADeg, decDeg = wcs.getCentreWCSCoords()
+    x, y = wcs.wcs2pix(RADeg, decDeg)
+    Q, QTheta500Arcmin, Qz = [], [], []
+    for z, M500MSun in zip(zRange, MRange):
+        painter = copy.copy(filterObj)                 # same geometry, beam handling and painter; another cluster size
+        painter.params = dict(filterObj.params, z=z, M500MSun=M500MSun)
+        signalMaps = []
+        for mapDict in mapDicts:
+            amplitude = convertToDeltaT(y0, mapDict['obsFreqGHz']) if mapDict.get('units') != 'yc' else y0
+            signalMap = painter.makeSignalTemplateMap(mapDict['beamFileName'], amplitude=amplitude)
+            signalMap = enmap.apply_window(signalMap, pow=1.0)
+            signalMaps.append(enmap.fft(signalMap))
+        filteredSignal = filterObj.applyFilter(np.array(signalMaps))
+        mapInterpolator = _interp.RectBivariateSpline(np.arange(filteredSignal.shape[0]), np.arange(filteredSignal.shape[1]),
+                                                      filteredSignal, kx=3, ky=3)
+        peakFilteredSignal = mapInterpolator(y, x)[0][0]
+        if peakFilteredSignal not in Q:
+            Q.append(peakFilteredSignal)
+            QTheta500Arcmin.append(calcTheta500Arcmin(z, M500MSun))
+            Qz.append(z)
+    Q = np.array(Q)
+    if abs(1 - Q[0] / y0) > 1e-6:
+        raise Exception("Q[0]/y0 outside tolerance")
+    Q = Q / y0
+    order = np.argsort(np.array(QTheta500Arcmin), kind='stable')
+    return Q[order], np.array(QTheta500Arcmin)[order], np.array(Qz)[order]
