@@ -15,8 +15,8 @@ Differences a caller can see:
   * filter caches, RMS maps and area masks are FITS files in the reference's layout, written and read by ``nemo_b200.fitsio``
     (astropy is not needed; tile compression is not implemented, the images are plain HDUs of the same pixel type);
   * options whose dependencies are absent raise instead of silently differing: noise methods ``model`` and
-    ``max(dataMap,CMB)``, ``noiseModelCatalog``, ``RMSEstimator`` biweight,
-    ``reshapeFilter``; tile sides must lie in 64..4096 (sides that are not powers of two take mixed-radix passes when
+    ``max(dataMap,CMB)``, ``noiseModelCatalog``, ``RMSEstimator`` biweight;
+    tile sides must lie in 64..4096 (sides that are not powers of two take mixed-radix passes when
     their prime factors are 2, 3, 5, 7, the slower Bluestein passes otherwise -- odd sides included).
 """
 
@@ -391,19 +391,50 @@ class MatchedFilter(MapFilter):
         self.loadFilter()
 
     def reshapeFilter(self, shape):
-        raise Exception("reshapeFilter needs pixell.enmap.laxes and is not implemented in nemo_b200; "
-                        "apply the filter to maps with the shape it was built for")
+        """The filter on the Fourier grid of a map of another shape with the same pixel scales (filters.py:797-821): linear
+        interpolation in (l_y, l_x), l = 2 pi fftfreq(n, d = pixel size in radians) along each axis (pixell's enmap.laxes).
+
+        The reference does this with scipy's interp1d (multipole -> fractional index of the old grid) and interp2d, which SciPy
+        1.14 removed; its index map also interpolates across the jump between the last negative multipole and zero.  Here the
+        multipole axes are put in ascending order first, so every output mode is interpolated between its two neighbours in l
+        along each axis; beyond the old grid's largest |l| the edge value is used."""
+        if len(shape) == 2:
+            shape = [np.asarray(self.filt).shape[0], shape[0], shape[1]]
+        assert (len(shape) == 3)
+        filt = np.asarray(self.filt, dtype=np.float64)
+        F, H, W = filt.shape
+
+        def axisWeights(nOld, nNew, degPerPix):
+            d = np.radians(degPerPix)
+            lOld, lNew = 2 * np.pi * fft.fftfreq(nOld, d=d), 2 * np.pi * fft.fftfreq(nNew, d=d)
+            order = np.argsort(lOld, kind='stable')
+            pos = np.interp(lNew, lOld[order], np.arange(nOld, dtype=np.float64))       # clamps beyond the ends
+            lo = np.minimum(np.floor(pos).astype(int), nOld - 2) if nOld > 1 else np.zeros(nNew, dtype=int)
+            frac = pos - lo
+            return order[lo], order[np.minimum(lo + 1, nOld - 1)], frac
+        y0, y1, fy = axisWeights(H, shape[1], self.degPerPixY)
+        x0, x1, fx = axisWeights(W, shape[2], self.degPerPixX)
+        reshapedFilt = np.zeros(shape)
+        for i in range(F):
+            top = filt[i][y0][:, x0] * (1 - fx)[None, :] + filt[i][y0][:, x1] * fx[None, :]
+            bottom = filt[i][y1][:, x0] * (1 - fx)[None, :] + filt[i][y1][:, x1] * fx[None, :]
+            reshapedFilt[i] = top * (1 - fy)[:, None] + bottom * fy[:, None]
+        return reshapedFilt
 
     def applyFilter(self, mapDataToFilter):
         """Applies the filter to a cube [F, H, W]: real maps are apodised and transformed first; complex input is
-        taken as the full-plane FFT of real maps (filters.py:824-859).  Returns a numpy array."""
+        taken as the full-plane FFT of real maps (filters.py:824-859).  Maps of another shape than the filter's get the filter
+        interpolated onto their Fourier grid (reshapeFilter).  Returns a numpy array."""
         ops = self.ops
         F = len(self.unfilteredMapsDictList)
         H, W = self.shape
         if isinstance(mapDataToFilter, DeviceArray):
             mapDataToFilter = mapDataToFilter.tensor
+        filtHT = self._filtHT
         if tuple(mapDataToFilter.shape) != (F, H, W):
-            self.reshapeFilter(mapDataToFilter.shape)
+            reshaped = self.reshapeFilter(tuple(mapDataToFilter.shape))
+            H, W = reshaped.shape[1:]
+            filtHT = ops.fold_filter(ops.to_device(reshaped[None], ops.torch.float64))
         isTensor = hasattr(mapDataToFilter, 'data_ptr')
         if not isTensor and 'complex' in np.asarray(mapDataToFilter).dtype.name:
             half = np.ascontiguousarray(np.asarray(mapDataToFilter)[:, :, :W // 2 + 1])
@@ -412,7 +443,7 @@ class MatchedFilter(MapFilter):
             fMaps = ops.rfft2(device.asTensor(mapDataToFilter, ops).reshape(F, H, W).contiguous(),
                               apodPix=self.apodPix).reshape(1, F, H, W // 2 + 1)
         normT = ops.to_device(np.array([self.signalNorm], dtype=np.float64), ops.torch.float64)
-        out = engine.applyFourierFilters(ops, fMaps, self._filtHT, 1, normT, None, bckSubSigmas=self._bckSubSigmas(), W=W)
+        out = engine.applyFourierFilters(ops, fMaps, filtHT, 1, normT, None, bckSubSigmas=self._bckSubSigmas(), W=W)
         return out[0].cpu().numpy()
 
 

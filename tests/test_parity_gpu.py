@@ -193,6 +193,38 @@ def test_files_are_written_in_the_reference_layout(tmp_path, report):
     report("reference_layout_files", ok=1)
 
 
+def test_reshape_filter_and_apply_to_another_shape(report):
+    """reshapeFilter (filters.py:797-821): onto its own grid it is the identity; onto a grid twice as fine in l_x it
+    interpolates linearly between neighbouring modes; applyFilter on a map of another shape uses it (filters.py:843-844), and
+    for a filter that is smooth in l the result agrees with filtering at the original shape where the two maps overlap."""
+    from nemo_b200 import filters
+    mapDicts, truth = synth.makeTile(shape=(128, 160), numObjects=3, kind='clusters', seed=31)
+    got, obj = filters.filterMaps(mapDicts, _copyFilter(_arnaud(grid=20.)), 'T0', verbose=False, returnFilter=True)
+    filt = np.asarray(obj.filt)
+    assert np.array_equal(obj.reshapeFilter(filt.shape), filt) and np.array_equal(obj.reshapeFilter(filt.shape[1:]), filt)
+    wide = obj.reshapeFilter((1, 128, 320))
+    assert wide.shape == (1, 128, 320)
+    assert np.allclose(wide[0][:, 0:160:2], filt[0][:, 0:80], rtol=0, atol=1e-12 * np.abs(filt).max())          # the shared modes
+    assert np.allclose(wide[0][:, 1:159:2], 0.5 * (filt[0][:, 0:79] + filt[0][:, 1:80]), rtol=0, atol=1e-12 * np.abs(filt).max())
+    # a smooth filter: a Gaussian low-pass in |l|
+    ly = 2 * np.pi * np.fft.fftfreq(128, d=np.radians(obj.degPerPixY))
+    lx = 2 * np.pi * np.fft.fftfreq(160, d=np.radians(obj.degPerPixX))
+    obj.filt = np.exp(-0.5 * (ly[:, None] ** 2 + lx[None, :] ** 2) / 2500.0 ** 2)[None]
+    obj.signalNorm = 1.0
+    rng = np.random.default_rng(3)
+    big = rng.standard_normal((1, 192, 240))
+    small = big[:, 32:160, 40:200]
+    a = obj.applyFilter(small.copy())
+    b = obj.applyFilter(big.copy())
+    inner = (slice(40, 88), slice(50, 110))
+    # enmap.fft carries 1 / sqrt(HW) and the inverse is un-normalised (filters.py:851-857): the same filter applied on a grid
+    # of another size comes out sqrt(H'W' / HW) larger -- the reference's own note next to its padding code (signals.py:987)
+    b = b / np.sqrt(192 * 240 / (128 * 160.0))
+    err = float(np.abs(a[inner] - b[32:160, 40:200][inner]).max() / np.abs(a[inner]).max())
+    report("reshape_filter", rel_diff_inner=err)
+    assert err < 2e-2
+
+
 def test_real_space_matched_filter_two_frequency(report):
     """BASELINE config 3 (one reduced tile): 90 + 150 GHz real-space kernel, symmetrised, bckSub."""
     from nemo_b200 import filters, photometry
