@@ -72,6 +72,39 @@ void nb_prof_end_(const char* name, cudaStream_t st) {
     g_prof_recs.push_back(r);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// tensor maps for the TMA column tiles (tma.cuh): cuTensorMapEncodeTiled through the runtime's driver entry point
+#include "tma.cuh"
+
+typedef CUresult (*NbEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int nb_make_tmap_2d(CUtensorMap* map, const void* base, int elemBytes, unsigned long long rows, unsigned long long cols,
+                    unsigned long long pitchBytes, unsigned boxRows, unsigned boxCols) {
+    static NbEncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        NB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        NB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, NB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = (NbEncodeTiled)fn;
+    }
+    NB_REQUIRE((elemBytes == 4 || elemBytes == 8) && boxRows >= 1 && boxRows <= 256 && boxCols >= 1 && boxCols <= 256 &&
+                   ((size_t)boxCols * elemBytes) % 16 == 0 && pitchBytes % 16 == 0 && ((uintptr_t)base & 15) == 0,
+               NB_ERR_ARG, "nb_make_tmap_2d: box %u x %u of %d-byte elements, pitch %llu, base %p cannot be a TMA tile", boxRows, boxCols,
+               elemBytes, pitchBytes, base);
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitchBytes};
+    const cuuint32_t box[2] = {boxCols, boxRows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(map, elemBytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
+                              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NB_REQUIRE(r == CUDA_SUCCESS, NB_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return NB_OK;
+}
+
 extern "C" {
 
 long long nb_launch_count(void) { return (long long)__atomic_load_n(&g_nb_launches, __ATOMIC_RELAXED); }

@@ -608,17 +608,18 @@ static bool use_sfft(int n) {
     return !off && nb_sfft_supported(n) != 0;
 }
 
-static int rows_fwd(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st) {
-    if (use_sfft(W)) return nb_sfft_rows_fwd(prec, in, out, B, H, W, apodPix, scale, st);
+static int rows_fwd(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st,
+                    unsigned char* zeroOut = nullptr) {
+    if (use_sfft(W)) return nb_sfft_rows_fwd(prec, in, out, B, H, W, apodPix, scale, zeroOut, st);
     if (!is_pow2_side(W)) return nb_bs_rows_fwd(prec, in, out, B, H, W, apodPix, scale, st);
     if (prec == NB_PREC_F64) return rfft_rows_t<double>((const double*)in, (double2*)out, B, H, W, apodPix, scale, st);
     return rfft_rows_t<float>((const float*)in, (float2*)out, B, H, W, apodPix, scale, st);
 }
 
 static int rows_inv(int prec, const void* in, void* out, int B, int H, int W, double scale, const double* norm, const unsigned char* mask,
-                    int maskDiv, const void* zeroRef, cudaStream_t st) {
+                    int maskDiv, const void* zeroRef, cudaStream_t st, const unsigned char* zeroBytes = nullptr) {
     if (maskDiv < 1) maskDiv = 1;
-    if (use_sfft(W)) return nb_sfft_rows_inv(prec, in, out, B, H, W, scale, norm, mask, maskDiv, zeroRef, st);
+    if (use_sfft(W)) return nb_sfft_rows_inv(prec, in, out, B, H, W, scale, norm, mask, maskDiv, zeroRef, zeroBytes, st);
     if (!is_pow2_side(W)) return nb_bs_rows_inv(prec, in, out, B, H, W, scale, norm, mask, maskDiv, zeroRef, st);
     if (prec == NB_PREC_F64) {
         C2RParams<double> ep = {scale, norm, mask, maskDiv, (const double*)zeroRef};
@@ -689,15 +690,18 @@ int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratc
     return rows_inv(prec, scratch, out, nOut, H, W, scale, norm, mask, S, nullptr, st);
 }
 
-int nb_window_deconv(int prec, void* data, void* scratch, int B, int H, int W, const void* wy, const void* wx,
-                     int restoreZeros, cudaStream_t st) {
+static int window_deconv(int prec, void* data, void* scratch, unsigned char* zeroBytes, int B, int H, int W, const void* wy, const void* wx,
+                         int restoreZeros, cudaStream_t st) {
     NB_REQUIRE(data && scratch && wy && wx && B > 0, NB_ERR_ARG, "nb_window_deconv: bad arguments");
     NB_REQUIRE(prec == NB_PREC_F64 || prec == NB_PREC_F32, NB_ERR_ARG, "nb_window_deconv: bad precision %d", prec);
     NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_window_deconv: tile %dx%d not supported (sides 64..4096)", H, W);
     int rc;
     const int Wc = W / 2 + 1;
     const double scale = 1.0 / ((double)H * (double)W);
-    if ((rc = rows_fwd(prec, data, scratch, B, H, W, 0, 1.0, st)) != NB_OK) return rc;
+    // zero restore through a byte map when the caller gave room for one and the TMA row kernels can stage it: the forward
+    // pass, which reads the data anyway, writes it; the inverse pass then reads 1 byte per pixel instead of the old value
+    const bool viaBytes = restoreZeros && zeroBytes && use_sfft(W) && nb_sfft_rows_bytes_ok(H, W);
+    if ((rc = rows_fwd(prec, data, scratch, B, H, W, 0, 1.0, st, viaBytes ? zeroBytes : nullptr)) != NB_OK) return rc;
     if (use_sfft(H)) {
         rc = prec == NB_PREC_F64 ? nb_sfft_cols_window_f64(scratch, B, H, Wc, wy, wx, st) : nb_sfft_cols_window_f32(scratch, B, H, Wc, wy, wx, st);
     } else if (!is_pow2_side(H)) {
@@ -708,7 +712,18 @@ int nb_window_deconv(int prec, void* data, void* scratch, int B, int H, int W, c
         rc = fft_cols_window_t<float>((float2*)scratch, B, H, Wc, (const float*)wy, (const float*)wx, st);
     }
     if (rc != NB_OK) return rc;
+    if (viaBytes) return rows_inv(prec, scratch, data, B, H, W, scale, nullptr, nullptr, 1, nullptr, st, zeroBytes);
     return rows_inv(prec, scratch, data, B, H, W, scale, nullptr, nullptr, 1, restoreZeros ? data : nullptr, st);
+}
+
+int nb_window_deconv(int prec, void* data, void* scratch, int B, int H, int W, const void* wy, const void* wx,
+                     int restoreZeros, cudaStream_t st) {
+    return window_deconv(prec, data, scratch, nullptr, B, H, W, wy, wx, restoreZeros, st);
+}
+
+int nb_window_deconv_z(int prec, void* data, void* scratch, unsigned char* zeroBytes, int B, int H, int W, const void* wy,
+                       const void* wx, cudaStream_t st) {
+    return window_deconv(prec, data, scratch, zeroBytes, B, H, W, wy, wx, 1, st);
 }
 
 }  // extern "C"

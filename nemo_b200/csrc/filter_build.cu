@@ -9,6 +9,7 @@
 #include "spline.cuh"
 #include "gauss.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------------
 // K2 pass 1: one CTA per (image, ky).  The cross-power row over the full kx range is rebuilt from the half
@@ -264,6 +265,15 @@ template <int F> __device__ __forceinline__ void solve_sym(const double* c /*P p
     }
 }
 
+// |v| of a complex template value.  np.abs is hypot; CUDA's fp64 hypot is ~90 instructions (scaling against overflow), which
+// made it the largest item of the filter build.  sqrt(x^2 + y^2) with one fused multiply-add is within 1 ulp of it wherever the
+// squares neither underflow nor overflow; outside that range (and for an exactly zero value) hypot itself is used.
+__device__ __forceinline__ double cabs_fast(double x, double y) {
+    const double s = fma(x, x, y * y);
+    if (!(s > 1e-280 && s < 1e280)) return hypot(x, y);
+    return sqrt(s);
+}
+
 struct FreqW {
     double w[NB_MAX_FREQ];
 };
@@ -291,11 +301,11 @@ __global__ void __launch_bounds__(256) build_filter_kernel(const double* __restr
 #pragma unroll
     for (int f = 0; f < F; ++f) {
         const C2 v = fsig[(((size_t)sidx * F + f) * H + ky) * Wc + kx];
-        rhs[f] = __dmul_rn(fw.w[f], hypot((double)v.x, (double)v.y));  // np.abs of a complex number is hypot
+        rhs[f] = __dmul_rn(fw.w[f], cabs_fast((double)v.x, (double)v.y));  // np.abs of a complex number is hypot
         rhs2[f] = rhs[f];
         if (ownMirror) {
             const C2 vm = fsig[(((size_t)sidx * F + f) * H + kym) * Wc + kx];
-            rhs2[f] = __dmul_rn(fw.w[f], hypot((double)vm.x, (double)vm.y));
+            rhs2[f] = __dmul_rn(fw.w[f], cabs_fast((double)vm.x, (double)vm.y));
         }
     }
 #pragma unroll
@@ -313,6 +323,271 @@ __global__ void __launch_bounds__(256) build_filter_kernel(const double* __restr
             ff[(size_t)ky * W + kx] = x1[f];
             if (kx > 0 && 2 * kx != W) ff[(size_t)kym * W + kxm] = x2[f];
         }
+    }
+}
+
+// The same solve for ALL filter scales of a tile in one thread: the covariance of a mode (and of its mirror) is read and
+// factorised once, every scale then costs its template modulus, the recorded row exchanges and multipliers applied to its
+// right-hand side, and the back substitution.  The operations on a right-hand side are exactly those of solve_sym (same
+// multipliers, same order, explicit round-to-nearest), so the filters are bit-identical to build_filter_kernel's; what goes
+// away is 2 P covariance loads, the pivot search, the elimination divisions and the index arithmetic per scale -- the
+// one-scale kernel was issue-bound (about 600 instructions per mode and scale, a quarter of them fp64).
+template <int F> struct LUFactor {
+    double U[F][F];      // upper triangle after elimination (rows exchanged)
+    double m[F][F];      // multipliers m[i][k], i > k
+    int piv[F];          // row exchanged with row k at step k
+    bool singular;
+};
+
+template <int F> __device__ __forceinline__ void lu_factor(const double* c /*P packed upper*/, LUFactor<F>& lu) {
+    int p = 0;
+#pragma unroll
+    for (int i = 0; i < F; ++i)
+#pragma unroll
+        for (int j = i; j < F; ++j) {
+            lu.U[i][j] = c[p];
+            lu.U[j][i] = c[p];
+            ++p;
+        }
+    lu.singular = false;
+#pragma unroll
+    for (int k = 0; k < F; ++k) {
+        int piv = k;
+        double best = fabs(lu.U[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < F; ++i) {
+            const double v = fabs(lu.U[i][k]);
+            if (v > best) {
+                best = v;
+                piv = i;
+            }
+        }
+        lu.piv[k] = piv;
+#pragma unroll
+        for (int i = k + 1; i < F; ++i) {
+            if (i == piv) {
+#pragma unroll
+                for (int j = 0; j < F; ++j) {
+                    const double t = lu.U[k][j];
+                    lu.U[k][j] = lu.U[i][j];
+                    lu.U[i][j] = t;
+                }
+            }
+        }
+        if (lu.U[k][k] == 0.0) lu.singular = true;
+#pragma unroll
+        for (int i = k + 1; i < F; ++i) {
+            const double mm = __ddiv_rn(lu.U[i][k], lu.U[k][k]);
+            lu.m[i][k] = mm;
+#pragma unroll
+            for (int j = k + 1; j < F; ++j) lu.U[i][j] = __dsub_rn(lu.U[i][j], __dmul_rn(mm, lu.U[k][j]));
+        }
+    }
+}
+
+template <int F> __device__ __forceinline__ void lu_solve(const LUFactor<F>& lu, const double* rhs, double* x) {
+    double bb[F];
+#pragma unroll
+    for (int i = 0; i < F; ++i) bb[i] = rhs[i];
+#pragma unroll
+    for (int k = 0; k < F; ++k) {
+#pragma unroll
+        for (int i = k + 1; i < F; ++i) {
+            if (i == lu.piv[k]) {
+                const double t = bb[k];
+                bb[k] = bb[i];
+                bb[i] = t;
+            }
+        }
+#pragma unroll
+        for (int i = k + 1; i < F; ++i) bb[i] = __dsub_rn(bb[i], __dmul_rn(lu.m[i][k], bb[k]));
+    }
+#pragma unroll
+    for (int i = F - 1; i >= 0; --i) {
+        double s = bb[i];
+#pragma unroll
+        for (int j = i + 1; j < F; ++j) s = __dsub_rn(s, __dmul_rn(lu.U[i][j], x[j]));
+        x[i] = __ddiv_rn(s, lu.U[i][i]);
+    }
+    if (lu.singular) {
+#pragma unroll
+        for (int i = 0; i < F; ++i) x[i] = 0.0;
+    }
+}
+
+template <typename T, int F>
+__global__ void __launch_bounds__(128) build_filter_multi_kernel(const double* __restrict__ cov,
+                                                                 const typename V2<T>::type* __restrict__ fsig, FreqW fw,
+                                                                 double* __restrict__ filtFull, T* __restrict__ filtH, int S,
+                                                                 int sigPerTile, int H, int W) {
+    typedef typename V2<T>::type C2;
+    constexpr int P = F * (F + 1) / 2;
+    const int Wc = W / 2 + 1;
+    const int kx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ky = blockIdx.y;
+    const int tile = blockIdx.z;
+    if (kx >= Wc) return;
+    const int kym = (H - ky) % H, kxm = (W - kx) % W;
+    const double* cv = cov + (size_t)tile * P * H * W;
+    const bool ownMirror = (kx == 0 || 2 * kx == W);       // see build_filter_kernel
+    const bool hasMirrorOut = (kx > 0 && 2 * kx != W);
+    LUFactor<F> lu1, lu2;
+    {
+        double c1[P], c2[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            c1[p] = cv[((size_t)p * H + ky) * W + kx];
+            c2[p] = cv[((size_t)p * H + kym) * W + kxm];
+        }
+        lu_factor<F>(c1, lu1);
+        lu_factor<F>(c2, lu2);
+    }
+    const size_t planeH = (size_t)H * Wc, planeF = (size_t)H * W;
+    const size_t offH = (size_t)ky * Wc + kx, offHm = (size_t)kym * Wc + kx;
+    const C2* sg = fsig + (sigPerTile ? (size_t)tile * S * F * planeH : (size_t)0);
+    T* dst = filtH + (size_t)tile * S * F * planeH + offH;
+    double* ff = filtFull ? filtFull + (size_t)tile * S * F * planeF : nullptr;
+#pragma unroll 2
+    for (int s = 0; s < S; ++s) {
+        double rhs[F], rhs2[F], x1[F], x2[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            const C2 v = sg[((size_t)s * F + f) * planeH + offH];
+            rhs[f] = __dmul_rn(fw.w[f], cabs_fast((double)v.x, (double)v.y));
+            rhs2[f] = rhs[f];
+            if (ownMirror) {
+                const C2 vm = sg[((size_t)s * F + f) * planeH + offHm];
+                rhs2[f] = __dmul_rn(fw.w[f], cabs_fast((double)vm.x, (double)vm.y));
+            }
+        }
+        lu_solve<F>(lu1, rhs, x1);
+        lu_solve<F>(lu2, rhs2, x2);
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            dst[((size_t)s * F + f) * planeH] = (T)(0.5 * __dadd_rn(x1[f], x2[f]));
+            if (ff) {
+                double* g = ff + ((size_t)s * F + f) * planeF;
+                g[(size_t)ky * W + kx] = x1[f];
+                if (hasMirrorOut) g[(size_t)kym * W + kxm] = x2[f];
+            }
+        }
+    }
+}
+
+// Templates shared by the tiles of a batch (the usual case): a thread keeps the right-hand sides of up to SC scales of its mode
+// in registers -- every template modulus is read and computed ONCE per batch -- and walks over the tiles: covariance of the mode
+// and of its mirror (the next tile's already requested), two factorisations, SC x 2 substitutions, SC x F stores.  DRAM traffic
+// per batch drops from nT x (templates + covariance + filters) to templates + nT x (covariance + filters): the per-tile kernel
+// above re-read the 310 MB of template spectra (16 scales x 2 frequencies of 840 x 1440) for every tile, 2.7 of its 4 GB.  The
+// two self-conjugate columns (kx = 0 and, for even W, W / 2), whose mirror mode has a template value of its own, are redone by
+// build_filter_selfmirror_kernel afterwards.
+template <typename T, int F, int SC>
+__global__ void __launch_bounds__(128) build_filter_batch_kernel(const double* __restrict__ cov,
+                                                                 const typename V2<T>::type* __restrict__ fsig, FreqW fw,
+                                                                 double* __restrict__ filtFull, T* __restrict__ filtH, int S, int nT,
+                                                                 int H, int W) {
+    typedef typename V2<T>::type C2;
+    constexpr int P = F * (F + 1) / 2;
+    // right-hand sides of the thread's mode: [scale][frequency][thread] (a thread only ever touches its own column of the
+    // array, so no barrier is needed; kept out of registers so that the scale loop need not be unrolled -- fully unrolled it took
+    // 246 registers, two CTAs per SM)
+    __shared__ double s_rhs[SC * F][128];
+    const int Wc = W / 2 + 1;
+    const int kx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ky = blockIdx.y;
+    const int s0 = blockIdx.z * SC;
+    if (kx >= Wc) return;
+    const int ns = (S - s0) < SC ? (S - s0) : SC;
+    const int kym = (H - ky) % H, kxm = (W - kx) % W;
+    const bool hasMirrorOut = (kx > 0 && 2 * kx != W);
+    const size_t planeH = (size_t)H * Wc, planeF = (size_t)H * W;
+    const size_t offH = (size_t)ky * Wc + kx;
+    const size_t off1 = (size_t)ky * W + kx, off2 = (size_t)kym * W + kxm;
+    {
+        const C2* sg = fsig + (size_t)s0 * F * planeH + offH;
+#pragma unroll 8
+        for (int q = 0; q < ns * F; ++q) {
+            const C2 v = sg[(size_t)q * planeH];
+            s_rhs[q][threadIdx.x] = __dmul_rn(fw.w[q % F], cabs_fast((double)v.x, (double)v.y));
+        }
+    }
+    double c1[P], c2[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        c1[p] = cov[(size_t)p * planeF + off1];
+        c2[p] = cov[(size_t)p * planeF + off2];
+    }
+    for (int tile = 0; tile < nT; ++tile) {
+        LUFactor<F> lu1, lu2;
+        lu_factor<F>(c1, lu1);
+        lu_factor<F>(c2, lu2);
+        if (tile + 1 < nT) {
+            const double* cv = cov + (size_t)(tile + 1) * P * planeF;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                c1[p] = cv[(size_t)p * planeF + off1];
+                c2[p] = cv[(size_t)p * planeF + off2];
+            }
+        }
+        T* dst = filtH + ((size_t)tile * S + s0) * F * planeH + offH;
+        double* ff = filtFull ? filtFull + ((size_t)tile * S + s0) * F * planeF : nullptr;
+#pragma unroll 2
+        for (int s = 0; s < ns; ++s) {
+            double rhs[F], x1[F], x2[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) rhs[f] = s_rhs[s * F + f][threadIdx.x];
+            lu_solve<F>(lu1, rhs, x1);
+            lu_solve<F>(lu2, rhs, x2);
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                dst[(size_t)f * planeH] = (T)(0.5 * __dadd_rn(x1[f], x2[f]));
+                if (ff) {
+                    ff[(size_t)f * planeF + off1] = x1[f];
+                    if (hasMirrorOut) ff[(size_t)f * planeF + off2] = x2[f];
+                }
+            }
+            dst += (size_t)F * planeH;
+            if (ff) ff += (size_t)F * planeF;
+        }
+    }
+}
+
+// the self-conjugate columns of build_filter_kernel's grid only: blockIdx.y selects kx = 0 or W / 2, threads run over ky
+template <typename T, int F>
+__global__ void __launch_bounds__(128) build_filter_selfmirror_kernel(const double* __restrict__ cov,
+                                                                      const typename V2<T>::type* __restrict__ fsig, FreqW fw,
+                                                                      double* __restrict__ filtFull, T* __restrict__ filtH, int S,
+                                                                      int sigPerTile, int H, int W) {
+    typedef typename V2<T>::type C2;
+    constexpr int P = F * (F + 1) / 2;
+    const int Wc = W / 2 + 1;
+    const int ky = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kx = blockIdx.y == 0 ? 0 : W / 2;
+    const int o = blockIdx.z;
+    if (ky >= H) return;
+    const int tile = o / S;
+    const int sidx = sigPerTile ? o : (o % S);
+    const int kym = (H - ky) % H;
+    const double* cv = cov + (size_t)tile * P * H * W;
+    double rhs[F], rhs2[F], c1[P], c2[P], x1[F], x2[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        const C2 v = fsig[(((size_t)sidx * F + f) * H + ky) * Wc + kx];
+        const C2 vm = fsig[(((size_t)sidx * F + f) * H + kym) * Wc + kx];
+        rhs[f] = __dmul_rn(fw.w[f], cabs_fast((double)v.x, (double)v.y));
+        rhs2[f] = __dmul_rn(fw.w[f], cabs_fast((double)vm.x, (double)vm.y));
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        c1[p] = cv[((size_t)p * H + ky) * W + kx];
+        c2[p] = cv[((size_t)p * H + kym) * W + kx];       // (W - kx) % W == kx on these columns
+    }
+    solve_sym<F>(c1, rhs, x1);
+    solve_sym<F>(c2, rhs2, x2);
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        filtH[(((size_t)o * F + f) * H + ky) * Wc + kx] = (T)(0.5 * __dadd_rn(x1[f], x2[f]));
+        if (filtFull) filtFull[((size_t)o * F + f) * H * W + (size_t)ky * W + kx] = x1[f];
     }
 }
 
@@ -462,11 +737,11 @@ __global__ void __launch_bounds__(256) build_filter_fused_kernel(const typename 
 #pragma unroll
             for (int f = 0; f < F; ++f) {
                 const C2 v = fsig[(((size_t)sg * F + f) * H + ky) * Wc + kx];
-                rhs[f] = __dmul_rn(fw.w[f], hypot((double)v.x, (double)v.y));
+                rhs[f] = __dmul_rn(fw.w[f], cabs_fast((double)v.x, (double)v.y));
                 rhs2[f] = rhs[f];
                 if (ownMirror) {
                     const C2 vm = fsig[(((size_t)sg * F + f) * H + kym) * Wc + kx];
-                    rhs2[f] = __dmul_rn(fw.w[f], hypot((double)vm.x, (double)vm.y));
+                    rhs2[f] = __dmul_rn(fw.w[f], cabs_fast((double)vm.x, (double)vm.y));
                 }
             }
             solve_sym<F>(c1, rhs, x1);
@@ -608,7 +883,20 @@ __global__ void __launch_bounds__(256) plane_values_partial_kernel(const typenam
                                                                    double* __restrict__ partial, int F, int H, int W, int S) {
     typedef typename V2<T>::type C2;
     extern __shared__ double s_col[];   // [Wc][2]: weight * (cos, sin) of 2 pi kx px / W
-    const int chunk = blockIdx.x, f = blockIdx.y, b = blockIdx.z;
+    int chunk = blockIdx.x, f = blockIdx.y, b = blockIdx.z;
+    if (S > 1 && gridDim.z % S == 0) {
+        // images that share a template spectrum (the same scale of every tile) next to each other in launch order, so that the
+        // template band comes from DRAM once and from L2 for the other tiles (the set of all templates, 310 MB for 16 scales
+        // x 2 frequencies of 840 x 1440, does not survive in L2 from one tile to the next)
+        const unsigned L = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        const unsigned nT = gridDim.z / S;
+        const unsigned tileIdx = L % nT;
+        unsigned rest = L / nT;
+        chunk = rest % gridDim.x;
+        rest /= gridDim.x;
+        f = rest % gridDim.y;
+        b = tileIdx * S + rest / gridDim.y;
+    }
     const int Wc = W / 2 + 1;
     const long long p = idx[b];
     const int py = (int)(p / W), px = (int)(p % W);
@@ -702,6 +990,25 @@ static int build_filter_tf(const double* cov, const void* fsig, const double* w,
     FreqW fw;
     for (int f = 0; f < NB_MAX_FREQ; ++f) fw.w[f] = f < F ? w[f] : 0.0;
     const int Wc = W / 2 + 1;
+    if (!sigPerTile && !getenv("NEMO_B200_BUILD_FILTER_ONE_SCALE") && !getenv("NEMO_B200_BUILD_FILTER_PER_TILE")) {
+        // templates shared by the tiles: right-hand sides in registers, tiles walked by the thread, self-mirror columns redone
+        constexpr int SC = 16 / (F <= 2 ? 1 : 2);
+        const int nT = nOut / S;
+        { NB_PROF_BEGIN(st); build_filter_batch_kernel<T, F, SC><<<dim3((Wc + 127) / 128, H, (S + SC - 1) / SC), 128, 0, st>>>(cov, (const C2*)fsig, fw, filtFull, (T*)filtH, S,
+                                                                             nT, H, W); NB_PROF_END("build_filter_kernel", st); }
+        NB_CHECK_LAUNCH();
+        { NB_PROF_BEGIN(st); build_filter_selfmirror_kernel<T, F><<<dim3((H + 127) / 128, (W % 2 == 0) ? 2 : 1, nOut), 128, 0, st>>>(cov, (const C2*)fsig, fw, filtFull, (T*)filtH, S,
+                                                                             0, H, W); NB_PROF_END("build_filter_selfmirror_kernel", st); }
+        NB_CHECK_LAUNCH();
+        return NB_OK;
+    }
+    if (S > 1 && !getenv("NEMO_B200_BUILD_FILTER_ONE_SCALE")) {
+        // all scales of a tile per thread (the profiler keeps the kernel's family name)
+        { NB_PROF_BEGIN(st); build_filter_multi_kernel<T, F><<<dim3((Wc + 127) / 128, H, nOut / S), 128, 0, st>>>(cov, (const C2*)fsig, fw, filtFull, (T*)filtH, S,
+                                                                             sigPerTile, H, W); NB_PROF_END("build_filter_kernel", st); }
+        NB_CHECK_LAUNCH();
+        return NB_OK;
+    }
     { NB_PROF_BEGIN(st); build_filter_kernel<T, F><<<dim3((Wc + 255) / 256, H, nOut), 256, 0, st>>>(cov, (const C2*)fsig, fw, filtFull, (T*)filtH, S,
                                                                              sigPerTile, H, W); NB_PROF_END("build_filter_kernel", st); }
     NB_CHECK_LAUNCH();
@@ -776,7 +1083,7 @@ int nb_xpower_smooth(int prec, const void* fmaps, double* cov, double* tmp, int 
 
 int nb_build_filter(int prec, const double* cov, const void* fsig, const double* w, double* filtFull, void* filtH,
                     int nOut, int S, int sigPerTile, int F, int H, int W, cudaStream_t st) {
-    NB_REQUIRE(cov && fsig && w && filtH && nOut > 0 && S > 0, NB_ERR_ARG, "nb_build_filter: bad arguments");
+    NB_REQUIRE(cov && fsig && w && filtH && nOut > 0 && S > 0 && nOut % S == 0, NB_ERR_ARG, "nb_build_filter: bad arguments");
     NB_REQUIRE(F >= 1 && F <= NB_MAX_FREQ, NB_ERR_UNSUPPORTED, "nb_build_filter: %d frequencies not supported", F);
 #define BF(T)                                                                                             \
     switch (F) {                                                                                          \

@@ -31,11 +31,28 @@ sfft_cols_kernel(const typename V2<T>::type* __restrict__ in, const T* __restric
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
     const int c = threadIdx.x % C, t = threadIdx.x / C;
-    const int col = blockIdx.x * C + c;
+    int cb = blockIdx.x, o = blockIdx.y;
+    if (MODE == 1 && S > 1 && gridDim.y % S == 0) {
+        // the images that multiply the same spectra (perScale: the same template for every tile; else the S scales of a tile)
+        // take the same column block one after the other in launch order: the spectra columns come from DRAM once and from L2
+        // for the others.  In image-major order the S scales of a tile re-read its spectra from DRAM (measured 3.7 GB of reads
+        // per 128 images against 2.6 GB algorithmic).
+        const unsigned L = blockIdx.y * gridDim.x + blockIdx.x;
+        const unsigned nG = gridDim.y / S;
+        if (perScale) {
+            const unsigned tileIdx = L % nG, rest = L / nG;
+            cb = rest % gridDim.x;
+            o = tileIdx * S + rest / gridDim.x;
+        } else {
+            const unsigned s = L % S, rest = L / S;
+            cb = rest % gridDim.x;
+            o = (rest / gridDim.x) * S + s;
+        }
+    }
+    const int col = cb * C + c;
     const bool valid = col < Wc;
     T* s_re = smem + c * Cfg::LD;
     T* s_im = smem + (C + c) * Cfg::LD;
-    const int o = blockIdx.y;
     const size_t plane = (size_t)H * Wc;
     T xr[S0::REGS], xi[S0::REGS];
 #pragma unroll

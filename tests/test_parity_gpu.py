@@ -150,8 +150,10 @@ def test_cached_filter_round_trip(tmp_path, report):
     got2, obj2 = filters.filterMaps(mapDicts, _copyFilter(f), 'T0', diagnosticsDir=d, selFnDir=d, verbose=False,
                                     useCachedFilter=True, returnFilter=True)
     assert obj2.signalNorm == obj1.signalNorm
-    assert np.array_equal(np.asarray(got1['SNMap']), np.asarray(got2['SNMap']))
+    # the filtered map is bit-identical; the noise map of the one-bin grid kernel sums its clipped samples in the order in
+    # which warps appended them to a list (one atomic per warp), so two runs agree to rounding, not to the bit
     assert np.array_equal(np.asarray(got1['data']), np.asarray(got2['data']))
+    assert np.allclose(np.asarray(got1['SNMap']), np.asarray(got2['SNMap']), rtol=1e-12, atol=1e-12)
     # applyFilter on real maps == what buildAndApply filtered
     again = obj2.applyFilter(np.array([m['data'] for m in mapDicts]))
     ref = filters_ref.filterMaps(mapDicts, _copyFilter(_arnaud()), 'T0', undoPixelWindow=False)
