@@ -73,13 +73,6 @@ int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratc
 int nb_window_deconv(int prec, void* data, void* scratch, int B, int H, int W, const void* wy, const void* wx,
                      int restoreZeros, cudaStream_t stream);
 
-/* The same with the zero restore (always on) carried by a byte map: zeroBytes [B, H, W] u8 is workspace the forward row pass
- * fills with "this pixel is exactly 0" while it reads the data (nemo/filters.py:102-104 keeps such pixels at 0), so that the
- * inverse row pass reads one byte per pixel instead of the old value.  Used when the tile's row kernels can stage the map
- * (rows of 2-3-5-7-smooth even length, W a multiple of 8, even H); otherwise identical to nb_window_deconv(.., 1, ..). */
-int nb_window_deconv_z(int prec, void* data, void* scratch, unsigned char* zeroBytes, int B, int H, int W, const void* wy,
-                       const void* wx, cudaStream_t stream);
-
 /* K2: noiseCov[i][j] = ndimage.gaussian_filter(Re(F_i conj(F_j)), (3, 3))  (nemo/filters.py:568-587), on the
  * full [H, W] plane in unshifted layout with scipy's 'reflect' boundary, truncate = 4 (radius 12).
  * fmaps [B, F, H, Wc] complex(T); cov [B, P, H, W] fp64 with P = F (F + 1) / 2 planes in the order

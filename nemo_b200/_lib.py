@@ -33,7 +33,6 @@ _PROTOTYPES = {
     "nb_irfft2": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr, c_int, c_ptr],
     "nb_apply_filter": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr, c_ptr],
     "nb_window_deconv": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr],
-    "nb_window_deconv_z": [c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr],
     "nb_xpower_smooth": [c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_ptr],
     "nb_build_filter": [c_int, c_ptr, c_ptr, ctypes.POINTER(c_dbl), c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr],
     "nb_build_filter_fused": [c_int, c_ptr, c_ptr, ctypes.POINTER(c_dbl), c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_dbl, c_ptr],

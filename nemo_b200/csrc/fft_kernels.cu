@@ -608,18 +608,17 @@ static bool use_sfft(int n) {
     return !off && nb_sfft_supported(n) != 0;
 }
 
-static int rows_fwd(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st,
-                    unsigned char* zeroOut = nullptr) {
-    if (use_sfft(W)) return nb_sfft_rows_fwd(prec, in, out, B, H, W, apodPix, scale, zeroOut, st);
+static int rows_fwd(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st) {
+    if (use_sfft(W)) return nb_sfft_rows_fwd(prec, in, out, B, H, W, apodPix, scale, st);
     if (!is_pow2_side(W)) return nb_bs_rows_fwd(prec, in, out, B, H, W, apodPix, scale, st);
     if (prec == NB_PREC_F64) return rfft_rows_t<double>((const double*)in, (double2*)out, B, H, W, apodPix, scale, st);
     return rfft_rows_t<float>((const float*)in, (float2*)out, B, H, W, apodPix, scale, st);
 }
 
 static int rows_inv(int prec, const void* in, void* out, int B, int H, int W, double scale, const double* norm, const unsigned char* mask,
-                    int maskDiv, const void* zeroRef, cudaStream_t st, const unsigned char* zeroBytes = nullptr) {
+                    int maskDiv, const void* zeroRef, cudaStream_t st) {
     if (maskDiv < 1) maskDiv = 1;
-    if (use_sfft(W)) return nb_sfft_rows_inv(prec, in, out, B, H, W, scale, norm, mask, maskDiv, zeroRef, zeroBytes, st);
+    if (use_sfft(W)) return nb_sfft_rows_inv(prec, in, out, B, H, W, scale, norm, mask, maskDiv, zeroRef, st);
     if (!is_pow2_side(W)) return nb_bs_rows_inv(prec, in, out, B, H, W, scale, norm, mask, maskDiv, zeroRef, st);
     if (prec == NB_PREC_F64) {
         C2RParams<double> ep = {scale, norm, mask, maskDiv, (const double*)zeroRef};
@@ -630,7 +629,13 @@ static int rows_inv(int prec, const void* in, void* out, int B, int H, int W, do
 }
 
 static int cols_plain(int prec, const void* in, void* out, int B, int H, int Wc, int dir, cudaStream_t st) {
-    if (use_sfft(H)) return prec == NB_PREC_F64 ? nb_sfft_cols_f64(in, out, B, H, Wc, dir, st) : nb_sfft_cols_f32(in, out, B, H, Wc, dir, st);
+    if (use_sfft(H)) {
+        if (prec == NB_PREC_F64) {
+            const int rc = nb_sfft_cols_tma_f64(in, out, B, H, Wc, dir, st);
+            if (rc != 1) return rc;
+        }
+        return prec == NB_PREC_F64 ? nb_sfft_cols_f64(in, out, B, H, Wc, dir, st) : nb_sfft_cols_f32(in, out, B, H, Wc, dir, st);
+    }
     if (!is_pow2_side(H)) return nb_bs_cols(prec, in, out, B, H, Wc, dir, st);
     if (prec == NB_PREC_F64) return fft_cols_t<double>((const double2*)in, (double2*)out, B, H, Wc, dir, 1.0, st);
     return fft_cols_t<float>((const float2*)in, (float2*)out, B, H, Wc, dir, 1.0, st);
@@ -664,8 +669,11 @@ int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratc
     int rc;
     const int Wc = W / 2 + 1;
     if (use_sfft(H)) {
-        rc = prec == NB_PREC_F64 ? nb_sfft_cols_apply_f64(fmaps, filtH, scratch, nOut, S, perScale, F, H, Wc, st)
-                                 : nb_sfft_cols_apply_f32(fmaps, filtH, scratch, nOut, S, perScale, F, H, Wc, st);
+        rc = 1;
+        if (prec == NB_PREC_F64) rc = nb_sfft_cols_apply_tma_f64(fmaps, filtH, scratch, nOut, S, perScale, F, H, Wc, st);
+        if (rc == 1)
+            rc = prec == NB_PREC_F64 ? nb_sfft_cols_apply_f64(fmaps, filtH, scratch, nOut, S, perScale, F, H, Wc, st)
+                                     : nb_sfft_cols_apply_f32(fmaps, filtH, scratch, nOut, S, perScale, F, H, Wc, st);
     } else if (!is_pow2_side(H)) {
         rc = nb_bs_cols_apply(prec, fmaps, filtH, scratch, nOut, S, perScale, F, H, Wc, st);
     } else {
@@ -690,20 +698,19 @@ int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratc
     return rows_inv(prec, scratch, out, nOut, H, W, scale, norm, mask, S, nullptr, st);
 }
 
-static int window_deconv(int prec, void* data, void* scratch, unsigned char* zeroBytes, int B, int H, int W, const void* wy, const void* wx,
-                         int restoreZeros, cudaStream_t st) {
+int nb_window_deconv(int prec, void* data, void* scratch, int B, int H, int W, const void* wy, const void* wx,
+                     int restoreZeros, cudaStream_t st) {
     NB_REQUIRE(data && scratch && wy && wx && B > 0, NB_ERR_ARG, "nb_window_deconv: bad arguments");
     NB_REQUIRE(prec == NB_PREC_F64 || prec == NB_PREC_F32, NB_ERR_ARG, "nb_window_deconv: bad precision %d", prec);
     NB_REQUIRE(tile_supported(H, W), NB_ERR_UNSUPPORTED, "nb_window_deconv: tile %dx%d not supported (sides 64..4096)", H, W);
     int rc;
     const int Wc = W / 2 + 1;
     const double scale = 1.0 / ((double)H * (double)W);
-    // zero restore through a byte map when the caller gave room for one and the TMA row kernels can stage it: the forward
-    // pass, which reads the data anyway, writes it; the inverse pass then reads 1 byte per pixel instead of the old value
-    const bool viaBytes = restoreZeros && zeroBytes && use_sfft(W) && nb_sfft_rows_bytes_ok(H, W);
-    if ((rc = rows_fwd(prec, data, scratch, B, H, W, 0, 1.0, st, viaBytes ? zeroBytes : nullptr)) != NB_OK) return rc;
+    if ((rc = rows_fwd(prec, data, scratch, B, H, W, 0, 1.0, st)) != NB_OK) return rc;
     if (use_sfft(H)) {
-        rc = prec == NB_PREC_F64 ? nb_sfft_cols_window_f64(scratch, B, H, Wc, wy, wx, st) : nb_sfft_cols_window_f32(scratch, B, H, Wc, wy, wx, st);
+        rc = 1;
+        if (prec == NB_PREC_F64) rc = nb_sfft_cols_window_tma_f64(scratch, B, H, Wc, wy, wx, st);
+        if (rc == 1) rc = prec == NB_PREC_F64 ? nb_sfft_cols_window_f64(scratch, B, H, Wc, wy, wx, st) : nb_sfft_cols_window_f32(scratch, B, H, Wc, wy, wx, st);
     } else if (!is_pow2_side(H)) {
         rc = nb_bs_cols_window(prec, scratch, B, H, Wc, wy, wx, st);
     } else if (prec == NB_PREC_F64) {
@@ -712,18 +719,7 @@ static int window_deconv(int prec, void* data, void* scratch, unsigned char* zer
         rc = fft_cols_window_t<float>((float2*)scratch, B, H, Wc, (const float*)wy, (const float*)wx, st);
     }
     if (rc != NB_OK) return rc;
-    if (viaBytes) return rows_inv(prec, scratch, data, B, H, W, scale, nullptr, nullptr, 1, nullptr, st, zeroBytes);
     return rows_inv(prec, scratch, data, B, H, W, scale, nullptr, nullptr, 1, restoreZeros ? data : nullptr, st);
-}
-
-int nb_window_deconv(int prec, void* data, void* scratch, int B, int H, int W, const void* wy, const void* wx,
-                     int restoreZeros, cudaStream_t st) {
-    return window_deconv(prec, data, scratch, nullptr, B, H, W, wy, wx, restoreZeros, st);
-}
-
-int nb_window_deconv_z(int prec, void* data, void* scratch, unsigned char* zeroBytes, int B, int H, int W, const void* wy,
-                       const void* wx, cudaStream_t st) {
-    return window_deconv(prec, data, scratch, zeroBytes, B, H, W, wy, wx, 1, st);
 }
 
 }  // extern "C"

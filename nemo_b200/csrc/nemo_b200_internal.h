@@ -21,13 +21,14 @@ int nb_bs_cols_window(int prec, void* data, int B, int H, int Wc, const void* wy
 // compile-time mixed-radix passes for the 2-3-5-7-smooth sides listed in sfft_host.cuh (sfft_rows.cu, sfft_cols_f64/f32.cu);
 // same contracts again
 int nb_sfft_supported(int n);
-// zeroOut (forward) / zeroBytes (inverse): optional [B, H, W] byte map "this pixel of the input was exactly zero", written by the
-// forward pass of the window undo and applied by its inverse pass (TMA row kernels only: nb_sfft_rows_bytes_ok)
-int nb_sfft_rows_fwd(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, unsigned char* zeroOut,
-                     cudaStream_t st);
+int nb_sfft_rows_fwd(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st);
 int nb_sfft_rows_inv(int prec, const void* in, void* out, int B, int H, int W, double scale, const double* norm, const unsigned char* mask,
-                     int maskDiv, const void* zeroRef, const unsigned char* zeroBytes, cudaStream_t st);
-int nb_sfft_rows_bytes_ok(int H, int W);
+                     int maskDiv, const void* zeroRef, cudaStream_t st);
+// TMA-fed column passes (sfft_cols_tma.cu, fp64): NB_OK when launched, 1 when the path does not apply (fall back), < 0 on error
+int nb_sfft_cols_tma_f64(const void* in, void* out, int B, int H, int Wc, int dir, cudaStream_t st);
+int nb_sfft_cols_window_tma_f64(void* data, int B, int H, int Wc, const void* wy, const void* wx, cudaStream_t st);
+int nb_sfft_cols_apply_tma_f64(const void* fmaps, const void* filt, void* out, int nOut, int S, int perScale, int F, int H, int Wc,
+                               cudaStream_t st);
 int nb_sfft_cols_f64(const void* in, void* out, int B, int H, int Wc, int dir, cudaStream_t st);
 int nb_sfft_cols_f32(const void* in, void* out, int B, int H, int Wc, int dir, cudaStream_t st);
 int nb_sfft_cols_apply_f64(const void* fmaps, const void* filt, void* out, int nOut, int S, int perScale, int F, int H, int Wc, cudaStream_t st);

@@ -9,9 +9,22 @@
 // threads, a thread does one butterfly per pass; two row pairs per CTA); pass radices and threads per column of the COLUMN
 // passes (about N / 2R threads, two butterflies per pass and at most 16 values per thread: a CTA of 4 columns is then small
 // enough in threads and registers for two CTAs per SM, one loading while the other computes)
+// (-DSFFT_COL_VARIANT=1 on the nvcc command line selects the one-butterfly-per-thread column plans for experiments; nvcc
+// splits option values at commas, so a plan cannot be passed directly)
+#ifndef SFFT_COL_VARIANT
+#define SFFT_COL_VARIANT 0
+#endif
+#if SFFT_COL_VARIANT == 1
+#define SFFT_COL_1440 10, 12, 12, 144
+#define SFFT_COL_840 7, 10, 12, 120
+#else
+#define SFFT_COL_1440 10, 12, 12, 144
+#define SFFT_COL_840 7, 8, 15, 60
+#endif
+#define SFFT_APPLY(X, ...) X(__VA_ARGS__)
 #define SFFT_FOR_SIZES(X) \
-    X(1440, 10, 12, 12, 144,  10, 12, 12, 144) \
-    X(840, 7, 10, 12, 120,    7, 8, 15, 60)    \
+    SFFT_APPLY(X, 1440, 10, 12, 12, 144,  SFFT_COL_1440) \
+    SFFT_APPLY(X, 840, 7, 10, 12, 120,    SFFT_COL_840)  \
     X(420, 5, 7, 12, 84,      5, 7, 12, 42)    \
     X(320, 5, 8, 8, 64,       5, 8, 8, 32)     \
     X(300, 5, 6, 10, 60,      5, 6, 10, 30)

@@ -147,13 +147,8 @@ class Ops(object):
         wy, wx = tables
         if scratch is None:
             scratch = self.empty((B, H, W // 2 + 1), self.cdtype)
-        if restoreZeros:
-            # the zero pattern travels as a byte map between the forward and the inverse row pass (nb_window_deconv_z)
-            zeroBytes = self.empty((B, H, W), self.torch.uint8)
-            _lib.call('nb_window_deconv_z', self.prec, _ptr(data), _ptr(scratch), _ptr(zeroBytes), B, H, W, _ptr(wy), _ptr(wx),
-                      self._stream())
-        else:
-            _lib.call('nb_window_deconv', self.prec, _ptr(data), _ptr(scratch), B, H, W, _ptr(wy), _ptr(wx), 0, self._stream())
+        _lib.call('nb_window_deconv', self.prec, _ptr(data), _ptr(scratch), B, H, W, _ptr(wy), _ptr(wx), 1 if restoreZeros else 0,
+                  self._stream())
         self.launches += 3
         return data
 
