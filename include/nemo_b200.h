@@ -264,6 +264,20 @@ int nb_gauss_filter(int prec, const void* in, void* tmp, void* out, int B, int H
 int nb_conv2d(int prec, const void* in, const double* kern, void* out, void* planes, int B, int F, int H, int W,
               int kh, int kw, double scale, const double* norm, const unsigned char* mask, cudaStream_t stream);
 
+/* K13 for a batch of (tile, filter) images with a kernel each (the batched real-space driver; filters.py:1200-1216, 1113):
+ *   out[b] = scale * norm[b] * mask[b / maskDiv] * sum_f ndimage.convolve(in[m(b), f], kern[k(b), f])   (reflect)
+ * m(b) = b % inMod when inMod > 0 (templates shared by the tiles), else b / inDiv (the inDiv filters of a tile);
+ * k(b) = b when kernPerImage != 0 (kern [B, F, kh, kw]), else 0 (kern [F, kh, kw]).  Same arithmetic as nb_conv2d,
+ * register-blocked (8 outputs per thread). */
+int nb_conv2d_batch(int prec, const void* in, const double* kern, void* out, void* planes, int B, int F, int H, int W,
+                    int kh, int kw, double scale, const double* norm, const unsigned char* mask, int inDiv, int inMod,
+                    int kernPerImage, int maskDiv, cudaStream_t stream);
+
+/* out[b, kx] = mean over ky of in[b, ky, kx] (fp64): the ky average of a folded filter, whose 1-D inverse transform is row 0
+ * of the filter's real-space form -- what MapFilter.makeRealSpaceFilterProfile reads (nemo/filters.py:282-304).
+ * in [B, H, Wc] T, out [B, Wc] fp64. */
+int nb_mean_over_rows(int prec, const void* in, double* out, int B, int H, int Wc, cudaStream_t stream);
+
 /* Small utilities used by the boundary module. */
 int nb_cast(int precIn, const void* in, int precOut, void* out, long long n, cudaStream_t stream);
 int nb_mask_to_u8(int precIn, const void* in, unsigned char* out, long long n, cudaStream_t stream);

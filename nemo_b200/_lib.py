@@ -66,6 +66,9 @@ _PROTOTYPES = {
     "nb_spline_eval": [c_int, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_dbl, c_ptr],
     "nb_gauss_filter": [c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_dbl, c_dbl, c_int, c_ptr],
     "nb_conv2d": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr, c_ptr],
+    "nb_conv2d_batch": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr,
+                        c_int, c_int, c_int, c_int, c_ptr],
+    "nb_mean_over_rows": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr],
     "nb_cast": [c_int, c_ptr, c_int, c_ptr, c_ll, c_ptr],
     "nb_mask_to_u8": [c_int, c_ptr, c_ptr, c_ll, c_ptr],
 }

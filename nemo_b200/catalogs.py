@@ -411,10 +411,15 @@ def crossMatchKeepBest(ra, dec, snr, radiusDeg, ops=None, comm=None):
     return device.toHost(mask) != 0
 
 
-def makeOptimalCatalog(catalogDict, constraintsList=[], ops=None):
+def makeOptimalCatalog(catalogDict, constraintsList=[], ops=None, stacked=None):
     """Keeps, for every group of detections within XMATCH_RADIUS_DEG of each other across filters, the one with
-    the highest S/N; sorted by (RADeg, decDeg)  (catalogs.py:149-189).  ops: evaluate the cross-match on the device."""
-    allCatalogs = [catalogDict[key]['catalog'] for key in catalogDict.keys() if len(catalogDict[key]['catalog']) > 0]
+    the highest S/N; sorted by (RADeg, decDeg)  (catalogs.py:149-189).  ops: evaluate the cross-match on the device.
+    stacked: tables that hold the rows of catalogDict's catalogs already stacked, in catalogDict's order (the batched driver
+    has one per tile batch) -- used instead of stacking the per-image tables."""
+    if stacked is not None:
+        allCatalogs = [t for t in stacked if len(t) > 0]
+    else:
+        allCatalogs = [catalogDict[key]['catalog'] for key in catalogDict.keys() if len(catalogDict[key]['catalog']) > 0]
     if len(allCatalogs) == 0:
         return Table(names=('SNR', 'RADeg', 'decDeg'))
     allCat = vstack(allCatalogs)

@@ -22,6 +22,23 @@ def toHost(t):
     return t.numpy()
 
 
+class HostCopy(object):
+    """Device tensor -> pinned host buffer, asynchronous on the current stream; ``.get()`` waits for THIS copy only (an event),
+    so kernels queued after it keep the device busy while the host works on the values."""
+
+    def __init__(self, t):
+        import torch
+        TRAFFIC['d2h'] += int(t.numel()) * t.element_size()
+        self.buf = torch.empty(t.shape, dtype=t.dtype, device='cpu', pin_memory=True)
+        self.buf.copy_(t.detach(), non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def get(self):
+        self.event.synchronize()
+        return self.buf.numpy()
+
+
 def countH2D(t):
     TRAFFIC['h2d'] += int(t.numel()) * t.element_size()
     return t

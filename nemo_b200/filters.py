@@ -221,12 +221,7 @@ class MapFilter(object):
         filt = np.asarray(self.filt)
         W = filt.shape[2]
         rowCut = fft.ifft(filt.mean(axis=1), axis=-1).real
-        rowCut = fft.fftshift(rowCut, axes=0)
-        cut = rowCut[:, :W - W // 2]
-        normFactor = abs(cut).max()
-        prof = cut / normFactor
-        arcminRange = np.arange(0, prof.shape[1]) * self.degPerPixX * 60.0
-        return prof, arcminRange
+        return realSpaceProfileFromRow(rowCut, W, self.degPerPixX)
 
     def makeNoiseMap(self, mapData):
         """Noise map from local 3-sigma-clipped measurements in grid cells (filters.py:345-483), on the GPU."""
@@ -507,52 +502,9 @@ class RealSpaceMatchedFilter(MapFilter):
         matchedFilter.buildAndApply()
         self.matchedFilter = matchedFilter
 
-        kernelMaxArcmin = self.params['noiseParams']['kernelMaxArcmin']
         prof, arcminRange = matchedFilter.makeRealSpaceFilterProfile()
-        rIndex = np.where(arcminRange > kernelMaxArcmin)[0][0]
-        mask = np.less(arcminRange, kernelMaxArcmin)
-        if 'symmetrize' in self.params['noiseParams'].keys() and self.params['noiseParams']['symmetrize'] == True:
-            rRadians = np.radians(arcminRange / 60.)
-            # The interpolated profile is zero beyond the last radius below kernelMaxArcmin, so only a window around the tile
-            # centre can hold the peak and the kernel: evaluating it there gives the same kern2d as the reference's full-map
-            # evaluation (filters.py:955-960) for a hundredth of the work.
-            rmap = matchedFilter.radiansMap
-            yc, xc = int(np.argmin(rmap[:, 0])), int(np.argmin(rmap[0, :]))
-            rMax = rRadians[mask].max() if mask.any() else 0.0
-            rows, cols = np.flatnonzero(rmap[:, xc] <= rMax), np.flatnonzero(rmap[yc, :] <= rMax)
-            pad = rIndex + 2
-            wy0, wy1 = max(rows.min() - pad, 0), min(rows.max() + pad + 1, rmap.shape[0])
-            wx0, wx1 = max(cols.min() - pad, 0), min(cols.max() + pad + 1, rmap.shape[1])
-            profile2d = []
-            for i in range(prof.shape[0]):
-                r2p = interpolate.interp1d(rRadians[mask], prof[i, mask], bounds_error=False, fill_value=0.0)
-                profile2d.append(r2p(rmap[wy0:wy1, wx0:wx1]))
-            profile2d = np.array(profile2d)
-            z, y, x = np.where(abs(profile2d) == abs(profile2d).max())
-            y, x = y[0], x[0]
-            if abs(profile2d).max() > 0 and y - rIndex >= 0 and x - rIndex >= 0 and y + rIndex <= profile2d.shape[1] and x + rIndex <= profile2d.shape[2]:
-                windowed = True
-            else:      # degenerate profile or a kernel that leaves the window: the full map, as the reference
-                windowed = False
-                profile2d = np.array([interpolate.interp1d(rRadians[mask], prof[i, mask], bounds_error=False, fill_value=0.0)(rmap)
-                                      for i in range(prof.shape[0])])
-        else:
-            profile2d = fft.ifft2(matchedFilter.filt).real
-            profile2d = fft.fftshift(profile2d)
-        z, y, x = np.where(abs(profile2d) == abs(profile2d).max())
-        y = y[0]
-        x = x[0]
-        yMin, yMax, xMin, xMax = y - rIndex, y + rIndex, x - rIndex, x + rIndex
-        if (yMax - yMin) % 2 == 0:
-            yMin = yMin + 1
-        if (xMax - xMin) % 2 == 0:
-            xMin = xMin + 1
-        self.kern2d = np.ascontiguousarray(profile2d[:, yMin:yMax, xMin:xMax])
-        if 'bckSubScaleArcmin' in self.params.keys():
-            self.bckSubScaleArcmin = self.params['bckSubScaleArcmin']
-        else:
-            func = np.min if np.greater(prof[0, 0], 0) == True else np.max
-            self.bckSubScaleArcmin = arcminRange[prof[0] == func(prof[0])][0]
+        self.kern2d, self.bckSubScaleArcmin = realSpaceKernelFromProfile(prof, arcminRange, matchedFilter.radiansMap, self.params,
+                                                                         filt=matchedFilter.filt)
 
         signalMaps = []
         for mapDict in self.unfilteredMapsDictList:
@@ -695,6 +647,159 @@ class RealSpaceMatchedFilter(MapFilter):
             out = self._applyOnDevice(cubeT, normT, None)
         return out[0].cpu().numpy()
 
+
+# -------------------------------------------------------------------------------------------------------------
+# Pieces of the real-space kernel construction shared by the class API (one tile at a time) and the batched driver
+# (nemo_b200.realspace): everything after the Fourier filter is small host work.
+def realSpaceProfileFromRow(rowCut, W, degPerPixX):
+    """(prof, arcminRange) of MapFilter.makeRealSpaceFilterProfile (filters.py:282-304) from rowCut [F, W] = row 0 of
+    ifft2(filt).real, i.e. the 1-d inverse transform along x of the ky-mean of the filter.  The reference takes row H/2,
+    columns W/2.. of fftshift(...) over ALL axes: the frequency axis is shifted too."""
+    rowCut = fft.fftshift(rowCut, axes=0)
+    cut = rowCut[:, :W - W // 2]
+    normFactor = abs(cut).max()
+    prof = cut / normFactor
+    arcminRange = np.arange(0, prof.shape[1]) * degPerPixX * 60.0
+    return prof, arcminRange
+
+
+_KERNEL_WINDOWS = {}
+
+
+def _interpProfile(r, xp, fp):
+    """interpolate.interp1d(xp, fp, bounds_error=False, fill_value=0.0)(r) for the linear default: scipy evaluates it with
+    np.interp and fills outside [xp[0], xp[-1]] (filters.py:957-958)."""
+    out = np.interp(r, xp, fp)
+    out[(r < xp[0]) | (r > xp[-1])] = 0.0
+    return out
+
+
+def _kernelWindow(rmap, rRadians, mask, rIndex, kernelMaxArcmin, arcminRange):
+    """The window of the radians map around the tile centre that can hold a symmetrised kernel (a function of the geometry
+    only: kept per radians map)."""
+    key = (id(rmap), rmap.shape, float(kernelMaxArcmin), len(arcminRange), float(arcminRange[1] if len(arcminRange) > 1 else 0.0))
+    win = _KERNEL_WINDOWS.get(key)
+    if win is None or win[0] is not rmap:
+        yc, xc = int(np.argmin(rmap[:, 0])), int(np.argmin(rmap[0, :]))
+        rMax = rRadians[mask].max() if mask.any() else 0.0
+        rows, cols = np.flatnonzero(rmap[:, xc] <= rMax), np.flatnonzero(rmap[yc, :] <= rMax)
+        pad = rIndex + 2
+        wy0, wy1 = max(rows.min() - pad, 0), min(rows.max() + pad + 1, rmap.shape[0])
+        wx0, wx1 = max(cols.min() - pad, 0), min(cols.max() + pad + 1, rmap.shape[1])
+        if len(_KERNEL_WINDOWS) >= 16:
+            _KERNEL_WINDOWS.pop(next(iter(_KERNEL_WINDOWS)))
+        win = _KERNEL_WINDOWS[key] = (rmap, np.ascontiguousarray(rmap[wy0:wy1, wx0:wx1]))
+    return win[1]
+
+
+def realSpaceKernelsFromRows(rowCuts, W, degPerPixX, rmap, params):
+    """realSpaceProfileFromRow + realSpaceKernelFromProfile for n filters at once (rowCuts [n, F, W]; symmetrised kernels with
+    a common kernelMaxArcmin and a given bckSubScaleArcmin, the batched driver's case): the same arithmetic written over
+    arrays -- the linear interpolation as np.interp evaluates it, slope * (x - xp[j]) + fp[j].  Returns kern2d [n, F, kh, kw];
+    kernels whose peak does not sit where the first one's does are made one by one."""
+    n, F, _ = rowCuts.shape
+    rc = np.roll(rowCuts, F // 2, axis=1)                       # fftshift over ALL axes shifts the frequency axis too
+    cut = rc[:, :, :W - W // 2]
+    prof = cut / np.abs(cut).reshape(n, -1).max(axis=1)[:, None, None]
+    arcminRange = np.arange(0, cut.shape[2]) * degPerPixX * 60.0
+    kernelMaxArcmin = params['noiseParams']['kernelMaxArcmin']
+    rIndex = np.where(arcminRange > kernelMaxArcmin)[0][0]
+    mask = np.less(arcminRange, kernelMaxArcmin)
+    rRadians = np.radians(arcminRange / 60.)
+    rwin = _kernelWindow(rmap, rRadians, mask, rIndex, kernelMaxArcmin, arcminRange)
+    xp = rRadians[mask]
+    one = lambda o: realSpaceKernelFromProfile(prof[o], arcminRange, rmap, params)[0]
+    if len(xp) < 2:
+        return np.array([one(o) for o in range(n)])
+    fp = np.ascontiguousarray(prof[:, :, mask])
+    slope = np.diff(fp, axis=2) / np.diff(xp)
+
+    def interp(sel, r):
+        """the interpolated profiles of filters `sel` at the radii r [h, w] -> [len(sel), F, h, w]"""
+        j = np.clip(np.searchsorted(xp, r, side='right') - 1, 0, len(xp) - 2)
+        v = slope[sel][:, :, j] * (r - xp[j]) + fp[sel][:, :, j]
+        v[:, :, r == xp[-1]] = fp[sel][:, :, -1][:, :, None]
+        v[:, :, (r < xp[0]) | (r > xp[-1])] = 0.0
+        return v
+
+    # The interpolated profile is piecewise linear in r, so its largest absolute value over the window is the largest |knot
+    # value|.  When that is the value at r = 0, strictly, the peak is the centre pixel (the only one at r = 0) and the kernel is
+    # the block of +- rIndex pixels around it: only that block is evaluated -- a fifth of the window.
+    out = [None] * n
+    cyx = np.argwhere(rwin == 0.0)
+    if len(cyx) == 1 and xp[0] == 0.0:
+        cy, cx = int(cyx[0][0]), int(cyx[0][1])
+        yMin, yMax, xMin, xMax = cy - rIndex, cy + rIndex, cx - rIndex, cx + rIndex
+        if yMin >= 0 and xMin >= 0 and yMax <= rwin.shape[0] and xMax <= rwin.shape[1]:
+            if (yMax - yMin) % 2 == 0:
+                yMin = yMin + 1
+            if (xMax - xMin) % 2 == 0:
+                xMin = xMin + 1
+            afp = np.abs(fp)
+            central = np.flatnonzero(afp[:, :, 0].max(axis=1) > afp[:, :, 1:].reshape(n, -1).max(axis=1))
+            if len(central) > 0:
+                block = interp(central, rwin[yMin:yMax, xMin:xMax])
+                for i, o in enumerate(central):
+                    out[o] = block[i]
+    rest = np.array([o for o in range(n) if out[o] is None], dtype=int)
+    if len(rest) == 0:
+        return np.ascontiguousarray(np.array(out))
+    profile2d = interp(rest, rwin)                                              # [len(rest), F, hw, ww]
+    n = len(rest)
+    ap = np.abs(profile2d).reshape(n, -1)
+    amax = ap.max(axis=1)
+    first = (ap == amax[:, None]).argmax(axis=1)
+    z, y, x = np.unravel_index(first, profile2d.shape[1:])
+    yMin, yMax, xMin, xMax = y - rIndex, y + rIndex, x - rIndex, x + rIndex
+    ok = (amax > 0) & (yMin >= 0) & (xMin >= 0) & (yMax <= profile2d.shape[2]) & (xMax <= profile2d.shape[3])
+    yMin = np.where((yMax - yMin) % 2 == 0, yMin + 1, yMin)
+    xMin = np.where((xMax - xMin) % 2 == 0, xMin + 1, xMin)
+    for i, o in enumerate(rest):
+        out[o] = profile2d[i, :, yMin[i]:yMax[i], xMin[i]:xMax[i]] if ok[i] else one(o)
+    return np.ascontiguousarray(np.array(out))
+
+
+def realSpaceKernelFromProfile(prof, arcminRange, rmap, params, filt=None):
+    """(kern2d [F, kh, kw], bckSubScaleArcmin) of RealSpaceMatchedFilter.buildKernel (filters.py:944-985) from the 1-d profile.
+    rmap: the radians map of the region the filter was built on; filt: the full Fourier filter, needed only without
+    'symmetrize' (the 2-d kernel is then cut out of its inverse transform)."""
+    kernelMaxArcmin = params['noiseParams']['kernelMaxArcmin']
+    rIndex = np.where(arcminRange > kernelMaxArcmin)[0][0]
+    mask = np.less(arcminRange, kernelMaxArcmin)
+    if 'symmetrize' in params['noiseParams'].keys() and params['noiseParams']['symmetrize'] == True:
+        rRadians = np.radians(arcminRange / 60.)
+        # The interpolated profile is zero beyond the last radius below kernelMaxArcmin, so only a window around the tile
+        # centre can hold the peak and the kernel: evaluating it there gives the same kern2d as the reference's full-map
+        # evaluation (filters.py:955-960) for a hundredth of the work.  The window depends on the geometry only: kept.
+        rwin = _kernelWindow(rmap, rRadians, mask, rIndex, kernelMaxArcmin, arcminRange)
+        xp = rRadians[mask]
+        profile2d = np.array([_interpProfile(rwin, xp, prof[i, mask]) for i in range(prof.shape[0])])
+        amax = abs(profile2d).max()
+        z, y, x = np.unravel_index(int(np.argmax(abs(profile2d) == amax)), profile2d.shape)
+        if not (amax > 0 and y - rIndex >= 0 and x - rIndex >= 0 and y + rIndex <= profile2d.shape[1]
+                and x + rIndex <= profile2d.shape[2]):
+            # degenerate profile or a kernel that leaves the window: the full map, as the reference
+            profile2d = np.array([_interpProfile(rmap, xp, prof[i, mask]) for i in range(prof.shape[0])])
+    else:
+        if filt is None:
+            raise Exception("a real-space kernel without 'symmetrize' is cut out of the filter's 2-d inverse transform: filt needed")
+        profile2d = fft.ifft2(np.asarray(filt)).real
+        profile2d = fft.fftshift(profile2d)
+    # first position (in z, y, x order) of the largest absolute value: np.where(abs(profile2d) == abs(profile2d).max())[..][0]
+    ap = abs(profile2d)
+    z, y, x = np.unravel_index(int(np.argmax(ap == ap.max())), profile2d.shape)
+    yMin, yMax, xMin, xMax = y - rIndex, y + rIndex, x - rIndex, x + rIndex
+    if (yMax - yMin) % 2 == 0:
+        yMin = yMin + 1
+    if (xMax - xMin) % 2 == 0:
+        xMin = xMin + 1
+    kern2d = np.ascontiguousarray(profile2d[:, yMin:yMax, xMin:xMax])
+    if 'bckSubScaleArcmin' in params.keys():
+        bckSubScaleArcmin = params['bckSubScaleArcmin']
+    else:
+        func = np.min if np.greater(prof[0, 0], 0) == True else np.max
+        bckSubScaleArcmin = arcminRange[prof[0] == func(prof[0])][0]
+    return kern2d, bckSubScaleArcmin
 
 # -------------------------------------------------------------------------------------------------------------
 # Signal templates are host-made inputs of the hot path and depend only on the tile geometry (shape and central pixel

@@ -527,6 +527,32 @@ class Ops(object):
         self.launches += 1
         return (out, planes) if wantPlanes else out
 
+    def conv2d_batch(self, maps, kern, nOut, scale=1.0, norm=None, mask=None, inDiv=1, inMod=0, maskDiv=1, wantPlanes=False):
+        """K13 for nOut (tile, filter) images: kern [nOut, F, kh, kw] (one kernel per image) or [F, kh, kw]; output image b reads
+        maps[b % inMod] (inMod > 0) or maps[b // inDiv], and mask[b // maskDiv]."""
+        self._check(maps, self.dtype, 'maps')
+        self._check(kern, self.torch.float64, 'kern')
+        nIn, F, H, W = maps.shape
+        kh, kw = kern.shape[-2], kern.shape[-1]
+        perImage = 1 if kern.dim() == 4 else 0
+        if perImage and kern.shape[0] != nOut:
+            raise Exception("conv2d_batch: %d kernels for %d images" % (kern.shape[0], nOut))
+        out = self.empty((nOut, H, W))
+        planes = self.empty((nOut, F, H, W)) if wantPlanes else None
+        _lib.call('nb_conv2d_batch', self.prec, _ptr(maps), _ptr(kern), _ptr(out), _ptr(planes), int(nOut), F, H, W, kh, kw, float(scale),
+                  _ptr(norm), _ptr(mask), int(inDiv), int(inMod), perImage, int(maskDiv), self._stream())
+        self.launches += 1
+        return (out, planes) if wantPlanes else out
+
+    def mean_over_rows(self, planes):
+        """[B, H, Wc] -> [B, Wc] fp64: mean over the rows of every plane."""
+        self._check(planes, self.dtype, 'planes')
+        B, H, Wc = planes.shape
+        out = self.empty((B, Wc), self.torch.float64)
+        _lib.call('nb_mean_over_rows', self.prec, _ptr(planes), _ptr(out), B, H, Wc, self._stream())
+        self.launches += 1
+        return out
+
     def scale_mask(self, maps, scale=1.0, norm=None, mask=None):
         """maps * scale * norm[b] * mask[b] via a 1x1 convolution (keeps all arithmetic in the library)."""
         # the 1 x 1 kernel is made once per Ops on the device: a host-to-device copy from pageable memory is not allowed while a

@@ -321,6 +321,32 @@ def splitObjects(flat, extra=None, keysToWrite=None):
     return out
 
 
+def flatTable(flat, extra=None, keysToWrite=None):
+    """All rows of a batch as ONE table, in the order splitObjects' tables stack (image by image): what
+    catalogs.makeOptimalCatalog stacks anyway, without the hundreds of small tables in between.  Columns are the flat arrays
+    themselves (no copies); None when nothing was found."""
+    counts = np.asarray(flat['counts'])
+    if flat['cols'] is None or int(counts.sum()) == 0:
+        return None
+    keys = keysToWrite if keysToWrite is not None else catalogs.COLUMN_NAMES
+    cols = dict(flat['cols'])
+    if extra:
+        cols.update(extra)
+    ident, longNames = flat['objIdent'], flat['longNames']
+    ordered = []
+    for key in keys:
+        if key == 'name':
+            ra, dec = cols['RADeg'], cols['decDeg']
+            ordered.append((key, catalogs.deferred(lambda ra=ra, dec=dec: catalogs.makeNames(ra, dec, prefix=ident, longNames=longNames))))
+        elif key == 'template':
+            ordered.append((key, np.repeat(np.array(flat['labels'], dtype=object), counts)))
+        elif key == 'tileName':
+            ordered.append((key, np.repeat(np.array(flat['tiles'], dtype=object), counts)))
+        elif key in cols:
+            ordered.append((key, cols[key]))
+    return catalogs.Table.fromColumns(ordered)
+
+
 def findObjectsBatch(ops, snMaps, wcsList, flagMaskList, labelList, tileNameList, threshold=3.0, minObjPix=3,
                      rejectBorder=10, findCenterOfMass=True, removeRings=True, ringThresholdSigma=0, invertMap=False,
                      objIdent='ACT-CL', longNames=False, useInterpolator=True, measureShapes=False):

@@ -190,8 +190,8 @@ class FilterSetTemplates(object):
         self.outputUnits = None
         for f in filtersList:
             cls = f['class'] if not isinstance(f['class'], str) else getattr(_filters, f['class'])
-            if not issubclass(cls, _filters.MatchedFilter):
-                raise Exception("FilterSetTemplates handles Fourier-space matched filters only")
+            if not (issubclass(cls, _filters.MatchedFilter) or issubclass(cls, _filters.RealSpaceMatchedFilter)):
+                raise Exception("FilterSetTemplates handles matched filters (Fourier-space or real-space) only")
             obj = cls.__new__(cls)
             obj.params = f['params']
             obj.unfilteredMapsDictList = mapDicts
@@ -629,10 +629,18 @@ def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measu
                         cols[prefix + 'err_fluxJy'] = np.where(nsr > 0, errFlux, 0.0)
     keys = catalogKeys(photScale is not None, mapUnits, measureFluxes)
     tables = photometry.splitObjects(flat, cols, keysToWrite=keys)
-    catalogDict = {}
+    catalogDict = _BatchCatalogs()
     for o in range(nT * S):
         catalogDict[labelList[o] + "#" + tileList[o]] = {'catalog': tables[o]}
+    # the same rows as one table: what the cross-scale merge stacks (filterMapsAndMakeCatalogs hands these to makeOptimalCatalog)
+    catalogDict.flat = photometry.flatTable(flat, cols, keysToWrite=keys)
     return catalogDict
+
+
+class _BatchCatalogs(dict):
+    """catalogDict of one tile batch ('<label>#<tileName>' -> {'catalog': ...}, the reference's layout) that also carries the
+    batch's rows as one table (.flat)."""
+    flat = None
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -803,13 +811,17 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     ranks ``areaMask_rank<r>.fits``) and ``<tile>/RMSMap_<filter>#<tile>.fits`` of the first filter of the list (the photFilter when
     there is one), as the reference writes them (pipelines.py:266-267, 336; filters.py:760-762) -- see nemo_b200/fitsio.py.
 
-    Only Fourier-space matched filters with a common noise set-up are batched here; use ``filters.filterMaps`` +
-    ``photometry.findObjects`` directly for anything else.
+    Batched here: Fourier-space matched filters with a common noise set-up (startTileBatch), and real-space matched filters
+    whose kernel is built from the whole tile and symmetrised (nemo_b200/realspace.py).  Any other filter set goes through the
+    reference's per-tile loop over the class API (_perTileLoop).
     """
     ops = device.getOps(precision)
     parDict = config.parDict
     filtersList = _orderedFilters(parDict)
-    if not _canBatch(filtersList):
+    from . import realspace
+    realSpaceBatched = (not _canBatch(filtersList)) and realspace.canBatch(filtersList, config.tileMaps) and not (
+        cacheFilters or useCachedFilters or useCachedRMSMap or restage or injectCatalogs is not None or writeAreaMask or writeRMSMaps)
+    if not _canBatch(filtersList) and not realSpaceBatched:
         if cacheFilters or useCachedRMSMap:
             raise Exception("filter caches on the device are kept by the batched (Fourier matched filter) path only")
         catalogDict = _perTileLoop(config, filtersList, measureFluxes=measureFluxes, invertMap=invertMap, verbose=verbose,
@@ -851,22 +863,43 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
         caches = getattr(config, '_cache', None)
         if caches is None or len(caches) != len(batches):
             raise Exception("no cached filters for these tile batches: run filterMapsAndMakeCatalogs(config, cacheFilters=True) first")
-    # with a cached RMS map the pixel window is undone after the S/N map has been made (pipelines.py:171-173, 216-232); the
-    # batched path always makes the S/N map before undoing the window, so the same flag serves both cases
-    results = processBatches(ops, batches, filtersList, templatesList, parDict, upload=True,
-                             undoPixelWindow=parDict.get('undoPixelWindow', True), measureFluxes=measureFluxes, invertMap=invertMap,
-                             keepMaps=cacheFilters, caches=caches, useCachedRMSMap=useCachedRMSMap, rmsTables=makeRMSTables,
-                             beforeSubmit=beforeSubmit, prepare=prepare,
-                             collect=(('areaMask',) if writeAreaMask else ()) + (('RMSMap',) if writeRMSMaps else ()))
+    if realSpaceBatched:
+        # real-space matched filters (filters.py:862-1218): kernels of all tiles of a batch built and applied together
+        # (nemo_b200/realspace.py); the next batch is uploaded while this one's catalogs are assembled
+        results = []
+        for i, batch in enumerate(batches):
+            uploadedHere = batch.dev is None
+            if uploadedHere:
+                batch.upload()
+            job = realspace.startRealSpaceTileBatch(ops, batch, filtersList, templatesList[i], parDict,
+                                                    undoPixelWindow=parDict.get('undoPixelWindow', True), invertMap=invertMap,
+                                                    rmsTables=makeRMSTables)
+            if i + 1 < len(batches) and batches[i + 1].dev is None:
+                batches[i + 1].upload()
+                batches[i + 1]._uploadedByDriver = True
+            results.append(finishTileBatch(job, measureFluxes=measureFluxes))
+            if uploadedHere or getattr(batch, '_uploadedByDriver', False):
+                batch.dev = None
+                batch._uploadedByDriver = False
+    else:
+        # with a cached RMS map the pixel window is undone after the S/N map has been made (pipelines.py:171-173, 216-232); the
+        # batched path always makes the S/N map before undoing the window, so the same flag serves both cases
+        results = processBatches(ops, batches, filtersList, templatesList, parDict, upload=True,
+                                 undoPixelWindow=parDict.get('undoPixelWindow', True), measureFluxes=measureFluxes, invertMap=invertMap,
+                                 keepMaps=cacheFilters, caches=caches, useCachedRMSMap=useCachedRMSMap, rmsTables=makeRMSTables,
+                                 beforeSubmit=beforeSubmit, prepare=prepare,
+                                 collect=(('areaMask',) if writeAreaMask else ()) + (('RMSMap',) if writeRMSMaps else ()))
     if writeAreaMask or writeRMSMaps:
         _writeSelFnMaps(config, batches, results, filtersList[0]['label'], comm)
     if cacheFilters:
         config._cache = [{'filtH': ex['filtH'], 'signalNorm': ex['signalNorm'], 'RMSMap': ex['RMSMap'], 'fRel': ex['fRel']}
                          for _, ex in results]
     RMSTabs = {}
+    flatTables = []
     for batch, (cd, extras) in zip(batches, results):
         names = batch.tileNames
         catalogDict.update(cd)
+        flatTables.append(getattr(cd, 'flat', None) if isinstance(cd, _BatchCatalogs) else False)
         for o, tab in enumerate(extras.get('RMSTabs') or []):
             RMSTabs[filtersList[o % len(filtersList)]['label'] + "#" + names[o // len(filtersList)]] = tab
         if extras['noiseTable'] is None:
@@ -874,7 +907,9 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
         tab = extras['noiseTable']
         for o in range(tab.shape[0]):
             noiseTables[filtersList[o % len(filtersList)]['label'] + "#" + names[o // len(filtersList)]] = tab[o]
-    optimalCatalog = catalogs.makeOptimalCatalog(catalogDict, constraintsList=parDict.get('catalogCuts', []), ops=ops)
+    # (every batch brought its rows as one table: stack those few instead of the hundreds of per-image tables -- same rows, same order)
+    stacked = [t for t in flatTables if t is not None] if all(t is not False for t in flatTables) else None
+    optimalCatalog = catalogs.makeOptimalCatalog(catalogDict, constraintsList=parDict.get('catalogCuts', []), ops=ops, stacked=stacked)
     if comm is not None and comm.size > 1:
         from . import distributed
         havePhot = parDict.get('photFilter') is not None and any(f['label'] == parDict['photFilter'] for f in filtersList)

@@ -704,6 +704,47 @@ def test_conv2d_f64(ops64, report, k):
     assert err < 1e-12 and errP < 1e-12
 
 
+@pytest.mark.parametrize("k,shape", [((29, 29), (200, 264)), ((5, 7), (97, 131)), ((1, 1), (64, 64)), ((63, 3), (128, 70))])
+def test_conv2d_batch_f64(ops64, report, k, shape):
+    """nb_conv2d_batch (register-blocked K13 with a kernel per image) against scipy.ndimage.convolve: templates shared by the
+    tiles (inMod) and the filters of a tile (inDiv), normalisation and mask fused."""
+    from scipy import ndimage
+    rng = np.random.default_rng(41)
+    H, W = shape
+    nT, S, F = 3, 2, 2
+    nOut = nT * S
+    kern = rng.standard_normal((nOut, F) + k)
+    norm = rng.uniform(0.5, 2.0, nOut)
+    mask = (rng.random((nT, H, W)) > 0.1).astype(np.uint8)
+    tiles = rng.standard_normal((nT, F, H, W))
+    templ = rng.standard_normal((S, F, H, W))
+    kT = ops64.to_device(kern, ops64.torch.float64)
+    got = _np(ops64.conv2d_batch(ops64.to_device(tiles), kT, nOut, norm=ops64.to_device(norm, ops64.torch.float64),
+                                 mask=ops64.to_device(mask, ops64.torch.uint8), inDiv=S, maskDiv=S))
+    gotT, planes = ops64.conv2d_batch(ops64.to_device(templ), kT, nOut, inMod=S, wantPlanes=True)
+    gotT, planes = _np(gotT), _np(planes)
+    worst = 0.0
+    for o in range(nOut):
+        ref = sum(ndimage.convolve(tiles[o // S, f], kern[o, f]) for f in range(F)) * norm[o] * mask[o // S]
+        refT = [ndimage.convolve(templ[o % S, f], kern[o, f]) for f in range(F)]
+        worst = max(worst, _relerr(got[o], ref), _relerr(gotT[o], sum(refT)), _relerr(planes[o], np.array(refT)))
+    # one common kernel for every image
+    got1 = _np(ops64.conv2d_batch(ops64.to_device(tiles), ops64.to_device(kern[0], ops64.torch.float64), nT))
+    for t in range(nT):
+        worst = max(worst, _relerr(got1[t], sum(ndimage.convolve(tiles[t, f], kern[0, f]) for f in range(F))))
+    report("conv2d_batch_f64", k=k, shape=shape, relerr=worst)
+    assert worst < 1e-12
+
+
+def test_mean_over_rows_f64(ops64, report):
+    rng = np.random.default_rng(42)
+    x = rng.standard_normal((5, 301, 211))
+    got = _np(ops64.mean_over_rows(ops64.to_device(x)))
+    err = _relerr(got, x.mean(axis=1))
+    report("mean_over_rows", relerr=err)
+    assert err < 1e-13
+
+
 @pytest.mark.parametrize("shape", [(840, 1440), (300, 420)])
 def test_rfft2_irfft2_smooth_size_f32(ops32, report, shape):
     """The compile-time mixed-radix passes in fp32 storage mode (sides 2-3-5-7-smooth with a plan in sfft_host.cuh)."""

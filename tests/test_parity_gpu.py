@@ -281,7 +281,63 @@ def test_batched_pipeline_matches_per_tile_oracle(report):
             nObj += len(refCat)
     assert nObj >= 6
     assert len(opt) > 0 and len(opt) <= nObj
+    # the driver merges the batches' stacked rows; stacking the per-image tables (the reference's vstack) gives the same catalog
+    optPerImage = catalogs.makeOptimalCatalog(config.catalogDict)
+    assert len(optPerImage) == len(opt)
+    for k in optPerImage.keys():
+        a, b = np.asarray(opt[k]), np.asarray(optPerImage[k])
+        assert np.array_equal(a, b), k
     report("batched_pipeline", objects=nObj, optimal=len(opt))
+
+
+def test_batched_real_space_driver(report, monkeypatch):
+    """Real-space matched filters through the batched driver (nemo_b200/realspace.py: kernels of all tiles of a batch built and
+    applied together; BASELINE configs[2] shape, reduced): catalogs against the oracle's per-tile loop
+    (filters.py:862-1218) and against this library's own per-tile class loop; two filter scales with a photFilter."""
+    from nemo_b200 import pipelines, realspace
+    tileMaps = {}
+    for t in range(3):
+        md, _ = synth.makeTile(shape=(256, 256), freqsGHz=(97.8, 149.6), noiseUK=(60.0, 40.0), beamFWHMArcmin=(2.2, 1.4),
+                               numObjects=6, kind='clusters', cmb=True, seed=170 + t)
+        tileMaps['tile%d' % t] = md
+
+    def rs(label, M, z):
+        p = {'M500MSun': M, 'z': z, 'outputUnits': 'yc', 'bckSub': True, 'bckSubScaleArcmin': 14.0, 'edgeTrimArcmin': 0.,
+             'noiseParams': {'method': 'dataMap', 'matchedFilterClass': 'ArnaudModelMatchedFilter', 'RADecSection': None,
+                             'kernelMaxArcmin': 7., 'symmetrize': True, 'noiseGridArcmin': 20.}}
+        return {'label': label, 'class': 'ArnaudModelRealSpaceMatchedFilter', 'params': p}
+    filtersList = [rs('RS_M2e14_z0p4', 2e14, 0.4), rs('RS_M4e14_z0p3', 4e14, 0.3)]
+    parDict = {'mapFilters': filtersList, 'photFilter': 'RS_M2e14_z0p4', 'thresholdSigma': 4.0, 'minObjPix': 1, 'findCenterOfMass': True,
+               'useInterpolator': True, 'rejectBorder': 0}
+    assert realspace.canBatch(filtersList, tileMaps)
+    config = pipelines.SimpleConfig(parDict, tileMaps)
+    opt = pipelines.filterMapsAndMakeCatalogs(config, verbose=False, tilesPerBatch=2)
+    batchedDict = config.catalogDict
+    # the oracle, in the reference's loop order
+    nObj = 0
+    for tileName, md in tileMaps.items():
+        phot = None
+        for f in pipelines._orderedFilters(config.parDict):
+            ref = filters_ref.filterMaps(md, _copyFilter(f), tileName)
+            if f['label'] == parDict['photFilter']:
+                phot = {'SNMap': ref['SNMap'], 'data': ref['data']}
+            refCat = photometry_ref.findObjects(ref, **DETECT)
+            photometry_ref.measureFluxes(refCat, ref, None, photFilteredMapDict=phot)
+            _compareCatalogs(batchedDict[f['label'] + "#" + tileName]['catalog'], refCat, ['SNR', 'y_c', 'err_y_c', 'fixed_SNR', 'fixed_y_c'])
+            nObj += len(refCat)
+    assert nObj >= 4 and 0 < len(opt) <= nObj
+    # the per-tile class loop of this library gives the same catalogs
+    monkeypatch.setattr(realspace, 'canBatch', lambda *a, **k: False)
+    config2 = pipelines.SimpleConfig(parDict, tileMaps)
+    opt2 = pipelines.filterMapsAndMakeCatalogs(config2, verbose=False)
+    assert len(opt2) == len(opt)
+    for key, entry in config2.catalogDict.items():
+        a, b = entry['catalog'], batchedDict[key]['catalog']
+        assert len(a) == len(b)
+        if len(a) > 0:
+            for col in ['SNR', 'y_c', 'fixed_SNR', 'x', 'y']:
+                assert np.allclose(np.asarray(a[col], dtype=float), np.asarray(b[col], dtype=float), rtol=1e-8, atol=1e-8), (key, col)
+    report("batched_real_space", objects=nObj, optimal=len(opt))
 
 
 @pytest.mark.parametrize("findCenterOfMass", [True, False])
