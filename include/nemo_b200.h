@@ -166,8 +166,9 @@ int nb_cell_rms(int prec, const void* map, const void* wmed, int nImg, int S, in
                 double* edges, cudaStream_t stream);
 
 /* nb_cell_rms with the RMS estimator of noiseParams['RMSEstimator'] (nemo/filters.py:460-479): 0 = 3-sigma clipped standard
- * deviation (the default, what nb_cell_rms does), 1 = 'percentile' = np.percentile(abs(binValues), 68.3).  Estimators other
- * than 0 run on the streaming kernel (exact order statistics by radix select over the cell). */
+ * deviation (the default, what nb_cell_rms does), 1 = 'percentile' = np.percentile(abs(binValues), 68.3), 2 = 'biweight' =
+ * astropy.stats.biweight_scale(binValues, c = 9.0, modify_sample_size = True) for bins of at least 10 pixels, else 0.
+ * Estimators other than 0 run on the streaming kernel (exact order statistics by radix select over the cell). */
 int nb_cell_rms_est(int prec, const void* map, const void* wmed, int nImg, int S, int H, int W, const int* yChunks, int ny,
                     const int* xChunks, int nx, int overlapPix, int numBins, int estimator, void* rms, double* table, double* edges,
                     cudaStream_t stream);

@@ -133,9 +133,11 @@ __device__ double select_kth(const T* __restrict__ m, const T* __restrict__ wm, 
 
 // k-th smallest (0-based) |value| among the good pixels of the cell whose weight lies in [wlo, whi): the same radix select on
 // the bit pattern of |v| (non-negative doubles order like their bits) -- the 'percentile' RMS estimator (filters.py:464-465)
-template <typename T>
+// SIGNED = false: key |v - shiftBy| (0: the percentile estimator; the median: the median absolute deviation of the biweight
+// estimator); SIGNED = true: key v - shiftBy itself through the order-preserving map enc_w (the median)
+template <typename T, bool SIGNED = false>
 __device__ double select_kth_abs(const T* __restrict__ m, const T* __restrict__ wm, int W, CellGeom g, long long k, double wlo, double whi,
-                                 int* s_hist, unsigned long long* s_sel) {
+                                 int* s_hist, unsigned long long* s_sel, double shiftBy = 0.0) {
     unsigned long long prefix = 0, maskbits = 0;
     const int cw = g.x1 - g.x0;
     const int n = (g.y1 - g.y0) * cw;
@@ -148,7 +150,7 @@ __device__ double select_kth_abs(const T* __restrict__ m, const T* __restrict__ 
             const size_t off = (size_t)(g.y0 + r) * W + g.x0 + c;
             const double v = (double)m[off], w = (double)wm[off];
             if (v != 0.0 && w >= wlo && w < whi) {
-                const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(v));
+                const unsigned long long key = SIGNED ? enc_w(v - shiftBy) : (unsigned long long)__double_as_longlong(fabs(v - shiftBy));
                 if ((key & maskbits) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 255ULL)], 1);
             }
         }
@@ -169,7 +171,17 @@ __device__ double select_kth_abs(const T* __restrict__ m, const T* __restrict__ 
         maskbits |= 0xFFULL << shift;
     }
     __syncthreads();
-    return __longlong_as_double((long long)prefix);
+    return SIGNED ? dec_w(prefix) : __longlong_as_double((long long)prefix);
+}
+
+// np.median of the keys above: the middle order statistic, or the mean of the two middle ones
+template <typename T, bool SIGNED>
+__device__ double median_of_bin(const T* __restrict__ m, const T* __restrict__ wm, int W, CellGeom g, long long n, double wlo, double whi,
+                                int* s_hist, unsigned long long* s_sel, double off) {
+    if (n & 1LL) return select_kth_abs<T, SIGNED>(m, wm, W, g, n / 2, wlo, whi, s_hist, s_sel, off);
+    const double a = select_kth_abs<T, SIGNED>(m, wm, W, g, n / 2 - 1, wlo, whi, s_hist, s_sel, off);
+    const double b = select_kth_abs<T, SIGNED>(m, wm, W, g, n / 2, wlo, whi, s_hist, s_sel, off);
+    return (a + b) / 2.0;
 }
 
 template <typename T>
@@ -276,6 +288,40 @@ __global__ void __launch_bounds__(CR_THREADS) cell_rms_stream_kernel(const T* __
                 rms = a + diff * gmm;           // numpy _lerp
                 if (gmm >= 0.5) rms = bb - diff * (1.0 - gmm);
                 if (gmm == 0.0) rms = a;
+            }
+        } else if (estimator == 2) {
+            // astropy.stats.biweight_scale(binValues, c = 9.0, modify_sample_size = True) for bins of at least 10 pixels, else 0
+            // (filters.py:461-465): M = median, MAD = median |v - M|, u = (v - M) / (c MAD), over |u| < 1:
+            // n' = count, f1 = sum (v - M)^2 (1 - u^2)^4, f2 = sum (1 - u^2) (1 - 5 u^2); scale = sqrt(n' f1) / |f2|; 0 when MAD = 0
+            if (c0 >= 10) {
+                const long long nn = (long long)c0;
+                const double M = median_of_bin<T, true>(m, wm, W, g, nn, lo, hi, s_hist, s_sel, 0.0);
+                const double mad = median_of_bin<T, false>(m, wm, W, g, nn, lo, hi, s_hist, s_sel, M);
+                if (mad > 0.0) {
+                    double cntU = 0, f1 = 0, f2 = 0, dmy = 0;
+                    const double cm = 9.0 * mad;
+                    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+                        const int r = e / cw, c = e - r * cw;
+                        const size_t off = (size_t)(g.y0 + r) * W + g.x0 + c;
+                        const double v = (double)m[off];
+                        const double w = (double)wm[off];
+                        if (v != 0.0 && w >= lo && w < hi) {
+                            const double d = v - M;
+                            double u = d / cm;
+                            if (fabs(u) < 1.0) {
+                                u = u * u;
+                                const double t = 1.0 - u;
+                                cntU += 1.0;
+                                f1 += d * d * (t * t) * (t * t);
+                                f2 += t * (1.0 - 5.0 * u);
+                            }
+                        }
+                    }
+                    block_sum2(cntU, f1, s_red);
+                    block_sum2(f2, dmy, s_red);
+                    const double af2 = fabs(f2);
+                    rms = sqrt(cntU * f1 / (af2 * af2));
+                }
             }
         } else if (c0 > 0) {
             double mean = s0 / c0;
@@ -1515,7 +1561,7 @@ int nb_cell_rms_est(int prec, const void* map, const void* wmed, int nImg, int S
     NB_REQUIRE(map && wmed && yChunks && xChunks && table && edges && nImg > 0 && S > 0 && ny > 0 && nx > 0, NB_ERR_ARG,
                "nb_cell_rms_est: bad arguments");
     NB_REQUIRE(numBins >= 1 && numBins <= 64, NB_ERR_ARG, "nb_cell_rms_est: numBins %d out of range (1..64)", numBins);
-    NB_REQUIRE(estimator == 0 || estimator == 1, NB_ERR_UNSUPPORTED, "nb_cell_rms_est: estimator %d not implemented (0 clip, 1 percentile)", estimator);
+    NB_REQUIRE(estimator >= 0 && estimator <= 2, NB_ERR_UNSUPPORTED, "nb_cell_rms_est: estimator %d not implemented (0 clip, 1 percentile, 2 biweight)", estimator);
     if (prec == NB_PREC_F64)
         return cell_rms_t<double>(map, wmed, nImg, S, H, W, yChunks, ny, xChunks, nx, overlapPix, numBins, rms, table, edges, st, estimator);
     if (prec == NB_PREC_F32)

@@ -26,7 +26,7 @@ def noiseGrid(shape, noiseParams, pixDeg):
     ('smart', numBins) for its 'smart' branch (:366-372)."""
     estimator = 'clip'
     if 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] == 'biweight':
-        raise Exception("RMSEstimator 'biweight' is not implemented in nemo_b200 (astropy's biweight_scale; 3-sigma clipping and 'percentile' are)")
+        estimator = 'biweight'
     if 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] == 'percentile':
         estimator = 'percentile'
     if noiseParams.get('noiseGridArcmin') == "smart":

@@ -249,10 +249,11 @@ class Ops(object):
         self.launches += 1
         return out
 
-    ESTIMATORS = {'clip': 0, 'percentile': 1}
+    ESTIMATORS = {'clip': 0, 'percentile': 1, 'biweight': 2}
 
     def cell_rms(self, maps, wmed, S, yChunks, xChunks, overlapPix, numBins, estimator='clip', paint=True):
-        """Cell RMS tables (estimator 'clip': 3-sigma clipped standard deviation; 'percentile': 68.3th percentile of |v|) and
+        """Cell RMS tables (estimator 'clip': 3-sigma clipped standard deviation; 'percentile': 68.3th percentile of |v|;
+        'biweight': astropy's biweight_scale with c = 9 and the sample size counted inside the cut, 0 below 10 pixels) and
         (paint=True) the painted RMS map; with paint=False returns (None, table, edges)."""
         self._check(maps, self.dtype, 'maps')
         self._check(wmed, self.dtype, 'wmed')
@@ -264,7 +265,7 @@ class Ops(object):
         yc = (ctypes.c_int * (ny + 1))(*[int(v) for v in yChunks])
         xc = (ctypes.c_int * (nx + 1))(*[int(v) for v in xChunks])
         if estimator not in self.ESTIMATORS:
-            raise Exception("RMSEstimator '%s' is not implemented in nemo_b200 (clip, percentile)" % estimator)
+            raise Exception("RMSEstimator '%s' is not implemented in nemo_b200 (clip, percentile, biweight)" % estimator)
         if estimator == 'clip':
             _lib.call('nb_cell_rms', self.prec, _ptr(maps), _ptr(wmed), nImg, int(S), H, W, yc, ny, xc, nx, int(overlapPix), int(numBins),
                       _ptr(rms), _ptr(table), _ptr(edges), self._stream())

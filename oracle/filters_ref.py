@@ -26,6 +26,36 @@ from . import signals_ref as signals
 from .wcs_stub import calcAngSepDeg
 
 
+def biweight_scale(data, c=9.0, modify_sample_size=False):
+    """astropy.stats.biweight_scale (astropy is absent from this image; third-party dependency of the reference, called at
+    nemo/filters.py:385 and :462 with c = 9.0, modify_sample_size = True).  Restated from astropy's published definition
+    (astropy.stats.biweight.biweight_midvariance, astropy >= 3.1): with M the median, MAD the median absolute deviation,
+    u = (x - M) / (c MAD) and the sums over |u| < 1,
+
+        zeta^2 = n sum (x - M)^2 (1 - u^2)^4 / (sum (1 - u^2)(1 - 5 u^2))^2,
+
+    n = the number of points with |u| < 1 when modify_sample_size, else the sample size; 0 where MAD = 0; scale = sqrt.
+    PARITY UNPINNED for this function: there is no astropy here to run it against; tests/test_oracle.py checks the properties
+    the definition implies (location / scale behaviour, the Gaussian limit, a hand-evaluated sample)."""
+    data = np.asanyarray(data).astype(np.float64)
+    M = np.median(data)
+    d = data - M
+    mad = np.median(np.abs(d))
+    if mad == 0.:
+        return 0.0
+    u = d / (c * mad)
+    mask = np.abs(u) >= 1
+    u = u ** 2
+    n = (~mask).sum() if modify_sample_size else data.size
+    f1 = d * d * (1. - u) ** 4
+    f1[mask] = 0.
+    f1 = f1.sum()
+    f2 = (1. - u) * (1. - 5. * u)
+    f2[mask] = 0.
+    f2 = np.abs(np.sum(f2)) ** 2
+    return float(np.sqrt(n * f1 / f2))
+
+
 class MapFilter(object):
 
     def __init__(self, label, unfilteredMapsDictList, paramsDict, tileName='PRIMARY', writeFilter=False,
@@ -88,11 +118,10 @@ class MapFilter(object):
     def makeNoiseMap(self, mapData):
         medWeights = np.median(np.array([m['weights'] for m in self.unfilteredMapsDictList]), axis=0)
         noiseParams = self.params['noiseParams']
-        if 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] == 'biweight':
-            raise Exception("oracle: the biweight estimator needs astropy.stats.biweight_scale, absent here")
+        biweightEstimator = 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] == 'biweight'
         percentileEstimator = 'RMSEstimator' in noiseParams and noiseParams['RMSEstimator'] == 'percentile'
-        if percentileEstimator and noiseParams.get('noiseGridArcmin') == "smart":
-            raise Exception("oracle: percentile estimator restated for the grid branch only")
+        if (percentileEstimator or biweightEstimator) and noiseParams.get('noiseGridArcmin') == "smart":
+            raise Exception("oracle: percentile / biweight estimators restated for the grid branch only")
         if noiseParams.get('noiseGridArcmin') == "smart":
             # 'smart' branch (filters.py:366-407): numBins - 1 whole-map bins between the smallest and the largest median weight,
             # strict inequalities on both sides (a pixel whose weight equals an edge is in no bin)
@@ -159,7 +188,13 @@ class MapFilter(object):
                     binMax = binEdges[b + 1]
                     binMask = np.logical_and(weightValues >= binMin, weightValues < binMax)
                     binValues = chunkValues[binMask * goodAreaMask]
-                    if percentileEstimator:
+                    if biweightEstimator:
+                        # filters.py:461-465
+                        if (binMask * goodAreaMask).sum() >= 10:
+                            chunkRMS = biweight_scale(binValues, c=9.0, modify_sample_size=True)
+                        else:
+                            chunkRMS = 0.
+                    elif percentileEstimator:
                         # filters.py:464-465; an empty bin gives nan (with a numpy warning), which paints nothing
                         chunkRMS = np.percentile(abs(binValues), 68.3) if len(binValues) > 0 else np.nan
                     elif np.not_equal(binValues, 0).sum() != 0:

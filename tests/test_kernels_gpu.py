@@ -386,6 +386,25 @@ def test_cell_rms_percentile_estimator(ops64, report, numBins, shape, gridArcmin
     assert err < 1e-14
 
 
+@pytest.mark.parametrize("numBins,shape,gridArcmin", [(1, (256, 256), 20.0), (4, (300, 420), 20.0), (8, (512, 640), 40.0), (64, (128, 128), 20.0)])
+def test_cell_rms_biweight_estimator(ops64, report, numBins, shape, gridArcmin):
+    """RMSEstimator: 'biweight' (filters.py:461-465): astropy's biweight_scale(binValues, c = 9, modify_sample_size = True) per
+    cell and weight bin for bins of at least 10 pixels (the last case has bins below that: RMS 0, nothing painted), median and
+    median absolute deviation by exact radix select, against the oracle's restatement of the published definition."""
+    m, weights = _noise_case(shape, 80 + numBins)
+    ref = _oracle_noise(m, weights, 0.5 / 60, gridArcmin, numBins if numBins > 1 else None, estimator='biweight')
+    H, W = m.shape
+    gridSize = int(round((gridArcmin / 60.) / (0.5 / 60)))
+    yc, xc, ov = _chunks(H, gridSize), _chunks(W, gridSize), gridSize // 2
+    wm = ops64.median_weights(ops64.to_device(np.array(weights)[None]))
+    rms, table, edges = ops64.cell_rms(ops64.to_device(m[None]), wm, 1, yc, xc, ov, numBins, estimator='biweight')
+    got = _np(rms)[0]
+    err = _relerr(got, ref)
+    report("cell_rms_biweight", numBins=numBins, shape=shape, relerr=err, painted=float((ref > 0).mean()))
+    assert np.array_equal(got == 0, ref == 0)
+    assert err < 1e-12
+
+
 @pytest.mark.parametrize("numBins", [2, 6, 100])
 @pytest.mark.parametrize("shape", [(256, 256), (300, 420)])
 def test_smart_noise_bins_f64(ops64, report, numBins, shape):

@@ -326,3 +326,24 @@ def test_model_image_painter_matches_reference_run():
                                                   minSNR=inp['minSNR']), ref['paint_cut'])
     far = dict(inp['catalog'], RADeg=inp['catalog']['RADeg'] + 90.0)
     assert maps_ref.makeModelImage(inp['shape'], inp['wcs'], far, beam) is None
+
+
+def test_biweight_scale_restatement():
+    """oracle.filters_ref.biweight_scale (astropy absent: restated from the published definition, parity unpinned): a sample
+    evaluated by hand, location / scale behaviour, robustness to an outlier, the Gaussian limit and the MAD = 0 case."""
+    from oracle.filters_ref import biweight_scale
+    # [1, 2, 3, 4, 100]: M = 3, MAD = 1, u = d / 9; the outlier has |u| > 1; n' = 4
+    # d = -2, -1, 0, 1: f1 = 4 (1 - 4/81)^4 + 2 (1 - 1/81)^4, f2 = (1 - 4/81)(1 - 20/81) + 2 (1 - 1/81)(1 - 5/81) + 1
+    a, b = 1 - 4 / 81., 1 - 1 / 81.
+    f1 = 4 * a ** 4 + 2 * b ** 4
+    f2 = a * (1 - 20 / 81.) + 2 * b * (1 - 5 / 81.) + 1
+    assert abs(biweight_scale(np.array([1., 2, 3, 4, 100]), 9.0, True) - np.sqrt(4 * f1) / f2) < 1e-14
+    # without modify_sample_size the factor is the sample size
+    assert abs(biweight_scale(np.array([1., 2, 3, 4, 100]), 9.0, False) - np.sqrt(5 * f1) / f2) < 1e-14
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal(100000)
+    s0 = biweight_scale(x, 9.0, True)
+    assert abs(s0 - 1.0) < 0.02
+    assert abs(biweight_scale(3.0 * x + 5.0, 9.0, True) - 3.0 * s0) < 1e-9
+    assert abs(biweight_scale(np.r_[x, 1e9], 9.0, True) - s0) < 1e-4
+    assert biweight_scale(np.array([2., 2, 2, 2, 7]), 9.0, True) == 0.0

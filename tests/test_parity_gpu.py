@@ -694,8 +694,9 @@ def test_rms_area_tables_match_reference_getRMSTab(report):
         report("rms_area_tables %s: %d levels in the last tile, %.3f deg2" % (f['params']['noiseParams']['noiseGridArcmin'], len(values), areas.sum()))
 
 
-def test_percentile_rms_estimator_end_to_end(report):
-    """noiseParams RMSEstimator: 'percentile' through filterMaps and the batched driver."""
+@pytest.mark.parametrize("estimator", ['percentile', 'biweight'])
+def test_rms_estimator_end_to_end(report, estimator):
+    """noiseParams RMSEstimator: 'percentile' / 'biweight' (filters.py:460-465) through filterMaps and the batched driver."""
     from nemo_b200 import filters, pipelines
     tileMaps = {}
     for t in range(2):
@@ -703,11 +704,11 @@ def test_percentile_rms_estimator_end_to_end(report):
                                borderPix=20)
         tileMaps['t%d' % t] = md
     f = _beam(grid=20., numBins=2, edgeTrimArcmin=0.0)
-    f['params']['noiseParams']['RMSEstimator'] = 'percentile'
+    f['params']['noiseParams']['RMSEstimator'] = estimator
     for name, md in tileMaps.items():
         ref = filters_ref.filterMaps(md, _copyFilter(f), name)
         got = filters.filterMaps(md, _copyFilter(f), name, verbose=False)
-        _compareMaps(got, ref, report, "beam_percentile_" + name)
+        _compareMaps(got, ref, report, "beam_" + estimator + "_" + name)
     parDict = {'mapFilters': [f], 'photFilter': None, 'thresholdSigma': 4.0, 'minObjPix': 1, 'findCenterOfMass': True,
                'useInterpolator': True, 'rejectBorder': 0}
     config = pipelines.SimpleConfig(parDict, tileMaps)

@@ -30,4 +30,11 @@ if [[ $what == *full* ]]; then
   sz=$(stat -c %s $rep.ncu-rep 2>/dev/null || echo 0)
   if [ "$sz" -gt 0 ] && [ "$sz" -lt 30000000 ]; then cp $rep.ncu-rep $out/; fi
 fi
+if [[ $what == *rsprof* ]]; then
+  rep=/tmp/${tag}_realspace_full
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv2d|gauss_" -s 4 -c 6 -o $rep -f \
+      python tools/time_realspace_batched.py --tiles 16 --steps 1 > $out/${tag}_ncu_realspace.log 2>&1
+  ncu -i $rep.ncu-rep --page raw --csv > $out/${tag}_realspace_full_raw.csv 2>/dev/null
+  ncu -i $rep.ncu-rep --page source --csv > $out/${tag}_realspace_full_source.csv 2>/dev/null
+fi
 du -sh $out; ls -la $out | grep ${tag}_
