@@ -457,7 +457,9 @@ def main():
         ent = tj.get(args.workload, {}).get(args.precision, {}).get(top['kernel'])
         if ent is not None:
             # ncu captured one launch of some batch size: scale to the bytes one average launch of this run moves
-            traffic = ent['dram_bytes_per_launch'] * (top['algorithmic_bytes_per_step'] / top['launches_per_step']) / ent['algorithmic_bytes_per_launch']
+            traffic = ent['dram_bytes_per_launch']
+            if ent.get('algorithmic_bytes_per_launch'):
+                traffic *= (top['algorithmic_bytes_per_step'] / top['launches_per_step']) / ent['algorithmic_bytes_per_launch']
             trafficSrc = ent['source']
     roofline = None
     if top is not None:

@@ -12,6 +12,7 @@ bandwidth-bound.  There is no collective on the data path -- (tile, scale) work 
 
 import os
 import numpy as np
+from collections.abc import Mapping
 
 from . import catalogs
 
@@ -192,6 +193,35 @@ def allGatherCatalog(comm, tab, keys, labels=None, tileNames=None, objIdent='ACT
     return ordered
 
 
+class GatheredTables(Mapping):
+    """Read-only {'<label>#<tileName>': table} over the row blocks a gather returned (columns: label index, tile index, flattened
+    table); the key index is built the first time it is needed."""
+
+    def __init__(self, blocks, labels, tileNames, shape):
+        self._blocks, self._labels, self._tiles, self._shape = blocks, labels, tileNames, shape
+        self._index = None
+
+    def _idx(self):
+        if self._index is None:
+            self._index = {}
+            for b, fl in enumerate(self._blocks):
+                li, ti = fl[:, 0].astype(int), fl[:, 1].astype(int)
+                for r in range(fl.shape[0]):
+                    self._index[self._labels[li[r]] + "#" + self._tiles[ti[r]]] = (b, r)
+        return self._index
+
+    def __getitem__(self, key):
+        b, r = self._idx()[key]
+        row = self._blocks[b][r, 2:]
+        return row.reshape(self._shape) if self._shape is not None else row.copy()
+
+    def __iter__(self):
+        return iter(self._idx())
+
+    def __len__(self):
+        return sum(fl.shape[0] for fl in self._blocks)
+
+
 def gatherNoiseTables(comm, noiseTables, labels=None, tileNames=None):
     """{label#tile: [nCells, nBins] array} from every rank -> the union on every rank (rank 0 is the consumer in the
     reference, pipelines.py:405-420; an all-gather costs the same for these sizes).  With `labels` / `tileNames` the keys
@@ -215,11 +245,10 @@ def gatherNoiseTables(comm, noiseTables, labels=None, tileNames=None):
         for i, k in enumerate(keysSorted[:flat.shape[0]]):
             lab, tile = k.split('#', 1)
             codes[i] = (lutL[lab], lutT[tile])
-        for fl in comm.allGatherArrays(np.concatenate([codes, flat], axis=1)):
-            for row in fl:
-                key = labels[int(row[0])] + "#" + tileNames[int(row[1])]
-                out[key] = row[2:].reshape(shape) if int(np.prod(shape)) == width else row[2:].copy()
-        return out
+        # thousands of tables at 8 ranks x 35 tiles x 16 scales: the rows stay in the gathered arrays and the
+        # '<label>#<tile>' dictionary is a view made on first use (building it eagerly cost 10 ms per step)
+        blocks = [fl for fl in comm.allGatherArrays(np.concatenate([codes, flat], axis=1)) if fl.shape[0] > 0]
+        return GatheredTables(blocks, labels, tileNames, shape if int(np.prod(shape)) == width else None)
     names = np.zeros((len(keysSorted), STR_WIDTH * 2), dtype=np.uint8)
     for i, s in enumerate(keysSorted):
         b = s.encode()[:STR_WIDTH * 2]
