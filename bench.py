@@ -125,23 +125,26 @@ def cpuBaseline(kind, cores=None, steps=1, warmup=0):
 
 
 # ------------------------------------------------------------------------------------------------------
-def algorithmicBytes(nT, F, S, H, W, E, rings=True, yc=True):
+def algorithmicBytes(nT, F, S, H, W, E, rings=True, yc=True, templateSpectraCached=True):
     """Algorithmic HBM bytes per step of every kernel of the batched Fourier path: own inputs read once + own outputs
     written once (SURVEY.md 8d / DESIGN.md), E = bytes per real (8 for f64, 4 for f32), complex = 2E.  Keyed by the names the
-    library's event timers report; kernels that serve several passes are charged the sum of those passes."""
+    library's event timers report; kernels that serve several passes are charged the sum of those passes.
+    templateSpectraCached: the transforms of the signal templates are made once per tile geometry (pipelines.templateSpectraOf),
+    not per batch, so no FFT pass of a step is charged for them."""
     N, Nc = H * W, H * (W // 2 + 1)
     P = F * (F + 1) // 2
     nOut = nT * S
     nPass = 2 if rings else 1
     nTpl = S * F
+    nTplFFT = 0 if templateSpectraCached else nTpl          # template images transformed inside the step
     rowFwd = N * E + Nc * 2 * E               # per image: real rows in, half spectrum out
     rowInv = Nc * 2 * E + N * E
     col = 2 * Nc * 2 * E                      # half spectrum in and out
-    fwdImgs = nT * F + nTpl + (2 * nTpl if yc else 0) + nOut         # maps, unit templates, (windowed) norm templates, window undo
-    plainColImgs = nT * F + nTpl + (nTpl if yc else 0)
-    windowColImgs = nOut + (nTpl if yc else 0)
+    fwdImgs = nT * F + nTplFFT + (2 * nTplFFT if yc else 0) + nOut         # maps, unit templates, (windowed) norm templates, window undo
+    plainColImgs = nT * F + nTplFFT + (nTplFFT if yc else 0)
+    windowColImgs = nOut + (nTplFFT if yc else 0)
     applyBytes = 2 * nOut * (F * Nc * E + Nc * 2 * E) + (nT * F + nTpl) * Nc * 2 * E     # filters in, product out; spectra once
-    invBytes = 2 * nOut * rowInv + nOut * N + nOut * rowInv + nOut * N * E + (nTpl * rowInv if yc else 0)   # + mask, + zero reference
+    invBytes = 2 * nOut * rowInv + nOut * N + nOut * rowInv + nOut * N * E + (nTplFFT * rowInv if yc else 0)   # + mask, + zero reference
     b = {}
     for rows in ('rfft_rows_kernel', 'bs_rows_fwd_kernel', 'sfft_rows_fwd_kernel'):
         b[rows] = fwdImgs * rowFwd

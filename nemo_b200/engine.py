@@ -111,14 +111,33 @@ def normAmplitudes(mapDicts, params, y0=2e-4):
 
 # ------------------------------------------------------------------------------------------------------
 # device pipeline
+def templateSpectra(ops, templUnit, templNorm, outputUnits):
+    """(fsig, fsigN): spectra of the unit templates (filters.py:590-611 takes their moduli) and of the normalisation templates
+    with the pixel window applied (:639-652; the unit spectra again for 'uK', :678-686).  A function of the templates only:
+    FilterSetTemplates keeps them per tile geometry, so that the tiles of a survey do not repeat these transforms."""
+    nS, F, H, W = templUnit.shape
+    Wc = W // 2 + 1
+    fsig = ops.rfft2(templUnit.reshape(nS * F, H, W), apodPix=0).reshape(nS, F, H, Wc)
+    if outputUnits == 'yc':
+        tn = templNorm.reshape(nS * F, H, W).clone()
+        ops.apply_window(tn, 1.0, restoreZeros=False)   # enmap.apply_window(signalMap, pow=1.0), filters.py:647
+        fsigN = ops.rfft2(tn, apodPix=0).reshape(nS, F, H, Wc)
+    elif outputUnits == 'uK':
+        fsigN = fsig
+    else:
+        raise Exception('need to specify "outputUnits" ("yc" or "uK") in filter params')
+    return fsig, fsigN
+
+
 def buildFourierFilters(ops, fmapsNoise, templUnit, templNorm, w, outputUnits, cy, cx, y0=2e-4, sigPerTile=False,
-                        wantFull=False, bckSubSigmas=None):
+                        wantFull=False, bckSubSigmas=None, spectra=None):
     """Builds matched filters for nT tiles x S scales.
 
     fmapsNoise [nT, F, H, Wc]    spectra the noise covariance is measured from
     templUnit  [nS*, F, H, W]    unit-normalised signal templates (nS* = S, or nT*S when sigPerTile)
     templNorm  same shape        templates with the normalisation amplitude, pixel window NOT yet applied ('yc');
                                  ignored for 'uK' (the unit templates are used, filters.py:678-686)
+    spectra    (fsig, fsigN) of templateSpectra() when they were made before (kept per tile geometry by the batched drivers)
     Returns dict: filtH [nT*S, F, H, Wc], filtFull (or None), signalNorm [nT*S] fp64, fRelWeights [nT*S, F] (or None),
     all on the device; nothing is synchronised.
     """
@@ -128,7 +147,8 @@ def buildFourierFilters(ops, fmapsNoise, templUnit, templNorm, w, outputUnits, c
     nS = templUnit.shape[0]
     S = nS // nT if sigPerTile else nS
     nOut = nT * S
-    fsig = ops.rfft2(templUnit.reshape(nS * F, H, W), apodPix=0).reshape(nS, F, H, Wc)
+    # spectra: (fsig, fsigN) made before (templateSpectra), e.g. once per tile geometry
+    fsig, fsigN = spectra if spectra is not None else templateSpectra(ops, templUnit, templNorm, outputUnits)
     if FUSED_FILTER_BUILD:
         # K2 + K3 in one kernel, the covariance staying in shared memory: saves the two fp64 [nT, P, H, W] arrays, but the 12-pixel
         # halos of its 32 x 32 tiles move more bytes through L2 than the covariance costs in HBM (0.51 ms against 0.39 ms for
@@ -140,13 +160,8 @@ def buildFourierFilters(ops, fmapsNoise, templUnit, templNorm, w, outputUnits, c
         filtH, filtFull = ops.build_filter(cov, fsig, w, S, sigPerTile, wantFull=wantFull)
         del cov
     if outputUnits == 'yc':
-        tn = templNorm.reshape(nS * F, H, W).clone()
-        ops.apply_window(tn, 1.0, restoreZeros=False)   # enmap.apply_window(signalMap, pow=1.0), filters.py:647
-        fsigN = ops.rfft2(tn, apodPix=0).reshape(nS, F, H, Wc)
-        del tn
         mode, numer = 1, y0
     elif outputUnits == 'uK':
-        fsigN = fsig
         mode, numer = 0, 1.0
     else:
         raise Exception('need to specify "outputUnits" ("yc" or "uK") in filter params')

@@ -211,9 +211,19 @@ class FilterSetTemplates(object):
         self.geometry = tileGeometry(mapDicts)
         self.unit = ops.to_device(np.array(unit))
         self.norm = ops.to_device(np.array(norm)) if len(norm) > 0 else None
+        self._spectra = None
         wcs = mapDicts[0]['wcs']
         cRADeg, cDecDeg = wcs.getCentreWCSCoords()
         self.cx, self.cy = wcs.wcs2pix(cRADeg, cDecDeg)
+
+
+def templateSpectraOf(ops, templates):
+    """(fsig, fsigN) of a FilterSetTemplates, made on first use and kept with it: the template transforms (K1 on 3 S F images and
+    a pixel-window pass on S F of them) are the same for every tile of a geometry -- a sixth of the FFT work of a DR5 batch.
+    Called outside CUDA-graph capture (the drivers call it when they fetch the templates)."""
+    if templates._spectra is None:
+        templates._spectra = engine.templateSpectra(ops, templates.unit, templates.norm, templates.outputUnits)
+    return templates._spectra
 
 
 def _sameNoiseSetup(filtersList):
@@ -241,6 +251,7 @@ def templatesFor(config, ops, filtersList, batch):
     hit = cache.get(key)
     if hit is None:
         hit = cache[key] = FilterSetTemplates(ops, filtersList, batch.mapDicts[0], tileName=batch.tileNames[0])
+    templateSpectraOf(ops, hit)
     return hit
 
 
@@ -276,7 +287,7 @@ def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=
     # K2, K3, K5: filters and their normalisation
     if cache is None:
         res = engine.buildFourierFilters(ops, fmaps, templates.unit, templates.norm, templates.w, templates.outputUnits,
-                                         templates.cy, templates.cx, bckSubSigmas=bck)
+                                         templates.cy, templates.cx, bckSubSigmas=bck, spectra=templates._spectra)
     else:
         res = {'filtH': cache['filtH'], 'signalNorm': cache['signalNorm'], 'fRel': cache.get('fRel')}
     # K4: apply, times the point-source mask
@@ -993,7 +1004,7 @@ def fitQ(config, precision=None, tilesPerBatch=4, verbose=False, y0=2e-04, scale
             bck = maps.smoothScalesPix(batch.wcsList[0], smoothScaleDeg=params0['bckSubScaleArcmin'] / 60.)
         fmaps = ops.rfft2(dev['data'].reshape(nT * F, H, W), apodPix=20).reshape(nT, F, H, Wc)
         res = engine.buildFourierFilters(ops, fmaps, templates.unit, templates.norm, templates.w, templates.outputUnits,
-                                         templates.cy, templates.cx, bckSubSigmas=bck)
+                                         templates.cy, templates.cx, bckSubSigmas=bck, spectra=templates._spectra)
         del fmaps
         for t, tileName in enumerate(batch.tileNames):
             filt = res['filtH'][t].unsqueeze(0).expand(nS, F, H, Wc).contiguous()

@@ -129,7 +129,8 @@ def buildKernels(ops, batch, filtersList, templates, fmaps):
     nT, F, H, W, S = batch.nT, batch.F, batch.H, batch.W, len(filtersList)
     Wc = W // 2 + 1
     # K2, K3: the nested Fourier matched filters (filters.py:568-630)
-    fsig = ops.rfft2(templates.unit.reshape(S * F, H, W), apodPix=0).reshape(S, F, H, Wc)
+    spectra = getattr(templates, '_spectra', None)
+    fsig = spectra[0] if spectra is not None else ops.rfft2(templates.unit.reshape(S * F, H, W), apodPix=0).reshape(S, F, H, Wc)
     cov = ops.xpower_smooth(fmaps, 3.0, W=W)
     filtH, _ = ops.build_filter(cov, fsig, templates.w, S, False, wantFull=False)
     del cov, fsig

@@ -105,8 +105,9 @@ def test_noise_grid_and_trim_follow_the_reference():
         engine.noiseGrid((64, 64), {'noiseGridArcmin': 'smart'}, pixDeg)                 # numNoiseBins is required (filters.py:367-370)
     with pytest.raises(Exception):
         engine.noiseGrid((64, 64), {'noiseGridArcmin': 'smart', 'numNoiseBins': 4, 'RMSEstimator': 'percentile'}, pixDeg)
+    assert engine.noiseGrid((64, 64), {'noiseGridArcmin': 20., 'RMSEstimator': 'biweight'}, pixDeg)[4] == 'biweight'
     with pytest.raises(Exception):
-        engine.noiseGrid((64, 64), {'noiseGridArcmin': 20., 'RMSEstimator': 'biweight'}, pixDeg)
+        engine.noiseGrid((64, 64), {'noiseGridArcmin': 'smart', 'numNoiseBins': 4, 'RMSEstimator': 'biweight'}, pixDeg)
     # filters.py:728-735: edgeTrimArcmin 0 means three noise cells
     p = {'noiseParams': {'noiseGridArcmin': 40.0}, 'edgeTrimArcmin': 0.0}
     assert engine.trimSizePix(p, pixDeg, realSpace=False) == 240

@@ -46,6 +46,7 @@ filtersList = pipelines._orderedFilters(config.parDict)
 batches = pipelines.stageTiles(config, args.tiles, args.precision)
 t0 = time.perf_counter()
 templates = pipelines.FilterSetTemplates(ops, filtersList, batches[0].mapDicts[0])
+pipelines.templateSpectraOf(ops, templates)      # once per geometry, as the drivers do
 print("templates (host, once per geometry): %.2f s" % (time.perf_counter() - t0))
 for b in batches: b.upload()
 def steps(n):
