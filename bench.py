@@ -165,7 +165,7 @@ def algorithmicBytes(nT, F, S, H, W, E, rings=True, yc=True, templateSpectraCach
     b['cell_clip_kernel'] = nOut * N * E
     b['edge_rows_kernel'] = nOut * (N * E + 2 * N)
     b['edge_cols_final_kernel'] = nOut * (2 * N * E + 3 * N + 3 * N * E + N)
-    b['edge_cols_final_paint_kernel'] = nOut * (2 * N * E + 3 * N + 3 * N * E + N)   # map, median weights, masks in; data, S/N, RMS, mask out
+    b['edge_cols_final_paint_kernel'] = nOut * (2 * N * E + 3 * N + 2 * N * E + N)   # map, median weights, masks in; data, S/N, mask out (the RMS map is not written unless asked for)
     b['detect_scan_kernel'] = b['detect_scan_multi_kernel'] = nOut * (N * E)         # S/N read once for both thresholds; the rest is sparse
     return b
 

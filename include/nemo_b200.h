@@ -186,7 +186,8 @@ int nb_snr_mask(int prec, void* map, void* rms, const unsigned char* psMask, con
 
 /* K6 painting fused into K7: as nb_snr_mask, but the RMS of every pixel is taken straight from the cell table of
  * nb_cell_rms (called with rms = NULL, which skips its painting pass) instead of from a painted RMS map; rmsOut receives
- * the painted and masked RMS map. */
+ * the painted and masked RMS map, or is NULL when nobody reads it (the reference keeps it only with saveRMSMap,
+ * filters.py:760-762; here also the noise tables of completeness.getRMSTab and the filter caches of the injection loop). */
 int nb_snr_mask_cells(int prec, void* map, const void* wmed, const double* table, const double* edges, const int* yChunks,
                       int ny, const int* xChunks, int nx, int overlapPix, int numBins, const unsigned char* psMask,
                       const unsigned char* surveyMask, int nImg, int S, int H, int W, int trimPix, int apodPix,

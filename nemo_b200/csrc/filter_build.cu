@@ -910,13 +910,21 @@ __global__ void __launch_bounds__(256) plane_values_partial_kernel(const typenam
         s_col[2 * kx] = wgt * cs;
         s_col[2 * kx + 1] = wgt * sn;
     }
-    __syncthreads();
+    // row factors of this CTA's band, once per CTA (every thread used to evaluate sincospi and a 64-bit modulo per row: three
+    // quarters of the kernel's instructions)
     const int rows = (H + PV_CHUNKS - 1) / PV_CHUNKS;
     const int ky0 = chunk * rows, ky1 = min(ky0 + rows, H);
+    double* s_row = s_col + 2 * Wc;      // [rows][2]: (cos, sin) of 2 pi ky py / H
+    for (int r = threadIdx.x; r < ky1 - ky0; r += blockDim.x) {
+        double rs, rc;
+        sincospi(2.0 * (double)(((long long)(ky0 + r) * py) % H) / (double)H, &rs, &rc);
+        s_row[2 * r] = rc;
+        s_row[2 * r + 1] = rs;
+    }
+    __syncthreads();
     double acc = 0;
     for (int ky = ky0; ky < ky1; ++ky) {
-        double rs, rc;
-        sincospi(2.0 * (double)(((long long)ky * py) % H) / (double)H, &rs, &rc);
+        const double rc = s_row[2 * (ky - ky0)], rs = s_row[2 * (ky - ky0) + 1];
         const C2* fm = fmaps + mbase + (size_t)ky * Wc;
         const T* fl = filtH + base + (size_t)ky * Wc;
         double rowRe = 0, rowIm = 0;     // sum over kx of G * colFactor
@@ -1141,7 +1149,7 @@ int nb_template_norm(int prec, const void* map, int B, int H, int W, int mode, d
 int nb_plane_values_at(int prec, const void* fmaps, const void* filtH, const long long* idx, double* out, int B, int S,
                        int F, int H, int W, double* scratch, cudaStream_t st) {
     NB_REQUIRE(fmaps && filtH && idx && out && scratch && B > 0 && F > 0, NB_ERR_ARG, "nb_plane_values_at: bad arguments");
-    const size_t smem = sizeof(double) * 2 * (size_t)(W / 2 + 1);
+    const size_t smem = sizeof(double) * 2 * ((size_t)(W / 2 + 1) + (size_t)((H + PV_CHUNKS - 1) / PV_CHUNKS));
     NB_REQUIRE(smem <= 48 * 1024, NB_ERR_UNSUPPORTED, "nb_plane_values_at: tile too wide");
     dim3 grid(PV_CHUNKS, F, B);
     if (prec == NB_PREC_F64) {

@@ -1399,7 +1399,7 @@ __global__ void __launch_bounds__(128) edge_cols_final_kernel(T* map, T* rms, co
             if (snv != snv) snv = (T)0;
             map[ib + o] = d;
             sn[ib + o] = snv;
-            rms[ib + o] = r0 * mo;
+            if (!PAINT || rms) rms[ib + o] = r0 * mo;      // (painting variant: the RMS map itself is optional)
             maskOut[ib + o] = (mo != (T)0) ? 1 : 0;
             cnt += (int)raIn[u] - (int)raOut[u];      // slide the window down by one row
         }
@@ -1589,8 +1589,8 @@ int nb_snr_mask_cells(int prec, void* map, const void* wmed, const double* table
                       const int* xChunks, int nx, int overlapPix, int numBins, const unsigned char* psMask,
                       const unsigned char* surveyMask, int nImg, int S, int H, int W, int trimPix, int apodPix, int realSpace, void* sn,
                       void* rmsOut, unsigned char* maskOut, unsigned char* scratch, cudaStream_t st) {
-    NB_REQUIRE(map && wmed && table && edges && yChunks && xChunks && psMask && surveyMask && sn && rmsOut && maskOut && nImg > 0 && S > 0,
-               NB_ERR_ARG, "nb_snr_mask_cells: bad arguments");
+    NB_REQUIRE(map && wmed && table && edges && yChunks && xChunks && psMask && surveyMask && sn && maskOut && nImg > 0 && S > 0,
+               NB_ERR_ARG, "nb_snr_mask_cells: bad arguments");      // rmsOut may be NULL: the painted RMS map is then not written
     NB_REQUIRE(trimPix == 0 || scratch, NB_ERR_ARG, "nb_snr_mask_cells: scratch required when trimPix > 0");
     NB_REQUIRE(trimPix >= 0, NB_ERR_ARG, "nb_snr_mask_cells: negative trimPix %d", trimPix);
     NB_REQUIRE(W <= 8192, NB_ERR_UNSUPPORTED, "nb_snr_mask_cells: tile too wide");

@@ -192,9 +192,10 @@ def applyFourierFilters(ops, fmaps, filtH, S, signalNorm, psMask, bckSubSigmas=N
     return ops.scale_mask(m, norm=signalNorm, mask=maskFull)
 
 
-def noiseSNAndMasks(ops, filtered, wmed, psMask, surveyMask, S, grid, trimPix, apodPix, realSpace):
+def noiseSNAndMasks(ops, filtered, wmed, psMask, surveyMask, S, grid, trimPix, apodPix, realSpace, wantRMS=True):
     """makeNoiseMap + S/N + edge trim + masks (filters.py:719-758).  `filtered` is overwritten with `data`.
-    Returns (data, SNMap, surveyMaskOut u8, RMSMap, cellTable, cellEdges)."""
+    Returns (data, SNMap, surveyMaskOut u8, RMSMap, cellTable, cellEdges); RMSMap is None with wantRMS=False on the grid path
+    (the map is then never materialised: the S/N map takes its RMS straight from the cell table)."""
     if isinstance(grid[0], str) and grid[0] == 'smart':
         rms, table, edges = ops.smart_rms(filtered, wmed, S, grid[1])
         data, sn, maskOut, rms = ops.snr_mask(filtered, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace)
@@ -202,7 +203,7 @@ def noiseSNAndMasks(ops, filtered, wmed, psMask, surveyMask, S, grid, trimPix, a
     yChunks, xChunks, overlapPix, numBins, estimator = grid
     _, table, edges = ops.cell_rms(filtered, wmed, S, yChunks, xChunks, overlapPix, numBins, estimator=estimator, paint=False)
     data, sn, maskOut, rms = ops.snr_mask_cells(filtered, wmed, table, edges, yChunks, xChunks, overlapPix, numBins, psMask, surveyMask,
-                                                S, trimPix, apodPix, realSpace)
+                                                S, trimPix, apodPix, realSpace, wantRMS=wantRMS)
     return data, sn, maskOut, rms, table, edges
 
 

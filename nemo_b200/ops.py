@@ -378,8 +378,9 @@ class Ops(object):
         return maps, sn, maskOut, rms
 
     def snr_mask_cells(self, maps, wmed, table, edges, yChunks, xChunks, overlapPix, numBins, psMask, surveyMask, S, trimPix, apodPix,
-                       realSpace):
-        """snr_mask with the RMS taken straight from the cell tables (painting fused); returns (data, SNMap, mask u8, RMS map)."""
+                       realSpace, wantRMS=True):
+        """snr_mask with the RMS taken straight from the cell tables (painting fused); returns (data, SNMap, mask u8, RMS map);
+        the RMS map is None with wantRMS=False (8 bytes per pixel less to write when nothing reads it)."""
         self._check(maps, self.dtype, 'maps')
         self._check(wmed, self.dtype, 'wmed')
         self._check(psMask, self.torch.uint8, 'psMask')
@@ -387,7 +388,7 @@ class Ops(object):
         nImg, H, W = maps.shape
         ny, nx = len(yChunks) - 1, len(xChunks) - 1
         sn = self.empty((nImg, H, W))
-        rms = self.empty((nImg, H, W))
+        rms = self.empty((nImg, H, W)) if wantRMS else None
         maskOut = self.empty((nImg, H, W), self.torch.uint8)
         scratch = self.empty((nImg, H, W), self.torch.uint8) if trimPix > 0 else None
         yc = (ctypes.c_int * (ny + 1))(*[int(v) for v in yChunks])

@@ -256,7 +256,7 @@ def templatesFor(config, ops, filtersList, batch):
 
 
 def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=True, invertMap=False, cache=None,
-                   useCachedRMSMap=False, rmsTables=False):
+                   useCachedRMSMap=False, rmsTables=False, wantRMS=True):
     """Launches, without waiting for any of it, the device work of one batch: filtering of every tile at every scale of
     `filtersList` (Fourier matched filters with a common noise set-up), noise / S-N maps, and the thresholding,
     labelling and moments of the detection step.  Returns the job to pass to finishTileBatch.
@@ -309,8 +309,10 @@ def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=
     else:
         # K6, K7
         grid = engine.noiseGrid((H, W), params0['noiseParams'], pixDeg)
+        # (wantRMS=False: job['RMSMap'] is None -- nothing downstream reads the painted map unless noise tables, filter caches or
+        # RMS files were asked for)
         data, sn, maskOut, rms, table, edges = engine.noiseSNAndMasks(ops, filtered, dev['wmed'], dev['psMask'], dev['surveyMask'],
-                                                                      S, grid, trimPix, 20, False)
+                                                                      S, grid, trimPix, 20, False, wantRMS=wantRMS or rmsTables)
     # noise level versus area (completeness.getRMSTab) of every image, while its RMS map is on the device
     rmsTabJob = None
     if rmsTables and table is not None:
@@ -402,6 +404,8 @@ class BatchPipeline(object):
         self.useGraphs = useGraphs
         self.graphs = ops.__dict__.setdefault('_batchGraphs', {})
         self.undoPixelWindow, self.measureFluxes, self.invertMap, self.keepMaps = undoPixelWindow, measureFluxes, invertMap, keepMaps
+        # the painted RMS maps are written only when something reads them: filter caches (keepMaps), noise tables, RMS files
+        self.wantRMS = bool(keepMaps or rmsTables or 'RMSMap' in tuple(collect))
         self.useCachedRMSMap = useCachedRMSMap
         # `depth` batches may be queued on the device while the host assembles the catalogs of the oldest one: with two, the
         # upload of batch i + 2 is already in the copy queue when the host starts waiting for batch i, so the copy engine
@@ -442,7 +446,7 @@ class BatchPipeline(object):
         cacheIdent = None
         if cache is not None:
             cacheIdent = (self.useCachedRMSMap,) + tuple(int(cache[k].data_ptr()) for k in ('filtH', 'signalNorm', 'RMSMap') if cache.get(k) is not None)
-        key = (slot, ident, cacheIdent, batch.nT, batch.F, batch.H, batch.W, ops.precision, templates.serial, self.undoPixelWindow, self.invertMap, self.rmsTables,
+        key = (slot, ident, cacheIdent, batch.nT, batch.F, batch.H, batch.W, ops.precision, templates.serial, self.undoPixelWindow, self.invertMap, self.rmsTables, self.wantRMS,
                repr(sorted((k, repr(v)) for k, v in self.parDict.items() if k != 'mapFilters')),
                _filtersKey(self.filtersList))
         entry = self.graphs.get(key)
@@ -463,7 +467,8 @@ class BatchPipeline(object):
                 view.dev['wmed'] = ops.median_weights(view.dev['weights']) if needWeights else None
             # one eager run first: twiddle tables, kernel attributes and other lazy set-up must not happen under capture
             startTileBatch(ops, view, self.filtersList, templates, self.parDict, undoPixelWindow=self.undoPixelWindow,
-                           invertMap=self.invertMap, rmsTables=self.rmsTables, cache=cache, useCachedRMSMap=self.useCachedRMSMap)
+                           invertMap=self.invertMap, rmsTables=self.rmsTables, cache=cache, useCachedRMSMap=self.useCachedRMSMap,
+                           wantRMS=self.wantRMS)
             st.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launchCount()
@@ -479,7 +484,7 @@ class BatchPipeline(object):
                     view.dev['wmed'] = ops.median_weights(view.dev['weights']) if needWeights else None
                 job = startTileBatch(ops, view, self.filtersList, templates, self.parDict,
                                      undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap, rmsTables=self.rmsTables,
-                                     cache=cache, useCachedRMSMap=self.useCachedRMSMap)
+                                     cache=cache, useCachedRMSMap=self.useCachedRMSMap, wantRMS=self.wantRMS)
             nLaunch = _lib.launchCount() - n0
         entry = (graph, job, static, nLaunch, templates)      # the templates the graph reads stay alive with it
         self.graphs[key] = entry
@@ -522,7 +527,7 @@ class BatchPipeline(object):
                     batch.upload()
                 job = startTileBatch(self.ops, batch, self.filtersList, self.templates if templates is None else templates, self.parDict,
                                      undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap, cache=cache,
-                                     useCachedRMSMap=self.useCachedRMSMap, rmsTables=self.rmsTables)
+                                     useCachedRMSMap=self.useCachedRMSMap, rmsTables=self.rmsTables, wantRMS=self.wantRMS)
         if self.serialize:
             st.synchronize()
         self.pending.append((job, st, upload))
