@@ -152,9 +152,11 @@ int nb_add_maps(int prec, const void* a, const void* b, void* out, long long n, 
  * stacked catalog lose to a higher-S/N detection of the same object.  raDeg, decDeg, snr [n] fp64 (device).  For every centre row
  * c in [firstCentre, firstCentre + numCentres): the rows within radiusDeg of c by astCoords.calcAngSepDeg(c, row) (c included); if
  * more than one, all but the highest-S/N one (lowest index on ties) get toRemove = 1.  toRemove [n] u8 must be zeroed by the
- * caller; calls over disjoint centre ranges (ranks of a multi-GPU run) are combined by OR. */
+ * caller; calls over disjoint centre ranges (ranks of a multi-GPU run) are combined by OR.  scratch: nb_xmatch_scratch_ints(n,
+ * radiusDeg) int32 words (the rows binned by declination). */
 int nb_xmatch_keep_best(const double* raDeg, const double* decDeg, const double* snr, int n, int firstCentre, int numCentres,
-                        double radiusDeg, unsigned char* toRemove, cudaStream_t stream);
+                        double radiusDeg, unsigned char* toRemove, int* scratch, cudaStream_t stream);
+long long nb_xmatch_scratch_ints(int n, double radiusDeg);
 
 /* K6: MapFilter.makeNoiseMap, grid branch, default 3-sigma-clipped estimator (nemo/filters.py:409-481).
  * map [nImg, H, W] (already multiplied by psMask); wmed [nImg / S, H, W] median weights;

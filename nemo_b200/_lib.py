@@ -43,7 +43,8 @@ _PROTOTYPES = {
     "nb_rms_area_table": [c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "nb_paint_objects": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr],
     "nb_add_maps": [c_int, c_ptr, c_ptr, c_ptr, c_ll, c_ll, c_ptr],
-    "nb_xmatch_keep_best": [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr],
+    "nb_xmatch_keep_best": [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr, c_ptr],
+    "nb_xmatch_scratch_ints": [c_int, c_dbl],
     "nb_smart_rms": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "nb_median_weights": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
     "nb_cell_rms": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int), c_int,
@@ -72,7 +73,7 @@ _PROTOTYPES = {
     "nb_cast": [c_int, c_ptr, c_int, c_ptr, c_ll, c_ptr],
     "nb_mask_to_u8": [c_int, c_ptr, c_ptr, c_ll, c_ptr],
 }
-_RESTYPES = {"nb_last_error": ctypes.c_char_p, "nb_label4_scratch_ints": c_ll, "nb_detect_scratch_ints": c_ll, "nb_find_objects_scratch_ints": c_ll, "nb_prof_report": c_ll, "nb_launch_count": c_ll, "nb_launch_count_add": c_ll}
+_RESTYPES = {"nb_last_error": ctypes.c_char_p, "nb_xmatch_scratch_ints": c_ll, "nb_label4_scratch_ints": c_ll, "nb_detect_scratch_ints": c_ll, "nb_find_objects_scratch_ints": c_ll, "nb_prof_report": c_ll, "nb_launch_count": c_ll, "nb_launch_count_add": c_ll}
 
 EXPORTED_SYMBOLS = sorted(_PROTOTYPES.keys())
 

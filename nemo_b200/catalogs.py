@@ -178,6 +178,31 @@ class Table(object):
         return [r.asDict() for r in self]
 
 
+class RowsOf(Table):
+    """Rows [lo, hi) of another table as a table of their own, cut out (copied) when first looked at: a tile batch has hundreds of
+    per-image catalogs ('<label>#<tileName>' -> {'catalog': ...}, the reference's layout) and a run usually reads only the
+    stacked rows.  The parent must not change afterwards (the batched driver's flat tables never do: vstack, row selection
+    and sort all make new tables)."""
+
+    def __init__(self, parent, lo, hi):
+        self._parent, self._lo, self._hi = parent, int(lo), int(hi)
+        self._made = None
+
+    @property
+    def _cols(self):
+        if self._made is None:
+            made = _LazyDict()
+            lo, hi = self._lo, self._hi
+            for k in self._parent.keys():
+                made.put(k, self._parent._derived(k, lambda v: v[lo:hi].copy()))
+            self._made = made
+            self._parent = None
+        return self._made
+
+    def __len__(self):
+        return self._hi - self._lo
+
+
 def vstack(tables):
     tables = [t for t in tables if len(t) > 0]
     out = Table()

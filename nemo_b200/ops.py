@@ -357,9 +357,10 @@ class Ops(object):
         snr = self.to_device(np.ascontiguousarray(SNR, dtype=np.float64), self.torch.float64)
         n = int(ra.shape[0])
         toRemove = self.zeros((n,), self.torch.uint8)
+        scratch = self.empty((max(1, int(_lib.load().nb_xmatch_scratch_ints(n, float(radiusDeg)))),), self.torch.int32)
         _lib.call('nb_xmatch_keep_best', _ptr(ra), _ptr(dec), _ptr(snr), n, int(firstCentre), int(n if numCentres is None else numCentres),
-                  float(radiusDeg), _ptr(toRemove), self._stream())
-        self.launches += 1
+                  float(radiusDeg), _ptr(toRemove), _ptr(scratch), self._stream())
+        self.launches += 4
         return toRemove
 
     def snr_mask(self, maps, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace):

@@ -289,35 +289,22 @@ def columnsToTable(cols, extra=None, keysToWrite=None):
     return splitObjects(flat, extra, keysToWrite)[0]
 
 
-def splitObjects(flat, extra=None, keysToWrite=None):
+def splitObjects(flat, extra=None, keysToWrite=None, stacked=None):
     """Per-image tables (``[]`` where nothing was found) from the flat columns of finishFindObjectsBatch, plus optional
-    extra flat columns (fluxes).  Object names are formatted the first time a table's 'name' column is read."""
+    extra flat columns (fluxes).  The tables are row ranges of the batch's one stacked table (`stacked`: flatTable of the same
+    arguments, made here when not given) that are cut out when first read (catalogs.RowsOf); object names are formatted the
+    first time a 'name' column is read."""
     counts = flat['counts']
+    if stacked is None:
+        stacked = flatTable(flat, extra, keysToWrite)
     out = []
-    keys = keysToWrite if keysToWrite is not None else catalogs.COLUMN_NAMES
-    cols = dict(flat['cols']) if flat['cols'] is not None else {}
-    if extra:
-        cols.update(extra)
-    ident, longNames = flat['objIdent'], flat['longNames']
     lo = 0
-    for b, cnt in enumerate(counts):
+    for cnt in counts:
         if cnt == 0:
             out.append([])
             continue
-        sl = slice(lo, lo + cnt)
+        out.append(catalogs.RowsOf(stacked, lo, lo + cnt))
         lo += cnt
-        ordered = []
-        for key in keys:
-            if key == 'name':
-                ra, dec = cols['RADeg'][sl], cols['decDeg'][sl]
-                ordered.append((key, catalogs.deferred(lambda ra=ra, dec=dec: catalogs.makeNames(ra, dec, prefix=ident, longNames=longNames))))
-            elif key == 'template':
-                ordered.append((key, np.full(cnt, flat['labels'][b], dtype=object)))
-            elif key == 'tileName':
-                ordered.append((key, np.full(cnt, flat['tiles'][b], dtype=object)))
-            elif key in cols:
-                ordered.append((key, cols[key][sl].copy()))
-        out.append(catalogs.Table.fromColumns(ordered))
     return out
 
 

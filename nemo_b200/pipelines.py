@@ -418,6 +418,12 @@ class BatchPipeline(object):
         while len(streams) < self.depth + 1:
             streams.append(torch.cuda.Stream(device=ops.device))
         self.streams = streams[:self.depth + 1]
+        # the host part of a batch (finishTileBatch) launches a few small kernels and copies between its waits; on the batch's
+        # own stream they queue behind the CTAs of the batches running on the other streams and each wait costs about a
+        # millisecond.  They go to a high-priority stream instead: its CTAs are placed first whenever an SM has room.
+        if getattr(ops, '_finishStream', None) is None:
+            ops._finishStream = torch.cuda.Stream(device=ops.device, priority=-1)
+        self.finishStream = ops._finishStream
         self.main = torch.cuda.current_stream(ops.device)
         for st in self.streams:
             st.wait_stream(self.main)      # templates and resident inputs were produced on the caller's stream
@@ -427,8 +433,11 @@ class BatchPipeline(object):
     def _finish(self):
         torch = self.ops.torch
         job, st, release = self.pending.pop(0)
-        with torch.cuda.stream(st):
+        fin = self.finishStream
+        fin.wait_stream(st)
+        with torch.cuda.stream(fin):
             out = finishTileBatch(job, measureFluxes=self.measureFluxes, keepMaps=self.keepMaps, collect=self.collect)
+        st.wait_stream(fin)      # the slot's next batch overwrites what the finish read
         if release:
             job['batch'].dev = None
         return out
@@ -644,12 +653,14 @@ def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measu
                         cols[prefix + 'fluxJy'] = np.where(nsr > 0, flux, 0.0)
                         cols[prefix + 'err_fluxJy'] = np.where(nsr > 0, errFlux, 0.0)
     keys = catalogKeys(photScale is not None, mapUnits, measureFluxes)
-    tables = photometry.splitObjects(flat, cols, keysToWrite=keys)
+    # the batch's rows as one table: what the cross-scale merge stacks (filterMapsAndMakeCatalogs hands these to
+    # makeOptimalCatalog); the per-image catalogs are row ranges of it
+    stacked = photometry.flatTable(flat, cols, keysToWrite=keys)
+    tables = photometry.splitObjects(flat, cols, keysToWrite=keys, stacked=stacked)
     catalogDict = _BatchCatalogs()
     for o in range(nT * S):
         catalogDict[labelList[o] + "#" + tileList[o]] = {'catalog': tables[o]}
-    # the same rows as one table: what the cross-scale merge stacks (filterMapsAndMakeCatalogs hands these to makeOptimalCatalog)
-    catalogDict.flat = photometry.flatTable(flat, cols, keysToWrite=keys)
+    catalogDict.flat = stacked
     return catalogDict
 
 
@@ -731,9 +742,11 @@ def stageTiles(config, tilesPerBatch=8, precision=None):
     groups = {}
     for name in config.tileNames:
         groups.setdefault((tileGeometry(config.tileMaps[name]), len(config.tileMaps[name])), []).append(name)
+    # (a list of batch sizes ramps up at the start of the run and down at its end, not at every change of geometry)
     batches = []
-    for names in groups.values():
-        batches += [TileBatch(ops, names[i:j], config.tileMaps) for i, j in _batchBounds(len(names), tilesPerBatch)]
+    for g, names in enumerate(groups.values()):
+        bounds = _batchBounds(len(names), tilesPerBatch, rampUp=g == 0, rampDown=g == len(groups) - 1)
+        batches += [TileBatch(ops, names[i:j], config.tileMaps) for i, j in bounds]
     config._staged = {'tilesPerBatch': _batchKey(tilesPerBatch), 'precision': ops.precision, 'batches': batches}
     return config._staged['batches']
 
@@ -766,18 +779,21 @@ def _batchKey(tilesPerBatch):
     return int(tilesPerBatch) if isinstance(tilesPerBatch, (int, np.integer)) else tuple(int(v) for v in tilesPerBatch)
 
 
-def _batchBounds(numTiles, tilesPerBatch):
+def _batchBounds(numTiles, tilesPerBatch, rampUp=True, rampDown=True):
     """[(first, last + 1)] of the batches.  tilesPerBatch: a batch size, or a sequence of sizes -- the last size repeats until
     the tiles run out, except that the list is mirrored at the end when it starts small: [2, 4] gives 2, 4, 4, ..., 4, 2.  A
     small first batch starts the device work sooner (nothing overlaps its upload), a small last one shortens the tail that
-    no upload overlaps."""
+    no upload overlaps.  rampUp / rampDown = False: without the small batches at the start / the mirrored ones at the end (the
+    tiles are one geometry group in the middle of a run)."""
     if isinstance(tilesPerBatch, (int, np.integer)):
         sizes = [int(tilesPerBatch)] * ((numTiles + int(tilesPerBatch) - 1) // int(tilesPerBatch))
     else:
         head = [int(v) for v in tilesPerBatch]
         if not head or min(head) < 1:
             raise Exception("tilesPerBatch needs positive batch sizes")
-        tail = head[:-1][::-1]
+        tail = head[:-1][::-1] if rampDown else []
+        if not rampUp:
+            head = head[-1:]
         sizes = []
         left = numTiles - sum(tail)
         for v in head:
@@ -794,6 +810,14 @@ def _batchBounds(numTiles, tilesPerBatch):
                 break
             sizes.append(min(v, left))
             left -= sizes[-1]
+    if not isinstance(tilesPerBatch, (int, np.integer)):
+        # a remainder in front of the mirrored tail joins the tail's first batch
+        i = len(tilesPerBatch) - 1 if rampUp else 0
+        while i + 1 < len(sizes):
+            if sizes[i] < sizes[i + 1] and sizes[i] + sizes[i + 1] <= int(np.max(tilesPerBatch)):
+                sizes[i:i + 2] = [sizes[i] + sizes[i + 1]]
+            else:
+                i += 1
     bounds, first = [], 0
     for v in sizes:
         if first >= numTiles:

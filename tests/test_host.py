@@ -246,13 +246,17 @@ def test_bench_byte_model_matches_survey_table():
 def test_batch_bounds_cover_all_tiles_in_order():
     """Batch sizes of the streaming driver: a single size, or a list mirrored at the end (small first and last batches)."""
     from nemo_b200.pipelines import _batchBounds, _batchKey
-    cases = {(16, 8): [8, 8], (16, (2, 4)): [2, 4, 4, 4, 2], (5, (2, 4)): [2, 1, 2], (1, (2, 4)): [1], (10, 4): [4, 4, 2],
+    cases = {(16, 8): [8, 8], (16, (2, 4)): [2, 4, 4, 4, 2], (5, (2, 4)): [2, 3], (1, (2, 4)): [1], (10, 4): [4, 4, 2],
              (7, (4,)): [4, 3], (3, (2, 4)): [1, 2]}
     for (n, tpb), sizes in cases.items():
         bounds = _batchBounds(n, list(tpb) if isinstance(tpb, tuple) else tpb)
         assert [j - i for i, j in bounds] == sizes
         assert bounds[0][0] == 0 and bounds[-1][1] == n
         assert all(bounds[k][1] == bounds[k + 1][0] for k in range(len(bounds) - 1))
+    # geometry groups in the middle of a run: no small batches at their start / no mirrored tail at their end
+    assert [j - i for i, j in _batchBounds(28, [2, 4, 8], rampDown=False)] == [2, 4, 8, 8, 6]
+    assert [j - i for i, j in _batchBounds(7, [2, 4, 8], rampUp=False)] == [5, 2]
+    assert [j - i for i, j in _batchBounds(20, [2, 4, 8], rampUp=False, rampDown=False)] == [8, 8, 4]
     assert _batchKey([2, 4]) == _batchKey((2, 4)) == (2, 4) and _batchKey(8) == 8
     with pytest.raises(Exception):
         _batchBounds(4, [0, 2])

@@ -48,3 +48,36 @@ print("largest compute-idle gaps (ms into the step, length ms, kernel after):")
 for s, t in sorted(big):
     nxt = next((e['name'][:60] for e in kern if e['ts'] >= t), '')
     print("   %7.2f  %6.2f  %s" % ((s - start) / 1e3, (t - s) / 1e3, nxt))
+# per-stream timeline: runs of activities on one stream separated by less than 0.2 ms, with their time span and what they are
+byStream = {}
+for e in ev:
+    byStream.setdefault(e.get('args', {}).get('stream', e.get('tid')), []).append(e)
+print("timeline (stream, start ms, end ms, busy ms, n, first .. last activity):")
+runs = []
+for sid, items in byStream.items():
+    cur = None
+    for e in items:
+        s, t = e['ts'], e['ts'] + e['dur']
+        kind = e['cat']
+        if cur is not None and s - cur['end'] < 200 and kind == cur['kind']:
+            cur['end'] = max(cur['end'], t); cur['busy'] += e['dur']; cur['n'] += 1; cur['last'] = e['name']
+            if kind == 'gpu_memcpy':
+                cur['bytes'] += e.get('args', {}).get('bytes', 0)
+        else:
+            cur = {'sid': sid, 'start': s, 'end': t, 'busy': e['dur'], 'n': 1, 'first': e['name'], 'last': e['name'], 'kind': kind,
+                   'bytes': e.get('args', {}).get('bytes', 0) if kind == 'gpu_memcpy' else 0}
+            runs.append(cur)
+for r in sorted(runs, key=lambda r: r['start']):
+    if r['end'] - r['start'] < 30 and r['n'] < 3:
+        continue
+    extra = (" %.1f MB" % (r['bytes'] / 1e6)) if r['bytes'] else ''
+    print("  s%-4s %7.2f %7.2f  busy %6.2f  n %4d  %s .. %s%s" % (r['sid'], (r['start'] - start) / 1e3, (r['end'] - start) / 1e3, r['busy'] / 1e3,
+                                                               r['n'], r['first'][:38], r['last'][:38], extra))
+# host side: the python-level calls of the step
+cpu = [e for e in json.load(open(path))['traceEvents'] if e.get('ph') == 'X' and e.get('cat') in ('cuda_runtime',) and e.get('name') in
+       ('cudaStreamSynchronize', 'cudaGraphLaunch', 'cudaEventSynchronize', 'cudaDeviceSynchronize')]
+cpu.sort(key=lambda e: e['ts'])
+print("host: graph launches and synchronisations (ms into the step, duration ms):")
+for e in cpu:
+    if e['name'] == 'cudaGraphLaunch' or e['dur'] > 300:
+        print("   %7.2f %6.2f %s" % ((e['ts'] - start) / 1e3, e['dur'] / 1e3, e['name']))
