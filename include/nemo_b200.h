@@ -216,6 +216,13 @@ long long nb_label4_scratch_ints(int B, int H, int W);
 int nb_label_moments(int prec, const void* map, double sign, const int* labels, double* table, int B, int H, int W,
                      int maxLabels, cudaStream_t stream);
 
+/* findObjects' SExtractor-style ellipses (measureShapes = True, nemo/photometry.py:126-178): per label of a segmentation map the
+ * corner of its bounding box and the S/N-weighted moments about that corner.  table [B, maxLabels + 1, 8] fp64 rows:
+ * {sum d, sum xs d, sum ys d, sum xs^2 d, sum ys^2 d, sum xs ys d, xMin, yMin} with xs = x - xMin, ys = y - yMin, d = sign * map
+ * (xMin = yMin = -1 for labels without pixels).  scratch: 2 * B * (maxLabels + 1) int32 words. */
+int nb_label_shapes(int prec, const void* map, double sign, const int* labels, double* table, int* scratch, int B, int H, int W,
+                    int maxLabels, cudaStream_t stream);
+
 /* K9 + K10 in one asynchronous call, for sparse foregrounds (the usual case above a detection threshold): one dense pass
  * over the map, then linking / numbering / moments over a compact list of the foreground pixels.  Same outputs as
  * nb_label4 + nb_label_moments (labels [B, H, W], nLabels [B], table [B, maxLabels + 1, 8]); flags bit 0 asks for the

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(CSRC, "build")
 LIBPATH = os.path.join(HERE, "libnemo_b200.so")
-SOURCES = ["api.cu", "fft_kernels.cu", "fft_bluestein.cu", "fft_bluestein_cols.cu", "sfft_rows.cu", "sfft_cols_f64.cu", "sfft_cols_f32.cu", "sfft_cols_tma.cu", "filter_build.cu", "noise.cu", "noise_onebin.cu", "noise_smart.cu", "detect.cu", "realspace.cu", "xmatch.cu", "paint.cu"]
+SOURCES = ["api.cu", "fft_kernels.cu", "fft_bluestein.cu", "fft_bluestein_cols.cu", "sfft_rows.cu", "sfft_cols_f64.cu", "sfft_cols_f32.cu", "sfft_cols_tma.cu", "filter_build.cu", "noise.cu", "noise_onebin.cu", "noise_smart.cu", "detect.cu", "realspace.cu", "xmatch.cu", "paint.cu", "shapes.cu"]
 # IEEE arithmetic everywhere (no fast-math); the CUDA runtime is linked statically so the library does not
 # depend on which libcudart the host process (PyTorch) happens to load
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

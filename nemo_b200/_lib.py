@@ -58,6 +58,7 @@ _PROTOTYPES = {
     "nb_label4": [c_int, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr],
     "nb_label4_scratch_ints": [c_int, c_int, c_int],
     "nb_label_moments": [c_int, c_ptr, c_dbl, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
+    "nb_label_shapes": [c_int, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
     "nb_detect": [c_int, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
     "nb_detect_scratch_ints": [c_int, c_int, c_int],
     "nb_find_objects": [c_int, c_ptr, c_dbl, c_dbl, c_int, c_dbl, c_dbl, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int,

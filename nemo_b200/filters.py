@@ -15,8 +15,7 @@ Differences a caller can see:
   * filter caches, RMS maps and area masks are FITS files in the reference's layout, written and read by ``nemo_b200.fitsio``
     (astropy is not needed; tile compression is not implemented, the images are plain HDUs of the same pixel type);
   * options whose dependencies are absent raise instead of silently differing: noise methods ``model`` and
-    ``max(dataMap,CMB)``, ``noiseModelCatalog``, ``RMSEstimator`` percentile / biweight together with the ``smart`` noise grid,
-    ``measureShapes``;
+    ``max(dataMap,CMB)``, ``noiseModelCatalog``, ``RMSEstimator`` percentile / biweight together with the ``smart`` noise grid;
     tile sides must lie in 64..4096 (sides that are not powers of two take mixed-radix passes when
     their prime factors are 2, 3, 5, 7, the slower Bluestein passes otherwise -- odd sides included).
 """

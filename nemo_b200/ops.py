@@ -491,6 +491,18 @@ class Ops(object):
         self.launches += 4
         return table
 
+    def label_shapes(self, maps, labels, maxLabels, sign=1.0):
+        """[B, maxLabels + 1, 8] fp64: bounding-box corner and S/N-weighted moments of every label (nb_label_shapes)."""
+        self._check(maps, self.dtype, 'maps')
+        self._check(labels, self.torch.int32, 'labels')
+        B, H, W = maps.shape
+        table = self.empty((B, int(maxLabels) + 1, 8), self.torch.float64)
+        scratch = self.empty((2 * B * (int(maxLabels) + 1),), self.torch.int32)
+        _lib.call('nb_label_shapes', self.prec, _ptr(maps), float(sign), _ptr(labels), _ptr(table), _ptr(scratch), B, H, W, int(maxLabels),
+                  self._stream())
+        self.launches += 4
+        return table
+
     def spline_eval(self, imgs, imgIdx, yx, sign=1.0):
         self._check(imgs, self.dtype, 'imgs')
         B, H, W = imgs.shape

@@ -137,24 +137,28 @@ def startFindObjectsBatch(ops, snMaps, threshold=3.0, findCenterOfMass=True, rem
                           invertMap=False, measureShapes=False):
     """Launches the device work of findObjects for a batch of S/N maps [B, H, W] (thresholding, labelling and moments at
     the detection and ring thresholds) without waiting for it; pass the result to finishFindObjectsBatch."""
-    if measureShapes == True:
-        raise Exception("measureShapes is not implemented in nemo_b200")
     if threshold < 0 or (removeRings == True and ringThresholdSigma < 0):
         raise Exception("Detection threshold (thresholdSigma in the config file) cannot be negative unless in forced photometry mode.")
     sign = -1.0 if invertMap == True else 1.0
     dev = ops.find_objects(snMaps, threshold, ringThresholdSigma if removeRings == True else None, sign=sign,
-                           minRingPix=MIN_RING_PIX, findCenterOfMass=findCenterOfMass)
-    return {'ops': ops, 'imgs': snMaps, 'sign': sign, 'thresholds': [threshold, ringThresholdSigma] if removeRings == True else [threshold],
+                           minRingPix=MIN_RING_PIX, findCenterOfMass=findCenterOfMass, wantLabels=measureShapes == True)
+    shapes = None
+    if measureShapes == True:
+        # second-order moments of every label for the SExtractor-style ellipses (photometry.py:126-178), queued behind the labelling
+        shapes = ops.label_shapes(snMaps, dev[4], dev[2].shape[1] - 1, sign=sign)
+    return {'shapes': shapes, 'ops': ops, 'imgs': snMaps, 'sign': sign, 'thresholds': [threshold, ringThresholdSigma] if removeRings == True else [threshold],
             'threshold': threshold, 'findCenterOfMass': findCenterOfMass, 'removeRings': removeRings, 'dev': dev}
 
 
 def _collectDetections(job):
-    """(nLabels host, moment table host [B, nmax + 1, 8], ring flags host [B, nmax + 1] or None) of a startFindObjectsBatch job.
+    """(nLabels host, moment table host [B, nmax + 1, 8], ring flags host [B, nmax + 1] or None, shape moments host or None) of a
+    startFindObjectsBatch job.
     One synchronising copy of the counts, then two small ones; nothing at the ring threshold leaves the device.  Batches
     that overflowed the sparse detector are redone with the dense kernels."""
     ops, imgs, sign = job['ops'], job['imgs'], job['sign']
     torch = ops.torch
     nLabels, status, table, flags, _ = job['dev']
+    shapes = job.get('shapes')
     info = device.toHost(torch.stack([nLabels, status]))
     n = info[0]
     if info[1].any() or (len(n) and int(n.max()) > table.shape[1] - 1):
@@ -168,10 +172,45 @@ def _collectDetections(job):
         flags = None
         if job['removeRings'] == True:
             flags = ops.ring_flags(table, nlDev, dense[1][0], dense[1][2], minRingPix=MIN_RING_PIX, findCenterOfMass=job['findCenterOfMass'])
+        if shapes is not None:
+            shapes = ops.label_shapes(imgs, dense[0][0], table.shape[1] - 1, sign=sign)
     nmax = int(n.max()) if len(n) else 0
     tableHost = device.toHost(table[:, :nmax + 1].contiguous())
     flagsHost = device.toHost(flags[:, :nmax + 1].contiguous()) if flags is not None else None
-    return n, tableHost, flagsHost
+    shapesHost = device.toHost(shapes[:, :nmax + 1].contiguous()) if shapes is not None else None
+    return n, tableHost, flagsHost, shapesHost
+
+
+ELLIPSE_KEYS = ('ellipse_PA', 'ellipse_A', 'ellipse_B', 'ellipse_x0', 'ellipse_y0', 'ellipse_e')
+
+
+def ellipsesFromMoments(rows, numSigPix):
+    """The six ellipse columns of findObjects(measureShapes = True) from the label moments of nb_label_shapes (rows [K, 8]:
+    sum d, sum xs d, sum ys d, sum xs^2 d, sum ys^2 d, sum xs ys d, xMin, yMin) -- the reference's operations, in its order
+    (photometry.py:139-178): -99 for objects of at most 9 pixels and where its sign test on theta and xy fails."""
+    rows = np.asarray(rows, dtype=np.float64).reshape(-1, 8)
+    numSigPix = np.asarray(numSigPix, dtype=np.float64)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        s0 = rows[:, 0]
+        cx2 = rows[:, 1] / s0
+        cy2 = rows[:, 2] / s0
+        x2 = (rows[:, 3] / s0) - cx2 ** 2
+        y2 = (rows[:, 4] / s0) - cy2 ** 2
+        xy = (rows[:, 5] / s0) - cx2 * cy2
+        theta = np.degrees(np.arctan(2 * (xy / (x2 - y2))) / 2.0)
+        up = (xy > 0) & (theta < 0)
+        down = ~up & (xy < 0) & (theta > 0)
+        theta = np.where(up, theta + 90, np.where(down, theta - 90, theta))
+        ok = (numSigPix > 9) & (((theta > 0) & (xy > 0)) | ((theta < 0) & (xy < 0)))
+        root = np.sqrt(((x2 - y2) / 2) ** 2 + xy ** 2)
+        A = np.sqrt((x2 + y2) / 2.0 + root)
+        B = np.sqrt((x2 + y2) / 2.0 - root)
+        scaleFactor = np.sqrt(numSigPix / (A * B * np.pi))
+        A = A * scaleFactor
+        B = B * scaleFactor
+        ecc = np.sqrt(1 - B ** 2 / A ** 2)
+    vals = (theta, A, B, cx2 + rows[:, 6], cy2 + rows[:, 7], ecc)
+    return {k: np.where(ok, v, -99.0) for k, v in zip(ELLIPSE_KEYS, vals)}
 
 
 def _flatObjects(table, n, shape, findCenterOfMass=True, minPix=None):
@@ -209,12 +248,13 @@ def finishFindObjectsBatch(job, wcsList, flagMaskList, labelList, tileNameList, 
     ops, snMaps, sign = job['ops'], job['imgs'], job['sign']
     threshold, findCenterOfMass, removeRings = job['threshold'], job['findCenterOfMass'], job['removeRings']
     B, H, W = snMaps.shape
-    n, table, ringFlags = _collectDetections(job)
+    n, table, ringFlags, shapeTable = _collectDetections(job)
     cb, cid, cy, cx, cn = _flatObjects(table, n, (H, W), findCenterOfMass, minPix=minObjPix)
     keep = cn > minObjPix
     if ringFlags is not None:
         # rings: > 30 pixels at ringThresholdSigma whose centroid pixel is not one of their own (photometry.py:60-70)
         keep &= ringFlags[cb, cid] == 0
+    ellipses = ellipsesFromMoments(shapeTable[cb[keep], cid[keep]], cn[keep]) if shapeTable is not None else None
     cb, cy, cx, cn = cb[keep].astype(np.int32), cy[keep], cx[keep], cn[keep]
     K = len(cb)
     flat = {'counts': np.zeros(B, dtype=np.int64), 'labels': list(labelList), 'tiles': list(tileNameList), 'objIdent': objIdent,
@@ -273,6 +313,8 @@ def finishFindObjectsBatch(job, wcsList, flagMaskList, labelList, tileNameList, 
     ra, dec = ra[sel], dec[sel]
     flat['cols'] = {'id': ids[sel], 'x': cx[sel], 'y': cy[sel], 'RADeg': ra, 'decDeg': dec, 'galacticLatDeg': _galacticLat(ra, dec),
                     'numSigPix': cn[sel], 'SNR': snr[sel].astype(np.float64), 'flags': flags[sel]}
+    if ellipses is not None:
+        flat['cols'].update({k: v[sel] for k, v in ellipses.items()})
     flat['samples'] = {k: v[sel] for k, v in samples.items()}
     flat['xy2'] = (xs2[sel], ys2[sel]) if extraSamples else None
     return flat

@@ -10,6 +10,7 @@ the same GPU so that the input FFTs and the smoothed noise covariance are shared
 ``photFilter`` maps (pipelines.py:238-241) are local.
 """
 
+import os
 import numpy as np
 
 from . import catalogs
@@ -424,20 +425,26 @@ class BatchPipeline(object):
         if getattr(ops, '_finishStream', None) is None:
             ops._finishStream = torch.cuda.Stream(device=ops.device, priority=-1)
         self.finishStream = ops._finishStream
+        # the device work of ALL batches runs on one stream, one batch after the other: side by side on their slots' streams the
+        # kernels of two or three batches interleave, evict each other's spectra and filters from L2 and take 64 ms per DR5 step
+        # instead of the 55.5 ms they take alone.  The slots' streams only carry the uploads (and `prepare`).
+        if getattr(ops, '_computeStream', None) is None:
+            ops._computeStream = torch.cuda.Stream(device=ops.device)
+        self.compute = ops._computeStream if os.environ.get('NEMO_B200_SERIAL_COMPUTE', '1') != '0' else None
         self.main = torch.cuda.current_stream(ops.device)
-        for st in self.streams:
+        for st in self.streams + ([self.compute] if self.compute is not None else []):
             st.wait_stream(self.main)      # templates and resident inputs were produced on the caller's stream
         self.pending = []
         self.count = 0
 
     def _finish(self):
         torch = self.ops.torch
-        job, st, release = self.pending.pop(0)
+        job, st, release, done = self.pending.pop(0)
         fin = self.finishStream
-        fin.wait_stream(st)
+        fin.wait_event(done)      # this batch only: the batches queued behind it keep the device busy meanwhile
         with torch.cuda.stream(fin):
             out = finishTileBatch(job, measureFluxes=self.measureFluxes, keepMaps=self.keepMaps, collect=self.collect)
-        st.wait_stream(fin)      # the slot's next batch overwrites what the finish read
+        # (finishTileBatch ends with a copy to the host that it waits for: what the finish read is free for the slot's next batch)
         if release:
             job['batch'].dev = None
         return out
@@ -517,6 +524,7 @@ class BatchPipeline(object):
         # the injection loop uploads its maps and masks, not the weight maps
         photInList = self.parDict.get('photFilter') is not None and any(f['label'] == self.parDict['photFilter'] for f in self.filtersList)
         skipKeys = ('weights', 'rowArea') if (cache is not None and self.useCachedRMSMap and photInList and not self.rmsTables) else ()
+        run = st if self.compute is None else self.compute
         if useGraph:
             graph, template, static, nLaunch, _ = self._graphEntry(slot, st, batch, upload, cache, templates)
             with torch.cuda.stream(st):
@@ -525,6 +533,8 @@ class BatchPipeline(object):
                         if k in skipKeys:
                             continue
                         static[k].copy_(device.countH2D(v), non_blocking=True)
+            run.wait_stream(st)
+            with torch.cuda.stream(run):
                 graph.replay()
             _lib.load().nb_launch_count_add(nLaunch)
             job = dict(template)
@@ -534,12 +544,17 @@ class BatchPipeline(object):
             with torch.cuda.stream(st):
                 if upload:
                     batch.upload()
+            run.wait_stream(st)
+            with torch.cuda.stream(run):
                 job = startTileBatch(self.ops, batch, self.filtersList, self.templates if templates is None else templates, self.parDict,
                                      undoPixelWindow=self.undoPixelWindow, invertMap=self.invertMap, cache=cache,
                                      useCachedRMSMap=self.useCachedRMSMap, rmsTables=self.rmsTables, wantRMS=self.wantRMS)
+        done = torch.cuda.Event()
+        done.record(run)
+        st.wait_event(done)       # the slot's next upload overwrites this batch's inputs
         if self.serialize:
-            st.synchronize()
-        self.pending.append((job, st, upload))
+            run.synchronize()
+        self.pending.append((job, st, upload, done))
         # a slot's buffers (graph outputs, static inputs) are reused by the batch submitted len(streams) calls later, so at
         # most `depth` jobs may stay unread
         return self._finish() if len(self.pending) > self.depth else None
@@ -549,7 +564,7 @@ class BatchPipeline(object):
         outs = []
         while self.pending:
             outs.append(self._finish())
-        for st in self.streams:
+        for st in self.streams + ([self.compute] if self.compute is not None else []):
             self.main.wait_stream(st)
         return outs
 
@@ -578,9 +593,9 @@ def processBatches(ops, batches, filtersList, templates, parDict, upload=True, u
     return results
 
 
-def catalogKeys(havePhotFilter, mapUnits, measureFluxes=True):
+def catalogKeys(havePhotFilter, mapUnits, measureFluxes=True, measureShapes=False):
     """Column list of the per-(tile, scale) catalogs, the same on every rank (what catalogListToTab is asked to write)."""
-    keys = [k for k in catalogs.COLUMN_NAMES if not k.startswith('ellipse_')]   # measureShapes is not supported
+    keys = [k for k in catalogs.COLUMN_NAMES if measureShapes == True or not k.startswith('ellipse_')]
     prefixes = ['', 'fixed_'] if havePhotFilter else ['']
     if havePhotFilter:
         keys.append('fixed_SNR')
@@ -652,7 +667,7 @@ def detectAndMeasure(ops, batch, filtersList, data, sn, mapUnits, parDict, measu
                         errFlux = photometry.deltaTToJyPerSr(cols[prefix + 'err_deltaT_c'], freq) * nsr * 1.e-9
                         cols[prefix + 'fluxJy'] = np.where(nsr > 0, flux, 0.0)
                         cols[prefix + 'err_fluxJy'] = np.where(nsr > 0, errFlux, 0.0)
-    keys = catalogKeys(photScale is not None, mapUnits, measureFluxes)
+    keys = catalogKeys(photScale is not None, mapUnits, measureFluxes, parDict.get('measureShapes', False))
     # the batch's rows as one table: what the cross-scale merge stacks (filterMapsAndMakeCatalogs hands these to
     # makeOptimalCatalog); the per-image catalogs are row ranges of it
     stacked = photometry.flatTable(flat, cols, keysToWrite=keys)
@@ -953,7 +968,7 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
     if comm is not None and comm.size > 1:
         from . import distributed
         havePhot = parDict.get('photFilter') is not None and any(f['label'] == parDict['photFilter'] for f in filtersList)
-        keys = catalogKeys(havePhot, templates.outputUnits, measureFluxes)
+        keys = catalogKeys(havePhot, templates.outputUnits, measureFluxes, parDict.get('measureShapes', False))
         labels = [f['label'] for f in filtersList]
         optimalCatalog = distributed.allGatherCatalog(comm, optimalCatalog, keys, labels, config.allTileNames,
                                                       objIdent=parDict['objIdent'], longNames=parDict['longNames'], ops=ops)

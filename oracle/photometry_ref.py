@@ -4,7 +4,7 @@ oracle/__init__.py.  Catalogs are lists of dicts (what the reference hands to
 ``catalogs.catalogListToTab``, catalogs.py:443-468); astropy is absent so no Table is built.
 
   getObjectPositions   photometry.py:193-222
-  findObjects          photometry.py:25-190   (measureShapes not restated)
+  findObjects          photometry.py:25-190   (incl. the measureShapes ellipses, :126-178)
   getSNRValues         photometry.py:225-255
   measureFluxes        photometry.py:258-351
 """
@@ -126,7 +126,47 @@ def findObjects(filteredMapDict, threshold=3.0, minObjPix=3, rejectBorder=10, fi
                 objDict['SNR'] = data[int(round(objDict['y'])), int(round(objDict['x']))]
             objDict['flags'] = flagMask[int(round(objDict['y'])), int(round(objDict['x']))]
             if measureShapes == True:
-                raise Exception("oracle: measureShapes not restated")
+                # SExtractor-style shape measurements (photometry.py:126-178)
+                doubleCheck = False
+                if objDict['numSigPix'] > 9:
+                    mask = np.equal(segMap, objIDs[i])
+                    ys, xs = np.where(segMap == objIDs[i])
+                    yMin, xMin = ys.min(), xs.min()
+                    xs = xs - xMin
+                    ys = ys - yMin
+                    cx2 = (xs * data[mask]).sum() / data[mask].sum()
+                    cy2 = (ys * data[mask]).sum() / data[mask].sum()
+                    x2 = (((xs ** 2) * data[mask]).sum() / data[mask].sum()) - cx2 ** 2
+                    y2 = (((ys ** 2) * data[mask]).sum() / data[mask].sum()) - cy2 ** 2
+                    xy = (((xs * ys) * data[mask]).sum() / data[mask].sum()) - cx2 * cy2
+                    with np.errstate(divide='ignore', invalid='ignore'):
+                        theta = np.degrees(np.arctan(2 * (xy / (x2 - y2))) / 2.0)
+                    if xy > 0 and theta < 0:
+                        theta = theta + 90
+                    elif xy < 0 and theta > 0:
+                        theta = theta - 90
+                    if theta > 0 and xy > 0:
+                        doubleCheck = True
+                    if theta < 0 and xy < 0:
+                        doubleCheck = True
+                    if doubleCheck == True:
+                        A = np.sqrt((x2 + y2) / 2.0 + np.sqrt(((x2 - y2) / 2) ** 2 + xy ** 2))
+                        B = np.sqrt((x2 + y2) / 2.0 - np.sqrt(((x2 - y2) / 2) ** 2 + xy ** 2))
+                        segArea = float(np.count_nonzero(np.equal(segMap, objIDs[i])))
+                        curArea = A * B * np.pi
+                        scaleFactor = np.sqrt(segArea / curArea)
+                        A = A * scaleFactor
+                        B = B * scaleFactor
+                        ecc = np.sqrt(1 - B ** 2 / A ** 2)
+                        objDict['ellipse_PA'] = theta
+                        objDict['ellipse_A'] = A
+                        objDict['ellipse_B'] = B
+                        objDict['ellipse_x0'] = cx2 + xMin
+                        objDict['ellipse_y0'] = cy2 + yMin
+                        objDict['ellipse_e'] = ecc
+                if objDict['numSigPix'] <= 9 or doubleCheck == False:
+                    for key in ('ellipse_PA', 'ellipse_A', 'ellipse_B', 'ellipse_x0', 'ellipse_y0', 'ellipse_e'):
+                        objDict[key] = -99
             if objDict['SNR'] > threshold:
                 catalog.append(objDict)
             idNumCount = idNumCount + 1

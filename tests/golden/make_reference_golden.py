@@ -355,11 +355,26 @@ def runBigCase(refFilters, refPhotometry, name, tmpDir):
     return res
 
 
+def runShapes(refPhotometry):
+    """The reference's findObjects with measureShapes = True (nemo/photometry.py:126-178) on the seeded S/N map of shape_case."""
+    import shape_case
+    import big_cases
+    tile = shape_case.shapeTile()
+    with np.errstate(divide='ignore', invalid='ignore'):
+        cat = refPhotometry.findObjects(tile, verbose=False, **shape_case.DETECT)
+    return big_cases.catalogColumns('shape_', cat)
+
+
 def main():
     import tempfile
     sys.path.insert(0, HERE)
     import make_golden
     refFilters, refPhotometry = loadReference()
+    shapes = runShapes(refPhotometry)
+    np.savez_compressed(os.path.join(HERE, 'ref_shapes.npz'), **shapes)
+    print("shapes: findObjects(measureShapes=True) stored (%d rows, %d with an ellipse)" % (len(shapes['shape_SNR']), int((shapes['shape_ellipse_A'] > 0).sum())))
+    if '--only-shapes' in sys.argv:
+        return
     tmpDir = tempfile.mkdtemp()
     paint = runPaint(tmpDir)
     np.savez_compressed(os.path.join(HERE, 'ref_paint.npz'), **paint)

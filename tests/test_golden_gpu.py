@@ -220,3 +220,50 @@ def test_batched_driver_matches_full_size_reference_run(report):
             np.testing.assert_allclose(np.asarray(cat[k], dtype=np.float64), ref[prefix + k], err_msg=k, **tol)
     assert len(opt) >= 20
     report("batched_reference_run_big", optimal=len(opt))
+
+
+def test_measure_shapes_matches_reference_run(report):
+    """findObjects(measureShapes = True) on the device (nb_label_shapes: bounding-box corners and S/N-weighted moments per label,
+    then the reference's formulas on the host) against the reference's own findObjects on the seeded S/N map of shape_case
+    (ref_shapes.npz): same rows, the same -99 rows for small objects, ellipse columns within 1e-9 (the moment sums are fp64 atomics,
+    so the last digits depend on the order).  The two exactly symmetric blobs, whose xy moment is rounding noise and whose
+    position angle therefore a coin toss, are compared on A, B only.  Also through the batched entry point with two images, the
+    second one inverted."""
+    import shape_case
+    from nemo_b200 import photometry, device
+    ops64 = device.getOps('f64')
+    ref = np.load(os.path.join(HERE, 'golden', 'ref_shapes.npz'))
+    tile = shape_case.shapeTile()
+    det = dict(shape_case.DETECT)
+    cat = photometry.findObjects(tile, verbose=False, **det)
+    assert len(cat) == len(ref['shape_SNR'])
+    np.testing.assert_allclose(np.asarray(cat['SNR'], dtype=float), ref['shape_SNR'], rtol=1e-6)
+    assert np.array_equal(np.asarray(cat['numSigPix'], dtype=float), ref['shape_numSigPix'])
+    small = ref['shape_numSigPix'] <= 9
+    knife = (~small) & ((ref['shape_ellipse_e'] < 1e-6) | (ref['shape_ellipse_A'] == -99))
+    robust = ~small & ~knife
+    assert robust.sum() >= 15 and small.sum() >= 2
+    worst = 0.0
+    for k in shape_case.SHAPE_KEYS:
+        got = np.asarray(cat[k], dtype=np.float64)
+        assert np.all(got[small] == -99), k
+        np.testing.assert_allclose(got[robust], ref['shape_' + k][robust], rtol=1e-9, atol=1e-9, err_msg=k)
+        worst = max(worst, float(np.abs(got[robust] - ref['shape_' + k][robust]).max()))
+    for k in ('ellipse_A', 'ellipse_B'):
+        got = np.asarray(cat[k], dtype=np.float64)[knife]
+        want = ref['shape_' + k][knife]
+        both = (got != -99) & (want != -99)
+        np.testing.assert_allclose(got[both], want[both], rtol=1e-9, err_msg=k)
+    # batched: image 0 as above, image 1 the negated map searched with invertMap (the same objects)
+    sn = ops64.to_device(np.stack([tile['SNMap'], tile['SNMap']]), ops64.dtype)
+    tabs = photometry.findObjectsBatch(ops64, sn[:1], [tile['wcs']], [tile['flagMask']], ['shapes'], ['T0'], threshold=det['threshold'],
+                                       minObjPix=det['minObjPix'], rejectBorder=0, removeRings=True, ringThresholdSigma=det['ringThresholdSigma'],
+                                       measureShapes=True)
+    inv = photometry.findObjectsBatch(ops64, -sn[1:], [tile['wcs']], [tile['flagMask']], ['shapes'], ['T0'], threshold=det['threshold'],
+                                      minObjPix=det['minObjPix'], rejectBorder=0, removeRings=True, ringThresholdSigma=det['ringThresholdSigma'],
+                                      invertMap=True, measureShapes=True)
+    for t in (tabs[0], inv[0]):
+        assert len(t) == len(cat)
+        for k in shape_case.SHAPE_KEYS:
+            np.testing.assert_allclose(np.asarray(t[k], dtype=float)[robust], np.asarray(cat[k], dtype=float)[robust], rtol=1e-9, atol=1e-9, err_msg=k)
+    report("measure_shapes_reference_run", rows=len(cat), ellipses=int(robust.sum()), max_abs_err=worst)

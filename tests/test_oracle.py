@@ -347,3 +347,39 @@ def test_biweight_scale_restatement():
     assert abs(biweight_scale(3.0 * x + 5.0, 9.0, True) - 3.0 * s0) < 1e-9
     assert abs(biweight_scale(np.r_[x, 1e9], 9.0, True) - s0) < 1e-4
     assert biweight_scale(np.array([2., 2, 2, 2, 7]), 9.0, True) == 0.0
+
+
+def test_oracle_ellipses_match_reference_run():
+    """findObjects(measureShapes = True): the oracle's restatement of the SExtractor-style ellipse block (photometry.py:126-178)
+    against what the reference's own findObjects computed for the seeded S/N map of tests/golden/shape_case.py (ref_shapes.npz,
+    made by make_reference_golden.py): every ellipse column bit for bit, the -99 rows (objects of at most 9 pixels, and the two
+    exactly symmetric blobs whose xy moment is zero or rounding noise) included.  The host formulas the CUDA path uses
+    (nemo_b200.photometry.ellipsesFromMoments) get the same numbers from moments summed here in numpy."""
+    import shape_case
+    from nemo_b200 import photometry
+    ref = np.load(os.path.join(HERE, 'golden', 'ref_shapes.npz'))
+    tile = shape_case.shapeTile()
+    with np.errstate(divide='ignore', invalid='ignore'):
+        cat = photometry_ref.findObjects(tile, verbose=False, **shape_case.DETECT)
+    assert len(cat) == len(ref['shape_SNR']) >= 20
+    assert np.array_equal(np.array([r['numSigPix'] for r in cat], dtype=np.float64), ref['shape_numSigPix'])
+    for k in shape_case.SHAPE_KEYS:
+        assert np.array_equal(np.array([r[k] for r in cat], dtype=np.float64), ref['shape_' + k]), k
+    assert int((ref['shape_ellipse_A'] > 0).sum()) >= 15 and int((ref['shape_ellipse_A'] == -99).sum()) >= 2
+    # moments of every kept object about its bounding-box corner -> the host formulas
+    ids, pos, numPix, seg = photometry_ref.getObjectPositions(tile['SNMap'], shape_case.DETECT['threshold'])
+    rows, nPix = [], []
+    for i in range(len(ids)):
+        if ids[i] == 0 or numPix[i] <= shape_case.DETECT['minObjPix']:
+            continue
+        ys, xs = np.where(seg == ids[i])
+        d = tile['SNMap'][ys, xs]
+        xs, ys = xs - xs.min(), ys - ys.min()
+        yMin, xMin = np.where(seg == ids[i])[0].min(), np.where(seg == ids[i])[1].min()
+        rows.append([d.sum(), (xs * d).sum(), (ys * d).sum(), (xs ** 2 * d).sum(), (ys ** 2 * d).sum(), (xs * ys * d).sum(), xMin, yMin])
+        nPix.append(numPix[i])
+    got = photometry.ellipsesFromMoments(np.array(rows), np.array(nPix))
+    assert len(rows) == len(cat)          # nothing on a ring, every object above the S/N cut in this map
+    robust = np.abs(ref['shape_ellipse_e']) > 1e-6      # away from the symmetric knife edge
+    for k in shape_case.SHAPE_KEYS:
+        np.testing.assert_allclose(got[k][robust], ref['shape_' + k][robust], rtol=1e-12, atol=1e-12, err_msg=k)
