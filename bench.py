@@ -125,12 +125,14 @@ def cpuBaseline(kind, cores=None, steps=1, warmup=0):
 
 
 # ------------------------------------------------------------------------------------------------------
-def algorithmicBytes(nT, F, S, H, W, E, rings=True, yc=True, templateSpectraCached=True):
+def algorithmicBytes(nT, F, S, H, W, E, rings=True, yc=True, templateSpectraCached=True, separableWindow=False):
     """Algorithmic HBM bytes per step of every kernel of the batched Fourier path: own inputs read once + own outputs
     written once (SURVEY.md 8d / DESIGN.md), E = bytes per real (8 for f64, 4 for f32), complex = 2E.  Keyed by the names the
     library's event timers report; kernels that serve several passes are charged the sum of those passes.
     templateSpectraCached: the transforms of the signal templates are made once per tile geometry (pipelines.templateSpectraOf),
-    not per batch, so no FFT pass of a step is charged for them."""
+    not per batch, so no FFT pass of a step is charged for them.
+    separableWindow: the pixel-window undo runs as a column pass on pairs of real columns and one row kernel (real rows in, real
+    rows out, the zero pattern of the old data read once) instead of forward rows / column window / inverse rows."""
     N, Nc = H * W, H * (W // 2 + 1)
     P = F * (F + 1) // 2
     nOut = nT * S
@@ -140,20 +142,25 @@ def algorithmicBytes(nT, F, S, H, W, E, rings=True, yc=True, templateSpectraCach
     rowFwd = N * E + Nc * 2 * E               # per image: real rows in, half spectrum out
     rowInv = Nc * 2 * E + N * E
     col = 2 * Nc * 2 * E                      # half spectrum in and out
-    fwdImgs = nT * F + nTplFFT + (2 * nTplFFT if yc else 0) + nOut         # maps, unit templates, (windowed) norm templates, window undo
+    fwdImgs = nT * F + nTplFFT + (2 * nTplFFT if yc else 0) + (0 if separableWindow else nOut)   # maps, unit templates, (windowed) norm templates, window undo
     plainColImgs = nT * F + nTplFFT + (nTplFFT if yc else 0)
     windowColImgs = nOut + (nTplFFT if yc else 0)
     applyBytes = 2 * nOut * (F * Nc * E + Nc * 2 * E) + (nT * F + nTpl) * Nc * 2 * E     # filters in, product out; spectra once
-    invBytes = 2 * nOut * rowInv + nOut * N + nOut * rowInv + nOut * N * E + (nTplFFT * rowInv if yc else 0)   # + mask, + zero reference
+    invBytes = 2 * nOut * rowInv + nOut * N + (0 if separableWindow else nOut * rowInv + nOut * N * E) + (nTplFFT * rowInv if yc else 0)   # + mask, + zero reference
     b = {}
     for rows in ('rfft_rows_kernel', 'bs_rows_fwd_kernel', 'sfft_rows_fwd_kernel'):
         b[rows] = fwdImgs * rowFwd
     for rows in ('irfft_rows_kernel', 'bs_rows_inv_kernel', 'sfft_rows_inv_kernel'):
         b[rows] = invBytes
+    if separableWindow:
+        windowCol = 2 * H * (W // 2) * 2 * E          # pairs of real columns in and out
+        b['sfft_rows_window_kernel'] = nOut * 3 * N * E      # filtered rows in, old data (zero pattern) in, data out
+    else:
+        windowCol = col
     b['fft_cols_kernel'] = plainColImgs * col
-    b['fft_cols_window_kernel'] = windowColImgs * col
+    b['fft_cols_window_kernel'] = windowColImgs * windowCol
     b['fft_cols_apply_kernel'] = applyBytes
-    b['bs_cols_kernel'] = b['sfft_cols_kernel'] = plainColImgs * col + windowColImgs * col + applyBytes
+    b['bs_cols_kernel'] = b['sfft_cols_kernel'] = plainColImgs * col + windowColImgs * windowCol + applyBytes
     b['xpower_smooth_x_kernel'] = b['xpower_smooth_x_rb_kernel'] = nT * (F * Nc * 2 * E + P * N * 8)
     b['smooth_y_f64_kernel'] = b['smooth_y_rb_kernel'] = nT * P * N * 8 * 2
     b['build_filter_kernel'] = nT * P * N * 8 + nTpl * Nc * 2 * E + nOut * F * Nc * E
@@ -440,7 +447,8 @@ def main():
         peaks = json.load(open(peakPath))
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peakSrc = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
-    algo = algorithmicBytes(nT, F, S, H, W, E, rings=parDict['removeRings'], yc=(outputUnits == 'yc'))
+    algo = algorithmicBytes(nT, F, S, H, W, E, rings=parDict['removeRings'], yc=(outputUnits == 'yc'),
+                            separableWindow='sfft_rows_window_kernel' in prof)
     table = []
     totalKernelMs = sum(ms for _, ms in prof.values()) / profSteps
     for name, (cnt, ms) in prof.items():

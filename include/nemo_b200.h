@@ -106,9 +106,11 @@ int nb_template_norm(int prec, const void* map, int B, int H, int W, int mode, d
 
 /* fRelWeights (nemo/filters.py:664-670): value at pixel idx[b] of each frequency plane of
  * Re(ifft_unnormalised(fmaps[m(b), f] * filtH[b, f])); m(b) = b when S == 0, else b % S (S template spectra shared
- * by all tiles); out [B, F] fp64; scratch: B * F * 16 doubles. */
+ * by all tiles); out [B, F] fp64; scratch: B * F * 16 doubles.  total (may be NULL): [B] fp64, the value at idx[b] of the sum of
+ * the planes (the filtered template itself, which nb_template_norm has just found); the last frequency's plane is then taken as
+ * total minus the others instead of a sum over the Fourier plane. */
 int nb_plane_values_at(int prec, const void* fmaps, const void* filtH, const long long* idx, double* out, int B,
-                       int S, int F, int H, int W, double* scratch, cudaStream_t stream);
+                       int S, int F, int H, int W, const double* total, double* scratch, cudaStream_t stream);
 
 /* Maps as they are on disk (FITS BITPIX -32; the reference's MapDict.loadTile hands such arrays to MapFilter, nemo/maps.py:83-180,
  * nemo/filters.py:157-164, and numpy widens them in the first arithmetic operation) uploaded as float32 and widened on the

@@ -38,7 +38,7 @@ _PROTOTYPES = {
     "nb_build_filter_fused": [c_int, c_ptr, c_ptr, ctypes.POINTER(c_dbl), c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_dbl, c_ptr],
     "nb_fold_filter": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr],
     "nb_template_norm": [c_int, c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
-    "nb_plane_values_at": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr],
+    "nb_plane_values_at": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr],
     "nb_widen_f32": [c_ptr, c_ptr, c_ll, c_ptr],
     "nb_rms_area_table": [c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "nb_paint_objects": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr],

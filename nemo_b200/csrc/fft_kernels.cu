@@ -706,6 +706,15 @@ int nb_window_deconv(int prec, void* data, void* scratch, int B, int H, int W, c
     int rc;
     const int Wc = W / 2 + 1;
     const double scale = 1.0 / ((double)H * (double)W);
+    static const bool separable = !(getenv("NEMO_B200_WINDOW_SEPARABLE") && atoi(getenv("NEMO_B200_WINDOW_SEPARABLE")) == 0);
+    if (separable && use_sfft(H) && use_sfft(W) && W % 2 == 0) {
+        // the window is a product wy(ky) wx(kx): a filter along y on pairs of adjacent real columns (data -> scratch), then one
+        // along x on pairs of real rows (scratch -> data, zeros of the old data restored); see sfft_rows_window_kernel
+        rc = prec == NB_PREC_F64 ? nb_sfft_cols_window_io_f64(data, scratch, B, H, W / 2, wy, nullptr, st)
+                                 : nb_sfft_cols_window_io_f32(data, scratch, B, H, W / 2, wy, nullptr, st);
+        if (rc != NB_OK) return rc;
+        return nb_sfft_rows_window(prec, scratch, data, B, H, W, wx, scale, restoreZeros, st);
+    }
     if ((rc = rows_fwd(prec, data, scratch, B, H, W, 0, 1.0, st)) != NB_OK) return rc;
     if (use_sfft(H)) {
         rc = 1;

@@ -949,12 +949,23 @@ __global__ void __launch_bounds__(256) plane_values_partial_kernel(const typenam
     }
 }
 
-__global__ void plane_values_sum_kernel(const double* __restrict__ partial, double* __restrict__ out, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double t = 0;
-    for (int c = 0; c < PV_CHUNKS; ++c) t += partial[(size_t)i * PV_CHUNKS + c];
-    out[i] = t;
+// total != nullptr: only the first F - 1 planes of every image were summed; the last one is what is left of the image's total
+// (the planes add up to the filtered template, whose value at the pixel the caller already has: by linearity of the transform)
+__global__ void plane_values_sum_kernel(const double* __restrict__ partial, double* __restrict__ out, int B, int F,
+                                        const double* __restrict__ total) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double others = 0;
+    for (int f = 0; f < F; ++f) {
+        if (total && f == F - 1) {
+            out[(size_t)b * F + f] = total[b] - others;
+            break;
+        }
+        double t = 0;
+        for (int c = 0; c < PV_CHUNKS; ++c) t += partial[((size_t)b * F + f) * PV_CHUNKS + c];
+        out[(size_t)b * F + f] = t;
+        others += t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1147,12 +1158,14 @@ int nb_template_norm(int prec, const void* map, int B, int H, int W, int mode, d
 }
 
 int nb_plane_values_at(int prec, const void* fmaps, const void* filtH, const long long* idx, double* out, int B, int S,
-                       int F, int H, int W, double* scratch, cudaStream_t st) {
+                       int F, int H, int W, const double* total, double* scratch, cudaStream_t st) {
     NB_REQUIRE(fmaps && filtH && idx && out && scratch && B > 0 && F > 0, NB_ERR_ARG, "nb_plane_values_at: bad arguments");
     const size_t smem = sizeof(double) * 2 * ((size_t)(W / 2 + 1) + (size_t)((H + PV_CHUNKS - 1) / PV_CHUNKS));
     NB_REQUIRE(smem <= 48 * 1024, NB_ERR_UNSUPPORTED, "nb_plane_values_at: tile too wide");
-    dim3 grid(PV_CHUNKS, F, B);
-    if (prec == NB_PREC_F64) {
+    const int nSum = total ? F - 1 : F;      // planes summed over the Fourier plane; with `total` the last one is the remainder
+    dim3 grid(PV_CHUNKS, nSum > 0 ? nSum : 1, B);
+    if (nSum == 0) {
+    } else if (prec == NB_PREC_F64) {
         { NB_PROF_BEGIN(st); plane_values_partial_kernel<double><<<grid, 256, smem, st>>>((const double2*)fmaps, (const double*)filtH, idx, scratch, F, H, W, S); NB_PROF_END("plane_values_partial_kernel", st); }
     } else if (prec == NB_PREC_F32) {
         { NB_PROF_BEGIN(st); plane_values_partial_kernel<float><<<grid, 256, smem, st>>>((const float2*)fmaps, (const float*)filtH, idx, scratch, F, H, W, S); NB_PROF_END("plane_values_partial_kernel", st); }
@@ -1161,7 +1174,7 @@ int nb_plane_values_at(int prec, const void* fmaps, const void* filtH, const lon
         return NB_ERR_ARG;
     }
     NB_CHECK_LAUNCH();
-    { NB_PROF_BEGIN(st); plane_values_sum_kernel<<<(B * F + 255) / 256, 256, 0, st>>>(scratch, out, B * F); NB_PROF_END("plane_values_sum_kernel", st); }
+    { NB_PROF_BEGIN(st); plane_values_sum_kernel<<<(B + 255) / 256, 256, 0, st>>>(scratch, out, B, F, total); NB_PROF_END("plane_values_sum_kernel", st); }
     NB_CHECK_LAUNCH();
     return NB_OK;
 }

@@ -35,3 +35,8 @@ int nb_sfft_cols_apply_f64(const void* fmaps, const void* filt, void* out, int n
 int nb_sfft_cols_apply_f32(const void* fmaps, const void* filt, void* out, int nOut, int S, int perScale, int F, int H, int Wc, cudaStream_t st);
 int nb_sfft_cols_window_f64(void* data, int B, int H, int Wc, const void* wy, const void* wx, cudaStream_t st);
 int nb_sfft_cols_window_f32(void* data, int B, int H, int Wc, const void* wy, const void* wx, cudaStream_t st);
+// out of place, wx may be null (window in y only): the column half of the separable window undo
+int nb_sfft_cols_window_io_f64(const void* in, void* out, int B, int H, int Wc, const void* wy, const void* wx, cudaStream_t st);
+int nb_sfft_cols_window_io_f32(const void* in, void* out, int B, int H, int Wc, const void* wy, const void* wx, cudaStream_t st);
+// real rows -> real rows: forward transform, times wx[min(k, W - k)] * scale, inverse, in one kernel (the row half of it)
+int nb_sfft_rows_window(int prec, const void* in, void* out, int B, int H, int W, const void* wx, double scale, int restoreZeros, cudaStream_t st);

@@ -1278,8 +1278,20 @@ __global__ void __launch_bounds__(256) edge_rows_kernel(const T* __restrict__ ma
     }
 }
 
-#define EC_SEG 64
-#define EC_UNR 4      // rows whose loads are issued together
+// A thread walks one column for `seg` rows.  With an edge trim its window count starts from a walk over the `trim` rows around
+// the segment's first row (240 rows for the reference's default of three noise-grid steps), so short segments spend more
+// loads on that than on their pixels: 64-row segments 1.81 ms per 128 images of 840 x 1440, 420-row segments 1.32 ms, and 1.27 ms
+// with two rows in flight instead of four (whole columns, 1.44 ms, leave too few CTAs).  ec_seg_rows picks about 420.
+#define EC_SEG_MAX 1024
+#ifndef EC_UNR
+#define EC_UNR 2      // rows whose loads are issued together
+#endif
+static int ec_seg_rows(int H) {
+    int nSeg = (H + 210) / 420;
+    if (nSeg < 1) nSeg = 1;
+    int seg = (H + nSeg - 1) / nSeg;
+    return seg > EC_SEG_MAX ? EC_SEG_MAX : seg;
+}
 struct PaintArgs {   // what edge_cols_final_kernel<T, true> needs to take the RMS straight from the cell table
     const void* wmed;
     const double* table;
@@ -1291,13 +1303,14 @@ template <typename T, bool PAINT>
 __global__ void __launch_bounds__(128) edge_cols_final_kernel(T* map, T* rms, const unsigned char* __restrict__ ps,
                                                               const unsigned char* __restrict__ survey, int S, int H, int W, int trim,
                                                               int apodPix, int realSpace, const unsigned char* __restrict__ rowAny,
-                                                              T* sn, unsigned char* __restrict__ maskOut, PaintArgs pa, const Chunks ch) {
+                                                              T* sn, unsigned char* __restrict__ maskOut, PaintArgs pa, const Chunks ch,
+                                                              const int seg) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ys = blockIdx.y * EC_SEG, img = blockIdx.z;
+    const int ys = blockIdx.y * seg, img = blockIdx.z;
     // candidate cell rows of every row of this segment: the same for all columns, so found once per block (the search divides)
-    __shared__ short s_iLo[EC_SEG], s_iHi[EC_SEG];
+    __shared__ short s_iLo[EC_SEG_MAX], s_iHi[EC_SEG_MAX];
     if constexpr (PAINT) {
-        for (int r = threadIdx.x; r < EC_SEG; r += blockDim.x) {
+        for (int r = threadIdx.x; r < seg; r += blockDim.x) {
             int a = 0, b = 0;
             if (ys + r < H) paint_axis_range(ys + r, ch.y, pa.ny, pa.ov, H, a, b);
             s_iLo[r] = (short)a;
@@ -1313,7 +1326,7 @@ __global__ void __launch_bounds__(128) edge_cols_final_kernel(T* map, T* rms, co
     if (trim > 0) {
         for (int d = lo; d <= hi; ++d) cnt += ra[(size_t)reflect_idx(ys + d, H) * W + x];
     }
-    const int ye = min(ys + EC_SEG, H);
+    const int ye = min(ys + seg, H);
     int kLo = 0, kHi = 0;
     if constexpr (PAINT) paint_axis_range(x, ch.x, pa.nx, pa.ov, W, kLo, kHi);   // the same for every row of this column
     // the last-written candidate cell (iHi, kHi) always covers the pixel and nearly always paints it; while the rows of this
@@ -1485,15 +1498,16 @@ static int snr_mask_t(void* map, void* rms, const unsigned char* ps, const unsig
         { NB_PROF_BEGIN(st); edge_rows_kernel<T><<<dim3(H, nImg), 256, sizeof(int) * (W + 1), st>>>((const T*)map, ps, S, H, W, trim, scratch); NB_PROF_END("edge_rows_kernel", st); }
         NB_CHECK_LAUNCH();
     }
+    const int seg = ec_seg_rows(H);
     if (pa) {
-        { NB_PROF_BEGIN(st); edge_cols_final_kernel<T, true><<<dim3((W + 127) / 128, (H + EC_SEG - 1) / EC_SEG, nImg), 128, 0, st>>>(
-            (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut, *pa, *chp); NB_PROF_END("edge_cols_final_paint_kernel", st); }
+        { NB_PROF_BEGIN(st); edge_cols_final_kernel<T, true><<<dim3((W + 127) / 128, (H + seg - 1) / seg, nImg), 128, 0, st>>>(
+            (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut, *pa, *chp, seg); NB_PROF_END("edge_cols_final_paint_kernel", st); }
     } else {
         PaintArgs none = {nullptr, nullptr, nullptr, 0, 0, 0, 0};
         Chunks ch0;
         memset(&ch0, 0, sizeof(ch0));
-        { NB_PROF_BEGIN(st); edge_cols_final_kernel<T, false><<<dim3((W + 127) / 128, (H + EC_SEG - 1) / EC_SEG, nImg), 128, 0, st>>>(
-            (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut, none, ch0); NB_PROF_END("edge_cols_final_kernel", st); }
+        { NB_PROF_BEGIN(st); edge_cols_final_kernel<T, false><<<dim3((W + 127) / 128, (H + seg - 1) / seg, nImg), 128, 0, st>>>(
+            (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut, none, ch0, seg); NB_PROF_END("edge_cols_final_kernel", st); }
     }
     NB_CHECK_LAUNCH();
     return NB_OK;

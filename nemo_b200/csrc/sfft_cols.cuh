@@ -100,7 +100,7 @@ sfft_cols_kernel(const typename V2<T>::type* __restrict__ in, const T* __restric
     if constexpr (MODE == 2) {
         typedef typename Last<PR, NT>::S SRL;
         run_from<PL, T, NT, -1, 0>(xr, xi, t, s_re, s_im, tw, BlockSync(), [&](auto& yr, auto& yi) {
-            const T wxc = valid ? wx[col] : (T)0;
+            const T wxc = valid ? (wx ? wx[col] : (T)1) : (T)0;      // wx == nullptr: a window in y only (separable undo)
 #pragma unroll
             for (int i = 0; i < SL::IT; ++i) {
                 const int j = t + i * NT;
@@ -179,4 +179,7 @@ static int sfft_cols_t(const typename V2<T>::type* in, const T* filt, typename V
     }                                                                                                                                     \
     int nb_sfft_cols_window_##SUFFIX(void* data, int B, int H, int Wc, const void* wy, const void* wx, cudaStream_t st) {                 \
         return sfft_cols_t<T, 2, -1, 1>((const C2T*)data, nullptr, (C2T*)data, B, 1, 0, H, Wc, (const T*)wy, (const T*)wx, st);            \
+    }                                                                                                                                     \
+    int nb_sfft_cols_window_io_##SUFFIX(const void* in, void* out, int B, int H, int Wc, const void* wy, const void* wx, cudaStream_t st) { \
+        return sfft_cols_t<T, 2, -1, 1>((const C2T*)in, nullptr, (C2T*)out, B, 1, 0, H, Wc, (const T*)wy, (const T*)wx, st);               \
     }

@@ -545,6 +545,136 @@ static int sfft_rows_inv_t(const typename V2<T>::type* in, T* out, int B, int H,
     return NB_ERR_UNSUPPORTED;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Row half of the separable window undo (K8: enmap.apply_window(data, pow = -1), filters.py:101-104).  The pixel window is a
+// product wy(ky) wx(kx), so dividing the 2-D spectrum by it is a filter along y followed by a filter along x, each of them a
+// transform, a REAL and EVEN multiplier and the inverse transform.  Such a multiplier commutes with the two-for-one packing:
+// with z = a + i b for two real rows a, b the product w Z is the transform of (w * a) + i (w * b), so the kernel transforms the
+// packed pair, multiplies by wx[min(k, W - k)], runs the reversed plan backwards (whose first pass wants exactly what the
+// forward's last pass left in each thread: no exchange in between) and stores the two real rows -- the half spectra never exist.
+// Together with the column kernel in MODE 2 on pairs of adjacent real columns (sfft_cols.cuh) the undo moves 40 bytes per pixel
+// instead of the 56 of forward rows / column window / inverse rows.  out may hold the data before the undo: where it is exactly
+// zero the result is zero (restoreZeros; the pattern is read up front, one bit per register slot, as in the inverse kernel).
+#ifndef SFFT_ROWW_G
+#define SFFT_ROWW_G 2
+#endif
+#ifndef SFFT_ROWW_MINB
+#define SFFT_ROWW_MINB 3      // two row pairs per CTA, three CTAs per SM: 1.54 ms per 128 images of 840 x 1440 (2.00 with two CTAs; one pair per CTA 1.69)
+#endif
+template <typename T, class PL, int NT, int G>
+__global__ void __launch_bounds__(NT * G, SFFT_ROWW_MINB)
+sfft_rows_window_kernel(const T* __restrict__ in, T* out, long long nrows, const T* __restrict__ wx, T scale, int restoreZeros,
+                        const typename V2<T>::type* __restrict__ tw, const typename V2<T>::type* __restrict__ twRev) {
+    typedef SRowCfg<T, PL::N, G> Cfg;
+    typedef typename Reversed<PL>::type PR;
+    typedef Stage<PL, NT, 0> S0;
+    typedef typename Last<PL, NT>::S SL;
+    typedef typename Last<PR, NT>::S SRL;
+    constexpr int W = PL::N;
+    static_assert(SRL::REGS <= 32, "one bit per register slot");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
+    const int g = threadIdx.x / NT, t = threadIdx.x % NT;
+    const long long r0 = ((long long)blockIdx.x * G + g) * 2, r1 = r0 + 1;
+    T* s_re = smem + g * Cfg::LD;
+    T* s_im = smem + (G + g) * Cfg::LD;
+    const bool v0 = r0 < nrows, v1 = r1 < nrows;
+    T* o0 = out + (size_t)(v0 ? r0 : 0) * W;
+    T* o1 = out + (size_t)(v1 ? r1 : 0) * W;
+    unsigned zb0 = 0u, zb1 = 0u;
+    if (restoreZeros) {
+#pragma unroll
+        for (int i = 0; i < SRL::IT; ++i) {
+            const int j = t + i * NT;
+#pragma unroll
+            for (int r = 0; r < SRL::R; ++r) {
+                if (SRL::IT * NT == SRL::NB || j < SRL::NB) {
+                    const int n = j + r * SRL::NB;
+                    if (v0 && o0[n] == (T)0) zb0 |= 1u << (i * SRL::R + r);
+                    if (v1 && o1[n] == (T)0) zb1 |= 1u << (i * SRL::R + r);
+                }
+            }
+        }
+    }
+    const T* row0 = in + (size_t)(v0 ? r0 : 0) * W;
+    const T* row1 = in + (size_t)(v1 ? r1 : 0) * W;
+    T xr[S0::REGS], xi[S0::REGS];
+#pragma unroll
+    for (int i = 0; i < S0::IT; ++i) {
+        const int j = t + i * NT;
+#pragma unroll
+        for (int r = 0; r < S0::R; ++r) {
+            T a = 0, b = 0;
+            if (S0::IT * NT == S0::NB || j < S0::NB) {
+                const int n = j + r * S0::NB;
+                a = row0[n];
+                b = row1[n];
+            }
+            xr[i * S0::R + r] = v0 ? a : (T)0;
+            xi[i * S0::R + r] = v1 ? b : (T)0;
+        }
+    }
+    run_from<PL, T, NT, -1, 0>(xr, xi, t, s_re, s_im, tw, BlockSync(), [&](auto& yr, auto& yi) {
+#pragma unroll
+        for (int i = 0; i < SL::IT; ++i) {
+            const int j = t + i * NT;
+            if (SL::IT * NT > SL::NB && j >= SL::NB) continue;
+#pragma unroll
+            for (int r = 0; r < SL::R; ++r) {
+                const int k = j + r * SL::NB;
+                const T w = wx[2 * k <= W ? k : W - k] * scale;
+                yr[i * SL::R + r] *= w;
+                yi[i * SL::R + r] *= w;
+            }
+        }
+        run_from<PR, T, NT, +1, 0>(yr, yi, t, s_re, s_im, twRev, BlockSync(), [&](auto& zr, auto& zi) {
+#pragma unroll
+            for (int i = 0; i < SRL::IT; ++i) {
+                const int j = t + i * NT;
+                if (SRL::IT * NT > SRL::NB && j >= SRL::NB) continue;
+#pragma unroll
+                for (int r = 0; r < SRL::R; ++r) {
+                    const int q = i * SRL::R + r, n = j + r * SRL::NB;
+                    if (v0) o0[n] = ((zb0 >> q) & 1u) ? (T)0 : zr[q];
+                    if (v1) o1[n] = ((zb1 >> q) & 1u) ? (T)0 : zi[q];
+                }
+            }
+        });
+    });
+}
+
+template <typename T>
+static int sfft_rows_window_t(const T* in, T* out, int B, int H, int W, const T* wx, double scale, int restoreZeros, cudaStream_t st) {
+    typedef typename V2<T>::type C2;
+    const int prec = sizeof(T) == 8 ? NB_PREC_F64 : NB_PREC_F32;
+    const long long nrows = (long long)B * H;
+    const long long npairs = (nrows + 1) / 2;
+    constexpr int G = SFFT_ROWW_G;
+    int rc;
+    const void *tw, *twRev;
+#define SFFT_CASE(NN, R0, R1, R2, NT, CR0, CR1, CR2, CNT)                                                                              \
+    if (W == NN) {                                                                                                        \
+        typedef Plan<NN, R0, R1, R2> PL;                                                                                  \
+        typedef SRowCfg<T, NN, G> Cfg;                                                                                    \
+        if ((rc = sfft_tw<PL>(prec, &tw)) != NB_OK) return rc;                                                            \
+        if ((rc = sfft_tw<typename Reversed<PL>::type>(prec, &twRev)) != NB_OK) return rc;                                \
+        if ((rc = sfft_set_smem(sfft_rows_window_kernel<T, PL, NT, G>, Cfg::SMEM)) != NB_OK) return rc;                   \
+        const unsigned grid = (unsigned)((npairs + G - 1) / G);                                                           \
+        { NB_PROF_BEGIN(st); sfft_rows_window_kernel<T, PL, NT, G><<<grid, NT * G, Cfg::SMEM, st>>>(in, out, nrows, wx, (T)scale, restoreZeros, (const C2*)tw, (const C2*)twRev); NB_PROF_END("sfft_rows_window_kernel", st); } \
+        NB_CHECK_LAUNCH();                                                                                                \
+        return NB_OK;                                                                                                     \
+    }
+    SFFT_FOR_SIZES(SFFT_CASE)
+#undef SFFT_CASE
+    nb_set_error("sfft: width %d has no compile-time plan", W);
+    return NB_ERR_UNSUPPORTED;
+}
+
+int nb_sfft_rows_window(int prec, const void* in, void* out, int B, int H, int W, const void* wx, double scale, int restoreZeros, cudaStream_t st) {
+    if (prec == NB_PREC_F64) return sfft_rows_window_t<double>((const double*)in, (double*)out, B, H, W, (const double*)wx, scale, restoreZeros, st);
+    return sfft_rows_window_t<float>((const float*)in, (float*)out, B, H, W, (const float*)wx, scale, restoreZeros, st);
+}
+
 int nb_sfft_rows_fwd(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st) {
     if (prec == NB_PREC_F64) return sfft_rows_fwd_t<double>((const double*)in, (double2*)out, B, H, W, apodPix, scale, st);
     return sfft_rows_fwd_t<float>((const float*)in, (float2*)out, B, H, W, apodPix, scale, st);

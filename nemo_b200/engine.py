@@ -175,7 +175,8 @@ def buildFourierFilters(ops, fmapsNoise, templUnit, templNorm, w, outputUnits, c
     signalNorm, argmaxIdx, maxVal, centreVal = ops.template_norm(filteredSignal, mode, cy, cx, numer)
     fRel = None
     if outputUnits == 'yc':
-        planes = ops.plane_values_at(fsigN, filtH, argmaxIdx, S=0 if sigPerTile else S, W=W)
+        # (the planes add up to filteredSignal -- unless a background was subtracted from it -- so the last one is the remainder)
+        planes = ops.plane_values_at(fsigN, filtH, argmaxIdx, S=0 if sigPerTile else S, W=W, total=maxVal if bckSubSigmas is None else None)
         # fRelWeight = plane value at the argmax pixel / total signal there (filters.py:664-670)
         fRel = (planes, maxVal)
     return {'filtH': filtH, 'filtFull': filtFull, 'signalNorm': signalNorm, 'fRel': fRel, 'S': S}

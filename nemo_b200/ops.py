@@ -218,15 +218,19 @@ class Ops(object):
         self.launches += 2
         return norm, argmax, maxVal, centre
 
-    def plane_values_at(self, fmaps, filtH, idx, S=0, W=None):
-        """Per-frequency filtered-template values at pixel idx[b]; S > 0: fmaps holds S template spectra shared by all tiles."""
+    def plane_values_at(self, fmaps, filtH, idx, S=0, W=None, total=None):
+        """Per-frequency filtered-template values at pixel idx[b]; S > 0: fmaps holds S template spectra shared by all tiles.
+        total [B] fp64: the value of the filtered template (all frequencies) at that pixel, when the caller has it -- the planes
+        add up to it, so the last frequency's plane is taken as the remainder instead of a sum over the Fourier plane."""
         self._check(fmaps, self.cdtype, 'fmaps')
         self._check(filtH, self.dtype, 'filtH')
         B, F, H, Wc = filtH.shape
         out = self.empty((B, F), self.torch.float64)
         scratch = self.empty((B * F * 16,), self.torch.float64)
+        if total is not None:
+            self._check(total, self.torch.float64, 'total')
         _lib.call('nb_plane_values_at', self.prec, _ptr(fmaps), _ptr(filtH), _ptr(idx), _ptr(out), B, int(S), F, H, self._width(Wc, W),
-                  _ptr(scratch), self._stream())
+                  _ptr(total), _ptr(scratch), self._stream())
         self.launches += 2
         return out
 

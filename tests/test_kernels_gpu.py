@@ -237,8 +237,12 @@ def test_plane_values_at_f64(ops64, report, H, W):
     filtH = ops64.fold_filter(ops64.to_device(filt))
     got = _np(ops64.plane_values_at(fmaps, filtH, ops64.to_device(idx, ops64.torch.int64), W=W))
     err = _relerr(got, ref)
-    report("plane_values_at", relerr=err)
-    assert err < 1e-11
+    # with the total given, the last plane is the remainder: the same numbers to rounding
+    total = ops64.to_device(ref.sum(axis=1))
+    got2 = _np(ops64.plane_values_at(fmaps, filtH, ops64.to_device(idx, ops64.torch.int64), W=W, total=total))
+    err2 = _relerr(got2, ref)
+    report("plane_values_at", relerr=err, relerr_with_total=err2)
+    assert err < 1e-11 and err2 < 1e-11
 
 
 # ----------------------------------------------------------------------------------------------------------
