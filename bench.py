@@ -165,7 +165,7 @@ def algorithmicBytes(nT, F, S, H, W, E, rings=True, yc=True, templateSpectraCach
     b['smooth_y_f64_kernel'] = b['smooth_y_rb_kernel'] = nT * P * N * 8 * 2
     b['build_filter_kernel'] = nT * P * N * 8 + nTpl * Nc * 2 * E + nOut * F * Nc * E
     b['template_argmax_partial_kernel'] = nOut * N * E
-    b['plane_values_partial_kernel'] = nOut * F * Nc * E + nTpl * Nc * 2 * E
+    b['plane_values_partial_kernel'] = (nOut * Nc * E + S * Nc * 2 * E) * max(F - 1, 0)    # the last frequency's plane is the remainder of the total
     for k6 in ('cell_rms_onchip_kernel', 'cell_rms_hybrid_kernel', 'cell_rms_stream_kernel', 'cell_rms_kernel', 'paint_rms_kernel'):
         b[k6] = nOut * N * E + nT * N * E      # every image's map; the median weights of its tile
     b['zone_moments_kernel'] = nOut * N * E + nT * N * E     # one-bin K6: map once + the tile's median weights; then the map once more
