@@ -62,10 +62,13 @@ int nb_irfft2(int prec, void* spec, void* out, int B, int H, int W, double scale
  * template spectra shared by all tiles: the normalisation pass, filters.py:653, 686).
  * fmaps [nOut / S or S, F, H, Wc] complex(T); filtH [nOut, F, H, Wc] real T = the filter folded onto the half plane,
  * (filt(k) + filt(-k)) / 2, which is what taking the real part of the full complex inverse transform does;
- * scratch [nOut, H, Wc] complex(T).  norm / mask may be NULL. */
+ * scratch [nOut, H, Wc] complex(T).  norm / mask may be NULL.
+ * zeroFlags (may be NULL): [nOut] int32, set to 0 for an image in which out + (1 - mask) is nowhere exactly zero -- the pixels
+ * the edge filter of nb_snr_mask* searches for (filters.py:730) -- and non-zero otherwise or when the path taken cannot tell (only the
+ * row passes with a compile-time plan report it, as a by-product of their store). */
 int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratch, void* out, int nOut, int S,
                     int perScale, int F, int H, int W, double scale, const double* norm, const unsigned char* mask,
-                    cudaStream_t stream);
+                    int* zeroFlags, cudaStream_t stream);
 
 /* K8: enmap.apply_window(data, pow) and the zero restore (nemo/filters.py:101-104; pipelines.py:229-232).
  * wy [H], wx [Wc] (type T) hold the window already raised to pow; data [B, H, W] is transformed in place;
@@ -183,10 +186,11 @@ int nb_cell_rms_est(int prec, const void* map, const void* wmed, int nImg, int S
  * Out (may alias the inputs): data = map * edgeCheck (* edgeCheck*surveyMask*psMask unless realSpace),
  * sn = where(rms > 0, map / rms, map) * maskOut with NaN -> 0, rms *= maskOut,
  * maskOut u8 = edgeCheck * surveyMask * psMask * apodMask (apodMask trims apodPix - 1 pixels per edge).
- * scratch: nImg * H * W bytes. */
+ * scratch: nImg * H * W bytes.  zeroFlags (may be NULL): [nImg] int32 from nb_apply_filter for this very map; an image whose
+ * flag is 0 has no zero for the rank filter to find, so edgeCheck is 1 everywhere and neither pass of the filter runs for it. */
 int nb_snr_mask(int prec, void* map, void* rms, const unsigned char* psMask, const unsigned char* surveyMask,
                 int nImg, int S, int H, int W, int trimPix, int apodPix, int realSpace, void* sn,
-                unsigned char* maskOut, unsigned char* scratch, cudaStream_t stream);
+                unsigned char* maskOut, unsigned char* scratch, const int* zeroFlags, cudaStream_t stream);
 
 /* K6 painting fused into K7: as nb_snr_mask, but the RMS of every pixel is taken straight from the cell table of
  * nb_cell_rms (called with rms = NULL, which skips its painting pass) instead of from a painted RMS map; rmsOut receives
@@ -196,7 +200,7 @@ int nb_snr_mask_cells(int prec, void* map, const void* wmed, const double* table
                       int ny, const int* xChunks, int nx, int overlapPix, int numBins, const unsigned char* psMask,
                       const unsigned char* surveyMask, int nImg, int S, int H, int W, int trimPix, int apodPix,
                       int realSpace, void* sn, void* rmsOut, unsigned char* maskOut, unsigned char* scratch,
-                      cudaStream_t stream);
+                      const int* zeroFlags, cudaStream_t stream);
 
 /* S/N from a cached RMS map (nemo/pipelines.py:216-228): sn = where(rms > 0, map / rms, map). */
 int nb_snr_from_rms(int prec, const void* map, const void* rms, void* sn, int nImg, int S, int H, int W,

@@ -31,7 +31,7 @@ _PROTOTYPES = {
     "nb_prof_report": [ctypes.c_char_p, c_ll],
     "nb_rfft2": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_ptr],
     "nb_irfft2": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr, c_int, c_ptr],
-    "nb_apply_filter": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr, c_ptr],
+    "nb_apply_filter": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr],
     "nb_window_deconv": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr],
     "nb_xpower_smooth": [c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_ptr],
     "nb_build_filter": [c_int, c_ptr, c_ptr, ctypes.POINTER(c_dbl), c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr],
@@ -51,9 +51,9 @@ _PROTOTYPES = {
                     c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "nb_cell_rms_est": [c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int), c_int,
                         c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
-    "nb_snr_mask": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
+    "nb_snr_mask": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "nb_snr_mask_cells": [c_int, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int), c_int, c_int, c_int, c_ptr, c_ptr,
-                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "nb_snr_from_rms": [c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
     "nb_label4": [c_int, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr],
     "nb_label4_scratch_ints": [c_int, c_int, c_int],

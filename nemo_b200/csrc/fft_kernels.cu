@@ -615,10 +615,15 @@ static int rows_fwd(int prec, const void* in, void* out, int B, int H, int W, in
     return rfft_rows_t<float>((const float*)in, (float2*)out, B, H, W, apodPix, scale, st);
 }
 
+// zeroFlags (may be null): [B] int32, 0 for an image in which out + (1 - mask) is nowhere exactly zero -- the pixels K7's edge
+// filter looks for, which it then need not search (nb_snr_mask*).  Only the row kernels with a compile-time plan report it, as a
+// by-product of their store; every other path answers 1 (unknown) for all images.
 static int rows_inv(int prec, const void* in, void* out, int B, int H, int W, double scale, const double* norm, const unsigned char* mask,
-                    int maskDiv, const void* zeroRef, cudaStream_t st) {
+                    int maskDiv, const void* zeroRef, cudaStream_t st, int* zeroFlags = nullptr) {
     if (maskDiv < 1) maskDiv = 1;
-    if (use_sfft(W)) return nb_sfft_rows_inv(prec, in, out, B, H, W, scale, norm, mask, maskDiv, zeroRef, st);
+    const bool flagsHere = zeroFlags && mask && use_sfft(W);
+    if (zeroFlags) NB_CHECK_CUDA(cudaMemsetAsync(zeroFlags, flagsHere ? 0 : 1, sizeof(int) * (size_t)B, st));
+    if (use_sfft(W)) return nb_sfft_rows_inv(prec, in, out, B, H, W, scale, norm, mask, maskDiv, zeroRef, flagsHere ? zeroFlags : nullptr, st);
     if (!is_pow2_side(W)) return nb_bs_rows_inv(prec, in, out, B, H, W, scale, norm, mask, maskDiv, zeroRef, st);
     if (prec == NB_PREC_F64) {
         C2RParams<double> ep = {scale, norm, mask, maskDiv, (const double*)zeroRef};
@@ -661,7 +666,7 @@ int nb_irfft2(int prec, void* spec, void* out, int B, int H, int W, double scale
 }
 
 int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratch, void* out, int nOut, int S, int perScale,
-                    int F, int H, int W, double scale, const double* norm, const unsigned char* mask, cudaStream_t st) {
+                    int F, int H, int W, double scale, const double* norm, const unsigned char* mask, int* zeroFlags, cudaStream_t st) {
     NB_REQUIRE(fmaps && filtH && scratch && out && nOut > 0 && S > 0, NB_ERR_ARG, "nb_apply_filter: bad arguments");
     NB_REQUIRE(prec == NB_PREC_F64 || prec == NB_PREC_F32, NB_ERR_ARG, "nb_apply_filter: bad precision %d", prec);
     NB_REQUIRE(F >= 1 && F <= NB_MAX_FREQ, NB_ERR_UNSUPPORTED, "nb_apply_filter: %d frequencies not supported (1..%d)", F, NB_MAX_FREQ);
@@ -695,7 +700,7 @@ int nb_apply_filter(int prec, const void* fmaps, const void* filtH, void* scratc
 #undef APPLY_F
     }
     if (rc != NB_OK) return rc;
-    return rows_inv(prec, scratch, out, nOut, H, W, scale, norm, mask, S, nullptr, st);
+    return rows_inv(prec, scratch, out, nOut, H, W, scale, norm, mask, S, nullptr, st, zeroFlags);
 }
 
 int nb_window_deconv(int prec, void* data, void* scratch, int B, int H, int W, const void* wy, const void* wx,

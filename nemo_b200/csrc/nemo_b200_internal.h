@@ -23,7 +23,7 @@ int nb_bs_cols_window(int prec, void* data, int B, int H, int Wc, const void* wy
 int nb_sfft_supported(int n);
 int nb_sfft_rows_fwd(int prec, const void* in, void* out, int B, int H, int W, int apodPix, double scale, cudaStream_t st);
 int nb_sfft_rows_inv(int prec, const void* in, void* out, int B, int H, int W, double scale, const double* norm, const unsigned char* mask,
-                     int maskDiv, const void* zeroRef, cudaStream_t st);
+                     int maskDiv, const void* zeroRef, int* zeroFlag, cudaStream_t st);
 // TMA-fed column passes (sfft_cols_tma.cu, fp64): NB_OK when launched, 1 when the path does not apply (fall back), < 0 on error
 int nb_sfft_cols_tma_f64(const void* in, void* out, int B, int H, int Wc, int dir, cudaStream_t st);
 int nb_sfft_cols_window_tma_f64(void* data, int B, int H, int Wc, const void* wy, const void* wx, cudaStream_t st);

@@ -1226,10 +1226,12 @@ __global__ void __launch_bounds__(256) paint_rms_kernel(const T* __restrict__ wm
 // fused with the final elementwise step.
 template <typename T>
 __global__ void __launch_bounds__(256) edge_rows_kernel(const T* __restrict__ map, const unsigned char* __restrict__ ps, int S, int H,
-                                                        int W, int trim, unsigned char* __restrict__ rowAny) {
+                                                        int W, int trim, unsigned char* __restrict__ rowAny,
+                                                        const int* __restrict__ zeroFlags) {
     extern __shared__ int s_pre[];  // W + 1 prefix counts of zeros
     __shared__ int s_part[256];
     const int y = blockIdx.x, img = blockIdx.y;
+    if (zeroFlags && zeroFlags[img] == 0) return;      // the kernel that wrote this image saw no zero: the column pass will not read rowAny
     const T* m = map + ((size_t)img * H + y) * W;
     const unsigned char* p = ps + ((size_t)(img / S) * H + y) * W;
     const int per = (W + blockDim.x - 1) / blockDim.x;
@@ -1304,9 +1306,11 @@ __global__ void __launch_bounds__(128) edge_cols_final_kernel(T* map, T* rms, co
                                                               const unsigned char* __restrict__ survey, int S, int H, int W, int trim,
                                                               int apodPix, int realSpace, const unsigned char* __restrict__ rowAny,
                                                               T* sn, unsigned char* __restrict__ maskOut, PaintArgs pa, const Chunks ch,
-                                                              const int seg) {
+                                                              const int seg, const int* __restrict__ zeroFlags) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int ys = blockIdx.y * seg, img = blockIdx.z;
+    // an image whose producer reported that map + (1 - psMask) is nowhere zero has edgeCheck = 1 everywhere: no window to count
+    if (zeroFlags && zeroFlags[img] == 0) trim = 0;
     // candidate cell rows of every row of this segment: the same for all columns, so found once per block (the search divides)
     __shared__ short s_iLo[EC_SEG_MAX], s_iHi[EC_SEG_MAX];
     if constexpr (PAINT) {
@@ -1493,21 +1497,21 @@ static int cell_rms_t(const void* map, const void* wmed, int nImg, int S, int H,
 template <typename T>
 static int snr_mask_t(void* map, void* rms, const unsigned char* ps, const unsigned char* survey, int nImg, int S, int H, int W,
                       int trim, int apodPix, int realSpace, void* sn, unsigned char* maskOut, unsigned char* scratch, cudaStream_t st,
-                      const PaintArgs* pa = nullptr, const Chunks* chp = nullptr) {
+                      const int* zeroFlags, const PaintArgs* pa = nullptr, const Chunks* chp = nullptr) {
     if (trim > 0) {
-        { NB_PROF_BEGIN(st); edge_rows_kernel<T><<<dim3(H, nImg), 256, sizeof(int) * (W + 1), st>>>((const T*)map, ps, S, H, W, trim, scratch); NB_PROF_END("edge_rows_kernel", st); }
+        { NB_PROF_BEGIN(st); edge_rows_kernel<T><<<dim3(H, nImg), 256, sizeof(int) * (W + 1), st>>>((const T*)map, ps, S, H, W, trim, scratch, zeroFlags); NB_PROF_END("edge_rows_kernel", st); }
         NB_CHECK_LAUNCH();
     }
     const int seg = ec_seg_rows(H);
     if (pa) {
         { NB_PROF_BEGIN(st); edge_cols_final_kernel<T, true><<<dim3((W + 127) / 128, (H + seg - 1) / seg, nImg), 128, 0, st>>>(
-            (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut, *pa, *chp, seg); NB_PROF_END("edge_cols_final_paint_kernel", st); }
+            (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut, *pa, *chp, seg, zeroFlags); NB_PROF_END("edge_cols_final_paint_kernel", st); }
     } else {
         PaintArgs none = {nullptr, nullptr, nullptr, 0, 0, 0, 0};
         Chunks ch0;
         memset(&ch0, 0, sizeof(ch0));
         { NB_PROF_BEGIN(st); edge_cols_final_kernel<T, false><<<dim3((W + 127) / 128, (H + seg - 1) / seg, nImg), 128, 0, st>>>(
-            (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut, none, ch0, seg); NB_PROF_END("edge_cols_final_kernel", st); }
+            (T*)map, (T*)rms, ps, survey, S, H, W, trim, apodPix, realSpace, scratch, (T*)sn, maskOut, none, ch0, seg, zeroFlags); NB_PROF_END("edge_cols_final_kernel", st); }
     }
     NB_CHECK_LAUNCH();
     return NB_OK;
@@ -1586,15 +1590,15 @@ int nb_cell_rms_est(int prec, const void* map, const void* wmed, int nImg, int S
 
 int nb_snr_mask(int prec, void* map, void* rms, const unsigned char* psMask, const unsigned char* surveyMask, int nImg, int S,
                 int H, int W, int trimPix, int apodPix, int realSpace, void* sn, unsigned char* maskOut, unsigned char* scratch,
-                cudaStream_t st) {
+                const int* zeroFlags, cudaStream_t st) {
     NB_REQUIRE(map && rms && psMask && surveyMask && sn && maskOut && nImg > 0 && S > 0, NB_ERR_ARG, "nb_snr_mask: bad arguments");
     NB_REQUIRE(trimPix == 0 || scratch, NB_ERR_ARG, "nb_snr_mask: scratch required when trimPix > 0");
     NB_REQUIRE(trimPix >= 0, NB_ERR_ARG, "nb_snr_mask: negative trimPix %d", trimPix);
     NB_REQUIRE(W <= 8192, NB_ERR_UNSUPPORTED, "nb_snr_mask: tile too wide");
     if (prec == NB_PREC_F64)
-        return snr_mask_t<double>(map, rms, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st);
+        return snr_mask_t<double>(map, rms, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st, zeroFlags);
     if (prec == NB_PREC_F32)
-        return snr_mask_t<float>(map, rms, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st);
+        return snr_mask_t<float>(map, rms, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st, zeroFlags);
     nb_set_error("nb_snr_mask: bad precision %d", prec);
     return NB_ERR_ARG;
 }
@@ -1602,7 +1606,7 @@ int nb_snr_mask(int prec, void* map, void* rms, const unsigned char* psMask, con
 int nb_snr_mask_cells(int prec, void* map, const void* wmed, const double* table, const double* edges, const int* yChunks, int ny,
                       const int* xChunks, int nx, int overlapPix, int numBins, const unsigned char* psMask,
                       const unsigned char* surveyMask, int nImg, int S, int H, int W, int trimPix, int apodPix, int realSpace, void* sn,
-                      void* rmsOut, unsigned char* maskOut, unsigned char* scratch, cudaStream_t st) {
+                      void* rmsOut, unsigned char* maskOut, unsigned char* scratch, const int* zeroFlags, cudaStream_t st) {
     NB_REQUIRE(map && wmed && table && edges && yChunks && xChunks && psMask && surveyMask && sn && maskOut && nImg > 0 && S > 0,
                NB_ERR_ARG, "nb_snr_mask_cells: bad arguments");      // rmsOut may be NULL: the painted RMS map is then not written
     NB_REQUIRE(trimPix == 0 || scratch, NB_ERR_ARG, "nb_snr_mask_cells: scratch required when trimPix > 0");
@@ -1615,9 +1619,9 @@ int nb_snr_mask_cells(int prec, void* map, const void* wmed, const double* table
     for (int i = 0; i <= nx; ++i) ch.x[i] = xChunks[i];
     PaintArgs pa = {wmed, table, edges, ny, nx, overlapPix, numBins};
     if (prec == NB_PREC_F64)
-        return snr_mask_t<double>(map, rmsOut, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st, &pa, &ch);
+        return snr_mask_t<double>(map, rmsOut, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st, zeroFlags, &pa, &ch);
     if (prec == NB_PREC_F32)
-        return snr_mask_t<float>(map, rmsOut, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st, &pa, &ch);
+        return snr_mask_t<float>(map, rmsOut, psMask, surveyMask, nImg, S, H, W, trimPix, apodPix, realSpace, sn, maskOut, scratch, st, zeroFlags, &pa, &ch);
     nb_set_error("nb_snr_mask_cells: bad precision %d", prec);
     return NB_ERR_ARG;
 }

@@ -138,6 +138,7 @@ template <typename T> struct SC2RParams {
     const unsigned char* mask;
     int maskDiv;
     const T* zeroRef;
+    int* zeroFlag;      // [images] or null: set to 1 for an image with a pixel where out + (1 - mask) == 0 (what K7's edge filter looks for)
 };
 
 template <typename T, class PL, int NT, int G>
@@ -235,6 +236,7 @@ sfft_rows_inv_kernel(const typename V2<T>::type* __restrict__ in, T* out, int H,
             T f = ep.scale;
             if (ep.norm) f *= (T)ep.norm[imgOf[rr]];
             T* orow = out + (size_t)row * W;
+            bool hasZero = false;
 #pragma unroll
             for (int i = 0; i < SL::IT; ++i) {
                 const int j = t + i * NT;
@@ -243,11 +245,16 @@ sfft_rows_inv_kernel(const typename V2<T>::type* __restrict__ in, T* out, int H,
                 for (int r = 0; r < SL::R; ++r) {
                     const int q = i * SL::R + r;
                     T v = (rr == 0 ? yr[q] : yi[q]) * f;
-                    if (ep.mask) v *= (T)((mpack[rr][q >> 2] >> (8 * (q & 3))) & 0xffu);
+                    if (ep.mask) {
+                        const unsigned mb = (mpack[rr][q >> 2] >> (8 * (q & 3))) & 0xffu;
+                        v *= (T)mb;
+                        hasZero |= (v + (T)(1 - (int)mb)) == (T)0;
+                    }
                     if ((zbits[rr] >> q) & 1u) v = 0;
                     orow[j + r * SL::NB] = v;
                 }
             }
+            if (hasZero && ep.mask && ep.zeroFlag) ep.zeroFlag[imgOf[rr]] = 1;
         }
     });
 }
@@ -417,6 +424,7 @@ sfft_rows_inv_tma_kernel(const typename V2<T>::type* __restrict__ in, T* out, in
                 T f = ep.scale;
                 if (ep.norm) f *= (T)ep.norm[(unsigned)row / H32];
                 T* orow = out + (size_t)row * W;
+                bool hasZero = false;
                 const unsigned char* brow = nullptr;
                 if (EP == 1) {
                     if (v1) brow = sb + rr * W;
@@ -434,11 +442,16 @@ sfft_rows_inv_tma_kernel(const typename V2<T>::type* __restrict__ in, T* out, in
                         const int q = i * SL::R + r;
                         const int n = j + r * SL::NB;
                         T v = (rr == 0 ? yr[q] : yi[q]) * f;
-                        if (EP == 1) v *= (T)brow[n];
+                        if (EP == 1) {
+                            const unsigned mb = brow[n];
+                            v *= (T)mb;
+                            hasZero |= (v + (T)(1 - (int)mb)) == (T)0;
+                        }
                         if (EP == 2 && ((zbits[rr] >> q) & 1u)) v = 0;
                         orow[n] = v;
                     }
                 }
+                if (EP == 1 && hasZero && ep.zeroFlag) ep.zeroFlag[(unsigned)row / H32] = 1;
             }
         });
         __syncthreads();      // the exchange buffer is free for the next tile's first scatter
@@ -681,11 +694,11 @@ int nb_sfft_rows_fwd(int prec, const void* in, void* out, int B, int H, int W, i
 }
 
 int nb_sfft_rows_inv(int prec, const void* in, void* out, int B, int H, int W, double scale, const double* norm, const unsigned char* mask,
-                     int maskDiv, const void* zeroRef, cudaStream_t st) {
+                     int maskDiv, const void* zeroRef, int* zeroFlag, cudaStream_t st) {
     if (prec == NB_PREC_F64) {
-        SC2RParams<double> ep = {scale, norm, mask, maskDiv < 1 ? 1 : maskDiv, (const double*)zeroRef};
+        SC2RParams<double> ep = {scale, norm, mask, maskDiv < 1 ? 1 : maskDiv, (const double*)zeroRef, zeroFlag};
         return sfft_rows_inv_t<double>((const double2*)in, (double*)out, B, H, W, ep, st);
     }
-    SC2RParams<float> ep = {(float)scale, norm, mask, maskDiv < 1 ? 1 : maskDiv, (const float*)zeroRef};
+    SC2RParams<float> ep = {(float)scale, norm, mask, maskDiv < 1 ? 1 : maskDiv, (const float*)zeroRef, zeroFlag};
     return sfft_rows_inv_t<float>((const float2*)in, (float*)out, B, H, W, ep, st);
 }

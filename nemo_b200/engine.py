@@ -182,29 +182,35 @@ def buildFourierFilters(ops, fmapsNoise, templUnit, templNorm, w, outputUnits, c
     return {'filtH': filtH, 'filtFull': filtFull, 'signalNorm': signalNorm, 'fRel': fRel, 'S': S}
 
 
-def applyFourierFilters(ops, fmaps, filtH, S, signalNorm, psMask, bckSubSigmas=None, W=None):
+def applyFourierFilters(ops, fmaps, filtH, S, signalNorm, psMask, bckSubSigmas=None, W=None, zeroFlags=False):
     """MatchedFilter.applyFilter (filters.py:824-859) for every (tile, scale), times psMask (:717).  W: the map width when it
-    is odd (or always); by default that of psMask, else the even width that goes with the half spectra."""
+    is odd (or always); by default that of psMask, else the even width that goes with the half spectra.  zeroFlags=True: returns
+    (maps, flags): per image, 0 when the map has no pixel for the edge filter of noiseSNAndMasks to find (None when not known)."""
     if bckSubSigmas is None:
-        return ops.apply_filter(fmaps, filtH, S, norm=signalNorm, mask=psMask, W=W)
+        if zeroFlags and psMask is not None:
+            return ops.apply_filter(fmaps, filtH, S, norm=signalNorm, mask=psMask, W=W, zeroFlags=True)
+        m = ops.apply_filter(fmaps, filtH, S, norm=signalNorm, mask=psMask, W=W)
+        return (m, None) if zeroFlags else m
+    if zeroFlags:
+        return applyFourierFilters(ops, fmaps, filtH, S, signalNorm, psMask, bckSubSigmas=bckSubSigmas, W=W), None
     m = ops.apply_filter(fmaps, filtH, S, W=W if W is not None else (int(psMask.shape[-1]) if psMask is not None else None))
     m = ops.gauss_filter(m, bckSubSigmas[0], bckSubSigmas[1], subtract=True)
     maskFull = psMask if S == 1 or psMask is None else psMask.repeat_interleave(S, dim=0)
     return ops.scale_mask(m, norm=signalNorm, mask=maskFull)
 
 
-def noiseSNAndMasks(ops, filtered, wmed, psMask, surveyMask, S, grid, trimPix, apodPix, realSpace, wantRMS=True):
+def noiseSNAndMasks(ops, filtered, wmed, psMask, surveyMask, S, grid, trimPix, apodPix, realSpace, wantRMS=True, zeroFlags=None):
     """makeNoiseMap + S/N + edge trim + masks (filters.py:719-758).  `filtered` is overwritten with `data`.
     Returns (data, SNMap, surveyMaskOut u8, RMSMap, cellTable, cellEdges); RMSMap is None with wantRMS=False on the grid path
     (the map is then never materialised: the S/N map takes its RMS straight from the cell table)."""
     if isinstance(grid[0], str) and grid[0] == 'smart':
         rms, table, edges = ops.smart_rms(filtered, wmed, S, grid[1])
-        data, sn, maskOut, rms = ops.snr_mask(filtered, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace)
+        data, sn, maskOut, rms = ops.snr_mask(filtered, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace, zeroFlags=zeroFlags)
         return data, sn, maskOut, rms, table, edges
     yChunks, xChunks, overlapPix, numBins, estimator = grid
     _, table, edges = ops.cell_rms(filtered, wmed, S, yChunks, xChunks, overlapPix, numBins, estimator=estimator, paint=False)
     data, sn, maskOut, rms = ops.snr_mask_cells(filtered, wmed, table, edges, yChunks, xChunks, overlapPix, numBins, psMask, surveyMask,
-                                                S, trimPix, apodPix, realSpace, wantRMS=wantRMS)
+                                                S, trimPix, apodPix, realSpace, wantRMS=wantRMS, zeroFlags=zeroFlags)
     return data, sn, maskOut, rms, table, edges
 
 

@@ -326,8 +326,8 @@ class MatchedFilter(MapFilter):
             self.params['saveFilter'] = False
             self.params['savePlots'] = False
 
-        filteredMap = engine.applyFourierFilters(ops, fMapsToFilter, self._filtHT, 1, self._signalNormT, dev['psMask'],
-                                                 bckSubSigmas=self._bckSubSigmas(), W=self.shape[1])
+        filteredMap, zeroFlags = engine.applyFourierFilters(ops, fMapsToFilter, self._filtHT, 1, self._signalNormT, dev['psMask'],
+                                                            bckSubSigmas=self._bckSubSigmas(), W=self.shape[1], zeroFlags=True)
         del fMapsToFilter
 
         if self.params['outputUnits'] == 'yc':
@@ -345,7 +345,8 @@ class MatchedFilter(MapFilter):
         grid = engine.noiseGrid(self.shape, self.params['noiseParams'], pixDeg)
         trimPix = engine.trimSizePix(self.params, pixDeg, realSpace=False)
         data, sn, maskOut, rms, table, edges = engine.noiseSNAndMasks(ops, filteredMap, dev['wmed'], dev['psMask'],
-                                                                      dev['surveyMask'], 1, grid, trimPix, self.apodPix, False)
+                                                                      dev['surveyMask'], 1, grid, trimPix, self.apodPix, False,
+                                                                      zeroFlags=zeroFlags)
         self.noiseTable = (table, edges)
         self.RMSMap = DeviceArray(rms[0])
 

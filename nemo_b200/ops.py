@@ -97,9 +97,10 @@ class Ops(object):
         self.launches += 2
         return out
 
-    def apply_filter(self, fmaps, filtH, S, scale=1.0, norm=None, mask=None, out=None, scratch=None, perScale=False, W=None):
+    def apply_filter(self, fmaps, filtH, S, scale=1.0, norm=None, mask=None, out=None, scratch=None, perScale=False, W=None, zeroFlags=False):
         """out[o] = scale * norm[o] * mask[o // S] * Re(ifft2(sum_f fmaps[o // S, f] * filt[o, f])); with perScale the
-        spectra are those of S templates shared by every tile, fmaps[o % S]."""
+        spectra are those of S templates shared by every tile, fmaps[o % S].  zeroFlags=True: returns (out, flags) with flags [nOut]
+        int32 = 0 for the images in which out + (1 - mask) is nowhere exactly zero (see nb_apply_filter; for snr_mask*)."""
         self._check(fmaps, self.cdtype, 'fmaps')
         self._check(filtH, self.dtype, 'filtH')
         nT, F, H, Wc = fmaps.shape
@@ -118,10 +119,11 @@ class Ops(object):
             self._check(norm, self.torch.float64, 'norm')
         if mask is not None:
             self._check(mask, self.torch.uint8, 'mask')
+        flags = self.empty((nOut,), self.torch.int32) if zeroFlags else None
         _lib.call('nb_apply_filter', self.prec, _ptr(fmaps), _ptr(filtH), _ptr(scratch), _ptr(out), nOut, int(S), 1 if perScale else 0, F, H, W,
-                  float(scale), _ptr(norm), _ptr(mask), self._stream())
+                  float(scale), _ptr(norm), _ptr(mask), _ptr(flags), self._stream())
         self.launches += 2
-        return out
+        return (out, flags) if zeroFlags else out
 
     def window_tables(self, H, W, power):
         """(wy, wx) of enmap.apply_window raised to `power`, on the device (wx on the half plane); cached."""
@@ -367,7 +369,7 @@ class Ops(object):
         self.launches += 4
         return toRemove
 
-    def snr_mask(self, maps, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace):
+    def snr_mask(self, maps, rms, psMask, surveyMask, S, trimPix, apodPix, realSpace, zeroFlags=None):
         """In place on maps / rms; returns (data, SNMap, surveyMaskOut u8, rms)."""
         self._check(maps, self.dtype, 'maps')
         self._check(rms, self.dtype, 'rms')
@@ -377,13 +379,15 @@ class Ops(object):
         sn = self.empty((nImg, H, W))
         maskOut = self.empty((nImg, H, W), self.torch.uint8)
         scratch = self.empty((nImg, H, W), self.torch.uint8) if trimPix > 0 else None
+        if zeroFlags is not None:
+            self._check(zeroFlags, self.torch.int32, 'zeroFlags')
         _lib.call('nb_snr_mask', self.prec, _ptr(maps), _ptr(rms), _ptr(psMask), _ptr(surveyMask), nImg, int(S), H, W, int(trimPix),
-                  int(apodPix), 1 if realSpace else 0, _ptr(sn), _ptr(maskOut), _ptr(scratch), self._stream())
+                  int(apodPix), 1 if realSpace else 0, _ptr(sn), _ptr(maskOut), _ptr(scratch), _ptr(zeroFlags), self._stream())
         self.launches += 2 if trimPix > 0 else 1
         return maps, sn, maskOut, rms
 
     def snr_mask_cells(self, maps, wmed, table, edges, yChunks, xChunks, overlapPix, numBins, psMask, surveyMask, S, trimPix, apodPix,
-                       realSpace, wantRMS=True):
+                       realSpace, wantRMS=True, zeroFlags=None):
         """snr_mask with the RMS taken straight from the cell tables (painting fused); returns (data, SNMap, mask u8, RMS map);
         the RMS map is None with wantRMS=False (8 bytes per pixel less to write when nothing reads it)."""
         self._check(maps, self.dtype, 'maps')
@@ -400,7 +404,7 @@ class Ops(object):
         xc = (ctypes.c_int * (nx + 1))(*[int(v) for v in xChunks])
         _lib.call('nb_snr_mask_cells', self.prec, _ptr(maps), _ptr(wmed), _ptr(table), _ptr(edges), yc, ny, xc, nx, int(overlapPix),
                   int(numBins), _ptr(psMask), _ptr(surveyMask), nImg, int(S), H, W, int(trimPix), int(apodPix), 1 if realSpace else 0,
-                  _ptr(sn), _ptr(rms), _ptr(maskOut), _ptr(scratch), self._stream())
+                  _ptr(sn), _ptr(rms), _ptr(maskOut), _ptr(scratch), _ptr(zeroFlags), self._stream())
         self.launches += 2 if trimPix > 0 else 1
         return maps, sn, maskOut, rms
 

@@ -292,7 +292,9 @@ def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=
     else:
         res = {'filtH': cache['filtH'], 'signalNorm': cache['signalNorm'], 'fRel': cache.get('fRel')}
     # K4: apply, times the point-source mask
-    filtered = engine.applyFourierFilters(ops, fmaps, res['filtH'], S, res['signalNorm'], dev['psMask'], bckSubSigmas=bck, W=batch.W)
+    # (zeroFlags: which images have a pixel for K7's edge filter to find -- a by-product of the last row pass; nearly always none)
+    filtered, zeroFlags = engine.applyFourierFilters(ops, fmaps, res['filtH'], S, res['signalNorm'], dev['psMask'], bckSubSigmas=bck, W=batch.W,
+                                                     zeroFlags=True)
     del fmaps
     trimPix = engine.trimSizePix(params0, pixDeg, realSpace=False)
     photScale = None
@@ -304,7 +306,7 @@ def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=
         # K7 with the cached noise: masks and `data` as usual, S/N = data / RMS(photFilter) where RMS > 0, else data
         rmsPhot = cache['RMSMap'].reshape(nT, S, H, W)[:, photScale].contiguous()
         rms = rmsPhot.repeat_interleave(S, dim=0) if S > 1 else rmsPhot.clone()
-        data, _, maskOut, rms = ops.snr_mask(filtered, rms, dev['psMask'], dev['surveyMask'], S, trimPix, 20, False)
+        data, _, maskOut, rms = ops.snr_mask(filtered, rms, dev['psMask'], dev['surveyMask'], S, trimPix, 20, False, zeroFlags=zeroFlags)
         sn = ops.snr_from_rms(data, rmsPhot, S)
         table = edges = None
     else:
@@ -313,7 +315,7 @@ def startTileBatch(ops, batch, filtersList, templates, parDict, undoPixelWindow=
         # (wantRMS=False: job['RMSMap'] is None -- nothing downstream reads the painted map unless noise tables, filter caches or
         # RMS files were asked for)
         data, sn, maskOut, rms, table, edges = engine.noiseSNAndMasks(ops, filtered, dev['wmed'], dev['psMask'], dev['surveyMask'],
-                                                                      S, grid, trimPix, 20, False, wantRMS=wantRMS or rmsTables)
+                                                                      S, grid, trimPix, 20, False, wantRMS=wantRMS or rmsTables, zeroFlags=zeroFlags)
     # noise level versus area (completeness.getRMSTab) of every image, while its RMS map is on the device
     rmsTabJob = None
     if rmsTables and table is not None:

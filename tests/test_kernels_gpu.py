@@ -503,6 +503,40 @@ def test_snr_mask_f64(ops64, report, trim, realSpace):
     report("snr_mask_f64", trim=trim, realSpace=realSpace, ok=1)
 
 
+@pytest.mark.parametrize("shape", [(300, 420), (128, 256)])
+def test_zero_flags_of_apply_filter_feed_the_edge_filter(ops64, report, shape):
+    """nb_apply_filter reports, per image, whether map + (1 - psMask) has an exactly zero pixel (what the rank filter of K7 looks
+    for, filters.py:730); nb_snr_mask* skips the filter for images without one.  Three images: random (no zero: flag 0 on the
+    compile-time-plan path), all-zero spectra (every pixel zero: flag 1), random with a point-source hole (the hole is filled back
+    in, flag 0).  The outputs with the flags must equal those without, bit for bit; sides without a compile-time plan answer 1
+    (unknown) for every image."""
+    H, W = shape
+    rng = np.random.default_rng(21)
+    t = ops64.torch
+    maps = rng.standard_normal((3, 1, H, W))
+    maps[1] = 0
+    ps = np.ones((3, H, W), dtype=np.uint8)
+    ps[2, 40:50, 60:80] = 0
+    survey = np.ones((3, H, W), dtype=np.uint8)
+    fm = ops64.rfft2(ops64.to_device(maps.reshape(3, H, W))).reshape(3, 1, H, W // 2 + 1)
+    filt = ops64.fold_filter(ops64.to_device(rng.random((3, 1, H, W)) + 0.5))
+    psT, svT = ops64.to_device(ps, t.uint8), ops64.to_device(survey, t.uint8)
+    out, flags = ops64.apply_filter(fm, filt, 1, mask=psT, W=W, zeroFlags=True)
+    ref = ops64.apply_filter(fm, filt, 1, mask=psT, W=W)
+    assert np.array_equal(_np(out), _np(ref))
+    want = [int(np.any(_np(ref)[b] + (1 - ps[b].astype(float)) == 0)) for b in range(3)]
+    assert want == [0, 1, 0]
+    planned = W in (300, 320, 420, 840, 1440)      # the row pass decides
+    assert [int(v != 0) for v in _np(flags)] == (want if planned else [1, 1, 1])
+    rms = ops64.to_device(np.abs(rng.standard_normal((3, H, W))) + 0.1)
+    a = ops64.snr_mask(out.clone(), rms.clone(), psT, svT, 1, 48, 20, False, zeroFlags=flags)
+    b = ops64.snr_mask(ref.clone(), rms.clone(), psT, svT, 1, 48, 20, False)
+    for x, y in zip(a, b):
+        assert np.array_equal(_np(x), _np(y))
+    assert not _np(a[2])[1].any() and _np(a[2])[0].any()      # the all-zero image is trimmed away entirely, the random one is not
+    report("zero_flags", shape=shape, flags=[int(v) for v in _np(flags)])
+
+
 # ----------------------------------------------------------------------------------------------------------
 NONPOW2 = [(96, 100), (300, 420), (420, 300), (257, 1024), (1024, 330), (840, 1440), (1440, 840), (256, 320), (320, 300), (1031, 1032),
            (1031, 1033), (301, 421), (128, 65), (840, 1441)]      # odd widths: Wc = (W + 1) / 2, no Nyquist column
