@@ -125,14 +125,16 @@ def cpuBaseline(kind, cores=None, steps=1, warmup=0):
 
 
 # ------------------------------------------------------------------------------------------------------
-def algorithmicBytes(nT, F, S, H, W, E, rings=True, yc=True, templateSpectraCached=True, separableWindow=False):
+def algorithmicBytes(nT, F, S, H, W, E, rings=True, yc=True, templateSpectraCached=True, separableWindow=False, edgeFilterRuns=True):
     """Algorithmic HBM bytes per step of every kernel of the batched Fourier path: own inputs read once + own outputs
     written once (SURVEY.md 8d / DESIGN.md), E = bytes per real (8 for f64, 4 for f32), complex = 2E.  Keyed by the names the
     library's event timers report; kernels that serve several passes are charged the sum of those passes.
     templateSpectraCached: the transforms of the signal templates are made once per tile geometry (pipelines.templateSpectraOf),
     not per batch, so no FFT pass of a step is charged for them.
     separableWindow: the pixel-window undo runs as a column pass on pairs of real columns and one row kernel (real rows in, real
-    rows out, the zero pattern of the old data read once) instead of forward rows / column window / inverse rows."""
+    rows out, the zero pattern of the old data read once) instead of forward rows / column window / inverse rows.
+    edgeFilterRuns=False: no image had a zero for K7's edge filter to find (nb_apply_filter's zeroFlags), so its row pass did not run
+    and its column pass reads no row flags."""
     N, Nc = H * W, H * (W // 2 + 1)
     P = F * (F + 1) // 2
     nOut = nT * S
@@ -171,8 +173,9 @@ def algorithmicBytes(nT, F, S, H, W, E, rings=True, yc=True, templateSpectraCach
     b['zone_moments_kernel'] = nOut * N * E + nT * N * E     # one-bin K6: map once + the tile's median weights; then the map once more
     b['cell_clip_kernel'] = nOut * N * E
     b['edge_rows_kernel'] = nOut * (N * E + 2 * N)
-    b['edge_cols_final_kernel'] = nOut * (2 * N * E + 3 * N + 3 * N * E + N)
-    b['edge_cols_final_paint_kernel'] = nOut * (2 * N * E + 3 * N + 2 * N * E + N)   # map, median weights, masks in; data, S/N, mask out (the RMS map is not written unless asked for)
+    nByteIn = 3 if edgeFilterRuns else 2      # point-source mask, survey mask, (row flags of the edge filter)
+    b['edge_cols_final_kernel'] = nOut * (2 * N * E + nByteIn * N + 3 * N * E + N)
+    b['edge_cols_final_paint_kernel'] = nOut * (2 * N * E + nByteIn * N + 2 * N * E + N)   # map, median weights, masks in; data, S/N, mask out (the RMS map is not written unless asked for)
     b['detect_scan_kernel'] = b['detect_scan_multi_kernel'] = nOut * (N * E)         # S/N read once for both thresholds; the rest is sparse
     return b
 
@@ -448,7 +451,7 @@ def main():
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peakSrc = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
     algo = algorithmicBytes(nT, F, S, H, W, E, rings=parDict['removeRings'], yc=(outputUnits == 'yc'),
-                            separableWindow='sfft_rows_window_kernel' in prof)
+                            separableWindow='sfft_rows_window_kernel' in prof, edgeFilterRuns=prof.get('edge_rows_kernel', (0, 0.0))[1] / max(prof.get('edge_rows_kernel', (1, 0.0))[0], 1) > 0.1)      # its CTAs return at once when no image has a zero
     table = []
     totalKernelMs = sum(ms for _, ms in prof.values()) / profSteps
     for name, (cnt, ms) in prof.items():

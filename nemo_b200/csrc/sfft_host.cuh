@@ -21,9 +21,65 @@
 #define SFFT_COL_1440 10, 12, 12, 144
 #define SFFT_COL_840 7, 8, 15, 60
 #endif
+// row plan of the 1440-wide DR5 tile (-DSFFT_ROW_VARIANT=n for experiments): the scatter of a plan's FIRST pass writes with a
+// stride of R values between lanes, a 2-way (R = 10) or 4-way (R = 12) bank conflict for doubles unless R is odd
+#ifndef SFFT_ROW_VARIANT
+#define SFFT_ROW_VARIANT 0
+#endif
+#if SFFT_ROW_VARIANT == 1
+#define SFFT_ROW_1440 15, 8, 12, 120
+#elif SFFT_ROW_VARIANT == 2
+#define SFFT_ROW_1440 9, 16, 10, 160
+#elif SFFT_ROW_VARIANT == 3
+#define SFFT_ROW_1440 12, 10, 12, 144
+#elif SFFT_ROW_VARIANT == 4
+#define SFFT_ROW_1440 9, 10, 16, 160
+#else
+#define SFFT_ROW_1440 10, 12, 12, 144
+#endif
+// the inverse row pass runs its plan in one direction only, so its first radix can be odd (15: conflict-free scatter) at 120
+// threads per row pair: 1.40 -> 1.09 ms per two launches of 128 images of 840 x 1440 (the same plan spills in the window kernel,
+// whose reversed plan would start with radix 12 anyway: 1.54 -> 2.07 ms; 9 x 16 x 10 and 12 x 10 x 12 gain nothing)
+#ifndef SFFT_ROW_INV_VARIANT
+#define SFFT_ROW_INV_VARIANT 1
+#endif
+#if SFFT_ROW_INV_VARIANT == 1
+#define SFFT_ROW_INV_1440 15, 8, 12, 120
+#elif SFFT_ROW_INV_VARIANT == 2
+#define SFFT_ROW_INV_1440 15, 12, 8, 120
+#elif SFFT_ROW_INV_VARIANT == 3
+#define SFFT_ROW_INV_1440 15, 8, 12, 180
+#elif SFFT_ROW_INV_VARIANT == 4
+#define SFFT_ROW_INV_1440 15, 6, 16, 120
+#else
+#define SFFT_ROW_INV_1440 SFFT_ROW_1440
+#endif
+#ifndef SFFT_ROW_WIN_VARIANT
+#define SFFT_ROW_WIN_VARIANT 0
+#endif
+#if SFFT_ROW_WIN_VARIANT == 1
+#define SFFT_ROW_WIN_1440 15, 8, 12, 120
+#elif SFFT_ROW_WIN_VARIANT == 2
+#define SFFT_ROW_WIN_1440 12, 8, 15, 120
+#else
+#define SFFT_ROW_WIN_1440 SFFT_ROW_1440
+#endif
 #define SFFT_APPLY(X, ...) X(__VA_ARGS__)
+#define SFFT_APPLY2(X, N, A, B) SFFT_APPLY(X, N, A, B)
+#define SFFT_FOR_SIZES_WIN(X) \
+    SFFT_APPLY2(X, 1440, SFFT_ROW_WIN_1440,  SFFT_COL_1440) \
+    SFFT_APPLY(X, 840, 7, 10, 12, 120,    SFFT_COL_840)  \
+    X(420, 5, 7, 12, 84,      5, 7, 12, 42)    \
+    X(320, 5, 8, 8, 64,       5, 8, 8, 32)     \
+    X(300, 5, 6, 10, 60,      5, 6, 10, 30)
+#define SFFT_FOR_SIZES_INV(X) \
+    SFFT_APPLY2(X, 1440, SFFT_ROW_INV_1440,  SFFT_COL_1440) \
+    SFFT_APPLY(X, 840, 7, 10, 12, 120,    SFFT_COL_840)  \
+    X(420, 5, 7, 12, 84,      5, 7, 12, 42)    \
+    X(320, 5, 8, 8, 64,       5, 8, 8, 32)     \
+    X(300, 5, 6, 10, 60,      5, 6, 10, 30)
 #define SFFT_FOR_SIZES(X) \
-    SFFT_APPLY(X, 1440, 10, 12, 12, 144,  SFFT_COL_1440) \
+    SFFT_APPLY2(X, 1440, SFFT_ROW_1440,  SFFT_COL_1440) \
     SFFT_APPLY(X, 840, 7, 10, 12, 120,    SFFT_COL_840)  \
     X(420, 5, 7, 12, 84,      5, 7, 12, 42)    \
     X(320, 5, 8, 8, 64,       5, 8, 8, 32)     \

@@ -552,7 +552,7 @@ static int sfft_rows_inv_t(const typename V2<T>::type* in, T* out, int B, int H,
         NB_CHECK_LAUNCH();                                                                                                \
         return NB_OK;                                                                                                     \
     }
-    SFFT_FOR_SIZES(SFFT_CASE)
+    SFFT_FOR_SIZES_INV(SFFT_CASE)
 #undef SFFT_CASE
     nb_set_error("sfft: width %d has no compile-time plan", W);
     return NB_ERR_UNSUPPORTED;
@@ -677,7 +677,7 @@ static int sfft_rows_window_t(const T* in, T* out, int B, int H, int W, const T*
         NB_CHECK_LAUNCH();                                                                                                \
         return NB_OK;                                                                                                     \
     }
-    SFFT_FOR_SIZES(SFFT_CASE)
+    SFFT_FOR_SIZES_WIN(SFFT_CASE)
 #undef SFFT_CASE
     nb_set_error("sfft: width %d has no compile-time plan", W);
     return NB_ERR_UNSUPPORTED;
