@@ -172,7 +172,8 @@ def algorithmicBytes(nT, F, S, H, W, E, rings=True, yc=True, templateSpectraCach
         b[k6] = nOut * N * E + nT * N * E      # every image's map; the median weights of its tile
     b['zone_moments_kernel'] = nOut * N * E + nT * N * E     # one-bin K6: map once + the tile's median weights; then the map once more
     b['cell_clip_kernel'] = nOut * N * E
-    b['edge_rows_kernel'] = nOut * (N * E + 2 * N)
+    if edgeFilterRuns:
+        b['edge_rows_kernel'] = nOut * (N * E + 2 * N)
     nByteIn = 3 if edgeFilterRuns else 2      # point-source mask, survey mask, (row flags of the edge filter)
     b['edge_cols_final_kernel'] = nOut * (2 * N * E + nByteIn * N + 3 * N * E + N)
     b['edge_cols_final_paint_kernel'] = nOut * (2 * N * E + nByteIn * N + 2 * N * E + N)   # map, median weights, masks in; data, S/N, mask out (the RMS map is not written unless asked for)

@@ -252,6 +252,45 @@ __global__ void moments_final_kernel(double* __restrict__ table, long long nRows
     if (t[6] == INFINITY) t[6] = -1.0;  // label 0 has no tracked first pixel
 }
 
+// The sparse detector knows an image's label count before it takes the moments, so only the rows it will fill are prepared and
+// finished (the tables have room for 8192 labels per image: 67 MB per 128 images, of which a step's images use a few dozen rows
+// each).  Row 0 (background, accumulated by the dense scan) is prepared before the scan; rows 1 .. min(nLabels, cap) after the
+// ranking.  Rows beyond an image's count are never read (the host cuts at the count, nb_ring_flags takes the counts).
+__global__ void moments_init_row0_kernel(double* __restrict__ table, int maxLabels, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double* t = table + (size_t)b * (maxLabels + 1) * 8;
+    t[0] = t[1] = t[2] = t[3] = 0.0;
+    reinterpret_cast<unsigned long long*>(t)[4] = 0ULL;
+    t[5] = INFINITY;
+    t[6] = INFINITY;
+    t[7] = 0.0;
+}
+
+template <bool FINAL>
+__global__ void moments_rows_kernel(double* __restrict__ table, int maxLabels, const int* __restrict__ nLabels) {
+    const int b = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x + (FINAL ? 0 : 1);
+    if (r > min(nLabels[b], maxLabels)) return;
+    double* t = table + ((size_t)b * (maxLabels + 1) + r) * 8;
+    if (!FINAL) {
+        t[0] = t[1] = t[2] = t[3] = 0.0;
+        reinterpret_cast<unsigned long long*>(t)[4] = 0ULL;
+        t[5] = INFINITY;
+        t[6] = INFINITY;
+        t[7] = 0.0;
+    } else {
+        const unsigned long long e = reinterpret_cast<unsigned long long*>(t)[4];
+        t[4] = (e == 0ULL) ? -INFINITY : dec_ordered(e);
+        if (t[3] == 0.0) {
+            t[5] = -1.0;
+            t[6] = -1.0;
+        }
+        if (t[5] == INFINITY) t[5] = -1.0;
+        if (t[6] == INFINITY) t[6] = -1.0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // K11.  One warp per evaluation point.
 template <typename T>
@@ -809,7 +848,8 @@ static int find_objects_t(const T* map, double thr, double ringThr, int haveRing
         const long long nRows = (long long)B * (p[q].maxLabels + 1);
         { NB_PROF_BEGIN(st); detect_reset_kernel<<<(B + 255) / 256, 256, 0, st>>>(p[q].sc.fgCount, p[q].sc.rootCount, p[q].status, B); NB_PROF_END("detect_reset_kernel", st); }
         NB_CHECK_LAUNCH();
-        { NB_PROF_BEGIN(st); moments_init_kernel<<<(unsigned)((nRows + 255) / 256), 256, 0, st>>>(p[q].table, nRows); NB_PROF_END("moments_init_kernel", st); }
+        (void)nRows;
+        { NB_PROF_BEGIN(st); moments_init_row0_kernel<<<(B + 255) / 256, 256, 0, st>>>(p[q].table, p[q].maxLabels, B); NB_PROF_END("moments_init_kernel", st); }
         NB_CHECK_LAUNCH();
     }
     dim3 gridDense((HW + DT_THREADS * DT_ITEMS - 1) / (DT_THREADS * DT_ITEMS), B);
@@ -828,6 +868,8 @@ static int find_objects_t(const T* map, double thr, double ringThr, int haveRing
         NB_CHECK_LAUNCH();
         { NB_PROF_BEGIN(st); detect_rank_kernel<<<B, 1024, 0, st>>>(p[q].sc, nl, HW); NB_PROF_END("detect_rank_kernel", st); }
         NB_CHECK_LAUNCH();
+        { NB_PROF_BEGIN(st); moments_rows_kernel<false><<<dim3((p[q].maxLabels + 255) / 256, B), 256, 0, st>>>(p[q].table, p[q].maxLabels, nl); NB_PROF_END("moments_init_kernel", st); }
+        NB_CHECK_LAUNCH();
         { NB_PROF_BEGIN(st); detect_moments_kernel<T><<<gridSparse, 256, 0, st>>>(map, sign, p[q].sc, (q == 0) ? labels : nullptr, p[q].table, H, W, p[q].maxLabels); NB_PROF_END("detect_moments_kernel", st); }
         NB_CHECK_LAUNCH();
     }
@@ -836,8 +878,7 @@ static int find_objects_t(const T* map, double thr, double ringThr, int haveRing
         NB_CHECK_LAUNCH();
     }
     for (int q = 0; q < NP; ++q) {
-        const long long nRows = (long long)B * (p[q].maxLabels + 1);
-        { NB_PROF_BEGIN(st); moments_final_kernel<<<(unsigned)((nRows + 255) / 256), 256, 0, st>>>(p[q].table, nRows); NB_PROF_END("moments_final_kernel", st); }
+        { NB_PROF_BEGIN(st); moments_rows_kernel<true><<<dim3((p[q].maxLabels + 1 + 255) / 256, B), 256, 0, st>>>(p[q].table, p[q].maxLabels, (q == 0) ? nLabels : ringN); NB_PROF_END("moments_final_kernel", st); }
         NB_CHECK_LAUNCH();
     }
     if (haveRing) {

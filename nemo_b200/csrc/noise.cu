@@ -1221,6 +1221,7 @@ __global__ void __launch_bounds__(256) paint_rms_kernel(const T* __restrict__ wm
 }
 
 // ------------------------------------------------------------------------------------------------------
+#define ER_ROWS 8
 // K7.  rank_filter(a, 0, size=(T,T)) > 0  <=>  no zero of a inside the T x T window, whose offsets along each axis are
 // [-T/2, T-1-T/2] with scipy's reflect boundary.  Done separably: row pass with a prefix sum, then a sliding column sum
 // fused with the final elementwise step.
@@ -1230,8 +1231,11 @@ __global__ void __launch_bounds__(256) edge_rows_kernel(const T* __restrict__ ma
                                                         const int* __restrict__ zeroFlags) {
     extern __shared__ int s_pre[];  // W + 1 prefix counts of zeros
     __shared__ int s_part[256];
-    const int y = blockIdx.x, img = blockIdx.y;
+    const int img = blockIdx.y;
     if (zeroFlags && zeroFlags[img] == 0) return;      // the kernel that wrote this image saw no zero: the column pass will not read rowAny
+    // (ER_ROWS rows per CTA: a hundred thousand one-row CTAs that only return still cost 54 us per launch)
+    for (int y = blockIdx.x * ER_ROWS; y < min((int)(blockIdx.x + 1) * ER_ROWS, H); ++y) {
+    __syncthreads();      // the previous row's prefix counts have been read
     const T* m = map + ((size_t)img * H + y) * W;
     const unsigned char* p = ps + ((size_t)(img / S) * H + y) * W;
     const int per = (W + blockDim.x - 1) / blockDim.x;
@@ -1277,6 +1281,7 @@ __global__ void __launch_bounds__(256) edge_rows_kernel(const T* __restrict__ ma
         else if (b < 0) cnt = ext(-a) - ext(-b - 1);     // position -k mirrors position k - 1
         else cnt = ext(-a) + ext(b + 1);
         out[x] = cnt > 0 ? 1 : 0;
+    }
     }
 }
 
@@ -1499,7 +1504,7 @@ static int snr_mask_t(void* map, void* rms, const unsigned char* ps, const unsig
                       int trim, int apodPix, int realSpace, void* sn, unsigned char* maskOut, unsigned char* scratch, cudaStream_t st,
                       const int* zeroFlags, const PaintArgs* pa = nullptr, const Chunks* chp = nullptr) {
     if (trim > 0) {
-        { NB_PROF_BEGIN(st); edge_rows_kernel<T><<<dim3(H, nImg), 256, sizeof(int) * (W + 1), st>>>((const T*)map, ps, S, H, W, trim, scratch, zeroFlags); NB_PROF_END("edge_rows_kernel", st); }
+        { NB_PROF_BEGIN(st); edge_rows_kernel<T><<<dim3((H + ER_ROWS - 1) / ER_ROWS, nImg), 256, sizeof(int) * (W + 1), st>>>((const T*)map, ps, S, H, W, trim, scratch, zeroFlags); NB_PROF_END("edge_rows_kernel", st); }
         NB_CHECK_LAUNCH();
     }
     const int seg = ec_seg_rows(H);
