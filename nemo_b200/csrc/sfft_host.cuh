@@ -54,8 +54,12 @@
 #else
 #define SFFT_ROW_INV_1440 SFFT_ROW_1440
 #endif
+// the window kernel (forward, multiply, reversed plan backwards) fed by the copy unit wants NO register cap: 15 x 8 x 12 at 120
+// threads, two CTAs per SM, 254 registers, nothing spilled: 1.00 ms per 128 images of 840 x 1440; the same plan at three / four
+// CTAs per SM (168 / 128 registers, 184 / 384 bytes spilled) 1.27 / 2.11 ms; 10 x 12 x 12 at 144 threads 1.39 (two CTAs) and 1.52
+// (three); register-staged 1.55
 #ifndef SFFT_ROW_WIN_VARIANT
-#define SFFT_ROW_WIN_VARIANT 0
+#define SFFT_ROW_WIN_VARIANT 1
 #endif
 #if SFFT_ROW_WIN_VARIANT == 1
 #define SFFT_ROW_WIN_1440 15, 8, 12, 120

@@ -290,7 +290,13 @@ template <typename T, int N, int G> struct SRowTmaCfg {
     static constexpr size_t smem(bool zref, bool mask) { return STAGE + EXCH + (zref ? ZREF : 0) + (mask ? 2 * BYTES : 0) + 16; }
 };
 // resident CTAs per SM asked of ptxas: at most 16 warps, so that no sub-partition holds more than four (128 registers each)
-constexpr int sfft_row_tma_minb(int threads) { return 16 / ((threads + 31) / 32) > 4 ? 4 : (16 / ((threads + 31) / 32) < 1 ? 1 : 16 / ((threads + 31) / 32)); }
+#ifdef SFFT_ROW_TMA_MINB_OVERRIDE
+constexpr int sfft_row_tma_minb(int) { return SFFT_ROW_TMA_MINB_OVERRIDE; }
+constexpr int sfft_row_tma_minb_default(int threads) {
+#else
+constexpr int sfft_row_tma_minb(int threads) {
+#endif
+    return 16 / ((threads + 31) / 32) > 4 ? 4 : (16 / ((threads + 31) / 32) < 1 ? 1 : 16 / ((threads + 31) / 32)); }
 
 // EP: 0 nothing per pixel, 1 byte mask, 2 zero reference
 template <typename T, class PL, int NT, int G, int EP>
@@ -656,6 +662,130 @@ sfft_rows_window_kernel(const T* __restrict__ in, T* out, long long nrows, const
     });
 }
 
+// The same, fed by the copy unit: a persistent CTA per resident slot walks over row pairs; the pair of input rows (adjacent in
+// memory: one cp.async.bulk) and the pair of rows of the old data (for the zero pattern) land in two staging buffers tracked by an
+// mbarrier, and the copy of the next pair is issued as soon as every thread has gathered from them -- under the six passes and the
+// store of the current pair.  In the register-staged kernel the long-scoreboard stall (its exposed loads) was 17 warp-cycles per
+// issued instruction.  Needs an even number of rows (every pair complete).
+#ifndef SFFT_ROWW_TMA_MINB
+#define SFFT_ROWW_TMA_MINB 2
+#endif
+template <typename T, class PL, int NT, bool restoreZeros>
+__global__ void __launch_bounds__(NT, SFFT_ROWW_TMA_MINB)
+sfft_rows_window_tma_kernel(const T* __restrict__ in, T* out, int nrows, int ntiles, const T* __restrict__ wx0, T scale,
+                            const typename V2<T>::type* __restrict__ tw0, const typename V2<T>::type* __restrict__ twRev0) {
+    typedef typename V2<T>::type C2;
+    typedef typename Reversed<PL>::type PR;
+    typedef Stage<PL, NT, 0> S0;
+    typedef typename Last<PL, NT>::S SL;
+    typedef typename Last<PR, NT>::S SRL;
+    constexpr int W = PL::N, LD = W + 2;
+    constexpr uint32_t PAIR_BYTES = 2u * W * (uint32_t)sizeof(T);
+    static_assert(SRL::REGS <= 32, "one bit per register slot");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* stage = reinterpret_cast<T*>(smem_raw);                       // [2][W] input rows
+    T* zref = stage + 2 * W;                                         // [2][W] rows of the old data
+    T* s_re = zref + 2 * W;
+    T* s_im = s_re + LD;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_im + LD);
+    const int t = threadIdx.x;
+    auto issue = [&](int tile) {
+        const size_t off = (size_t)tile * 2 * W;
+        tma::mbar_arrive_expect_tx(bar, restoreZeros ? 2u * PAIR_BYTES : PAIR_BYTES);
+        tma::bulk_g2s(stage, in + off, PAIR_BYTES, bar);
+        if (restoreZeros) tma::bulk_g2s(zref, out + off, PAIR_BYTES, bar);
+    };
+    if (t == 0) {
+        tma::mbar_init(bar, 1);
+        tma::fence_mbar_init();
+    }
+    __syncthreads();
+    int tile = (int)blockIdx.x;
+    if (t == 0 && tile < ntiles) issue(tile);
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (; tile < ntiles; tile += (int)gridDim.x) {
+        // (laundered per iteration: the compiler would otherwise hoist the loop-invariant twiddle loads out of the loop)
+        const C2* tw = tw0;
+        const C2* twRev = twRev0;
+        const T* wx = wx0;
+        asm volatile("" : "+l"(tw));
+        asm volatile("" : "+l"(twRev));
+        asm volatile("" : "+l"(wx));
+        tma::mbar_wait(bar, phase);
+        phase ^= 1u;
+        T xr[S0::REGS], xi[S0::REGS];
+#pragma unroll
+        for (int i = 0; i < S0::IT; ++i) {
+            const int j = t + i * NT;
+#pragma unroll
+            for (int r = 0; r < S0::R; ++r) {
+                T a = 0, b = 0;
+                if (S0::IT * NT == S0::NB || j < S0::NB) {
+                    const int n = j + r * S0::NB;
+                    a = stage[n];
+                    b = stage[W + n];
+                }
+                xr[i * S0::R + r] = a;
+                xi[i * S0::R + r] = b;
+            }
+        }
+        unsigned zb0 = 0u, zb1 = 0u;
+        if (restoreZeros) {
+#pragma unroll
+            for (int i = 0; i < SRL::IT; ++i) {
+                const int j = t + i * NT;
+#pragma unroll
+                for (int r = 0; r < SRL::R; ++r) {
+                    if (SRL::IT * NT == SRL::NB || j < SRL::NB) {
+                        const int n = j + r * SRL::NB;
+                        if (zref[n] == (T)0) zb0 |= 1u << (i * SRL::R + r);
+                        if (zref[W + n] == (T)0) zb1 |= 1u << (i * SRL::R + r);
+                    }
+                }
+            }
+        }
+        __syncthreads();      // every thread has read the staging buffers: they can take the next pair
+        if (t == 0) {
+            const int next = tile + (int)gridDim.x;
+            if (next < ntiles) {
+                tma::fence_proxy_async();
+                issue(next);
+            }
+        }
+        T* o0 = out + (size_t)tile * 2 * W;
+        T* o1 = o0 + W;
+        run_from<PL, T, NT, -1, 0>(xr, xi, t, s_re, s_im, tw, BlockSync(), [&](auto& yr, auto& yi) {
+#pragma unroll
+            for (int i = 0; i < SL::IT; ++i) {
+                const int j = t + i * NT;
+                if (SL::IT * NT > SL::NB && j >= SL::NB) continue;
+#pragma unroll
+                for (int r = 0; r < SL::R; ++r) {
+                    const int k = j + r * SL::NB;
+                    const T w = wx[2 * k <= W ? k : W - k] * scale;
+                    yr[i * SL::R + r] *= w;
+                    yi[i * SL::R + r] *= w;
+                }
+            }
+            run_from<PR, T, NT, +1, 0>(yr, yi, t, s_re, s_im, twRev, BlockSync(), [&](auto& zr, auto& zi) {
+#pragma unroll
+                for (int i = 0; i < SRL::IT; ++i) {
+                    const int j = t + i * NT;
+                    if (SRL::IT * NT > SRL::NB && j >= SRL::NB) continue;
+#pragma unroll
+                    for (int r = 0; r < SRL::R; ++r) {
+                        const int q = i * SRL::R + r, n = j + r * SRL::NB;
+                        o0[n] = ((zb0 >> q) & 1u) ? (T)0 : zr[q];
+                        o1[n] = ((zb1 >> q) & 1u) ? (T)0 : zi[q];
+                    }
+                }
+            });
+        });
+        __syncthreads();      // the exchange buffer is free for the next pair's first scatter
+    }
+}
+
 template <typename T>
 static int sfft_rows_window_t(const T* in, T* out, int B, int H, int W, const T* wx, double scale, int restoreZeros, cudaStream_t st) {
     typedef typename V2<T>::type C2;
@@ -663,6 +793,8 @@ static int sfft_rows_window_t(const T* in, T* out, int B, int H, int W, const T*
     const long long nrows = (long long)B * H;
     const long long npairs = (nrows + 1) / 2;
     constexpr int G = SFFT_ROWW_G;
+    static const bool noWinTma = getenv("NEMO_B200_ROWW_NO_TMA") != nullptr;
+    const bool tmaOk = sfft_use_tma() && !noWinTma && (nrows % 2) == 0 && nrows < (1LL << 30) && (W % 2) == 0;
     int rc;
     const void *tw, *twRev;
 #define SFFT_CASE(NN, R0, R1, R2, NT, CR0, CR1, CR2, CNT)                                                                              \
@@ -671,6 +803,19 @@ static int sfft_rows_window_t(const T* in, T* out, int B, int H, int W, const T*
         typedef SRowCfg<T, NN, G> Cfg;                                                                                    \
         if ((rc = sfft_tw<PL>(prec, &tw)) != NB_OK) return rc;                                                            \
         if ((rc = sfft_tw<typename Reversed<PL>::type>(prec, &twRev)) != NB_OK) return rc;                                \
+        if (tmaOk) {                                                                                                      \
+            const size_t smem = ((size_t)4 * NN + 2 * (NN + 2)) * sizeof(T) + 16;                                         \
+            if ((rc = sfft_set_smem(sfft_rows_window_tma_kernel<T, PL, NT, true>, smem)) != NB_OK) return rc;             \
+            if ((rc = sfft_set_smem(sfft_rows_window_tma_kernel<T, PL, NT, false>, smem)) != NB_OK) return rc;            \
+            const long long cap = (long long)nb_sm_count() * SFFT_ROWW_TMA_MINB;                                          \
+            const unsigned pgrid = (unsigned)(npairs < cap ? npairs : cap);                                               \
+            { NB_PROF_BEGIN(st);                                                                                          \
+              if (restoreZeros) sfft_rows_window_tma_kernel<T, PL, NT, true><<<pgrid, NT, smem, st>>>(in, out, (int)nrows, (int)npairs, wx, (T)scale, (const C2*)tw, (const C2*)twRev); \
+              else sfft_rows_window_tma_kernel<T, PL, NT, false><<<pgrid, NT, smem, st>>>(in, out, (int)nrows, (int)npairs, wx, (T)scale, (const C2*)tw, (const C2*)twRev); \
+              NB_PROF_END("sfft_rows_window_kernel", st); }                                                               \
+            NB_CHECK_LAUNCH();                                                                                            \
+            return NB_OK;                                                                                                 \
+        }                                                                                                                 \
         if ((rc = sfft_set_smem(sfft_rows_window_kernel<T, PL, NT, G>, Cfg::SMEM)) != NB_OK) return rc;                   \
         const unsigned grid = (unsigned)((npairs + G - 1) / G);                                                           \
         { NB_PROF_BEGIN(st); sfft_rows_window_kernel<T, PL, NT, G><<<grid, NT * G, Cfg::SMEM, st>>>(in, out, nrows, wx, (T)scale, restoreZeros, (const C2*)tw, (const C2*)twRev); NB_PROF_END("sfft_rows_window_kernel", st); } \
