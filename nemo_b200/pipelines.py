@@ -390,9 +390,10 @@ class _BatchView(object):
 
 
 class BatchPipeline(object):
-    """Two-stage software pipeline over tile batches on two CUDA streams: ``submit(batch)`` queues the device work of that
-    batch (upload included when asked) and only then assembles the catalogs of the batch submitted before it, so the host
-    part of batch i runs while the GPU works on batch i + 1.  ``submit`` returns the (catalogDict, extras) of the previous
+    """Two-stage software pipeline over tile batches: ``submit(batch)`` queues the device work of that batch (its upload on the
+    slot's stream, its kernels -- one CUDA graph -- on the compute stream all batches share) and only then assembles the
+    catalogs of the batch submitted before it (on a high-priority stream), so the host part of batch i runs while the GPU works
+    on batch i + 1.  ``submit`` returns the (catalogDict, extras) of the previous
     batch (None for the first one); ``flush()`` returns the last.  This is how a run over many tiles keeps both sides busy;
     nothing is shared between batches except the read-only templates."""
 
@@ -446,7 +447,9 @@ class BatchPipeline(object):
         fin.wait_event(done)      # this batch only: the batches queued behind it keep the device busy meanwhile
         with torch.cuda.stream(fin):
             out = finishTileBatch(job, measureFluxes=self.measureFluxes, keepMaps=self.keepMaps, collect=self.collect)
-        # (finishTileBatch ends with a copy to the host that it waits for: what the finish read is free for the slot's next batch)
+        # what the finish read must be free before the slot's next batch overwrites it (finishTileBatch normally ends with a copy to
+        # the host that it waits for, so this returns at once)
+        fin.synchronize()
         if release:
             job['batch'].dev = None
         return out

@@ -325,3 +325,26 @@ def test_row_areas_match_the_reference_pixel_area_map():
     rmsBig[:300] = 1.0
     with pytest.raises(Exception):
         completeness_ref.getRMSTab(rmsBig, areaBig, SimpleCARWCS((600, 600), 0.5 / 60))
+
+
+def test_rows_of_is_a_lazy_independent_copy_of_a_row_range():
+    """catalogs.RowsOf: the per-image catalogs of a tile batch are row ranges of the batch's one stacked table, cut out (copied) the
+    first time they are looked at; deferred columns (object names) stay deferred; stacking such views gives the parent's rows."""
+    from nemo_b200 import catalogs
+    calls = []
+
+    def names():
+        calls.append(1)
+        return np.array(['a', 'b', 'c', 'd', 'e'], dtype=object)
+
+    parent = catalogs.Table.fromColumns([('SNR', np.array([5., 6., 7., 8., 9.])), ('x', np.arange(5.)), ('name', catalogs.deferred(names))])
+    parts = [catalogs.RowsOf(parent, 0, 2), catalogs.RowsOf(parent, 2, 5)]
+    assert [len(p) for p in parts] == [2, 3] and not calls          # lengths without cutting anything out
+    assert list(parts[1]['SNR']) == [7., 8., 9.] and not calls       # numeric columns do not touch the deferred one
+    assert list(parts[1]['name']) == ['c', 'd', 'e'] and len(calls) == 1
+    parts[0]['SNR'][0] = -1.0                                        # a copy: the parent keeps its values
+    assert parent['SNR'][0] == 5.0
+    both = catalogs.vstack(parts)
+    assert list(both['x']) == [0., 1., 2., 3., 4.] and list(both['name']) == ['a', 'b', 'c', 'd', 'e']
+    sub = parts[1][np.array([True, False, True])]
+    assert list(sub['x']) == [2., 4.] and parts[1].keys() == ['SNR', 'x', 'name']
