@@ -72,6 +72,32 @@ class Comm(object):
                 cap *= 2
             caps[rowBytes] = cap
 
+    def allGatherBlobs(self, blob, key='blob'):
+        """Every rank contributes a byte string (1-D uint8 array) of its own length; returns the list of every rank's bytes, in
+        rank order.  One collective in the usual case, as allGatherArrays: fixed-capacity buffers (kept per `key`, growing only)
+        whose first eight bytes carry the length."""
+        torch, dist = self.torch, self.dist
+        raw = np.ascontiguousarray(blob, dtype=np.uint8).reshape(-1)
+        n = raw.size
+        caps = self.__dict__.setdefault('_blobCaps', {})
+        cap = caps.get(key, 65536)
+        while True:
+            host = np.zeros(8 + cap, dtype=np.uint8)
+            host[:8] = np.frombuffer(np.int64(n).tobytes(), dtype=np.uint8)
+            m = min(n, cap)
+            host[8:8 + m] = raw[:m]
+            buf = torch.from_numpy(host).to(self.device)
+            out = torch.empty(self.size * host.size, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(out, buf)
+            got = out.cpu().numpy().reshape(self.size, host.size)
+            counts = [int(np.frombuffer(got[r, :8].tobytes(), dtype=np.int64)[0]) for r in range(self.size)]
+            if max(counts) <= cap:
+                caps[key] = cap
+                return [got[r, 8:8 + c] for r, c in enumerate(counts)]
+            while cap < max(counts):
+                cap *= 2
+            caps[key] = cap
+
     def maxOverRanks(self, value):
         t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.device)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
@@ -220,6 +246,38 @@ class GatheredTables(Mapping):
 
     def __len__(self):
         return sum(fl.shape[0] for fl in self._blocks)
+
+
+def noiseTableBlock(tab, labelIndex, tileIndex):
+    """Rows (label index, tile index, flattened table) for a stack of noise tables tab [n, nCells, nBins] -- what GatheredTables
+    reads and gatherNoiseBlocks sends."""
+    tab = np.asarray(tab, dtype=np.float64)
+    n = tab.shape[0]
+    return np.concatenate([np.asarray(labelIndex, dtype=np.float64).reshape(n, 1), np.asarray(tileIndex, dtype=np.float64).reshape(n, 1),
+                           tab.reshape(n, -1)], axis=1)
+
+
+def gatherNoiseBlocks(comm, blocks, labels, tileNames, shape):
+    """The noise tables of every rank as one read-only {'<label>#<tileName>': table} (GatheredTables) on every rank.  blocks: this
+    rank's noiseTableBlock arrays (one per tile batch, possibly none); shape: (nCells, nBins) of a table, or None on a rank that has
+    none.  ONE collective: the rows travel as bytes behind a header (rows, columns, table shape), so ranks need not agree on the
+    width beforehand (a rank without tiles has no tables to know it from).  comm None: this rank's blocks only."""
+    blocks = [b for b in blocks if b.shape[0] > 0]
+    if comm is None or comm.size == 1:
+        return GatheredTables(blocks, labels, tileNames, tuple(shape) if shape is not None else None) if blocks else {}
+    local = np.ascontiguousarray(np.concatenate(blocks, axis=0)) if blocks else np.zeros((0, 0))
+    sh = tuple(shape) if shape is not None and len(shape) == 2 else (0, 0)
+    header = np.array([local.shape[0], local.shape[1], sh[0], sh[1]], dtype=np.int64)
+    blob = np.concatenate([header.view(np.uint8), local.view(np.uint8).reshape(-1)])
+    out, outShape = [], None
+    for raw in comm.allGatherBlobs(blob, key='noiseTables'):
+        h = np.frombuffer(raw[:32].tobytes(), dtype=np.int64)
+        if h[0] == 0:
+            continue
+        out.append(np.frombuffer(raw[32:32 + h[0] * h[1] * 8].tobytes(), dtype=np.float64).reshape(int(h[0]), int(h[1])))
+        if h[2] * h[3] == h[1] - 2:
+            outShape = (int(h[2]), int(h[3]))
+    return GatheredTables(out, labels, tileNames, outShape) if out else {}
 
 
 def gatherNoiseTables(comm, noiseTables, labels=None, tileNames=None):

@@ -956,6 +956,10 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
                          for _, ex in results]
     RMSTabs = {}
     flatTables = []
+    from . import distributed
+    allTileNames = list(getattr(config, 'allTileNames', None) or config.tileNames)
+    tileIndexOf = {n: i for i, n in enumerate(allTileNames)}
+    noiseBlocks, noiseShape = [], None
     for batch, (cd, extras) in zip(batches, results):
         names = batch.tileNames
         catalogDict.update(cd)
@@ -964,9 +968,19 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
             RMSTabs[filtersList[o % len(filtersList)]['label'] + "#" + names[o // len(filtersList)]] = tab
         if extras['noiseTable'] is None:
             continue
-        tab = extras['noiseTable']
-        for o in range(tab.shape[0]):
-            noiseTables[filtersList[o % len(filtersList)]['label'] + "#" + names[o // len(filtersList)]] = tab[o]
+        # the batch's tables stay one array with (filter, tile) index columns in front: the '<label>#<tileName>' dictionary is a
+        # view made when somebody reads it, here and after the gather (hundreds of entries per step otherwise)
+        tab = np.asarray(extras['noiseTable'])
+        o = np.arange(tab.shape[0])
+        for n in names:      # (a configuration object without allTileNames, or one that does not list this rank's tiles)
+            if n not in tileIndexOf:
+                if comm is not None and comm.size > 1:
+                    raise Exception("config.allTileNames must list the tiles of every rank (tile %s is missing)" % n)
+                tileIndexOf[n] = len(allTileNames)
+                allTileNames.append(n)
+        tileIdx = np.array([tileIndexOf[n] for n in names], dtype=np.int64)[o // len(filtersList)]
+        noiseBlocks.append(distributed.noiseTableBlock(tab, o % len(filtersList), tileIdx))
+        noiseShape = tuple(tab.shape[1:])
     # (every batch brought its rows as one table: stack those few instead of the hundreds of per-image tables -- same rows, same order)
     stacked = [t for t in flatTables if t is not None] if all(t is not False for t in flatTables) else None
     optimalCatalog = catalogs.makeOptimalCatalog(catalogDict, constraintsList=parDict.get('catalogCuts', []), ops=ops, stacked=stacked)
@@ -977,10 +991,11 @@ def filterMapsAndMakeCatalogs(config, useCachedFilters=False, useCachedRMSMap=Fa
         labels = [f['label'] for f in filtersList]
         optimalCatalog = distributed.allGatherCatalog(comm, optimalCatalog, keys, labels, config.allTileNames,
                                                       objIdent=parDict['objIdent'], longNames=parDict['longNames'], ops=ops)
-        noiseTables = distributed.gatherNoiseTables(comm, noiseTables, labels, config.allTileNames)
     if makeRMSTables and comm is not None and comm.size > 1:
         from . import distributed
         RMSTabs = distributed.gatherRMSTabs(comm, RMSTabs, [f['label'] for f in filtersList], config.allTileNames)
+    noiseTables = distributed.gatherNoiseBlocks(comm, noiseBlocks, [f['label'] for f in filtersList], allTileNames,
+                                                noiseShape if noiseShape is not None and len(noiseShape) == 2 else None)
     config.catalogDict = catalogDict
     config.noiseTables = noiseTables
     config.RMSTabs = RMSTabs      # {'<label>#<tileName>': (y0RMS ascending, areaDeg2)} -- completeness.getRMSTab per tile and filter

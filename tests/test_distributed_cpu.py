@@ -64,6 +64,15 @@ def _worker(rank, world, port, q):
         empty = distributed.allGatherCatalog(comm, [] if rank == 1 else tab, keys)
         noise2 = distributed.gatherNoiseTables(comm, {'F#tile%d' % rank: np.full((4, 2), float(rank + 1))})
         assert sorted(noise2.keys()) == sorted(noise.keys()) and np.array_equal(noise2['F#tile1'], noise['F#tile1'])
+        # block form (what the batched driver sends): stacks of tables with (filter, tile) index columns, one collective of bytes;
+        # rank 0 has two batches, rank 1 none at all (and therefore no table shape to offer)
+        blocks = [distributed.noiseTableBlock(np.full((2, 3, 2), 1.0 + k), [0, 1], [k, k]) for k in range(2)] if rank == 0 else []
+        view = distributed.gatherNoiseBlocks(comm, blocks, labels, tileNames, (3, 2) if rank == 0 else None)
+        assert sorted(view.keys()) == ['Arnaud_M2e14_z0p4#tile0', 'Arnaud_M2e14_z0p4#tile1', 'other#tile0', 'other#tile1'] and len(view) == 4
+        assert view['other#tile1'].shape == (3, 2) and np.all(view['other#tile1'] == 2.0) and np.all(view['Arnaud_M2e14_z0p4#tile0'] == 1.0)
+        assert distributed.gatherNoiseBlocks(comm, [], labels, tileNames, None) == {}
+        alone = distributed.gatherNoiseBlocks(None, [distributed.noiseTableBlock(np.full((1, 3, 2), 5.0), [1], [0])], labels, tileNames, (3, 2))
+        assert list(alone.keys()) == ['other#tile0'] and alone['other#tile0'].shape == (3, 2)
         tabs = distributed.gatherRMSTabs(comm, {'Arnaud_M2e14_z0p4#tile%d' % rank: (np.arange(3 + rank) + 1.0, np.full(3 + rank, 0.5 + rank))},
                                          labels, tileNames)
         assert sorted(tabs.keys()) == ['Arnaud_M2e14_z0p4#tile0', 'Arnaud_M2e14_z0p4#tile1']
